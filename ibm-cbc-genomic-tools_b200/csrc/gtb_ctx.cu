@@ -1,0 +1,180 @@
+// gtb_ctx.cu -- context life cycle, stream selection, launch accounting / CUDA-event profiling,
+// and the multi-block inclusive scan used by the finalisation kernels.
+#include "gtb_internal.cuh"
+
+extern "C" int gtb_abi_version(void) { return GTB200_ABI_VERSION; }
+
+extern "C" int gtb_ctx_create(int device, gtb_ctx **out) {
+  if (!out) return GTB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return GTB_ERR_NO_DEVICE;   // no CPU fallback, by design
+  if (device < 0 || device >= n) return GTB_ERR_ARG;
+  gtb_ctx *ctx = new gtb_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return GTB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  }
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx; return GTB_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return GTB_OK;
+}
+
+extern "C" void gtb_ctx_destroy(gtb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+extern "C" int gtb_ctx_set_stream(gtb_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return GTB_ERR_ARG;
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GTB_OK;
+}
+
+extern "C" int gtb_ctx_synchronize(gtb_ctx *ctx) {
+  if (!ctx) return GTB_ERR_ARG;
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return GTB_OK;
+}
+
+extern "C" const char *gtb_ctx_last_error(const gtb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int64_t gtb_ctx_launch_count(const gtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static void drain_pending(gtb_ctx *ctx) {
+  for (auto &p : ctx->pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(p.b);
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      auto &s = ctx->stats[p.name];
+      s.launches++; s.total_ms += ms;
+    }
+    cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+  }
+  ctx->pending.clear();
+}
+
+extern "C" int gtb_ctx_profile(gtb_ctx *ctx, int enable) {
+  if (!ctx) return GTB_ERR_ARG;
+  drain_pending(ctx);
+  ctx->profiling = enable != 0;
+  if (enable) { ctx->stats.clear(); ctx->launches = 0; }
+  return GTB_OK;
+}
+
+extern "C" int gtb_ctx_profile_report(gtb_ctx *ctx, char *buf, size_t buf_size) {
+  if (!ctx || !buf || buf_size < 3) return GTB_ERR_ARG;
+  drain_pending(ctx);
+  std::string s = "{";
+  bool first = true;
+  for (auto &kv : ctx->stats) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %lld, \"total_ms\": %.6f}", first ? "" : ", ",
+             kv.first.c_str(), (long long)kv.second.launches, kv.second.total_ms);
+    s += line; first = false;
+  }
+  s += "}";
+  if (s.size() + 1 > buf_size) return GTB_ERR_ARG;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return GTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inclusive scan (uint64, wrapping).  Three launches: per-tile scan + tile totals, scan of totals
+// by one block, add-back.  Used on arrays of at most a few million evaluation points, so it is
+// sized for simplicity; traffic is 3 reads + 2 writes per element.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *total) {
+  __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0ull;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  unsigned long long base = warp > 0 ? warp_sums[warp - 1] : 0ull;
+  if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+  unsigned long long r = base + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(unsigned long long *d, int64_t n, unsigned long long *tile_totals) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? d[base + i] : 0ull; sum += v[i]; }
+  unsigned long long total;
+  unsigned long long ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) { ex += v[i]; if (base + i < n) d[base + i] = ex; }
+  if (threadIdx.x == 0) tile_totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(unsigned long long *totals, int64_t n_tiles) {
+  // one block walks the tile totals in chunks, carrying the running sum (exclusive result in place)
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+    int64_t i = base + threadIdx.x;
+    unsigned long long v = i < n_tiles ? totals[i] : 0ull, total;
+    unsigned long long ex = block_exclusive_scan(v, &total);
+    if (i < n_tiles) totals[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_addback_kernel(unsigned long long *d, int64_t n, const unsigned long long *tile_offsets) {
+  const unsigned long long off = tile_offsets[blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS)
+    if (base + i < n) d[base + i] += off;
+}
+}  // namespace
+
+int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch) {
+  if (n <= 0) return GTB_OK;
+  const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  GTB_TRY(scratch.reserve(ctx, (size_t)n_tiles));
+  GTB_LAUNCH(ctx, "scan_tiles", scan_tiles_kernel, (unsigned)n_tiles, SCAN_THREADS, 0, d, n, scratch.p);
+  if (n_tiles > 1) {
+    GTB_LAUNCH(ctx, "scan_totals", scan_totals_kernel, 1, SCAN_THREADS, 0, scratch.p, n_tiles);
+    GTB_LAUNCH(ctx, "scan_addback", scan_addback_kernel, (unsigned)n_tiles, SCAN_THREADS, 0, d, n, scratch.p);
+  }
+  return gtb_check_launch(ctx);
+}

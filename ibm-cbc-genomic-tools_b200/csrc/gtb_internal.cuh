@@ -1,0 +1,116 @@
+// gtb_internal.cuh -- shared internals of libgtb200 (context, device buffers, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/gtb200.h"
+
+#define GTB_SM_COUNT_FALLBACK 148
+
+struct gtb_kernel_stat {
+  int64_t launches = 0;
+  double total_ms = 0.0;
+};
+
+struct gtb_ctx {
+  int device = 0;
+  int sm_count = GTB_SM_COUNT_FALLBACK;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // H2D staging overlaps kernels on `stream`
+  cudaStream_t stream = nullptr;           // where kernels go (own_stream or caller's)
+  std::string last_error;
+  int64_t launches = 0;
+  bool profiling = false;
+  struct pending_event { const char *name; cudaEvent_t a, b; };
+  std::vector<pending_event> pending;
+  std::map<std::string, gtb_kernel_stat> stats;
+};
+
+// ---- error plumbing ---------------------------------------------------------------------------
+#define GTB_CUDA_OK(ctx, call)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      char b__[512];                                                                        \
+      snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+               cudaGetErrorString(e__));                                                    \
+      (ctx)->last_error = b__;                                                              \
+      return e__ == cudaErrorMemoryAllocation ? GTB_ERR_NOMEM : GTB_ERR_CUDA;               \
+    }                                                                                       \
+  } while (0)
+
+#define GTB_TRY(expr)                  \
+  do {                                 \
+    int rc__ = (expr);                 \
+    if (rc__ != GTB_OK) return rc__;   \
+  } while (0)
+
+static inline int gtb_fail(gtb_ctx *ctx, int code, const char *msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+// ---- growable device buffer -------------------------------------------------------------------
+template <typename T>
+struct dbuf {
+  T *p = nullptr;
+  size_t cap = 0;   // elements
+  int reserve(gtb_ctx *ctx, size_t n) {
+    if (n <= cap) return GTB_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 256;
+    GTB_CUDA_OK(ctx, cudaMalloc((void **)&p, want * sizeof(T)));
+    cap = want;
+    return GTB_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ---- kernel launch accounting -----------------------------------------------------------------
+// Every kernel goes through GTB_LAUNCH so that gtb_ctx_launch_count() is exact and, with profiling
+// on, each launch is bracketed by CUDA events on the launching stream.
+struct gtb_launch_scope {
+  gtb_ctx *ctx; const char *name; cudaEvent_t a = nullptr, b = nullptr;
+  gtb_launch_scope(gtb_ctx *c, const char *n) : ctx(c), name(n) {
+    ctx->launches++;
+    if (ctx->profiling) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~gtb_launch_scope() {
+    if (ctx->profiling) {
+      cudaEventRecord(b, ctx->stream);
+      ctx->pending.push_back({name, a, b});
+    }
+  }
+};
+#define GTB_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                       \
+  do {                                                                              \
+    gtb_launch_scope scope__((ctx), (name));                                        \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+  } while (0)
+
+static inline int gtb_check_launch(gtb_ctx *ctx) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("kernel launch failed: ") + cudaGetErrorString(e);
+    return GTB_ERR_CUDA;
+  }
+  return GTB_OK;
+}
+
+static inline unsigned gtb_grid_for(int64_t n_items, int per_block, int64_t max_blocks) {
+  int64_t g = (n_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (unsigned)g;
+}
+
+// in-place inclusive prefix sum over n uint64 values on ctx->stream (gtb_scan_util.cu)
+int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch);

@@ -1,0 +1,599 @@
+// gtb_overlap.cu -- overlap count / coverage: index construction, the general RANK and ENUMERATE
+// engines, finalisation, and the streaming C-ABI around them (include/gtb200.h).
+#include "gtb_overlap.cuh"
+#include <algorithm>
+#include <limits.h>
+
+// =================================================================================================
+// device helpers
+// =================================================================================================
+namespace {
+
+__device__ __forceinline__ void report_error(ull *err, int64_t index, int code) {
+  atomicMin(err, ((ull)index << 8) | (ull)code);
+}
+
+// first slot j in [lo,hi) with points[j] >= x ; the group's last slot is a +inf sentinel so the
+// answer always exists when called with hi = group end.
+__device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ p, int lo, int hi, int32_t x) {
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(p + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int64_t lower_bound_u64(const ull *__restrict__ p, int64_t n, ull x) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(p + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Shared front half of both engines: the per-query-region checks the reference performs, in its
+// order.  Returns false if the region contributes nothing (or was reported as fatal).
+//   well-formedness: GenomicRegion::IsCompatibleSortedAndNonoverlapping, genomic_intervals.cpp:1153-1161,
+//                    applied to every query in GetQuery/NextQuery (:5698, :5709)
+//   chromosome unknown to the index -> no matches, no checks (:5719-5720, :5731)
+//   stop <= 0, start > stop -> fatal (:5740-5741)
+__device__ __forceinline__ bool admit_query(const QueryView &q, int64_t r, const uint8_t *__restrict__ present,
+                                            int32_t n_chrom, ull *err, int64_t &lo, int64_t &hi) {
+  if (q.region_offset) { lo = q.region_offset[r] - q.interval_base; hi = q.region_offset[r + 1] - q.interval_base; }
+  else { lo = r; hi = r + 1; }
+  if (hi <= lo) return false;
+  const int32_t c = q.chrom[lo];
+  const int8_t sb = q.strand[lo];
+  for (int64_t i = lo + 1; i < hi; i++) {
+    if (q.chrom[i] != c || q.strand[i] != sb || q.start[i] < q.start[i - 1] || q.start[i] <= q.stop[i - 1]) {
+      report_error(err, q.index_base + r, GTB_ERR_QUERY_REGION);
+      return false;
+    }
+  }
+  if (c < 0 || c >= n_chrom || !present[c]) return false;
+  const int32_t qs = q.start[lo], qe = q.stop[hi - 1];
+  if (qe <= 0) { report_error(err, q.index_base + r, GTB_ERR_QUERY_STOP_NONPOSITIVE); return false; }
+  if (qs > qe) { report_error(err, q.index_base + r, GTB_ERR_QUERY_START_GT_STOP); return false; }
+  return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// RANK engine, general form: binary search in global memory, 64-bit atomics on the slot histograms.
+// One thread per query region.  Handles weights, any interval length, negative coordinates,
+// multi-interval queries (spans under -gaps, blocks for coverage).
+// -------------------------------------------------------------------------------------------------
+template <bool COVERAGE>
+__device__ __forceinline__ void rank_item(const RankView &ix, int gb, int ge, int32_t qs, int32_t qe, int64_t w) {
+  const int jS = lower_bound_i32(ix.points, gb, ge - 1, qs);      // ge-1 is the sentinel: result <= ge-1
+  const int jE = lower_bound_i32(ix.points, jS, ge - 1, qe);
+  ull *h = ix.hist;
+  const int64_t K = ix.n_slots;
+  if (jS == jE) {
+    if (COVERAGE) atomicAdd(h + H_BOTH * K + jS, (ull)(w * ((int64_t)qe - qs + 1)));
+    else atomicAdd(h + H_BOTH * K + jS, (ull)w);
+  } else {
+    atomicAdd(h + H_SCNT * K + jS, (ull)w);
+    atomicAdd(h + H_ECNT * K + jE, (ull)w);
+    if (COVERAGE) {
+      atomicAdd(h + H_SSUM * K + jS, (ull)(w * (int64_t)qs));
+      atomicAdd(h + H_ESUM * K + jE, (ull)(w * (int64_t)qe));
+    }
+  }
+}
+
+template <bool COVERAGE, bool BLOCKS>
+__global__ void __launch_bounds__(256) rank_accumulate_kernel(QueryView q, RankView ix) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    int64_t lo, hi;
+    if (!admit_query(q, r, ix.chrom_present, ix.n_chrom, ix.err, lo, hi)) continue;
+    const int cls = ix.class_of[(uint8_t)q.strand[lo]];            // front-interval strand, :5229
+    if (cls < 0) continue;
+    const int g = q.chrom[lo] * ix.n_class + cls;
+    const int gb = ix.goff[g], ge = ix.goff[g + 1];
+    if (ge == gb) continue;
+    const int64_t w = q.weight ? (int64_t)q.weight[r] : 1;
+    if (!BLOCKS) {
+      rank_item<COVERAGE>(ix, gb, ge, q.start[lo], q.stop[hi - 1], w);   // span: count, or -gaps (:5227, :5277)
+    } else {
+      for (int64_t i = lo; i < hi; i++) {                           // coverage = sum over block pairs (:1196-1202)
+        const int32_t bs = q.start[i], be = q.stop[i];
+        if (bs > be) continue;                                      // CalcOverlap clamps such blocks to 0 (:427-432)
+        rank_item<COVERAGE>(ix, gb, ge, bs, be, w);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// ENUMERATE engine: candidates from the (chromosome, level, bin) CSR, exact predicate per pair.
+// -------------------------------------------------------------------------------------------------
+constexpr int ENUM_LEVELS = 6;
+__constant__ int c_enum_bits[ENUM_LEVELS] = {14, 17, 20, 23, 26, 62};
+
+__device__ __forceinline__ ull enum_key(int32_t c, int level, int64_t bin) {
+  return ((ull)(uint32_t)c << 35) | ((ull)level << 32) | (ull)(uint32_t)bin;
+}
+
+template <bool COVERAGE>
+__global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix, EnumView ev, bool match_gaps, bool ignore_strand) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    int64_t lo, hi;
+    if (!admit_query(q, r, ix.chrom_present, ix.n_chrom, ix.err, lo, hi)) continue;
+    const int32_t c = q.chrom[lo];
+    const int8_t qstrand = q.strand[lo];
+    const int64_t qs_true = q.start[lo], qe = q.stop[hi - 1];
+    const int64_t qs = qs_true <= 0 ? 1 : qs_true;                  // :5742
+    const int64_t w = q.weight ? (int64_t)q.weight[r] : 1;
+    for (int l = 0; l < ENUM_LEVELS; l++) {
+      const ull k_lo = enum_key(c, l, qs >> c_enum_bits[l]);
+      const ull k_hi = enum_key(c, l, qe >> c_enum_bits[l]);
+      for (int64_t e = lower_bound_u64(ev.keys, ev.n_entries, k_lo); e < ev.n_entries && ev.keys[e] <= k_hi; e++) {
+        const int32_t k = ev.rid[e];
+        const int64_t ilo = ev.r_off[k], ihi = ev.r_off[k + 1];
+        if (!(qs <= ev.r_stop[ihi - 1] && qe >= ev.r_start[ilo])) continue;             // span test, :5752
+        if (!ignore_strand && qstrand != ev.r_strand[ilo]) continue;                   // :5229
+        int64_t cc = 0;
+        bool any = false;
+        if (match_gaps) {                                                              // :5227, :5277
+          any = true;
+          const int64_t a = qe < ev.r_stop[ihi - 1] ? qe : ev.r_stop[ihi - 1];
+          const int64_t b = qs_true > ev.r_start[ilo] ? qs_true : ev.r_start[ilo];
+          cc = a - b + 1;
+        } else {
+          for (int64_t i = lo; i < hi; i++)
+            for (int64_t j = ilo; j < ihi; j++) {
+              // chromosome and (unless -i) strand are region-wide after the well-formedness checks
+              const int64_t a = q.stop[i] < ev.r_stop[j] ? q.stop[i] : ev.r_stop[j];
+              const int64_t b = q.start[i] > ev.r_start[j] ? q.start[i] : ev.r_start[j];
+              if (!(q.start[i] > ev.r_stop[j] || q.stop[i] < ev.r_start[j])) any = true;   // :624-630
+              if (a - b + 1 > 0) cc += a - b + 1;                                      // :427-432
+            }
+        }
+        if (!any) continue;
+        atomicAdd(ev.direct + k, COVERAGE ? (ull)(cc * w) : (ull)w);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// finalisation: after the slot histograms have been prefix-summed, evaluate every target and sum
+// the targets of each region.  One thread per region.
+// -------------------------------------------------------------------------------------------------
+template <bool COVERAGE>
+__global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const int64_t *__restrict__ t_off,
+                                                       const int32_t *__restrict__ t_hi, const int32_t *__restrict__ t_lo,
+                                                       const int32_t *__restrict__ t_base, const int32_t *__restrict__ points,
+                                                       const ull *__restrict__ scan, int64_t K,
+                                                       const ull *__restrict__ direct, ull *__restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_regions) return;
+  ull total = direct ? direct[k] : 0ull;
+  for (int64_t t = t_off[k]; t < t_off[k + 1]; t++) {
+    const int hi = t_hi[t], lo = t_lo[t], base = t_base[t];
+    // group-relative inclusive prefix of plane p at slot j
+    auto pre = [&](int p, int j) -> ull {
+      const ull *a = scan + (int64_t)p * K;
+      return a[j] - (base > 0 ? a[base - 1] : 0ull);
+    };
+    if (!COVERAGE) {
+      const ull starts_le_te = pre(H_BOTH, hi) + pre(H_SCNT, hi);      // #{qs <= te}
+      const ull stops_lt_ts = pre(H_BOTH, lo) + pre(H_ECNT, lo);       // #{qe <= ts-1}
+      total += starts_le_te - stops_lt_ts;
+    } else {
+      auto F = [&](int j) -> ull {
+        const ull x = (ull)(int64_t)points[j];
+        return pre(H_BOTH, j) + (x + 1ull) * pre(H_SCNT, j) - pre(H_SSUM, j) - x * pre(H_ECNT, j) + pre(H_ESUM, j);
+      };
+      total += F(hi) - F(lo);
+    }
+  }
+  out[k] = total;
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side: index construction
+// =================================================================================================
+static bool region_well_formed(const gtb_set *s, int64_t k) {
+  const int64_t lo = s->region_offset ? s->region_offset[k] : k, hi = s->region_offset ? s->region_offset[k + 1] : k + 1;
+  for (int64_t i = lo + 1; i < hi; i++) {
+    if (s->chrom[i] != s->chrom[lo] || s->strand[i] != s->strand[lo]) return false;
+    if (s->start[i] < s->start[i - 1] || s->start[i] <= s->stop[i - 1]) return false;
+  }
+  return true;
+}
+
+template <typename T>
+static int upload(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
+  GTB_TRY(d.reserve(ctx, h.size() ? h.size() : 1));
+  if (h.size()) GTB_CUDA_OK(ctx, cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return GTB_OK;
+}
+
+static int build_rank_structures(gtb_index *ix) {
+  gtb_ctx *ctx = ix->ctx;
+  const int64_t M = ix->n_regions;
+  const bool use_blocks = ix->op == GTB_OP_COVERAGE && !ix->match_gaps;
+  auto lo_of = [&](int64_t k) { return ix->h_off[k]; };
+  auto hi_of = [&](int64_t k) { return ix->h_off[k + 1]; };
+  auto indexable = [&](int64_t k) {
+    if (hi_of(k) <= lo_of(k)) return false;
+    int64_t s = ix->h_start[lo_of(k)], e = ix->h_stop[hi_of(k) - 1];
+    return !(s > e || e <= 0);                                        // :5610, :5659
+  };
+  // chromosome table and strand classes
+  int32_t max_chrom = -1;
+  for (int64_t k = 0; k < M; k++) if (indexable(k)) max_chrom = std::max(max_chrom, ix->h_chrom[lo_of(k)]);
+  ix->n_chrom = max_chrom + 1;
+  ix->h_present.assign((size_t)std::max(ix->n_chrom, 1), 0);
+  ix->h_class_of.assign(256, (int8_t)(ix->ignore_strand ? 0 : -1));
+  ix->n_class = ix->ignore_strand ? 1 : 0;
+  for (int64_t k = 0; k < M; k++) {
+    if (!indexable(k)) continue;
+    if (ix->h_chrom[lo_of(k)] < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative chromosome id in index set");
+    ix->h_present[ix->h_chrom[lo_of(k)]] = 1;
+    uint8_t sb = (uint8_t)ix->h_strand[lo_of(k)];
+    if (!ix->ignore_strand && ix->h_class_of[sb] < 0) {
+      if (ix->n_class >= 120) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "too many distinct strand characters");
+      ix->h_class_of[sb] = (int8_t)ix->n_class++;
+    }
+  }
+  if (ix->n_class == 0) ix->n_class = 1;
+  if ((int64_t)ix->n_chrom * ix->n_class > (int64_t)INT_MAX / 4) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "too many chromosome groups");
+  ix->n_groups = ix->n_chrom * ix->n_class;
+
+  // targets
+  struct target { int32_t g; int32_t ts, te; };
+  std::vector<target> targets;
+  std::vector<int64_t> t_off((size_t)M + 1, 0);
+  for (int64_t k = 0; k < M; k++) {
+    t_off[k] = (int64_t)targets.size();
+    if (!indexable(k)) continue;
+    const int32_t g = ix->h_chrom[lo_of(k)] * ix->n_class + ix->h_class_of[(uint8_t)ix->h_strand[lo_of(k)]];
+    if (!use_blocks) targets.push_back({g, ix->h_start[lo_of(k)], ix->h_stop[hi_of(k) - 1]});
+    else for (int64_t i = lo_of(k); i < hi_of(k); i++)
+      if (ix->h_start[i] <= ix->h_stop[i]) targets.push_back({g, ix->h_start[i], ix->h_stop[i]});
+  }
+  t_off[M] = (int64_t)targets.size();
+  ix->n_targets = (int64_t)targets.size();
+
+  // evaluation points per group: {te} U {ts-1}, sorted, distinct, + sentinel
+  std::vector<std::pair<int32_t, int32_t>> pts;     // (group, x)
+  pts.reserve(targets.size() * 2);
+  for (auto &t : targets) {
+    pts.push_back({t.g, t.te});
+    pts.push_back({t.g, t.ts == INT32_MIN ? INT32_MIN : t.ts - 1});
+  }
+  std::sort(pts.begin(), pts.end());
+  pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+  ix->h_goff.assign((size_t)ix->n_groups + 1, 0);
+  ix->h_points.clear();
+  ix->h_points.reserve(pts.size() + 64);
+  {
+    size_t i = 0;
+    for (int32_t g = 0; g < ix->n_groups; g++) {
+      ix->h_goff[g] = (int32_t)ix->h_points.size();
+      const size_t begin = i;
+      while (i < pts.size() && pts[i].first == g) ix->h_points.push_back(pts[i++].second);
+      if (i > begin) ix->h_points.push_back(INT32_MAX);              // sentinel slot
+    }
+    ix->h_goff[ix->n_groups] = (int32_t)ix->h_points.size();
+  }
+  ix->n_slots = (int64_t)ix->h_points.size();
+  if (ix->n_slots > (int64_t)INT_MAX - 8) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "too many evaluation points");
+
+  std::vector<int32_t> t_hi(targets.size()), t_lo(targets.size()), t_base(targets.size());
+  for (size_t t = 0; t < targets.size(); t++) {
+    const int32_t gb = ix->h_goff[targets[t].g], ge = ix->h_goff[targets[t].g + 1];
+    const int32_t *b = ix->h_points.data() + gb, *e = ix->h_points.data() + ge - 1;
+    const int32_t lo_x = targets[t].ts == INT32_MIN ? INT32_MIN : targets[t].ts - 1;
+    t_hi[t] = (int32_t)(std::lower_bound(b, e, targets[t].te) - ix->h_points.data());
+    t_lo[t] = (int32_t)(std::lower_bound(b, e, lo_x) - ix->h_points.data());
+    t_base[t] = gb;
+  }
+
+  GTB_TRY(upload(ctx, ix->d_class_of, ix->h_class_of));
+  GTB_TRY(upload(ctx, ix->d_present, ix->h_present));
+  GTB_TRY(upload(ctx, ix->d_goff, ix->h_goff));
+  GTB_TRY(upload(ctx, ix->d_points, ix->h_points));
+  GTB_TRY(upload(ctx, ix->d_t_hi, t_hi));
+  GTB_TRY(upload(ctx, ix->d_t_lo, t_lo));
+  GTB_TRY(upload(ctx, ix->d_t_base, t_base));
+  GTB_TRY(upload(ctx, ix->d_t_off, t_off));
+  ix->planes = ix->op == GTB_OP_COVERAGE ? H_PLANES_COVERAGE : H_PLANES_COUNT;
+  const size_t hist_elems = (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1);
+  GTB_TRY(ix->d_hist.reserve(ctx, hist_elems));
+  GTB_TRY(ix->d_hist_scan.reserve(ctx, hist_elems));
+  GTB_TRY(ix->d_err.reserve(ctx, 1));
+  GTB_TRY(ix->d_out.reserve(ctx, (size_t)std::max<int64_t>(M, 1)));
+  GTB_TRY(ix->d_direct.reserve(ctx, (size_t)std::max<int64_t>(M, 1)));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));               // host vectors above go out of scope
+  return GTB_OK;
+}
+
+static int build_enum_structures(gtb_index *ix) {
+  if (ix->enum_ready) return GTB_OK;
+  gtb_ctx *ctx = ix->ctx;
+  static const int bits[6] = {14, 17, 20, 23, 26, 62};
+  std::vector<std::pair<ull, int32_t>> ent;
+  ent.reserve((size_t)ix->n_regions);
+  for (int64_t k = 0; k < ix->n_regions; k++) {
+    const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
+    if (hi <= lo) continue;
+    int64_t s = ix->h_start[lo], e = ix->h_stop[hi - 1];
+    if (s > e || e <= 0) continue;
+    if (s <= 0) s = 1;                                                // :5660
+    for (int l = 0; l < 6; l++)
+      if ((s >> bits[l]) == (e >> bits[l])) {
+        ent.push_back({((ull)(uint32_t)ix->h_chrom[lo] << 35) | ((ull)l << 32) | (ull)(uint32_t)(s >> bits[l]), (int32_t)k});
+        break;
+      }
+  }
+  std::sort(ent.begin(), ent.end());
+  std::vector<ull> keys(ent.size());
+  std::vector<int32_t> rid(ent.size());
+  for (size_t i = 0; i < ent.size(); i++) { keys[i] = ent[i].first; rid[i] = ent[i].second; }
+  ix->n_entries = (int64_t)ent.size();
+  GTB_TRY(upload(ctx, ix->d_keys, keys));
+  GTB_TRY(upload(ctx, ix->d_rid, rid));
+  GTB_TRY(upload(ctx, ix->d_r_chrom, ix->h_chrom));
+  GTB_TRY(upload(ctx, ix->d_r_start, ix->h_start));
+  GTB_TRY(upload(ctx, ix->d_r_stop, ix->h_stop));
+  GTB_TRY(upload(ctx, ix->d_r_strand, ix->h_strand));
+  GTB_TRY(upload(ctx, ix->d_r_off, ix->h_off));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ix->enum_ready = true;
+  return GTB_OK;
+}
+
+extern "C" int gtb_index_reset(gtb_index *ix) {
+  if (!ix) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_hist.p, 0, sizeof(ull) * (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_direct.p, 0, sizeof(ull) * (size_t)std::max<int64_t>(ix->n_regions, 1), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
+  ix->queries_seen = 0;
+  return GTB_OK;
+}
+
+extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, unsigned flags, gtb_index **out, int64_t *err_index) {
+  if (!ctx || !regions || !out) return GTB_ERR_ARG;
+  *out = nullptr;
+  if (err_index) *err_index = -1;
+  if (op != GTB_OP_COUNT && op != GTB_OP_COVERAGE) return gtb_fail(ctx, GTB_ERR_ARG, "op must be GTB_OP_COUNT or GTB_OP_COVERAGE");
+  if (regions->n_regions < 0 || regions->n_intervals < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative sizes");
+  if (!regions->region_offset && regions->n_regions != regions->n_intervals)
+    return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
+  if (regions->n_intervals > 0 && (!regions->chrom || !regions->start || !regions->stop || !regions->strand))
+    return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  for (int64_t k = 0; k < regions->n_regions; k++)
+    if (!region_well_formed(regions, k)) {                             // fatal in the reference, :5607
+      if (err_index) *err_index = k;
+      return gtb_fail(ctx, GTB_ERR_INDEX_REGION, "index regions should be compatible, sorted and non-overlapping!");
+    }
+  gtb_index *ix = new gtb_index();
+  ix->ctx = ctx; ix->op = op;
+  ix->match_gaps = (flags & GTB_MATCH_GAPS) != 0;
+  ix->ignore_strand = (flags & GTB_IGNORE_STRAND) != 0;
+  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET);
+  ix->n_regions = regions->n_regions; ix->n_intervals = regions->n_intervals;
+  const size_t ni = (size_t)regions->n_intervals;
+  ix->h_chrom.assign(regions->chrom, regions->chrom + ni);
+  ix->h_start.assign(regions->start, regions->start + ni);
+  ix->h_stop.assign(regions->stop, regions->stop + ni);
+  ix->h_strand.assign(regions->strand, regions->strand + ni);
+  ix->h_off.resize((size_t)regions->n_regions + 1);
+  for (int64_t k = 0; k <= regions->n_regions; k++) ix->h_off[k] = regions->region_offset ? regions->region_offset[k] : k;
+  for (int64_t k = 0; k < regions->n_regions; k++) if (ix->h_off[k + 1] - ix->h_off[k] > 1) ix->index_multi = true;
+  for (auto &st : ix->stages) {
+    cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming);
+  }
+  int rc = build_rank_structures(ix);
+  if (rc == GTB_OK) rc = gtb_index_reset(ix);
+  if (rc != GTB_OK) { gtb_index_destroy(ix); return rc; }
+  *out = ix;
+  return GTB_OK;
+}
+
+extern "C" void gtb_index_destroy(gtb_index *ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->ctx->device);
+  gtb_ctx_synchronize(ix->ctx);
+  gtb_bucket_destroy(ix);
+  ix->d_class_of.release(); ix->d_present.release(); ix->d_goff.release(); ix->d_points.release();
+  ix->d_t_hi.release(); ix->d_t_lo.release(); ix->d_t_base.release(); ix->d_t_off.release();
+  ix->d_hist.release(); ix->d_hist_scan.release(); ix->d_scan_scratch.release();
+  ix->d_keys.release(); ix->d_rid.release(); ix->d_r_chrom.release(); ix->d_r_start.release();
+  ix->d_r_stop.release(); ix->d_r_strand.release(); ix->d_r_off.release(); ix->d_direct.release();
+  ix->d_err.release(); ix->d_out.release();
+  for (auto &st : ix->stages) {
+    st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release();
+    if (st.copied) cudaEventDestroy(st.copied);
+    if (st.consumed) cudaEventDestroy(st.consumed);
+  }
+  delete ix;
+}
+
+// =================================================================================================
+// accumulate
+// =================================================================================================
+static RankView rank_view(gtb_index *ix) {
+  RankView v;
+  v.n_chrom = ix->n_chrom; v.n_class = ix->n_class;
+  v.class_of = ix->d_class_of.p; v.chrom_present = ix->d_present.p;
+  v.goff = ix->d_goff.p; v.points = ix->d_points.p; v.n_slots = ix->n_slots;
+  v.hist = ix->d_hist.p; v.err = ix->d_err.p;
+  return v;
+}
+
+// which engine may serve this (index, batch) pair
+static unsigned choose_engine(const gtb_index *ix, const QueryView &q, bool batch_multi) {
+  const bool rank_valid = ix->op == GTB_OP_COVERAGE || ix->match_gaps || (!ix->index_multi && !batch_multi);
+  if (ix->engine & GTB_ENGINE_ENUMERATE) return GTB_ENGINE_ENUMERATE;
+  if (!rank_valid) return GTB_ENGINE_ENUMERATE;
+  if (ix->engine & GTB_ENGINE_RANK) return GTB_ENGINE_RANK;
+  if (gtb_bucket_supported(ix, q)) return GTB_ENGINE_BUCKET;
+  return GTB_ENGINE_RANK;
+}
+
+static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi) {
+  gtb_ctx *ctx = ix->ctx;
+  if (q.n_regions <= 0) return GTB_OK;
+  const unsigned engine = choose_engine(ix, q, batch_multi);
+  if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
+  RankView rv = rank_view(ix);
+  if (engine == GTB_ENGINE_ENUMERATE) {
+    GTB_TRY(build_enum_structures(ix));
+    EnumView ev;
+    ev.n_entries = ix->n_entries; ev.keys = ix->d_keys.p; ev.rid = ix->d_rid.p;
+    ev.r_chrom = ix->d_r_chrom.p; ev.r_start = ix->d_r_start.p; ev.r_stop = ix->d_r_stop.p;
+    ev.r_strand = ix->d_r_strand.p; ev.r_off = ix->d_r_off.p; ev.direct = ix->d_direct.p;
+    const unsigned grid = gtb_grid_for(q.n_regions, 128, (int64_t)ctx->sm_count * 16);
+    if (ix->op == GTB_OP_COVERAGE)
+      GTB_LAUNCH(ctx, "enumerate_coverage", enumerate_kernel<true>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand);
+    else
+      GTB_LAUNCH(ctx, "enumerate_count", enumerate_kernel<false>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand);
+    return gtb_check_launch(ctx);
+  }
+  const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 8);
+  const bool blocks = ix->op == GTB_OP_COVERAGE && !ix->match_gaps && batch_multi;
+  if (ix->op == GTB_OP_COVERAGE) {
+    if (blocks) GTB_LAUNCH(ctx, "rank_coverage_blocks", (rank_accumulate_kernel<true, true>), grid, 256, 0, q, rv);
+    else GTB_LAUNCH(ctx, "rank_coverage", (rank_accumulate_kernel<true, false>), grid, 256, 0, q, rv);
+  } else {
+    GTB_LAUNCH(ctx, "rank_count", (rank_accumulate_kernel<false, false>), grid, 256, 0, q, rv);
+  }
+  return gtb_check_launch(ctx);
+}
+
+extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsigned mem) {
+  if (!ix || !queries) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (queries->n_regions < 0 || queries->n_intervals < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative sizes");
+  if (queries->n_regions == 0) return GTB_OK;
+  if (!queries->region_offset && queries->n_regions != queries->n_intervals)
+    return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
+  if (!queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const bool batch_multi = queries->region_offset != nullptr && queries->n_intervals != queries->n_regions;
+  // a CSR whose regions all have one interval is passed on as the plain single-interval layout
+  const bool pass_offsets = batch_multi;
+
+  if (mem & GTB_MEM_DEVICE) {
+    QueryView q;
+    q.n_regions = queries->n_regions; q.chrom = queries->chrom; q.start = queries->start; q.stop = queries->stop;
+    q.strand = queries->strand; q.weight = queries->weight; q.region_offset = pass_offsets ? queries->region_offset : nullptr;
+    q.interval_base = 0; q.index_base = ix->queries_seen;
+    GTB_TRY(accumulate_device(ix, q, batch_multi));
+    ix->queries_seen += queries->n_regions;
+    return GTB_OK;
+  }
+
+  // host-resident batch: chunk, stage through two device buffers, copies on copy_stream overlap
+  // the kernels of the previous chunk on the compute stream.
+  const int64_t CHUNK = (int64_t)8 << 20;
+  for (int64_t r0 = 0; r0 < queries->n_regions; r0 += CHUNK) {
+    const int64_t r1 = std::min(queries->n_regions, r0 + CHUNK);
+    const int64_t i0 = pass_offsets ? queries->region_offset[r0] : r0;
+    const int64_t i1 = pass_offsets ? queries->region_offset[r1] : r1;
+    const size_t nr = (size_t)(r1 - r0), ni = (size_t)(i1 - i0);
+    gtb_index::stage &st = ix->stages[ix->next_stage];
+    ix->next_stage ^= 1;
+    if (st.in_flight) GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, st.consumed, 0));
+    GTB_TRY(st.chrom.reserve(ctx, ni)); GTB_TRY(st.start.reserve(ctx, ni)); GTB_TRY(st.stop.reserve(ctx, ni));
+    GTB_TRY(st.strand.reserve(ctx, ni));
+    cudaStream_t cs = ctx->copy_stream;
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.chrom.p, queries->chrom + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, queries->start + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.stop.p, queries->stop + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.strand.p, queries->strand + i0, ni, cudaMemcpyHostToDevice, cs));
+    if (queries->weight) {
+      GTB_TRY(st.weight.reserve(ctx, nr));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.weight.p, queries->weight + r0, nr * 4, cudaMemcpyHostToDevice, cs));
+    }
+    if (pass_offsets) {
+      GTB_TRY(st.off.reserve(ctx, nr + 1));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.off.p, queries->region_offset + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs));
+    }
+    GTB_CUDA_OK(ctx, cudaEventRecord(st.copied, cs));
+    GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied, 0));
+    QueryView q;
+    q.n_regions = (int64_t)nr; q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
+    q.weight = queries->weight ? st.weight.p : nullptr; q.region_offset = pass_offsets ? st.off.p : nullptr;
+    q.interval_base = i0; q.index_base = ix->queries_seen + r0;
+    GTB_TRY(accumulate_device(ix, q, batch_multi));
+    GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));
+    st.in_flight = true;
+  }
+  ix->queries_seen += queries->n_regions;
+  return GTB_OK;
+}
+
+// =================================================================================================
+// finish
+// =================================================================================================
+extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int64_t *err_index) {
+  if (!ix || (!out && ix->n_regions > 0)) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (err_index) *err_index = -1;
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  GTB_TRY(gtb_bucket_flush(ix));
+  const int64_t K = std::max<int64_t>(ix->n_slots, 1);
+  // scan a copy so that more batches may still be added after a finish
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(ix->d_hist_scan.p, ix->d_hist.p, sizeof(ull) * (size_t)ix->planes * (size_t)K,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ix->n_slots > 0)
+    for (int p = 0; p < ix->planes; p++)
+      GTB_TRY(gtb_inclusive_scan_u64(ctx, ix->d_hist_scan.p + (int64_t)p * K, ix->n_slots, ix->d_scan_scratch));
+  if (ix->n_regions > 0) {
+    const unsigned grid = (unsigned)((ix->n_regions + 255) / 256);
+    if (ix->op == GTB_OP_COVERAGE)
+      GTB_LAUNCH(ctx, "finalize_coverage", finalize_kernel<true>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
+    else
+      GTB_LAUNCH(ctx, "finalize_count", finalize_kernel<false>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(out, ix->d_out.p, sizeof(ull) * (size_t)ix->n_regions,
+                                     (mem & GTB_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  ull err = ~0ull;
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(&err, ix->d_err.p, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (err != ~0ull) {
+    if (err_index) *err_index = (int64_t)(err >> 8);
+    const int code = (int)(err & 0xFF);
+    return gtb_fail(ctx, code, code == GTB_ERR_QUERY_STOP_NONPOSITIVE ? "stop position must be positive!"
+                               : code == GTB_ERR_QUERY_START_GT_STOP ? "start position cannot be greater than stop position!"
+                               : "query regions should be compatible, sorted and non-overlapping!");
+  }
+  return GTB_OK;
+}
+
+static int one_shot(gtb_ctx *ctx, int op, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
+                    unsigned flags, uint64_t *out, int64_t *err_index) {
+  gtb_index *ix = nullptr;
+  int rc = gtb_index_create(ctx, regions, op, flags, &ix, err_index);
+  if (rc != GTB_OK) return rc;
+  rc = gtb_index_add_queries(ix, queries, queries_mem);
+  if (rc == GTB_OK) rc = gtb_index_finish(ix, out, GTB_MEM_HOST, err_index);
+  gtb_index_destroy(ix);
+  return rc;
+}
+
+extern "C" int gtb_overlap_count(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
+                                 unsigned flags, uint64_t *out, int64_t *err_index) {
+  return one_shot(ctx, GTB_OP_COUNT, queries, queries_mem, regions, flags, out, err_index);
+}
+
+extern "C" int gtb_overlap_coverage(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
+                                    unsigned flags, uint64_t *out, int64_t *err_index) {
+  return one_shot(ctx, GTB_OP_COVERAGE, queries, queries_mem, regions, flags, out, err_index);
+}

@@ -1,0 +1,177 @@
+/* gtb200.h -- C ABI of the B200-native interval overlap / coverage / window-count engine.
+ *
+ * This is the drop-in boundary for the hot path of GenomicTools 2.8.1a (tsirigos/ibm-cbc-genomic-tools).
+ * The reference has no FFI; the seam this ABI replaces is the C++ class API its drivers call
+ * (SURVEY.md section 8b).  Each entry point below cites the reference interface it stands in for
+ * (paths relative to the reference's gtools/ directory).  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only.  Every function returns an int status (GTB_OK == 0) and
+ *    never calls exit(); the host driver maps a status to the reference's message and exit code.
+ *  - Coordinates are the reference's internal ones: 1-based, closed (genomic_intervals.h:333-337),
+ *    i.e. BED start+1 (genomic_intervals.cpp:2163), REG/GFF as written.
+ *  - Chromosome ids are small non-negative integers chosen by the caller.  For gtb_scan_* they must
+ *    be assigned in strcmp order of the names, because ascending id is the output order
+ *    (the reference iterates a std::map<string,...>, genomic_intervals.cpp:5099, :5125-5141).
+ *  - Strand is the byte the reference keeps in GenomicInterval::STRAND: '+', '-', or for GFF the
+ *    raw first character of column 7 (genomic_intervals.cpp:3512).
+ *  - Weights are GenomicRegion::GetLabelValue(max_label_value) (genomic_intervals.cpp:1081-1085),
+ *    computed by the caller while parsing: 1 when max_label_value <= 1, else min(max, atol(label)).
+ *  - The library owns all device memory.  One host thread per context.  There is no CPU fallback:
+ *    without a CUDA device gtb_ctx_create fails with GTB_ERR_NO_DEVICE.
+ */
+#ifndef GTB200_H
+#define GTB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTB200_ABI_VERSION 1
+
+typedef struct gtb_ctx gtb_ctx;         /* device, streams, scratch                                */
+typedef struct gtb_index gtb_index;     /* an index (reference) region set resident on the device  */
+typedef struct gtb_scan gtb_scan;       /* a genome-wide micro-window histogram on the device      */
+
+/* A region set in struct-of-arrays form.  Replaces the reference's
+ * GenomicRegion{LABEL, vector<GenomicInterval*>} objects (genomic_intervals.h:962-964, :333-337).
+ * Region k owns intervals [region_offset[k], region_offset[k+1]); region_offset == NULL means one
+ * interval per region (n_intervals == n_regions), which is what BED3-BED11, GFF and single-interval
+ * REG lines produce. */
+typedef struct {
+  int64_t n_regions;
+  int64_t n_intervals;
+  const int32_t *chrom;          /* [n_intervals] */
+  const int32_t *start;          /* [n_intervals] */
+  const int32_t *stop;           /* [n_intervals] */
+  const int8_t  *strand;         /* [n_intervals] */
+  const int32_t *weight;         /* [n_regions] or NULL (= 1) */
+  const int64_t *region_offset;  /* [n_regions+1] or NULL */
+} gtb_set;
+
+/* option bits (the reference's -gaps and -i, genomic_overlaps.cpp:206-221, :191) */
+enum {
+  GTB_MATCH_GAPS       = 1u << 0,
+  GTB_IGNORE_STRAND    = 1u << 1,
+  /* where the arrays of a query/read gtb_set live */
+  GTB_MEM_HOST         = 0u,        /* host memory (pinned or pageable); copied inside the call */
+  GTB_MEM_DEVICE       = 1u << 8,   /* device pointers on the context's device                   */
+  /* engine selection (testing / benchmarking; results are identical) */
+  GTB_ENGINE_AUTO      = 0u,
+  GTB_ENGINE_ENUMERATE = 1u << 16,  /* candidate enumeration (general; any region shape)         */
+  GTB_ENGINE_RANK      = 1u << 17,  /* rank/rank-sum with global binary search                    */
+  GTB_ENGINE_BUCKET    = 1u << 18   /* partition by genome bucket + shared-memory rank (fast path) */
+};
+
+enum { GTB_OP_COUNT = 0, GTB_OP_COVERAGE = 1 };
+
+enum {
+  GTB_OK = 0,
+  GTB_ERR_ARG = 1,
+  /* fatal input conditions of the reference; *err_index = 0-based index of the offending region */
+  GTB_ERR_QUERY_STOP_NONPOSITIVE = 2,   /* genomic_intervals.cpp:5740 "stop position must be positive!" */
+  GTB_ERR_QUERY_START_GT_STOP    = 3,   /* genomic_intervals.cpp:5741 "start position cannot be greater than stop position!" */
+  GTB_ERR_QUERY_REGION           = 4,   /* genomic_intervals.cpp:5698,:5709 "query regions should be compatible, sorted and non-overlapping!" */
+  GTB_ERR_INDEX_REGION           = 5,   /* genomic_intervals.cpp:5607 "index regions should be compatible, sorted and non-overlapping!" */
+  GTB_ERR_WINDOW                 = 6,   /* genomic_intervals.cpp:4845 window size not a multiple of window step */
+  GTB_ERR_UNSUPPORTED            = 7,
+  GTB_ERR_NO_DEVICE              = 100,
+  GTB_ERR_CUDA                   = 101,
+  GTB_ERR_NOMEM                  = 102
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  gtb_abi_version(void);
+int  gtb_ctx_create(int device, gtb_ctx **out);
+void gtb_ctx_destroy(gtb_ctx *ctx);
+/* Launch all work of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g.
+ * so that a caller can bracket it with its own events.  NULL restores the context's own stream. */
+int  gtb_ctx_set_stream(gtb_ctx *ctx, void *cuda_stream);
+int  gtb_ctx_synchronize(gtb_ctx *ctx);
+const char *gtb_ctx_last_error(const gtb_ctx *ctx);
+/* Kernel accounting: number of kernels launched by this context since creation / last reset, and
+ * (when profiling is on) per-kernel CUDA-event times written as a JSON object into buf. */
+int64_t gtb_ctx_launch_count(const gtb_ctx *ctx);
+int  gtb_ctx_profile(gtb_ctx *ctx, int enable);
+int  gtb_ctx_profile_report(gtb_ctx *ctx, char *buf, size_t buf_size);
+
+/* ---- overlap count / coverage ------------------------------------------------------------- */
+/* Builds the device index for an in-memory reference region set.
+ * Stands in for the UnsortedGenomicRegionSetOverlaps / SortedGenomicRegionSetOverlaps constructors
+ * (genomic_intervals.cpp:5593-5675, :5807-5816) over a GenomicRegionSet loaded with
+ * load_in_memory=true (genomic_overlaps.cpp:412).  `regions` are host arrays.  op is GTB_OP_COUNT or
+ * GTB_OP_COVERAGE; flags carries GTB_MATCH_GAPS / GTB_IGNORE_STRAND and optionally an engine bit.
+ * GTB_ERR_INDEX_REGION: *err_index is the first malformed region (the reference is fatal, :5607). */
+int  gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, unsigned flags,
+                      gtb_index **out, int64_t *err_index);
+void gtb_index_destroy(gtb_index *index);
+/* Forget all queries seen so far (values back to zero). */
+int  gtb_index_reset(gtb_index *index);
+/* Streams one batch of query regions through the index and accumulates; asynchronous on the
+ * context's stream.  Stands in for one stretch of the query loop
+ * `for (qreg=GetQuery(); qreg; qreg=NextQuery())` of CountIndexOverlaps / CalcIndexCoverage
+ * (genomic_intervals.cpp:5310-5314, :5275-5282).  mem is GTB_MEM_HOST or GTB_MEM_DEVICE.
+ * Batches may be any size; region indices reported in errors count across batches. */
+int  gtb_index_add_queries(gtb_index *index, const gtb_set *queries, unsigned mem);
+/* Completes the accumulation and writes one value per index region, in index-file order:
+ * the `unsigned long *hits` / `*coverage` array CountIndexOverlaps / CalcIndexCoverage return
+ * (genomic_intervals.cpp:5308, :5273).  out is host memory unless mem == GTB_MEM_DEVICE.
+ * A fatal query condition (GTB_ERR_QUERY_*) is reported here with *err_index = the first offending
+ * query region in stream order; out is then unspecified (the reference prints nothing). */
+int  gtb_index_finish(gtb_index *index, uint64_t *out, unsigned mem, int64_t *err_index);
+
+/* One-shot conveniences == create + add + finish + destroy.
+ * gtb_overlap_count    <-> GenomicRegionSetOverlaps::CountIndexOverlaps(match_gaps, ignore_strand, max_label_value)  genomic_intervals.h:2471, .cpp:5304-5317
+ * gtb_overlap_coverage <-> GenomicRegionSetOverlaps::CalcIndexCoverage(match_gaps, ignore_strand, max_label_value)   genomic_intervals.h:2453, .cpp:5269-5285 */
+int  gtb_overlap_count(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
+                       unsigned flags, uint64_t *out, int64_t *err_index);
+int  gtb_overlap_coverage(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
+                          unsigned flags, uint64_t *out, int64_t *err_index);
+
+/* ---- sliding-window read counts ----------------------------------------------------------- */
+typedef struct {
+  int64_t win_step;        /* -d, genomic_scans.cpp:120 */
+  int64_t win_size;        /* -w, genomic_scans.cpp:119; must be a multiple of win_step */
+  int64_t min_reads;       /* -min, genomic_scans.cpp:121 */
+  int32_t op;              /* '1' = interval start, 'c' = interval centre (-op, genomic_scans.cpp:117) */
+  int32_t ignore_strand;   /* -i */
+  int32_t emulate_sorted;  /* 0: UnsortedGenomicRegionSetScanner semantics incl. its spurious window on
+                              chromosomes shorter than a window; 1: SortedGenomicRegionSetScanner values */
+  int32_t reserved;
+} gtb_scan_params;
+
+/* Allocates the per-chromosome, per-strand micro-window histograms on the device.
+ * Stands in for the UnsortedGenomicRegionSetScanner constructor's allocation
+ * (genomic_intervals.cpp:5024-5033) given ReadBounds() output (genomic_intervals.cpp:5997-6015):
+ * bound[c] = STOP of chromosome c in the genome file, < 0 if c is not in the genome file. */
+int  gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bound, const gtb_scan_params *params,
+                     gtb_scan **out);
+void gtb_scan_destroy(gtb_scan *scan);
+int  gtb_scan_reset(gtb_scan *scan);
+/* Histogram pass over a batch of reads (every interval of every region counts once,
+ * genomic_intervals.cpp:5038-5053).  Asynchronous on the context's stream. */
+int  gtb_scan_add_reads(gtb_scan *scan, const gtb_set *reads, unsigned mem);
+/* Sliding sum of win_size/win_step micro-windows (genomic_intervals.cpp:5058-5075) followed by the
+ * `v >= MIN_READS` filter of RunCounts (genomic_scans.cpp:421-428), compacted on the device in the
+ * reference's output order.  *n_windows = number of qualifying windows. */
+int  gtb_scan_finish(gtb_scan *scan, int64_t *n_windows);
+/* Copies qualifying windows [first, first+count) to host arrays: chromosome id, strand ('+'/'-'),
+ * 1-based window number k (interval = [win_step*(k-1)+1, win_step*(k-1)+win_size],
+ * genomic_intervals.cpp:5109-5112) and value -- what successive Scanner::Next() calls return
+ * (genomic_intervals.h:2213-2217).  Any output pointer may be NULL. */
+int  gtb_scan_fetch(gtb_scan *scan, int64_t first, int64_t count, int32_t *chrom, int8_t *strand,
+                    int64_t *win, int64_t *value);
+
+/* ---- synthetic inputs (bench / tests) ------------------------------------------------------ */
+/* Fills DEVICE arrays with reads [first, first+n) of the counter-based generator documented in
+ * DESIGN.md ("Synthetic inputs"); identical to tests/support.py:synth_reads. */
+int  gtb_synth_reads(gtb_ctx *ctx, uint64_t seed, int64_t first, int64_t n, int32_t read_len,
+                     int32_t n_chrom, const int64_t *chrom_len /*host*/, int32_t *d_chrom, int32_t *d_start,
+                     int32_t *d_stop, int8_t *d_strand);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,180 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the committed golden vectors.
+Bit-exact: all of this is integer arithmetic."""
+import numpy as np
+import pytest
+
+import goldens
+import randcases
+import support
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16}
+
+
+@pytest.fixture(scope="module")
+def gtb():
+    import gtb200
+    return gtb200
+
+
+@pytest.fixture(scope="module")
+def ctx(gtb):
+    c = gtb.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return support.Oracle()
+
+
+@pytest.mark.parametrize("engine", list(ENGINES))
+@pytest.mark.parametrize("case", goldens.overlap_cases(), ids=lambda c: c["name"])
+def test_overlap_golden(ctx, case, engine):
+    multi = case["ioff"] is not None or case["qoff"] is not None
+    for (op, flags), want in case["expect"].items():
+        if engine == "rank" and multi and op == "count" and not (flags & 1):
+            continue        # ranks cannot express "any block pair overlaps"; auto routes these to enumerate
+        fn = ctx.overlap_count if op == "count" else ctx.overlap_coverage
+        got = fn(case["queries"], case["index"], flags | ENGINES[engine], qweight=case["qw"],
+                 qoffsets=case["qoff"], roffsets=case["ioff"])
+        assert np.array_equal(got, want), (case["name"], op, flags, engine)
+
+
+@pytest.mark.parametrize("case", goldens.scan_cases(), ids=lambda c: c["name"])
+def test_scan_golden(gtb, ctx, case):
+    sc = gtb.Scan(ctx, case["bounds"], case["win_step"], case["win_size"], case["op"], case["ignore_strand"], case["min_reads"])
+    sc.add_host(case["reads"], weight=case["rw"])
+    n = sc.finish()
+    assert n == len(case["expect"]["value"])
+    got = sc.fetch(0, n)
+    for k in ("chrom", "strand", "win", "value"):
+        assert np.array_equal(got[k], case["expect"][k]), (case["name"], k)
+    sc.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_vs_oracle(ctx, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    if seed % 2 == 0:
+        idx = (randcases.rand_grid if seed % 4 else randcases.rand_single)(rng, 300)
+        q = (randcases.rand_grid if seed % 4 else randcases.rand_single)(rng, 20000)
+        ioff = qoff = None
+    else:
+        idx, ioff = randcases.rand_multi(rng, 200)
+        q, qoff = randcases.rand_multi(rng, 8000)
+    w = rng.integers(-3, 9, size=(len(qoff) - 1) if qoff is not None else len(q["chrom"])).astype(np.int32)
+    for flags in range(4):
+        for weights in (None, w):
+            rc, want, _ = oracle.count(q, idx, flags, qw=weights, qoff=qoff, ioff=ioff)
+            got = ctx.overlap_count(q, idx, flags, qweight=weights, qoffsets=qoff, roffsets=ioff)
+            assert rc == 0 and np.array_equal(got, want), ("count", flags, seed)
+            rc, want, _ = oracle.coverage(q, idx, flags, qw=weights, qoff=qoff, ioff=ioff)
+            got = ctx.overlap_coverage(q, idx, flags, qweight=weights, qoffsets=qoff, roffsets=ioff)
+            assert rc == 0 and np.array_equal(got, want), ("coverage", flags, seed)
+            got = ctx.overlap_coverage(q, idx, flags | ENGINES["enumerate"], qweight=weights, qoffsets=qoff, roffsets=ioff)
+            assert np.array_equal(got, want), ("coverage/enumerate", flags, seed)
+
+
+def test_negative_and_degenerate_coordinates(ctx, oracle):
+    """Index regions with start<=0, invalid index regions (value 0), queries starting at <= 0."""
+    idx = {"chrom": [0, 0, 0, 0, 1], "start": [301, -49, -4, 5, 1], "stop": [250, 0, 20, 5, 2147483647], "strand": [43] * 5}
+    q = {"chrom": [0, 0, 0, 1, 1], "start": [1, -2, 5, 2147483000, 1], "stop": [400, 2, 5, 2147483647, 1], "strand": [43] * 5}
+    for flags in (0, 1, 2, 3):
+        for fn_o, fn_g in ((oracle.count, ctx.overlap_count), (oracle.coverage, ctx.overlap_coverage)):
+            rc, want, _ = fn_o(q, idx, flags)
+            assert rc == 0 and np.array_equal(fn_g(q, idx, flags), want)
+            assert np.array_equal(fn_g(q, idx, flags | ENGINES["enumerate"]), want)
+
+
+def test_fatal_conditions(gtb, ctx, oracle):
+    idx = {"chrom": [0], "start": [101], "stop": [200], "strand": [43]}
+    cases = [({"chrom": [0, 0, 0], "start": [151, 301, 7], "stop": [160, 250, 3], "strand": [43] * 3}, 3, 1),
+             ({"chrom": [0, 0], "start": [150, -9], "stop": [160, 0], "strand": [43] * 2}, 2, 1),
+             ({"chrom": [1, 0], "start": [301, 151], "stop": [250, 160], "strand": [43] * 2}, 0, -1)]
+    for q, code, where in cases:
+        rc, _, ei = oracle.count(q, idx, 0)
+        assert (rc, ei) == (code, where)
+        for eng in ENGINES.values():
+            if code == 0:
+                assert ctx.overlap_count(q, idx, eng).tolist() == [1]
+            else:
+                with pytest.raises(gtb.GtbError) as e:
+                    ctx.overlap_count(q, idx, eng)
+                assert (e.value.code, e.value.index) == (code, where)
+    # malformed regions: blocks out of order / overlapping / on different strands
+    bad = {"chrom": [0, 0], "start": [50, 10], "stop": [60, 20], "strand": [43, 43]}
+    off = [0, 2]
+    rc, _, ei = oracle.count(bad, idx, 0, qoff=off)
+    assert (rc, ei) == (4, 0)
+    with pytest.raises(gtb.GtbError) as e:
+        ctx.overlap_count(bad, idx, 0, qoffsets=off)
+    assert (e.value.code, e.value.index) == (4, 0)
+    rc, _, ei = oracle.count(idx, bad, 0, ioff=off)
+    assert (rc, ei) == (5, 0)
+    with pytest.raises(gtb.GtbError) as e:
+        ctx.overlap_count(idx, bad, 0, roffsets=off)
+    assert (e.value.code, e.value.index) == (5, 0)
+
+
+def test_empty_inputs(ctx):
+    empty = {"chrom": [], "start": [], "stop": [], "strand": []}
+    idx = {"chrom": [0], "start": [1], "stop": [10], "strand": [43]}
+    assert ctx.overlap_count(empty, idx).tolist() == [0]
+    assert ctx.overlap_count(idx, empty).tolist() == []
+    assert ctx.overlap_coverage(empty, empty).tolist() == []
+
+
+def test_streaming_batches_equal_one_shot(gtb, ctx, oracle):
+    reads = support.synth_reads(300_000, seed=21)
+    regions = support.synth_regions(3_000, seed=22)
+    rc, want, _ = oracle.coverage(reads, regions, 0)
+    ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, 0)
+    for lo in range(0, 300_000, 70_001):
+        ix.add_host({k: v[lo:lo + 70_001] for k, v in reads.items()})
+    assert np.array_equal(ix.finish(), want)
+    assert np.array_equal(ix.finish(), want), "finish must be repeatable"
+    ix.reset()
+    ix.add_host(reads)
+    assert np.array_equal(ix.finish(), want)
+    ix.close()
+
+
+def test_hg19_shaped_medium(gtb, ctx, oracle):
+    """2 M hg19-shaped 50-bp reads vs 5 000 gene-like regions, every flag combination, plus
+    device-resident inputs generated by the library's own generator (== the numpy generator)."""
+    import torch
+    n = 2_000_000
+    reads = support.synth_reads(n, seed=2)
+    regions = support.synth_regions(5_000, seed=3)
+    dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
+           "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
+    ctx.synth_reads(2, 0, n, 50, support.HG19_LENS, dev)
+    for k in dev:
+        assert np.array_equal(dev[k].cpu().numpy(), reads[k]), k
+    for flags in (0, gtb.IGNORE_STRAND):
+        for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+            rc, want, _ = fn(reads, regions, flags)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, flags)
+            ix.add_device(dev)
+            assert np.array_equal(ix.finish(), want), (op, flags)
+            ix.close()
+
+
+def test_scan_hg19_vs_oracle(gtb, ctx, oracle):
+    reads = support.synth_reads(1_000_000, seed=4)
+    bound = support.HG19_LENS.copy()
+    bound[5] = -1                                    # one chromosome missing from the genome file
+    for (w, d, op, ign, mn) in ((200, 50, "1", False, 2), (500, 25, "c", True, 3), (1000, 1000, "1", False, 1)):
+        n, want = oracle.scan_counts(reads, bound, d, w, op, ign, mn)
+        sc = gtb.Scan(ctx, bound, d, w, op, ign, mn)
+        for lo in range(0, 1_000_000, 400_000):
+            sc.add_host({k: v[lo:lo + 400_000] for k, v in reads.items()})
+        assert sc.finish() == n
+        got = sc.fetch(0, n)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (w, d, op, k)
+        sc.close()
