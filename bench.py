@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the overlap-count hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at N=1 = BASELINE.json configs[1]: 100 M synthetic 50-bp hg19-shaped reads vs 60 000
+gene-like regions, strand-aware `genomic_overlaps count`.  A step is one full pass of the hot path
+over the batch: reset -> accumulate every query -> finalise per-region counts.
+  value  : query intervals / s, device-timed (CUDA events), inputs already resident in HBM
+  e2e    : the same through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
+  roofline : dominant kernel's algorithmic bytes / its mean CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline : the CPU path timed on this box's host cores on a bounded sample
+For N > 1 (torchrun, one rank per GPU) every rank streams its own 100 M-read shard (weak scaling) and
+the per-region partial counts are merged by ONE NCCL reduction; value = all reads / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "ibm-cbc-genomic-tools_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_READS = 100_000_000
+N_REGIONS = 60_000
+READ_LEN = 50
+SEED_READS, SEED_REGIONS = 2, 3
+BYTES_PER_QUERY, BYTES_PER_REGION = 13, 21
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_port(regions, sample=2_000_000):
+    """Oracle (scalar C port of the reference engine) on one host core, bounded sample."""
+    import support
+    orc = support.Oracle()
+    reads = support.synth_reads(sample, SEED_READS)
+    t0 = time.perf_counter()
+    rc, _, _ = orc.count(reads, regions, 0)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return {"value": sample / dt, "unit": "query intervals/s", "cores": 1, "kind": "port",
+            "sample": "first %d of the %d reads vs all %d regions, engine only (no parsing)" % (sample, N_READS, N_REGIONS)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import support
+    regions = support.synth_regions(N_REGIONS, SEED_REGIONS)
+    cores = os.cpu_count() or 1
+    sample = 1_000_000
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_engine")
+    kind = "reference" if os.path.exists(exe) else "port"
+    times = []
+    if kind == "reference":
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="gtb_ref_")
+        rf = os.path.join(tmp, "regions.bed")
+        support.write_bed(rf, regions, support.HG19_NAMES)
+        for step in range(args.warmup + args.steps):
+            procs = [subprocess.Popen([exe, rf, str(SEED_READS), str((step * cores + p) * sample), str(sample), str(READ_LEN)],
+                                      stdout=subprocess.PIPE, text=True) for p in range(cores)]
+            outs = [p.communicate()[0] for p in procs]
+            secs = [float(json.loads(o.strip().splitlines()[-1])["engine_seconds"]) for o in outs]
+            if step >= args.warmup:
+                times.append(max(secs))
+    else:
+        orc = support.Oracle()
+        cores = 1
+        for step in range(args.warmup + args.steps):
+            reads = support.synth_reads(sample, SEED_READS, first=step * sample)
+            t0 = time.perf_counter()
+            orc.count(reads, regions, 0)
+            if step >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sample * cores * len(times)
+    value = total / sum(times)
+    line = {"impl": "reference", "metric": "query intervals/sec (overlap-count)", "value": value, "unit": "query intervals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "100M synthetic 50bp hg19 reads vs 60k gene regions, strand-aware count (configs[1])",
+                       "n_regions": N_REGIONS, "read_len": READ_LEN},
+            "cpu_baseline": {"value": value, "unit": "query intervals/s", "cores": cores, "kind": kind,
+                             "sample": "%d reads per core per step x %d cores, engine only (CountIndexOverlaps), regions=%d" % (sample, cores, N_REGIONS)},
+            "e2e": {"value": value, "unit": "query intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU (default: the BASELINE config)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "rank", "bucket", "enumerate"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import gtb200
+    import support
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.reads
+    regions = support.synth_regions(N_REGIONS, SEED_REGIONS)
+    ctx = gtb200.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "bucket": gtb200.ENGINE_BUCKET, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
+    index = gtb200.Index(ctx, regions, gtb200.OP_COUNT, engine)
+
+    dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
+           "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
+    ctx.synth_reads(SEED_READS, rank * n, n, READ_LEN, support.HG19_LENS, dev)     # rank r streams reads [r*n, (r+1)*n)
+    dset, keep = gtb200.device_set(dev)
+    out_dev = torch.zeros(N_REGIONS, dtype=torch.int64, device="cuda")
+
+    def step_device():
+        index.reset()
+        index.add_set(dset, gtb200.MEM_DEVICE)
+        index.finish_ptr(out_dev.data_ptr(), gtb200.MEM_DEVICE)
+        if dist is not None:
+            dist.all_reduce(out_dev)                     # the single collective: per-region partial counts
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`) ----------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    counts_check = int(out_dev.sum().item())
+
+    # ---- per-kernel CUDA-event profile for the roofline (outside the timed region) -------------------
+    ctx.profile(True)
+    for _ in range(3):
+        step_device()
+    torch.cuda.synchronize()
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    dom_name, dom = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
+    dom_ms = dom["total_ms"] / dom["launches"]
+    total_prof_ms = sum(v["total_ms"] for v in prof.values())
+    peak, peak_kind = measured_peak()
+    alg_bytes = BYTES_PER_QUERY * n                      # one launch of the dominant kernel streams the whole batch
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel_ms": dom_ms, "kernel_share_of_step": dom["total_ms"] / total_prof_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "step_frac": (BYTES_PER_QUERY * n + BYTES_PER_REGION * N_REGIONS) / (ms_per_step * 1e-3) / 1e9 / peak,
+                "kernels": {k: {"launches_per_step": v["launches"] / 3, "ms_per_launch": v["total_ms"] / v["launches"]} for k, v in prof.items()}}
+
+    # ---- end to end through the C ABI with host buffers (`e2e`) -------------------------------------
+    n_e2e = n
+    host = {k: torch.empty(n_e2e, dtype=v.dtype).pin_memory() for k, v in dev.items()}
+    for k in host:
+        host[k].copy_(dev[k][:n_e2e])
+    hset, keep2 = gtb200.pinned_set(host)
+    out_host = np.zeros(N_REGIONS, dtype=np.uint64)
+
+    def step_e2e():
+        index.reset()
+        index.add_set(hset, gtb200.MEM_HOST)
+        index.finish(out_host)
+        if dist is not None:
+            t = torch.from_numpy(out_host.view(np.int64)).cuda()
+            dist.all_reduce(t)
+            out_host[:] = t.cpu().numpy().view(np.uint64)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * n_e2e / e2e_s, "unit": "query intervals/s", "h2d_bytes_per_step": BYTES_PER_QUERY * n_e2e,
+           "d2h_bytes_per_step": 8 * N_REGIONS, "ms_per_step": e2e_s * 1e3}
+
+    if rank == 0:
+        line = {"metric": "query intervals/sec (overlap-count, device-timed)", "value": value, "unit": "query intervals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": "100M synthetic 50bp hg19 reads vs 60k gene regions, strand-aware count (configs[1])",
+                           "reads_per_gpu": n, "n_regions": N_REGIONS, "read_len": READ_LEN, "engine": args.engine,
+                           "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_QUERY * n / 1e9),
+                           "parallelism": "query-sharded x%d, one NCCL all-reduce of per-region counts" % world if world > 1 else "single GPU"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+                "checksum": counts_check}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(regions)
+        print(json.dumps(line))
+    index.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
