@@ -1,6 +1,6 @@
 // gtb_overlap.cu -- overlap count / coverage: index construction, the general RANK and ENUMERATE
 // engines, finalisation, and the streaming C-ABI around them (include/gtb200.h).
-#include "gtb_overlap.cuh"
+#include "gtb_rank_device.cuh"
 #include <algorithm>
 #include <limits.h>
 
@@ -8,20 +8,6 @@
 // device helpers
 // =================================================================================================
 namespace {
-
-__device__ __forceinline__ void report_error(ull *err, int64_t index, int code) {
-  atomicMin(err, ((ull)index << 8) | (ull)code);
-}
-
-// first slot j in [lo,hi) with points[j] >= x ; the group's last slot is a +inf sentinel so the
-// answer always exists when called with hi = group end.
-__device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ p, int lo, int hi, int32_t x) {
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(p + mid) < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 __device__ __forceinline__ int64_t lower_bound_u64(const ull *__restrict__ p, int64_t n, ull x) {
   int64_t lo = 0, hi = n;
@@ -63,25 +49,6 @@ __device__ __forceinline__ bool admit_query(const QueryView &q, int64_t r, const
 // One thread per query region.  Handles weights, any interval length, negative coordinates,
 // multi-interval queries (spans under -gaps, blocks for coverage).
 // -------------------------------------------------------------------------------------------------
-template <bool COVERAGE>
-__device__ __forceinline__ void rank_item(const RankView &ix, int gb, int ge, int32_t qs, int32_t qe, int64_t w) {
-  const int jS = lower_bound_i32(ix.points, gb, ge - 1, qs);      // ge-1 is the sentinel: result <= ge-1
-  const int jE = lower_bound_i32(ix.points, jS, ge - 1, qe);
-  ull *h = ix.hist;
-  const int64_t K = ix.n_slots;
-  if (jS == jE) {
-    if (COVERAGE) atomicAdd(h + H_BOTH * K + jS, (ull)(w * ((int64_t)qe - qs + 1)));
-    else atomicAdd(h + H_BOTH * K + jS, (ull)w);
-  } else {
-    atomicAdd(h + H_SCNT * K + jS, (ull)w);
-    atomicAdd(h + H_ECNT * K + jE, (ull)w);
-    if (COVERAGE) {
-      atomicAdd(h + H_SSUM * K + jS, (ull)(w * (int64_t)qs));
-      atomicAdd(h + H_ESUM * K + jE, (ull)(w * (int64_t)qe));
-    }
-  }
-}
-
 template <bool COVERAGE, bool BLOCKS>
 __global__ void __launch_bounds__(256) rank_accumulate_kernel(QueryView q, RankView ix) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -166,27 +133,42 @@ __global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix
 template <bool COVERAGE>
 __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const int64_t *__restrict__ t_off,
                                                        const int32_t *__restrict__ t_hi, const int32_t *__restrict__ t_lo,
-                                                       const int32_t *__restrict__ t_base, const int32_t *__restrict__ points,
-                                                       const ull *__restrict__ scan, int64_t K,
-                                                       const ull *__restrict__ direct, ull *__restrict__ out) {
+                                                       const int32_t *__restrict__ t_group, const int32_t *__restrict__ goff,
+                                                       const int32_t *__restrict__ points, const ull *__restrict__ scan, int64_t K,
+                                                       CellFinalView cf, const ull *__restrict__ direct, ull *__restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_regions) return;
   ull total = direct ? direct[k] : 0ull;
   for (int64_t t = t_off[k]; t < t_off[k + 1]; t++) {
-    const int hi = t_hi[t], lo = t_lo[t], base = t_base[t];
-    // group-relative inclusive prefix of plane p at slot j
+    const int hi = t_hi[t], lo = t_lo[t], g = t_group[t], base = goff[g];
+    // RANK engine: group-relative inclusive prefix of slot plane p at slot j
     auto pre = [&](int p, int j) -> ull {
       const ull *a = scan + (int64_t)p * K;
       return a[j] - (base > 0 ? a[base - 1] : 0ull);
     };
+    // CELL engine: everything in the group's cells before the cell of slot j's point, plus the
+    // point's own correction counter.  cp = cell plane, xp = correction plane (-1: none).
+    auto cel = [&](int cp, int xp, int j) -> ull {
+      if (!cf.cells_scan) return 0ull;
+      const uint32_t c = cf.slot_cell[j];
+      if (c == 0xFFFFFFFFu) return 0ull;            // point <= 0 or sentinel: no fast-path query can be <= it
+      const uint32_t gb = cf.gbase[g];
+      const ull *a = cf.cells_scan + (int64_t)cp * cf.n_cells;
+      ull v = (c > 0 ? a[c - 1] : 0ull) - (gb > 0 ? a[gb - 1] : 0ull);
+      if (xp >= 0) v += cf.corr[(int64_t)xp * K + j];
+      return v;
+    };
     if (!COVERAGE) {
-      const ull starts_le_te = pre(H_BOTH, hi) + pre(H_SCNT, hi);      // #{qs <= te}
-      const ull stops_lt_ts = pre(H_BOTH, lo) + pre(H_ECNT, lo);       // #{qe <= ts-1}
+      const ull starts_le_te = pre(H_BOTH, hi) + pre(H_SCNT, hi) + cel(C_BOTH, -1, hi) + cel(C_SCNT, X_SCNT, hi);   // #{qs <= te}
+      const ull stops_lt_ts = pre(H_BOTH, lo) + pre(H_ECNT, lo) + cel(C_BOTH, -1, lo) + cel(C_ECNT, X_ECNT, lo);    // #{qe <= ts-1}
       total += starts_le_te - stops_lt_ts;
     } else {
       auto F = [&](int j) -> ull {
         const ull x = (ull)(int64_t)points[j];
-        return pre(H_BOTH, j) + (x + 1ull) * pre(H_SCNT, j) - pre(H_SSUM, j) - x * pre(H_ECNT, j) + pre(H_ESUM, j);
+        const ull L = pre(H_BOTH, j) + cel(C_BOTH, -1, j);
+        const ull cs = pre(H_SCNT, j) + cel(C_SCNT, X_SCNT, j), ss = pre(H_SSUM, j) + cel(C_SSUM, X_SSUM, j);
+        const ull ce = pre(H_ECNT, j) + cel(C_ECNT, X_ECNT, j), se = pre(H_ESUM, j) + cel(C_ESUM, X_ESUM, j);
+        return L + (x + 1ull) * cs - ss - x * ce + se;
       };
       total += F(hi) - F(lo);
     }
@@ -287,14 +269,14 @@ static int build_rank_structures(gtb_index *ix) {
   ix->n_slots = (int64_t)ix->h_points.size();
   if (ix->n_slots > (int64_t)INT_MAX - 8) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "too many evaluation points");
 
-  std::vector<int32_t> t_hi(targets.size()), t_lo(targets.size()), t_base(targets.size());
+  std::vector<int32_t> t_hi(targets.size()), t_lo(targets.size()), t_group(targets.size());
   for (size_t t = 0; t < targets.size(); t++) {
     const int32_t gb = ix->h_goff[targets[t].g], ge = ix->h_goff[targets[t].g + 1];
     const int32_t *b = ix->h_points.data() + gb, *e = ix->h_points.data() + ge - 1;
     const int32_t lo_x = targets[t].ts == INT32_MIN ? INT32_MIN : targets[t].ts - 1;
     t_hi[t] = (int32_t)(std::lower_bound(b, e, targets[t].te) - ix->h_points.data());
     t_lo[t] = (int32_t)(std::lower_bound(b, e, lo_x) - ix->h_points.data());
-    t_base[t] = gb;
+    t_group[t] = targets[t].g;
   }
 
   GTB_TRY(upload(ctx, ix->d_class_of, ix->h_class_of));
@@ -303,7 +285,7 @@ static int build_rank_structures(gtb_index *ix) {
   GTB_TRY(upload(ctx, ix->d_points, ix->h_points));
   GTB_TRY(upload(ctx, ix->d_t_hi, t_hi));
   GTB_TRY(upload(ctx, ix->d_t_lo, t_lo));
-  GTB_TRY(upload(ctx, ix->d_t_base, t_base));
+  GTB_TRY(upload(ctx, ix->d_t_base, t_group));
   GTB_TRY(upload(ctx, ix->d_t_off, t_off));
   ix->planes = ix->op == GTB_OP_COVERAGE ? H_PLANES_COVERAGE : H_PLANES_COUNT;
   const size_t hist_elems = (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1);
@@ -357,6 +339,7 @@ extern "C" int gtb_index_reset(gtb_index *ix) {
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_hist.p, 0, sizeof(ull) * (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_direct.p, 0, sizeof(ull) * (size_t)std::max<int64_t>(ix->n_regions, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
+  GTB_TRY(gtb_cell_reset(ix));
   ix->queries_seen = 0;
   return GTB_OK;
 }
@@ -381,7 +364,7 @@ extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, un
   ix->ctx = ctx; ix->op = op;
   ix->match_gaps = (flags & GTB_MATCH_GAPS) != 0;
   ix->ignore_strand = (flags & GTB_IGNORE_STRAND) != 0;
-  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET);
+  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_CELL);
   ix->n_regions = regions->n_regions; ix->n_intervals = regions->n_intervals;
   const size_t ni = (size_t)regions->n_intervals;
   ix->h_chrom.assign(regions->chrom, regions->chrom + ni);
@@ -406,7 +389,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   if (!ix) return;
   cudaSetDevice(ix->ctx->device);
   gtb_ctx_synchronize(ix->ctx);
-  gtb_bucket_destroy(ix);
+  gtb_cell_destroy(ix);
   ix->d_class_of.release(); ix->d_present.release(); ix->d_goff.release(); ix->d_points.release();
   ix->d_t_hi.release(); ix->d_t_lo.release(); ix->d_t_base.release(); ix->d_t_off.release();
   ix->d_hist.release(); ix->d_hist_scan.release(); ix->d_scan_scratch.release();
@@ -434,12 +417,12 @@ static RankView rank_view(gtb_index *ix) {
 }
 
 // which engine may serve this (index, batch) pair
-static unsigned choose_engine(const gtb_index *ix, const QueryView &q, bool batch_multi) {
+static unsigned choose_engine(gtb_index *ix, const QueryView &q, bool batch_multi) {
   const bool rank_valid = ix->op == GTB_OP_COVERAGE || ix->match_gaps || (!ix->index_multi && !batch_multi);
   if (ix->engine & GTB_ENGINE_ENUMERATE) return GTB_ENGINE_ENUMERATE;
   if (!rank_valid) return GTB_ENGINE_ENUMERATE;
   if (ix->engine & GTB_ENGINE_RANK) return GTB_ENGINE_RANK;
-  if (gtb_bucket_supported(ix, q)) return GTB_ENGINE_BUCKET;
+  if (gtb_cell_supported(ix, q, batch_multi)) return GTB_ENGINE_CELL;
   return GTB_ENGINE_RANK;
 }
 
@@ -447,7 +430,7 @@ static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi
   gtb_ctx *ctx = ix->ctx;
   if (q.n_regions <= 0) return GTB_OK;
   const unsigned engine = choose_engine(ix, q, batch_multi);
-  if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
+  if (engine == GTB_ENGINE_CELL) return gtb_cell_accumulate(ix, q);
   RankView rv = rank_view(ix);
   if (engine == GTB_ENGINE_ENUMERATE) {
     GTB_TRY(build_enum_structures(ix));
@@ -544,7 +527,9 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
   gtb_ctx *ctx = ix->ctx;
   if (err_index) *err_index = -1;
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  GTB_TRY(gtb_bucket_flush(ix));
+  CellFinalView cf{};
+  GTB_TRY(gtb_cell_scan_for_finish(ix, &cf));
+  cf.t_group = ix->d_t_base.p;
   const int64_t K = std::max<int64_t>(ix->n_slots, 1);
   // scan a copy so that more batches may still be added after a finish
   GTB_CUDA_OK(ctx, cudaMemcpyAsync(ix->d_hist_scan.p, ix->d_hist.p, sizeof(ull) * (size_t)ix->planes * (size_t)K,
@@ -556,10 +541,10 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
     const unsigned grid = (unsigned)((ix->n_regions + 255) / 256);
     if (ix->op == GTB_OP_COVERAGE)
       GTB_LAUNCH(ctx, "finalize_coverage", finalize_kernel<true>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
-                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, cf, ix->d_direct.p, ix->d_out.p);
     else
       GTB_LAUNCH(ctx, "finalize_count", finalize_kernel<false>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
-                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, cf, ix->d_direct.p, ix->d_out.p);
     GTB_TRY(gtb_check_launch(ctx));
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(out, ix->d_out.p, sizeof(ull) * (size_t)ix->n_regions,
                                      (mem & GTB_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));

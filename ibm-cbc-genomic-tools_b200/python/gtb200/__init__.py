@@ -19,7 +19,7 @@ MEM_DEVICE = 1 << 8
 ENGINE_AUTO = 0
 ENGINE_ENUMERATE = 1 << 16
 ENGINE_RANK = 1 << 17
-ENGINE_BUCKET = 1 << 18
+ENGINE_CELL = 1 << 18
 OP_COUNT = 0
 OP_COVERAGE = 1
 
