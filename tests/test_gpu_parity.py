@@ -9,7 +9,15 @@ import support
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16}
+ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18}
+CELL_KS = ("3", "6", "10")      # cell widths 8 / 64 / 1024 bp: mostly-cold, mixed, and overfull-hot-cell regimes
+
+
+@pytest.fixture(params=CELL_KS)
+def cell_k(request, monkeypatch):
+    monkeypatch.setenv("GTB_CELL_K", request.param)
+    return request.param
+
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +40,9 @@ def oracle():
 
 @pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("case", goldens.overlap_cases(), ids=lambda c: c["name"])
-def test_overlap_golden(ctx, case, engine):
+def test_overlap_golden(ctx, case, engine, cell_k):
+    if engine != "cell" and cell_k != CELL_KS[0]:
+        pytest.skip("cell width only matters to the cell engine")
     multi = case["ioff"] is not None or case["qoff"] is not None
     for (op, flags), want in case["expect"].items():
         if engine == "rank" and multi and op == "count" and not (flags & 1):
@@ -56,7 +66,7 @@ def test_scan_golden(gtb, ctx, case):
 
 
 @pytest.mark.parametrize("seed", range(8))
-def test_random_vs_oracle(ctx, oracle, seed):
+def test_random_vs_oracle(ctx, oracle, seed, cell_k):
     rng = np.random.default_rng(1000 + seed)
     if seed % 2 == 0:
         idx = (randcases.rand_grid if seed % 4 else randcases.rand_single)(rng, 300)
@@ -78,7 +88,7 @@ def test_random_vs_oracle(ctx, oracle, seed):
             assert np.array_equal(got, want), ("coverage/enumerate", flags, seed)
 
 
-def test_negative_and_degenerate_coordinates(ctx, oracle):
+def test_negative_and_degenerate_coordinates(ctx, oracle, cell_k):
     """Index regions with start<=0, invalid index regions (value 0), queries starting at <= 0."""
     idx = {"chrom": [0, 0, 0, 0, 1], "start": [301, -49, -4, 5, 1], "stop": [250, 0, 20, 5, 2147483647], "strand": [43] * 5}
     q = {"chrom": [0, 0, 0, 1, 1], "start": [1, -2, 5, 2147483000, 1], "stop": [400, 2, 5, 2147483647, 1], "strand": [43] * 5}
@@ -87,6 +97,7 @@ def test_negative_and_degenerate_coordinates(ctx, oracle):
             rc, want, _ = fn_o(q, idx, flags)
             assert rc == 0 and np.array_equal(fn_g(q, idx, flags), want)
             assert np.array_equal(fn_g(q, idx, flags | ENGINES["enumerate"]), want)
+            assert np.array_equal(fn_g(q, idx, flags | ENGINES["rank"]), want)
 
 
 def test_fatal_conditions(gtb, ctx, oracle):
