@@ -7,7 +7,7 @@
 // more.  The evaluation points (2 per region) do not fit in shared memory, but one BIT per genome
 // cell does:
 //   * every group's coordinate axis [0, size_g+1] is cut into cells of 2^k bp, laid end to end
-//     (n_cells <= 851 968, so bitmap + per-word hot-rank fit in 208 KB of shared memory);
+//     (n_cells <= 1 572 864, so the bitmap fits in 192 KB of shared memory; hg19 x 2 strands: k = 12);
 //   * a cell is HOT if it contains an evaluation point.  A query whose start and stop fall into the
 //     same COLD cell lies inside one inter-point segment: a single red.global.add on the cell's
 //     "both" counter (table is a few MB: L2 resident, no HBM traffic);
@@ -16,18 +16,23 @@
 //     beyond the coordinate gets a red on its correction counter;
 //   * finalisation turns the cell tables into prefix sums, so for an evaluation point p
 //       #{qs <= p} = sum(cells of the group before cell(p)) + correction[p]            (exactly).
+// Divergence: ~8 % of queries touch a hot cell, so nearly every warp would have a lane on the slow
+// branch.  The kernel therefore works tile by tile (4 096 queries per CTA): cold queries are
+// retired on the spot, the rest are compacted into a shared-memory queue (warp ballot + one
+// shared atomic per warp) and processed afterwards with all lanes busy.
 // Queries the scheme cannot place (start <= 0, a cell holding more than 13 points) take the
-// general rank step inline; results add up because every table is a sum over queries.
+// general rank step; results add up because every table is a sum over queries.
 #include "gtb_rank_device.cuh"
 #include <algorithm>
 
 namespace {
 
-constexpr uint32_t CELL_MAX_CELLS = 851968;      // 26 624 words * 8 B = 208 KB of shared memory
+constexpr uint32_t CELL_MAX_CELLS = 1638400;     // 51 200 bitmap words = 200 KB of shared memory
+constexpr int CELL_QCAP = 1024;                  // deferred-query queue entries (16 B each, 16 KB)
 constexpr int CELL_MIN_K = 3;
 constexpr int CELL_MAX_K = 16;                   // point offsets inside a cell are stored in 16 bits
-constexpr int CELL_THREADS = 1024;
-constexpr int CELL_SMEM_GROUPS = 1024;           // group tables are staged in shared memory up to this many groups
+constexpr int CELL_THREADS = 512;
+constexpr int CELL_SMEM_GROUPS = 512;            // group tables are staged in shared memory up to this many groups
 
 struct CellView {
   int k;
@@ -38,6 +43,7 @@ struct CellView {
   const uint8_t *chrom_present;
   const int32_t *gsize;
   const uint32_t *gbase;
+  const int2 *gtab;                              // (gsize, gbase) interleaved, for genomes with many groups
   uint32_t n_cells, n_words;
   const uint32_t *bitmap, *wrank;
   const HotRec *hot;
@@ -65,127 +71,193 @@ __device__ __forceinline__ void red_add(ull *p, ull v) {
   asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ void load_hot(const HotRec *__restrict__ hot, uint32_t h, uint32_t (&w)[8]) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4 *>(hot + h));
-  const uint4 b = __ldg(reinterpret_cast<const uint4 *>(hot + h) + 1);
-  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-}
-__device__ __forceinline__ uint32_t hot_n(const uint32_t (&w)[8]) { return w[1] & 0xFFFFu; }
-__device__ __forceinline__ uint32_t hot_off(const uint32_t (&w)[8], int i) {      // off[i], i in [0,13)
-  const int h = i + 3;                                                            // halfword index inside the record
-  return (w[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu;
+// One endpoint (start or stop) of a deferred query: bump the cell's start/stop counter and, if the
+// cell is hot, the correction counter of every point at or beyond the coordinate.
+//   rec = the hot cell's 32-byte record (8 words), n = its point count (0 if the cell is cold).
+template <bool COVERAGE>
+__device__ __forceinline__ void endpoint_update(const CellView &cv, int64_t K, int cnt_plane, int sum_plane, int xcnt_plane,
+                                                int xsum_plane, uint32_t cell, uint32_t off, const uint4 &ra, const uint4 &rb,
+                                                uint32_t n, ull w, ull wx) {
+  red_add(cv.cells + (int64_t)cnt_plane * cv.n_cells + cell, w);
+  if (COVERAGE) red_add(cv.cells + (int64_t)sum_plane * cv.n_cells + cell, wx);
+  if (n == 0) return;
+  const uint32_t words[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+  const uint32_t sb = ra.x;
+#pragma unroll
+  for (int i = 0; i < HOT_MAX; i++) {                     // fully unrolled: the record stays in registers
+    const int h = i + 3;
+    const uint32_t po = (words[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu;
+    if ((uint32_t)i < n && off <= po) {
+      red_add(cv.corr + (int64_t)xcnt_plane * K + sb + i, w);
+      if (COVERAGE) red_add(cv.corr + (int64_t)xsum_plane * K + sb + i, wx);
+    }
+  }
 }
 
+// A deferred query: start and stop in different cells, or in a hot cell.
 template <bool COVERAGE>
-__device__ __forceinline__ void process_query(const CellView &cv, const RankView &rv, const uint32_t *__restrict__ s_bitmap,
-                                              const uint32_t *__restrict__ s_wrank, const int32_t *__restrict__ gsize,
-                                              const uint32_t *__restrict__ gbase, int32_t c, int32_t qs, int32_t qe, int strand,
-                                              int64_t w, int64_t index, int64_t K) {
-  if ((uint32_t)c >= (uint32_t)cv.n_chrom) return;                         // chromosome unknown to the index, :5719-5720
-  if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
-    if (cv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
-    return;
+__device__ __forceinline__ void careful_query(const CellView &cv, const RankView &rv, const uint32_t *__restrict__ s_bitmap,
+                                              const int2 *__restrict__ gtab, int32_t qs, int32_t qe, int g, int64_t w, int64_t K) {
+  const int2 gt = gtab[g];                                // (size, first cell)
+  const int32_t gs = gt.x;
+  const int32_t qe_c = qe < gs + 1 ? qe : gs + 1;
+  const uint32_t cs = (uint32_t)gt.y + ((uint32_t)qs >> cv.k), ce = (uint32_t)gt.y + ((uint32_t)qe_c >> cv.k);
+  const uint32_t word_s = s_bitmap[cs >> 5], word_e = s_bitmap[ce >> 5];
+  const bool hot_s = (word_s >> (cs & 31)) & 1u, hot_e = (word_e >> (ce & 31)) & 1u;
+  uint4 sa = make_uint4(0, 0, 0, 0), sb = sa, ea = sa, eb = sa;
+  if (hot_s) {
+    const uint32_t h = __ldg(cv.wrank + (cs >> 5)) + __popc(word_s & ((1u << (cs & 31)) - 1u));
+    sa = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h)); sb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h) + 1);
   }
-  const int cls = strand == '+' ? cv.cls_plus : (strand == '-' ? cv.cls_minus : (int)cv.class_of[(uint8_t)strand]);
-  if (cls < 0) return;                                                     // no index region carries this strand, :5229
-  const int g = c * cv.n_class + cls;
-  const int32_t gs = gsize[g];
-  if (gs <= 0) {                                                           // no point > 0 in the group
-    if (qs < 1 || gs < 0) {                                                // ... but there may be points <= 0: general step
-      const int gb = rv.goff[g], ge = rv.goff[g + 1];
-      if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
+  if (hot_e) {
+    if (ce == cs) { ea = sa; eb = sb; }
+    else {
+      const uint32_t h = __ldg(cv.wrank + (ce >> 5)) + __popc(word_e & ((1u << (ce & 31)) - 1u));
+      ea = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h)); eb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h) + 1);
     }
-    return;
   }
-  if (qs > gs) return;                                                     // beyond every evaluation point of the group
-  if (qs < 1) {                                                            // cells start at coordinate 0
+  const uint32_t ns = hot_s ? (sa.y & 0xFFFFu) : 0u, ne = hot_e ? (ea.y & 0xFFFFu) : 0u;
+  if (ns > (uint32_t)HOT_MAX || ne > (uint32_t)HOT_MAX) {                  // overfull cell: general step
     rank_item<COVERAGE>(rv, rv.goff[g], rv.goff[g + 1], qs, qe, w);
     return;
   }
+  endpoint_update<COVERAGE>(cv, K, C_SCNT, C_SSUM, X_SCNT, X_SSUM, cs, (uint32_t)qs & cv.cell_mask, sa, sb, ns, (ull)w, (ull)(w * (int64_t)qs));
+  endpoint_update<COVERAGE>(cv, K, C_ECNT, C_ESUM, X_ECNT, X_ESUM, ce, (uint32_t)qe_c & cv.cell_mask, ea, eb, ne, (ull)w, (ull)(w * (int64_t)qe));
+}
+
+// Front half, per query: the reference's admission checks, then either retire it (cold cell: one
+// reduction) or report that it must be deferred.  Returns true if the query is to be deferred.
+template <bool COVERAGE>
+__device__ __forceinline__ bool quick_query(const CellView &cv, const RankView &rv, const uint32_t *__restrict__ s_bitmap,
+                                            const int2 *__restrict__ gtab, int32_t c, int32_t qs, int32_t qe, int strand,
+                                            int64_t w, int64_t index, int &g_out) {
+  if ((uint32_t)c >= (uint32_t)cv.n_chrom) return false;                   // chromosome unknown to the index, :5719-5720
+  if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
+    if (cv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
+    return false;
+  }
+  const int cls = strand == '+' ? cv.cls_plus : (strand == '-' ? cv.cls_minus : (int)cv.class_of[(uint8_t)strand]);
+  if (cls < 0) return false;                                               // no index region carries this strand, :5229
+  const int g = c * cv.n_class + cls;
+  const int2 gt = gtab[g];
+  const int32_t gs = gt.x;
+  if (gs <= 0 || qs < 1) {                                                 // no point > 0 in the group, or start before the cells
+    const int gb = rv.goff[g], ge = rv.goff[g + 1];
+    if (ge > gb && (qs < 1 || gs < 0)) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
+    return false;
+  }
+  if (qs > gs) return false;                                               // beyond every evaluation point of the group
   const int32_t qe_c = qe < gs + 1 ? qe : gs + 1;                          // everything past the last point is one segment
-  const uint32_t base = gbase[g];
-  const uint32_t cs = base + ((uint32_t)qs >> cv.k), ce = base + ((uint32_t)qe_c >> cv.k);
-  const uint32_t word_s = s_bitmap[cs >> 5];
-  const bool hot_s = (word_s >> (cs & 31)) & 1u;
-  ull *cells = cv.cells;
-  const int64_t NC = cv.n_cells;
+  const uint32_t cs = (uint32_t)gt.y + ((uint32_t)qs >> cv.k), ce = (uint32_t)gt.y + ((uint32_t)qe_c >> cv.k);
+  const bool hot_s = (s_bitmap[cs >> 5] >> (cs & 31)) & 1u;
   if (cs == ce && !hot_s) {                                                // the common case: one cold cell
-    red_add(cells + C_BOTH * NC + cs, COVERAGE ? (ull)(w * ((int64_t)qe - qs + 1)) : (ull)w);
-    return;
+    red_add(cv.cells + cs, COVERAGE ? (ull)(w * ((int64_t)qe - qs + 1)) : (ull)w);      // plane C_BOTH == 0
+    return false;
   }
-  const uint32_t word_e = s_bitmap[ce >> 5];
-  const bool hot_e = (word_e >> (ce & 31)) & 1u;
-  uint32_t rec_s[8], rec_e[8];
-  if (hot_s) load_hot(cv.hot, s_wrank[cs >> 5] + __popc(word_s & ((1u << (cs & 31)) - 1u)), rec_s);
-  if (hot_e) load_hot(cv.hot, s_wrank[ce >> 5] + __popc(word_e & ((1u << (ce & 31)) - 1u)), rec_e);
-  if ((hot_s && hot_n(rec_s) > (uint32_t)HOT_MAX) || (hot_e && hot_n(rec_e) > (uint32_t)HOT_MAX)) {
-    rank_item<COVERAGE>(rv, rv.goff[g], rv.goff[g + 1], qs, qe, w);        // overfull cell: general step
-    return;
-  }
-  // start coordinate: counted for every point >= qs
-  red_add(cells + C_SCNT * NC + cs, (ull)w);
-  if (COVERAGE) red_add(cells + C_SSUM * NC + cs, (ull)(w * (int64_t)qs));
-  if (hot_s) {
-    const uint32_t o = (uint32_t)qs & cv.cell_mask, n = hot_n(rec_s), sb = rec_s[0];
-    for (uint32_t i = 0; i < n; i++)
-      if (o <= hot_off(rec_s, i)) {
-        red_add(cv.corr + X_SCNT * K + sb + i, (ull)w);
-        if (COVERAGE) red_add(cv.corr + X_SSUM * K + sb + i, (ull)(w * (int64_t)qs));
-      }
-  }
-  // stop coordinate: counted for every point >= qe
-  red_add(cells + C_ECNT * NC + ce, (ull)w);
-  if (COVERAGE) red_add(cells + C_ESUM * NC + ce, (ull)(w * (int64_t)qe));
-  if (hot_e) {
-    const uint32_t o = (uint32_t)qe_c & cv.cell_mask, n = hot_n(rec_e), sb = rec_e[0];
-    for (uint32_t i = 0; i < n; i++)
-      if (o <= hot_off(rec_e, i)) {
-        red_add(cv.corr + X_ECNT * K + sb + i, (ull)w);
-        if (COVERAGE) red_add(cv.corr + X_ESUM * K + sb + i, (ull)(w * (int64_t)qe));
-      }
-  }
+  g_out = g;
+  return true;
 }
 
 // VEC: 8 = 256-bit loads of chrom/start/stop (+ 64 bits of strand) per thread, 1 = scalar (unaligned batches)
 template <bool COVERAGE, bool WEIGHTED, int VEC>
 __global__ void __launch_bounds__(CELL_THREADS, 1) cell_accumulate_kernel(QueryView q, RankView rv, CellView cv) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *s_bitmap = smem;
-  uint32_t *s_wrank = smem + cv.n_words;
-  int32_t *s_gsize = reinterpret_cast<int32_t *>(smem + 2 * cv.n_words);
-  uint32_t *s_gbase = reinterpret_cast<uint32_t *>(s_gsize + CELL_SMEM_GROUPS);
-  for (uint32_t i = threadIdx.x; i < cv.n_words; i += blockDim.x) { s_bitmap[i] = cv.bitmap[i]; s_wrank[i] = cv.wrank[i]; }
+  int4 *s_queue = reinterpret_cast<int4 *>(smem);                                    // [CELL_QCAP] (qs, qe, group, weight)
+  int2 *s_gtab = reinterpret_cast<int2 *>(smem + 4 * CELL_QCAP);                     // [CELL_SMEM_GROUPS] (size, first cell)
+  uint32_t *s_bitmap = smem + 4 * CELL_QCAP + 2 * CELL_SMEM_GROUPS;                  // [n_words]
+  __shared__ unsigned s_qcount[2];
+  for (uint32_t i = threadIdx.x; i < cv.n_words; i += blockDim.x) s_bitmap[i] = cv.bitmap[i];
   const bool groups_in_smem = cv.n_groups <= CELL_SMEM_GROUPS;
   if (groups_in_smem)
-    for (int i = threadIdx.x; i < cv.n_groups; i += blockDim.x) { s_gsize[i] = cv.gsize[i]; s_gbase[i] = cv.gbase[i]; }
+    for (int i = threadIdx.x; i < cv.n_groups; i += blockDim.x) s_gtab[i] = make_int2(cv.gsize[i], (int)cv.gbase[i]);
+  if (threadIdx.x < 2) s_qcount[threadIdx.x] = 0;
   __syncthreads();
-  const int32_t *gsize = groups_in_smem ? s_gsize : cv.gsize;
-  const uint32_t *gbase = groups_in_smem ? s_gbase : cv.gbase;
+  const int2 *gtab = groups_in_smem ? s_gtab : cv.gtab;
   const int64_t K = rv.n_slots;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  constexpr int PER_THREAD = 8;
+  const int64_t tile_items = (int64_t)CELL_THREADS * PER_THREAD;
+  const int64_t n_tiles = (q.n_regions + tile_items - 1) / tile_items;
 
-  if (VEC == 8) {
-    const int64_t n8 = q.n_regions >> 3;
-    for (int64_t v = tid; v < n8; v += stride) {
-      const int8v c = ldg_stream256(q.chrom + (v << 3)), s = ldg_stream256(q.start + (v << 3)), e = ldg_stream256(q.stop + (v << 3));
-      const int2 st = ldg_stream64(reinterpret_cast<const int *>(q.strand + (v << 3)));
-      int8v w;
-      if (WEIGHTED) w = ldg_stream256(q.weight + (v << 3));
-      const int64_t idx = q.index_base + (v << 3);
+  // tile data lives in registers; the next tile's loads are issued before this tile is processed
+  int32_t c[PER_THREAD], s[PER_THREAD], e[PER_THREAD], wt[PER_THREAD], nc[PER_THREAD], ns[PER_THREAD], ne[PER_THREAD], nw[PER_THREAD];
+  int st[PER_THREAD];
+  int2 nst = make_int2(0, 0);
+  auto fetch = [&](int64_t tile) {
+    const int64_t first = tile * tile_items + (int64_t)threadIdx.x * PER_THREAD;
+    if (VEC == 8 && first + PER_THREAD <= q.n_regions) {
+      const int8v cc = ldg_stream256(q.chrom + first), ss = ldg_stream256(q.start + first), ee = ldg_stream256(q.stop + first);
+      nst = ldg_stream64(reinterpret_cast<const int *>(q.strand + first));
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int sw = i < 4 ? st.x : st.y;
-        process_query<COVERAGE>(cv, rv, s_bitmap, s_wrank, gsize, gbase, c.v[i], s.v[i], e.v[i],
-                                (int)(int8_t)((sw >> ((i & 3) * 8)) & 0xFF), WEIGHTED ? (int64_t)w.v[i] : 1, idx + i, K);
+      for (int i = 0; i < PER_THREAD; i++) { nc[i] = cc.v[i]; ns[i] = ss.v[i]; ne[i] = ee.v[i]; }
+      if (WEIGHTED) {
+        const int8v ww = ldg_stream256(q.weight + first);
+#pragma unroll
+        for (int i = 0; i < PER_THREAD; i++) nw[i] = ww.v[i];
+      }
+    } else {
+      unsigned sx = 0, sy = 0;
+#pragma unroll
+      for (int i = 0; i < PER_THREAD; i++) {
+        const int64_t r = first + i;
+        const bool ok = r < q.n_regions;
+        nc[i] = ok ? q.chrom[r] : -1; ns[i] = ok ? q.start[r] : 1; ne[i] = ok ? q.stop[r] : 1;
+        const unsigned sb = ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+';
+        if (i < 4) sx |= sb << (i * 8); else sy |= sb << ((i & 3) * 8);
+        if (WEIGHTED) nw[i] = ok ? q.weight[r] : 1;
+      }
+      nst = make_int2((int)sx, (int)sy);
+    }
+  };
+  if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+
+  for (int64_t tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, it++) {
+    const int64_t first = tile * tile_items + (int64_t)threadIdx.x * PER_THREAD;
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; i++) {
+      c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; wt[i] = WEIGHTED ? nw[i] : 1;
+      st[i] = (int)(int8_t)(((i < 4 ? nst.x : nst.y) >> ((i & 3) * 8)) & 0xFF);
+    }
+    if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+    // front half: retire cold queries, remember which ones must be deferred
+    unsigned pending = 0;
+    int grp[PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; i++) {
+      grp[i] = 0;
+      if (quick_query<COVERAGE>(cv, rv, s_bitmap, gtab, c[i], s[i], e[i], st[i], (int64_t)wt[i], q.index_base + first + i, grp[i]))
+        pending |= 1u << i;
+    }
+    // compact the deferred queries of this tile into the shared-memory queue
+    const int mine = __popc(pending);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned *qcount = &s_qcount[it & 1];
+    unsigned warp_base = 0;
+    if (warp_total > 0) {
+      if (lane == 31) warp_base = atomicAdd(qcount, (unsigned)warp_total);
+      warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+    }
+    unsigned slot = warp_base + (unsigned)(incl - mine);
+#pragma unroll
+    for (int i = 0; i < PER_THREAD; i++) {
+      if (pending & (1u << i)) {
+        if (slot < (unsigned)CELL_QCAP) s_queue[slot] = make_int4(s[i], e[i], grp[i], wt[i]);
+        else careful_query<COVERAGE>(cv, rv, s_bitmap, gtab, s[i], e[i], grp[i], (int64_t)wt[i], K);   // queue full: do it now
+        slot++;
       }
     }
-    for (int64_t r = (n8 << 3) + tid; r < q.n_regions; r += stride)
-      process_query<COVERAGE>(cv, rv, s_bitmap, s_wrank, gsize, gbase, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r],
-                              WEIGHTED ? (int64_t)q.weight[r] : 1, q.index_base + r, K);
-  } else {
-    for (int64_t r = tid; r < q.n_regions; r += stride)
-      process_query<COVERAGE>(cv, rv, s_bitmap, s_wrank, gsize, gbase, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r],
-                              WEIGHTED ? (int64_t)q.weight[r] : 1, q.index_base + r, K);
+    __syncthreads();
+    // back half: the queue, all lanes busy
+    const unsigned n_q = min(*qcount, (unsigned)CELL_QCAP);
+    for (unsigned j = threadIdx.x; j < n_q; j += blockDim.x) {
+      const int4 d = s_queue[j];
+      careful_query<COVERAGE>(cv, rv, s_bitmap, gtab, d.x, d.y, d.z, (int64_t)d.w, K);
+    }
+    if (threadIdx.x == 0) s_qcount[(it + 1) & 1] = 0;       // the other counter is idle until the next tile's appends
+    __syncthreads();
   }
 }
 
@@ -261,9 +333,14 @@ int gtb_cell_prepare(gtb_index *ix) {
   }
   cs->cell_planes = ix->op == GTB_OP_COVERAGE ? 5 : 3;
   cs->corr_planes = ix->op == GTB_OP_COVERAGE ? 4 : 2;
-  cs->smem_bytes = (size_t)cs->n_words * 8 + (size_t)CELL_SMEM_GROUPS * 8;
+  cs->smem_bytes = (size_t)CELL_QCAP * 16 + (size_t)CELL_SMEM_GROUPS * 8 + (size_t)cs->n_words * 4;
   GTB_TRY(upload_v(ctx, cs->d_gsize, gsize));
   GTB_TRY(upload_v(ctx, cs->d_gbase, gbase));
+  {
+    std::vector<int2> gtab((size_t)std::max(G, 1));
+    for (int g = 0; g < G; g++) gtab[g] = make_int2(gsize[g], (int)gbase[g]);
+    GTB_TRY(upload_v(ctx, cs->d_gtab, gtab));
+  }
   GTB_TRY(upload_v(ctx, cs->d_bitmap, bitmap));
   GTB_TRY(upload_v(ctx, cs->d_wrank, wrank));
   GTB_TRY(upload_v(ctx, cs->d_hot, hot));
@@ -311,7 +388,7 @@ int gtb_cell_accumulate(gtb_index *ix, const QueryView &q) {
   cv.n_chrom = ix->n_chrom; cv.n_class = ix->n_class; cv.n_groups = ix->n_groups;
   cv.cls_plus = ix->h_class_of[(uint8_t)'+']; cv.cls_minus = ix->h_class_of[(uint8_t)'-'];
   cv.class_of = ix->d_class_of.p; cv.chrom_present = ix->d_present.p;
-  cv.gsize = cs->d_gsize.p; cv.gbase = cs->d_gbase.p;
+  cv.gsize = cs->d_gsize.p; cv.gbase = cs->d_gbase.p; cv.gtab = cs->d_gtab.p;
   cv.n_cells = cs->n_cells; cv.n_words = cs->n_words;
   cv.bitmap = cs->d_bitmap.p; cv.wrank = cs->d_wrank.p; cv.hot = cs->d_hot.p;
   cv.cells = cs->d_cells.p; cv.corr = cs->d_corr.p;
@@ -323,7 +400,7 @@ int gtb_cell_accumulate(gtb_index *ix, const QueryView &q) {
                        ((uintptr_t)q.strand % 8 == 0) && (!q.weight || (uintptr_t)q.weight % 32 == 0);
   const bool cov = ix->op == GTB_OP_COVERAGE, wt = q.weight != nullptr;
   const size_t smem = cs->smem_bytes;
-  const int64_t per_block = (int64_t)CELL_THREADS * (aligned ? 8 : 1);
+  const int64_t per_block = (int64_t)CELL_THREADS * 8;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (q.n_regions + per_block - 1) / per_block));
 
 #define GTB_CELL_LAUNCH(COV, WT, VEC)                                                                                   \
@@ -364,7 +441,7 @@ int gtb_cell_scan_for_finish(gtb_index *ix, CellFinalView *out) {
 void gtb_cell_destroy(gtb_index *ix) {
   gtb_cell_state *cs = ix->cell;
   if (!cs) return;
-  cs->d_gsize.release(); cs->d_gbase.release(); cs->d_bitmap.release(); cs->d_wrank.release(); cs->d_hot.release();
+  cs->d_gsize.release(); cs->d_gbase.release(); cs->d_gtab.release(); cs->d_bitmap.release(); cs->d_wrank.release(); cs->d_hot.release();
   cs->d_slot_cell.release(); cs->d_cells.release(); cs->d_cells_scan.release(); cs->d_corr.release();
   delete cs;
   ix->cell = nullptr;

@@ -133,6 +133,7 @@ struct gtb_cell_state {
   size_t smem_bytes = 0;
   dbuf<int32_t> d_gsize;           // [n_groups] largest evaluation point of the group (0 = empty group)
   dbuf<uint32_t> d_gbase;          // [n_groups] first cell of the group
+  dbuf<int2> d_gtab;               // [n_groups] (gsize, gbase) interleaved
   dbuf<uint32_t> d_bitmap, d_wrank;   // [n_words]
   dbuf<HotRec> d_hot;              // [n_hot]
   dbuf<uint32_t> d_slot_cell;      // [n_slots] cell of each slot's point (0xFFFFFFFF: point <= 0 or sentinel)
