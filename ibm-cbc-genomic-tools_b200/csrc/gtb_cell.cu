@@ -17,9 +17,10 @@
 //   * finalisation turns the cell tables into prefix sums, so for an evaluation point p
 //       #{qs <= p} = sum(cells of the group before cell(p)) + correction[p]            (exactly).
 // Divergence: ~8 % of queries touch a hot cell, so nearly every warp would have a lane on the slow
-// branch.  The kernel therefore works tile by tile (4 096 queries per CTA): cold queries are
-// retired on the spot, the rest are compacted into a shared-memory queue (warp ballot + one
-// shared atomic per warp) and processed afterwards with all lanes busy.
+// branch.  The kernel therefore works tile by tile (4 096 queries per CTA): a branch-free front
+// half retires cold queries on the spot; the rest are compacted into a shared-memory queue (warp
+// scan + one shared atomic per warp) and processed with all lanes busy while the NEXT tile's front
+// half runs (two queue buffers, one barrier per tile).
 // Queries the scheme cannot place (start <= 0, a cell holding more than 13 points) take the
 // general rank step; results add up because every table is a sum over queries.
 #include "gtb_rank_device.cuh"
@@ -27,8 +28,8 @@
 
 namespace {
 
-constexpr uint32_t CELL_MAX_CELLS = 1638400;     // 51 200 bitmap words = 200 KB of shared memory
-constexpr int CELL_QCAP = 1024;                  // deferred-query queue entries (16 B each, 16 KB)
+constexpr uint32_t CELL_MAX_CELLS = 1572864;     // 49 152 bitmap words = 192 KB of shared memory
+constexpr int CELL_QCAP = 768;                   // deferred-query queue entries per buffer (2 buffers x 20 B)
 constexpr int CELL_MIN_K = 3;
 constexpr int CELL_MAX_K = 16;                   // point offsets inside a cell are stored in 16 bits
 constexpr int CELL_THREADS = 512;
@@ -72,8 +73,8 @@ __device__ __forceinline__ void red_add(ull *p, ull v) {
 }
 
 // One endpoint (start or stop) of a deferred query: bump the cell's start/stop counter and, if the
-// cell is hot, the correction counter of every point at or beyond the coordinate.
-//   rec = the hot cell's 32-byte record (8 words), n = its point count (0 if the cell is cold).
+// cell is hot, the correction counter of every point at or beyond the coordinate.  The cell's
+// points are sorted, so "at or beyond" is a suffix [f, n) of the record.
 template <bool COVERAGE>
 __device__ __forceinline__ void endpoint_update(const CellView &cv, int64_t K, int cnt_plane, int sum_plane, int xcnt_plane,
                                                 int xsum_plane, uint32_t cell, uint32_t off, const uint4 &ra, const uint4 &rb,
@@ -82,40 +83,52 @@ __device__ __forceinline__ void endpoint_update(const CellView &cv, int64_t K, i
   if (COVERAGE) red_add(cv.cells + (int64_t)sum_plane * cv.n_cells + cell, wx);
   if (n == 0) return;
   const uint32_t words[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-  const uint32_t sb = ra.x;
+  uint32_t f = 0;
 #pragma unroll
   for (int i = 0; i < HOT_MAX; i++) {                     // fully unrolled: the record stays in registers
     const int h = i + 3;
     const uint32_t po = (words[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu;
-    if ((uint32_t)i < n && off <= po) {
-      red_add(cv.corr + (int64_t)xcnt_plane * K + sb + i, w);
-      if (COVERAGE) red_add(cv.corr + (int64_t)xsum_plane * K + sb + i, wx);
-    }
+    f += ((uint32_t)i < n && po < off) ? 1u : 0u;
+  }
+  ull *xc = cv.corr + (int64_t)xcnt_plane * K + ra.x, *xs = cv.corr + (int64_t)xsum_plane * K + ra.x;
+  for (uint32_t i = f; i < n; i++) {
+    red_add(xc + i, w);
+    if (COVERAGE) red_add(xs + i, wx);
   }
 }
 
-// A deferred query: start and stop in different cells, or in a hot cell.
+// A deferred query (everything the branch-free front half did not retire): the reference's
+// admission checks, the general rank step for what cells cannot express, else the hot-cell path.
 template <bool COVERAGE>
-__device__ __forceinline__ void careful_query(const CellView &cv, const RankView &rv, const uint32_t *__restrict__ s_bitmap,
-                                              const int2 *__restrict__ gtab, int32_t qs, int32_t qe, int g, int64_t w, int64_t K) {
-  const int2 gt = gtab[g];                                // (size, first cell)
+__device__ __noinline__ void deferred_query(const CellView &cv, const RankView &rv, const uint32_t *s_bitmap, const int2 *gtab,
+                                            int32_t c, int32_t qs, int32_t qe, int strand, int64_t w, int64_t index) {
+  // (the front half only defers queries on chromosome ids the index knows)
+  if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
+    if (cv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
+    return;
+  }
+  const int cls = cv.class_of[(uint8_t)strand];
+  if (cls < 0) return;                                                     // no index region carries this strand, :5229
+  const int g = c * cv.n_class + cls;
+  const int2 gt = gtab[g];                                                 // (largest point, first cell)
   const int32_t gs = gt.x;
+  if (gs <= 0 || qs < 1) {                                                 // no point > 0 in the group, or start before the cells
+    const int gb = rv.goff[g], ge = rv.goff[g + 1];
+    if (ge > gb && (qs < 1 || gs < 0)) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
+    return;
+  }
+  if (qs > gs) return;
+  const int64_t K = rv.n_slots;
   const int32_t qe_c = qe < gs + 1 ? qe : gs + 1;
   const uint32_t cs = (uint32_t)gt.y + ((uint32_t)qs >> cv.k), ce = (uint32_t)gt.y + ((uint32_t)qe_c >> cv.k);
   const uint32_t word_s = s_bitmap[cs >> 5], word_e = s_bitmap[ce >> 5];
   const bool hot_s = (word_s >> (cs & 31)) & 1u, hot_e = (word_e >> (ce & 31)) & 1u;
   uint4 sa = make_uint4(0, 0, 0, 0), sb = sa, ea = sa, eb = sa;
-  if (hot_s) {
-    const uint32_t h = __ldg(cv.wrank + (cs >> 5)) + __popc(word_s & ((1u << (cs & 31)) - 1u));
-    sa = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h)); sb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h) + 1);
-  }
-  if (hot_e) {
-    if (ce == cs) { ea = sa; eb = sb; }
-    else {
-      const uint32_t h = __ldg(cv.wrank + (ce >> 5)) + __popc(word_e & ((1u << (ce & 31)) - 1u));
-      ea = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h)); eb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + h) + 1);
-    }
-  }
+  uint32_t hs = 0, he = 0;
+  if (hot_s) hs = __ldg(cv.wrank + (cs >> 5)) + __popc(word_s & ((1u << (cs & 31)) - 1u));
+  if (hot_e) he = __ldg(cv.wrank + (ce >> 5)) + __popc(word_e & ((1u << (ce & 31)) - 1u));
+  if (hot_s) { sa = __ldg(reinterpret_cast<const uint4 *>(cv.hot + hs)); sb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + hs) + 1); }
+  if (hot_e) { ea = __ldg(reinterpret_cast<const uint4 *>(cv.hot + he)); eb = __ldg(reinterpret_cast<const uint4 *>(cv.hot + he) + 1); }
   const uint32_t ns = hot_s ? (sa.y & 0xFFFFu) : 0u, ne = hot_e ? (ea.y & 0xFFFFu) : 0u;
   if (ns > (uint32_t)HOT_MAX || ne > (uint32_t)HOT_MAX) {                  // overfull cell: general step
     rank_item<COVERAGE>(rv, rv.goff[g], rv.goff[g + 1], qs, qe, w);
@@ -125,63 +138,30 @@ __device__ __forceinline__ void careful_query(const CellView &cv, const RankView
   endpoint_update<COVERAGE>(cv, K, C_ECNT, C_ESUM, X_ECNT, X_ESUM, ce, (uint32_t)qe_c & cv.cell_mask, ea, eb, ne, (ull)w, (ull)(w * (int64_t)qe));
 }
 
-// Front half, per query: the reference's admission checks, then either retire it (cold cell: one
-// reduction) or report that it must be deferred.  Returns true if the query is to be deferred.
-template <bool COVERAGE>
-__device__ __forceinline__ bool quick_query(const CellView &cv, const RankView &rv, const uint32_t *__restrict__ s_bitmap,
-                                            const int2 *__restrict__ gtab, int32_t c, int32_t qs, int32_t qe, int strand,
-                                            int64_t w, int64_t index, int &g_out) {
-  if ((uint32_t)c >= (uint32_t)cv.n_chrom) return false;                   // chromosome unknown to the index, :5719-5720
-  if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
-    if (cv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
-    return false;
-  }
-  const int cls = strand == '+' ? cv.cls_plus : (strand == '-' ? cv.cls_minus : (int)cv.class_of[(uint8_t)strand]);
-  if (cls < 0) return false;                                               // no index region carries this strand, :5229
-  const int g = c * cv.n_class + cls;
-  const int2 gt = gtab[g];
-  const int32_t gs = gt.x;
-  if (gs <= 0 || qs < 1) {                                                 // no point > 0 in the group, or start before the cells
-    const int gb = rv.goff[g], ge = rv.goff[g + 1];
-    if (ge > gb && (qs < 1 || gs < 0)) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
-    return false;
-  }
-  if (qs > gs) return false;                                               // beyond every evaluation point of the group
-  const int32_t qe_c = qe < gs + 1 ? qe : gs + 1;                          // everything past the last point is one segment
-  const uint32_t cs = (uint32_t)gt.y + ((uint32_t)qs >> cv.k), ce = (uint32_t)gt.y + ((uint32_t)qe_c >> cv.k);
-  const bool hot_s = (s_bitmap[cs >> 5] >> (cs & 31)) & 1u;
-  if (cs == ce && !hot_s) {                                                // the common case: one cold cell
-    red_add(cv.cells + cs, COVERAGE ? (ull)(w * ((int64_t)qe - qs + 1)) : (ull)w);      // plane C_BOTH == 0
-    return false;
-  }
-  g_out = g;
-  return true;
-}
-
 // VEC: 8 = 256-bit loads of chrom/start/stop (+ 64 bits of strand) per thread, 1 = scalar (unaligned batches)
 template <bool COVERAGE, bool WEIGHTED, int VEC>
 __global__ void __launch_bounds__(CELL_THREADS, 1) cell_accumulate_kernel(QueryView q, RankView rv, CellView cv) {
   extern __shared__ __align__(16) uint32_t smem[];
-  int4 *s_queue = reinterpret_cast<int4 *>(smem);                                    // [CELL_QCAP] (qs, qe, group, weight)
-  int2 *s_gtab = reinterpret_cast<int2 *>(smem + 4 * CELL_QCAP);                     // [CELL_SMEM_GROUPS] (size, first cell)
-  uint32_t *s_bitmap = smem + 4 * CELL_QCAP + 2 * CELL_SMEM_GROUPS;                  // [n_words]
-  __shared__ unsigned s_qcount[2];
+  int4 *s_queue = reinterpret_cast<int4 *>(smem);                                    // [2][CELL_QCAP] (qs, qe, chrom | strand << 24, weight)
+  uint32_t *s_qidx = smem + 8 * CELL_QCAP;                                           // [2][CELL_QCAP] index inside the batch
+  int2 *s_gtab = reinterpret_cast<int2 *>(smem + 10 * CELL_QCAP);                    // [CELL_SMEM_GROUPS] (largest point, first cell)
+  uint32_t *s_bitmap = smem + 10 * CELL_QCAP + 2 * CELL_SMEM_GROUPS;                 // [n_words]
+  __shared__ unsigned s_qcount[3];
   for (uint32_t i = threadIdx.x; i < cv.n_words; i += blockDim.x) s_bitmap[i] = cv.bitmap[i];
   const bool groups_in_smem = cv.n_groups <= CELL_SMEM_GROUPS;
   if (groups_in_smem)
-    for (int i = threadIdx.x; i < cv.n_groups; i += blockDim.x) s_gtab[i] = make_int2(cv.gsize[i], (int)cv.gbase[i]);
-  if (threadIdx.x < 2) s_qcount[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < cv.n_groups; i += blockDim.x) s_gtab[i] = cv.gtab[i];
+  if (threadIdx.x < 3) s_qcount[threadIdx.x] = 0;
   __syncthreads();
   const int2 *gtab = groups_in_smem ? s_gtab : cv.gtab;
-  const int64_t K = rv.n_slots;
   const int lane = threadIdx.x & 31;
   constexpr int PER_THREAD = 8;
   const int64_t tile_items = (int64_t)CELL_THREADS * PER_THREAD;
   const int64_t n_tiles = (q.n_regions + tile_items - 1) / tile_items;
+  const uint32_t last_cell = cv.n_cells - 1;
 
   // tile data lives in registers; the next tile's loads are issued before this tile is processed
-  int32_t c[PER_THREAD], s[PER_THREAD], e[PER_THREAD], wt[PER_THREAD], nc[PER_THREAD], ns[PER_THREAD], ne[PER_THREAD], nw[PER_THREAD];
-  int st[PER_THREAD];
+  int32_t nc[PER_THREAD], ns[PER_THREAD], ne[PER_THREAD], nw[PER_THREAD];
   int2 nst = make_int2(0, 0);
   auto fetch = [&](int64_t tile) {
     const int64_t first = tile * tile_items + (int64_t)threadIdx.x * PER_THREAD;
@@ -211,54 +191,80 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) cell_accumulate_kernel(QueryV
   };
   if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
 
-  for (int64_t tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, it++) {
+  // drains queue buffer `buf` whose fill count is in counter `cnt`
+  auto drain = [&](int buf, int cnt) {
+    const unsigned n_q = min(s_qcount[cnt], (unsigned)CELL_QCAP);
+    for (unsigned j = threadIdx.x; j < n_q; j += blockDim.x) {
+      const int4 d = s_queue[buf * CELL_QCAP + j];
+      deferred_query<COVERAGE>(cv, rv, s_bitmap, gtab, d.z & 0xFFFFFF, d.x, d.y, (int)(int8_t)((unsigned)d.z >> 24), (int64_t)d.w,
+                               q.index_base + s_qidx[buf * CELL_QCAP + j]);
+    }
+  };
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const int64_t first = tile * tile_items + (int64_t)threadIdx.x * PER_THREAD;
+    int32_t c[PER_THREAD], s[PER_THREAD], e[PER_THREAD], wt[PER_THREAD];
+    const int2 stw = nst;
 #pragma unroll
-    for (int i = 0; i < PER_THREAD; i++) {
-      c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; wt[i] = WEIGHTED ? nw[i] : 1;
-      st[i] = (int)(int8_t)(((i < 4 ? nst.x : nst.y) >> ((i & 3) * 8)) & 0xFF);
-    }
+    for (int i = 0; i < PER_THREAD; i++) { c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; wt[i] = WEIGHTED ? nw[i] : 1; }
     if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
-    // front half: retire cold queries, remember which ones must be deferred
+
+    // ---- front half: straight-line, predicated.  Retires queries that sit in one cold cell (one
+    // reduction) and those that provably contribute nothing; everything else is deferred.
     unsigned pending = 0;
-    int grp[PER_THREAD];
 #pragma unroll
     for (int i = 0; i < PER_THREAD; i++) {
-      grp[i] = 0;
-      if (quick_query<COVERAGE>(cv, rv, s_bitmap, gtab, c[i], s[i], e[i], st[i], (int64_t)wt[i], q.index_base + first + i, grp[i]))
-        pending |= 1u << i;
+      const int strand = ((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF;
+      const bool known = (uint32_t)c[i] < (uint32_t)cv.n_chrom && (uint32_t)c[i] < 0x1000000u;   // else: no match, no checks (:5719)
+      const int cls = strand == '+' ? cv.cls_plus : (strand == '-' ? cv.cls_minus : -1);
+      const bool plain = known && cls >= 0 && s[i] >= 1 && s[i] <= e[i];
+      const int2 gt = gtab[plain ? c[i] * cv.n_class + cls : 0];
+      const bool in_cells = plain && gt.x > 0;
+      const bool beyond = in_cells && s[i] > gt.x;                        // past every evaluation point: contributes nothing
+      const int32_t qe_c = min(e[i], gt.x + 1);
+      const uint32_t cs = min((uint32_t)gt.y + ((uint32_t)s[i] >> cv.k), last_cell);
+      const uint32_t ce = (uint32_t)gt.y + ((uint32_t)qe_c >> cv.k);
+      const bool hot_s = (s_bitmap[cs >> 5] >> (cs & 31)) & 1u;
+      const bool cold = in_cells && !beyond && cs == ce && !hot_s;
+      if (cold) red_add(cv.cells + cs, COVERAGE ? (ull)((int64_t)wt[i] * ((int64_t)e[i] - s[i] + 1)) : (ull)(int64_t)wt[i]);   // plane C_BOTH
+      // defer: hot or straddling cells, odd strand bytes, start <= 0, invalid intervals, point-free groups
+      const bool skip = !known || cold || beyond || (plain && gt.x == 0) ||                  // empty group: nothing to count
+                        (known && (strand == '+' || strand == '-') && cls < 0 && s[i] <= e[i] && e[i] > 0);
+      if (!skip) pending |= 1u << i;
     }
-    // compact the deferred queries of this tile into the shared-memory queue
+    // ---- compact this tile's deferred queries into queue buffer it&1
     const int mine = __popc(pending);
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned *qcount = &s_qcount[it & 1];
     unsigned warp_base = 0;
     if (warp_total > 0) {
-      if (lane == 31) warp_base = atomicAdd(qcount, (unsigned)warp_total);
+      if (lane == 31) warp_base = atomicAdd(&s_qcount[it % 3], (unsigned)warp_total);
       warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
     }
     unsigned slot = warp_base + (unsigned)(incl - mine);
+    const int buf = it & 1;
 #pragma unroll
     for (int i = 0; i < PER_THREAD; i++) {
       if (pending & (1u << i)) {
-        if (slot < (unsigned)CELL_QCAP) s_queue[slot] = make_int4(s[i], e[i], grp[i], wt[i]);
-        else careful_query<COVERAGE>(cv, rv, s_bitmap, gtab, s[i], e[i], grp[i], (int64_t)wt[i], K);   // queue full: do it now
+        const int strand = ((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF;
+        if (slot < (unsigned)CELL_QCAP) {
+          s_queue[buf * CELL_QCAP + slot] = make_int4(s[i], e[i], c[i] | (strand << 24), wt[i]);
+          s_qidx[buf * CELL_QCAP + slot] = (uint32_t)(first + i);
+        } else {                                                          // queue full: do it now
+          deferred_query<COVERAGE>(cv, rv, s_bitmap, gtab, c[i], s[i], e[i], (int)(int8_t)strand, (int64_t)wt[i], q.index_base + first + i);
+        }
         slot++;
       }
     }
-    __syncthreads();
-    // back half: the queue, all lanes busy
-    const unsigned n_q = min(*qcount, (unsigned)CELL_QCAP);
-    for (unsigned j = threadIdx.x; j < n_q; j += blockDim.x) {
-      const int4 d = s_queue[j];
-      careful_query<COVERAGE>(cv, rv, s_bitmap, gtab, d.x, d.y, d.z, (int64_t)d.w, K);
-    }
-    if (threadIdx.x == 0) s_qcount[(it + 1) & 1] = 0;       // the other counter is idle until the next tile's appends
+    // ---- back half of the PREVIOUS tile (its queue was completed by the barrier below), all lanes busy
+    if (it > 0) drain(buf ^ 1, (it + 2) % 3);
+    if (threadIdx.x == 0) s_qcount[(it + 1) % 3] = 0;      // drained during the previous iteration; next tile appends here
     __syncthreads();
   }
+  if (it > 0) drain((it - 1) & 1, (it + 2) % 3);
 }
 
 template <typename T>
@@ -333,7 +339,7 @@ int gtb_cell_prepare(gtb_index *ix) {
   }
   cs->cell_planes = ix->op == GTB_OP_COVERAGE ? 5 : 3;
   cs->corr_planes = ix->op == GTB_OP_COVERAGE ? 4 : 2;
-  cs->smem_bytes = (size_t)CELL_QCAP * 16 + (size_t)CELL_SMEM_GROUPS * 8 + (size_t)cs->n_words * 4;
+  cs->smem_bytes = (size_t)CELL_QCAP * 40 + (size_t)CELL_SMEM_GROUPS * 8 + (size_t)cs->n_words * 4;
   GTB_TRY(upload_v(ctx, cs->d_gsize, gsize));
   GTB_TRY(upload_v(ctx, cs->d_gbase, gbase));
   {
@@ -358,7 +364,7 @@ int gtb_cell_prepare(gtb_index *ix) {
 
 bool gtb_cell_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
   if (batch_multi || q.region_offset) return false;                  // single-interval batches only
-  if (ix->n_slots == 0) return false;
+  if (ix->n_slots == 0 || ix->n_chrom > (1 << 24) || q.n_regions >= ((int64_t)1 << 32)) return false;
   if (ix->cell && !ix->cell->ready) return false;                    // a previous prepare said "unsupported"
   if (!ix->cell) {
     int rc = gtb_cell_prepare(ix);
