@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU (default: the BASELINE config)")
-    ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "enumerate"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "bucket", "enumerate"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -177,7 +177,7 @@ def main():
     ctx = gtb200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "cell": gtb200.ENGINE_CELL, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
+    engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "cell": gtb200.ENGINE_CELL, "bucket": gtb200.ENGINE_BUCKET, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
     index = gtb200.Index(ctx, regions, gtb200.OP_COUNT, engine)
 
     dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),

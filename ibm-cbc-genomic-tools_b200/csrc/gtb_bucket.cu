@@ -1,0 +1,618 @@
+// gtb_bucket.cu -- BUCKET engine: partition the queries by genome bucket, then rank them against the
+// bucket's evaluation points entirely in shared memory.
+//
+// Why (measured on B200, profiles/microbench/red_rate_b200.txt): a random-address red.global costs
+// ~1.47 SM-cycles per element (1.9e11/s chip-wide, the same for u32 and u64) whereas a random
+// shared-memory atomicAdd costs ~0.18.  One global reduction per query therefore caps any
+// single-pass design at ~2e11 queries/s before any other work; counting in shared memory does not.
+// Shared memory cannot hold the evaluation points of a whole genome, so the queries are first
+// bucketed by position:
+//
+//   pass 1  bucket_partition_kernel   13 B/query in, 4 B/query out
+//       The groups' coordinate axes are laid end to end into one axis u (cells of 2^k bp only serve
+//       as alignment / directory granularity).  A bucket is 2^ub consecutive u (ub <= 24).  A query
+//       becomes one 32-bit element  (u_start - bucket_start) | length << ub.  Per tile of 4 096
+//       queries: rank inside the bucket with ONE shared-memory atomicAdd per query, exclusive scan
+//       of the bucket counts, scatter into a shared staging buffer, copy out in bucket order so the
+//       global stores are runs.  Bucket storage is paged (4 096-element pages from a pool, page
+//       table per bucket) so memory is exact whatever the skew; a tile reserves its slice of each
+//       bucket with one global atomicAdd per non-empty bucket.
+//   pass 2  bucket_count_kernel       4 B/query in
+//       Work units of 65 536 elements; a CTA walks a contiguous range of units.  Per bucket it
+//       loads the bucket's evaluation points (bucket-local u) and a per-cell directory into shared
+//       memory, then for every element: directory lookup + a short forward scan give the slots of
+//       start and stop, and the slot histograms (the RANK engine's both / S / E planes) take
+//       shared-memory atomics.  Histograms are flushed to the global planes with a reduction per
+//       non-zero slot when the CTA moves to another bucket.
+//
+// What cannot be expressed in an element (start <= 0, length >= 2^(32-ub), a query that crosses the
+// end of its bucket, strand bytes other than '+'/'-', invalid intervals) takes the general rank
+// step inline in pass 1.  Finalisation is the RANK engine's.
+#include "gtb_rank_device.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int PART_THREADS = 512;
+constexpr int PART_ITEMS = 8;
+constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4 096 queries
+constexpr int PAGE_SHIFT = 12;
+constexpr uint32_t PAGE = 1u << PAGE_SHIFT;               // elements per page (== PART_TILE: a tile's slice spans <= 2 pages)
+constexpr int UNIT_PAGES = 16;                            // pass-2 work unit = 65 536 elements
+constexpr int MAX_BUCKETS = 2048;
+constexpr int SMEM_GROUPS = 512;
+constexpr int COUNT_THREADS = 512;
+constexpr size_t COUNT_SMEM_BUDGET = 200 * 1024;
+
+struct BucketView {
+  int k, ub;                        // cell = 2^k bp, bucket = 2^ub u
+  int32_t n_chrom, n_class, n_groups;
+  int cls_plus, cls_minus;
+  const int8_t *class_of;
+  const uint8_t *chrom_present;
+  const int2 *gtab;                 // per group: (largest point, first cell)
+  uint32_t n_buckets;
+  // paged bucket storage
+  uint32_t *pool;                   // pages of PAGE elements
+  uint32_t *page_table;             // [n_buckets * pt_stride]  page id + 1, 0 = not allocated yet
+  uint32_t pt_stride;
+  uint32_t *cursor;                 // [n_buckets] elements appended so far
+  uint32_t *next_page;
+  // pass 2
+  const int32_t *j0;                // [n_buckets + 1] first slot of each bucket
+  const uint32_t *slot_lu;          // [n_slots] bucket-local u of each slot
+  const ull *slot_u0;               // [n_slots] u of coordinate 0 of the slot's group
+  const uint16_t *dir;              // [n_buckets << (ub - k)] first local slot at or after the cell start
+  uint32_t *unit_off;               // [n_buckets + 1]
+  int max_local;                    // largest number of slots in a bucket (excluding the catch-all)
+};
+
+struct int8v { int v[8]; };
+__device__ __forceinline__ int8v ldg_stream256(const int *p) {
+  int8v r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int2 ldg_stream64(const int *p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_add64(ull *p, ull v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The rare queries an element cannot describe: admission checks of the reference, then the general
+// rank step (binary search in global memory).
+template <bool COVERAGE>
+__device__ __noinline__ void special_query(const BucketView &bv, const RankView &rv, int32_t c, int32_t qs, int32_t qe, int strand,
+                                           int64_t w, int64_t index) {
+  if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
+    if (bv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
+    return;
+  }
+  const int cls = bv.class_of[(uint8_t)strand];
+  if (cls < 0) return;                                                     // no index region carries this strand, :5229
+  const int g = c * bv.n_class + cls;
+  const int gb = rv.goff[g], ge = rv.goff[g + 1];
+  if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------------
+template <bool COVERAGE, int VEC>
+__global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *s_stage = smem;                                           // [PART_TILE] elements in bucket order
+  uint16_t *s_bid = reinterpret_cast<uint16_t *>(smem + PART_TILE);   // [PART_TILE] bucket of each staged element
+  int2 *s_gtab = reinterpret_cast<int2 *>(smem + PART_TILE + PART_TILE / 2);            // [SMEM_GROUPS]
+  uint32_t *s_cnt = smem + PART_TILE + PART_TILE / 2 + 2 * SMEM_GROUPS;                 // [nb4] per-bucket counts of this tile
+  const uint32_t nb4 = (bv.n_buckets + 3) & ~3u;
+  uint32_t *s_off = s_cnt + nb4;                                      // [nb4] exclusive scan of s_cnt
+  uint32_t *s_g0 = s_off + nb4;                                       // [nb4] global element address of the slice's first part
+  uint32_t *s_g1 = s_g0 + nb4;                                        // [nb4] ... of the part that spilled into the next page
+  uint32_t *s_split = s_g1 + nb4;                                     // [nb4] elements in the first part
+  __shared__ uint32_t s_warp_tot[PART_THREADS / 32];
+
+  const bool groups_in_smem = bv.n_groups <= SMEM_GROUPS;
+  if (groups_in_smem)
+    for (int i = threadIdx.x; i < bv.n_groups; i += blockDim.x) s_gtab[i] = bv.gtab[i];
+  for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int2 *gtab = groups_in_smem ? s_gtab : bv.gtab;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
+  const uint32_t kmask = (1u << bv.k) - 1u, ubmask = (1u << bv.ub) - 1u;
+  const int cb = bv.ub - bv.k;                                         // cell bits inside a bucket
+  const uint32_t len_max = bv.ub >= 32 ? 0u : (0xFFFFFFFFu >> bv.ub);
+
+  int32_t nc[PART_ITEMS], ns[PART_ITEMS], ne[PART_ITEMS];
+  int2 nst = make_int2(0, 0);
+  auto fetch = [&](int64_t tile) {
+    const int64_t first = tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS;
+    if (VEC == 8 && first + PART_ITEMS <= q.n_regions) {
+      const int8v cc = ldg_stream256(q.chrom + first), ss = ldg_stream256(q.start + first), ee = ldg_stream256(q.stop + first);
+      nst = ldg_stream64(reinterpret_cast<const int *>(q.strand + first));
+#pragma unroll
+      for (int i = 0; i < PART_ITEMS; i++) { nc[i] = cc.v[i]; ns[i] = ss.v[i]; ne[i] = ee.v[i]; }
+    } else {
+      unsigned sx = 0, sy = 0;
+#pragma unroll
+      for (int i = 0; i < PART_ITEMS; i++) {
+        const int64_t r = first + i;
+        const bool ok = r < q.n_regions;
+        nc[i] = ok ? q.chrom[r] : -1; ns[i] = ok ? q.start[r] : 1; ne[i] = ok ? q.stop[r] : 1;
+        const unsigned sb = ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+';
+        if (i < 4) sx |= sb << (i * 8); else sy |= sb << ((i & 3) * 8);
+      }
+      nst = make_int2((int)sx, (int)sy);
+    }
+  };
+  if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t first = tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS;
+    int32_t c[PART_ITEMS], s[PART_ITEMS], e[PART_ITEMS];
+    const int2 stw = nst;
+#pragma unroll
+    for (int i = 0; i < PART_ITEMS; i++) { c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; }
+    if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+
+    // ---- classify, build the element, rank inside the bucket (one shared atomic per query)
+    uint32_t elem[PART_ITEMS], bkt[PART_ITEMS], rnk[PART_ITEMS];
+    unsigned special = 0;
+#pragma unroll
+    for (int i = 0; i < PART_ITEMS; i++) {
+      const int strand = ((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF;
+      const int known = (uint32_t)c[i] < (uint32_t)bv.n_chrom;                    // else: no match, no checks (:5719)
+      const int is_pm = (strand == '+') | (strand == '-');
+      const int cls = strand == '+' ? bv.cls_plus : (strand == '-' ? bv.cls_minus : -1);
+      const int valid = (s[i] <= e[i]) & (e[i] > 0);
+      const int plain = known & (cls >= 0) & (s[i] >= 1) & valid;
+      const int2 gt = gtab[plain ? c[i] * bv.n_class + cls : 0];
+      const int in_cells = plain & (gt.x > 0);
+      const int beyond = in_cells & (s[i] > gt.x);                                // past every evaluation point: nothing to count
+      const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
+      const uint32_t cell = (uint32_t)gt.y + ((uint32_t)s[i] >> bv.k);
+      const uint32_t lu = ((cell & ((1u << cb) - 1u)) << bv.k) | ((uint32_t)s[i] & kmask);
+      const int fits = (len <= len_max) & (lu + len <= ubmask);
+      const int normal = in_cells & !beyond & fits;
+      // nothing to do: unknown chromosome, beyond the last point, empty group, or a '+'/'-' strand no index region carries
+      const int nothing = !known | beyond | (plain & (gt.x == 0)) | (known & is_pm & (cls < 0) & valid);
+      special |= (unsigned)(!normal & !nothing) << i;
+      bkt[i] = normal ? (cell >> cb) : 0xFFFFFFFFu;
+      elem[i] = lu | (len << bv.ub);
+      rnk[i] = 0;
+      if (normal) rnk[i] = atomicAdd(&s_cnt[bkt[i]], 1u);
+    }
+    if (special) {
+#pragma unroll
+      for (int i = 0; i < PART_ITEMS; i++)
+        if (special & (1u << i))
+          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)(((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF), 1, q.index_base + first + i);
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the bucket counts (4 counters per thread), reserve global space
+    {
+      uint32_t v[4] = {0, 0, 0, 0}, sum = 0;
+      const uint32_t b0 = threadIdx.x * 4;
+      if (b0 < nb4) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(s_cnt + b0);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; sum = t.x + t.y + t.z + t.w;
+      }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+      if (lane == 31) s_warp_tot[warp] = inc;
+      // reserve: one global atomic per non-empty bucket; allocate the pages whose first element is ours
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t b = b0 + j;
+        if (b < bv.n_buckets && v[j] > 0) {
+          const uint32_t old = atomicAdd(bv.cursor + b, v[j]);
+          const uint32_t p_first = old >> PAGE_SHIFT, p_last = (old + v[j] - 1) >> PAGE_SHIFT;
+          uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
+          if ((old & (PAGE - 1)) == 0) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_first, pid + 1); }
+          if (p_last != p_first) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_last, pid + 1); }
+          uint32_t id0, id1;
+          while ((id0 = ld_volatile_u32(pt + p_first)) == 0) {}
+          id1 = id0;
+          if (p_last != p_first) while ((id1 = ld_volatile_u32(pt + p_last)) == 0) {}
+          s_g0[b] = ((id0 - 1) << PAGE_SHIFT) + (old & (PAGE - 1));
+          s_g1[b] = (id1 - 1) << PAGE_SHIFT;
+          s_split[b] = min(v[j], PAGE - (old & (PAGE - 1)));
+        }
+      }
+      __syncthreads();
+      uint32_t base = inc - sum;
+      for (int w = 0; w < warp; w++) base += s_warp_tot[w];
+      if (b0 < nb4) {
+        uint4 o;
+        o.x = base; o.y = base + v[0]; o.z = o.y + v[1]; o.w = o.z + v[2];
+        *reinterpret_cast<uint4 *>(s_off + b0) = o;
+      }
+    }
+    __syncthreads();
+
+    // ---- scatter into the staging buffer in bucket order
+#pragma unroll
+    for (int i = 0; i < PART_ITEMS; i++) {
+      if (bkt[i] != 0xFFFFFFFFu) {
+        const uint32_t p = s_off[bkt[i]] + rnk[i];
+        s_stage[p] = elem[i];
+        s_bid[p] = (uint16_t)bkt[i];
+      }
+    }
+    __syncthreads();
+
+    // ---- copy out: consecutive staged elements of a bucket go to consecutive addresses
+    const uint32_t total = s_off[nb4 - 1] + s_cnt[nb4 - 1];
+    for (uint32_t p = threadIdx.x; p < total; p += PART_THREADS) {
+      const uint32_t b = s_bid[p];
+      const uint32_t r = p - s_off[b];
+      const uint32_t sp = s_split[b];
+      const uint32_t addr = r < sp ? s_g0[b] + r : s_g1[b] + (r - sp);
+      bv.pool[addr] = s_stage[p];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// between the passes: work units per bucket (exclusive scan of ceil(count / unit size))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
+  __shared__ uint32_t s_tot[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < bv.n_buckets; base += blockDim.x) {
+    const uint32_t b = base + threadIdx.x;
+    const uint32_t u = b < bv.n_buckets ? (bv.cursor[b] + (PAGE * UNIT_PAGES) - 1) / (PAGE * UNIT_PAGES) : 0;
+    uint32_t inc = u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_tot[warp] = inc;
+    __syncthreads();
+    uint32_t pre = carry;
+    for (int w = 0; w < warp; w++) pre += s_tot[w];
+    if (b < bv.n_buckets) bv.unit_off[b] = pre + inc - u;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = pre + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bv.unit_off[bv.n_buckets] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2
+// ------------------------------------------------------------------------------------------------
+template <bool COVERAGE>
+__global__ void __launch_bounds__(COUNT_THREADS, 1) bucket_count_kernel(BucketView bv, RankView rv) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int cb = bv.ub - bv.k;
+  const uint32_t n_dir = 1u << cb;
+  uint16_t *s_dir = reinterpret_cast<uint16_t *>(smem);                       // [n_dir]
+  uint32_t *s_pts = smem + ((n_dir / 2 + 1) & ~1u);                           // [max_local + 1], last = +inf (even word offset)
+  const uint32_t cap = (uint32_t)bv.max_local + 1;
+  // histogram planes: count -> 3 planes of u32 ; coverage -> 5 planes of u64
+  uint32_t *s_h32 = s_pts + ((cap + 1) & ~1u);
+  ull *s_h64 = reinterpret_cast<ull *>(s_h32);
+
+  const uint32_t total_units = bv.unit_off[bv.n_buckets];
+  const uint32_t u_begin = (uint32_t)(((ull)total_units * blockIdx.x) / gridDim.x);
+  const uint32_t u_end = (uint32_t)(((ull)total_units * (blockIdx.x + 1)) / gridDim.x);
+  if (u_begin >= u_end) return;
+  const uint32_t kmaskless = bv.k;
+  const uint32_t ubmask = (1u << bv.ub) - 1u;
+  const int64_t K = rv.n_slots;
+
+  // bucket of the first unit: last b with unit_off[b] <= u_begin
+  uint32_t b;
+  {
+    uint32_t lo = 0, hi = bv.n_buckets;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (bv.unit_off[mid] <= u_begin) lo = mid; else hi = mid; }
+    b = lo;
+    while (b + 1 < bv.n_buckets && bv.unit_off[b + 1] <= u_begin) b++;      // skip empty buckets sharing the offset
+  }
+  int loaded = -1;
+  uint32_t n_local = 0;
+  int32_t slot0 = 0;
+
+  auto flush = [&]() {
+    if (loaded < 0) return;
+    const ull bucket_u = (ull)(uint32_t)loaded << bv.ub;
+    for (uint32_t j = threadIdx.x; j <= n_local; j += blockDim.x) {
+      const int64_t J = (int64_t)slot0 + j;
+      if (J >= K) continue;
+      if (!COVERAGE) {
+        const uint32_t vb = s_h32[j], vs = s_h32[cap + j], ve = s_h32[2 * cap + j];
+        if (vb) red_add64(rv.hist + H_BOTH * K + J, vb);
+        if (vs) red_add64(rv.hist + H_SCNT * K + J, vs);
+        if (ve) red_add64(rv.hist + H_ECNT * K + J, ve);
+      } else {
+        const ull vb = s_h64[j], vs = s_h64[cap + j], ve = s_h64[2 * cap + j], ss = s_h64[3 * cap + j], se = s_h64[4 * cap + j];
+        const ull shift = bucket_u - bv.slot_u0[J];                     // bucket-local u -> coordinate inside the slot's group
+        if (vb) red_add64(rv.hist + H_BOTH * K + J, vb);
+        if (vs) { red_add64(rv.hist + H_SCNT * K + J, vs); red_add64(rv.hist + H_SSUM * K + J, ss + vs * shift); }
+        if (ve) { red_add64(rv.hist + H_ECNT * K + J, ve); red_add64(rv.hist + H_ESUM * K + J, se + ve * shift); }
+      }
+    }
+  };
+  auto load_bucket = [&](uint32_t nb) {
+    __syncthreads();
+    flush();
+    __syncthreads();
+    loaded = (int)nb;
+    slot0 = bv.j0[nb];
+    n_local = (uint32_t)(bv.j0[nb + 1] - slot0);
+    const uint16_t *gdir = bv.dir + ((size_t)nb << cb);
+    for (uint32_t i = threadIdx.x; i < n_dir; i += blockDim.x) s_dir[i] = gdir[i];
+    for (uint32_t i = threadIdx.x; i < n_local; i += blockDim.x) s_pts[i] = bv.slot_lu[slot0 + i];
+    if (threadIdx.x == 0) s_pts[n_local] = 0xFFFFFFFFu;
+    const uint32_t words = COVERAGE ? 5 * cap * 2 : 3 * cap;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s_h32[i] = 0;
+    __syncthreads();
+  };
+
+  for (uint32_t u = u_begin; u < u_end; u++) {
+    while (b + 1 < bv.n_buckets && bv.unit_off[b + 1] <= u) b++;
+    if ((int)b != loaded) load_bucket(b);
+    const uint32_t part = u - bv.unit_off[b];
+    const uint32_t cnt = bv.cursor[b];
+    const uint32_t e_begin = part * (PAGE * UNIT_PAGES), e_end = min(cnt, e_begin + PAGE * UNIT_PAGES);
+    const uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
+    const uint32_t n_el = e_end - e_begin;                               // elements of this unit (e_begin is page aligned)
+    const uint32_t n_v4 = (n_el + 3) >> 2;
+    constexpr int UNROLL = 4;
+    for (uint32_t base = 0; base < n_v4; base += COUNT_THREADS * UNROLL) {
+      uint4 d[UNROLL];
+#pragma unroll
+      for (int r = 0; r < UNROLL; r++) {
+        const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
+        d[r] = make_uint4(0, 0, 0, 0);
+        if (v4 < n_v4) {
+          const uint32_t pg = (e_begin >> PAGE_SHIFT) + (v4 >> (PAGE_SHIFT - 2));
+          const uint32_t page_id = __ldg(pt + pg) - 1;
+          d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + ((size_t)page_id << PAGE_SHIFT)) + (v4 & ((PAGE >> 2) - 1)));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < UNROLL; r++) {
+        const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
+        const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (v4 * 4 + i >= n_el) break;
+          const uint32_t us = el[i] & ubmask, len = el[i] >> bv.ub, ue = us + len;
+          uint32_t jS = s_dir[us >> kmaskless];
+          while (s_pts[jS] < us) jS++;
+          uint32_t jE = jS;
+          while (s_pts[jE] < ue) jE++;
+          if (!COVERAGE) {
+            if (jS == jE) atomicAdd(&s_h32[jS], 1u);
+            else { atomicAdd(&s_h32[cap + jS], 1u); atomicAdd(&s_h32[2 * cap + jE], 1u); }
+          } else {
+            if (jS == jE) atomicAdd(&s_h64[jS], (ull)len + 1ull);
+            else {
+              atomicAdd(&s_h64[cap + jS], 1ull); atomicAdd(&s_h64[2 * cap + jE], 1ull);
+              atomicAdd(&s_h64[3 * cap + jS], (ull)us); atomicAdd(&s_h64[4 * cap + jE], (ull)ue);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  flush();
+}
+
+template <typename T>
+int upload_b(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
+  GTB_TRY(d.reserve(ctx, h.size() ? h.size() : 1));
+  if (h.size()) GTB_CUDA_OK(ctx, cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return GTB_OK;
+}
+
+}  // namespace
+
+struct gtb_bucket_state {
+  bool ready = false, failed = false;
+  int k = 0, ub = 0;
+  uint32_t n_buckets = 0;
+  int max_local = 0;
+  size_t count_smem = 0, part_smem = 0;
+  dbuf<int2> d_gtab;
+  dbuf<int32_t> d_j0;
+  dbuf<uint32_t> d_slot_lu;
+  dbuf<ull> d_slot_u0;
+  dbuf<uint16_t> d_dir;
+  dbuf<uint32_t> d_pool, d_page_table, d_cursor, d_next_page, d_unit_off;
+};
+
+static size_t count_smem_bytes(int ub, int k, int max_local, bool coverage) {
+  const size_t n_dir = (size_t)1 << (ub - k);
+  const size_t cap = (size_t)max_local + 1;
+  return n_dir * 2 + 8 + ((cap + 1) & ~(size_t)1) * 4 + (coverage ? 5 * cap * 8 : 3 * cap * 4) + 16;
+}
+
+int gtb_bucket_prepare(gtb_index *ix) {
+  if (ix->bucket && (ix->bucket->ready || ix->bucket->failed)) return ix->bucket->ready ? GTB_OK : GTB_ERR_UNSUPPORTED;
+  gtb_ctx *ctx = ix->ctx;
+  if (!ix->bucket) ix->bucket = new gtb_bucket_state();
+  gtb_bucket_state *bs = ix->bucket;
+  bs->failed = true;                                                    // until proven otherwise
+  const int G = ix->n_groups;
+  if (ix->n_slots == 0) return GTB_ERR_UNSUPPORTED;
+  std::vector<int32_t> gsize((size_t)std::max(G, 1), 0);
+  uint64_t span = 0, n_points = 0;
+  for (int g = 0; g < G; g++) {
+    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1];
+    if (ge - gb >= 2) { const int32_t mx = ix->h_points[ge - 2]; gsize[g] = mx >= 1 ? mx : -1; n_points += (uint64_t)(ge - gb - 1); }
+    if (gsize[g] > 0) span += (uint64_t)gsize[g] + 2;
+  }
+  if (span == 0) return GTB_ERR_UNSUPPORTED;
+  // cell width: about half an evaluation point per cell, so the forward scan in pass 2 is ~0 steps
+  int k = 4;
+  while (k < 14 && (span >> (k + 1)) >= 2 * n_points) k++;
+  if (const char *env = getenv("GTB_BUCKET_K")) k = std::max(0, std::min(16, atoi(env)));
+  std::vector<uint32_t> gbase((size_t)std::max(G, 1), 0);
+  uint64_t cells = 0;
+  for (int g = 0; g < G; g++) {
+    gbase[g] = (uint32_t)cells;
+    if (gsize[g] > 0) cells += (((uint64_t)gsize[g] + 1) >> k) + 1;
+    if (cells >= ((uint64_t)1 << 31)) return GTB_ERR_UNSUPPORTED;
+  }
+  // slot coordinates on the concatenated axis
+  std::vector<ull> slot_u((size_t)ix->n_slots), slot_u0((size_t)ix->n_slots);
+  for (int g = 0; g < G; g++) {
+    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1];
+    if (ge == gb) continue;
+    const ull u0 = (ull)gbase[g] << k;
+    const ull n_cells_g = gsize[g] > 0 ? ((((ull)gsize[g] + 1) >> k) + 1) : 0;
+    for (int32_t j = gb; j < ge; j++) {
+      const int32_t p = ix->h_points[j];
+      slot_u0[j] = u0;
+      if (j == ge - 1) slot_u[j] = n_cells_g ? u0 + (n_cells_g << k) - 1 : u0;   // sentinel: last u of the group
+      else slot_u[j] = p >= 1 ? u0 + (ull)p : u0;
+    }
+  }
+  // groups without a positive point occupy no cells: their slots share u with the next group's start,
+  // which is harmless because no element is ever produced for them.
+  for (size_t j = 1; j < slot_u.size(); j++) if (slot_u[j] < slot_u[j - 1]) slot_u[j] = slot_u[j - 1];
+  const ull total_u = std::max<ull>(cells << k, 1);
+  int ub = 24;
+  if (const char *env = getenv("GTB_BUCKET_BITS")) ub = std::max(k + 1, std::min(24, atoi(env)));
+  if (ub < k + 1) ub = k + 1;
+  std::vector<int32_t> j0;
+  int max_local = 0;
+  const bool cov = ix->op == GTB_OP_COVERAGE;
+  for (;; ub--) {
+    if (ub < k + 1 || ub < 8) return GTB_ERR_UNSUPPORTED;
+    const ull nb = (total_u + ((ull)1 << ub) - 1) >> ub;
+    if (nb > MAX_BUCKETS) return GTB_ERR_UNSUPPORTED;
+    j0.assign((size_t)nb + 1, 0);
+    max_local = 0;
+    for (ull b = 0; b <= nb; b++)
+      j0[b] = (int32_t)(std::lower_bound(slot_u.begin(), slot_u.end(), b << ub) - slot_u.begin());
+    for (ull b = 0; b < nb; b++) max_local = std::max(max_local, j0[b + 1] - j0[b]);
+    if (max_local < 65000 && count_smem_bytes(ub, k, max_local, cov) <= std::min(COUNT_SMEM_BUDGET, ctx->smem_optin)) break;
+  }
+  const uint32_t nb = (uint32_t)(j0.size() - 1);
+  bs->k = k; bs->ub = ub; bs->n_buckets = nb; bs->max_local = max_local;
+  bs->count_smem = count_smem_bytes(ub, k, max_local, cov);
+  const uint32_t nb4 = (nb + 3) & ~3u;
+  bs->part_smem = (size_t)PART_TILE * 4 + (size_t)PART_TILE * 2 + (size_t)SMEM_GROUPS * 8 + (size_t)nb4 * 20;
+  // directory and bucket-local slot coordinates
+  const int cb = ub - k;
+  std::vector<uint16_t> dir((size_t)nb << cb);
+  std::vector<uint32_t> slot_lu((size_t)ix->n_slots);
+  for (uint32_t b = 0; b < nb; b++) {
+    const ull bu = (ull)b << ub;
+    int32_t j = j0[b];
+    for (uint32_t cidx = 0; cidx < (1u << cb); cidx++) {
+      const ull cu = bu + ((ull)cidx << k);
+      while (j < j0[b + 1] && slot_u[j] < cu) j++;
+      dir[((size_t)b << cb) + cidx] = (uint16_t)(j - j0[b]);
+    }
+    for (int32_t jj = j0[b]; jj < j0[b + 1]; jj++) slot_lu[jj] = (uint32_t)(slot_u[jj] - bu);
+  }
+  std::vector<int2> gtab((size_t)std::max(G, 1));
+  for (int g = 0; g < G; g++) gtab[g] = make_int2(gsize[g], (int)gbase[g]);
+  GTB_TRY(upload_b(ctx, bs->d_gtab, gtab));
+  GTB_TRY(upload_b(ctx, bs->d_j0, j0));
+  GTB_TRY(upload_b(ctx, bs->d_slot_lu, slot_lu));
+  GTB_TRY(upload_b(ctx, bs->d_slot_u0, slot_u0));
+  GTB_TRY(upload_b(ctx, bs->d_dir, dir));
+  GTB_TRY(bs->d_cursor.reserve(ctx, nb));
+  GTB_TRY(bs->d_next_page.reserve(ctx, 1));
+  GTB_TRY(bs->d_unit_off.reserve(ctx, (size_t)nb + 1));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  bs->ready = true; bs->failed = false;
+  return GTB_OK;
+}
+
+bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
+  if (batch_multi || q.region_offset || q.weight) return false;        // single-interval, unweighted batches
+  if (q.n_regions >= ((int64_t)1 << 31)) return false;
+  if (gtb_bucket_prepare(ix) != GTB_OK) return false;
+  return ix->bucket->part_smem <= ix->ctx->smem_optin && ix->bucket->count_smem <= ix->ctx->smem_optin;
+}
+
+int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
+  gtb_ctx *ctx = ix->ctx;
+  if (gtb_bucket_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "bucket engine cannot serve this index");
+  gtb_bucket_state *bs = ix->bucket;
+  if (q.region_offset || q.weight) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "bucket engine takes single-interval, unweighted batches");
+  const uint32_t nb = bs->n_buckets;
+  const uint64_t n = (uint64_t)q.n_regions;
+  const uint32_t pt_stride = (uint32_t)((n + PAGE - 1) / PAGE + 1);
+  const uint64_t n_pages = (n + PAGE - 1) / PAGE + nb + 1;
+  GTB_TRY(bs->d_pool.reserve(ctx, (size_t)n_pages * PAGE));
+  GTB_TRY(bs->d_page_table.reserve(ctx, (size_t)nb * pt_stride));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_page_table.p, 0, (size_t)nb * pt_stride * 4, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_cursor.p, 0, (size_t)nb * 4, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_next_page.p, 0, 4, ctx->stream));
+
+  BucketView bv;
+  bv.k = bs->k; bv.ub = bs->ub; bv.n_chrom = ix->n_chrom; bv.n_class = ix->n_class; bv.n_groups = ix->n_groups;
+  bv.cls_plus = ix->h_class_of[(uint8_t)'+']; bv.cls_minus = ix->h_class_of[(uint8_t)'-'];
+  bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p;
+  bv.n_buckets = nb; bv.pool = bs->d_pool.p; bv.page_table = bs->d_page_table.p; bv.pt_stride = pt_stride;
+  bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p;
+  bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
+  bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
+  RankView rv;
+  rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p;
+
+  const bool cov = ix->op == GTB_OP_COVERAGE;
+  const bool aligned = ((uintptr_t)q.chrom % 32 == 0) && ((uintptr_t)q.start % 32 == 0) && ((uintptr_t)q.stop % 32 == 0) &&
+                       ((uintptr_t)q.strand % 8 == 0);
+  const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
+  const unsigned grid1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles));
+#define GTB_PART_LAUNCH(COV, VEC)                                                                                          \
+  do {                                                                                                                     \
+    auto kern = bucket_partition_kernel<COV, VEC>;                                                                         \
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->part_smem));         \
+    GTB_LAUNCH(ctx, "bucket_partition", kern, grid1, PART_THREADS, bs->part_smem, q, rv, bv);                              \
+  } while (0)
+  if (cov) { if (aligned) GTB_PART_LAUNCH(true, 8); else GTB_PART_LAUNCH(true, 1); }
+  else { if (aligned) GTB_PART_LAUNCH(false, 8); else GTB_PART_LAUNCH(false, 1); }
+#undef GTB_PART_LAUNCH
+  GTB_TRY(gtb_check_launch(ctx));
+  GTB_LAUNCH(ctx, "bucket_units", bucket_units_kernel, 1, 1024, 0, bv);
+  const unsigned grid2 = (unsigned)ctx->sm_count;
+  if (cov) {
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+    GTB_LAUNCH(ctx, "bucket_coverage", bucket_count_kernel<true>, grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+  } else {
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+    GTB_LAUNCH(ctx, "bucket_count", bucket_count_kernel<false>, grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+  }
+  return gtb_check_launch(ctx);
+}
+
+void gtb_bucket_destroy(gtb_index *ix) {
+  gtb_bucket_state *bs = ix->bucket;
+  if (!bs) return;
+  bs->d_gtab.release(); bs->d_j0.release(); bs->d_slot_lu.release(); bs->d_slot_u0.release(); bs->d_dir.release();
+  bs->d_pool.release(); bs->d_page_table.release(); bs->d_cursor.release(); bs->d_next_page.release(); bs->d_unit_off.release();
+  delete bs;
+  ix->bucket = nullptr;
+}

@@ -97,6 +97,8 @@ struct gtb_index {
 
   // cell engine state (gtb_cell.cu)
   struct gtb_cell_state *cell = nullptr;
+  // bucket engine state (gtb_bucket.cu)
+  struct gtb_bucket_state *bucket = nullptr;
 
   // results / errors
   dbuf<ull> d_err, d_out;
@@ -157,3 +159,9 @@ int gtb_cell_reset(gtb_index *ix);
 int gtb_cell_scan_for_finish(gtb_index *ix, CellFinalView *out);
 void gtb_cell_destroy(gtb_index *ix);
 bool gtb_cell_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
+
+// ---- bucket engine (gtb_bucket.cu) ---------------------------------------------------------------
+int gtb_bucket_prepare(gtb_index *ix);
+int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q);
+void gtb_bucket_destroy(gtb_index *ix);
+bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

@@ -20,6 +20,7 @@ ENGINE_AUTO = 0
 ENGINE_ENUMERATE = 1 << 16
 ENGINE_RANK = 1 << 17
 ENGINE_CELL = 1 << 18
+ENGINE_BUCKET = 1 << 19
 OP_COUNT = 0
 OP_COVERAGE = 1
 

@@ -62,7 +62,8 @@ enum {
   GTB_ENGINE_AUTO      = 0u,
   GTB_ENGINE_ENUMERATE = 1u << 16,  /* candidate enumeration (general; any region shape)         */
   GTB_ENGINE_RANK      = 1u << 17,  /* rank/rank-sum with global binary search                    */
-  GTB_ENGINE_CELL      = 1u << 18   /* genome-cell histogram, hot-cell bitmap in shared memory (fast path) */
+  GTB_ENGINE_CELL      = 1u << 18,  /* single pass: genome-cell tables, hot-cell bitmap in shared memory        */
+  GTB_ENGINE_BUCKET    = 1u << 19   /* two passes: partition by genome bucket, rank in shared memory (default fast path) */
 };
 
 enum { GTB_OP_COUNT = 0, GTB_OP_COVERAGE = 1 };

@@ -9,13 +9,16 @@ import support
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18}
+ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18, "bucket": 1 << 19}
 CELL_KS = ("3", "6", "10")      # cell widths 8 / 64 / 1024 bp: mostly-cold, mixed, and overfull-hot-cell regimes
 
 
 @pytest.fixture(params=CELL_KS)
 def cell_k(request, monkeypatch):
     monkeypatch.setenv("GTB_CELL_K", request.param)
+    # the bucket engine's knobs ride along: cell width and bucket width (12..16 bits -> several buckets on the toy genomes)
+    monkeypatch.setenv("GTB_BUCKET_K", {"3": "2", "6": "5", "10": "8"}[request.param])
+    monkeypatch.setenv("GTB_BUCKET_BITS", {"3": "9", "6": "12", "10": "16"}[request.param])
     return request.param
 
 
@@ -41,8 +44,8 @@ def oracle():
 @pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("case", goldens.overlap_cases(), ids=lambda c: c["name"])
 def test_overlap_golden(ctx, case, engine, cell_k):
-    if engine != "cell" and cell_k != CELL_KS[0]:
-        pytest.skip("cell width only matters to the cell engine")
+    if engine not in ("cell", "bucket") and cell_k != CELL_KS[0]:
+        pytest.skip("cell width only matters to the cell / bucket engines")
     multi = case["ioff"] is not None or case["qoff"] is not None
     for (op, flags), want in case["expect"].items():
         if engine == "rank" and multi and op == "count" and not (flags & 1):
