@@ -40,8 +40,8 @@ constexpr int PAGE_SHIFT = 12;
 constexpr uint32_t PAGE = 1u << PAGE_SHIFT;               // elements per page (== PART_TILE: a tile's slice spans <= 2 pages)
 constexpr int UNIT_PAGES = 16;                            // pass-2 work unit = 65 536 elements
 constexpr int MAX_BUCKETS = 2048;
-constexpr int SMEM_GROUPS = 512;
-constexpr int COUNT_THREADS = 512;
+constexpr int SMEM_GROUPS = 512;                          // entries of the (chromosome, +/-) table staged in shared memory
+constexpr int COUNT_THREADS = 256;
 constexpr size_t COUNT_SMEM_BUDGET = 200 * 1024;
 
 struct BucketView {
@@ -51,6 +51,7 @@ struct BucketView {
   const int8_t *class_of;
   const uint8_t *chrom_present;
   const int2 *gtab;                 // per group: (largest point, first cell)
+  const int2 *pm_tab;               // [2 * n_chrom] the same for (chromosome, '+') and (chromosome, '-'); (0,0) if no such group
   uint32_t n_buckets;
   // paged bucket storage
   uint32_t *pool;                   // pages of PAGE elements
@@ -111,7 +112,7 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
-template <bool COVERAGE, int VEC>
+template <bool COVERAGE, int VEC, int RES>
 __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *s_stage = smem;                                           // [PART_TILE] elements in bucket order
@@ -120,17 +121,16 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
   uint32_t *s_cnt = smem + PART_TILE + PART_TILE / 2 + 2 * SMEM_GROUPS;                 // [nb4] per-bucket counts of this tile
   const uint32_t nb4 = (bv.n_buckets + 3) & ~3u;
   uint32_t *s_off = s_cnt + nb4;                                      // [nb4] exclusive scan of s_cnt
-  uint32_t *s_g0 = s_off + nb4;                                       // [nb4] global element address of the slice's first part
-  uint32_t *s_g1 = s_g0 + nb4;                                        // [nb4] ... of the part that spilled into the next page
-  uint32_t *s_split = s_g1 + nb4;                                     // [nb4] elements in the first part
+  uint2 *s_dl = reinterpret_cast<uint2 *>(s_off + nb4);               // [nb4] (global address - staged position, staged position where the slice spills into the next page)
+  uint32_t *s_g1 = s_off + 3 * nb4;                                   // [nb4] global address of the spilled part
   __shared__ uint32_t s_warp_tot[PART_THREADS / 32];
 
-  const bool groups_in_smem = bv.n_groups <= SMEM_GROUPS;
+  const bool groups_in_smem = 2 * bv.n_chrom <= SMEM_GROUPS;
   if (groups_in_smem)
-    for (int i = threadIdx.x; i < bv.n_groups; i += blockDim.x) s_gtab[i] = bv.gtab[i];
+    for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_gtab[i] = bv.pm_tab[i];
   for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
-  const int2 *gtab = groups_in_smem ? s_gtab : bv.gtab;
+  const int2 *pm = groups_in_smem ? s_gtab : bv.pm_tab;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
   const uint32_t kmask = (1u << bv.k) - 1u, ubmask = (1u << bv.ub) - 1u;
@@ -174,23 +174,18 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
     unsigned special = 0;
 #pragma unroll
     for (int i = 0; i < PART_ITEMS; i++) {
-      const int strand = ((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF;
+      const uint32_t d = (uint32_t)(((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF) - (uint32_t)'+';   // '+' -> 0, '-' -> 2
       const int known = (uint32_t)c[i] < (uint32_t)bv.n_chrom;                    // else: no match, no checks (:5719)
-      const int is_pm = (strand == '+') | (strand == '-');
-      const int cls = strand == '+' ? bv.cls_plus : (strand == '-' ? bv.cls_minus : -1);
-      const int valid = (s[i] <= e[i]) & (e[i] > 0);
-      const int plain = known & (cls >= 0) & (s[i] >= 1) & valid;
-      const int2 gt = gtab[plain ? c[i] * bv.n_class + cls : 0];
-      const int in_cells = plain & (gt.x > 0);
-      const int beyond = in_cells & (s[i] > gt.x);                                // past every evaluation point: nothing to count
+      const int ok = known & ((d & ~2u) == 0) & (s[i] >= 1) & (s[i] <= e[i]);     // '+'/'-' strand, start inside the cells, valid interval
+      const int2 gt = pm[ok ? 2 * c[i] + (int)(d >> 1) : 0];                      // (largest point, first cell) of the query's group
       const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
       const uint32_t cell = (uint32_t)gt.y + ((uint32_t)s[i] >> bv.k);
       const uint32_t lu = ((cell & ((1u << cb) - 1u)) << bv.k) | ((uint32_t)s[i] & kmask);
-      const int fits = (len <= len_max) & (lu + len <= ubmask);
-      const int normal = in_cells & !beyond & fits;
-      // nothing to do: unknown chromosome, beyond the last point, empty group, or a '+'/'-' strand no index region carries
-      const int nothing = !known | beyond | (plain & (gt.x == 0)) | (known & is_pm & (cls < 0) & valid);
-      special |= (unsigned)(!normal & !nothing) << i;
+      const int inside = ok & (gt.x > 0) & (s[i] <= gt.x);                        // group has points and the query starts before the last one
+      const int normal = inside & (len <= len_max) & (lu + len <= ubmask);
+      // not expressible as an element, yet possibly contributing (or fatal): start <= 0, invalid interval, other strand
+      // bytes, too long, crossing the bucket end, a group whose points are all <= 0.  (ok && !inside && gt.x >= 0: nothing to count.)
+      special |= (unsigned)(known & !normal & !(ok & !inside & (gt.x >= 0))) << i;
       bkt[i] = normal ? (cell >> cb) : 0xFFFFFFFFu;
       elem[i] = lu | (len << bv.ub);
       rnk[i] = 0;
@@ -204,7 +199,16 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
     }
     __syncthreads();
 
-    // ---- exclusive scan of the bucket counts (4 counters per thread), reserve global space
+    // ---- reserve global space: one global atomic per non-empty bucket, one bucket per thread, all
+    // issued before anything waits on them; the exclusive scan of the counts runs in their shadow
+    uint32_t r_cnt[RES], r_old[RES], r_g0[RES], r_g1[RES], r_split[RES];
+#pragma unroll
+    for (int j = 0; j < RES; j++) {
+      const uint32_t b = threadIdx.x + j * PART_THREADS;
+      r_cnt[j] = b < bv.n_buckets ? s_cnt[b] : 0u;
+      r_old[j] = 0; r_g0[j] = 0; r_g1[j] = 0; r_split[j] = 0;
+      if (r_cnt[j]) r_old[j] = atomicAdd(bv.cursor + b, r_cnt[j]);
+    }
     {
       uint32_t v[4] = {0, 0, 0, 0}, sum = 0;
       const uint32_t b0 = threadIdx.x * 4;
@@ -216,25 +220,6 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
       if (lane == 31) s_warp_tot[warp] = inc;
-      // reserve: one global atomic per non-empty bucket; allocate the pages whose first element is ours
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t b = b0 + j;
-        if (b < bv.n_buckets && v[j] > 0) {
-          const uint32_t old = atomicAdd(bv.cursor + b, v[j]);
-          const uint32_t p_first = old >> PAGE_SHIFT, p_last = (old + v[j] - 1) >> PAGE_SHIFT;
-          uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
-          if ((old & (PAGE - 1)) == 0) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_first, pid + 1); }
-          if (p_last != p_first) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_last, pid + 1); }
-          uint32_t id0, id1;
-          while ((id0 = ld_volatile_u32(pt + p_first)) == 0) {}
-          id1 = id0;
-          if (p_last != p_first) while ((id1 = ld_volatile_u32(pt + p_last)) == 0) {}
-          s_g0[b] = ((id0 - 1) << PAGE_SHIFT) + (old & (PAGE - 1));
-          s_g1[b] = (id1 - 1) << PAGE_SHIFT;
-          s_split[b] = min(v[j], PAGE - (old & (PAGE - 1)));
-        }
-      }
       __syncthreads();
       uint32_t base = inc - sum;
       for (int w = 0; w < warp; w++) base += s_warp_tot[w];
@@ -244,7 +229,35 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
         *reinterpret_cast<uint4 *>(s_off + b0) = o;
       }
     }
+    // pages: allocate the ones whose first element is ours, wait for the ones somebody else allocates
+#pragma unroll
+    for (int j = 0; j < RES; j++) {
+      if (r_cnt[j]) {
+        const uint32_t b = threadIdx.x + j * PART_THREADS, old = r_old[j];
+        const uint32_t p_first = old >> PAGE_SHIFT, p_last = (old + r_cnt[j] - 1) >> PAGE_SHIFT;
+        uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
+        if ((old & (PAGE - 1)) == 0) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_first, pid + 1); }
+        if (p_last != p_first) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_last, pid + 1); }
+        uint32_t id0, id1;
+        while ((id0 = ld_volatile_u32(pt + p_first)) == 0) {}
+        id1 = id0;
+        if (p_last != p_first) while ((id1 = ld_volatile_u32(pt + p_last)) == 0) {}
+        r_g0[j] = ((id0 - 1) << PAGE_SHIFT) + (old & (PAGE - 1));
+        r_g1[j] = (id1 - 1) << PAGE_SHIFT;
+        r_split[j] = min(r_cnt[j], PAGE - (old & (PAGE - 1)));
+      }
+    }
     __syncthreads();
+    // per bucket: (address delta of the first part, staged position where the second part begins) and the second part's base
+#pragma unroll
+    for (int j = 0; j < RES; j++) {
+      const uint32_t b = threadIdx.x + j * PART_THREADS;
+      if (b < bv.n_buckets) {
+        const uint32_t off = s_off[b];
+        s_dl[b] = make_uint2(r_g0[j] - off, off + r_split[j]);
+        s_g1[b] = r_g1[j];
+      }
+    }
 
     // ---- scatter into the staging buffer in bucket order
 #pragma unroll
@@ -255,18 +268,16 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
         s_bid[p] = (uint16_t)bkt[i];
       }
     }
+    const uint32_t total = s_off[nb4 - 1] + s_cnt[nb4 - 1];
     __syncthreads();
 
     // ---- copy out: consecutive staged elements of a bucket go to consecutive addresses
-    const uint32_t total = s_off[nb4 - 1] + s_cnt[nb4 - 1];
     for (uint32_t p = threadIdx.x; p < total; p += PART_THREADS) {
       const uint32_t b = s_bid[p];
-      const uint32_t r = p - s_off[b];
-      const uint32_t sp = s_split[b];
-      const uint32_t addr = r < sp ? s_g0[b] + r : s_g1[b] + (r - sp);
+      const uint2 dl = s_dl[b];
+      const uint32_t addr = p < dl.y ? p + dl.x : s_g1[b] + (p - dl.y);
       bv.pool[addr] = s_stage[p];
     }
-    __syncthreads();
     for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
   }
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
 // pass 2
 // ------------------------------------------------------------------------------------------------
 template <bool COVERAGE>
-__global__ void __launch_bounds__(COUNT_THREADS, 1) bucket_count_kernel(BucketView bv, RankView rv) {
+__global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketView bv, RankView rv) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int cb = bv.ub - bv.k;
   const uint32_t n_dir = 1u << cb;
@@ -396,22 +407,26 @@ __global__ void __launch_bounds__(COUNT_THREADS, 1) bucket_count_kernel(BucketVi
       for (int r = 0; r < UNROLL; r++) {
         const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
         const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};
+        uint32_t us[4], ue[4], jS[4], pS[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { us[i] = el[i] & ubmask; ue[i] = us[i] + (el[i] >> bv.ub); jS[i] = s_dir[us[i] >> kmaskless]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) pS[i] = s_pts[jS[i]];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (v4 * 4 + i >= n_el) break;
-          const uint32_t us = el[i] & ubmask, len = el[i] >> bv.ub, ue = us + len;
-          uint32_t jS = s_dir[us >> kmaskless];
-          while (s_pts[jS] < us) jS++;
-          uint32_t jE = jS;
-          while (s_pts[jE] < ue) jE++;
-          if (!COVERAGE) {
-            if (jS == jE) atomicAdd(&s_h32[jS], 1u);
-            else { atomicAdd(&s_h32[cap + jS], 1u); atomicAdd(&s_h32[2 * cap + jE], 1u); }
-          } else {
-            if (jS == jE) atomicAdd(&s_h64[jS], (ull)len + 1ull);
-            else {
-              atomicAdd(&s_h64[cap + jS], 1ull); atomicAdd(&s_h64[2 * cap + jE], 1ull);
-              atomicAdd(&s_h64[3 * cap + jS], (ull)us); atomicAdd(&s_h64[4 * cap + jE], (ull)ue);
+          while (pS[i] < us[i]) pS[i] = s_pts[++jS[i]];                  // first slot whose point is >= start
+          uint32_t jE = jS[i], pE = pS[i];
+          while (pE < ue[i]) pE = s_pts[++jE];                           // ... >= stop
+          if (v4 * 4 + i < n_el) {
+            if (!COVERAGE) {
+              if (jS[i] == jE) atomicAdd(&s_h32[jS[i]], 1u);
+              else { atomicAdd(&s_h32[cap + jS[i]], 1u); atomicAdd(&s_h32[2 * cap + jE], 1u); }
+            } else {
+              if (jS[i] == jE) atomicAdd(&s_h64[jS[i]], (ull)(ue[i] - us[i]) + 1ull);
+              else {
+                atomicAdd(&s_h64[cap + jS[i]], 1ull); atomicAdd(&s_h64[2 * cap + jE], 1ull);
+                atomicAdd(&s_h64[3 * cap + jS[i]], (ull)us[i]); atomicAdd(&s_h64[4 * cap + jE], (ull)ue[i]);
+              }
             }
           }
         }
@@ -437,7 +452,7 @@ struct gtb_bucket_state {
   uint32_t n_buckets = 0;
   int max_local = 0;
   size_t count_smem = 0, part_smem = 0;
-  dbuf<int2> d_gtab;
+  dbuf<int2> d_gtab, d_pm;
   dbuf<int32_t> d_j0;
   dbuf<uint32_t> d_slot_lu;
   dbuf<ull> d_slot_u0;
@@ -535,6 +550,15 @@ int gtb_bucket_prepare(gtb_index *ix) {
   std::vector<int2> gtab((size_t)std::max(G, 1));
   for (int g = 0; g < G; g++) gtab[g] = make_int2(gsize[g], (int)gbase[g]);
   GTB_TRY(upload_b(ctx, bs->d_gtab, gtab));
+  {
+    std::vector<int2> pm((size_t)std::max(ix->n_chrom, 1) * 2, make_int2(0, 0));
+    const int cp = ix->h_class_of[(uint8_t)'+'], cm = ix->h_class_of[(uint8_t)'-'];
+    for (int c = 0; c < ix->n_chrom; c++) {
+      if (cp >= 0) pm[2 * c] = gtab[(size_t)c * ix->n_class + cp];
+      if (cm >= 0) pm[2 * c + 1] = gtab[(size_t)c * ix->n_class + cm];
+    }
+    GTB_TRY(upload_b(ctx, bs->d_pm, pm));
+  }
   GTB_TRY(upload_b(ctx, bs->d_j0, j0));
   GTB_TRY(upload_b(ctx, bs->d_slot_lu, slot_lu));
   GTB_TRY(upload_b(ctx, bs->d_slot_u0, slot_u0));
@@ -572,7 +596,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   BucketView bv;
   bv.k = bs->k; bv.ub = bs->ub; bv.n_chrom = ix->n_chrom; bv.n_class = ix->n_class; bv.n_groups = ix->n_groups;
   bv.cls_plus = ix->h_class_of[(uint8_t)'+']; bv.cls_minus = ix->h_class_of[(uint8_t)'-'];
-  bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p;
+  bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p; bv.pm_tab = bs->d_pm.p;
   bv.n_buckets = nb; bv.pool = bs->d_pool.p; bv.page_table = bs->d_page_table.p; bv.pt_stride = pt_stride;
   bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p;
   bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
@@ -588,7 +612,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   const unsigned grid1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles));
 #define GTB_PART_LAUNCH(COV, VEC)                                                                                          \
   do {                                                                                                                     \
-    auto kern = bucket_partition_kernel<COV, VEC>;                                                                         \
+    auto kern = nb <= PART_THREADS ? bucket_partition_kernel<COV, VEC, 1> : bucket_partition_kernel<COV, VEC, MAX_BUCKETS / PART_THREADS>;                                                                       \
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->part_smem));         \
     GTB_LAUNCH(ctx, "bucket_partition", kern, grid1, PART_THREADS, bs->part_smem, q, rv, bv);                              \
   } while (0)
@@ -597,7 +621,9 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
 #undef GTB_PART_LAUNCH
   GTB_TRY(gtb_check_launch(ctx));
   GTB_LAUNCH(ctx, "bucket_units", bucket_units_kernel, 1, 1024, 0, bv);
-  const unsigned grid2 = (unsigned)ctx->sm_count;
+  const size_t per_sm = 227 * 1024;
+  const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (bs->count_smem + 1024)));
+  const unsigned grid2 = (unsigned)ctx->sm_count * ctas_per_sm;
   if (cov) {
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
     GTB_LAUNCH(ctx, "bucket_coverage", bucket_count_kernel<true>, grid2, COUNT_THREADS, bs->count_smem, bv, rv);
@@ -611,7 +637,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
 void gtb_bucket_destroy(gtb_index *ix) {
   gtb_bucket_state *bs = ix->bucket;
   if (!bs) return;
-  bs->d_gtab.release(); bs->d_j0.release(); bs->d_slot_lu.release(); bs->d_slot_u0.release(); bs->d_dir.release();
+  bs->d_gtab.release(); bs->d_pm.release(); bs->d_j0.release(); bs->d_slot_lu.release(); bs->d_slot_u0.release(); bs->d_dir.release();
   bs->d_pool.release(); bs->d_page_table.release(); bs->d_cursor.release(); bs->d_next_page.release(); bs->d_unit_off.release();
   delete bs;
   ix->bucket = nullptr;
