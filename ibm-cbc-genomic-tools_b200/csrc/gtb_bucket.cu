@@ -51,7 +51,7 @@ struct BucketView {
   const int8_t *class_of;
   const uint8_t *chrom_present;
   const int2 *gtab;                 // per group: (largest point, first cell)
-  const int2 *pm_tab;               // [2 * n_chrom] the same for (chromosome, '+') and (chromosome, '-'); (0,0) if no such group
+  const int4 *pm_tab;               // [2 * n_chrom] per (chromosome, '+'/'-'): (largest point, u0 & (2^ub - 1), u0 >> ub, 0)
   uint32_t n_buckets;
   // paged bucket storage
   uint32_t *pool;                   // pages of PAGE elements
@@ -112,30 +112,30 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
+// Per (chromosome, '+'/'-') group, staged in shared memory as one 16-byte entry:
+//   x = largest evaluation point (0: no such group / no points, < 0: only points <= 0)
+//   y = (u of coordinate 0 of the group) & (bucket size - 1)      z = (u of coordinate 0) >> ub
+// so that for a start coordinate s:  t = y + s,  bucket = z + (t >> ub),  bucket-local u = t & (2^ub - 1).
 template <bool COVERAGE, int VEC, int RES>
 __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *s_stage = smem;                                           // [PART_TILE] elements in bucket order
-  uint16_t *s_bid = reinterpret_cast<uint16_t *>(smem + PART_TILE);   // [PART_TILE] bucket of each staged element
-  int2 *s_gtab = reinterpret_cast<int2 *>(smem + PART_TILE + PART_TILE / 2);            // [SMEM_GROUPS]
-  uint32_t *s_cnt = smem + PART_TILE + PART_TILE / 2 + 2 * SMEM_GROUPS;                 // [nb4] per-bucket counts of this tile
+  uint2 *s_stage = reinterpret_cast<uint2 *>(smem);                   // [PART_TILE] (element, bucket) in bucket order
+  uint32_t *s_cnt = smem + 2 * PART_TILE;                             // [nb4] per-bucket counts of this tile
   const uint32_t nb4 = (bv.n_buckets + 3) & ~3u;
   uint32_t *s_off = s_cnt + nb4;                                      // [nb4] exclusive scan of s_cnt
   uint2 *s_dl = reinterpret_cast<uint2 *>(s_off + nb4);               // [nb4] (global address - staged position, staged position where the slice spills into the next page)
   uint32_t *s_g1 = s_off + 3 * nb4;                                   // [nb4] global address of the spilled part
+  int4 *s_pm = reinterpret_cast<int4 *>(s_off + 4 * nb4);             // [2 * n_chrom] group table
   __shared__ uint32_t s_warp_tot[PART_THREADS / 32];
 
-  const bool groups_in_smem = 2 * bv.n_chrom <= SMEM_GROUPS;
-  if (groups_in_smem)
-    for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_gtab[i] = bv.pm_tab[i];
+  for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_pm[i] = bv.pm_tab[i];
   for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
-  const int2 *pm = groups_in_smem ? s_gtab : bv.pm_tab;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
-  const uint32_t kmask = (1u << bv.k) - 1u, ubmask = (1u << bv.ub) - 1u;
-  const int cb = bv.ub - bv.k;                                         // cell bits inside a bucket
-  const uint32_t len_max = bv.ub >= 32 ? 0u : (0xFFFFFFFFu >> bv.ub);
+  const uint32_t ubmask = (1u << bv.ub) - 1u;
+  const uint32_t len_max = 0xFFFFFFFFu >> bv.ub;
+  const uint32_t n_chrom = (uint32_t)bv.n_chrom;
 
   int32_t nc[PART_ITEMS], ns[PART_ITEMS], ne[PART_ITEMS];
   int2 nst = make_int2(0, 0);
@@ -162,40 +162,40 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
   if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t first = tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS;
-    int32_t c[PART_ITEMS], s[PART_ITEMS], e[PART_ITEMS];
-    const int2 stw = nst;
-#pragma unroll
-    for (int i = 0; i < PART_ITEMS; i++) { c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; }
-    if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
-
     // ---- classify, build the element, rank inside the bucket (one shared atomic per query)
-    uint32_t elem[PART_ITEMS], bkt[PART_ITEMS], rnk[PART_ITEMS];
-    unsigned special = 0;
+    uint32_t elem[PART_ITEMS], br[PART_ITEMS];                         // br = bucket << 16 | rank  (0xFFFFFFFF: no element)
+    {
+      int32_t c[PART_ITEMS], s[PART_ITEMS], e[PART_ITEMS];
+      const int2 stw = nst;
 #pragma unroll
-    for (int i = 0; i < PART_ITEMS; i++) {
-      const uint32_t d = (uint32_t)(((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF) - (uint32_t)'+';   // '+' -> 0, '-' -> 2
-      const int known = (uint32_t)c[i] < (uint32_t)bv.n_chrom;                    // else: no match, no checks (:5719)
-      const int ok = known & ((d & ~2u) == 0) & (s[i] >= 1) & (s[i] <= e[i]);     // '+'/'-' strand, start inside the cells, valid interval
-      const int2 gt = pm[ok ? 2 * c[i] + (int)(d >> 1) : 0];                      // (largest point, first cell) of the query's group
-      const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
-      const uint32_t cell = (uint32_t)gt.y + ((uint32_t)s[i] >> bv.k);
-      const uint32_t lu = ((cell & ((1u << cb) - 1u)) << bv.k) | ((uint32_t)s[i] & kmask);
-      const int inside = ok & (gt.x > 0) & (s[i] <= gt.x);                        // group has points and the query starts before the last one
-      const int normal = inside & (len <= len_max) & (lu + len <= ubmask);
-      // not expressible as an element, yet possibly contributing (or fatal): start <= 0, invalid interval, other strand
-      // bytes, too long, crossing the bucket end, a group whose points are all <= 0.  (ok && !inside && gt.x >= 0: nothing to count.)
-      special |= (unsigned)(known & !normal & !(ok & !inside & (gt.x >= 0))) << i;
-      bkt[i] = normal ? (cell >> cb) : 0xFFFFFFFFu;
-      elem[i] = lu | (len << bv.ub);
-      rnk[i] = 0;
-      if (normal) rnk[i] = atomicAdd(&s_cnt[bkt[i]], 1u);
-    }
-    if (special) {
+      for (int i = 0; i < PART_ITEMS; i++) { c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; }
+      if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
 #pragma unroll
-      for (int i = 0; i < PART_ITEMS; i++)
-        if (special & (1u << i))
-          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)(((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFF), 1, q.index_base + first + i);
+      for (int i = 0; i < PART_ITEMS; i++) {
+        const uint32_t sbyte = ((uint32_t)(i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFFu;
+        const uint32_t d = sbyte - (uint32_t)'+';                                   // '+' -> 0, '-' -> 2
+        const bool addressable = (uint32_t)c[i] < n_chrom && (d & ~2u) == 0;        // known chromosome, '+'/'-' strand
+        const int4 gt = s_pm[addressable ? 2 * c[i] + (int)(d >> 1) : 0];
+        const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
+        const uint32_t t = (uint32_t)gt.y + (uint32_t)s[i];
+        const uint32_t lu = t & ubmask;
+        // the common case: valid interval starting inside the cells, before the group's last point, short
+        // enough for the length field, not crossing the end of its bucket
+        const bool normal = addressable && s[i] >= 1 && s[i] <= e[i] && s[i] <= gt.x && len <= len_max && lu + len <= ubmask;
+        elem[i] = lu | (len << bv.ub);
+        br[i] = 0xFFFFFFFFu;
+        if (normal) {
+          const uint32_t b = (uint32_t)gt.z + (t >> bv.ub);
+          br[i] = (b << 16) | atomicAdd(&s_cnt[b], 1u);
+        } else if ((uint32_t)c[i] < n_chrom) {
+          // rare: decide between "nothing to count" and the general path.  Nothing: a valid '+'/'-' query that
+          // starts at >= 1 in a group without points, or beyond the group's last point.
+          const bool nothing = addressable && s[i] >= 1 && s[i] <= e[i] && gt.x >= 0 && (gt.x == 0 || s[i] > gt.x);
+          if (!nothing)
+            special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)sbyte, 1,
+                                    q.index_base + tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS + i);
+        }
+      }
     }
     __syncthreads();
 
@@ -262,10 +262,9 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
     // ---- scatter into the staging buffer in bucket order
 #pragma unroll
     for (int i = 0; i < PART_ITEMS; i++) {
-      if (bkt[i] != 0xFFFFFFFFu) {
-        const uint32_t p = s_off[bkt[i]] + rnk[i];
-        s_stage[p] = elem[i];
-        s_bid[p] = (uint16_t)bkt[i];
+      if (br[i] != 0xFFFFFFFFu) {
+        const uint32_t b = br[i] >> 16;
+        s_stage[s_off[b] + (br[i] & 0xFFFFu)] = make_uint2(elem[i], b);
       }
     }
     const uint32_t total = s_off[nb4 - 1] + s_cnt[nb4 - 1];
@@ -273,10 +272,10 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
 
     // ---- copy out: consecutive staged elements of a bucket go to consecutive addresses
     for (uint32_t p = threadIdx.x; p < total; p += PART_THREADS) {
-      const uint32_t b = s_bid[p];
-      const uint2 dl = s_dl[b];
-      const uint32_t addr = p < dl.y ? p + dl.x : s_g1[b] + (p - dl.y);
-      bv.pool[addr] = s_stage[p];
+      const uint2 eb = s_stage[p];
+      const uint2 dl = s_dl[eb.y];
+      const uint32_t addr = p < dl.y ? p + dl.x : s_g1[eb.y] + (p - dl.y);
+      bv.pool[addr] = eb.x;
     }
     for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
@@ -452,7 +451,8 @@ struct gtb_bucket_state {
   uint32_t n_buckets = 0;
   int max_local = 0;
   size_t count_smem = 0, part_smem = 0;
-  dbuf<int2> d_gtab, d_pm;
+  dbuf<int2> d_gtab;
+  dbuf<int4> d_pm;
   dbuf<int32_t> d_j0;
   dbuf<uint32_t> d_slot_lu;
   dbuf<ull> d_slot_u0;
@@ -532,7 +532,7 @@ int gtb_bucket_prepare(gtb_index *ix) {
   bs->k = k; bs->ub = ub; bs->n_buckets = nb; bs->max_local = max_local;
   bs->count_smem = count_smem_bytes(ub, k, max_local, cov);
   const uint32_t nb4 = (nb + 3) & ~3u;
-  bs->part_smem = (size_t)PART_TILE * 4 + (size_t)PART_TILE * 2 + (size_t)SMEM_GROUPS * 8 + (size_t)nb4 * 20;
+  bs->part_smem = (size_t)PART_TILE * 8 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
@@ -551,11 +551,15 @@ int gtb_bucket_prepare(gtb_index *ix) {
   for (int g = 0; g < G; g++) gtab[g] = make_int2(gsize[g], (int)gbase[g]);
   GTB_TRY(upload_b(ctx, bs->d_gtab, gtab));
   {
-    std::vector<int2> pm((size_t)std::max(ix->n_chrom, 1) * 2, make_int2(0, 0));
+    std::vector<int4> pm((size_t)std::max(ix->n_chrom, 1) * 2, make_int4(0, 0, 0, 0));
     const int cp = ix->h_class_of[(uint8_t)'+'], cm = ix->h_class_of[(uint8_t)'-'];
+    auto entry = [&](int g) {
+      const ull u0 = (ull)gbase[g] << k;
+      return make_int4(gsize[g], (int)(u0 & (((ull)1 << ub) - 1)), (int)(u0 >> ub), 0);
+    };
     for (int c = 0; c < ix->n_chrom; c++) {
-      if (cp >= 0) pm[2 * c] = gtab[(size_t)c * ix->n_class + cp];
-      if (cm >= 0) pm[2 * c + 1] = gtab[(size_t)c * ix->n_class + cm];
+      if (cp >= 0) pm[2 * c] = entry(c * ix->n_class + cp);
+      if (cm >= 0) pm[2 * c + 1] = entry(c * ix->n_class + cm);
     }
     GTB_TRY(upload_b(ctx, bs->d_pm, pm));
   }
