@@ -40,7 +40,6 @@ constexpr int PAGE_SHIFT = 12;
 constexpr uint32_t PAGE = 1u << PAGE_SHIFT;               // elements per page (== PART_TILE: a tile's slice spans <= 2 pages)
 constexpr int UNIT_PAGES = 16;                            // pass-2 work unit = 65 536 elements
 constexpr int MAX_BUCKETS = 2048;
-constexpr int SMEM_GROUPS = 512;                          // entries of the (chromosome, +/-) table staged in shared memory
 constexpr int COUNT_THREADS = 256;
 constexpr size_t COUNT_SMEM_BUDGET = 200 * 1024;
 
@@ -68,19 +67,6 @@ struct BucketView {
   int max_local;                    // largest number of slots in a bucket (excluding the catch-all)
 };
 
-struct int8v { int v[8]; };
-__device__ __forceinline__ int8v ldg_stream256(const int *p) {
-  int8v r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ int2 ldg_stream64(const int *p) {
-  int2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
 __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -92,6 +78,25 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+// ---- TMA bulk copy (global -> shared) with mbarrier completion, sm_90+/sm_100 PTX -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // The rare queries an element cannot describe: admission checks of the reference, then the general
 // rank step (binary search in global memory).
@@ -118,61 +123,77 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
 // so that for a start coordinate s:  t = y + s,  bucket = z + (t >> ub),  bucket-local u = t & (2^ub - 1).
 template <bool COVERAGE, int VEC, int RES>
 __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint2 *s_stage = reinterpret_cast<uint2 *>(smem);                   // [PART_TILE] (element, bucket) in bucket order
-  uint32_t *s_cnt = smem + 2 * PART_TILE;                             // [nb4] per-bucket counts of this tile
+  extern __shared__ __align__(128) uint32_t smem[];
+  // raw tile, filled by TMA bulk copies: chrom | start | stop (PART_TILE ints each) | strand (PART_TILE bytes)
+  int32_t *s_chrom = reinterpret_cast<int32_t *>(smem);
+  int32_t *s_start = s_chrom + PART_TILE;
+  int32_t *s_stop = s_start + PART_TILE;
+  int8_t *s_strand = reinterpret_cast<int8_t *>(s_stop + PART_TILE);
+  uint2 *s_stage = reinterpret_cast<uint2 *>(smem + 3 * PART_TILE + PART_TILE / 4);   // [PART_TILE] (element, bucket) in bucket order
+  uint32_t *s_cnt = smem + 3 * PART_TILE + PART_TILE / 4 + 2 * PART_TILE + 4;         // [nb4 + 4] per-bucket counts of this tile (+ dummy)
   const uint32_t nb4 = (bv.n_buckets + 3) & ~3u;
-  uint32_t *s_off = s_cnt + nb4;                                      // [nb4] exclusive scan of s_cnt
-  uint2 *s_dl = reinterpret_cast<uint2 *>(s_off + nb4);               // [nb4] (global address - staged position, staged position where the slice spills into the next page)
-  uint32_t *s_g1 = s_off + 3 * nb4;                                   // [nb4] global address of the spilled part
-  int4 *s_pm = reinterpret_cast<int4 *>(s_off + 4 * nb4);             // [2 * n_chrom] group table
+  uint32_t *s_off = s_cnt + nb4 + 4;                                  // [nb4 + 4] exclusive scan of s_cnt
+  uint2 *s_dl = reinterpret_cast<uint2 *>(s_off + nb4 + 4);           // [nb4] (global address - staged position, staged position where the slice spills into the next page)
+  uint32_t *s_g1 = s_off + 3 * nb4 + 4;                               // [nb4] global address of the spilled part
+  int4 *s_pm = reinterpret_cast<int4 *>(s_off + 4 * nb4 + 4);         // [2 * n_chrom] group table
   __shared__ uint32_t s_warp_tot[PART_THREADS / 32];
+  __shared__ __align__(8) uint64_t s_bar;
 
   for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_pm[i] = bv.pm_tab[i];
-  for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
+  for (uint32_t i = threadIdx.x; i < nb4 + 4; i += blockDim.x) s_cnt[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); fence_proxy_async(); }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
+  const int64_t n_full = VEC == 8 ? q.n_regions / PART_TILE : 0;      // tiles that TMA can fetch (complete, aligned)
   const uint32_t ubmask = (1u << bv.ub) - 1u;
   const uint32_t len_max = 0xFFFFFFFFu >> bv.ub;
   const uint32_t n_chrom = (uint32_t)bv.n_chrom;
+  constexpr uint32_t TILE_BYTES = PART_TILE * 13;
 
-  int32_t nc[PART_ITEMS], ns[PART_ITEMS], ne[PART_ITEMS];
-  int2 nst = make_int2(0, 0);
-  auto fetch = [&](int64_t tile) {
-    const int64_t first = tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS;
-    if (VEC == 8 && first + PART_ITEMS <= q.n_regions) {
-      const int8v cc = ldg_stream256(q.chrom + first), ss = ldg_stream256(q.start + first), ee = ldg_stream256(q.stop + first);
-      nst = ldg_stream64(reinterpret_cast<const int *>(q.strand + first));
-#pragma unroll
-      for (int i = 0; i < PART_ITEMS; i++) { nc[i] = cc.v[i]; ns[i] = ss.v[i]; ne[i] = ee.v[i]; }
-    } else {
-      unsigned sx = 0, sy = 0;
-#pragma unroll
-      for (int i = 0; i < PART_ITEMS; i++) {
-        const int64_t r = first + i;
-        const bool ok = r < q.n_regions;
-        nc[i] = ok ? q.chrom[r] : -1; ns[i] = ok ? q.start[r] : 1; ne[i] = ok ? q.stop[r] : 1;
-        const unsigned sb = ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+';
-        if (i < 4) sx |= sb << (i * 8); else sy |= sb << ((i & 3) * 8);
-      }
-      nst = make_int2((int)sx, (int)sy);
-    }
+  auto issue = [&](int64_t tile) {                                    // one thread: 4 bulk copies, 53 248 bytes
+    const int64_t first = tile * PART_TILE;
+    mbar_expect_tx(&s_bar, TILE_BYTES);
+    tma_bulk_g2s(s_chrom, q.chrom + first, PART_TILE * 4, &s_bar);
+    tma_bulk_g2s(s_start, q.start + first, PART_TILE * 4, &s_bar);
+    tma_bulk_g2s(s_stop, q.stop + first, PART_TILE * 4, &s_bar);
+    tma_bulk_g2s(s_strand, q.strand + first, PART_TILE, &s_bar);
   };
-  if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+  if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_full) issue(blockIdx.x);
+  uint32_t parity = 0;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- classify, build the element, rank inside the bucket (one shared atomic per query)
-    uint32_t elem[PART_ITEMS], br[PART_ITEMS];                         // br = bucket << 16 | rank  (0xFFFFFFFF: no element)
+    uint32_t elem[PART_ITEMS], br[PART_ITEMS];                         // br = bucket << 16 | rank  (bucket nb4: no element)
     {
       int32_t c[PART_ITEMS], s[PART_ITEMS], e[PART_ITEMS];
-      const int2 stw = nst;
+      uint2 stw;
+      if (tile < n_full) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        const int4 c0 = reinterpret_cast<const int4 *>(s_chrom)[threadIdx.x * 2], c1 = reinterpret_cast<const int4 *>(s_chrom)[threadIdx.x * 2 + 1];
+        const int4 s0 = reinterpret_cast<const int4 *>(s_start)[threadIdx.x * 2], s1 = reinterpret_cast<const int4 *>(s_start)[threadIdx.x * 2 + 1];
+        const int4 e0 = reinterpret_cast<const int4 *>(s_stop)[threadIdx.x * 2], e1 = reinterpret_cast<const int4 *>(s_stop)[threadIdx.x * 2 + 1];
+        stw = reinterpret_cast<const uint2 *>(s_strand)[threadIdx.x];
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+        e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
+      } else {
+        const int64_t first = tile * PART_TILE + (int64_t)threadIdx.x * PART_ITEMS;
+        unsigned sx = 0, sy = 0;
 #pragma unroll
-      for (int i = 0; i < PART_ITEMS; i++) { c[i] = nc[i]; s[i] = ns[i]; e[i] = ne[i]; }
-      if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        for (int i = 0; i < PART_ITEMS; i++) {
+          const int64_t r = first + i;
+          const bool ok = r < q.n_regions;
+          c[i] = ok ? q.chrom[r] : -1; s[i] = ok ? q.start[r] : 1; e[i] = ok ? q.stop[r] : 1;
+          const unsigned sb = ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+';
+          if (i < 4) sx |= sb << (i * 8); else sy |= sb << ((i & 3) * 8);
+        }
+        stw = make_uint2(sx, sy);
+      }
 #pragma unroll
       for (int i = 0; i < PART_ITEMS; i++) {
-        const uint32_t sbyte = ((uint32_t)(i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFFu;
+        const uint32_t sbyte = ((i < 4 ? stw.x : stw.y) >> ((i & 3) * 8)) & 0xFFu;
         const uint32_t d = sbyte - (uint32_t)'+';                                   // '+' -> 0, '-' -> 2
         const bool addressable = (uint32_t)c[i] < n_chrom && (d & ~2u) == 0;        // known chromosome, '+'/'-' strand
         const int4 gt = s_pm[addressable ? 2 * c[i] + (int)(d >> 1) : 0];
@@ -183,7 +204,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
         // enough for the length field, not crossing the end of its bucket
         const bool normal = addressable && s[i] >= 1 && s[i] <= e[i] && s[i] <= gt.x && len <= len_max && lu + len <= ubmask;
         elem[i] = lu | (len << bv.ub);
-        br[i] = 0xFFFFFFFFu;
+        br[i] = nb4 << 16;                                                          // bucket nb4: no element
         if (normal) {
           const uint32_t b = (uint32_t)gt.z + (t >> bv.ub);
           br[i] = (b << 16) | atomicAdd(&s_cnt[b], 1u);
@@ -198,6 +219,8 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
       }
     }
     __syncthreads();
+    // the raw tile has been consumed by every thread: fetch the next one while the rest of this tile is processed
+    if (threadIdx.x == 0 && tile + gridDim.x < n_full) { fence_proxy_async(); issue(tile + gridDim.x); }
 
     // ---- reserve global space: one global atomic per non-empty bucket, one bucket per thread, all
     // issued before anything waits on them; the exclusive scan of the counts runs in their shadow
@@ -262,22 +285,22 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
     // ---- scatter into the staging buffer in bucket order
 #pragma unroll
     for (int i = 0; i < PART_ITEMS; i++) {
-      if (br[i] != 0xFFFFFFFFu) {
-        const uint32_t b = br[i] >> 16;
-        s_stage[s_off[b] + (br[i] & 0xFFFFu)] = make_uint2(elem[i], b);
-      }
+      const uint32_t b = br[i] >> 16;
+      const uint32_t pos = b == nb4 ? (uint32_t)PART_TILE : s_off[b] + (br[i] & 0xFFFFu);    // PART_TILE = trash slot
+      s_stage[pos] = make_uint2(elem[i], b);
     }
     const uint32_t total = s_off[nb4 - 1] + s_cnt[nb4 - 1];
     __syncthreads();
 
     // ---- copy out: consecutive staged elements of a bucket go to consecutive addresses
+#pragma unroll 4
     for (uint32_t p = threadIdx.x; p < total; p += PART_THREADS) {
       const uint2 eb = s_stage[p];
       const uint2 dl = s_dl[eb.y];
       const uint32_t addr = p < dl.y ? p + dl.x : s_g1[eb.y] + (p - dl.y);
       bv.pool[addr] = eb.x;
     }
-    for (uint32_t i = threadIdx.x; i < nb4; i += blockDim.x) s_cnt[i] = 0;
+    for (uint32_t i = threadIdx.x; i < nb4 + 4; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
   }
 }
@@ -532,7 +555,7 @@ int gtb_bucket_prepare(gtb_index *ix) {
   bs->k = k; bs->ub = ub; bs->n_buckets = nb; bs->max_local = max_local;
   bs->count_smem = count_smem_bytes(ub, k, max_local, cov);
   const uint32_t nb4 = (nb + 3) & ~3u;
-  bs->part_smem = (size_t)PART_TILE * 8 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
+  bs->part_smem = (size_t)PART_TILE * 13 + (size_t)PART_TILE * 8 + 64 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
@@ -610,8 +633,8 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p;
 
   const bool cov = ix->op == GTB_OP_COVERAGE;
-  const bool aligned = ((uintptr_t)q.chrom % 32 == 0) && ((uintptr_t)q.start % 32 == 0) && ((uintptr_t)q.stop % 32 == 0) &&
-                       ((uintptr_t)q.strand % 8 == 0);
+  const bool aligned = ((uintptr_t)q.chrom % 16 == 0) && ((uintptr_t)q.start % 16 == 0) && ((uintptr_t)q.stop % 16 == 0) &&
+                       ((uintptr_t)q.strand % 16 == 0);          // TMA bulk copies need 16-byte aligned sources
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
   const unsigned grid1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles));
 #define GTB_PART_LAUNCH(COV, VEC)                                                                                          \
