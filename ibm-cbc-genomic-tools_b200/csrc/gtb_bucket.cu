@@ -54,7 +54,8 @@ struct BucketView {
   uint32_t n_buckets;
   // paged bucket storage
   uint32_t *pool;                   // pages of PAGE elements
-  uint32_t *page_table;             // [n_buckets * pt_stride]  page id + 1, 0 = not allocated yet
+  uint32_t *page_table;             // [n_buckets * pt_stride]  gen << 24 | (page id + 1); an entry counts only if its tag is the batch's
+  uint32_t gen;                     // generation tag of this batch (1..255) -- saves clearing the table per batch
   uint32_t pt_stride;
   uint32_t *cursor;                 // [n_buckets] elements appended so far
   uint32_t *next_page;
@@ -259,12 +260,14 @@ __global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(Query
         const uint32_t b = threadIdx.x + j * PART_THREADS, old = r_old[j];
         const uint32_t p_first = old >> PAGE_SHIFT, p_last = (old + r_cnt[j] - 1) >> PAGE_SHIFT;
         uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
-        if ((old & (PAGE - 1)) == 0) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_first, pid + 1); }
-        if (p_last != p_first) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_last, pid + 1); }
+        const uint32_t tag = bv.gen << 24;
+        if ((old & (PAGE - 1)) == 0) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_first, tag | (pid + 1)); }
+        if (p_last != p_first) { const uint32_t pid = atomicAdd(bv.next_page, 1u); atomicExch(pt + p_last, tag | (pid + 1)); }
         uint32_t id0, id1;
-        while ((id0 = ld_volatile_u32(pt + p_first)) == 0) {}
+        while (((id0 = ld_volatile_u32(pt + p_first)) >> 24) != bv.gen) {}
         id1 = id0;
-        if (p_last != p_first) while ((id1 = ld_volatile_u32(pt + p_last)) == 0) {}
+        if (p_last != p_first) while (((id1 = ld_volatile_u32(pt + p_last)) >> 24) != bv.gen) {}
+        id0 &= 0xFFFFFFu; id1 &= 0xFFFFFFu;
         r_g0[j] = ((id0 - 1) << PAGE_SHIFT) + (old & (PAGE - 1));
         r_g1[j] = (id1 - 1) << PAGE_SHIFT;
         r_split[j] = min(r_cnt[j], PAGE - (old & (PAGE - 1)));
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
         d[r] = make_uint4(0, 0, 0, 0);
         if (v4 < n_v4) {
           const uint32_t pg = (e_begin >> PAGE_SHIFT) + (v4 >> (PAGE_SHIFT - 2));
-          const uint32_t page_id = __ldg(pt + pg) - 1;
+          const uint32_t page_id = (__ldg(pt + pg) & 0xFFFFFFu) - 1;
           d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + ((size_t)page_id << PAGE_SHIFT)) + (v4 & ((PAGE >> 2) - 1)));
         }
       }
@@ -470,6 +473,7 @@ int upload_b(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
 
 struct gtb_bucket_state {
   bool ready = false, failed = false;
+  uint32_t gen = 0;                 // page-table generation tag
   int k = 0, ub = 0;
   uint32_t n_buckets = 0;
   int max_local = 0;
@@ -615,8 +619,12 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   const uint32_t pt_stride = (uint32_t)((n + PAGE - 1) / PAGE + 1);
   const uint64_t n_pages = (n + PAGE - 1) / PAGE + nb + 1;
   GTB_TRY(bs->d_pool.reserve(ctx, (size_t)n_pages * PAGE));
-  GTB_TRY(bs->d_page_table.reserve(ctx, (size_t)nb * pt_stride));
-  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_page_table.p, 0, (size_t)nb * pt_stride * 4, ctx->stream));
+  if (n_pages >= (1u << 24) - 2) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "batch too large for the bucket engine's page table");
+  if (bs->d_page_table.cap < (size_t)nb * pt_stride) { GTB_TRY(bs->d_page_table.reserve(ctx, (size_t)nb * pt_stride)); bs->gen = 255; }
+  if (++bs->gen >= 256) {                                               // new table or tag wrap-around: clear once
+    GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_page_table.p, 0, bs->d_page_table.cap * 4, ctx->stream));
+    bs->gen = 1;
+  }
   GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_cursor.p, 0, (size_t)nb * 4, ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_next_page.p, 0, 4, ctx->stream));
 
@@ -625,7 +633,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   bv.cls_plus = ix->h_class_of[(uint8_t)'+']; bv.cls_minus = ix->h_class_of[(uint8_t)'-'];
   bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p; bv.pm_tab = bs->d_pm.p;
   bv.n_buckets = nb; bv.pool = bs->d_pool.p; bv.page_table = bs->d_page_table.p; bv.pt_stride = pt_stride;
-  bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p;
+  bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p; bv.gen = bs->gen;
   bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
   bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
   RankView rv;

@@ -432,10 +432,7 @@ int gtb_cell_scan_for_finish(gtb_index *ix, CellFinalView *out) {
   gtb_cell_state *cs = ix->cell;
   if (!cs || !cs->ready || !cs->dirty) return GTB_OK;
   gtb_ctx *ctx = ix->ctx;
-  const size_t n = (size_t)cs->cell_planes * cs->n_cells;
-  GTB_CUDA_OK(ctx, cudaMemcpyAsync(cs->d_cells_scan.p, cs->d_cells.p, n * sizeof(ull), cudaMemcpyDeviceToDevice, ctx->stream));
-  for (int p = 0; p < cs->cell_planes; p++)
-    GTB_TRY(gtb_inclusive_scan_u64(ctx, cs->d_cells_scan.p + (size_t)p * cs->n_cells, cs->n_cells, ix->d_scan_scratch));
+  GTB_TRY(gtb_inclusive_scan_planes_u64(ctx, cs->d_cells.p, cs->d_cells_scan.p, cs->n_cells, cs->cell_planes, cs->n_cells, ix->d_scan_scratch));
   out->cells_scan = cs->d_cells_scan.p;
   out->corr = cs->d_corr.p;
   out->slot_cell = cs->d_slot_cell.p;

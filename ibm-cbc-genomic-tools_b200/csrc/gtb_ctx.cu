@@ -131,11 +131,13 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(unsigned long long *d, int64_t n, unsigned long long *tile_totals) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const unsigned long long *src, unsigned long long *d, int64_t n, int64_t plane_stride,
+                                                                   unsigned long long *tile_totals) {
+  src += (int64_t)blockIdx.y * plane_stride; d += (int64_t)blockIdx.y * plane_stride; tile_totals += (int64_t)blockIdx.y * gridDim.x;
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   unsigned long long v[SCAN_ITEMS], sum = 0;
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? d[base + i] : 0ull; sum += v[i]; }
+  for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? src[base + i] : 0ull; sum += v[i]; }
   unsigned long long total;
   unsigned long long ex = block_exclusive_scan(sum, &total);
 #pragma unroll
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(unsigned long 
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(unsigned long long *totals, int64_t n_tiles) {
+  totals += (int64_t)blockIdx.y * n_tiles;
   // one block walks the tile totals in chunks, carrying the running sum (exclusive result in place)
   __shared__ unsigned long long carry;
   if (threadIdx.x == 0) carry = 0;
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(unsigned long
   }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_addback_kernel(unsigned long long *d, int64_t n, const unsigned long long *tile_offsets) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_addback_kernel(unsigned long long *d, int64_t n, int64_t plane_stride, const unsigned long long *tile_offsets) {
+  d += (int64_t)blockIdx.y * plane_stride; tile_offsets += (int64_t)blockIdx.y * gridDim.x;
   const unsigned long long off = tile_offsets[blockIdx.x];
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
   for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS)
@@ -167,14 +171,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_addback_kernel(unsigned lon
 }
 }  // namespace
 
-int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch) {
-  if (n <= 0) return GTB_OK;
+int gtb_inclusive_scan_planes_u64(gtb_ctx *ctx, const unsigned long long *src, unsigned long long *dst, int64_t n, int planes,
+                                    int64_t plane_stride, dbuf<unsigned long long> &scratch) {
+  if (n <= 0 || planes <= 0) return GTB_OK;
   const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  GTB_TRY(scratch.reserve(ctx, (size_t)n_tiles));
-  GTB_LAUNCH(ctx, "scan_tiles", scan_tiles_kernel, (unsigned)n_tiles, SCAN_THREADS, 0, d, n, scratch.p);
+  GTB_TRY(scratch.reserve(ctx, (size_t)n_tiles * planes));
+  GTB_LAUNCH(ctx, "scan_tiles", scan_tiles_kernel, dim3((unsigned)n_tiles, (unsigned)planes), SCAN_THREADS, 0, src, dst, n, plane_stride, scratch.p);
   if (n_tiles > 1) {
-    GTB_LAUNCH(ctx, "scan_totals", scan_totals_kernel, 1, SCAN_THREADS, 0, scratch.p, n_tiles);
-    GTB_LAUNCH(ctx, "scan_addback", scan_addback_kernel, (unsigned)n_tiles, SCAN_THREADS, 0, d, n, scratch.p);
+    GTB_LAUNCH(ctx, "scan_totals", scan_totals_kernel, dim3(1, (unsigned)planes), SCAN_THREADS, 0, scratch.p, n_tiles);
+    GTB_LAUNCH(ctx, "scan_addback", scan_addback_kernel, dim3((unsigned)n_tiles, (unsigned)planes), SCAN_THREADS, 0, dst, n, plane_stride, scratch.p);
   }
   return gtb_check_launch(ctx);
+}
+
+int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch) {
+  return gtb_inclusive_scan_planes_u64(ctx, d, d, n, 1, n, scratch);
 }

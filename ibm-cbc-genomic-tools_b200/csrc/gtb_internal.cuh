@@ -114,3 +114,6 @@ static inline unsigned gtb_grid_for(int64_t n_items, int per_block, int64_t max_
 
 // in-place inclusive prefix sum over n uint64 values on ctx->stream (gtb_scan_util.cu)
 int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch);
+// the same for `planes` arrays of n values spaced plane_stride apart, reading src and writing dst (may alias)
+int gtb_inclusive_scan_planes_u64(gtb_ctx *ctx, const unsigned long long *src, unsigned long long *dst, int64_t n, int planes,
+                                    int64_t plane_stride, dbuf<unsigned long long> &scratch);

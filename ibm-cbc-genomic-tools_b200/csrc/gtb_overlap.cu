@@ -534,12 +534,9 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
   GTB_TRY(gtb_cell_scan_for_finish(ix, &cf));
   cf.t_group = ix->d_t_base.p;
   const int64_t K = std::max<int64_t>(ix->n_slots, 1);
-  // scan a copy so that more batches may still be added after a finish
-  GTB_CUDA_OK(ctx, cudaMemcpyAsync(ix->d_hist_scan.p, ix->d_hist.p, sizeof(ull) * (size_t)ix->planes * (size_t)K,
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
+  // scan into a second buffer so that more batches may still be added after a finish
   if (ix->n_slots > 0)
-    for (int p = 0; p < ix->planes; p++)
-      GTB_TRY(gtb_inclusive_scan_u64(ctx, ix->d_hist_scan.p + (int64_t)p * K, ix->n_slots, ix->d_scan_scratch));
+    GTB_TRY(gtb_inclusive_scan_planes_u64(ctx, ix->d_hist.p, ix->d_hist_scan.p, ix->n_slots, ix->planes, K, ix->d_scan_scratch));
   if (ix->n_regions > 0) {
     const unsigned grid = (unsigned)((ix->n_regions + 255) / 256);
     if (ix->op == GTB_OP_COVERAGE)
