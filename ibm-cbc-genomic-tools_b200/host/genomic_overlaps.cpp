@@ -1,0 +1,213 @@
+// genomic_overlaps -- drop-in driver for `genomic_overlaps count | coverage | density | rpkm` on the B200 engine.
+//
+// Same operations, flags, defaults, usage text, stdout format and exit codes as the reference driver
+// (gtools/genomic_overlaps.cpp:73-261 flags, :408-490 count/coverage/density, :746-775 rpkm); the engine calls
+// GenomicRegionSetOverlaps::CountIndexOverlaps / CalcIndexCoverage are replaced by the C ABI of include/gtb200.h.
+// The other operations of the reference (annotate, bin, dist, intersect, offset, overlap, subset) enumerate
+// pairs and are outside the accelerated path: they are listed for the usage text and refuse to run.
+#include <stdlib.h>
+#include <string.h>
+#include <iostream>
+#include "gt_host.h"
+#include "gtb200.h"
+
+static const char *PROGRAM = "genomic_overlaps";
+static const char *VERSION = "genomic_tools 2.8.1a";
+
+static bool HELP, VERBOSE, IS_SORTED, SORTED_BY_STRAND, IGNORE_STRAND, MATCH_GAPS;
+static const char *BIN_BITS;
+static long MAX_LABEL_VALUE;
+static unsigned long MIN_COUNT;
+static double MIN_RPKM, MIN_DENSITY;
+
+static const char *DETAILS_REGION =
+    "* Input formats: REG, GFF, BED, SAM\n"
+    "  * Operands: region, region-set\n"
+    "  * Region requirements: chromosome/strand-compatible, sorted, non-overlapping\n"
+    "  * Region-set requirements: sorted if -S option is used";
+
+static void check(gtb_ctx *ctx, int rc, const char *what) {
+  if (rc == GTB_OK) return;
+  fprintf(stderr, "\nError: [%s] %s (status %d)\n", what, ctx ? gtb_ctx_last_error(ctx) : "", rc);
+  exit(1);
+}
+
+static gtb_set as_set(const gt::RegionBatch &b) {
+  gtb_set s;
+  s.n_regions = b.n_regions();
+  s.n_intervals = (int64_t)b.chrom.size();
+  s.chrom = b.chrom.data(); s.start = b.start.data(); s.stop = b.stop.data(); s.strand = b.strand.data();
+  s.weight = b.weight.empty() ? nullptr : b.weight.data();
+  s.region_offset = b.multi ? b.offset.data() : nullptr;
+  return s;
+}
+
+int main(int argc, char *argv[]) {
+  gt::CmdLine cmd(PROGRAM, VERSION);
+  const char *USAGE = "[OPTIONS] REFERENCE-REGION-FILE <TEST-REGION-FILE>";
+  cmd.AddOperation("annotate", USAGE, "Annotates test regions according to reference regions.", "");
+  cmd.AddOperation("bin", USAGE, "Finds overlaps of interval pairs with reference regions.", "");
+  cmd.AddOperation("count", USAGE, "Counts the number of overlapping test regions per reference region.", DETAILS_REGION);
+  cmd.AddOperation("coverage", USAGE, "Calculates the depth coverage (i.e. the total number of overlapping nucleotides) per reference region.", DETAILS_REGION);
+  cmd.AddOperation("density", USAGE, "Computes the density (i.e. the coverage divided by the size of the reference region) of overlaps per reference region.", DETAILS_REGION);
+  cmd.AddOperation("dist", USAGE, "Computes the distance between a pair of intervals given breakpoints in reference file (e.g. restriction enzyme sites) [UNDER DEVELOPMENT].", "");
+  cmd.AddOperation("intersect", USAGE, "Computes the intersection between all pairs of test and reference regions. Results are grouped by test region.", "");
+  cmd.AddOperation("offset", USAGE, "Computes the distances of test regions from their overlapping reference regions.", "");
+  cmd.AddOperation("overlap", USAGE, "Finds the overlaps between all pairs of test and reference regions. Results are grouped by test region.", "");
+  cmd.AddOperation("rpkm", USAGE, "Computing reference region RPKM values.", DETAILS_REGION);
+  cmd.AddOperation("subset", USAGE, "Picks a subset of test regions depending on their overlap with reference regions. Results are grouped by test region.", "");
+  if (argc < 2) {
+    cmd.OperationSummary("OPERATION [OPTIONS] REFERENCE-REGION-FILE <TEST-REGION-FILE>",
+                         "Performs overlap operations between a test and a reference set of genomic regions.");
+    exit(1);
+  }
+  std::string op = argv[1];
+  if (op[0] == '-') op = op.substr(1);                                // compatibility with the previous version (genomic_overlaps.cpp:181)
+  cmd.SetCurrentOperation(op);
+  cmd.AddOption("--help", &HELP, false, "help");
+  cmd.AddOption("-h", &HELP, false, "help");
+  cmd.AddOption("-v", &VERBOSE, false, "verbose mode");
+  cmd.AddOption("-B", &BIN_BITS, "17,20,23,26", "number of shift-bits for each bin level");
+  cmd.AddOption("-S", &IS_SORTED, false, "test and reference regions are sorted by chromosome and start position");
+  cmd.AddOption("-s", &SORTED_BY_STRAND, false, "test and reference regions are also sorted by strand (-S must be set)");
+  cmd.AddOption("-i", &IGNORE_STRAND, false, "ignore strand while finding overlaps");
+  if (op == "count") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("--max-label-value", &MAX_LABEL_VALUE, 1L, "maximum region label value to be used");
+    cmd.AddOption("-min", &MIN_COUNT, 0UL, "minimum count");
+  } else if (op == "coverage") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("--max-label-value", &MAX_LABEL_VALUE, 1L, "maximum region label value to be used");
+    cmd.AddOption("-min", &MIN_COUNT, 0UL, "minimum coverage");
+  } else if (op == "density") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("--max-label-value", &MAX_LABEL_VALUE, 1L, "maximum region label value to be used");
+    cmd.AddOption("-min", &MIN_DENSITY, 0.0, "minimum density");
+  } else if (op == "rpkm") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("--max-label-value", &MAX_LABEL_VALUE, 1L, "maximum region label value to be used");
+    cmd.AddOption("-min", &MIN_RPKM, 0.0, "minimum RPKM");
+  } else if (cmd.HasOperation(op)) {
+    std::cerr << "Operation '" << op << "' is outside the GPU-accelerated path of this build (count, coverage, density, rpkm are available)!\n";
+    exit(1);
+  } else {
+    std::cerr << "Unknown operation '" << op << "'!\n";
+    exit(1);
+  }
+  const int next_arg = cmd.Read(argv + 1, argc - 1) + 1;
+  if (HELP || argc - next_arg < 1) { cmd.OperationUsage(); exit(1); }
+  if (IS_SORTED && SORTED_BY_STRAND && IGNORE_STRAND) {
+    fprintf(stderr, "[Error]: the input is sorted by chromosome/strand/start (i.e. -S and -s are set), therefore the overlap algorithm can only report strand-specific results (i.e. -i cannot be set)!\n");
+    exit(1);
+  }
+  const char *ref_file = argv[next_arg];
+  const char *test_file = next_arg + 1 == argc ? nullptr : argv[next_arg + 1];
+
+  // ---- reference (index) set: loaded in memory, labels kept for the output
+  gt::ChromTable chroms;
+  gt::RegionBatch ref;
+  {
+    gt::RegionReader rr(ref_file, &chroms, true, 1);
+    rr.Read(&ref, INT64_MAX);
+    if (VERBOSE) std::cerr << "Reading from '" << ref_file << "'; number of regions = " << ref.n_regions() << "; format = " << rr.format() << "\n";
+  }
+  if (IS_SORTED) {
+    gt::SortChecker sc; sc.by_strand = SORTED_BY_STRAND;
+    for (int64_t k = 0; k < ref.n_regions(); k++) {
+      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line[k], "index regions should be compatible, sorted and non-overlapping!");
+      const int64_t i = ref.offset[k];
+      if (!sc.Accept(chroms.name[ref.chrom[i]], (char)ref.strand[i], ref.start[i]))
+        gt::die_line(ref.line[k], std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+    }
+  }
+
+  gtb_ctx *ctx = nullptr;
+  int rc = gtb_ctx_create(0, &ctx);
+  if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
+  const bool want_coverage = op == "coverage" || op == "density";
+  const unsigned flags = (MATCH_GAPS ? GTB_MATCH_GAPS : 0u) | (IGNORE_STRAND ? GTB_IGNORE_STRAND : 0u);
+  gtb_index *index = nullptr;
+  int64_t err_index = -1;
+  gtb_set ref_set = as_set(ref);
+  ref_set.weight = nullptr;
+  rc = gtb_index_create(ctx, &ref_set, want_coverage ? GTB_OP_COVERAGE : GTB_OP_COUNT, flags, &index, &err_index);
+  if (rc == GTB_ERR_INDEX_REGION) gt::die_line(ref.line[err_index], "index regions should be compatible, sorted and non-overlapping!");
+  check(ctx, rc, "gtb_index_create");
+
+  // ---- test (query) set: streamed in chunks; parsing of chunk k+1 overlaps the device work of chunk k
+  const int64_t CHUNK = 4 << 20;
+  gt::RegionBatch chunk[2];
+  std::vector<long> chunk_first_line;                                  // to translate a query index into a line number
+  std::vector<int64_t> chunk_first_index;
+  std::vector<std::vector<long>> chunk_lines;
+  {
+    gt::RegionReader qr(test_file, &chroms, false, MAX_LABEL_VALUE);
+    if (VERBOSE) std::cerr << "Reading from '" << (test_file ? test_file : "<standard input>") << "'; format = " << qr.format() << "\n";
+    gt::SortChecker sc; sc.by_strand = SORTED_BY_STRAND;
+    int which = 0;
+    int64_t seen = 0;
+    for (;;) {
+      gt::RegionBatch &b = chunk[which];
+      check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");     // the buffer about to be overwritten has been consumed
+      if (qr.Read(&b, CHUNK) == 0) break;
+      if (IS_SORTED)
+        for (int64_t k = 0; k < b.n_regions(); k++) {
+          const int64_t i = b.offset[k];
+          if (!gt::RegionWellFormed(b, k)) gt::die_line(b.line[k], "query regions should be compatible, sorted and non-overlapping!");
+          if (!sc.Accept(chroms.name[b.chrom[i]], (char)b.strand[i], b.start[i]))
+            gt::die_line(b.line[k], std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+        }
+      gtb_set qs = as_set(b);
+      check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");
+      chunk_first_index.push_back(seen);
+      chunk_lines.push_back(b.line);
+      seen += b.n_regions();
+      which ^= 1;
+    }
+  }
+  std::vector<uint64_t> values((size_t)std::max<int64_t>(ref.n_regions(), 1));
+  rc = gtb_index_finish(index, values.data(), GTB_MEM_HOST, &err_index);
+  if (rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION) {
+    long line = 0;
+    for (size_t c = 0; c < chunk_first_index.size(); c++)
+      if (err_index >= chunk_first_index[c] && err_index < chunk_first_index[c] + (int64_t)chunk_lines[c].size())
+        line = chunk_lines[c][(size_t)(err_index - chunk_first_index[c])];
+    gt::die_line(line, rc == GTB_ERR_QUERY_STOP_NONPOSITIVE ? "stop position must be positive!"
+                       : rc == GTB_ERR_QUERY_START_GT_STOP ? "start position cannot be greater than stop position!"
+                                                            : "query regions should be compatible, sorted and non-overlapping!");
+  }
+  check(ctx, rc, "gtb_index_finish");
+
+  // ---- output, reference-file order (genomic_overlaps.cpp:420-427, :449-455, :476-486, :763-772)
+  auto region_size = [&](int64_t k, bool skip_gaps) -> long {        // GenomicRegion::GetSize, genomic_intervals.cpp:1047-1055
+    const int64_t lo = ref.offset[k], hi = ref.offset[k + 1];
+    if (!skip_gaps) return (long)ref.stop[hi - 1] - (long)ref.start[lo] + 1;
+    size_t size = 0;
+    for (int64_t i = lo; i < hi; i++) size += ref.start[i] > ref.stop[i] ? 0 : (size_t)((long)ref.stop[i] - (long)ref.start[i] + 1);
+    return (long)size;
+  };
+  if (op == "count" || op == "coverage") {
+    for (int64_t k = 0; k < ref.n_regions(); k++)
+      if (values[k] >= MIN_COUNT) printf("%s\t%lu\n", ref.label[k].c_str(), (unsigned long)values[k]);
+  } else if (op == "density") {
+    for (int64_t k = 0; k < ref.n_regions(); k++) {
+      const long size = region_size(k, !MATCH_GAPS);
+      const double density = (double)values[k] / size;
+      if (density >= MIN_DENSITY) printf("%s\t%.4e\n", ref.label[k].c_str(), density);
+    }
+  } else {  // rpkm
+    unsigned long nreads = 0;
+    for (int64_t k = 0; k < ref.n_regions(); k++) nreads += values[k];
+    if (VERBOSE) fprintf(stderr, "* %lu reads overlap reference regions.\n", nreads);
+    const double mreads = (double)nreads / 1000000;
+    for (int64_t k = 0; k < ref.n_regions(); k++) {
+      // the reference filters on MIN_COUNT here, which its rpkm branch never sets (0): every region is printed
+      const long eff_len = region_size(k, !MATCH_GAPS);
+      const double rpkm = eff_len <= 0 ? 0.0 / 0.0 : (double)1000 * values[k] / eff_len / mreads;
+      printf("%s\t%.4e\n", ref.label[k].c_str(), rpkm);
+    }
+  }
+  gtb_index_destroy(index);
+  gtb_ctx_destroy(ctx);
+  return 0;
+}
