@@ -1,0 +1,271 @@
+"""Drop-in parity of the host drivers: `genomic_overlaps count|coverage|density|rpkm` and `genomic_scans counts`
+of this repo (C++ host + CUDA engine) against the reference binaries built into oracle/_ref/ -- stdout
+byte-for-byte and exit codes, over the flag combinations and input formats of SURVEY.md section 8a'.
+Needs a GPU (the drivers have no CPU path) and the reference binaries (they travel with the snapshot)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import randcases
+import support
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(support.ROOT, "ibm-cbc-genomic-tools_b200", "bin")
+NAMES = randcases.NAMES
+
+
+def run_new(tool, args, stdin=None):
+    p = subprocess.run([os.path.join(BIN, tool)] + [str(a) for a in args], input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return p.returncode, p.stdout, p.stderr
+
+
+def both(tool, args, stdin=None):
+    if not support.have_ref():
+        pytest.skip("reference binaries not built (oracle/_ref)")
+    want = support.run_ref(tool, args, stdin=stdin, check=False)
+    got = run_new(tool, args, stdin=stdin)
+    return want, got
+
+
+def assert_same(tool, args, stdin=None, nonempty=False):
+    want, got = both(tool, args, stdin)
+    assert got[0] == want[0], (args, got[2][-300:], want[2][-300:])
+    assert got[1] == want[1], (args, got[1][:300], want[1][:300])
+    if nonempty:
+        assert len(want[1]) > 0, args
+    return want
+
+
+# ------------------------------------------------------------------------------------------------
+# the hand-derived known-answer test of SURVEY.md section 8c
+# ------------------------------------------------------------------------------------------------
+KAT_REF = ("chr1\t100\t200\tgA\t0\t+\n"
+           "chr1\t150\t400\tgB\t0\t-\n"
+           "chr1\t1000\t2000\tgD\t0\t+\t1000\t2000\t0\t2\t100,100\t0,900\n")
+KAT_REF_GFF = "chr2\tsrc\tgene\t11\t20\t.\t.\t.\tgC\n"
+KAT_TEST = ("chr1\t190\t210\t5\t0\t+\n"
+            "chr1\t199\t200\t7\t0\t-\n"
+            "chr1\t200\t201\t2\t0\t+\n"
+            "chr3\t1\t5\tx\t0\t+\n"
+            "chr2\t19\t25\t3\t0\t+\n"
+            "chr1\t1200\t1300\t4\t0\t+\n"
+            "chr1\t1050\t1950\t9\t0\t+\t1050\t1950\t0\t2\t10,10\t0,890\n"
+            "chr1\t100\t200\tdropped\t0\t+")            # no trailing newline: dropped by the reference
+
+
+@pytest.fixture(scope="module")
+def kat(tmp_path_factory):
+    d = tmp_path_factory.mktemp("kat")
+    (d / "ref.bed").write_text(KAT_REF)
+    (d / "ref.gff").write_text(KAT_REF_GFF)
+    (d / "test.bed").write_text(KAT_TEST)
+    return d
+
+
+@pytest.mark.parametrize("op", ["count", "coverage", "density", "rpkm"])
+@pytest.mark.parametrize("flags", [[], ["-i"], ["-gaps"], ["-gaps", "-i"], ["--max-label-value", "6"], ["-min", "1"]])
+def test_kat(kat, op, flags):
+    if op in ("rpkm", "density") and flags == ["-min", "1"]:
+        flags = ["-min", "0.05"]
+    want = assert_same("genomic_overlaps", [op] + flags + [kat / "ref.bed", kat / "test.bed"], nonempty=True)
+    if op == "count" and flags == []:
+        assert want[1] == b"gA\t1\ngB\t1\ngD\t1\n"
+    if op == "coverage" and flags == []:
+        assert want[1] == b"gA\t10\ngB\t1\ngD\t20\n"
+
+
+def test_kat_gff_strand(kat):
+    assert_same("genomic_overlaps", ["count", kat / "ref.gff", kat / "test.bed"])
+    assert_same("genomic_overlaps", ["count", "-i", kat / "ref.gff", kat / "test.bed"])
+    assert_same("genomic_overlaps", ["density", "-i", kat / "ref.gff", kat / "test.bed"])
+
+
+def test_stdin_and_legacy_dash(kat):
+    data = (kat / "test.bed").read_bytes()
+    assert_same("genomic_overlaps", ["-count", kat / "ref.bed"], stdin=data, nonempty=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised files in every supported format
+# ------------------------------------------------------------------------------------------------
+def write_gff(path, s, names, labels):
+    with open(path, "w") as f:
+        for k in range(len(s["chrom"])):
+            f.write("\t".join([names[s["chrom"][k]], "src", "feat", str(int(s["start"][k])), str(int(s["stop"][k])), ".",
+                               chr(int(s["strand"][k])), ".", labels[k]]) + "\n")
+
+
+def write_bed12(path, s, off, names, labels):
+    with open(path, "w") as f:
+        for k in range(len(off) - 1):
+            lo, hi = off[k], off[k + 1]
+            st, en = int(s["start"][lo]) - 1, int(s["stop"][hi - 1])
+            sizes = ",".join(str(int(s["stop"][i]) - int(s["start"][i]) + 1) for i in range(lo, hi))
+            starts = ",".join(str(int(s["start"][i]) - 1 - st) for i in range(lo, hi))
+            f.write("\t".join([names[s["chrom"][lo]], str(st), str(en), labels[k], "0", chr(int(s["strand"][lo])), str(st), str(en), "0",
+                               str(hi - lo), sizes, starts]) + "\n")
+
+
+def gz(path):
+    with open(path, "rb") as f, gzip.open(str(path) + ".gz", "wb") as g:
+        g.write(f.read())
+    return str(path) + ".gz"
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("rand")
+    rng = np.random.default_rng(77)
+    out = {}
+    idx = randcases.rand_single(rng, 400)
+    q = randcases.rand_single(rng, 30000, n_chrom=5)
+    ilab = ["g%d" % k for k in range(400)]
+    qlab = [str(int(v)) for v in rng.integers(-3, 12, size=30000)]
+    support.write_bed(d / "idx.bed", idx, NAMES, ilab)
+    support.write_bed(d / "idx_space.bed", idx, NAMES, ilab, sep=" ")
+    support.write_reg(d / "idx.reg", idx, NAMES, ilab)
+    write_gff(d / "idx.gff", idx, NAMES, ilab)
+    support.write_bed(d / "q.bed", q, NAMES, qlab)
+    support.write_reg(d / "q.reg", q, NAMES, qlab)
+    write_gff(d / "q.gff", q, NAMES, qlab)
+    out["qgz"] = gz(d / "q.bed")
+    out["igz"] = gz(d / "idx.bed")
+    midx, moff = randcases.rand_multi(rng, 300)
+    mq, mqoff = randcases.rand_multi(rng, 20000)
+    write_bed12(d / "midx.bed", midx, moff, NAMES, ["m%d" % k for k in range(300)])
+    support.write_reg(d / "midx.reg", midx, NAMES, ["m%d" % k for k in range(300)], offsets=moff)
+    write_bed12(d / "mq.bed", mq, mqoff, NAMES, [str(k % 7) for k in range(20000)])
+    support.write_reg(d / "mq.reg", mq, NAMES, [str(k % 7) for k in range(20000)], offsets=mqoff)
+    # sorted copies for -S (LC_ALL=C sort -k1,1 -k2,2n == strcmp(chrom), start)
+    for name in ("idx.bed", "q.bed"):
+        env = dict(os.environ, LC_ALL="C")
+        with open(d / ("s_" + name), "wb") as f:
+            subprocess.check_call(["sort", "-k1,1", "-k2,2n", str(d / name)], stdout=f, env=env)
+        with open(d / ("ss_" + name), "wb") as f:
+            subprocess.check_call(["sort", "-k1,1", "-k6,6", "-k2,2n", str(d / name)], stdout=f, env=env)
+    out["dir"] = d
+    return out
+
+
+@pytest.mark.parametrize("op", ["count", "coverage", "density"])
+@pytest.mark.parametrize("pair", [("idx.bed", "q.bed"), ("idx_space.bed", "q.reg"), ("idx.reg", "q.gff"), ("idx.gff", "q.bed"),
+                                  ("idx.bed.gz", "q.bed.gz"), ("midx.bed", "mq.bed"), ("midx.reg", "mq.reg"), ("midx.bed", "q.bed"),
+                                  ("idx.bed", "mq.reg")])
+@pytest.mark.parametrize("flags", [[], ["-i"], ["-gaps"], ["--max-label-value", "5", "-i"]])
+def test_random_files(files, op, pair, flags):
+    d = files["dir"]
+    assert_same("genomic_overlaps", [op] + flags + [d / pair[0], d / pair[1]], nonempty=True)
+
+
+@pytest.mark.parametrize("op", ["count", "coverage"])
+def test_sorted_flags(files, op):
+    d = files["dir"]
+    assert_same("genomic_overlaps", [op, "-S", d / "s_idx.bed", d / "s_q.bed"], nonempty=True)
+    assert_same("genomic_overlaps", [op, "-S", "-s", d / "ss_idx.bed", d / "ss_q.bed"], nonempty=True)
+    assert_same("genomic_overlaps", [op, "-S", "-i", d / "s_idx.bed", d / "s_q.bed"], nonempty=True)
+    assert_same("genomic_overlaps", [op, "-min", "40", d / "idx.bed", d / "q.bed"])
+    # toggling semantics of boolean flags (core.cpp:2212): -i -i == no -i
+    assert_same("genomic_overlaps", [op, "-i", "-i", d / "idx.bed", d / "q.bed"], nonempty=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# error paths: same exit code, nothing on stdout
+# ------------------------------------------------------------------------------------------------
+def test_errors(files, tmp_path):
+    d = files["dir"]
+    (tmp_path / "bad_stop.bed").write_text("chr1\t5\t20\ta\t0\t+\nchr1\t-10\t-3\tb\t0\t+\nchr1\t7\t9\tc\t0\t+\n")
+    (tmp_path / "bad_order.bed").write_text("chr1\t5\t20\ta\t0\t+\nchr1\t30\t10\tb\t0\t+\n")
+    (tmp_path / "bad_strand.bed").write_text("chr1\t5\t20\ta\t0\t?\n")
+    (tmp_path / "other_chrom_bad.bed").write_text("chrZ\t30\t10\tb\t0\t+\nchr1\t5\t20\ta\t0\t+\n")
+    (tmp_path / "empty.bed").write_text("")
+    for bad in ("bad_stop.bed", "bad_order.bed", "bad_strand.bed", "other_chrom_bad.bed", "empty.bed"):
+        for op in ("count", "coverage"):
+            want, got = both("genomic_overlaps", [op, d / "idx.bed", tmp_path / bad])
+            assert got[0] == want[0], (bad, op, got, want)
+            assert got[1] == want[1], (bad, op)
+    # unsorted input under -S is fatal
+    want, got = both("genomic_overlaps", ["count", "-S", d / "s_idx.bed", d / "q.bed"])
+    assert got[0] == want[0] == 1 and got[1] == want[1] == b""
+    want, got = both("genomic_overlaps", ["count", "-S", "-s", "-i", d / "s_idx.bed", d / "s_q.bed"])
+    assert got[0] == want[0] == 1 and got[1] == want[1]
+    want, got = both("genomic_overlaps", ["count", "-nonsense", d / "idx.bed", d / "q.bed"])
+    assert got[0] == want[0] and got[1] == want[1]
+    # invalid index regions are skipped silently: value 0 for count, omitted for density
+    (tmp_path / "idx_bad.bed").write_text("chr1\t5\t20\ta\t0\t+\nchr1\t30\t10\tb\t0\t+\nchr1\t-9\t-2\tc\t0\t+\nchr1\t-5\t50\td\t0\t+\n")
+    for op in ("count", "coverage", "density"):
+        assert_same("genomic_overlaps", [op, tmp_path / "idx_bad.bed", d / "q.bed"], nonempty=True)
+
+
+def test_usage_text():
+    for args in ([], ["count"], ["count", "-h"], ["density", "--help"], ["rpkm"], ["bogus"]):
+        want, got = both("genomic_overlaps", args)
+        assert got[0] == want[0] and got[1] == want[1], args
+    for args in ([], ["counts", "-h"], ["bogus"]):
+        want, got = both("genomic_scans", args)
+        assert got[0] == want[0] and got[1] == want[1], args
+
+
+# ------------------------------------------------------------------------------------------------
+# genomic_scans counts
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def scanfiles(tmp_path_factory):
+    d = tmp_path_factory.mktemp("scan")
+    rng = np.random.default_rng(5)
+    lens = {"chr1": 30000, "chr10": 21000, "chr2": 777, "chrM": 120, "chrX": 9000}
+    with open(d / "genome.bed", "w") as f:
+        for n in ("chrX", "chr1", "chr2", "chr10", "chrM"):                    # deliberately not in sorted order
+            f.write("%s\t0\t%d\n" % (n, lens[n]))
+    n = 40000
+    chrom = rng.integers(0, 5, size=n).astype(np.int32)
+    L = np.array([lens[x] for x in NAMES])[chrom]
+    start = (rng.integers(0, 1 << 30, size=n) % (L + 200) - 50).astype(np.int32)   # some reads start < 1 or beyond the end
+    stop = (start + rng.integers(0, 90, size=n)).astype(np.int32)
+    ok = stop > 0
+    reads = {"chrom": chrom[ok], "start": np.maximum(start[ok], -20), "stop": stop[ok], "strand": np.where(rng.integers(0, 2, size=ok.sum()) == 1, ord("-"), ord("+")).astype(np.int8)}
+    names6 = NAMES + ["chrUn"]
+    reads["chrom"][::97] = 5                                                    # a chromosome the genome file lacks
+    labels = [str(int(v)) for v in rng.integers(0, 9, size=len(reads["chrom"]))]
+    support.write_bed(d / "reads.bed", reads, names6, labels)
+    gz(d / "reads.bed")
+    ref = randcases.rand_single(rng, 60, n_chrom=5, span=20000, max_len=900)
+    support.write_bed(d / "ref.bed", ref, NAMES, ["r%d" % k for k in range(60)])
+    env = dict(os.environ, LC_ALL="C")
+    valid = (reads["start"] >= 1)
+    vr = {k: v[valid] for k, v in reads.items()}
+    vr["chrom"] = np.where(vr["chrom"] == 5, 0, vr["chrom"]).astype(np.int32)
+    support.write_bed(d / "valid.bed", vr, NAMES, [labels[i] for i in np.nonzero(valid)[0]])
+    with open(d / "s_valid.bed", "wb") as f:
+        subprocess.check_call(["sort", "-k1,1", "-k6,6", "-k2,2n", str(d / "valid.bed")], stdout=f, env=env)
+    with open(d / "si_valid.bed", "wb") as f:
+        subprocess.check_call(["sort", "-k1,1", "-k2,2n", str(d / "valid.bed")], stdout=f, env=env)
+    return d
+
+
+@pytest.mark.parametrize("flags", [["-w", "200", "-d", "50", "-min", "3"], ["-w", "200", "-d", "50", "-min", "1", "-i"],
+                                   ["-min", "5"], ["-w", "100", "-d", "100", "-min", "0"], ["-w", "300", "-d", "100", "-op", "c", "-min", "2"],
+                                   ["-w", "200", "-d", "50", "-min", "4", "--max-label-value", "6"],
+                                   ["-w", "1000", "-d", "250", "-min", "1"]])
+def test_scans_counts(scanfiles, flags):
+    d = scanfiles
+    assert_same("genomic_scans", ["counts", "-g", d / "genome.bed"] + flags + [d / "reads.bed"], nonempty=True)
+
+
+def test_scans_variants(scanfiles):
+    d = scanfiles
+    base = ["counts", "-g", d / "genome.bed", "-w", "200", "-d", "50", "-min", "2"]
+    assert_same("genomic_scans", base + [d / "reads.bed.gz"], nonempty=True)
+    assert_same("genomic_scans", base, stdin=(d / "reads.bed").read_bytes(), nonempty=True)
+    assert_same("genomic_scans", base + ["-r", d / "ref.bed", d / "reads.bed"], nonempty=True)
+    assert_same("genomic_scans", base + ["-i", "-r", d / "ref.bed", d / "reads.bed"], nonempty=True)
+    assert_same("genomic_scans", base + ["-S", d / "s_valid.bed"], nonempty=True)
+    assert_same("genomic_scans", base + ["-S", "-i", d / "si_valid.bed"], nonempty=True)
+    # fatal conditions
+    for args in (["counts", "-w", "200", "-d", "30", "-g", d / "genome.bed", d / "reads.bed"], ["counts", d / "reads.bed"],
+                 ["counts", "-g", d / "genome.bed", "-S", d / "valid.bed"]):
+        want, got = both("genomic_scans", args)
+        assert got[0] == want[0] and got[1] == want[1], args
