@@ -83,9 +83,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_port(regions, sample=2_000_000):
-    """Oracle (scalar C port of the reference engine) on one host core, bounded sample."""
+def run_ref_engine(regions, reads_per_core, first_step, cores):
+    """The UNMODIFIED reference engine (oracle/_ref/ref_engine: CountIndexOverlaps over in-memory sets) on `cores`
+    processes, each on its own slice of the read stream.  Returns (reads processed, seconds = slowest process)."""
+    import tempfile
     import support
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_engine")
+    tmp = tempfile.mkdtemp(prefix="gtb_ref_")
+    rf = os.path.join(tmp, "regions.bed")
+    support.write_bed(rf, regions, support.HG19_NAMES)
+    procs = [subprocess.Popen([exe, rf, str(SEED_READS), str((first_step * cores + p) * reads_per_core), str(reads_per_core), str(READ_LEN)],
+                              stdout=subprocess.PIPE, text=True) for p in range(cores)]
+    outs = [p.communicate()[0] for p in procs]
+    secs = [float(json.loads(o.strip().splitlines()[-1])["engine_seconds"]) for o in outs]
+    return reads_per_core * cores, max(secs)
+
+
+def cpu_baseline(regions):
+    """CPU path beside the GPU number: the reference's own engine on all host cores (kind "reference") when its
+    binary travelled with the snapshot, else the scalar C port of the oracle on one core (kind "port").
+    Bounded sample of the same workload, ~10-30 s of CPU work."""
+    import support
+    cores = os.cpu_count() or 1
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_engine")):
+        per_core = 1_500_000
+        n, secs = run_ref_engine(regions, per_core, 0, cores)
+        return {"value": n / secs, "unit": "query intervals/s", "cores": cores, "kind": "reference",
+                "sample": "%d reads per core x %d cores of the %d-read stream vs all %d regions; UnsortedGenomicRegionSetOverlaps + "
+                          "CountIndexOverlaps only (sets pre-parsed in memory, no text parsing)" % (per_core, cores, N_READS, N_REGIONS)}
+    sample = 40_000_000
     orc = support.Oracle()
     reads = support.synth_reads(sample, SEED_READS)
     t0 = time.perf_counter()
@@ -110,17 +136,10 @@ def run_reference(args):
     kind = "reference" if os.path.exists(exe) else "port"
     times = []
     if kind == "reference":
-        import tempfile
-        tmp = tempfile.mkdtemp(prefix="gtb_ref_")
-        rf = os.path.join(tmp, "regions.bed")
-        support.write_bed(rf, regions, support.HG19_NAMES)
         for step in range(args.warmup + args.steps):
-            procs = [subprocess.Popen([exe, rf, str(SEED_READS), str((step * cores + p) * sample), str(sample), str(READ_LEN)],
-                                      stdout=subprocess.PIPE, text=True) for p in range(cores)]
-            outs = [p.communicate()[0] for p in procs]
-            secs = [float(json.loads(o.strip().splitlines()[-1])["engine_seconds"]) for o in outs]
+            _, secs = run_ref_engine(regions, sample, step, cores)
             if step >= args.warmup:
-                times.append(max(secs))
+                times.append(secs)
     else:
         orc = support.Oracle()
         cores = 1
@@ -178,20 +197,66 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "cell": gtb200.ENGINE_CELL, "bucket": gtb200.ENGINE_BUCKET, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
-    index = gtb200.Index(ctx, regions, gtb200.OP_COUNT, engine)
 
     dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
            "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
-    ctx.synth_reads(SEED_READS, rank * n, n, READ_LEN, support.HG19_LENS, dev)     # rank r streams reads [r*n, (r+1)*n)
-    dset, keep = gtb200.device_set(dev)
     out_dev = torch.zeros(N_REGIONS, dtype=torch.int64, device="cuda")
+    sharding = {}
+    if world == 1:
+        index = gtb200.Index(ctx, regions, gtb200.OP_COUNT, engine)
+        ctx.synth_reads(SEED_READS, 0, n, READ_LEN, support.HG19_LENS, dev)
+        dset, keep = gtb200.device_set(dev)
+        n_local = n
 
-    def step_device():
-        index.reset()
-        index.add_set(dset, gtb200.MEM_DEVICE)
-        index.finish_ptr(out_dev.data_ptr(), gtb200.MEM_DEVICE)
-        if dist is not None:
-            dist.all_reduce(out_dev)                     # the single collective: per-region partial counts
+        def step_device():
+            index.reset()
+            index.add_set(dset, gtb200.MEM_DEVICE)
+            index.finish_ptr(out_dev.data_ptr(), gtb200.MEM_DEVICE)
+            return out_dev
+    else:
+        # Genome-sharded: rank r owns a contiguous (chromosome, coordinate) range holding 1/world of the
+        # read mass and every region whose span starts there; its n reads are drawn inside that range (weak scaling).
+        # Reads that reach regions owned by a neighbour are replicated to it once, at ingest (untimed, like parsing);
+        # a step then has no data-path exchange besides the final all-gather of per-region counts.
+        from gtb200 import sharded
+        plan = sharded.ShardPlan(regions, world, chrom_extent=support.HG19_LENS)
+        eff = np.maximum(support.HG19_LENS - READ_LEN + 1, 0)
+        cum_eff = np.concatenate([[0], np.cumsum(eff)]).astype(np.int64)
+        P = [0] + [int(cum_eff[c] + min(max(pos - 1, 0), int(eff[c]))) for c, pos in plan.cut_positions()] + [int(cum_eff[-1])]
+        ctx.synth_reads(SEED_READS, rank * n, n, READ_LEN, support.HG19_LENS, dev, p_range=(P[rank], P[rank + 1]))
+        send = {}
+        for s_ in range(world):
+            if s_ == rank:
+                continue
+            ids = torch.nonzero(sharded.route_mask_torch(plan, dev, s_)).flatten()
+            send[s_] = {k: v[ids].cpu().numpy() for k, v in dev.items()}
+        own_mask_ok = bool(sharded.route_mask_torch(plan, dev, rank).sum().item() <= n)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, send)
+        halo = [gathered[r][rank] for r in range(world) if r != rank and rank in gathered[r]]
+        n_halo = sum(len(h["chrom"]) for h in halo)
+        own = dev
+        dev = {k: torch.cat([own[k]] + [torch.from_numpy(h[k]).cuda() for h in halo]) for k in own}
+        n_local = n + n_halo
+        dset, keep = gtb200.device_set(dev)
+        sh = sharded.ShardedDeviceOverlap(ctx, regions, plan, gtb200.OP_COUNT, engine)
+
+        def step_device():
+            return sh.step(dset, gtb200.MEM_DEVICE)
+
+        # cross-check (untimed): the query-sharded decomposition -- every rank counts its OWN reads against ALL regions,
+        # one sum-reduction -- must give the same per-region counts as ownership + gather
+        full = gtb200.Index(ctx, regions, gtb200.OP_COUNT, engine)
+        own_set, keep_own = gtb200.device_set(own)
+        full.add_set(own_set, gtb200.MEM_DEVICE)
+        full.finish_ptr(out_dev.data_ptr(), gtb200.MEM_DEVICE)
+        dist.all_reduce(out_dev)
+        got = step_device()
+        sharding = {"decomposition": "genome ranges, region ownership, all-gather", "halo_reads_this_rank": n_halo,
+                    "owned_regions_this_rank": int(len(plan.owned[rank])),
+                    "matches_query_sharded_allreduce": bool(torch.equal(got, out_dev)) and own_mask_ok}
+        full.close()
+        index = sh.index
 
     def barrier():
         if dist is not None:
@@ -218,7 +283,7 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
-    counts_check = int(out_dev.sum().item())
+    counts_check = int(step_device().sum().item())
 
     # ---- per-kernel CUDA-event profile for the roofline (outside the timed region) -------------------
     ctx.profile(True)
@@ -241,20 +306,19 @@ def main():
 
     # ---- end to end through the C ABI with host buffers (`e2e`) -------------------------------------
     n_e2e = n
-    host = {k: torch.empty(n_e2e, dtype=v.dtype).pin_memory() for k, v in dev.items()}
+    host = {k: torch.empty(n_local, dtype=v.dtype).pin_memory() for k, v in dev.items()}
     for k in host:
-        host[k].copy_(dev[k][:n_e2e])
+        host[k].copy_(dev[k])
     hset, keep2 = gtb200.pinned_set(host)
-    out_host = np.zeros(N_REGIONS, dtype=np.uint64)
+    out_host = torch.zeros(N_REGIONS, dtype=torch.int64).pin_memory()
 
     def step_e2e():
-        index.reset()
-        index.add_set(hset, gtb200.MEM_HOST)
-        index.finish(out_host)
-        if dist is not None:
-            t = torch.from_numpy(out_host.view(np.int64)).cuda()
-            dist.all_reduce(t)
-            out_host[:] = t.cpu().numpy().view(np.uint64)
+        if world == 1:
+            index.reset()
+            index.add_set(hset, gtb200.MEM_HOST)
+            index.finish_ptr(out_host.data_ptr(), gtb200.MEM_HOST)
+        else:
+            out_host.copy_(sh.step(hset, gtb200.MEM_HOST))           # H2D of the local reads, gather, D2H of all counts
 
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
@@ -268,7 +332,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * n_e2e / e2e_s, "unit": "query intervals/s", "h2d_bytes_per_step": BYTES_PER_QUERY * n_e2e,
+    e2e = {"value": world * n_e2e / e2e_s, "unit": "query intervals/s", "h2d_bytes_per_step": BYTES_PER_QUERY * n_local,
            "d2h_bytes_per_step": 8 * N_REGIONS, "ms_per_step": e2e_s * 1e3}
 
     if rank == 0:
@@ -278,13 +342,19 @@ def main():
                 "config": {"workload": "100M synthetic 50bp hg19 reads vs 60k gene regions, strand-aware count (configs[1])",
                            "reads_per_gpu": n, "n_regions": N_REGIONS, "read_len": READ_LEN, "engine": args.engine,
                            "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_QUERY * n / 1e9),
-                           "parallelism": "query-sharded x%d, one NCCL all-reduce of per-region counts" % world if world > 1 else "single GPU"},
+                           "parallelism": "genome-sharded x%d: region ownership by range, boundary reads replicated at ingest, one NCCL "
+                                          "all-gather of per-region counts" % world if world > 1 else "single GPU"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
                 "checksum": counts_check}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port(regions)
+        if sharding:
+            line["sharding"] = sharding
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(regions)
         print(json.dumps(line))
-    index.close()
+    if world == 1:
+        index.close()
+    else:
+        sh.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

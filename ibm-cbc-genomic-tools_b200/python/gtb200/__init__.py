@@ -39,7 +39,7 @@ EXPORTS = [
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_finish",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
-    "gtb_synth_reads",
+    "gtb_synth_reads", "gtb_synth_reads_range",
 ]
 
 
@@ -93,6 +93,8 @@ def load_library(path=LIB_PATH):
         "gtb_scan_finish": (ci, [vp, P(i64)]),
         "gtb_scan_fetch": (ci, [vp, i64, i64, vp, vp, vp, vp]),
         "gtb_synth_reads": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp]),
+        "gtb_synth_reads_range": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_uint64,
+                                       ctypes.c_uint64, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -205,11 +207,13 @@ class Context:
     def overlap_coverage(self, queries, regions, flags=0, qweight=None, qoffsets=None, roffsets=None):
         return self._one_shot(lib().gtb_overlap_coverage, queries, regions, flags, qweight, qoffsets, roffsets)
 
-    def synth_reads(self, seed, first, n, read_len, chrom_len, out):
-        """out: dict of preallocated torch CUDA tensors."""
+    def synth_reads(self, seed, first, n, read_len, chrom_len, out, p_range=None):
+        """out: dict of preallocated torch CUDA tensors; p_range = (p_lo, p_hi) restricts the effective positions."""
         cl = np.ascontiguousarray(chrom_len, dtype=np.int64)
-        self.check(lib().gtb_synth_reads(self._h, seed, first, n, read_len, len(cl), _np_ptr(cl), out["chrom"].data_ptr(),
-                                         out["start"].data_ptr(), out["stop"].data_ptr(), out["strand"].data_ptr()))
+        p_lo, p_hi = (0, (1 << 64) - 1) if p_range is None else p_range
+        self.check(lib().gtb_synth_reads_range(self._h, seed, first, n, read_len, len(cl), _np_ptr(cl), p_lo, p_hi,
+                                               out["chrom"].data_ptr(), out["start"].data_ptr(), out["stop"].data_ptr(),
+                                               out["strand"].data_ptr()))
 
 
 class Index:

@@ -1,0 +1,325 @@
+"""Genome-sharded multi-GPU driver for overlap count / coverage (north-star decomposition).
+
+One process per GPU (torch.distributed; NCCL on the GPUs, gloo in the CPU tests).  The genome is cut into
+G contiguous (chromosome, coordinate) ranges balanced by read mass.  Every index region is OWNED by exactly one
+shard -- the one whose range contains the region's span start -- and that shard computes the region's final
+value, so the merge is a GATHER of per-region values, not a reduction.  A shard therefore needs every query
+that can overlap a region it owns: the queries intersecting [range start, max stop of the owned regions].
+Queries reaching across a range boundary are replicated to both neighbours (`route`).  There is no data-path
+collective besides the final gather (plus a gather of the (index, code) pair of the first fatal query, so that
+error behaviour matches the single-GPU engine, genomic_intervals.cpp:5740-5741).
+
+Nothing here computes counts: the per-shard engine is the CUDA library (gtb200.Index).  Tests may inject another
+engine factory to exercise the planning / routing / gather logic without a GPU.
+"""
+import numpy as np
+
+from . import ERR_INDEX_REGION, MEM_DEVICE, OK, OP_COUNT, Context, GtbError, Index
+
+_MARGIN = 2          # empty positions between chromosomes on the linear axis
+
+
+class ShardPlan:
+    """Cut points of the genome and region ownership.
+
+    regions  : dict chrom/start/stop/strand (+ roffsets for multi-interval regions), file order
+    n_shards : G
+    read_hist: optional (bin_width, {chrom id: int64 array of read counts per bin}) -- a coarse histogram of
+               read START positions used to balance the shards by read count; without it the cut points
+               balance genome length (exact for uniform reads)
+    """
+
+    def __init__(self, regions, n_shards, roffsets=None, read_hist=None, chrom_extent=None):
+        chrom = np.asarray(regions["chrom"], dtype=np.int64)
+        start = np.asarray(regions["start"], dtype=np.int64)
+        stop = np.asarray(regions["stop"], dtype=np.int64)
+        off = np.arange(len(chrom) + 1, dtype=np.int64) if roffsets is None else np.asarray(roffsets, dtype=np.int64)
+        self.n_regions = len(off) - 1
+        self.n_shards = int(n_shards)
+        first, last = off[:-1], np.maximum(off[1:] - 1, off[:-1])
+        has = off[1:] > off[:-1]
+        r_chrom = np.where(has, chrom[np.minimum(first, max(len(chrom) - 1, 0))], 0) if len(chrom) else np.zeros(self.n_regions, np.int64)
+        r_start = np.where(has, start[np.minimum(first, max(len(chrom) - 1, 0))], 1) if len(chrom) else np.ones(self.n_regions, np.int64)
+        r_stop = np.where(has, stop[np.minimum(last, max(len(chrom) - 1, 0))], 0) if len(chrom) else np.zeros(self.n_regions, np.int64)
+        n_chrom = int(r_chrom.max()) + 1 if self.n_regions else 1
+        # linear axis: chromosome c occupies [cum[c], cum[c] + extent[c] + 1]; position p of c maps to cum[c] + clip(p, 0, extent[c] + 1)
+        extent = np.zeros(n_chrom, dtype=np.int64)
+        if self.n_regions:
+            np.maximum.at(extent, r_chrom, np.maximum(r_stop, 0))
+        if chrom_extent is not None:
+            ce = np.asarray(chrom_extent, dtype=np.int64)
+            if len(ce) > n_chrom:
+                extent = np.concatenate([extent, np.zeros(len(ce) - n_chrom, dtype=np.int64)])
+                n_chrom = len(ce)
+            extent[:len(ce)] = np.maximum(extent[:len(ce)], ce)
+        self.n_chrom = n_chrom
+        self.extent = extent
+        self.cum = np.concatenate([[0], np.cumsum(extent + 1 + _MARGIN)]).astype(np.int64)
+        total = int(self.cum[-1])
+        # ---- cut points
+        if read_hist is None:
+            cuts = [(total * s) // self.n_shards for s in range(self.n_shards + 1)]
+        else:
+            width, per_chrom = read_hist
+            pos, mass = [], []
+            for c in range(n_chrom):
+                h = np.asarray(per_chrom.get(c, []), dtype=np.int64)
+                if len(h) == 0:
+                    continue
+                p = self.cum[c] + np.minimum((np.arange(len(h), dtype=np.int64) + 1) * width, extent[c] + 1)   # right edge of each bin
+                pos.append(p); mass.append(h)
+            if pos:
+                pos = np.concatenate(pos); mass = np.concatenate(mass)
+                cs = np.cumsum(mass)
+                tot = int(cs[-1]) if len(cs) else 0
+            else:
+                tot = 0
+            cuts = [0]
+            for s in range(1, self.n_shards):
+                if tot == 0:
+                    cuts.append((total * s) // self.n_shards)
+                else:
+                    k = int(np.searchsorted(cs, (tot * s + self.n_shards - 1) // self.n_shards, side="left"))
+                    cuts.append(int(pos[min(k, len(pos) - 1)]))
+            cuts.append(total)
+            for s in range(1, len(cuts)):
+                cuts[s] = max(cuts[s], cuts[s - 1])
+        cuts[0], cuts[-1] = -(1 << 62), 1 << 62          # the outer shards are open-ended
+        self.lo = np.array(cuts[:-1], dtype=np.int64)     # shard s owns linear positions [lo[s], lo[s+1])
+        # ---- ownership: the shard containing the span start
+        self.region_lin_start = self.lin(r_chrom, r_start)
+        self.region_lin_stop = np.maximum(self.lin(r_chrom, r_stop), self.region_lin_start)
+        self.owner = (np.searchsorted(self.lo, self.region_lin_start, side="right") - 1).astype(np.int64)
+        self.owned = [np.nonzero(self.owner == s)[0] for s in range(self.n_shards)]          # file order within a shard
+        self.max_owned = max((len(o) for o in self.owned), default=0)
+        # what a shard must see: [lo[s], reach[s]]
+        self.reach = np.array([int(self.region_lin_stop[o].max()) if len(o) else int(self.lo[s]) - 1 for s, o in enumerate(self.owned)],
+                              dtype=np.int64)
+        self._off = off
+
+    def lin(self, chrom, pos):
+        chrom = np.asarray(chrom, dtype=np.int64)
+        pos = np.asarray(pos, dtype=np.int64)
+        known = (chrom >= 0) & (chrom < self.n_chrom)
+        c = np.where(known, chrom, 0)
+        v = self.cum[c] + np.clip(pos, 0, self.extent[c] + 1)
+        return np.where(known, v, -1)                     # unknown chromosomes overlap nothing; park them in shard 0
+
+    def cut_positions(self):
+        """Cut points as (chromosome id, 1-based position) pairs, for generators that work per chromosome."""
+        out = []
+        for s in range(1, self.n_shards):
+            c = int(np.searchsorted(self.cum, self.lo[s], side="right") - 1)
+            c = min(max(c, 0), self.n_chrom - 1)
+            out.append((c, int(self.lo[s] - self.cum[c])))
+        return out
+
+    def subset(self, regions, shard, roffsets=None):
+        """The index regions a shard owns (file order kept) as (regions dict, roffsets or None)."""
+        ids = self.owned[shard]
+        off = self._off
+        if roffsets is None:
+            return {k: np.ascontiguousarray(np.asarray(regions[k])[ids]) for k in ("chrom", "start", "stop", "strand")}, None
+        lens = off[ids + 1] - off[ids]
+        new_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        take = np.concatenate([np.arange(off[i], off[i + 1]) for i in ids]) if len(ids) else np.zeros(0, dtype=np.int64)
+        return {k: np.ascontiguousarray(np.asarray(regions[k])[take]) for k in ("chrom", "start", "stop", "strand")}, new_off
+
+    def route(self, queries, shard, qoffsets=None):
+        """Indices (into the query REGION list) of the queries shard `shard` must process."""
+        chrom = np.asarray(queries["chrom"], dtype=np.int64)
+        start = np.asarray(queries["start"], dtype=np.int64)
+        stop = np.asarray(queries["stop"], dtype=np.int64)
+        if qoffsets is not None:
+            off = np.asarray(qoffsets, dtype=np.int64)
+            first, last = off[:-1], off[1:] - 1
+            chrom, start, stop = chrom[first], start[first], stop[last]
+        invalid = (stop <= 0) | (start > stop)            # potentially fatal: every shard must see them (chromosome presence decides)
+        q_lo = self.lin(chrom, start)
+        q_hi = np.maximum(self.lin(chrom, stop), q_lo)
+        need = (q_hi >= self.lo[shard]) & (q_lo <= self.reach[shard])
+        return np.nonzero(need | invalid)[0]
+
+
+def _take_queries(queries, ids, qweight=None, qoffsets=None):
+    if qoffsets is None:
+        sub = {k: np.ascontiguousarray(np.asarray(queries[k])[ids]) for k in ("chrom", "start", "stop", "strand")}
+        return sub, (None if qweight is None else np.ascontiguousarray(np.asarray(qweight)[ids])), None
+    off = np.asarray(qoffsets, dtype=np.int64)
+    lens = off[ids + 1] - off[ids]
+    new_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    take = np.concatenate([np.arange(off[i], off[i + 1]) for i in ids]) if len(ids) else np.zeros(0, dtype=np.int64)
+    sub = {k: np.ascontiguousarray(np.asarray(queries[k])[take]) for k in ("chrom", "start", "stop", "strand")}
+    return sub, (None if qweight is None else np.ascontiguousarray(np.asarray(qweight)[ids])), new_off
+
+
+def first_malformed_region(regions, roffsets):
+    """Index of the first multi-interval region that is not same-chromosome / same-strand / start-sorted /
+    non-overlapping (GenomicRegion::IsCompatibleSortedAndNonoverlapping, genomic_intervals.cpp:1153-1161), or -1.
+    Checked on every rank before sharding so that all ranks fail alike (the engine would report a shard-local index)."""
+    if roffsets is None:
+        return -1
+    off = np.asarray(roffsets, dtype=np.int64)
+    chrom, start, stop, strand = (np.asarray(regions[k]) for k in ("chrom", "start", "stop", "strand"))
+    n = len(chrom)
+    if n < 2:
+        return -1
+    same_region = np.ones(n - 1, dtype=bool)
+    same_region[off[1:-1][(off[1:-1] > 0) & (off[1:-1] < n)] - 1] = False          # pairs (i, i+1) straddling a region boundary
+    bad = same_region & ((chrom[1:] != chrom[:-1]) | (strand[1:] != strand[:-1]) | (start[1:] < start[:-1]) | (start[1:] <= stop[:-1]))
+    if not bad.any():
+        return -1
+    i = int(np.nonzero(bad)[0][0]) + 1
+    return int(np.searchsorted(off, i, side="right") - 1)
+
+
+class CudaShardEngine:
+    """The per-shard engine of the product: a gtb200.Index on this rank's GPU."""
+
+    def __init__(self, regions, roffsets, op, flags, device):
+        self.ctx = Context(device)
+        self.index = Index(self.ctx, regions, op, flags, roffsets=roffsets)
+
+    def add(self, queries, weight, offsets):
+        self.index.add_host(queries, weight=weight, offsets=offsets)
+
+    def finish(self):
+        """-> (status, local index of the first fatal query or -1, values)"""
+        try:
+            return OK, -1, self.index.finish()
+        except GtbError as e:
+            return e.code, e.index, np.zeros(self.index.n_regions, dtype=np.uint64)
+
+    def close(self):
+        self.index.close()
+        self.ctx.close()
+
+
+class ShardedOverlap:
+    """count / coverage over G ranks.  Every rank calls the same methods with the same index regions; queries may be
+    given in full on every rank (each keeps what `route` assigns to it) or pre-routed with add_routed()."""
+
+    def __init__(self, regions, op=OP_COUNT, flags=0, roffsets=None, read_hist=None, chrom_extent=None, group=None,
+                 engine_factory=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        bad = first_malformed_region(regions, roffsets)
+        if bad >= 0:
+            raise GtbError(ERR_INDEX_REGION, "index regions should be compatible, sorted and non-overlapping!", bad)
+        self.plan = ShardPlan(regions, self.world, roffsets=roffsets, read_hist=read_hist, chrom_extent=chrom_extent)
+        sub, sub_off = self.plan.subset(regions, self.rank, roffsets)
+        if engine_factory is None:
+            dev = self.rank if device is None else device
+            engine_factory = lambda r, o, op_, fl: CudaShardEngine(r, o, op_, fl, dev)
+        self.engine = engine_factory(sub, sub_off, op, flags)
+        self.global_ids = []          # per added batch: global stream index of every local query
+        self.seen = 0
+
+    def add(self, queries, qweight=None, qoffsets=None):
+        """All ranks pass the SAME batch; this rank processes its routed part."""
+        ids = self.plan.route(queries, self.rank, qoffsets)
+        n = (len(qoffsets) - 1) if qoffsets is not None else len(queries["chrom"])
+        sub, w, off = _take_queries(queries, ids, qweight, qoffsets)
+        self.global_ids.append(self.seen + ids)
+        self.seen += n
+        if len(ids):
+            self.engine.add(sub, w, off)
+
+    def add_routed(self, queries, global_index, qweight=None, qoffsets=None):
+        """This rank passes only the queries it is responsible for (e.g. read from a per-range file);
+        global_index[i] = position of query i in the overall stream (for error reporting)."""
+        self.global_ids.append(np.asarray(global_index, dtype=np.int64))
+        self.engine.add(queries, qweight, qoffsets)
+
+    def finish(self):
+        """-> uint64 values in index-file order on every rank (one all-gather); raises GtbError like the single-GPU engine."""
+        import torch
+        status, local_idx, vals = self.engine.finish()
+        gids = np.concatenate(self.global_ids) if self.global_ids else np.zeros(0, dtype=np.int64)
+        err_global = int(gids[local_idx]) if status != OK and 0 <= local_idx < len(gids) else (1 << 62)
+        pad = self.plan.max_owned
+        send = np.zeros(pad + 2, dtype=np.int64)
+        send[:len(vals)] = np.asarray(vals, dtype=np.uint64).view(np.int64)
+        send[pad] = err_global
+        send[pad + 1] = status
+        backend = self.dist.get_backend(self.group) if self.dist.is_initialized() else "none"
+        dev = "cuda" if backend == "nccl" else "cpu"
+        t = torch.from_numpy(send).to(dev)
+        if self.world > 1:
+            out = torch.empty(self.world * (pad + 2), dtype=torch.int64, device=dev)
+            self.dist.all_gather_into_tensor(out, t, group=self.group)            # THE collective
+            table = out.cpu().numpy().reshape(self.world, pad + 2)
+        else:
+            table = send[None, :]
+        first = min(range(self.world), key=lambda s: (int(table[s, pad]), s))
+        if int(table[first, pad + 1]) != OK and int(table[first, pad]) < (1 << 62):
+            raise GtbError(int(table[first, pad + 1]), "fatal query (reported by shard %d)" % first, int(table[first, pad]))
+        result = np.zeros(self.plan.n_regions, dtype=np.uint64)
+        for s in range(self.world):
+            ids = self.plan.owned[s]
+            result[ids] = table[s, :len(ids)].view(np.uint64)
+        return result
+
+    def close(self):
+        self.engine.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-resident form (bench.py, pipelines that keep the reads in HBM): same plan, same gather, torch tensors
+# ---------------------------------------------------------------------------------------------------------------
+def route_mask_torch(plan, t, shard):
+    """Boolean CUDA tensor: which single-interval reads of the device set `t` shard `shard` must process (== ShardPlan.route)."""
+    import torch
+    dev = t["chrom"].device
+    cum = torch.from_numpy(plan.cum).to(dev)
+    ext = torch.from_numpy(plan.extent).to(dev)
+    c = t["chrom"].long()
+    known = (c >= 0) & (c < plan.n_chrom)
+    cc = torch.where(known, c, torch.zeros_like(c))
+    s, e = t["start"].long(), t["stop"].long()
+    q_lo = torch.where(known, cum[cc] + torch.minimum(torch.clamp(s, min=0), ext[cc] + 1), torch.full_like(c, -1))
+    q_hi = torch.maximum(torch.where(known, cum[cc] + torch.minimum(torch.clamp(e, min=0), ext[cc] + 1), torch.full_like(c, -1)), q_lo)
+    invalid = (e <= 0) | (s > e)
+    return ((q_hi >= int(plan.lo[shard])) & (q_lo <= int(plan.reach[shard]))) | invalid
+
+
+class ShardedDeviceOverlap:
+    """One rank of the genome-sharded count/coverage with device-resident reads.  step() = reset, stream the local
+    reads (own range + replicated boundary reads), finalise the owned regions, ONE all-gather, scatter to file order."""
+
+    def __init__(self, ctx, regions, plan, op=OP_COUNT, flags=0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        assert plan.n_shards == self.world
+        self.plan, self.ctx = plan, ctx
+        sub, _ = plan.subset(regions, self.rank, None)
+        self.index = Index(ctx, sub, op, flags)
+        pad = max(plan.max_owned, 1)
+        self.pad = pad
+        self.vals = torch.zeros(pad, dtype=torch.int64, device="cuda")
+        self.table = torch.zeros(self.world * pad, dtype=torch.int64, device="cuda")
+        src = np.concatenate([s * pad + np.arange(len(plan.owned[s])) for s in range(self.world)]) if plan.n_regions else np.zeros(0, np.int64)
+        dst = np.concatenate(plan.owned) if plan.n_regions else np.zeros(0, np.int64)
+        order = np.argsort(dst, kind="stable")
+        self.src_in_file_order = torch.from_numpy(src[order].astype(np.int64)).cuda()      # result[k] = table[src_in_file_order[k]]
+        self.result = torch.zeros(plan.n_regions, dtype=torch.int64, device="cuda")
+
+    def step(self, dset, mem):
+        self.index.reset()
+        self.index.add_set(dset, mem)
+        self.index.finish_ptr(self.vals.data_ptr(), MEM_DEVICE)                # owned values stay on the device
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.table, self.vals, group=self.group)        # THE collective
+            self.torch.index_select(self.table, 0, self.src_in_file_order, out=self.result)
+        else:
+            self.torch.index_select(self.vals, 0, self.src_in_file_order, out=self.result)
+        return self.result
+
+    def close(self):
+        self.index.close()

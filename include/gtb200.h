@@ -172,6 +172,13 @@ int  gtb_synth_reads(gtb_ctx *ctx, uint64_t seed, int64_t first, int64_t n, int3
                      int32_t n_chrom, const int64_t *chrom_len /*host*/, int32_t *d_chrom, int32_t *d_start,
                      int32_t *d_stop, int8_t *d_strand);
 
+/* The same generator restricted to effective positions p in [p_lo, p_hi) of the concatenated genome
+ * (p counts valid read starts: chromosome c contributes chrom_len[c] - read_len + 1 of them) -- the reads
+ * of one genome shard of the multi-GPU driver.  p_hi is clamped to the genome end. */
+int  gtb_synth_reads_range(gtb_ctx *ctx, uint64_t seed, int64_t first, int64_t n, int32_t read_len,
+                           int32_t n_chrom, const int64_t *chrom_len /*host*/, uint64_t p_lo, uint64_t p_hi,
+                           int32_t *d_chrom, int32_t *d_start, int32_t *d_stop, int8_t *d_strand);
+
 #ifdef __cplusplus
 }
 #endif

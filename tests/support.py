@@ -35,7 +35,7 @@ def splitmix64(z):
         return z ^ (z >> np.uint64(31))
 
 
-def synth_reads(n, seed, read_len=50, chrom_lens=HG19_LENS, first=0):
+def synth_reads(n, seed, read_len=50, chrom_lens=HG19_LENS, first=0, p_range=None):
     """Counter-based synthetic reads: read i depends only on (seed, i) so the CUDA generator
     (gtb_synth_reads) and this function produce identical streams.
       a = splitmix64(seed * 0x9E3779B97F4A7C15 + i); b = splitmix64(a)
@@ -48,7 +48,11 @@ def synth_reads(n, seed, read_len=50, chrom_lens=HG19_LENS, first=0):
     with np.errstate(over="ignore"):
         a = splitmix64((np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + i) & _M64)
     b = splitmix64(a)
-    p = a % cum[-1]
+    if p_range is None:
+        p = a % cum[-1]
+    else:                                             # one genome shard: gtb_synth_reads_range
+        p_lo, p_hi = np.uint64(p_range[0]), np.uint64(min(p_range[1], int(cum[-1])))
+        p = p_lo + a % (p_hi - p_lo)
     chrom = (np.searchsorted(cum, p, side="right") - 1).astype(np.int32)
     start = (p - cum[chrom] + np.uint64(1)).astype(np.int32)
     stop = (start + np.int32(read_len - 1)).astype(np.int32)

@@ -192,3 +192,61 @@ def test_scan_hg19_vs_oracle(gtb, ctx, oracle):
         for k in want:
             assert np.array_equal(got[k], want[k]), (w, d, op, k)
         sc.close()
+
+
+@pytest.mark.parametrize("shards", [2, 4])
+@pytest.mark.parametrize("op", ["count", "coverage"])
+def test_sharded_plan_cuda(gtb, ctx, oracle, shards, op):
+    """The genome-sharded decomposition with the CUDA engine, the G shards run one after the other on this GPU:
+    ownership + routing + per-shard Index + assembly by owner must equal the unsharded oracle."""
+    from gtb200 import sharded
+    reads = support.synth_reads(400_000, seed=21)
+    regions = support.synth_regions(3_000, seed=22)
+    plan = sharded.ShardPlan(regions, shards, chrom_extent=support.HG19_LENS)
+    fn = oracle.count if op == "count" else oracle.coverage
+    rc, want, _ = fn(reads, regions, 0)
+    assert rc == 0
+    result = np.zeros(len(regions["chrom"]), dtype=np.uint64)
+    routed = 0
+    for s in range(shards):
+        sub, _ = plan.subset(regions, s)
+        ids = plan.route(reads, s)
+        routed += len(ids)
+        q, _, _ = sharded._take_queries(reads, ids)
+        ix = gtb.Index(ctx, sub, gtb.OP_COUNT if op == "count" else gtb.OP_COVERAGE, 0)
+        ix.add_host(q)
+        result[plan.owned[s]] = ix.finish()
+        ix.close()
+    assert np.array_equal(result, want)
+    assert routed <= 1.05 * 400_000           # replication across the cut points stays marginal
+
+
+def test_sharded_device_world1(gtb, ctx, oracle):
+    """ShardedDeviceOverlap degenerates to the single-GPU engine when there is one rank."""
+    import torch
+    from gtb200 import sharded
+    reads = support.synth_reads(300_000, seed=31)
+    regions = support.synth_regions(2_000, seed=32)
+    plan = sharded.ShardPlan(regions, 1, chrom_extent=support.HG19_LENS)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in reads.items()}
+    assert bool(sharded.route_mask_torch(plan, dev, 0).cpu().numpy()[plan.route(reads, 0)].all())
+    sh = sharded.ShardedDeviceOverlap(ctx, regions, plan, gtb.OP_COUNT, 0)
+    dset, keep = gtb.device_set(dev)
+    got = sh.step(dset, gtb.MEM_DEVICE).cpu().numpy().view(np.uint64)
+    rc, want, _ = oracle.count(reads, regions, 0)
+    assert rc == 0 and np.array_equal(got, want)
+    sh.close()
+
+
+def test_synth_range_matches_numpy(gtb, ctx):
+    import torch
+    n = 100_000
+    eff = support.HG19_LENS - 50 + 1
+    total = int(eff.sum())
+    rng = (total // 3, total // 2)
+    dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
+           "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
+    ctx.synth_reads(9, 12345, n, 50, support.HG19_LENS, dev, p_range=rng)
+    want = support.synth_reads(n, 9, first=12345, p_range=rng)
+    for k in want:
+        assert np.array_equal(dev[k].cpu().numpy(), want[k]), k
