@@ -250,3 +250,56 @@ def test_synth_range_matches_numpy(gtb, ctx):
     want = support.synth_reads(n, 9, first=12345, p_range=rng)
     for k in want:
         assert np.array_equal(dev[k].cpu().numpy(), want[k]), k
+
+
+def test_full_size_properties(gtb, ctx, oracle):
+    """BASELINE.json configs[1] at full size (100 M reads x 60 000 regions, strand-aware), where the oracle is too slow:
+    size-independent properties.  (1) three independent device algorithms agree (bucket, cell, rank engines);
+    (2) permutation invariance; (3) additivity over query batches; (4) checksum of checksums: sum_r count[r] equals
+    sum_q #regions overlapping q, the latter from an independent per-QUERY formulation (torch.searchsorted over the
+    regions' sorted starts / stops); (5) coverage >= count and coverage <= 50 * count for 50-bp reads;
+    (6) the first 1 M reads of the same stream agree with the oracle."""
+    import torch
+    n, m = 100_000_000, 60_000
+    regions = support.synth_regions(m, seed=3)
+    dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
+           "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
+    ctx.synth_reads(2, 0, n, 50, support.HG19_LENS, dev)
+
+    def run(tensors, op=gtb.OP_COUNT, engine=0, parts=1):
+        ix = gtb.Index(ctx, regions, op, engine)
+        step = (tensors["chrom"].numel() + parts - 1) // parts
+        for lo in range(0, tensors["chrom"].numel(), step):
+            ix.add_device({k: v[lo:lo + step] for k, v in tensors.items()})
+        out = ix.finish()
+        ix.close()
+        return out
+
+    base = run(dev)
+    assert np.array_equal(run(dev, engine=gtb.ENGINE_BUCKET), base)
+    assert np.array_equal(run(dev, engine=gtb.ENGINE_CELL), base)
+    assert np.array_equal(run(dev, engine=gtb.ENGINE_RANK), base)
+    assert np.array_equal(run(dev, parts=3), base)                                  # 33 333 334-read batches (unaligned tails)
+    perm = torch.randperm(n, device="cuda")
+    shuffled = {k: v[perm] for k, v in dev.items()}
+    del perm
+    assert np.array_equal(run(shuffled), base)
+    del shuffled
+    # per-query dual: #overlaps(q) = #{r in group: rs <= qe} - #{r in group: re < qs}
+    grp_r = torch.from_numpy(regions["chrom"].astype(np.int64) * 2 + (regions["strand"] == ord("-"))).cuda()
+    ks = torch.sort((grp_r << 32) + torch.from_numpy(regions["start"].astype(np.int64)).cuda()).values
+    ke = torch.sort((grp_r << 32) + torch.from_numpy(regions["stop"].astype(np.int64)).cuda()).values
+    total = 0
+    for lo in range(0, n, 25_000_000):
+        sl = slice(lo, lo + 25_000_000)
+        g = (dev["chrom"][sl].long() * 2 + (dev["strand"][sl] == ord("-")).long()) << 32
+        a = torch.searchsorted(ks, g + dev["stop"][sl].long(), right=True) - torch.searchsorted(ks, g, right=False)
+        b = torch.searchsorted(ke, g + dev["start"][sl].long(), right=False) - torch.searchsorted(ke, g, right=False)
+        total += int((a - b).sum().item())
+    assert int(base.sum()) == total
+    cov = run(dev, op=gtb.OP_COVERAGE)
+    assert np.all(cov >= base) and np.all(cov <= 50 * base)
+    sub = {k: v[:1_000_000].cpu().numpy() for k, v in dev.items()}
+    rc, want, _ = oracle.count(sub, regions, 0)
+    got = run({k: v[:1_000_000] for k, v in dev.items()})
+    assert rc == 0 and np.array_equal(got, want)
