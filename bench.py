@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU (default: the BASELINE config)")
     ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "bucket", "enumerate"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg (the line is then not a valid bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -306,6 +307,11 @@ def main():
 
     # ---- end to end through the C ABI with host buffers (`e2e`) -------------------------------------
     n_e2e = n
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "kernels": {k: round(v["ms_per_launch"], 4) for k, v in roofline["kernels"].items()},
+                              "checksum": counts_check}))
+        return
     host = {k: torch.empty(n_local, dtype=v.dtype).pin_memory() for k, v in dev.items()}
     for k in host:
         host[k].copy_(dev[k])

@@ -10,7 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libgtb200.so")
+LIB_PATH = os.environ.get("GTB200_LIB") or os.path.join(PKG_ROOT, "lib", "libgtb200.so")     # override: kernel A/B experiments
 
 MATCH_GAPS = 1 << 0
 IGNORE_STRAND = 1 << 1
