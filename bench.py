@@ -329,6 +329,7 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
     barrier()
+    xfer0 = ctx.transfer_stats()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
@@ -338,8 +339,14 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * n_e2e / e2e_s, "unit": "query intervals/s", "h2d_bytes_per_step": BYTES_PER_QUERY * n_local,
-           "d2h_bytes_per_step": 8 * N_REGIONS, "ms_per_step": e2e_s * 1e3}
+    xfer1 = ctx.transfer_stats()
+    # bytes that actually crossed PCIe per step on this rank (the library re-encodes host chunks to 8 B/interval when it can);
+    # host_buffer_bytes is what the caller handed over in the ABI layout (13 B/interval)
+    e2e = {"value": world * n_e2e / e2e_s, "unit": "query intervals/s",
+           "h2d_bytes_per_step": (xfer1["h2d_bytes"] - xfer0["h2d_bytes"]) // e2e_steps,
+           "d2h_bytes_per_step": (xfer1["d2h_bytes"] - xfer0["d2h_bytes"]) // e2e_steps + (8 * N_REGIONS if world > 1 else 0),
+           "host_buffer_bytes_per_step": BYTES_PER_QUERY * n_local, "packed_chunks": xfer1["packed_chunks"] - xfer0["packed_chunks"],
+           "raw_chunks": xfer1["raw_chunks"] - xfer0["raw_chunks"], "ms_per_step": e2e_s * 1e3}
 
     if rank == 0:
         line = {"metric": "query intervals/sec (overlap-count, device-timed)", "value": value, "unit": "query intervals/s",

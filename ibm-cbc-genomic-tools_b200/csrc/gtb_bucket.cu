@@ -33,7 +33,14 @@
 
 namespace {
 
-constexpr int PART_THREADS = 512;
+#ifndef GTB_PART_THREADS
+#define GTB_PART_THREADS 512
+#endif
+#ifndef GTB_PART_CTAS
+#define GTB_PART_CTAS 2
+#endif
+constexpr int PART_THREADS = GTB_PART_THREADS;
+constexpr int PART_CTAS = GTB_PART_CTAS;                  // resident CTAs per SM the kernel is sized for
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4 096 queries
 constexpr int PAGE_SHIFT = 12;
@@ -123,7 +130,7 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
 //   y = (u of coordinate 0 of the group) & (bucket size - 1)      z = (u of coordinate 0) >> ub
 // so that for a start coordinate s:  t = y + s,  bucket = z + (t >> ub),  bucket-local u = t & (2^ub - 1).
 template <bool COVERAGE, int VEC, int RES>
-__global__ void __launch_bounds__(PART_THREADS, 2) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
+__global__ void __launch_bounds__(PART_THREADS, PART_CTAS) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
   extern __shared__ __align__(128) uint32_t smem[];
   // raw tile, filled by TMA bulk copies: chrom | start | stop (PART_TILE ints each) | strand (PART_TILE bytes)
   int32_t *s_chrom = reinterpret_cast<int32_t *>(smem);
@@ -540,7 +547,7 @@ int gtb_bucket_prepare(gtb_index *ix) {
   for (size_t j = 1; j < slot_u.size(); j++) if (slot_u[j] < slot_u[j - 1]) slot_u[j] = slot_u[j - 1];
   const ull total_u = std::max<ull>(cells << k, 1);
   int ub = 24;
-  if (const char *env = getenv("GTB_BUCKET_BITS")) ub = std::max(k + 1, std::min(24, atoi(env)));
+  if (const char *env = getenv("GTB_BUCKET_BITS")) ub = std::max(k + 1, std::min(27, atoi(env)));
   if (ub < k + 1) ub = k + 1;
   std::vector<int32_t> j0;
   int max_local = 0;
@@ -645,10 +652,12 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   const bool aligned = ((uintptr_t)q.chrom % 16 == 0) && ((uintptr_t)q.start % 16 == 0) && ((uintptr_t)q.stop % 16 == 0) &&
                        ((uintptr_t)q.strand % 16 == 0);          // TMA bulk copies need 16-byte aligned sources
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
-  const unsigned grid1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, n_tiles));
+  const unsigned grid1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * PART_CTAS, n_tiles));
 #define GTB_PART_LAUNCH(COV, VEC)                                                                                          \
   do {                                                                                                                     \
-    auto kern = nb <= PART_THREADS ? bucket_partition_kernel<COV, VEC, 1> : bucket_partition_kernel<COV, VEC, MAX_BUCKETS / PART_THREADS>;                                                                       \
+    auto kern = nb <= PART_THREADS ? bucket_partition_kernel<COV, VEC, 1>                                                  \
+                : nb <= 2 * PART_THREADS ? bucket_partition_kernel<COV, VEC, 2>                                            \
+                                         : bucket_partition_kernel<COV, VEC, MAX_BUCKETS / PART_THREADS>;                  \
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->part_smem));         \
     GTB_LAUNCH(ctx, "bucket_partition", kern, grid1, PART_THREADS, bs->part_smem, q, rv, bv);                              \
   } while (0)

@@ -1,6 +1,7 @@
 // gtb_ctx.cu -- context life cycle, stream selection, launch accounting / CUDA-event profiling,
 // and the multi-block inclusive scan used by the finalisation kernels.
 #include "gtb_internal.cuh"
+#include <thread>
 
 extern "C" int gtb_abi_version(void) { return GTB200_ABI_VERSION; }
 
@@ -34,7 +35,41 @@ extern "C" void gtb_ctx_destroy(gtb_ctx *ctx) {
   for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  gtb_ingest_destroy(ctx->ingest);
+  for (auto &sl : ctx->slots) {
+    if (sl.meta) cudaFreeHost(sl.meta);
+    if (sl.start) cudaFreeHost(sl.start);
+    if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+  }
   delete ctx;
+}
+
+// Lazily starts the packing pool and hands out the next pinned staging slot, sized for n_intervals and no longer
+// referenced by a copy in flight.  Returns GTB_ERR_UNSUPPORTED when packing is off (GTB_INGEST_THREADS=0, one core).
+int gtb_ctx_ingest_ready(gtb_ctx *ctx, size_t n_intervals, gtb_pinned_slot **slot) {
+  if (!ctx->ingest_tried) {
+    ctx->ingest_tried = true;
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) threads /= w; }   // torchrun: ranks share the host
+    if (threads > 32) threads = 32;
+    if (const char *env = getenv("GTB_INGEST_THREADS")) threads = atoi(env);
+    if (threads >= 2) ctx->ingest = gtb_ingest_create(threads);
+  }
+  if (!ctx->ingest) return GTB_ERR_UNSUPPORTED;
+  gtb_pinned_slot &sl = ctx->slots[ctx->next_slot];
+  ctx->next_slot = (ctx->next_slot + 1) % 3;
+  if (sl.in_flight) { GTB_CUDA_OK(ctx, cudaEventSynchronize(sl.h2d_done)); sl.in_flight = false; }
+  if (sl.cap < n_intervals) {
+    if (sl.meta) cudaFreeHost(sl.meta);
+    if (sl.start) cudaFreeHost(sl.start);
+    sl.meta = nullptr; sl.start = nullptr; sl.cap = 0;
+    GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&sl.meta, n_intervals * sizeof(uint32_t), cudaHostAllocDefault));
+    GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&sl.start, n_intervals * sizeof(int32_t), cudaHostAllocDefault));
+    sl.cap = n_intervals;
+  }
+  if (!sl.h2d_done) GTB_CUDA_OK(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+  *slot = &sl;
+  return GTB_OK;
 }
 
 extern "C" int gtb_ctx_set_stream(gtb_ctx *ctx, void *cuda_stream) {
@@ -52,6 +87,15 @@ extern "C" int gtb_ctx_synchronize(gtb_ctx *ctx) {
 }
 
 extern "C" const char *gtb_ctx_last_error(const gtb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int gtb_ctx_transfer_stats(const gtb_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *packed_chunks, int64_t *raw_chunks) {
+  if (!ctx) return GTB_ERR_ARG;
+  if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+  if (packed_chunks) *packed_chunks = ctx->packed_chunks;
+  if (raw_chunks) *raw_chunks = ctx->raw_chunks;
+  return GTB_OK;
+}
 
 extern "C" int64_t gtb_ctx_launch_count(const gtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

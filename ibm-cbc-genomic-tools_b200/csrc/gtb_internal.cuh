@@ -16,6 +16,22 @@ struct gtb_kernel_stat {
   double total_ms = 0.0;
 };
 
+// host-side re-encoding of query chunks before they cross PCIe (gtb_ingest.cpp)
+struct gtb_ingest;
+gtb_ingest *gtb_ingest_create(int threads);
+void gtb_ingest_destroy(gtb_ingest *p);
+int gtb_ingest_threads(const gtb_ingest *p);
+int gtb_ingest_pack(gtb_ingest *p, const int32_t *chrom, const int32_t *start, const int32_t *stop, const int8_t *strand, int64_t n,
+                    uint32_t *meta, int32_t *start_out);
+
+struct gtb_pinned_slot {                   // pinned host staging for one packed chunk
+  uint32_t *meta = nullptr;
+  int32_t *start = nullptr;
+  size_t cap = 0;                          // intervals
+  cudaEvent_t h2d_done = nullptr;
+  bool in_flight = false;
+};
+
 struct gtb_ctx {
   int device = 0;
   int sm_count = GTB_SM_COUNT_FALLBACK;
@@ -29,7 +45,15 @@ struct gtb_ctx {
   struct pending_event { const char *name; cudaEvent_t a, b; };
   std::vector<pending_event> pending;
   std::map<std::string, gtb_kernel_stat> stats;
+  // packed host->device path
+  gtb_ingest *ingest = nullptr;
+  bool ingest_tried = false;
+  gtb_pinned_slot slots[3];
+  int next_slot = 0;
+  int64_t packed_chunks = 0, raw_chunks = 0;   // how the host-resident chunks travelled (diagnostics)
+  int64_t h2d_bytes = 0, d2h_bytes = 0;        // bytes of query batches / results that crossed the host link
 };
+int gtb_ctx_ingest_ready(gtb_ctx *ctx, size_t n_intervals, gtb_pinned_slot **slot);   // gtb_ctx.cu
 
 // ---- error plumbing ---------------------------------------------------------------------------
 #define GTB_CUDA_OK(ctx, call)                                                              \

@@ -176,6 +176,27 @@ __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const 
   out[k] = total;
 }
 
+// Expands a packed chunk (start + meta, see gtb_ingest.cpp) into the SoA layout the engines read.
+__global__ void __launch_bounds__(256) unpack_kernel(int64_t n, const uint32_t *__restrict__ meta, const int32_t *__restrict__ start,
+                                                     int32_t *__restrict__ chrom, int32_t *__restrict__ stop, int8_t *__restrict__ strand) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const uint4 m = *reinterpret_cast<const uint4 *>(meta + i);
+      const int4 s = *reinterpret_cast<const int4 *>(start + i);
+      *reinterpret_cast<int4 *>(chrom + i) = make_int4((m.x >> 16) & 0x3FFF, (m.y >> 16) & 0x3FFF, (m.z >> 16) & 0x3FFF, (m.w >> 16) & 0x3FFF);
+      *reinterpret_cast<int4 *>(stop + i) = make_int4(s.x + (int)(m.x & 0xFFFF), s.y + (int)(m.y & 0xFFFF), s.z + (int)(m.z & 0xFFFF), s.w + (int)(m.w & 0xFFFF));
+      const uint32_t b = ((m.x >> 30) ? 45u : 43u) | (((m.y >> 30) ? 45u : 43u) << 8) | (((m.z >> 30) ? 45u : 43u) << 16) | (((m.w >> 30) ? 45u : 43u) << 24);
+      *reinterpret_cast<uint32_t *>(strand + i) = b;
+    } else {
+      for (int64_t j = i; j < n; j++) {
+        const uint32_t m = meta[j];
+        chrom[j] = (m >> 16) & 0x3FFF; stop[j] = start[j] + (int)(m & 0xFFFF); strand[j] = (m >> 30) ? '-' : '+';
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -398,7 +419,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   ix->d_r_stop.release(); ix->d_r_strand.release(); ix->d_r_off.release(); ix->d_direct.release();
   ix->d_err.release(); ix->d_out.release();
   for (auto &st : ix->stages) {
-    st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release();
+    st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release(); st.meta.release();
     if (st.copied) cudaEventDestroy(st.copied);
     if (st.consumed) cudaEventDestroy(st.consumed);
   }
@@ -484,7 +505,7 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
 
   // host-resident batch: chunk, stage through two device buffers, copies on copy_stream overlap
   // the kernels of the previous chunk on the compute stream.
-  const int64_t CHUNK = (int64_t)8 << 20;
+  const int64_t CHUNK = (int64_t)4 << 20;
   for (int64_t r0 = 0; r0 < queries->n_regions; r0 += CHUNK) {
     const int64_t r1 = std::min(queries->n_regions, r0 + CHUNK);
     const int64_t i0 = pass_offsets ? queries->region_offset[r0] : r0;
@@ -496,20 +517,51 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     GTB_TRY(st.chrom.reserve(ctx, ni)); GTB_TRY(st.start.reserve(ctx, ni)); GTB_TRY(st.stop.reserve(ctx, ni));
     GTB_TRY(st.strand.reserve(ctx, ni));
     cudaStream_t cs = ctx->copy_stream;
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.chrom.p, queries->chrom + i0, ni * 4, cudaMemcpyHostToDevice, cs));
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, queries->start + i0, ni * 4, cudaMemcpyHostToDevice, cs));
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.stop.p, queries->stop + i0, ni * 4, cudaMemcpyHostToDevice, cs));
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.strand.p, queries->strand + i0, ni, cudaMemcpyHostToDevice, cs));
+    // Packed path (single-interval, unweighted chunks): host threads re-encode 13 B/interval into 8 B/interval in pinned
+    // staging while the previous chunk is on the wire; unpack_kernel expands it next to the engine.
+    bool packed = false;
+    gtb_pinned_slot *slot = nullptr;
+    if (!pass_offsets && !queries->weight && ni >= 65536 && gtb_ctx_ingest_ready(ctx, ni, &slot) == GTB_OK) {
+      cudaPointerAttributes attr;
+      const bool start_is_pinned = cudaPointerGetAttributes(&attr, queries->start + i0) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      packed = gtb_ingest_pack(ctx->ingest, queries->chrom + i0, queries->start + i0, queries->stop + i0, queries->strand + i0, (int64_t)ni,
+                               slot->meta, start_is_pinned ? nullptr : slot->start) != 0;
+      if (packed) {
+        GTB_TRY(st.meta.reserve(ctx, ni));
+        GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, start_is_pinned ? queries->start + i0 : slot->start, ni * 4, cudaMemcpyHostToDevice, cs));
+        GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.meta.p, slot->meta, ni * 4, cudaMemcpyHostToDevice, cs));
+        GTB_CUDA_OK(ctx, cudaEventRecord(slot->h2d_done, cs));
+        slot->in_flight = true;
+        ctx->packed_chunks++;
+        ctx->h2d_bytes += (int64_t)ni * 8;
+      }
+    }
+    if (!packed) {
+      ctx->raw_chunks++;
+      ctx->h2d_bytes += (int64_t)ni * 13;
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.chrom.p, queries->chrom + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, queries->start + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.stop.p, queries->stop + i0, ni * 4, cudaMemcpyHostToDevice, cs));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.strand.p, queries->strand + i0, ni, cudaMemcpyHostToDevice, cs));
+    }
     if (queries->weight) {
       GTB_TRY(st.weight.reserve(ctx, nr));
       GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.weight.p, queries->weight + r0, nr * 4, cudaMemcpyHostToDevice, cs));
+      ctx->h2d_bytes += (int64_t)nr * 4;
     }
     if (pass_offsets) {
       GTB_TRY(st.off.reserve(ctx, nr + 1));
       GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.off.p, queries->region_offset + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, cs));
+      ctx->h2d_bytes += (int64_t)(nr + 1) * 8;
     }
     GTB_CUDA_OK(ctx, cudaEventRecord(st.copied, cs));
     GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied, 0));
+    if (packed) {
+      GTB_LAUNCH(ctx, "unpack", unpack_kernel, gtb_grid_for((int64_t)(ni + 3) / 4, 256, (int64_t)ctx->sm_count * 8), 256, 0, (int64_t)ni,
+                 st.meta.p, st.start.p, st.chrom.p, st.stop.p, st.strand.p);
+      GTB_TRY(gtb_check_launch(ctx));
+    }
     QueryView q;
     q.n_regions = (int64_t)nr; q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
     q.weight = queries->weight ? st.weight.p : nullptr; q.region_offset = pass_offsets ? st.off.p : nullptr;
@@ -548,6 +600,7 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
     GTB_TRY(gtb_check_launch(ctx));
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(out, ix->d_out.p, sizeof(ull) * (size_t)ix->n_regions,
                                      (mem & GTB_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(mem & GTB_MEM_DEVICE)) ctx->d2h_bytes += (int64_t)sizeof(ull) * ix->n_regions;
   }
   ull err = ~0ull;
   GTB_CUDA_OK(ctx, cudaMemcpyAsync(&err, ix->d_err.p, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));

@@ -109,6 +109,7 @@ struct gtb_index {
     dbuf<int32_t> chrom, start, stop, weight;
     dbuf<int8_t> strand;
     dbuf<int64_t> off;
+    dbuf<uint32_t> meta;                       // packed form of a chunk (gtb_ingest.cpp), expanded by unpack_kernel
     cudaEvent_t copied = nullptr, consumed = nullptr;
     bool in_flight = false;
   } stages[2];

@@ -35,7 +35,7 @@ ERR_NO_DEVICE = 100
 
 EXPORTS = [
     "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_synchronize",
-    "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_profile", "gtb_ctx_profile_report",
+    "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_transfer_stats", "gtb_ctx_profile", "gtb_ctx_profile_report",
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_finish",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
@@ -77,6 +77,7 @@ def load_library(path=LIB_PATH):
         "gtb_ctx_synchronize": (ci, [vp]),
         "gtb_ctx_last_error": (ctypes.c_char_p, [vp]),
         "gtb_ctx_launch_count": (i64, [vp]),
+        "gtb_ctx_transfer_stats": (ci, [vp, P(i64), P(i64), P(i64), P(i64)]),
         "gtb_ctx_profile": (ci, [vp, ci]),
         "gtb_ctx_profile_report": (ci, [vp, ctypes.c_char_p, ctypes.c_size_t]),
         "gtb_index_create": (ci, [vp, P(_Set), ci, u32, P(vp), P(i64)]),
@@ -182,6 +183,12 @@ class Context:
 
     def launch_count(self):
         return int(lib().gtb_ctx_launch_count(self._h))
+
+    def transfer_stats(self):
+        """{'h2d_bytes', 'd2h_bytes', 'packed_chunks', 'raw_chunks'} since the context was created."""
+        v = [ctypes.c_int64(0) for _ in range(4)]
+        self.check(lib().gtb_ctx_transfer_stats(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("h2d_bytes", "d2h_bytes", "packed_chunks", "raw_chunks"), [int(x.value) for x in v]))
 
     def profile(self, enable):
         self.check(lib().gtb_ctx_profile(self._h, int(enable)))

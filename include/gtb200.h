@@ -95,6 +95,10 @@ const char *gtb_ctx_last_error(const gtb_ctx *ctx);
 /* Kernel accounting: number of kernels launched by this context since creation / last reset, and
  * (when profiling is on) per-kernel CUDA-event times written as a JSON object into buf. */
 int64_t gtb_ctx_launch_count(const gtb_ctx *ctx);
+/* Bytes this context actually moved over the host link since creation, and how the host-resident query chunks
+ * travelled: re-encoded to 8 B/interval by the host packing pool ("packed") or in the plain 13 B/interval layout
+ * ("raw").  Any pointer may be NULL.  GTB_INGEST_THREADS=0 in the environment switches the packing pool off. */
+int  gtb_ctx_transfer_stats(const gtb_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *packed_chunks, int64_t *raw_chunks);
 int  gtb_ctx_profile(gtb_ctx *ctx, int enable);
 int  gtb_ctx_profile_report(gtb_ctx *ctx, char *buf, size_t buf_size);
 

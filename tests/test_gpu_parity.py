@@ -303,3 +303,27 @@ def test_full_size_properties(gtb, ctx, oracle):
     rc, want, _ = oracle.count(sub, regions, 0)
     got = run({k: v[:1_000_000] for k, v in dev.items()})
     assert rc == 0 and np.array_equal(got, want)
+
+
+def test_packed_host_path(gtb, ctx, oracle, monkeypatch):
+    """Host-resident chunks travel re-encoded (8 B/interval) when every query fits the packed form and in the plain
+    layout otherwise; both must give the oracle's values, as must a run with the packing pool switched off."""
+    reads = support.synth_reads(600_000, seed=41)
+    regions = support.synth_regions(4_000, seed=42)
+    odd = {k: v.copy() for k, v in reads.items()}
+    odd["stop"][123_456] = odd["start"][123_456] + 70_000          # longer than the packed length field
+    odd["strand"][400_000] = ord(".")                               # a strand byte the packed form cannot carry
+    odd["chrom"][7] = 20_000                                        # chromosome id beyond the packed field (not in the index)
+    for q in (reads, odd):
+        for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+            rc, want, _ = fn(q, regions, 0)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, 0)
+            ix.add_host(q)
+            assert np.array_equal(ix.finish(), want)
+            ix.close()
+    monkeypatch.setenv("GTB_INGEST_THREADS", "0")
+    c2 = gtb.Context(0)
+    rc, want, _ = oracle.count(reads, regions, 0)
+    assert np.array_equal(c2.overlap_count(reads, regions, 0), want)
+    c2.close()
