@@ -73,6 +73,17 @@ struct BucketView {
   const uint16_t *dir;              // [n_buckets << (ub - k)] first local slot at or after the cell start
   uint32_t *unit_off;               // [n_buckets + 1]
   int max_local;                    // largest number of slots in a bucket (excluding the catch-all)
+  // write-combining form of pass 1 (wc_partition_kernel): elements leave shared memory as full 64-byte lines, eight lines of one
+  // bucket to a 512-byte BLOCK, into block slots the CTA owns outright (CTA c owns slots [c * lines_per_cta, (c + 1) *
+  // lines_per_cta)) -- no global reservation at all.  ("line_*" below counts blocks.)
+  uint32_t lines_per_cta;
+  uint32_t *line_info;              // [grid * lines_per_cta] bucket | (elements in the block - 1) << 16
+  uint32_t *cta_lines;              // [grid] block slots used by each CTA
+  uint32_t *n_lines;                // [n_buckets] blocks per bucket (from pass 1)
+  uint32_t *line_off;               // [n_buckets + 1] exclusive scan of n_lines
+  uint32_t *line_cursor;            // [n_buckets] scatter cursors
+  uint32_t *sorted_lines;           // [total blocks] block slot | (elements - 1) << 25, grouped by bucket
+  unsigned long long *diverted;     // queries that found their bucket's ring full and took the general path
 };
 
 __device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
@@ -130,7 +141,8 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
 //   y = (u of coordinate 0 of the group) & (bucket size - 1)      z = (u of coordinate 0) >> ub
 // so that for a start coordinate s:  t = y + s,  bucket = z + (t >> ub),  bucket-local u = t & (2^ub - 1).
 template <bool COVERAGE, int VEC, int RES>
-__global__ void __launch_bounds__(PART_THREADS, PART_CTAS) bucket_partition_kernel(QueryView q, RankView rv, BucketView bv) {
+__global__ void __launch_bounds__(PART_THREADS, PART_CTAS) bucket_partition_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
+                                                                                    const __grid_constant__ BucketView bv) {
   extern __shared__ __align__(128) uint32_t smem[];
   // raw tile, filled by TMA bulk copies: chrom | start | stop (PART_TILE ints each) | strand (PART_TILE bytes)
   int32_t *s_chrom = reinterpret_cast<int32_t *>(smem);
@@ -315,6 +327,267 @@ __global__ void __launch_bounds__(PART_THREADS, PART_CTAS) bucket_partition_kern
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pass 1, write-combining form (default when the bucket count allows it)
+// ------------------------------------------------------------------------------------------------
+// The paged form above spends most of its time between barriers: rank -> scan -> reserve (global atomics) -> stage ->
+// copy out, five barriers and ~8 dependent shared-memory accesses per query (profiles/r1_experiments.md).  Here every
+// bucket has a 32-element ring in shared memory.  A query costs one shared atomic (its position in the ring, from a word that
+// also carries the ring's free space and write position) and one store.  After the round's barrier the thread that owns a bucket
+// moves every complete 16-element line of its ring to global memory with four 128-bit stores, into the next line slot of a
+// range only this CTA writes, and notes the line's bucket; a tiny kernel then groups the line slots by bucket for pass 2.
+// No scan, no staging buffer, no global reservation, two barriers per round.
+// A query that finds its ring full (more than ~16-32 queries of one 2 048-query round in one bucket, i.e. heavily skewed input)
+// takes the general rank step instead; the host watches the diverted count and goes back to the paged form if it is large.
+#ifndef GTB_WC_THREADS
+#define GTB_WC_THREADS 512
+#endif
+constexpr int WC_THREADS = GTB_WC_THREADS;
+constexpr int WC_ITEMS = 4;
+constexpr int WC_TILE = WC_THREADS * WC_ITEMS;            // 2 048 queries per round
+constexpr int WC_LINE = 16;                               // elements per line (64 bytes)
+constexpr int WC_BLOCK = 8;                               // lines per block: the unit pass 2 looks up (512 bytes of one bucket)
+constexpr int WC_BLOCK_ELEMS = WC_LINE * WC_BLOCK;
+constexpr int WC_CAP = 32;                                // ring capacity per bucket
+constexpr int WC_STRIDE = 36;                             // words between rings: 144 B keeps 16-byte alignment, spreads owners over all banks
+constexpr int WC_MAX_BUCKETS = 512;                       // one owner thread per bucket
+#ifndef GTB_WC_STAGES
+#define GTB_WC_STAGES 1
+#endif
+constexpr int WC_STAGES = GTB_WC_STAGES;                  // raw tiles in flight per CTA
+
+template <bool COVERAGE>
+__global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
+                                                                             const __grid_constant__ BucketView bv) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  // raw tiles: WC_STAGES buffers of chrom | start | stop (WC_TILE ints each) | strand (WC_TILE bytes), filled by TMA bulk copies
+  constexpr int RAW_WORDS = 3 * WC_TILE + WC_TILE / 4;
+  uint32_t *s_ring = smem + WC_STAGES * RAW_WORDS;                    // [n_buckets][WC_STRIDE]
+  uint32_t *s_word = s_ring + (size_t)bv.n_buckets * WC_STRIDE;       // [n_buckets] count of this round | free << 12 | write position << 18
+  int4 *s_pm = reinterpret_cast<int4 *>(s_word + ((bv.n_buckets + 3) & ~3u));   // [2 * n_chrom] group table
+  __shared__ __align__(8) uint64_t s_bar[WC_STAGES];
+  __shared__ uint32_t s_next_line;
+
+  for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_pm[i] = bv.pm_tab[i];
+  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_word[i] = (uint32_t)WC_CAP << 12;
+  if (threadIdx.x == 0) {
+    s_next_line = 0;
+    for (int st = 0; st < WC_STAGES; st++) mbar_init(&s_bar[st], 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const int64_t n_tiles = (q.n_regions + WC_TILE - 1) / WC_TILE;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(q.chrom) | reinterpret_cast<uintptr_t>(q.start) | reinterpret_cast<uintptr_t>(q.stop) |
+                         reinterpret_cast<uintptr_t>(q.strand)) & 15) == 0;
+  const int64_t n_full = aligned ? q.n_regions / WC_TILE : 0;         // tiles that TMA can fetch (complete, aligned)
+  const uint32_t ubmask = (1u << bv.ub) - 1u;
+  const uint32_t len_max = 0xFFFFFFFFu >> bv.ub;
+  const uint32_t n_chrom = (uint32_t)bv.n_chrom;
+  constexpr uint32_t TILE_BYTES = WC_TILE * 13;
+  const size_t line_base = (size_t)blockIdx.x * bv.lines_per_cta;
+  uint32_t diverted = 0;
+
+  auto issue = [&](int64_t tile, int st) {                             // one thread: 4 bulk copies into stage st
+    const int64_t first = tile * WC_TILE;
+    uint32_t *raw = smem + st * RAW_WORDS;
+    mbar_expect_tx(&s_bar[st], TILE_BYTES);
+    tma_bulk_g2s(raw, q.chrom + first, WC_TILE * 4, &s_bar[st]);
+    tma_bulk_g2s(raw + WC_TILE, q.start + first, WC_TILE * 4, &s_bar[st]);
+    tma_bulk_g2s(raw + 2 * WC_TILE, q.stop + first, WC_TILE * 4, &s_bar[st]);
+    tma_bulk_g2s(raw + 3 * WC_TILE, q.strand + first, WC_TILE, &s_bar[st]);
+  };
+  // The owner of a bucket appends its lines to the bucket's open block (blk: block slot of this CTA, used: lines in it) and
+  // opens the next one -- `fresh`, handed out by warp_slots -- when that is full.
+  uint32_t blk = 0xFFFFFFFFu, used = 0, last_fill = WC_LINE;
+  auto close_block = [&](uint32_t b) {
+    if (blk != 0xFFFFFFFFu) bv.line_info[line_base + blk] = b | (((used - 1u) * WC_LINE + last_fill - 1u) << 16);
+  };
+  auto flush_line = [&](uint32_t b, uint32_t pos, uint32_t fresh, uint32_t fill) {
+    if (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) { close_block(b); blk = fresh; used = 0; }
+    const uint4 *src = reinterpret_cast<const uint4 *>(s_ring + (size_t)b * WC_STRIDE + pos);
+    uint4 *dst = reinterpret_cast<uint4 *>(bv.pool + ((line_base + blk) * WC_BLOCK + used) * WC_LINE);
+    const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+    used++; last_fill = fill;
+  };
+  // line slots for a whole warp of owners with ONE shared atomic (a same-address atomic per line costs far more than the copy)
+  const int lane = threadIdx.x & 31;
+  auto warp_slots = [&](uint32_t mine) -> uint32_t {
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    uint32_t base = 0;
+    if (lane == 31 && inc) base = atomicAdd(&s_next_line, inc);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - mine;
+  };
+  uint32_t my_lines = 0;                                              // blocks of the bucket this thread owns (reported once, at the end)
+  if (threadIdx.x == 0)
+    for (int st = 0; st < WC_STAGES; st++)
+      if ((int64_t)blockIdx.x + (int64_t)st * gridDim.x < n_full) issue(blockIdx.x + (int64_t)st * gridDim.x, st);
+  uint32_t round = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, round++) {
+    // ---- load + classify: touches no shared structure that the previous round's owners may still be updating
+    int32_t c[WC_ITEMS], s[WC_ITEMS], e[WC_ITEMS];
+    uint32_t stw;
+    const int stage = (int)(round % WC_STAGES);
+    if (tile < n_full) {
+      mbar_wait(&s_bar[stage], (round / WC_STAGES) & 1u);
+      const uint32_t *raw = smem + stage * RAW_WORDS;
+      const int4 c0 = reinterpret_cast<const int4 *>(raw)[threadIdx.x], s0 = reinterpret_cast<const int4 *>(raw + WC_TILE)[threadIdx.x];
+      const int4 e0 = reinterpret_cast<const int4 *>(raw + 2 * WC_TILE)[threadIdx.x];
+      stw = (raw + 3 * WC_TILE)[threadIdx.x];
+      c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w;
+      e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w;
+    } else {
+      const int64_t first = tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS;
+      stw = 0;
+#pragma unroll
+      for (int i = 0; i < WC_ITEMS; i++) {
+        const int64_t r = first + i;
+        const bool ok = r < q.n_regions;
+        c[i] = ok ? q.chrom[r] : -1; s[i] = ok ? q.start[r] : 1; e[i] = ok ? q.stop[r] : 1;
+        stw |= (ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+') << (i * 8);
+      }
+    }
+    uint32_t elem[WC_ITEMS], bk[WC_ITEMS];                             // bk = bucket, or 0xFFFFFFFF: nothing to insert
+#pragma unroll
+    for (int i = 0; i < WC_ITEMS; i++) {
+      const uint32_t sbyte = (stw >> (i * 8)) & 0xFFu;
+      const uint32_t d = sbyte - (uint32_t)'+';                                     // '+' -> 0, '-' -> 2
+      const bool addressable = (uint32_t)c[i] < n_chrom && (d & ~2u) == 0;        // known chromosome, '+'/'-' strand
+      const int4 gt = s_pm[addressable ? 2 * c[i] + (int)(d >> 1) : 0];
+      const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
+      const uint32_t t = (uint32_t)gt.y + (uint32_t)s[i];
+      const uint32_t lu = t & ubmask;
+      const bool normal = addressable && s[i] >= 1 && s[i] <= e[i] && s[i] <= gt.x && len <= len_max && lu + len <= ubmask;
+      elem[i] = lu | (len << bv.ub);
+      bk[i] = normal ? (uint32_t)gt.z + (t >> bv.ub) : 0xFFFFFFFFu;
+      if (!normal && (uint32_t)c[i] < n_chrom) {
+        const bool nothing = addressable && s[i] >= 1 && s[i] <= e[i] && gt.x >= 0 && (gt.x == 0 || s[i] > gt.x);
+        if (!nothing)
+          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)sbyte, 1, q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
+      }
+    }
+    __syncthreads();                    // B1: raw tile consumed by everybody; ring words of the previous round are final
+    if (threadIdx.x == 0 && tile + (int64_t)WC_STAGES * gridDim.x < n_full) { fence_proxy_async(); issue(tile + (int64_t)WC_STAGES * gridDim.x, stage); }
+
+    // ---- insert: one shared atomic and one store per query
+#ifdef GTB_WC_FRONT_ONLY
+#pragma unroll
+    for (int i = 0; i < WC_ITEMS; i++) diverted += (elem[i] ^ bk[i]) & 1u;      // timing experiment: front end only
+    continue;
+#endif
+#pragma unroll
+    for (int i = 0; i < WC_ITEMS; i++) {
+      if (bk[i] != 0xFFFFFFFFu) {
+        const uint32_t w = atomicAdd(&s_word[bk[i]], 1u);
+        const uint32_t cnt = w & 0xFFFu, free_ = (w >> 12) & 0x3Fu, wp = (w >> 18) & 0x1Fu;
+        if (cnt < free_) s_ring[(size_t)bk[i] * WC_STRIDE + ((wp + cnt) & (WC_CAP - 1))] = elem[i];
+#ifndef GTB_WC_NO_DIVERT
+        else {                          // ring full: general step (exact, slow; skewed input only)
+          diverted++;
+          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)((stw >> (i * 8)) & 0xFFu), 1,
+                                  q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
+        }
+#endif
+      }
+    }
+    __syncthreads();                    // B2: all elements of the round are in the rings
+
+    // ---- owners: move complete lines out, publish the ring state for the next round
+    if ((threadIdx.x & ~31u) < bv.n_buckets) {                        // warp-uniform: the warps that hold owners
+      const uint32_t b = threadIdx.x;
+      uint32_t nl = 0, occ = 0, head = 0, cnt = 0;
+      if (b < bv.n_buckets) {
+        const uint32_t w = s_word[b];
+        const uint32_t free_ = (w >> 12) & 0x3Fu, wp = (w >> 18) & 0x1Fu;
+        cnt = w & 0xFFFu;
+        occ = (WC_CAP - free_) + min(cnt, free_);
+        head = (wp - (WC_CAP - free_)) & (WC_CAP - 1);                // always a multiple of WC_LINE
+        nl = cnt ? occ / WC_LINE : 0u;
+      }
+      const uint32_t fresh_needed = nl && (blk == 0xFFFFFFFFu || used + nl > (uint32_t)WC_BLOCK) ? 1u : 0u;     // nl <= 2 <= WC_BLOCK
+      const uint32_t fresh = warp_slots(fresh_needed);
+      for (uint32_t l = 0; l < nl; l++) { flush_line(b, head, fresh, WC_LINE); head = (head + WC_LINE) & (WC_CAP - 1); occ -= WC_LINE; }
+      my_lines += fresh_needed;
+      if (cnt) s_word[b] = ((WC_CAP - occ) << 12) | (((head + occ) & (WC_CAP - 1)) << 18);
+    }
+  }
+  __syncthreads();
+  // ---- the rings' remainders leave as partial lines
+  if ((threadIdx.x & ~31u) < bv.n_buckets) {
+    const uint32_t b = threadIdx.x;
+    uint32_t occ = 0, wp = 0;
+    if (b < bv.n_buckets) {
+      const uint32_t w = s_word[b];
+      occ = WC_CAP - ((w >> 12) & 0x3Fu); wp = (w >> 18) & 0x1Fu;
+    }
+    const uint32_t fresh_needed = occ && (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) ? 1u : 0u;
+    const uint32_t fresh = warp_slots(fresh_needed);
+    if (occ) flush_line(b, (wp - occ) & (WC_CAP - 1), fresh, occ);
+    my_lines += fresh_needed;
+    if (b < bv.n_buckets) close_block(b);
+    if (my_lines) atomicAdd(bv.n_lines + b, my_lines);
+  }
+#ifdef GTB_WC_FRONT_ONLY
+  if (diverted == 0x7FFFFFF1u) atomicAdd(bv.diverted, 1ull);
+#else
+  if (diverted) atomicAdd(bv.diverted, (unsigned long long)diverted);
+#endif
+  __syncthreads();
+  if (threadIdx.x == 0) bv.cta_lines[blockIdx.x] = s_next_line;
+}
+
+// exclusive scan of the per-bucket line counts (one CTA) and reset of the scatter cursors
+__global__ void __launch_bounds__(1024) wc_line_offsets_kernel(BucketView bv) {
+  __shared__ uint32_t s_tot[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < bv.n_buckets; base += blockDim.x) {
+    const uint32_t b = base + threadIdx.x;
+    const uint32_t u = b < bv.n_buckets ? bv.n_lines[b] : 0;
+    uint32_t inc = u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_tot[warp] = inc;
+    __syncthreads();
+    uint32_t pre = carry;
+    for (int w = 0; w < warp; w++) pre += s_tot[w];
+    if (b < bv.n_buckets) { bv.line_off[b] = pre + inc - u; bv.line_cursor[b] = 0; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = pre + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bv.line_off[bv.n_buckets] = carry;
+}
+
+// groups the line slots by bucket: CTA c walks the slots CTA c of pass 1 filled (same grid)
+__global__ void __launch_bounds__(512) wc_line_scatter_kernel(BucketView bv) {
+  __shared__ uint32_t s_cnt[WC_MAX_BUCKETS], s_base[WC_MAX_BUCKETS];
+  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const uint32_t n = bv.cta_lines[blockIdx.x];
+  const size_t first = (size_t)blockIdx.x * bv.lines_per_cta;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_cnt[bv.line_info[first + i] & 0xFFFFu], 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < bv.n_buckets; b += blockDim.x) {
+    const uint32_t c = s_cnt[b];
+    s_base[b] = bv.line_off[b] + (c ? atomicAdd(bv.line_cursor + b, c) : 0u);
+    s_cnt[b] = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t info = bv.line_info[first + i];
+    const uint32_t b = info & 0xFFFFu;
+    const uint32_t pos = s_base[b] + atomicAdd(&s_cnt[b], 1u);
+    bv.sorted_lines[pos] = (uint32_t)(first + i) | ((info >> 16) << 25);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // between the passes: work units per bucket (exclusive scan of ceil(count / unit size))
 // ------------------------------------------------------------------------------------------------
@@ -345,7 +618,7 @@ __global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
-template <bool COVERAGE>
+template <bool COVERAGE, bool LINES>
 __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketView bv, RankView rv) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int cb = bv.ub - bv.k;
@@ -357,7 +630,9 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
   uint32_t *s_h32 = s_pts + ((cap + 1) & ~1u);
   ull *s_h64 = reinterpret_cast<ull *>(s_h32);
 
-  const uint32_t total_units = bv.unit_off[bv.n_buckets];
+  // work items: 65 536-element units of the paged buckets, or 16-element lines of the write-combined ones
+  const uint32_t *w_off = LINES ? bv.line_off : bv.unit_off;
+  const uint32_t total_units = w_off[bv.n_buckets];
   const uint32_t u_begin = (uint32_t)(((ull)total_units * blockIdx.x) / gridDim.x);
   const uint32_t u_end = (uint32_t)(((ull)total_units * (blockIdx.x + 1)) / gridDim.x);
   if (u_begin >= u_end) return;
@@ -369,9 +644,9 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
   uint32_t b;
   {
     uint32_t lo = 0, hi = bv.n_buckets;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (bv.unit_off[mid] <= u_begin) lo = mid; else hi = mid; }
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (w_off[mid] <= u_begin) lo = mid; else hi = mid; }
     b = lo;
-    while (b + 1 < bv.n_buckets && bv.unit_off[b + 1] <= u_begin) b++;      // skip empty buckets sharing the offset
+    while (b + 1 < bv.n_buckets && w_off[b + 1] <= u_begin) b++;            // skip empty buckets sharing the offset
   }
   int loaded = -1;
   uint32_t n_local = 0;
@@ -413,31 +688,48 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
     __syncthreads();
   };
 
-  for (uint32_t u = u_begin; u < u_end; u++) {
-    while (b + 1 < bv.n_buckets && bv.unit_off[b + 1] <= u) b++;
+  for (uint32_t u = u_begin; u < u_end;) {
+    while (b + 1 < bv.n_buckets && w_off[b + 1] <= u) b++;
     if ((int)b != loaded) load_bucket(b);
-    const uint32_t part = u - bv.unit_off[b];
-    const uint32_t cnt = bv.cursor[b];
-    const uint32_t e_begin = part * (PAGE * UNIT_PAGES), e_end = min(cnt, e_begin + PAGE * UNIT_PAGES);
-    const uint32_t *pt = bv.page_table + (size_t)b * bv.pt_stride;
-    const uint32_t n_el = e_end - e_begin;                               // elements of this unit (e_begin is page aligned)
-    const uint32_t n_v4 = (n_el + 3) >> 2;
+    uint32_t n_el, n_v4, e_begin = 0;
+    const uint32_t *pt = nullptr;
+    if (LINES) {                                                          // all lines of this bucket inside the CTA's range
+      const uint32_t seg_end = min(u_end, w_off[b + 1]);
+      n_v4 = (seg_end - u) * (WC_BLOCK_ELEMS / 4); n_el = n_v4 * 4;
+    } else {
+      const uint32_t part = u - bv.unit_off[b];
+      const uint32_t cnt = bv.cursor[b];
+      e_begin = part * (PAGE * UNIT_PAGES);
+      const uint32_t e_end = min(cnt, e_begin + PAGE * UNIT_PAGES);
+      pt = bv.page_table + (size_t)b * bv.pt_stride;
+      n_el = e_end - e_begin;                                             // elements of this unit (e_begin is page aligned)
+      n_v4 = (n_el + 3) >> 2;
+    }
     constexpr int UNROLL = 4;
     for (uint32_t base = 0; base < n_v4; base += COUNT_THREADS * UNROLL) {
       uint4 d[UNROLL];
+      uint32_t nv[UNROLL];                                                // valid elements of each 128-bit load
 #pragma unroll
       for (int r = 0; r < UNROLL; r++) {
         const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
         d[r] = make_uint4(0, 0, 0, 0);
+        nv[r] = 0;
         if (v4 < n_v4) {
-          const uint32_t pg = (e_begin >> PAGE_SHIFT) + (v4 >> (PAGE_SHIFT - 2));
-          const uint32_t page_id = (__ldg(pt + pg) & 0xFFFFFFu) - 1;
-          d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + ((size_t)page_id << PAGE_SHIFT)) + (v4 & ((PAGE >> 2) - 1)));
+          if (LINES) {
+            const uint32_t entry = __ldg(bv.sorted_lines + u + (v4 >> 5));                       // 32 loads of 128 bits per block
+            const uint32_t fill = (entry >> 25) + 1u, q4 = (v4 & 31u) * 4u;
+            nv[r] = fill > q4 ? min(fill - q4, 4u) : 0u;
+            if (nv[r]) d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + (size_t)(entry & 0x01FFFFFFu) * WC_BLOCK_ELEMS) + (v4 & 31u));
+          } else {
+            const uint32_t pg = (e_begin >> PAGE_SHIFT) + (v4 >> (PAGE_SHIFT - 2));
+            const uint32_t page_id = (__ldg(pt + pg) & 0xFFFFFFu) - 1;
+            nv[r] = min(n_el - v4 * 4, 4u);
+            d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + ((size_t)page_id << PAGE_SHIFT)) + (v4 & ((PAGE >> 2) - 1)));
+          }
         }
       }
 #pragma unroll
       for (int r = 0; r < UNROLL; r++) {
-        const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
         const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};
         uint32_t us[4], ue[4], jS[4], pS[4];
 #pragma unroll
@@ -449,7 +741,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
           while (pS[i] < us[i]) pS[i] = s_pts[++jS[i]];                  // first slot whose point is >= start
           uint32_t jE = jS[i], pE = pS[i];
           while (pE < ue[i]) pE = s_pts[++jE];                           // ... >= stop
-          if (v4 * 4 + i < n_el) {
+          if ((uint32_t)i < nv[r]) {
             if (!COVERAGE) {
               if (jS[i] == jE) atomicAdd(&s_h32[jS[i]], 1u);
               else { atomicAdd(&s_h32[cap + jS[i]], 1u); atomicAdd(&s_h32[2 * cap + jE], 1u); }
@@ -464,6 +756,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
         }
       }
     }
+    u = LINES ? min(u_end, w_off[b + 1]) : u + 1;
   }
   __syncthreads();
   flush();
@@ -492,6 +785,14 @@ struct gtb_bucket_state {
   dbuf<ull> d_slot_u0;
   dbuf<uint16_t> d_dir;
   dbuf<uint32_t> d_pool, d_page_table, d_cursor, d_next_page, d_unit_off;
+  // write-combining form
+  bool wc_ok = false;                                   // the bucket count fits (one owner thread per bucket)
+  bool wc_off = false;                                  // switched off after a batch with many diverted queries
+  size_t wc_smem = 0;
+  dbuf<uint32_t> d_line_info, d_cta_lines, d_n_lines, d_line_off, d_line_cursor, d_sorted_lines;
+  dbuf<ull> d_diverted;
+  ull diverted_seen = 0;
+  int64_t wc_queries = 0;                               // queries sent through the write-combining form since the last check
 };
 
 static size_t count_smem_bytes(int ub, int k, int max_local, bool coverage) {
@@ -568,6 +869,8 @@ int gtb_bucket_prepare(gtb_index *ix) {
   bs->count_smem = count_smem_bytes(ub, k, max_local, cov);
   const uint32_t nb4 = (nb + 3) & ~3u;
   bs->part_smem = (size_t)PART_TILE * 13 + (size_t)PART_TILE * 8 + 64 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
+  bs->wc_ok = nb <= (uint32_t)WC_MAX_BUCKETS;
+  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)nb * WC_STRIDE * 4 + (size_t)nb4 * 4 + (size_t)std::max(ix->n_chrom, 1) * 32 + 64;
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
@@ -605,6 +908,11 @@ int gtb_bucket_prepare(gtb_index *ix) {
   GTB_TRY(bs->d_cursor.reserve(ctx, nb));
   GTB_TRY(bs->d_next_page.reserve(ctx, 1));
   GTB_TRY(bs->d_unit_off.reserve(ctx, (size_t)nb + 1));
+  GTB_TRY(bs->d_n_lines.reserve(ctx, (size_t)nb + 1));
+  GTB_TRY(bs->d_line_off.reserve(ctx, (size_t)nb + 1));
+  GTB_TRY(bs->d_line_cursor.reserve(ctx, (size_t)nb + 1));
+  GTB_TRY(bs->d_diverted.reserve(ctx, 1));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_diverted.p, 0, sizeof(ull), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   bs->ready = true; bs->failed = false;
   return GTB_OK;
@@ -624,6 +932,73 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   if (q.region_offset || q.weight) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "bucket engine takes single-interval, unweighted batches");
   const uint32_t nb = bs->n_buckets;
   const uint64_t n = (uint64_t)q.n_regions;
+  BucketView bv;
+  bv.k = bs->k; bv.ub = bs->ub; bv.n_chrom = ix->n_chrom; bv.n_class = ix->n_class; bv.n_groups = ix->n_groups;
+  bv.cls_plus = ix->h_class_of[(uint8_t)'+']; bv.cls_minus = ix->h_class_of[(uint8_t)'-'];
+  bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p; bv.pm_tab = bs->d_pm.p;
+  bv.n_buckets = nb; bv.pool = nullptr; bv.page_table = nullptr; bv.pt_stride = 0;
+  bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p; bv.gen = 0;
+  bv.lines_per_cta = 0; bv.line_info = nullptr; bv.cta_lines = nullptr; bv.n_lines = nullptr; bv.line_off = nullptr;
+  bv.line_cursor = nullptr; bv.sorted_lines = nullptr; bv.diverted = bs->d_diverted.p;
+  bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
+  bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
+  RankView rv;
+  rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p;
+
+  const bool cov = ix->op == GTB_OP_COVERAGE;
+  const size_t per_sm = 227 * 1024;
+  const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (bs->count_smem + 1024)));
+  const unsigned grid2 = (unsigned)ctx->sm_count * ctas_per_sm;
+
+  // ---- write-combining form of pass 1 (default)
+  if (bs->wc_ok && !bs->wc_off && bs->wc_smem <= ctx->smem_optin && !getenv("GTB_BUCKET_PAGED")) {
+    // skew watchdog: many queries diverted to the general path => go back to the paged form from now on.  Checked at the
+    // first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
+    if (bs->wc_queries > 0 && (q.index_base == 0 || bs->wc_queries >= ((int64_t)64 << 20))) {
+      ull host_div = 0;
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(&host_div, bs->d_diverted.p, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+      GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+      if ((int64_t)(host_div - bs->diverted_seen) > bs->wc_queries / 16) bs->wc_off = true;
+      bs->diverted_seen = host_div; bs->wc_queries = 0;
+    }
+    const int64_t wc_tiles = (q.n_regions + WC_TILE - 1) / WC_TILE;
+    const unsigned gridw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, wc_tiles));
+    const uint64_t tiles_cta = ((uint64_t)wc_tiles + gridw - 1) / gridw;
+    const uint64_t lines_per_cta = tiles_cta * (WC_TILE / WC_BLOCK_ELEMS) + nb + 1;          // block slots: full blocks + one open block per bucket
+    const uint64_t total_slots = lines_per_cta * gridw;
+    if (!bs->wc_off && total_slots < ((uint64_t)1 << 25)) {
+      GTB_TRY(bs->d_pool.reserve(ctx, (size_t)total_slots * WC_BLOCK_ELEMS));
+      GTB_TRY(bs->d_line_info.reserve(ctx, (size_t)total_slots));
+      GTB_TRY(bs->d_sorted_lines.reserve(ctx, (size_t)total_slots));
+      GTB_TRY(bs->d_cta_lines.reserve(ctx, (size_t)gridw));
+      GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_n_lines.p, 0, (size_t)nb * 4, ctx->stream));
+      bv.lines_per_cta = (uint32_t)lines_per_cta; bv.line_info = bs->d_line_info.p; bv.cta_lines = bs->d_cta_lines.p;
+      bv.n_lines = bs->d_n_lines.p; bv.line_off = bs->d_line_off.p; bv.line_cursor = bs->d_line_cursor.p;
+      bv.sorted_lines = bs->d_sorted_lines.p; bv.diverted = bs->d_diverted.p; bv.pool = bs->d_pool.p;
+      if (cov) {
+        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(wc_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->wc_smem));
+        GTB_LAUNCH(ctx, "bucket_partition", wc_partition_kernel<true>, gridw, WC_THREADS, bs->wc_smem, q, rv, bv);
+      } else {
+        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(wc_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->wc_smem));
+        GTB_LAUNCH(ctx, "bucket_partition", wc_partition_kernel<false>, gridw, WC_THREADS, bs->wc_smem, q, rv, bv);
+      }
+      GTB_TRY(gtb_check_launch(ctx));
+      GTB_LAUNCH(ctx, "bucket_line_offsets", wc_line_offsets_kernel, 1, 1024, 0, bv);
+      GTB_LAUNCH(ctx, "bucket_line_scatter", wc_line_scatter_kernel, gridw, 512, 0, bv);
+      if (cov) {
+        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+        GTB_LAUNCH(ctx, "bucket_coverage", (bucket_count_kernel<true, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+      } else {
+        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+        GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+      }
+      bs->wc_queries += q.n_regions;
+      return gtb_check_launch(ctx);
+    }
+  }
+
+  // ---- paged form
   const uint32_t pt_stride = (uint32_t)((n + PAGE - 1) / PAGE + 1);
   const uint64_t n_pages = (n + PAGE - 1) / PAGE + nb + 1;
   GTB_TRY(bs->d_pool.reserve(ctx, (size_t)n_pages * PAGE));
@@ -635,20 +1010,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   }
   GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_cursor.p, 0, (size_t)nb * 4, ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_next_page.p, 0, 4, ctx->stream));
-
-  BucketView bv;
-  bv.k = bs->k; bv.ub = bs->ub; bv.n_chrom = ix->n_chrom; bv.n_class = ix->n_class; bv.n_groups = ix->n_groups;
-  bv.cls_plus = ix->h_class_of[(uint8_t)'+']; bv.cls_minus = ix->h_class_of[(uint8_t)'-'];
-  bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p; bv.pm_tab = bs->d_pm.p;
-  bv.n_buckets = nb; bv.pool = bs->d_pool.p; bv.page_table = bs->d_page_table.p; bv.pt_stride = pt_stride;
-  bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p; bv.gen = bs->gen;
-  bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
-  bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
-  RankView rv;
-  rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
-  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p;
-
-  const bool cov = ix->op == GTB_OP_COVERAGE;
+  bv.pool = bs->d_pool.p; bv.page_table = bs->d_page_table.p; bv.pt_stride = pt_stride; bv.gen = bs->gen;
   const bool aligned = ((uintptr_t)q.chrom % 16 == 0) && ((uintptr_t)q.start % 16 == 0) && ((uintptr_t)q.stop % 16 == 0) &&
                        ((uintptr_t)q.strand % 16 == 0);          // TMA bulk copies need 16-byte aligned sources
   const int64_t n_tiles = (q.n_regions + PART_TILE - 1) / PART_TILE;
@@ -666,15 +1028,12 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
 #undef GTB_PART_LAUNCH
   GTB_TRY(gtb_check_launch(ctx));
   GTB_LAUNCH(ctx, "bucket_units", bucket_units_kernel, 1, 1024, 0, bv);
-  const size_t per_sm = 227 * 1024;
-  const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (bs->count_smem + 1024)));
-  const unsigned grid2 = (unsigned)ctx->sm_count * ctas_per_sm;
   if (cov) {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-    GTB_LAUNCH(ctx, "bucket_coverage", bucket_count_kernel<true>, grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+    GTB_LAUNCH(ctx, "bucket_coverage", (bucket_count_kernel<true, false>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
   } else {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-    GTB_LAUNCH(ctx, "bucket_count", bucket_count_kernel<false>, grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
+    GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, false>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
   }
   return gtb_check_launch(ctx);
 }
@@ -684,6 +1043,8 @@ void gtb_bucket_destroy(gtb_index *ix) {
   if (!bs) return;
   bs->d_gtab.release(); bs->d_pm.release(); bs->d_j0.release(); bs->d_slot_lu.release(); bs->d_slot_u0.release(); bs->d_dir.release();
   bs->d_pool.release(); bs->d_page_table.release(); bs->d_cursor.release(); bs->d_next_page.release(); bs->d_unit_off.release();
+  bs->d_line_info.release(); bs->d_cta_lines.release(); bs->d_n_lines.release(); bs->d_line_off.release(); bs->d_line_cursor.release();
+  bs->d_sorted_lines.release(); bs->d_diverted.release();
   delete bs;
   ix->bucket = nullptr;
 }

@@ -51,6 +51,7 @@ int gtb_ctx_ingest_ready(gtb_ctx *ctx, size_t n_intervals, gtb_pinned_slot **slo
     ctx->ingest_tried = true;
     int threads = (int)std::thread::hardware_concurrency();
     if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) threads /= w; }   // torchrun: ranks share the host
+    threads = threads * 3 / 4;                         // leave cores to the caller's thread and the driver (measured: 12 of 16 is best)
     if (threads > 32) threads = 32;
     if (const char *env = getenv("GTB_INGEST_THREADS")) threads = atoi(env);
     if (threads >= 2) ctx->ingest = gtb_ingest_create(threads);

@@ -52,6 +52,8 @@ struct gtb_ctx {
   int next_slot = 0;
   int64_t packed_chunks = 0, raw_chunks = 0;   // how the host-resident chunks travelled (diagnostics)
   int64_t h2d_bytes = 0, d2h_bytes = 0;        // bytes of query batches / results that crossed the host link
+  double pack_rate = 0.0;                      // measured packing throughput of this context's pool, intervals/s (0: not yet known)
+  int64_t pack_skipped = 0;                    // chunks sent raw because packing would have been the slower leg
 };
 int gtb_ctx_ingest_ready(gtb_ctx *ctx, size_t n_intervals, gtb_pinned_slot **slot);   // gtb_ctx.cu
 

@@ -1,6 +1,7 @@
 // gtb_overlap.cu -- overlap count / coverage: index construction, the general RANK and ENUMERATE
 // engines, finalisation, and the streaming C-ABI around them (include/gtb200.h).
 #include "gtb_rank_device.cuh"
+#include <chrono>
 #include <algorithm>
 #include <limits.h>
 
@@ -521,12 +522,19 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     // staging while the previous chunk is on the wire; unpack_kernel expands it next to the engine.
     bool packed = false;
     gtb_pinned_slot *slot = nullptr;
-    if (!pass_offsets && !queries->weight && ni >= 65536 && gtb_ctx_ingest_ready(ctx, ni, &slot) == GTB_OK) {
+    // Packing pays only while the pool re-encodes faster than the link would move the 5 bytes it saves: 13 B/interval at
+    // ~52 GB/s is 4 G intervals/s.  With several ranks per host (few threads each, shared memory bandwidth) it does not, and
+    // the chunk goes raw; the rate is re-measured every 64 chunks.
+    const bool pack_worthwhile = ctx->pack_rate == 0.0 || ctx->pack_rate > 4.2e9 || (++ctx->pack_skipped % 64) == 0;
+    if (!pass_offsets && !queries->weight && ni >= 65536 && pack_worthwhile && gtb_ctx_ingest_ready(ctx, ni, &slot) == GTB_OK) {
       cudaPointerAttributes attr;
       const bool start_is_pinned = cudaPointerGetAttributes(&attr, queries->start + i0) == cudaSuccess && attr.type == cudaMemoryTypeHost;
       cudaGetLastError();
+      const auto t0 = std::chrono::steady_clock::now();
       packed = gtb_ingest_pack(ctx->ingest, queries->chrom + i0, queries->start + i0, queries->stop + i0, queries->strand + i0, (int64_t)ni,
                                slot->meta, start_is_pinned ? nullptr : slot->start) != 0;
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt > 0) ctx->pack_rate = ctx->pack_rate == 0.0 ? (double)ni / dt : 0.5 * ctx->pack_rate + 0.5 * (double)ni / dt;
       if (packed) {
         GTB_TRY(st.meta.reserve(ctx, ni));
         GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, start_is_pinned ? queries->start + i0 : slot->start, ni * 4, cudaMemcpyHostToDevice, cs));

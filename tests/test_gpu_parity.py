@@ -19,6 +19,8 @@ def cell_k(request, monkeypatch):
     # the bucket engine's knobs ride along: cell width and bucket width (12..16 bits -> several buckets on the toy genomes)
     monkeypatch.setenv("GTB_BUCKET_K", {"3": "2", "6": "5", "10": "8"}[request.param])
     monkeypatch.setenv("GTB_BUCKET_BITS", {"3": "9", "6": "12", "10": "16"}[request.param])
+    if request.param == "6":
+        monkeypatch.setenv("GTB_BUCKET_PAGED", "1")       # the paged form of pass 1 (the write-combining form is the default)
     return request.param
 
 
