@@ -357,35 +357,58 @@ constexpr int WC_MAX_BUCKETS = 512;                       // one owner thread pe
 #endif
 constexpr int WC_STAGES = GTB_WC_STAGES;                  // raw tiles in flight per CTA
 
+// shared-memory accessors on 32-bit shared-window addresses: no generic-address arithmetic in the hot loop
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
+  uint32_t r;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
+  return r;
+}
+
 template <bool COVERAGE>
 __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
                                                                              const __grid_constant__ BucketView bv) {
   extern __shared__ __align__(128) uint32_t smem[];
   // raw tiles: WC_STAGES buffers of chrom | start | stop (WC_TILE ints each) | strand (WC_TILE bytes), filled by TMA bulk copies
   constexpr int RAW_WORDS = 3 * WC_TILE + WC_TILE / 4;
-  uint32_t *s_ring = smem + WC_STAGES * RAW_WORDS;                    // [n_buckets][WC_STRIDE]
-  uint32_t *s_word = s_ring + (size_t)bv.n_buckets * WC_STRIDE;       // [n_buckets] count of this round | free << 12 | write position << 18
-  int4 *s_pm = reinterpret_cast<int4 *>(s_word + ((bv.n_buckets + 3) & ~3u));   // [2 * n_chrom] group table
+  // (ring and word n_buckets are a sink: queries with nothing to insert go there, which keeps the insert step free of branches)
+  uint32_t *s_ring = smem + WC_STAGES * RAW_WORDS;                    // [n_buckets + 1][WC_STRIDE]
+  uint32_t *s_word = s_ring + (size_t)(bv.n_buckets + 1) * WC_STRIDE; // [n_buckets + 1] count of this round | free << 12 | write position << 18
+  int4 *s_pm = reinterpret_cast<int4 *>(s_word + ((bv.n_buckets + 4) & ~3u));   // [2 * n_chrom + 2] group table, last two = "no such group"
   __shared__ __align__(8) uint64_t s_bar[WC_STAGES];
   __shared__ uint32_t s_next_line;
 
-  for (int i = threadIdx.x; i < 2 * bv.n_chrom; i += blockDim.x) s_pm[i] = bv.pm_tab[i];
-  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_word[i] = (uint32_t)WC_CAP << 12;
+  // group entries for the hot path: x = max(largest point, 0) so that one unsigned compare covers 1 <= start <= x;
+  // w keeps the signed value for the rare general path
+  for (int i = threadIdx.x; i < 2 * bv.n_chrom + 2; i += blockDim.x) {
+    int4 g = i < 2 * bv.n_chrom ? bv.pm_tab[i] : make_int4(0, 0, 0, 0);
+    g.w = g.x; g.x = max(g.x, 0);
+    s_pm[i] = g;
+  }
+  for (uint32_t i = threadIdx.x; i <= bv.n_buckets; i += blockDim.x) s_word[i] = i < bv.n_buckets ? (uint32_t)WC_CAP << 12 : 0u;   // the sink has no room
   if (threadIdx.x == 0) {
     s_next_line = 0;
     for (int st = 0; st < WC_STAGES; st++) mbar_init(&s_bar[st], 1);
     fence_proxy_async();
   }
   __syncthreads();
+  const uint32_t a_raw = smem_u32(smem), a_ring = smem_u32(s_ring), a_word = smem_u32(s_word), a_pm = smem_u32(s_pm);
   const int64_t n_tiles = (q.n_regions + WC_TILE - 1) / WC_TILE;
   const bool aligned = ((reinterpret_cast<uintptr_t>(q.chrom) | reinterpret_cast<uintptr_t>(q.start) | reinterpret_cast<uintptr_t>(q.stop) |
                          reinterpret_cast<uintptr_t>(q.strand)) & 15) == 0;
   const int64_t n_full = aligned ? q.n_regions / WC_TILE : 0;         // tiles that TMA can fetch (complete, aligned)
-  const uint32_t ubmask = (1u << bv.ub) - 1u;
-  const uint32_t len_max = 0xFFFFFFFFu >> bv.ub;
+  const uint32_t ub = (uint32_t)bv.ub, ubmask = (1u << ub) - 1u;
+  const uint32_t len_max = 0xFFFFFFFFu >> ub;
   const uint32_t n_chrom = (uint32_t)bv.n_chrom;
   constexpr uint32_t TILE_BYTES = WC_TILE * 13;
   const size_t line_base = (size_t)blockIdx.x * bv.lines_per_cta;
+  const int lane = threadIdx.x & 31;
   uint32_t diverted = 0;
 
   auto issue = [&](int64_t tile, int st) {                             // one thread: 4 bulk copies into stage st
@@ -397,32 +420,41 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
     tma_bulk_g2s(raw + 2 * WC_TILE, q.stop + first, WC_TILE * 4, &s_bar[st]);
     tma_bulk_g2s(raw + 3 * WC_TILE, q.strand + first, WC_TILE, &s_bar[st]);
   };
-  // The owner of a bucket appends its lines to the bucket's open block (blk: block slot of this CTA, used: lines in it) and
-  // opens the next one -- `fresh`, handed out by warp_slots -- when that is full.
-  uint32_t blk = 0xFFFFFFFFu, used = 0, last_fill = WC_LINE;
-  auto close_block = [&](uint32_t b) {
-    if (blk != 0xFFFFFFFFu) bv.line_info[line_base + blk] = b | (((used - 1u) * WC_LINE + last_fill - 1u) << 16);
+  // ---- owner state (thread b owns bucket b): ring occupancy carried over (< WC_LINE), its head (0 or WC_LINE), and the open block
+  uint32_t occ = 0, head = 0;
+  uint32_t blk = 0xFFFFFFFFu, used = 0, last_fill = WC_LINE, my_blocks = 0;
+  const uint32_t a_myring = a_ring + threadIdx.x * (uint32_t)(WC_STRIDE * 4), a_myword = a_word + threadIdx.x * 4u;
+  auto close_block = [&]() {
+    if (blk != 0xFFFFFFFFu) bv.line_info[line_base + blk] = threadIdx.x | (((used - 1u) * WC_LINE + last_fill - 1u) << 16);
   };
-  auto flush_line = [&](uint32_t b, uint32_t pos, uint32_t fresh, uint32_t fill) {
-    if (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) { close_block(b); blk = fresh; used = 0; }
-    const uint4 *src = reinterpret_cast<const uint4 *>(s_ring + (size_t)b * WC_STRIDE + pos);
-    uint4 *dst = reinterpret_cast<uint4 *>(bv.pool + ((line_base + blk) * WC_BLOCK + used) * WC_LINE);
-    const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+  // one 64-byte line of the owner's ring -> the next line of the bucket's open block (`fresh` replaces a full block)
+  auto flush_line = [&](uint32_t pos, uint32_t fresh, uint32_t fill) {
+    if (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) { close_block(); blk = fresh; used = 0; }
+    const uint32_t src = a_myring + pos * 4u;
+    const uint4 a0 = lds128(src), a1 = lds128(src + 16), a2 = lds128(src + 32), a3 = lds128(src + 48);
+    uint4 *dst = reinterpret_cast<uint4 *>(bv.pool) + ((line_base + blk) * WC_BLOCK + used) * (WC_LINE / 4);
     dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
     used++; last_fill = fill;
   };
-  // line slots for a whole warp of owners with ONE shared atomic (a same-address atomic per line costs far more than the copy)
-  const int lane = threadIdx.x & 31;
-  auto warp_slots = [&](uint32_t mine) -> uint32_t {
-    uint32_t inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  // block slots for a whole warp of owners with ONE shared atomic (a same-address atomic per owner costs far more than the copy)
+  auto warp_slots = [&](bool mine) -> uint32_t {
+    const uint32_t mask = __ballot_sync(0xffffffffu, mine);
     uint32_t base = 0;
-    if (lane == 31 && inc) base = atomicAdd(&s_next_line, inc);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + inc - mine;
+    if (lane == 0 && mask) base = atomicAdd(&s_next_line, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
   };
-  uint32_t my_lines = 0;                                              // blocks of the bucket this thread owns (reported once, at the end)
+  // everything the fast classification cannot decide (rare): the reference's admission rules, then the general rank step
+  auto general = [&](int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) {
+    if ((uint32_t)c >= n_chrom) return;                                            // chromosome the index has never seen
+    const uint32_t d = sbyte - (uint32_t)'+';
+    const bool addressable = (d & ~2u) == 0;
+    const int gx = addressable ? bv.pm_tab[2 * c + (int)(d >> 1)].x : 0;
+    const bool valid = s >= 1 && s <= e;
+    const bool nothing = addressable && valid && gx >= 0 && (gx == 0 || s > gx);  // no points in the group / start beyond the last one
+    if (!nothing) special_query<COVERAGE>(bv, rv, c, s, e, (int)(int8_t)sbyte, 1, index);
+  };
+
   if (threadIdx.x == 0)
     for (int st = 0; st < WC_STAGES; st++)
       if ((int64_t)blockIdx.x + (int64_t)st * gridDim.x < n_full) issue(blockIdx.x + (int64_t)st * gridDim.x, st);
@@ -434,12 +466,11 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
     const int stage = (int)(round % WC_STAGES);
     if (tile < n_full) {
       mbar_wait(&s_bar[stage], (round / WC_STAGES) & 1u);
-      const uint32_t *raw = smem + stage * RAW_WORDS;
-      const int4 c0 = reinterpret_cast<const int4 *>(raw)[threadIdx.x], s0 = reinterpret_cast<const int4 *>(raw + WC_TILE)[threadIdx.x];
-      const int4 e0 = reinterpret_cast<const int4 *>(raw + 2 * WC_TILE)[threadIdx.x];
-      stw = (raw + 3 * WC_TILE)[threadIdx.x];
-      c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w;
-      e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w;
+      const uint32_t a = a_raw + (uint32_t)stage * (RAW_WORDS * 4) + threadIdx.x * 16u;
+      const uint4 c0 = lds128(a), s0 = lds128(a + WC_TILE * 4), e0 = lds128(a + 2 * WC_TILE * 4);
+      stw = lds32(a_raw + (uint32_t)stage * (RAW_WORDS * 4) + 3 * WC_TILE * 4 + threadIdx.x * 4u);
+      c[0] = (int)c0.x; c[1] = (int)c0.y; c[2] = (int)c0.z; c[3] = (int)c0.w; s[0] = (int)s0.x; s[1] = (int)s0.y; s[2] = (int)s0.z; s[3] = (int)s0.w;
+      e[0] = (int)e0.x; e[1] = (int)e0.y; e[2] = (int)e0.z; e[3] = (int)e0.w;
     } else {
       const int64_t first = tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS;
       stw = 0;
@@ -451,85 +482,98 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
         stw |= (ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+') << (i * 8);
       }
     }
+    // strands: '+' = 0x2B, '-' = 0x2D.  xw has 0x00 / 0x06 in the bytes of '+' / '-' queries; any other bit: a strand the fast path does not take
+    const uint32_t xw = stw ^ 0x2B2B2B2Bu;
     uint32_t elem[WC_ITEMS], bk[WC_ITEMS];                             // bk = bucket, or 0xFFFFFFFF: nothing to insert
+    uint4 g[WC_ITEMS];
 #pragma unroll
     for (int i = 0; i < WC_ITEMS; i++) {
-      const uint32_t sbyte = (stw >> (i * 8)) & 0xFFu;
-      const uint32_t d = sbyte - (uint32_t)'+';                                     // '+' -> 0, '-' -> 2
-      const bool addressable = (uint32_t)c[i] < n_chrom && (d & ~2u) == 0;        // known chromosome, '+'/'-' strand
-      const int4 gt = s_pm[addressable ? 2 * c[i] + (int)(d >> 1) : 0];
-      const uint32_t len = (uint32_t)(min(e[i], gt.x + 1) - s[i]);
-      const uint32_t t = (uint32_t)gt.y + (uint32_t)s[i];
+      const uint32_t idx = 2u * min((uint32_t)c[i], n_chrom) + ((xw >> (8 * i + 1)) & 1u);      // unknown chromosome -> an empty entry
+      g[i] = lds128(a_pm + idx * 16u);
+    }
+    uint32_t slow = (xw & 0xF9F9F9F9u) ? 0xFu : 0u;                    // bit i: item i goes through the exact general decision
+#pragma unroll
+    for (int i = 0; i < WC_ITEMS; i++) {
+      const uint32_t t = g[i].y + (uint32_t)s[i];
       const uint32_t lu = t & ubmask;
-      const bool normal = addressable && s[i] >= 1 && s[i] <= e[i] && s[i] <= gt.x && len <= len_max && lu + len <= ubmask;
-      elem[i] = lu | (len << bv.ub);
-      bk[i] = normal ? (uint32_t)gt.z + (t >> bv.ub) : 0xFFFFFFFFu;
-      if (!normal && (uint32_t)c[i] < n_chrom) {
-        const bool nothing = addressable && s[i] >= 1 && s[i] <= e[i] && gt.x >= 0 && (gt.x == 0 || s[i] > gt.x);
-        if (!nothing)
-          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)sbyte, 1, q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
-      }
+      const uint32_t len = (uint32_t)(min(e[i], (int)g[i].x + 1) - s[i]);           // e < s wraps to a huge value and fails the next test
+      const bool ok = (uint32_t)(s[i] - 1) < g[i].x && len <= len_max && lu + len <= ubmask;
+      elem[i] = lu | (len << ub);
+      bk[i] = ok ? g[i].z + (t >> ub) : 0xFFFFFFFFu;
+      slow |= ok ? 0u : (1u << i);
+    }
+    if (slow) {
+#pragma unroll
+      for (int i = 0; i < WC_ITEMS; i++)
+        if ((slow >> i) & 1u) {
+          const uint32_t sbyte = (stw >> (8 * i)) & 0xFFu;
+          const bool fast_ok = bk[i] != 0xFFFFFFFFu && ((sbyte - (uint32_t)'+') & ~2u) == 0;   // only flagged because a sibling has an odd strand
+          if (!fast_ok) {
+            bk[i] = 0xFFFFFFFFu;
+            general(c[i], s[i], e[i], sbyte, q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
+          }
+        }
     }
     __syncthreads();                    // B1: raw tile consumed by everybody; ring words of the previous round are final
     if (threadIdx.x == 0 && tile + (int64_t)WC_STAGES * gridDim.x < n_full) { fence_proxy_async(); issue(tile + (int64_t)WC_STAGES * gridDim.x, stage); }
 
-    // ---- insert: one shared atomic and one store per query
+    // ---- insert: one shared atomic and one store per query; the four atomics are issued back to back
 #ifdef GTB_WC_FRONT_ONLY
 #pragma unroll
     for (int i = 0; i < WC_ITEMS; i++) diverted += (elem[i] ^ bk[i]) & 1u;      // timing experiment: front end only
     continue;
 #endif
+    uint32_t w[WC_ITEMS], bx[WC_ITEMS];
 #pragma unroll
     for (int i = 0; i < WC_ITEMS; i++) {
-      if (bk[i] != 0xFFFFFFFFu) {
-        const uint32_t w = atomicAdd(&s_word[bk[i]], 1u);
-        const uint32_t cnt = w & 0xFFFu, free_ = (w >> 12) & 0x3Fu, wp = (w >> 18) & 0x1Fu;
-        if (cnt < free_) s_ring[(size_t)bk[i] * WC_STRIDE + ((wp + cnt) & (WC_CAP - 1))] = elem[i];
-#ifndef GTB_WC_NO_DIVERT
-        else {                          // ring full: general step (exact, slow; skewed input only)
+      bx[i] = min(bk[i], bv.n_buckets);                                // nothing to insert -> the sink
+      w[i] = atoms_add32(a_word + bx[i] * 4u, 1u);
+    }
+    slow = 0;
+#pragma unroll
+    for (int i = 0; i < WC_ITEMS; i++) {
+      const uint32_t cnt = w[i] & 0xFFFu, free_ = (w[i] >> 12) & 0x3Fu, wp = (w[i] >> 18) & (uint32_t)(WC_CAP - 1);
+      const bool fits = cnt < free_;
+      // a query that does not fit its ring stores into the sink's ring instead (and then takes the general step below)
+      sts32(a_ring + ((fits ? bx[i] : bv.n_buckets) * (uint32_t)WC_STRIDE + ((wp + cnt) & (uint32_t)(WC_CAP - 1))) * 4u, elem[i]);
+      slow |= (bk[i] != 0xFFFFFFFFu && !fits) ? (1u << i) : 0u;
+    }
+    if (slow) {                         // ring full: general step (exact, slow; skewed input only)
+#pragma unroll
+      for (int i = 0; i < WC_ITEMS; i++)
+        if ((slow >> i) & 1u) {
           diverted++;
           special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)((stw >> (i * 8)) & 0xFFu), 1,
                                   q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
         }
-#endif
-      }
     }
     __syncthreads();                    // B2: all elements of the round are in the rings
 
     // ---- owners: move complete lines out, publish the ring state for the next round
     if ((threadIdx.x & ~31u) < bv.n_buckets) {                        // warp-uniform: the warps that hold owners
-      const uint32_t b = threadIdx.x;
-      uint32_t nl = 0, occ = 0, head = 0, cnt = 0;
-      if (b < bv.n_buckets) {
-        const uint32_t w = s_word[b];
-        const uint32_t free_ = (w >> 12) & 0x3Fu, wp = (w >> 18) & 0x1Fu;
-        cnt = w & 0xFFFu;
-        occ = (WC_CAP - free_) + min(cnt, free_);
-        head = (wp - (WC_CAP - free_)) & (WC_CAP - 1);                // always a multiple of WC_LINE
-        nl = cnt ? occ / WC_LINE : 0u;
-      }
-      const uint32_t fresh_needed = nl && (blk == 0xFFFFFFFFu || used + nl > (uint32_t)WC_BLOCK) ? 1u : 0u;     // nl <= 2 <= WC_BLOCK
-      const uint32_t fresh = warp_slots(fresh_needed);
-      for (uint32_t l = 0; l < nl; l++) { flush_line(b, head, fresh, WC_LINE); head = (head + WC_LINE) & (WC_CAP - 1); occ -= WC_LINE; }
-      my_lines += fresh_needed;
-      if (cnt) s_word[b] = ((WC_CAP - occ) << 12) | (((head + occ) & (WC_CAP - 1)) << 18);
+      const bool owner = threadIdx.x < bv.n_buckets;
+      const uint32_t cnt = owner ? lds32(a_myword) & 0xFFFu : 0u;
+      occ += min(cnt, (uint32_t)WC_CAP - occ);                        // what the inserters were allowed to store
+      const uint32_t nl = occ / WC_LINE;                              // 0, 1 or 2 complete lines
+      const bool want_block = nl && (blk == 0xFFFFFFFFu || used + nl > (uint32_t)WC_BLOCK);
+      const uint32_t fresh = warp_slots(want_block);
+      my_blocks += want_block ? 1u : 0u;
+      for (uint32_t l = 0; l < nl; l++) { flush_line(head, fresh, WC_LINE); head ^= (uint32_t)WC_LINE; }
+      occ &= (uint32_t)(WC_LINE - 1);
+      if (cnt) sts32(a_myword, (((uint32_t)WC_CAP - occ) << 12) | (((head + occ) & (uint32_t)(WC_CAP - 1)) << 18));
     }
   }
   __syncthreads();
   // ---- the rings' remainders leave as partial lines
   if ((threadIdx.x & ~31u) < bv.n_buckets) {
-    const uint32_t b = threadIdx.x;
-    uint32_t occ = 0, wp = 0;
-    if (b < bv.n_buckets) {
-      const uint32_t w = s_word[b];
-      occ = WC_CAP - ((w >> 12) & 0x3Fu); wp = (w >> 18) & 0x1Fu;
-    }
-    const uint32_t fresh_needed = occ && (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) ? 1u : 0u;
-    const uint32_t fresh = warp_slots(fresh_needed);
-    if (occ) flush_line(b, (wp - occ) & (WC_CAP - 1), fresh, occ);
-    my_lines += fresh_needed;
-    if (b < bv.n_buckets) close_block(b);
-    if (my_lines) atomicAdd(bv.n_lines + b, my_lines);
+    const bool owner = threadIdx.x < bv.n_buckets;
+    const bool rest = owner && occ != 0;
+    const bool want_block = rest && (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK);
+    const uint32_t fresh = warp_slots(want_block);
+    my_blocks += want_block ? 1u : 0u;
+    if (rest) flush_line(head, fresh, occ);
+    if (owner) close_block();
+    if (my_blocks) atomicAdd(bv.n_lines + threadIdx.x, my_blocks);
   }
 #ifdef GTB_WC_FRONT_ONLY
   if (diverted == 0x7FFFFFF1u) atomicAdd(bv.diverted, 1ull);
@@ -870,7 +914,7 @@ int gtb_bucket_prepare(gtb_index *ix) {
   const uint32_t nb4 = (nb + 3) & ~3u;
   bs->part_smem = (size_t)PART_TILE * 13 + (size_t)PART_TILE * 8 + 64 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
   bs->wc_ok = nb <= (uint32_t)WC_MAX_BUCKETS;
-  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)nb * WC_STRIDE * 4 + (size_t)nb4 * 4 + (size_t)std::max(ix->n_chrom, 1) * 32 + 64;
+  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)(nb + 1) * WC_STRIDE * 4 + (size_t)(nb4 + 4) * 4 + (size_t)std::max(ix->n_chrom, 1) * 32 + 32 + 64;
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
