@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
   // (ring and word n_buckets are a sink: queries with nothing to insert go there, which keeps the insert step free of branches)
   uint32_t *s_ring = smem + WC_STAGES * RAW_WORDS;                    // [n_buckets + 1][WC_STRIDE]
   uint32_t *s_word = s_ring + (size_t)(bv.n_buckets + 1) * WC_STRIDE; // [n_buckets + 1] count of this round | free << 12 | write position << 18
-  int4 *s_pm = reinterpret_cast<int4 *>(s_word + ((bv.n_buckets + 4) & ~3u));   // [2 * n_chrom + 2] group table, last two = "no such group"
+  uint32_t *s_direct = s_word + ((bv.n_buckets + 4) & ~3u);           // [n_buckets] blocks written straight from registers (below)
+  int4 *s_pm = reinterpret_cast<int4 *>(s_direct + ((bv.n_buckets + 3) & ~3u)); // [2 * n_chrom + 2] group table, last two = "no such group"
   __shared__ __align__(8) uint64_t s_bar[WC_STAGES];
   __shared__ uint32_t s_next_line;
 
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
     s_pm[i] = g;
   }
   for (uint32_t i = threadIdx.x; i <= bv.n_buckets; i += blockDim.x) s_word[i] = i < bv.n_buckets ? (uint32_t)WC_CAP << 12 : 0u;   // the sink has no room
+  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_direct[i] = 0;
   if (threadIdx.x == 0) {
     s_next_line = 0;
     for (int st = 0; st < WC_STAGES; st++) mbar_init(&s_bar[st], 1);
@@ -523,6 +525,24 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
     for (int i = 0; i < WC_ITEMS; i++) diverted += (elem[i] ^ bk[i]) & 1u;      // timing experiment: front end only
     continue;
 #endif
+    // Position-sorted input (what -S promises, and what aligners emit): the 128 queries of a warp fall into one bucket.  They
+    // would overfill its ring at once, and they need no combining either: the warp writes them as one full 512-byte block.
+    {
+      const uint32_t lead = __shfl_sync(0xffffffffu, bk[0], 0);
+      const bool same = lead != 0xFFFFFFFFu && bk[0] == lead && bk[1] == lead && bk[2] == lead && bk[3] == lead;
+      if (__all_sync(0xffffffffu, same)) {
+        uint32_t slot = 0;
+        if (lane == 0) {
+          slot = atomicAdd(&s_next_line, 1u);
+          atomicAdd(&s_direct[lead], 1u);
+          bv.line_info[line_base + slot] = lead | ((uint32_t)(WC_BLOCK_ELEMS - 1) << 16);
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        reinterpret_cast<uint4 *>(bv.pool)[(line_base + slot) * (WC_BLOCK_ELEMS / 4) + lane] = make_uint4(elem[0], elem[1], elem[2], elem[3]);
+#pragma unroll
+        for (int i = 0; i < WC_ITEMS; i++) bk[i] = 0xFFFFFFFFu;        // nothing left for the rings
+      }
+    }
     uint32_t w[WC_ITEMS], bx[WC_ITEMS];
 #pragma unroll
     for (int i = 0; i < WC_ITEMS; i++) {
@@ -572,7 +592,7 @@ __global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __gri
     const uint32_t fresh = warp_slots(want_block);
     my_blocks += want_block ? 1u : 0u;
     if (rest) flush_line(head, fresh, occ);
-    if (owner) close_block();
+    if (owner) { close_block(); my_blocks += s_direct[threadIdx.x]; }
     if (my_blocks) atomicAdd(bv.n_lines + threadIdx.x, my_blocks);
   }
 #ifdef GTB_WC_FRONT_ONLY
@@ -781,10 +801,27 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
 #pragma unroll
         for (int i = 0; i < 4; i++) pS[i] = s_pts[jS[i]];
 #pragma unroll
+        uint32_t jEv[4];
+#pragma unroll
         for (int i = 0; i < 4; i++) {
           while (pS[i] < us[i]) pS[i] = s_pts[++jS[i]];                  // first slot whose point is >= start
           uint32_t jE = jS[i], pE = pS[i];
           while (pE < ue[i]) pE = s_pts[++jE];                           // ... >= stop
+          jEv[i] = jE;
+        }
+        // Sorted input: the whole warp (4 x 32 consecutive elements) sits in one slot; one atomic instead of 128 on one address
+        if (!COVERAGE) {
+          const uint32_t j0s = __shfl_sync(0xffffffffu, jS[0], 0);
+          const bool same = nv[r] == 4u && jS[0] == j0s && jS[1] == j0s && jS[2] == j0s && jS[3] == j0s && jEv[0] == j0s && jEv[1] == j0s &&
+                            jEv[2] == j0s && jEv[3] == j0s;
+          if (__all_sync(0xffffffffu, same)) {
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_h32[j0s], 128u);
+            continue;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t jE = jEv[i];
           if ((uint32_t)i < nv[r]) {
             if (!COVERAGE) {
               if (jS[i] == jE) atomicAdd(&s_h32[jS[i]], 1u);
@@ -891,7 +928,10 @@ int gtb_bucket_prepare(gtb_index *ix) {
   // which is harmless because no element is ever produced for them.
   for (size_t j = 1; j < slot_u.size(); j++) if (slot_u[j] < slot_u[j - 1]) slot_u[j] = slot_u[j - 1];
   const ull total_u = std::max<ull>(cells << k, 1);
+  // bucket width: 2^24 u at most (the element keeps 32 - ub bits for the length), narrower while that leaves fewer than 256
+  // buckets -- the write-combining pass wants <= ~8 queries per bucket and round (-i halves the axis: 2^23 there)
   int ub = 24;
+  while (ub > 20 && ub > k + 1 && ((total_u + ((ull)1 << ub) - 1) >> ub) < 256) ub--;
   if (const char *env = getenv("GTB_BUCKET_BITS")) ub = std::max(k + 1, std::min(27, atoi(env)));
   if (ub < k + 1) ub = k + 1;
   std::vector<int32_t> j0;
@@ -913,8 +953,9 @@ int gtb_bucket_prepare(gtb_index *ix) {
   bs->count_smem = count_smem_bytes(ub, k, max_local, cov);
   const uint32_t nb4 = (nb + 3) & ~3u;
   bs->part_smem = (size_t)PART_TILE * 13 + (size_t)PART_TILE * 8 + 64 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
-  bs->wc_ok = nb <= (uint32_t)WC_MAX_BUCKETS;
-  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)(nb + 1) * WC_STRIDE * 4 + (size_t)(nb4 + 4) * 4 + (size_t)std::max(ix->n_chrom, 1) * 32 + 32 + 64;
+  // with fewer than 256 buckets a 2 048-query round overfills the 32-element rings too often; GTB_BUCKET_WC=1 forces it (tests)
+  bs->wc_ok = nb <= (uint32_t)WC_MAX_BUCKETS && (nb >= 256 || getenv("GTB_BUCKET_WC") != nullptr);
+  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)(nb + 1) * WC_STRIDE * 4 + (size_t)(nb4 + 4) * 8 + (size_t)std::max(ix->n_chrom, 1) * 32 + 32 + 64;
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
@@ -1038,6 +1079,14 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
         GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
       }
       bs->wc_queries += q.n_regions;
+      if (getenv("GTB_DEBUG_WC")) {                                      // diagnostics: how the batch travelled
+        ull host_div = 0; uint32_t blocks = 0;
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(&host_div, bs->d_diverted.p, sizeof(ull), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&blocks, bs->d_line_off.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[gtb wc] queries %lld buckets %u blocks %u (%.1f elements/block) diverted so far %llu\n", (long long)q.n_regions, nb, blocks,
+                blocks ? (double)q.n_regions / blocks : 0.0, host_div);
+      }
       return gtb_check_launch(ctx);
     }
   }
