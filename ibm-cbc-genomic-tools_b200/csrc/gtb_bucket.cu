@@ -29,6 +29,7 @@
 // end of its bucket, strand bytes other than '+'/'-', invalid intervals) takes the general rank
 // step inline in pass 1.  Finalisation is the RANK engine's.
 #include "gtb_rank_device.cuh"
+#include "gtb_wc_partition.cuh"
 #include <algorithm>
 
 namespace {
@@ -73,24 +74,11 @@ struct BucketView {
   const uint16_t *dir;              // [n_buckets << (ub - k)] first local slot at or after the cell start
   uint32_t *unit_off;               // [n_buckets + 1]
   int max_local;                    // largest number of slots in a bucket (excluding the catch-all)
-  // write-combining form of pass 1 (wc_partition_kernel): elements leave shared memory as full 64-byte lines, eight lines of one
-  // bucket to a 512-byte BLOCK, into block slots the CTA owns outright (CTA c owns slots [c * lines_per_cta, (c + 1) *
-  // lines_per_cta)) -- no global reservation at all.  ("line_*" below counts blocks.)
-  uint32_t lines_per_cta;
-  uint32_t *line_info;              // [grid * lines_per_cta] bucket | (elements in the block - 1) << 16
-  uint32_t *cta_lines;              // [grid] block slots used by each CTA
-  uint32_t *n_lines;                // [n_buckets] blocks per bucket (from pass 1)
-  uint32_t *line_off;               // [n_buckets + 1] exclusive scan of n_lines
-  uint32_t *line_cursor;            // [n_buckets] scatter cursors
-  uint32_t *sorted_lines;           // [total blocks] block slot | (elements - 1) << 25, grouped by bucket
-  unsigned long long *diverted;     // queries that found their bucket's ring full and took the general path
+  // write-combining form of pass 1 (gtb_wc_partition.cuh): what pass 2 reads of it
+  const uint32_t *line_off;         // [n_buckets + 1] first block of each bucket in sorted_lines
+  const uint32_t *sorted_lines;     // [total blocks] block slot | (elements - 1) << 25, grouped by bucket
 };
 
-__device__ __forceinline__ uint4 ldg_stream128(const uint4 *p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
 __device__ __forceinline__ void red_add64(ull *p, ull v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
   uint32_t v;
@@ -98,24 +86,6 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
   return v;
 }
 
-// ---- TMA bulk copy (global -> shared) with mbarrier completion, sm_90+/sm_100 PTX -----------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // The rare queries an element cannot describe: admission checks of the reference, then the general
 // rank step (binary search in global memory).
@@ -132,6 +102,52 @@ __device__ __noinline__ void special_query(const BucketView &bv, const RankView 
   const int gb = rv.goff[g], ge = rv.goff[g + 1];
   if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
 }
+
+// The overlap engines' front for the write-combining partition (gtb_wc_partition.cuh).  Table: one 16-byte entry per
+// (chromosome, '+'/'-') group, x = max(largest evaluation point, 0) so that one unsigned compare covers 1 <= start <= x,
+// y = (u of coordinate 0 of the group) & (bucket size - 1), z = (u of coordinate 0) >> ub, w = the signed largest point;
+// the last two entries mean "no such group".  For a start coordinate s:  t = y + s,  bucket = z + (t >> ub),  bucket-local
+// u = t & (2^ub - 1);  element = local u | length << ub.
+template <bool COVERAGE>
+struct OverlapFront {
+  static constexpr bool FAIL_IS_SLOW = true;
+  RankView rv;
+  BucketView bv;
+  __device__ __forceinline__ uint32_t table_size() const { return 2u * (uint32_t)bv.n_chrom + 2u; }
+  __device__ __forceinline__ uint4 table_entry(uint32_t i) const {
+    int4 g = i < 2u * (uint32_t)bv.n_chrom ? bv.pm_tab[i] : make_int4(0, 0, 0, 0);
+    g.w = g.x; g.x = max(g.x, 0);
+    return make_uint4((uint32_t)g.x, (uint32_t)g.y, (uint32_t)g.z, (uint32_t)g.w);
+  }
+  __device__ __forceinline__ uint32_t table_index(int32_t c, uint32_t xw, int i) const {
+    return 2u * min((uint32_t)c, (uint32_t)bv.n_chrom) + ((xw >> (8 * i + 1)) & 1u);          // unknown chromosome -> an empty entry
+  }
+  __device__ __forceinline__ uint32_t slow_mask(uint32_t xw) const { return (xw & 0xF9F9F9F9u) ? 0xFu : 0u; }   // a strand other than '+'/'-'
+  __device__ __forceinline__ uint32_t classify(uint4 g, int32_t s, int32_t e, uint32_t &elem) const {
+    const uint32_t ub = (uint32_t)bv.ub, ubmask = (1u << ub) - 1u, len_max = 0xFFFFFFFFu >> ub;
+    const uint32_t t = g.y + (uint32_t)s;
+    const uint32_t lu = t & ubmask;
+    const uint32_t len = (uint32_t)(min(e, (int)g.x + 1) - s);                                // e < s wraps to a huge value and fails the next test
+    const bool ok = (uint32_t)(s - 1) < g.x && len <= len_max && lu + len <= ubmask;
+    elem = lu | (len << ub);
+    return ok ? g.z + (t >> ub) : WC_NONE;
+  }
+  // everything the fast classification cannot decide (rare): the reference's admission rules, then the general rank step
+  __device__ __forceinline__ uint32_t resolve(uint32_t bucket, int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) const {
+    const uint32_t d = sbyte - (uint32_t)'+';
+    const bool addressable = (d & ~2u) == 0;
+    if (bucket != WC_NONE && addressable) return bucket;                                       // only flagged because a sibling has an odd strand
+    if ((uint32_t)c >= (uint32_t)bv.n_chrom) return WC_NONE;                                   // chromosome the index has never seen
+    const int gx = addressable ? bv.pm_tab[2 * c + (int)(d >> 1)].x : 0;
+    const bool valid = s >= 1 && s <= e;
+    const bool nothing = addressable && valid && gx >= 0 && (gx == 0 || s > gx);              // no points in the group / start beyond the last one
+    if (!nothing) special_query<COVERAGE>(bv, rv, c, s, e, (int)(int8_t)sbyte, 1, index);
+    return WC_NONE;
+  }
+  __device__ __forceinline__ void divert(int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) const {
+    special_query<COVERAGE>(bv, rv, c, s, e, (int)(int8_t)sbyte, 1, index);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // pass 1
@@ -329,330 +345,6 @@ __global__ void __launch_bounds__(PART_THREADS, PART_CTAS) bucket_partition_kern
 
 
 // ------------------------------------------------------------------------------------------------
-// pass 1, write-combining form (default when the bucket count allows it)
-// ------------------------------------------------------------------------------------------------
-// The paged form above spends most of its time between barriers: rank -> scan -> reserve (global atomics) -> stage ->
-// copy out, five barriers and ~8 dependent shared-memory accesses per query (profiles/r1_experiments.md).  Here every
-// bucket has a 32-element ring in shared memory.  A query costs one shared atomic (its position in the ring, from a word that
-// also carries the ring's free space and write position) and one store.  After the round's barrier the thread that owns a bucket
-// moves every complete 16-element line of its ring to global memory with four 128-bit stores, into the next line slot of a
-// range only this CTA writes, and notes the line's bucket; a tiny kernel then groups the line slots by bucket for pass 2.
-// No scan, no staging buffer, no global reservation, two barriers per round.
-// A query that finds its ring full (more than ~16-32 queries of one 2 048-query round in one bucket, i.e. heavily skewed input)
-// takes the general rank step instead; the host watches the diverted count and goes back to the paged form if it is large.
-#ifndef GTB_WC_THREADS
-#define GTB_WC_THREADS 512
-#endif
-constexpr int WC_THREADS = GTB_WC_THREADS;
-constexpr int WC_ITEMS = 4;
-constexpr int WC_TILE = WC_THREADS * WC_ITEMS;            // 2 048 queries per round
-constexpr int WC_LINE = 16;                               // elements per line (64 bytes)
-constexpr int WC_BLOCK = 8;                               // lines per block: the unit pass 2 looks up (512 bytes of one bucket)
-constexpr int WC_BLOCK_ELEMS = WC_LINE * WC_BLOCK;
-constexpr int WC_CAP = 32;                                // ring capacity per bucket
-constexpr int WC_STRIDE = 36;                             // words between rings: 144 B keeps 16-byte alignment, spreads owners over all banks
-constexpr int WC_MAX_BUCKETS = 512;                       // one owner thread per bucket
-#ifndef GTB_WC_STAGES
-#define GTB_WC_STAGES 1
-#endif
-constexpr int WC_STAGES = GTB_WC_STAGES;                  // raw tiles in flight per CTA
-
-// shared-memory accessors on 32-bit shared-window addresses: no generic-address arithmetic in the hot loop
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t atoms_add32(uint32_t a, uint32_t v) {
-  uint32_t r;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
-  return r;
-}
-
-template <bool COVERAGE>
-__global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
-                                                                             const __grid_constant__ BucketView bv) {
-  extern __shared__ __align__(128) uint32_t smem[];
-  // raw tiles: WC_STAGES buffers of chrom | start | stop (WC_TILE ints each) | strand (WC_TILE bytes), filled by TMA bulk copies
-  constexpr int RAW_WORDS = 3 * WC_TILE + WC_TILE / 4;
-  // (ring and word n_buckets are a sink: queries with nothing to insert go there, which keeps the insert step free of branches)
-  uint32_t *s_ring = smem + WC_STAGES * RAW_WORDS;                    // [n_buckets + 1][WC_STRIDE]
-  uint32_t *s_word = s_ring + (size_t)(bv.n_buckets + 1) * WC_STRIDE; // [n_buckets + 1] count of this round | free << 12 | write position << 18
-  uint32_t *s_direct = s_word + ((bv.n_buckets + 4) & ~3u);           // [n_buckets] blocks written straight from registers (below)
-  int4 *s_pm = reinterpret_cast<int4 *>(s_direct + ((bv.n_buckets + 3) & ~3u)); // [2 * n_chrom + 2] group table, last two = "no such group"
-  __shared__ __align__(8) uint64_t s_bar[WC_STAGES];
-  __shared__ uint32_t s_next_line;
-
-  // group entries for the hot path: x = max(largest point, 0) so that one unsigned compare covers 1 <= start <= x;
-  // w keeps the signed value for the rare general path
-  for (int i = threadIdx.x; i < 2 * bv.n_chrom + 2; i += blockDim.x) {
-    int4 g = i < 2 * bv.n_chrom ? bv.pm_tab[i] : make_int4(0, 0, 0, 0);
-    g.w = g.x; g.x = max(g.x, 0);
-    s_pm[i] = g;
-  }
-  for (uint32_t i = threadIdx.x; i <= bv.n_buckets; i += blockDim.x) s_word[i] = i < bv.n_buckets ? (uint32_t)WC_CAP << 12 : 0u;   // the sink has no room
-  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_direct[i] = 0;
-  if (threadIdx.x == 0) {
-    s_next_line = 0;
-    for (int st = 0; st < WC_STAGES; st++) mbar_init(&s_bar[st], 1);
-    fence_proxy_async();
-  }
-  __syncthreads();
-  const uint32_t a_raw = smem_u32(smem), a_ring = smem_u32(s_ring), a_word = smem_u32(s_word), a_pm = smem_u32(s_pm);
-  const int64_t n_tiles = (q.n_regions + WC_TILE - 1) / WC_TILE;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(q.chrom) | reinterpret_cast<uintptr_t>(q.start) | reinterpret_cast<uintptr_t>(q.stop) |
-                         reinterpret_cast<uintptr_t>(q.strand)) & 15) == 0;
-  const int64_t n_full = aligned ? q.n_regions / WC_TILE : 0;         // tiles that TMA can fetch (complete, aligned)
-  const uint32_t ub = (uint32_t)bv.ub, ubmask = (1u << ub) - 1u;
-  const uint32_t len_max = 0xFFFFFFFFu >> ub;
-  const uint32_t n_chrom = (uint32_t)bv.n_chrom;
-  constexpr uint32_t TILE_BYTES = WC_TILE * 13;
-  const size_t line_base = (size_t)blockIdx.x * bv.lines_per_cta;
-  const int lane = threadIdx.x & 31;
-  uint32_t diverted = 0;
-
-  auto issue = [&](int64_t tile, int st) {                             // one thread: 4 bulk copies into stage st
-    const int64_t first = tile * WC_TILE;
-    uint32_t *raw = smem + st * RAW_WORDS;
-    mbar_expect_tx(&s_bar[st], TILE_BYTES);
-    tma_bulk_g2s(raw, q.chrom + first, WC_TILE * 4, &s_bar[st]);
-    tma_bulk_g2s(raw + WC_TILE, q.start + first, WC_TILE * 4, &s_bar[st]);
-    tma_bulk_g2s(raw + 2 * WC_TILE, q.stop + first, WC_TILE * 4, &s_bar[st]);
-    tma_bulk_g2s(raw + 3 * WC_TILE, q.strand + first, WC_TILE, &s_bar[st]);
-  };
-  // ---- owner state (thread b owns bucket b): ring occupancy carried over (< WC_LINE), its head (0 or WC_LINE), and the open block
-  uint32_t occ = 0, head = 0;
-  uint32_t blk = 0xFFFFFFFFu, used = 0, last_fill = WC_LINE, my_blocks = 0;
-  const uint32_t a_myring = a_ring + threadIdx.x * (uint32_t)(WC_STRIDE * 4), a_myword = a_word + threadIdx.x * 4u;
-  auto close_block = [&]() {
-    if (blk != 0xFFFFFFFFu) bv.line_info[line_base + blk] = threadIdx.x | (((used - 1u) * WC_LINE + last_fill - 1u) << 16);
-  };
-  // one 64-byte line of the owner's ring -> the next line of the bucket's open block (`fresh` replaces a full block)
-  auto flush_line = [&](uint32_t pos, uint32_t fresh, uint32_t fill) {
-    if (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK) { close_block(); blk = fresh; used = 0; }
-    const uint32_t src = a_myring + pos * 4u;
-    const uint4 a0 = lds128(src), a1 = lds128(src + 16), a2 = lds128(src + 32), a3 = lds128(src + 48);
-    uint4 *dst = reinterpret_cast<uint4 *>(bv.pool) + ((line_base + blk) * WC_BLOCK + used) * (WC_LINE / 4);
-    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
-    used++; last_fill = fill;
-  };
-  // block slots for a whole warp of owners with ONE shared atomic (a same-address atomic per owner costs far more than the copy)
-  auto warp_slots = [&](bool mine) -> uint32_t {
-    const uint32_t mask = __ballot_sync(0xffffffffu, mine);
-    uint32_t base = 0;
-    if (lane == 0 && mask) base = atomicAdd(&s_next_line, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-  };
-  // everything the fast classification cannot decide (rare): the reference's admission rules, then the general rank step
-  auto general = [&](int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) {
-    if ((uint32_t)c >= n_chrom) return;                                            // chromosome the index has never seen
-    const uint32_t d = sbyte - (uint32_t)'+';
-    const bool addressable = (d & ~2u) == 0;
-    const int gx = addressable ? bv.pm_tab[2 * c + (int)(d >> 1)].x : 0;
-    const bool valid = s >= 1 && s <= e;
-    const bool nothing = addressable && valid && gx >= 0 && (gx == 0 || s > gx);  // no points in the group / start beyond the last one
-    if (!nothing) special_query<COVERAGE>(bv, rv, c, s, e, (int)(int8_t)sbyte, 1, index);
-  };
-
-  if (threadIdx.x == 0)
-    for (int st = 0; st < WC_STAGES; st++)
-      if ((int64_t)blockIdx.x + (int64_t)st * gridDim.x < n_full) issue(blockIdx.x + (int64_t)st * gridDim.x, st);
-  uint32_t round = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, round++) {
-    // ---- load + classify: touches no shared structure that the previous round's owners may still be updating
-    int32_t c[WC_ITEMS], s[WC_ITEMS], e[WC_ITEMS];
-    uint32_t stw;
-    const int stage = (int)(round % WC_STAGES);
-    if (tile < n_full) {
-      mbar_wait(&s_bar[stage], (round / WC_STAGES) & 1u);
-      const uint32_t a = a_raw + (uint32_t)stage * (RAW_WORDS * 4) + threadIdx.x * 16u;
-      const uint4 c0 = lds128(a), s0 = lds128(a + WC_TILE * 4), e0 = lds128(a + 2 * WC_TILE * 4);
-      stw = lds32(a_raw + (uint32_t)stage * (RAW_WORDS * 4) + 3 * WC_TILE * 4 + threadIdx.x * 4u);
-      c[0] = (int)c0.x; c[1] = (int)c0.y; c[2] = (int)c0.z; c[3] = (int)c0.w; s[0] = (int)s0.x; s[1] = (int)s0.y; s[2] = (int)s0.z; s[3] = (int)s0.w;
-      e[0] = (int)e0.x; e[1] = (int)e0.y; e[2] = (int)e0.z; e[3] = (int)e0.w;
-    } else {
-      const int64_t first = tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS;
-      stw = 0;
-#pragma unroll
-      for (int i = 0; i < WC_ITEMS; i++) {
-        const int64_t r = first + i;
-        const bool ok = r < q.n_regions;
-        c[i] = ok ? q.chrom[r] : -1; s[i] = ok ? q.start[r] : 1; e[i] = ok ? q.stop[r] : 1;
-        stw |= (ok ? (unsigned)(uint8_t)q.strand[r] : (unsigned)'+') << (i * 8);
-      }
-    }
-    // strands: '+' = 0x2B, '-' = 0x2D.  xw has 0x00 / 0x06 in the bytes of '+' / '-' queries; any other bit: a strand the fast path does not take
-    const uint32_t xw = stw ^ 0x2B2B2B2Bu;
-    uint32_t elem[WC_ITEMS], bk[WC_ITEMS];                             // bk = bucket, or 0xFFFFFFFF: nothing to insert
-    uint4 g[WC_ITEMS];
-#pragma unroll
-    for (int i = 0; i < WC_ITEMS; i++) {
-      const uint32_t idx = 2u * min((uint32_t)c[i], n_chrom) + ((xw >> (8 * i + 1)) & 1u);      // unknown chromosome -> an empty entry
-      g[i] = lds128(a_pm + idx * 16u);
-    }
-    uint32_t slow = (xw & 0xF9F9F9F9u) ? 0xFu : 0u;                    // bit i: item i goes through the exact general decision
-#pragma unroll
-    for (int i = 0; i < WC_ITEMS; i++) {
-      const uint32_t t = g[i].y + (uint32_t)s[i];
-      const uint32_t lu = t & ubmask;
-      const uint32_t len = (uint32_t)(min(e[i], (int)g[i].x + 1) - s[i]);           // e < s wraps to a huge value and fails the next test
-      const bool ok = (uint32_t)(s[i] - 1) < g[i].x && len <= len_max && lu + len <= ubmask;
-      elem[i] = lu | (len << ub);
-      bk[i] = ok ? g[i].z + (t >> ub) : 0xFFFFFFFFu;
-      slow |= ok ? 0u : (1u << i);
-    }
-    if (slow) {
-#pragma unroll
-      for (int i = 0; i < WC_ITEMS; i++)
-        if ((slow >> i) & 1u) {
-          const uint32_t sbyte = (stw >> (8 * i)) & 0xFFu;
-          const bool fast_ok = bk[i] != 0xFFFFFFFFu && ((sbyte - (uint32_t)'+') & ~2u) == 0;   // only flagged because a sibling has an odd strand
-          if (!fast_ok) {
-            bk[i] = 0xFFFFFFFFu;
-            general(c[i], s[i], e[i], sbyte, q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
-          }
-        }
-    }
-    __syncthreads();                    // B1: raw tile consumed by everybody; ring words of the previous round are final
-    if (threadIdx.x == 0 && tile + (int64_t)WC_STAGES * gridDim.x < n_full) { fence_proxy_async(); issue(tile + (int64_t)WC_STAGES * gridDim.x, stage); }
-
-    // ---- insert: one shared atomic and one store per query; the four atomics are issued back to back
-#ifdef GTB_WC_FRONT_ONLY
-#pragma unroll
-    for (int i = 0; i < WC_ITEMS; i++) diverted += (elem[i] ^ bk[i]) & 1u;      // timing experiment: front end only
-    continue;
-#endif
-    // Position-sorted input (what -S promises, and what aligners emit): the 128 queries of a warp fall into one bucket.  They
-    // would overfill its ring at once, and they need no combining either: the warp writes them as one full 512-byte block.
-    {
-      const uint32_t lead = __shfl_sync(0xffffffffu, bk[0], 0);
-      const bool same = lead != 0xFFFFFFFFu && bk[0] == lead && bk[1] == lead && bk[2] == lead && bk[3] == lead;
-      if (__all_sync(0xffffffffu, same)) {
-        uint32_t slot = 0;
-        if (lane == 0) {
-          slot = atomicAdd(&s_next_line, 1u);
-          atomicAdd(&s_direct[lead], 1u);
-          bv.line_info[line_base + slot] = lead | ((uint32_t)(WC_BLOCK_ELEMS - 1) << 16);
-        }
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        reinterpret_cast<uint4 *>(bv.pool)[(line_base + slot) * (WC_BLOCK_ELEMS / 4) + lane] = make_uint4(elem[0], elem[1], elem[2], elem[3]);
-#pragma unroll
-        for (int i = 0; i < WC_ITEMS; i++) bk[i] = 0xFFFFFFFFu;        // nothing left for the rings
-      }
-    }
-    uint32_t w[WC_ITEMS], bx[WC_ITEMS];
-#pragma unroll
-    for (int i = 0; i < WC_ITEMS; i++) {
-      bx[i] = min(bk[i], bv.n_buckets);                                // nothing to insert -> the sink
-      w[i] = atoms_add32(a_word + bx[i] * 4u, 1u);
-    }
-    slow = 0;
-#pragma unroll
-    for (int i = 0; i < WC_ITEMS; i++) {
-      const uint32_t cnt = w[i] & 0xFFFu, free_ = (w[i] >> 12) & 0x3Fu, wp = (w[i] >> 18) & (uint32_t)(WC_CAP - 1);
-      const bool fits = cnt < free_;
-      // a query that does not fit its ring stores into the sink's ring instead (and then takes the general step below)
-      sts32(a_ring + ((fits ? bx[i] : bv.n_buckets) * (uint32_t)WC_STRIDE + ((wp + cnt) & (uint32_t)(WC_CAP - 1))) * 4u, elem[i]);
-      slow |= (bk[i] != 0xFFFFFFFFu && !fits) ? (1u << i) : 0u;
-    }
-    if (slow) {                         // ring full: general step (exact, slow; skewed input only)
-#pragma unroll
-      for (int i = 0; i < WC_ITEMS; i++)
-        if ((slow >> i) & 1u) {
-          diverted++;
-          special_query<COVERAGE>(bv, rv, c[i], s[i], e[i], (int)(int8_t)((stw >> (i * 8)) & 0xFFu), 1,
-                                  q.index_base + tile * WC_TILE + (int64_t)threadIdx.x * WC_ITEMS + i);
-        }
-    }
-    __syncthreads();                    // B2: all elements of the round are in the rings
-
-    // ---- owners: move complete lines out, publish the ring state for the next round
-    if ((threadIdx.x & ~31u) < bv.n_buckets) {                        // warp-uniform: the warps that hold owners
-      const bool owner = threadIdx.x < bv.n_buckets;
-      const uint32_t cnt = owner ? lds32(a_myword) & 0xFFFu : 0u;
-      occ += min(cnt, (uint32_t)WC_CAP - occ);                        // what the inserters were allowed to store
-      const uint32_t nl = occ / WC_LINE;                              // 0, 1 or 2 complete lines
-      const bool want_block = nl && (blk == 0xFFFFFFFFu || used + nl > (uint32_t)WC_BLOCK);
-      const uint32_t fresh = warp_slots(want_block);
-      my_blocks += want_block ? 1u : 0u;
-      for (uint32_t l = 0; l < nl; l++) { flush_line(head, fresh, WC_LINE); head ^= (uint32_t)WC_LINE; }
-      occ &= (uint32_t)(WC_LINE - 1);
-      if (cnt) sts32(a_myword, (((uint32_t)WC_CAP - occ) << 12) | (((head + occ) & (uint32_t)(WC_CAP - 1)) << 18));
-    }
-  }
-  __syncthreads();
-  // ---- the rings' remainders leave as partial lines
-  if ((threadIdx.x & ~31u) < bv.n_buckets) {
-    const bool owner = threadIdx.x < bv.n_buckets;
-    const bool rest = owner && occ != 0;
-    const bool want_block = rest && (blk == 0xFFFFFFFFu || used == (uint32_t)WC_BLOCK);
-    const uint32_t fresh = warp_slots(want_block);
-    my_blocks += want_block ? 1u : 0u;
-    if (rest) flush_line(head, fresh, occ);
-    if (owner) { close_block(); my_blocks += s_direct[threadIdx.x]; }
-    if (my_blocks) atomicAdd(bv.n_lines + threadIdx.x, my_blocks);
-  }
-#ifdef GTB_WC_FRONT_ONLY
-  if (diverted == 0x7FFFFFF1u) atomicAdd(bv.diverted, 1ull);
-#else
-  if (diverted) atomicAdd(bv.diverted, (unsigned long long)diverted);
-#endif
-  __syncthreads();
-  if (threadIdx.x == 0) bv.cta_lines[blockIdx.x] = s_next_line;
-}
-
-// exclusive scan of the per-bucket line counts (one CTA) and reset of the scatter cursors
-__global__ void __launch_bounds__(1024) wc_line_offsets_kernel(BucketView bv) {
-  __shared__ uint32_t s_tot[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < bv.n_buckets; base += blockDim.x) {
-    const uint32_t b = base + threadIdx.x;
-    const uint32_t u = b < bv.n_buckets ? bv.n_lines[b] : 0;
-    uint32_t inc = u;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) s_tot[warp] = inc;
-    __syncthreads();
-    uint32_t pre = carry;
-    for (int w = 0; w < warp; w++) pre += s_tot[w];
-    if (b < bv.n_buckets) { bv.line_off[b] = pre + inc - u; bv.line_cursor[b] = 0; }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = pre + inc;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) bv.line_off[bv.n_buckets] = carry;
-}
-
-// groups the line slots by bucket: CTA c walks the slots CTA c of pass 1 filled (same grid)
-__global__ void __launch_bounds__(512) wc_line_scatter_kernel(BucketView bv) {
-  __shared__ uint32_t s_cnt[WC_MAX_BUCKETS], s_base[WC_MAX_BUCKETS];
-  for (uint32_t i = threadIdx.x; i < bv.n_buckets; i += blockDim.x) s_cnt[i] = 0;
-  __syncthreads();
-  const uint32_t n = bv.cta_lines[blockIdx.x];
-  const size_t first = (size_t)blockIdx.x * bv.lines_per_cta;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_cnt[bv.line_info[first + i] & 0xFFFFu], 1u);
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < bv.n_buckets; b += blockDim.x) {
-    const uint32_t c = s_cnt[b];
-    s_base[b] = bv.line_off[b] + (c ? atomicAdd(bv.line_cursor + b, c) : 0u);
-    s_cnt[b] = 0;
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint32_t info = bv.line_info[first + i];
-    const uint32_t b = info & 0xFFFFu;
-    const uint32_t pos = s_base[b] + atomicAdd(&s_cnt[b], 1u);
-    bv.sorted_lines[pos] = (uint32_t)(first + i) | ((info >> 16) << 25);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // between the passes: work units per bucket (exclusive scan of ceil(count / unit size))
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
@@ -684,7 +376,7 @@ __global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
 // ------------------------------------------------------------------------------------------------
 template <bool COVERAGE, bool LINES>
 __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketView bv, RankView rv) {
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(128) uint32_t smem[];
   const int cb = bv.ub - bv.k;
   const uint32_t n_dir = 1u << cb;
   uint16_t *s_dir = reinterpret_cast<uint16_t *>(smem);                       // [n_dir]
@@ -800,7 +492,6 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
         for (int i = 0; i < 4; i++) { us[i] = el[i] & ubmask; ue[i] = us[i] + (el[i] >> bv.ub); jS[i] = s_dir[us[i] >> kmaskless]; }
 #pragma unroll
         for (int i = 0; i < 4; i++) pS[i] = s_pts[jS[i]];
-#pragma unroll
         uint32_t jEv[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -827,7 +518,11 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
               if (jS[i] == jE) atomicAdd(&s_h32[jS[i]], 1u);
               else { atomicAdd(&s_h32[cap + jS[i]], 1u); atomicAdd(&s_h32[2 * cap + jE], 1u); }
             } else {
-              if (jS[i] == jE) atomicAdd(&s_h64[jS[i]], (ull)(ue[i] - us[i]) + 1ull);
+              if (jS[i] == jE) {                                          // 64-bit sum as a 32-bit atomic + a rare carry: far cheaper than atom.shared.add.u64
+                const uint32_t v = ue[i] - us[i] + 1u;
+                const uint32_t old = atomicAdd(&s_h32[2 * jS[i]], v);
+                if (old + v < old) atomicAdd(&s_h32[2 * jS[i] + 1], 1u);
+              }
               else {
                 atomicAdd(&s_h64[cap + jS[i]], 1ull); atomicAdd(&s_h64[2 * cap + jE], 1ull);
                 atomicAdd(&s_h64[3 * cap + jS[i]], (ull)us[i]); atomicAdd(&s_h64[4 * cap + jE], (ull)ue[i]);
@@ -870,8 +565,7 @@ struct gtb_bucket_state {
   bool wc_ok = false;                                   // the bucket count fits (one owner thread per bucket)
   bool wc_off = false;                                  // switched off after a batch with many diverted queries
   size_t wc_smem = 0;
-  dbuf<uint32_t> d_line_info, d_cta_lines, d_n_lines, d_line_off, d_line_cursor, d_sorted_lines;
-  dbuf<ull> d_diverted;
+  WcBuffers wc;
   ull diverted_seen = 0;
   int64_t wc_queries = 0;                               // queries sent through the write-combining form since the last check
 };
@@ -955,7 +649,7 @@ int gtb_bucket_prepare(gtb_index *ix) {
   bs->part_smem = (size_t)PART_TILE * 13 + (size_t)PART_TILE * 8 + 64 + (size_t)nb4 * 20 + (size_t)std::max(ix->n_chrom, 1) * 32;
   // with fewer than 256 buckets a 2 048-query round overfills the 32-element rings too often; GTB_BUCKET_WC=1 forces it (tests)
   bs->wc_ok = nb <= (uint32_t)WC_MAX_BUCKETS && (nb >= 256 || getenv("GTB_BUCKET_WC") != nullptr);
-  bs->wc_smem = (size_t)WC_STAGES * WC_TILE * 13 + (size_t)(nb + 1) * WC_STRIDE * 4 + (size_t)(nb4 + 4) * 8 + (size_t)std::max(ix->n_chrom, 1) * 32 + 32 + 64;
+  bs->wc_smem = wc_smem_bytes(nb, (size_t)2 * std::max(ix->n_chrom, 1) + 2);
   // directory and bucket-local slot coordinates
   const int cb = ub - k;
   std::vector<uint16_t> dir((size_t)nb << cb);
@@ -993,11 +687,6 @@ int gtb_bucket_prepare(gtb_index *ix) {
   GTB_TRY(bs->d_cursor.reserve(ctx, nb));
   GTB_TRY(bs->d_next_page.reserve(ctx, 1));
   GTB_TRY(bs->d_unit_off.reserve(ctx, (size_t)nb + 1));
-  GTB_TRY(bs->d_n_lines.reserve(ctx, (size_t)nb + 1));
-  GTB_TRY(bs->d_line_off.reserve(ctx, (size_t)nb + 1));
-  GTB_TRY(bs->d_line_cursor.reserve(ctx, (size_t)nb + 1));
-  GTB_TRY(bs->d_diverted.reserve(ctx, 1));
-  GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_diverted.p, 0, sizeof(ull), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   bs->ready = true; bs->failed = false;
   return GTB_OK;
@@ -1023,8 +712,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   bv.class_of = ix->d_class_of.p; bv.chrom_present = ix->d_present.p; bv.gtab = bs->d_gtab.p; bv.pm_tab = bs->d_pm.p;
   bv.n_buckets = nb; bv.pool = nullptr; bv.page_table = nullptr; bv.pt_stride = 0;
   bv.cursor = bs->d_cursor.p; bv.next_page = bs->d_next_page.p; bv.gen = 0;
-  bv.lines_per_cta = 0; bv.line_info = nullptr; bv.cta_lines = nullptr; bv.n_lines = nullptr; bv.line_off = nullptr;
-  bv.line_cursor = nullptr; bv.sorted_lines = nullptr; bv.diverted = bs->d_diverted.p;
+  bv.line_off = nullptr; bv.sorted_lines = nullptr;
   bv.j0 = bs->d_j0.p; bv.slot_lu = bs->d_slot_lu.p; bv.slot_u0 = bs->d_slot_u0.p; bv.dir = bs->d_dir.p;
   bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
   RankView rv;
@@ -1038,43 +726,29 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
 
   // ---- write-combining form of pass 1 (default)
   if (bs->wc_ok && !bs->wc_off && bs->wc_smem <= ctx->smem_optin && !getenv("GTB_BUCKET_PAGED")) {
-    // skew watchdog: many queries diverted to the general path => go back to the paged form from now on.  Checked at the
-    // first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
-    if (bs->wc_queries > 0 && (q.index_base == 0 || bs->wc_queries >= ((int64_t)64 << 20))) {
-      ull host_div = 0;
-      GTB_CUDA_OK(ctx, cudaMemcpyAsync(&host_div, bs->d_diverted.p, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
-      GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-      if ((int64_t)(host_div - bs->diverted_seen) > bs->wc_queries / 16) bs->wc_off = true;
-      bs->diverted_seen = host_div; bs->wc_queries = 0;
-    }
-    const int64_t wc_tiles = (q.n_regions + WC_TILE - 1) / WC_TILE;
-    const unsigned gridw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, wc_tiles));
-    const uint64_t tiles_cta = ((uint64_t)wc_tiles + gridw - 1) / gridw;
-    const uint64_t lines_per_cta = tiles_cta * (WC_TILE / WC_BLOCK_ELEMS) + nb + 1;          // block slots: full blocks + one open block per bucket
-    const uint64_t total_slots = lines_per_cta * gridw;
-    if (!bs->wc_off && total_slots < ((uint64_t)1 << 25)) {
-      GTB_TRY(bs->d_pool.reserve(ctx, (size_t)total_slots * WC_BLOCK_ELEMS));
-      GTB_TRY(bs->d_line_info.reserve(ctx, (size_t)total_slots));
-      GTB_TRY(bs->d_sorted_lines.reserve(ctx, (size_t)total_slots));
-      GTB_TRY(bs->d_cta_lines.reserve(ctx, (size_t)gridw));
-      GTB_CUDA_OK(ctx, cudaMemsetAsync(bs->d_n_lines.p, 0, (size_t)nb * 4, ctx->stream));
-      bv.lines_per_cta = (uint32_t)lines_per_cta; bv.line_info = bs->d_line_info.p; bv.cta_lines = bs->d_cta_lines.p;
-      bv.n_lines = bs->d_n_lines.p; bv.line_off = bs->d_line_off.p; bv.line_cursor = bs->d_line_cursor.p;
-      bv.sorted_lines = bs->d_sorted_lines.p; bv.diverted = bs->d_diverted.p; bv.pool = bs->d_pool.p;
-      if (cov) {
-        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(wc_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->wc_smem));
-        GTB_LAUNCH(ctx, "bucket_partition", wc_partition_kernel<true>, gridw, WC_THREADS, bs->wc_smem, q, rv, bv);
-      } else {
-        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(wc_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->wc_smem));
-        GTB_LAUNCH(ctx, "bucket_partition", wc_partition_kernel<false>, gridw, WC_THREADS, bs->wc_smem, q, rv, bv);
+    WcView wv;
+    unsigned gridw = 0;
+    const bool planned = bs->wc.plan(ctx, q.n_regions, nb, &wv, &gridw) == GTB_OK;   // not OK: more block slots than their ids can name
+    if (planned) {
+      // skew watchdog: many queries diverted to the general path => go back to the paged form from now on.  Checked at the
+      // first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
+      if (bs->wc_queries > 0 && (q.index_base == 0 || bs->wc_queries >= ((int64_t)64 << 20))) {
+        ull host_div = 0;
+        GTB_CUDA_OK(ctx, cudaMemcpyAsync(&host_div, wv.diverted, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+        GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((int64_t)(host_div - bs->diverted_seen) > bs->wc_queries / 16) bs->wc_off = true;
+        bs->diverted_seen = host_div; bs->wc_queries = 0;
       }
-      GTB_TRY(gtb_check_launch(ctx));
-      GTB_LAUNCH(ctx, "bucket_line_offsets", wc_line_offsets_kernel, 1, 1024, 0, bv);
-      GTB_LAUNCH(ctx, "bucket_line_scatter", wc_line_scatter_kernel, gridw, 512, 0, bv);
+    }
+    if (planned && !bs->wc_off) {
+      bv.pool = wv.pool; bv.line_off = wv.line_off; bv.sorted_lines = wv.sorted_lines;
+      const WcQueries wq{q.n_regions, q.chrom, q.start, q.stop, q.strand, q.index_base};
       if (cov) {
+        GTB_TRY(wc_partition_launch(ctx, "bucket_partition", wq, OverlapFront<true>{rv, bv}, wv, gridw, bs->wc_smem));
         GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
         GTB_LAUNCH(ctx, "bucket_coverage", (bucket_count_kernel<true, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
       } else {
+        GTB_TRY(wc_partition_launch(ctx, "bucket_partition", wq, OverlapFront<false>{rv, bv}, wv, gridw, bs->wc_smem));
         GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
         GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
       }
@@ -1082,8 +756,8 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
       if (getenv("GTB_DEBUG_WC")) {                                      // diagnostics: how the batch travelled
         ull host_div = 0; uint32_t blocks = 0;
         cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(&host_div, bs->d_diverted.p, sizeof(ull), cudaMemcpyDeviceToHost);
-        cudaMemcpy(&blocks, bs->d_line_off.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&host_div, wv.diverted, sizeof(ull), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&blocks, wv.line_off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[gtb wc] queries %lld buckets %u blocks %u (%.1f elements/block) diverted so far %llu\n", (long long)q.n_regions, nb, blocks,
                 blocks ? (double)q.n_regions / blocks : 0.0, host_div);
       }
@@ -1136,8 +810,7 @@ void gtb_bucket_destroy(gtb_index *ix) {
   if (!bs) return;
   bs->d_gtab.release(); bs->d_pm.release(); bs->d_j0.release(); bs->d_slot_lu.release(); bs->d_slot_u0.release(); bs->d_dir.release();
   bs->d_pool.release(); bs->d_page_table.release(); bs->d_cursor.release(); bs->d_next_page.release(); bs->d_unit_off.release();
-  bs->d_line_info.release(); bs->d_cta_lines.release(); bs->d_n_lines.release(); bs->d_line_off.release(); bs->d_line_cursor.release();
-  bs->d_sorted_lines.release(); bs->d_diverted.release();
+  bs->wc.release();
   delete bs;
   ix->bucket = nullptr;
 }

@@ -5,7 +5,18 @@
 // the `v >= MIN_READS` filter of RunCounts (genomic_scans.cpp:421-428) as a device stream
 // compaction that preserves the reference's output order (chromosome id ascending, '+' then '-',
 // window ascending).
+//
+// Two ways to build the histogram:
+//   * scan_histogram_kernel: one global reduction per read.  The table of a genome (hg19, step 50: 1 GB) is far larger than
+//     L2, so every reduction is a 32-byte read-modify-write in HBM: ~21 G reads/s measured on B200.  Kept for small batches,
+//     weighted reads and tiny genomes.
+//   * bucketed (default for large unweighted batches): the write-combining partition of gtb_wc_partition.cuh sorts the reads'
+//     micro-window numbers into <= 512 genome buckets (13 B in, 4 B out per read); scan_bucket_hist_kernel then counts each
+//     bucket in shared memory -- 65 536 16-bit counters per CTA, a bucket wider than that is walked by several CTAs, each
+//     keeping its own sub-range (the bucket's elements come from L2 after the first of them) -- and adds the non-zero
+//     counters to the table with plain coalesced read-modify-writes: a bucket range belongs to exactly one CTA.
 #include "gtb_internal.cuh"
+#include "gtb_wc_partition.cuh"
 #include <algorithm>
 
 typedef unsigned long long ull;
@@ -22,7 +33,7 @@ struct SlotTable {                 // device pointers, one entry per slot (+1 fo
 };
 
 struct ReadView {
-  int64_t n_regions;
+  int64_t n_regions, n_intervals;
   const int32_t *chrom, *start, *stop;
   const int8_t *strand;
   const int32_t *weight;
@@ -57,9 +68,109 @@ __global__ void __launch_bounds__(256) scan_histogram_kernel(ReadView q, int32_t
   }
 }
 
+// ---- bucketed histogram ----------------------------------------------------------------------------------------------------
+// Front of the write-combining partition for reads.  Table: one 16-byte entry per (chromosome, strand selector):
+//   x = last position that counts (n_micro * win_step; 0: chromosome not in the genome file), y = first micro-window of the slot.
+// Element = micro-window number inside the bucket; bucket = global micro-window number >> mb.
+struct ScanFront {
+  static constexpr bool FAIL_IS_SLOW = false;         // a read that counts nowhere is simply dropped (:5040-5049)
+  const uint4 *tab;                                   // [2 * n_chrom + 2], the last two entries are empty
+  uint32_t n_chrom;
+  uint32_t magic; int shift;                          // (pos - 1) / win_step == ((pos - 1) * magic) >> shift for pos - 1 < 2^31
+  uint32_t mb;
+  int centre, ignore_strand;
+  ull *hist;
+  __device__ __forceinline__ uint32_t table_size() const { return 2u * n_chrom + 2u; }
+  __device__ __forceinline__ uint4 table_entry(uint32_t i) const { return tab[i]; }
+  __device__ __forceinline__ uint32_t table_index(int32_t c, uint32_t xw, int i) const {
+    const uint32_t sel = ignore_strand ? 0u : (((xw >> (8 * i)) & 0xFFu) != 0u ? 1u : 0u);       // '+' -> forward, anything else -> reverse (:5048)
+    return 2u * min((uint32_t)c, n_chrom) + sel;
+  }
+  __device__ __forceinline__ uint32_t slow_mask(uint32_t) const { return 0u; }
+  __device__ __forceinline__ bool micro(uint4 g, int32_t s, int32_t e, uint32_t &m) const {
+    const uint32_t d = (uint32_t)e - (uint32_t)s;                                                // exact when s <= e
+    const int32_t pos = centre ? s + (int32_t)(d >> 1) : s;                                      // :5044-5045
+    m = g.y + (uint32_t)(((uint64_t)(uint32_t)(pos - 1) * magic) >> shift);
+    return s <= e && (uint32_t)(pos - 1) < g.x;                                                  // pos >= 1 (hence stop > 0) and inside the micro-windows
+  }
+  __device__ __forceinline__ uint32_t classify(uint4 g, int32_t s, int32_t e, uint32_t &elem) const {
+    uint32_t m;
+    const bool ok = micro(g, s, e, m);
+    elem = m & ((1u << mb) - 1u);
+    return ok ? m >> mb : WC_NONE;
+  }
+  __device__ __forceinline__ uint32_t resolve(uint32_t bucket, int32_t, int32_t, int32_t, uint32_t, int64_t) const { return bucket; }
+  __device__ __forceinline__ void divert(int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t) const {
+    const uint32_t sel = ignore_strand ? 0u : (sbyte != (uint32_t)'+' ? 1u : 0u);
+    uint32_t m;
+    if (micro(tab[2u * min((uint32_t)c, n_chrom) + sel], s, e, m)) atomicAdd(hist + m, 1ull);
+  }
+};
+
+constexpr int SB_THREADS = 1024;
+constexpr int SB_SUB_BITS = 16;                        // micro-windows per CTA: 65 536 16-bit counters = 128 KB of shared memory
+
+// CTA (bucket b, sub-range z): counts the elements of b that fall into [z << 16, (z + 1) << 16) and adds them to the table.
+// Counters are 16 bits, two to a word.  The thread whose add takes a counter from below 2^15 to 2^15 or more moves 2^15 to the
+// table; a thread that finds a counter at 3 * 2^14 or more (that correction still pending) takes its own add back and sends it to
+// the table instead.  Every thread has at most one add of <= 4 in flight, so a counter stays below 3 * 2^14 + 4 096 < 2^16.
+__global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView wv, uint32_t mb, uint32_t n_sub, uint32_t words, ull *__restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t s_cnt[];   // [words]
+  const uint32_t b = blockIdx.x / n_sub, z = blockIdx.x % n_sub;
+  const uint32_t first = wv.line_off[b], last = wv.line_off[b + 1];
+  if (first == last) return;
+  for (uint32_t i = threadIdx.x; i < words; i += SB_THREADS) s_cnt[i] = 0;
+  __syncthreads();
+  const uint32_t lo = z << SB_SUB_BITS, span = 2u * words;
+  const ull m0 = ((ull)b << mb) + lo;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto add = [&](uint32_t loc, uint32_t v) {
+    const uint32_t sh = (loc & 1u) * 16u;
+    const uint32_t old = (atomicAdd(&s_cnt[loc >> 1], v << sh) >> sh) & 0xFFFFu;
+    if (old + v >= 0x8000u) {                          // rare
+      if (old < 0x8000u) {                             // this add crossed 2^15: move 2^15 to the table
+        atomicSub(&s_cnt[loc >> 1], 0x8000u << sh);
+        atomicAdd(hist + m0 + loc, 0x8000ull);
+      } else if (old + v >= 0xC000u) {                 // the correction above is still pending and the counter keeps climbing: count elsewhere
+        atomicSub(&s_cnt[loc >> 1], v << sh);
+        atomicAdd(hist + m0 + loc, (ull)v);
+      }
+      __threadfence();                                 // ordered before this CTA's plain read-modify-write of the same entry below
+    }
+  };
+  for (uint32_t blk = first + warp; blk < last; blk += SB_THREADS / 32) {
+    const uint32_t entry = __ldg(wv.sorted_lines + blk);
+    const uint32_t fill = (entry >> 25) + 1u, q4 = lane * 4u;
+    if (fill <= q4) continue;
+    const uint4 d = ldg_stream128(reinterpret_cast<const uint4 *>(wv.pool + (size_t)(entry & 0x01FFFFFFu) * WC_BLOCK_ELEMS) + lane);
+    const uint32_t el[4] = {d.x, d.y, d.z, d.w};
+    const uint32_t nv = min(fill - q4, 4u);
+    // runs of equal elements (position-sorted reads) leave as one add
+    uint32_t run = 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if ((uint32_t)i >= nv) break;
+      const bool more = (uint32_t)(i + 1) < nv && el[i + 1 < 4 ? i + 1 : 3] == el[i];
+      if (more) { run++; continue; }
+      const uint32_t loc = el[i] - lo;
+      if (loc < span) add(loc, run);
+      run = 1;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < words; i += SB_THREADS) {
+    const uint32_t w = s_cnt[i];
+    if (w) {
+      if (w & 0xFFFFu) hist[m0 + 2 * i] += (ull)(w & 0xFFFFu);
+      if (w >> 16) hist[m0 + 2 * i + 1] += (ull)(w >> 16);
+    }
+  }
+}
+
 constexpr int WIN_THREADS = 256;
 constexpr int WIN_ITEMS = 8;
 constexpr int WIN_TILE = WIN_THREADS * WIN_ITEMS;
+constexpr int WIN_MAX_COMBINE = 64;                    // micro-windows per window the staged form handles
 
 __device__ __forceinline__ int find_slot(const int64_t *__restrict__ win_off, int n_slots, int64_t g) {
   int lo = 0, hi = n_slots;            // last slot with win_off[slot] <= g
@@ -87,20 +198,47 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
                                                                     int64_t *__restrict__ o_win, int64_t *__restrict__ o_value) {
   __shared__ int warp_counts[WIN_THREADS / 32];
   __shared__ ull tile_base;
-  const int64_t first = (int64_t)blockIdx.x * WIN_TILE + (int64_t)threadIdx.x * WIN_ITEMS;
+  // the tile's micro-windows, staged with one pad entry per 8 so that thread t's run (8 t ...) starts in its own bank pair
+  __shared__ ull s_h[(WIN_TILE + WIN_MAX_COMBINE) + (WIN_TILE + WIN_MAX_COMBINE) / 8 + 1];
+  const int64_t tile_first = (int64_t)blockIdx.x * WIN_TILE;
+  const int64_t tile_last = min(total_windows, tile_first + WIN_TILE) - 1;
+  const int64_t first = tile_first + (int64_t)threadIdx.x * WIN_ITEMS;
   long long val[WIN_ITEMS];
   int slot_of[WIN_ITEMS];
   unsigned keep = 0;
-  int slot = first < total_windows ? find_slot(t.win_off, t.n_slots, first) : 0;
+  const int slot_a = find_slot(t.win_off, t.n_slots, tile_first);
+  if (tile_last < t.win_off[slot_a + 1] && !t.spurious[slot_a] && combine <= WIN_MAX_COMBINE) {
+    // the whole tile lies in one (chromosome, strand) slot -- all but a few dozen tiles: coalesced load, sliding sums from shared memory
+    const int n_w = (int)(tile_last - tile_first + 1), n_h = n_w + combine - 1;
+    const ull *src = hist + t.hist_off[slot_a] + (tile_first - t.win_off[slot_a]);
+    for (int i = threadIdx.x; i < n_h; i += WIN_THREADS) s_h[i + (i >> 3)] = src[i];
+    __syncthreads();
+    const int w0 = threadIdx.x * WIN_ITEMS;
+    auto at = [&](int i) { return s_h[i + (i >> 3)]; };
+    ull sum = 0;
+    if (w0 < n_w)
+      for (int j = 0; j < combine; j++) sum += at(w0 + j);                   // :5066-5073
 #pragma unroll
-  for (int i = 0; i < WIN_ITEMS; i++) {
-    const int64_t g = first + i;
-    val[i] = 0; slot_of[i] = slot;
-    if (g < total_windows) {
-      while (g >= t.win_off[slot + 1]) slot++;
-      slot_of[i] = slot;
-      val[i] = window_value(t, hist, slot, g - t.win_off[slot], combine);
-      if (val[i] >= min_reads) keep |= 1u << i;
+    for (int i = 0; i < WIN_ITEMS; i++) {
+      val[i] = 0; slot_of[i] = slot_a;
+      if (w0 + i < n_w) {
+        val[i] = (long long)sum;
+        if (val[i] >= min_reads) keep |= 1u << i;
+        if (w0 + i + 1 < n_w) sum += at(w0 + i + combine) - at(w0 + i);
+      }
+    }
+  } else {
+    int slot = first < total_windows ? find_slot(t.win_off, t.n_slots, first) : 0;
+#pragma unroll
+    for (int i = 0; i < WIN_ITEMS; i++) {
+      const int64_t g = first + i;
+      val[i] = 0; slot_of[i] = slot;
+      if (g < total_windows) {
+        while (g >= t.win_off[slot + 1]) slot++;
+        slot_of[i] = slot;
+        val[i] = window_value(t, hist, slot, g - t.win_off[slot], combine);
+        if (val[i] >= min_reads) keep |= 1u << i;
+      }
     }
   }
   const int mine = __popc(keep);
@@ -151,6 +289,13 @@ struct gtb_scan {
   dbuf<int64_t> d_hist_off, d_win_off;
   dbuf<ull> d_hist, d_tile_counts, d_scan_scratch;
   dbuf<int32_t> o_chrom; dbuf<int8_t> o_strand; dbuf<int64_t> o_win, o_value;
+  // bucketed histogram (unweighted batches of at least bucket_min intervals)
+  bool bucket_ok = false;
+  int64_t bucket_min = (int64_t)2 << 20;
+  uint32_t mb = 0, n_buckets = 0, n_sub = 1, sb_words = 0;
+  uint32_t magic = 0; int shift = 0;
+  dbuf<uint4> d_front_tab;
+  WcBuffers wc;
   struct stage {
     dbuf<int32_t> chrom, start, stop, weight; dbuf<int8_t> strand; dbuf<int64_t> off;
     cudaEvent_t copied = nullptr, consumed = nullptr; bool in_flight = false;
@@ -206,6 +351,37 @@ extern "C" int gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bou
   sc->n_slots = (int32_t)slot_chrom.size();
   sc->total_micro = hist_off.back(); sc->total_windows = win_off.back();
   int rc = upload_vec(ctx, sc->d_slot_of_chrom, slot_of_chrom);
+  // bucketed histogram: <= 512 buckets of 2^mb micro-windows, at least 256 of them (fewer overfill the partition's rings);
+  // a bucket wider than one CTA's 65 536 counters is walked by 2^(mb - 16) CTAs, at most 16
+  {
+    uint32_t mb = 10;
+    while (mb < 24 && ((sc->total_micro + (((int64_t)1 << mb) - 1)) >> mb) > WC_MAX_BUCKETS) mb++;
+    const int64_t nb = (sc->total_micro + (((int64_t)1 << mb) - 1)) >> mb;
+    const size_t smem = wc_smem_bytes((uint32_t)std::max<int64_t>(nb, 1), (size_t)2 * std::max(n_chrom, 1) + 2);
+    if (mb <= SB_SUB_BITS + 4 && nb >= 256 && params->win_step < ((int64_t)1 << 31) && smem <= ctx->smem_optin && !getenv("GTB_SCAN_DIRECT")) {
+      sc->bucket_ok = true; sc->mb = mb; sc->n_buckets = (uint32_t)nb;
+      sc->n_sub = mb > SB_SUB_BITS ? 1u << (mb - SB_SUB_BITS) : 1u;
+      sc->sb_words = (mb > SB_SUB_BITS ? 1u << SB_SUB_BITS : 1u << mb) / 2;
+      const uint64_t d = (uint64_t)params->win_step;
+      int l = 0;
+      while (((uint64_t)1 << l) < d) l++;
+      sc->shift = 31 + l;
+      sc->magic = (uint32_t)((((uint64_t)1 << sc->shift) + d - 1) / d);      // ceil(2^(31 + l) / d): exact quotients for dividends < 2^31
+      std::vector<uint4> tab((size_t)2 * std::max(n_chrom, 1) + 2, make_uint4(0, 0, 0, 0));
+      for (int32_t c = 0; c < n_chrom; c++) {
+        const int32_t s0 = slot_of_chrom[c];
+        if (s0 < 0) continue;
+        for (int z = 0; z < 2; z++) {
+          const int32_t slot = s0 + (z && n_strands == 2 ? 1 : 0);
+          const int64_t n_micro = hist_off[slot + 1] - hist_off[slot];
+          const int64_t last_pos = std::min<int64_t>(n_micro * params->win_step, 0x7FFFFFFF);
+          tab[2 * c + z] = make_uint4((uint32_t)last_pos, (uint32_t)hist_off[slot], 0, 0);
+        }
+      }
+      if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_front_tab, tab);
+      if (const char *env = getenv("GTB_SCAN_BUCKET_MIN")) sc->bucket_min = std::max<long long>(1, atoll(env));
+    }
+  }
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_spurious, spurious);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_slot_chrom, slot_chrom);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_slot_strand, slot_strand);
@@ -230,6 +406,7 @@ extern "C" void gtb_scan_destroy(gtb_scan *sc) {
   sc->d_slot_of_chrom.release(); sc->d_spurious.release(); sc->d_slot_chrom.release(); sc->d_slot_strand.release();
   sc->d_hist_off.release(); sc->d_win_off.release(); sc->d_hist.release(); sc->d_tile_counts.release(); sc->d_scan_scratch.release();
   sc->o_chrom.release(); sc->o_strand.release(); sc->o_win.release(); sc->o_value.release();
+  sc->d_front_tab.release(); sc->wc.release();
   for (auto &st : sc->stages) {
     st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release();
     if (st.copied) cudaEventDestroy(st.copied);
@@ -241,6 +418,22 @@ extern "C" void gtb_scan_destroy(gtb_scan *sc) {
 static int scan_accumulate_device(gtb_scan *sc, const ReadView &q) {
   gtb_ctx *ctx = sc->ctx;
   if (q.n_regions <= 0 || sc->n_slots == 0) return GTB_OK;
+  if (sc->bucket_ok && !q.weight && q.n_intervals >= sc->bucket_min && q.n_intervals < ((int64_t)1 << 31)) {
+    // every interval of every region counts once (:5039): without weights the region structure does not matter
+    WcView wv;
+    unsigned gridw = 0;
+    if (sc->wc.plan(ctx, q.n_intervals, sc->n_buckets, &wv, &gridw) == GTB_OK) {
+      const ScanFront front{sc->d_front_tab.p, (uint32_t)sc->n_chrom, sc->magic, sc->shift, sc->mb, sc->prm.op == 'c' ? 1 : 0,
+                            sc->prm.ignore_strand ? 1 : 0, sc->d_hist.p};
+      const WcQueries wq{q.n_intervals, q.chrom, q.start, q.stop, q.strand, 0};
+      GTB_TRY(wc_partition_launch(ctx, "scan_partition", wq, front, wv, gridw, wc_smem_bytes(sc->n_buckets, (size_t)2 * std::max(sc->n_chrom, 1) + 2)));
+      const size_t smem = (size_t)sc->sb_words * 4;
+      GTB_CUDA_OK(ctx, cudaFuncSetAttribute(scan_bucket_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GTB_LAUNCH(ctx, "scan_bucket_hist", scan_bucket_hist_kernel, sc->n_buckets * sc->n_sub, SB_THREADS, smem, wv, sc->mb, sc->n_sub, sc->sb_words,
+                 sc->d_hist.p);
+      return gtb_check_launch(ctx);
+    }
+  }
   const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 8);
   GTB_LAUNCH(ctx, "scan_histogram", scan_histogram_kernel, grid, 256, 0, q, sc->n_chrom, sc->d_slot_of_chrom.p, sc->d_hist_off.p,
              (long long)sc->prm.win_step, (int)sc->prm.op, (int)sc->prm.ignore_strand, sc->d_hist.p);
@@ -258,7 +451,7 @@ extern "C" int gtb_scan_add_reads(gtb_scan *sc, const gtb_set *reads, unsigned m
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   const bool multi = reads->region_offset != nullptr && reads->n_intervals != reads->n_regions;
   if (mem & GTB_MEM_DEVICE) {
-    ReadView q{reads->n_regions, reads->chrom, reads->start, reads->stop, reads->strand, reads->weight,
+    ReadView q{reads->n_regions, reads->n_intervals, reads->chrom, reads->start, reads->stop, reads->strand, reads->weight,
                multi ? reads->region_offset : nullptr, 0};
     return scan_accumulate_device(sc, q);
   }
@@ -286,7 +479,7 @@ extern "C" int gtb_scan_add_reads(gtb_scan *sc, const gtb_set *reads, unsigned m
     }
     GTB_CUDA_OK(ctx, cudaEventRecord(st.copied, cs));
     GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied, 0));
-    ReadView q{(int64_t)nr, st.chrom.p, st.start.p, st.stop.p, st.strand.p, reads->weight ? st.weight.p : nullptr,
+    ReadView q{(int64_t)nr, (int64_t)ni, st.chrom.p, st.start.p, st.stop.p, st.strand.p, reads->weight ? st.weight.p : nullptr,
                multi ? st.off.p : nullptr, i0};
     GTB_TRY(scan_accumulate_device(sc, q));
     GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));

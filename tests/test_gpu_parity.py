@@ -209,7 +209,18 @@ def test_sorted_and_clustered_input(gtb, ctx, oracle):
                 ix.close()
 
 
-def test_scan_hg19_vs_oracle(gtb, ctx, oracle):
+@pytest.fixture(params=("bucketed", "direct"))
+def scan_form(request, monkeypatch):
+    """Both ways of building the micro-window histogram: the write-combining partition + shared-memory counters (forced for
+    batches of any size), and one global reduction per read."""
+    if request.param == "bucketed":
+        monkeypatch.setenv("GTB_SCAN_BUCKET_MIN", "1")
+    else:
+        monkeypatch.setenv("GTB_SCAN_DIRECT", "1")
+    return request.param
+
+
+def test_scan_hg19_vs_oracle(gtb, ctx, oracle, scan_form):
     reads = support.synth_reads(1_000_000, seed=4)
     bound = support.HG19_LENS.copy()
     bound[5] = -1                                    # one chromosome missing from the genome file
@@ -223,6 +234,71 @@ def test_scan_hg19_vs_oracle(gtb, ctx, oracle):
         for k in want:
             assert np.array_equal(got[k], want[k]), (w, d, op, k)
         sc.close()
+
+
+def _scan_check(gtb, ctx, oracle, reads, bound, d, w, op, ign, mn, batches=1, offsets=None, weight=None, device=False):
+    import torch
+    n, want = oracle.scan_counts(reads, bound, d, w, op, ign, mn, weight=weight, offsets=offsets)
+    sc = gtb.Scan(ctx, bound, d, w, op, ign, mn)
+    for rep in range(2):                              # the second round checks reset + accumulation into a used table
+        if rep:
+            sc.reset()
+        if device:
+            dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in reads.items()}
+            sc.add_device(dev)
+        elif batches == 1:
+            sc.add_host(reads, weight=weight, offsets=offsets)
+        else:
+            total = len(reads["chrom"])
+            step = (total + batches - 1) // batches
+            for lo in range(0, total, step):
+                sc.add_host({k: v[lo:lo + step] for k, v in reads.items()})
+        assert sc.finish() == n, (d, w, op, ign, mn, rep)
+        got = sc.fetch(0, n)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (d, w, op, ign, mn, k, rep)
+    sc.close()
+
+
+def test_scan_bucketed_forms(gtb, ctx, oracle, scan_form):
+    """The bucketed histogram on everything that bends it: buckets walked by 1, 4 and 8 CTAs, position-sorted reads (whole
+    warps in one bucket, runs of equal elements), reads piled onto one micro-window (16-bit counters spill many times, rings
+    overflow), reads that count nowhere, odd strand bytes, negative starts with the centre operator, device-resident input."""
+    n = 1_200_000
+    reads = support.synth_reads(n, seed=41)
+    bound = support.HG19_LENS.copy()
+    bound[3] = -1
+    # sprinkle reads the scanner must ignore, and strands other than '+'/'-'
+    rng = np.random.default_rng(7)
+    bad = rng.choice(n, 5_000, replace=False)
+    reads["stop"][bad[:1000]] = reads["start"][bad[:1000]] - 1            # start > stop
+    reads["start"][bad[1000:2000]] = -40; reads["stop"][bad[1000:2000]] = -3   # stop <= 0
+    reads["chrom"][bad[2000:3000]] = 99                                   # unknown chromosome
+    reads["start"][bad[3000:4000]] = -20; reads["stop"][bad[3000:4000]] = 60   # start < 1: counts only under -op c
+    reads["strand"][bad[4000:5000]] = ord(".")
+    for (w, d, op, ign, mn) in ((200, 50, "1", False, 1), (100, 25, "c", False, 2), (400, 200, "1", True, 1), (5000, 1000, "c", False, 3)):
+        _scan_check(gtb, ctx, oracle, reads, bound, d, w, op, ign, mn, batches=3)
+    order = np.lexsort((reads["start"], reads["strand"], reads["chrom"]))
+    srt = {k: np.ascontiguousarray(v[order]) for k, v in reads.items()}
+    _scan_check(gtb, ctx, oracle, srt, bound, 50, 200, "1", False, 2, device=True)
+    piled = {k: v.copy() for k, v in support.synth_reads(n, seed=42).items()}
+    piled["chrom"][:] = 7
+    piled["start"] = (piled["start"] % 180 + 5_000_000).astype(np.int32)   # four micro-windows of 50 bp
+    piled["stop"] = (piled["start"] + 49).astype(np.int32)
+    _scan_check(gtb, ctx, oracle, piled, bound, 50, 200, "1", False, 10)
+    psrt = {k: np.ascontiguousarray(v[np.argsort(piled["start"], kind="stable")]) for k, v in piled.items()}
+    _scan_check(gtb, ctx, oracle, psrt, bound, 50, 200, "1", True, 10, device=True)
+
+
+def test_scan_multi_interval_and_weights(gtb, ctx, oracle, scan_form):
+    """Multi-interval reads count once per block (bucketed when unweighted); weighted reads take the direct form."""
+    n = 300_000
+    reads = support.synth_reads(n, seed=43)
+    bound = support.HG19_LENS.copy()
+    offsets = np.arange(0, n + 1, 3, dtype=np.int64)                      # regions of three blocks
+    _scan_check(gtb, ctx, oracle, reads, bound, 50, 200, "1", False, 2, offsets=offsets)
+    weight = (np.arange(len(offsets) - 1) % 5).astype(np.int32)
+    _scan_check(gtb, ctx, oracle, reads, bound, 50, 200, "1", False, 2, offsets=offsets, weight=weight)
 
 
 @pytest.mark.parametrize("shards", [2, 4])
