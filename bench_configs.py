@@ -21,7 +21,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=100_000_000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--only", default="", help="comma-separated subset of: count, coverage, sorted, scan")
     args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+
+    def wanted(tag):
+        return not only or tag in only
     import torch
     import gtb200
     import support
@@ -65,6 +70,8 @@ def main():
     out = torch.zeros(60_000, dtype=torch.int64, device="cuda")
     for name, op, flags in (("count (configs[1])", gtb200.OP_COUNT, 0), ("count -i", gtb200.OP_COUNT, gtb200.IGNORE_STRAND),
                             ("coverage (configs[3], single-interval variant)", gtb200.OP_COVERAGE, 0)):
+        if not wanted("coverage" if op == gtb200.OP_COVERAGE else "count"):
+            continue
         ix = gtb200.Index(ctx, regions, op, flags)
 
         def step(ix=ix):
@@ -74,35 +81,37 @@ def main():
         timed(name, step, 13 * n + 21 * 60_000)
         ix.close()
 
-    # sorted input (what -S promises): same reads ordered by (chromosome, strand, start)
-    key = (dev["chrom"].long() << 33) | ((dev["strand"] == ord("-")).long() << 32) | dev["start"].long()
-    order = torch.argsort(key)
-    del key
-    sdev = {k: v[order].contiguous() for k, v in dev.items()}
-    del order
-    sset, keep2 = gtb200.device_set(sdev)
-    ix = gtb200.Index(ctx, regions, gtb200.OP_COUNT, 0)
+    if wanted("sorted"):
+        # sorted input (what -S promises): same reads ordered by (chromosome, strand, start)
+        key = (dev["chrom"].long() << 33) | ((dev["strand"] == ord("-")).long() << 32) | dev["start"].long()
+        order = torch.argsort(key)
+        del key
+        sdev = {k: v[order].contiguous() for k, v in dev.items()}
+        del order
+        sset, keep2 = gtb200.device_set(sdev)
+        ix = gtb200.Index(ctx, regions, gtb200.OP_COUNT, 0)
 
-    def step_sorted():
-        ix.reset()
-        ix.add_set(sset, gtb200.MEM_DEVICE)
-        ix.finish_ptr(out.data_ptr(), gtb200.MEM_DEVICE)
-    timed("count, reads sorted by chromosome/strand/start", step_sorted, 13 * n + 21 * 60_000)
-    ix.close()
-    del sdev, sset
+        def step_sorted():
+            ix.reset()
+            ix.add_set(sset, gtb200.MEM_DEVICE)
+            ix.finish_ptr(out.data_ptr(), gtb200.MEM_DEVICE)
+        timed("count, reads sorted by chromosome/strand/start", step_sorted, 13 * n + 21 * 60_000)
+        ix.close()
+        del sdev, sset
 
-    # scans: 200-bp windows, step 50, -min 10, strand-aware
-    sc = gtb200.Scan(ctx, support.HG19_LENS, 50, 200, "1", False, 10)
-    res = {}
+    if wanted("scan"):
+        # scans: 200-bp windows, step 50, -min 10, strand-aware
+        sc = gtb200.Scan(ctx, support.HG19_LENS, 50, 200, "1", False, 10)
+        res = {}
 
-    def step_scan():
-        sc.reset()
-        sc.add_set(dset, gtb200.MEM_DEVICE)
-        res["n"] = sc.finish()
-    windows = int(sum(max(int(L) // 50 - 3, 0) for L in support.HG19_LENS) * 2)
-    timed("genomic_scans counts -w 200 -d 50 -min 10 (configs[2])", step_scan, 9 * n + 8 * windows, {"windows": windows})
-    print(json.dumps({"qualifying_windows": res.get("n")}))
-    sc.close()
+        def step_scan():
+            sc.reset()
+            sc.add_set(dset, gtb200.MEM_DEVICE)
+            res["n"] = sc.finish()
+        windows = int(sum(max(int(L) // 50 - 3, 0) for L in support.HG19_LENS) * 2)
+        timed("genomic_scans counts -w 200 -d 50 -min 10 (configs[2])", step_scan, 9 * n + 8 * windows, {"windows": windows})
+        print(json.dumps({"qualifying_windows": res.get("n")}))
+        sc.close()
     ctx.close()
 
 

@@ -462,6 +462,16 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
       n_v4 = (n_el + 3) >> 2;
     }
     constexpr int UNROLL = 4;
+    // block ids of a trip (LINES): fetched one trip ahead, so that a trip waits for one memory latency, not two dependent ones
+    uint32_t ent[UNROLL];
+    auto fetch_entries = [&](uint32_t base) {
+#pragma unroll
+      for (int r = 0; r < UNROLL; r++) {
+        const uint32_t v4 = base + r * COUNT_THREADS + threadIdx.x;
+        ent[r] = v4 < n_v4 ? __ldg(bv.sorted_lines + u + (v4 >> 5)) : 0u;                        // 32 loads of 128 bits per block
+      }
+    };
+    if (LINES) fetch_entries(0);
     for (uint32_t base = 0; base < n_v4; base += COUNT_THREADS * UNROLL) {
       uint4 d[UNROLL];
       uint32_t nv[UNROLL];                                                // valid elements of each 128-bit load
@@ -472,7 +482,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
         nv[r] = 0;
         if (v4 < n_v4) {
           if (LINES) {
-            const uint32_t entry = __ldg(bv.sorted_lines + u + (v4 >> 5));                       // 32 loads of 128 bits per block
+            const uint32_t entry = ent[r];
             const uint32_t fill = (entry >> 25) + 1u, q4 = (v4 & 31u) * 4u;
             nv[r] = fill > q4 ? min(fill - q4, 4u) : 0u;
             if (nv[r]) d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(bv.pool + (size_t)(entry & 0x01FFFFFFu) * WC_BLOCK_ELEMS) + (v4 & 31u));
@@ -484,6 +494,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
           }
         }
       }
+      if (LINES) fetch_entries(base + COUNT_THREADS * UNROLL);
 #pragma unroll
       for (int r = 0; r < UNROLL; r++) {
         const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};

@@ -107,62 +107,104 @@ struct ScanFront {
   }
 };
 
-constexpr int SB_THREADS = 1024;
 constexpr int SB_SUB_BITS = 16;                        // micro-windows per CTA: 65 536 16-bit counters = 128 KB of shared memory
 
 // CTA (bucket b, sub-range z): counts the elements of b that fall into [z << 16, (z + 1) << 16) and adds them to the table.
 // Counters are 16 bits, two to a word.  The thread whose add takes a counter from below 2^15 to 2^15 or more moves 2^15 to the
 // table; a thread that finds a counter at 3 * 2^14 or more (that correction still pending) takes its own add back and sends it to
 // the table instead.  Every thread has at most one add of <= 4 in flight, so a counter stays below 3 * 2^14 + 4 096 < 2^16.
+template <int SB_THREADS, int SB_UNROLL_>
 __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView wv, uint32_t mb, uint32_t n_sub, uint32_t words, ull *__restrict__ hist) {
-  extern __shared__ __align__(16) uint32_t s_cnt[];   // [words]
+  extern __shared__ __align__(16) uint32_t s_cnt[];   // [words] counters + [32] one dummy word per lane
   const uint32_t b = blockIdx.x / n_sub, z = blockIdx.x % n_sub;
   const uint32_t first = wv.line_off[b], last = wv.line_off[b + 1];
   if (first == last) return;
-  for (uint32_t i = threadIdx.x; i < words; i += SB_THREADS) s_cnt[i] = 0;
+  for (uint32_t i = threadIdx.x * 4; i < words + 32; i += SB_THREADS * 4) *reinterpret_cast<uint4 *>(s_cnt + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const uint32_t lo = z << SB_SUB_BITS, span = 2u * words;
   const ull m0 = ((ull)b << mb) + lo;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the rare part of an add of v that found the counter at `old`
+  auto fixup = [&](uint32_t loc, uint32_t v, uint32_t old) {
+    const uint32_t sh = (loc & 1u) * 16u;
+    if (old < 0x8000u) {                               // this add crossed 2^15: move 2^15 to the table
+      atomicSub(&s_cnt[loc >> 1], 0x8000u << sh);
+      atomicAdd(hist + m0 + loc, 0x8000ull);
+    } else if (old + v >= 0xC000u) {                   // the correction above is still pending and the counter keeps climbing: count elsewhere
+      atomicSub(&s_cnt[loc >> 1], v << sh);
+      atomicAdd(hist + m0 + loc, (ull)v);
+    }
+    __threadfence();                                   // ordered before this CTA's plain read-modify-write of the same entry below
+  };
   auto add = [&](uint32_t loc, uint32_t v) {
     const uint32_t sh = (loc & 1u) * 16u;
     const uint32_t old = (atomicAdd(&s_cnt[loc >> 1], v << sh) >> sh) & 0xFFFFu;
-    if (old + v >= 0x8000u) {                          // rare
-      if (old < 0x8000u) {                             // this add crossed 2^15: move 2^15 to the table
-        atomicSub(&s_cnt[loc >> 1], 0x8000u << sh);
-        atomicAdd(hist + m0 + loc, 0x8000ull);
-      } else if (old + v >= 0xC000u) {                 // the correction above is still pending and the counter keeps climbing: count elsewhere
-        atomicSub(&s_cnt[loc >> 1], v << sh);
-        atomicAdd(hist + m0 + loc, (ull)v);
-      }
-      __threadfence();                                 // ordered before this CTA's plain read-modify-write of the same entry below
-    }
+    if (old + v >= 0x8000u) fixup(loc, v, old);
   };
-  for (uint32_t blk = first + warp; blk < last; blk += SB_THREADS / 32) {
-    const uint32_t entry = __ldg(wv.sorted_lines + blk);
-    const uint32_t fill = (entry >> 25) + 1u, q4 = lane * 4u;
-    if (fill <= q4) continue;
-    const uint4 d = ldg_stream128(reinterpret_cast<const uint4 *>(wv.pool + (size_t)(entry & 0x01FFFFFFu) * WC_BLOCK_ELEMS) + lane);
-    const uint32_t el[4] = {d.x, d.y, d.z, d.w};
-    const uint32_t nv = min(fill - q4, 4u);
-    // runs of equal elements (position-sorted reads) leave as one add
-    uint32_t run = 1;
+  // a warp takes SB_UNROLL blocks (512 bytes each) per trip, and the block ids of the next trip are fetched while this trip's
+  // data is on its way: one memory latency per trip instead of two dependent ones, 128 KB in flight per SM
+  constexpr uint32_t SB_UNROLL = SB_UNROLL_, SB_WARPS = SB_THREADS / 32;
+  uint32_t blk0 = first + warp * SB_UNROLL;
+  uint32_t e_next = blk0 + lane < last && lane < SB_UNROLL ? __ldg(wv.sorted_lines + blk0 + lane) : 0u;
+  for (; blk0 < last; blk0 += SB_WARPS * SB_UNROLL) {
+    const uint32_t e_mine = e_next;
+    uint32_t fill[SB_UNROLL];
+    uint4 d[SB_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if ((uint32_t)i >= nv) break;
-      const bool more = (uint32_t)(i + 1) < nv && el[i + 1 < 4 ? i + 1 : 3] == el[i];
-      if (more) { run++; continue; }
-      const uint32_t loc = el[i] - lo;
-      if (loc < span) add(loc, run);
-      run = 1;
+    for (uint32_t r = 0; r < SB_UNROLL; r++) {
+      const uint32_t entry = __shfl_sync(0xffffffffu, e_mine, r);
+      fill[r] = blk0 + r < last ? (entry >> 25) + 1u : 0u;
+      d[r] = make_uint4(0, 0, 0, 0);
+      if (fill[r] > lane * 4u) d[r] = ldg_stream128(reinterpret_cast<const uint4 *>(wv.pool + (size_t)(entry & 0x01FFFFFFu) * WC_BLOCK_ELEMS) + lane);
+    }
+    {
+      const uint32_t nb0 = blk0 + SB_WARPS * SB_UNROLL;
+      e_next = nb0 + lane < last && lane < SB_UNROLL ? __ldg(wv.sorted_lines + nb0 + lane) : 0u;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < SB_UNROLL; r++) {
+      const uint32_t q4 = lane * 4u;
+      if (fill[r] <= q4) continue;
+      const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};
+      const uint32_t nv = min(fill[r] - q4, 4u);
+      // this CTA's sub-range only (a bucket wider than 65 536 micro-windows is read by several CTAs): keep the test lean
+      const uint32_t l0 = el[0] - lo, l1 = el[1] - lo, l2 = el[2] - lo, l3 = el[3] - lo;
+      const bool in0 = l0 < span, in1 = l1 < span && nv > 1u, in2 = l2 < span && nv > 2u, in3 = l3 < span && nv > 3u;
+      if (!(in0 | in1 | in2 | in3)) continue;
+      if (nv == 4u && el[0] == el[3] && el[0] == el[1] && el[0] == el[2]) { add(l0, 4u); continue; }   // position-sorted reads: one add
+      // the four adds go out back to back; their results are only looked at afterwards (and almost never matter)
+      const uint32_t s0 = (l0 & 1u) * 16u, s1 = (l1 & 1u) * 16u, s2 = (l2 & 1u) * 16u, s3 = (l3 & 1u) * 16u;
+      // (an element outside the sub-range adds 0 to the lane's own dummy word: no branch, no reconvergence barrier around the atomic)
+      const uint32_t dummy = words + lane;
+      const uint32_t o0 = atomicAdd(&s_cnt[in0 ? l0 >> 1 : dummy], in0 ? 1u << s0 : 0u) >> s0;
+      const uint32_t o1 = atomicAdd(&s_cnt[in1 ? l1 >> 1 : dummy], in1 ? 1u << s1 : 0u) >> s1;
+      const uint32_t o2 = atomicAdd(&s_cnt[in2 ? l2 >> 1 : dummy], in2 ? 1u << s2 : 0u) >> s2;
+      const uint32_t o3 = atomicAdd(&s_cnt[in3 ? l3 >> 1 : dummy], in3 ? 1u << s3 : 0u) >> s3;
+      if (((o0 + 1u) | (o1 + 1u) | (o2 + 1u) | (o3 + 1u)) & 0x8000u) {     // some counter was at 2^15 - 1 or beyond
+        if (in0 && (o0 & 0xFFFFu) >= 0x7FFFu) fixup(l0, 1u, o0 & 0xFFFFu);
+        if (in1 && (o1 & 0xFFFFu) >= 0x7FFFu) fixup(l1, 1u, o1 & 0xFFFFu);
+        if (in2 && (o2 & 0xFFFFu) >= 0x7FFFu) fixup(l2, 1u, o2 & 0xFFFFu);
+        if (in3 && (o3 & 0xFFFFu) >= 0x7FFFu) fixup(l3, 1u, o3 & 0xFFFFu);
+      }
     }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < words; i += SB_THREADS) {
-    const uint32_t w = s_cnt[i];
-    if (w) {
-      if (w & 0xFFFFu) hist[m0 + 2 * i] += (ull)(w & 0xFFFFu);
-      if (w >> 16) hist[m0 + 2 * i + 1] += (ull)(w >> 16);
+  // four counters (two words) per thread and trip: 32-byte reads and writes of the table, all loads of a trip issued before its stores
+  constexpr uint32_t FL_UNROLL = 4;
+  ulonglong2 *hv = reinterpret_cast<ulonglong2 *>(hist + m0);                 // m0 is a multiple of 1 024: 16-byte aligned
+  for (uint32_t i0 = threadIdx.x; i0 < words; i0 += SB_THREADS * FL_UNROLL) {
+    uint32_t w[FL_UNROLL];
+    ulonglong2 h[FL_UNROLL];
+#pragma unroll
+    for (uint32_t r = 0; r < FL_UNROLL; r++) {
+      const uint32_t i = i0 + r * SB_THREADS;
+      w[r] = i < words ? s_cnt[i] : 0u;
+      if (w[r]) h[r] = hv[i];
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < FL_UNROLL; r++) {
+      const uint32_t i = i0 + r * SB_THREADS;
+      if (w[r]) { h[r].x += (ull)(w[r] & 0xFFFFu); h[r].y += (ull)(w[r] >> 16); hv[i] = h[r]; }
     }
   }
 }
@@ -262,17 +304,27 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
     return;
   }
   if (threadIdx.x == 0) tile_base = blockIdx.x == 0 ? 0ull : tile_counts[blockIdx.x - 1];   // inclusive-scanned counts
-  __syncthreads();
-  int64_t o = (int64_t)tile_base + (warp > 0 ? warp_counts[warp - 1] : 0) + inc - mine;
+  __syncthreads();                                                     // also: everybody is done reading s_h
+  // the kept windows go to shared memory in output order and leave as coalesced runs of the four output arrays
+  __shared__ uint16_t s_idx[WIN_TILE], s_slot[WIN_TILE];
+  ull *s_val = s_h;
+  int r = (warp > 0 ? warp_counts[warp - 1] : 0) + inc - mine;
 #pragma unroll
   for (int i = 0; i < WIN_ITEMS; i++) {
     if (keep & (1u << i)) {
-      const int s = slot_of[i];
-      o_chrom[o] = t.chrom[s]; o_strand[o] = t.strand[s];
-      o_win[o] = first + i - t.win_off[s] + 1;                     // 1-based window number, :5109-5112
-      o_value[o] = val[i];
-      o++;
+      s_val[r] = (ull)val[i];
+      s_idx[r] = (uint16_t)(threadIdx.x * WIN_ITEMS + i);
+      s_slot[r] = (uint16_t)(slot_of[i] - slot_a);                     // a tile spans at most WIN_TILE slots
+      r++;
     }
+  }
+  __syncthreads();
+  const int64_t o0 = (int64_t)tile_base;
+  for (int j = threadIdx.x; j < block_total; j += WIN_THREADS) {
+    const int s = slot_a + s_slot[j];
+    o_chrom[o0 + j] = t.chrom[s]; o_strand[o0 + j] = t.strand[s];
+    o_win[o0 + j] = tile_first + s_idx[j] - t.win_off[s] + 1;           // 1-based window number, :5109-5112
+    o_value[o0 + j] = (long long)s_val[j];
   }
 }
 
@@ -387,7 +439,7 @@ extern "C" int gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bou
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_slot_strand, slot_strand);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_hist_off, hist_off);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_win_off, win_off);
-  if (rc == GTB_OK) rc = sc->d_hist.reserve(ctx, (size_t)std::max<int64_t>(sc->total_micro, 1));
+  if (rc == GTB_OK) rc = sc->d_hist.reserve(ctx, (size_t)std::max<int64_t>(sc->total_micro, 1) + 2);   // + 2: the bucketed flush moves entries in pairs
   if (rc == GTB_OK) rc = gtb_scan_reset(sc);
   if (rc == GTB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GTB_ERR_CUDA;
   for (auto &st : sc->stages) {
@@ -427,10 +479,18 @@ static int scan_accumulate_device(gtb_scan *sc, const ReadView &q) {
                             sc->prm.ignore_strand ? 1 : 0, sc->d_hist.p};
       const WcQueries wq{q.n_intervals, q.chrom, q.start, q.stop, q.strand, 0};
       GTB_TRY(wc_partition_launch(ctx, "scan_partition", wq, front, wv, gridw, wc_smem_bytes(sc->n_buckets, (size_t)2 * std::max(sc->n_chrom, 1) + 2)));
-      const size_t smem = (size_t)sc->sb_words * 4;
-      GTB_CUDA_OK(ctx, cudaFuncSetAttribute(scan_bucket_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      GTB_LAUNCH(ctx, "scan_bucket_hist", scan_bucket_hist_kernel, sc->n_buckets * sc->n_sub, SB_THREADS, smem, wv, sc->mb, sc->n_sub, sc->sb_words,
-                 sc->d_hist.p);
+      const size_t smem = ((size_t)sc->sb_words + 32) * 4;
+      static const int variant = getenv("GTB_SB_VARIANT") ? atoi(getenv("GTB_SB_VARIANT")) : 0;    // tuning knob
+#define GTB_SB_LAUNCH(T, U)                                                                                                          \
+  do {                                                                                                                               \
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(scan_bucket_hist_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    GTB_LAUNCH(ctx, "scan_bucket_hist", (scan_bucket_hist_kernel<T, U>), sc->n_buckets * sc->n_sub, T, smem, wv, sc->mb, sc->n_sub,  \
+               sc->sb_words, sc->d_hist.p);                                                                                          \
+  } while (0)
+      if (variant == 1) GTB_SB_LAUNCH(1024, 2);
+      else if (variant == 2) GTB_SB_LAUNCH(512, 8);
+      else GTB_SB_LAUNCH(1024, 4);
+#undef GTB_SB_LAUNCH
       return gtb_check_launch(ctx);
     }
   }

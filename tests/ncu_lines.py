@@ -18,6 +18,11 @@ def main(path, kernel, top=30):
         if len(r) < len(hdr) or not r[0].isdigit():
             continue
         f = lambda n: float(r[ci[n]] or 0) if n in ci and r[ci[n]] not in ("", "-") else 0.0
+        try:                                          # source lines with quotes and commas (inline asm) do not survive the CSV export
+            f("Instructions Executed"), f("# Samples"), f("L1 Wavefronts Shared"), f("L1 Wavefronts Shared Ideal"), f("stall_short_sb")
+            f("stall_long_sb"), f("stall_barrier"), f("stall_wait"), f("stall_mio"), f("stall_selected"), f("L2 Theoretical Sectors Global")
+        except ValueError:
+            continue
         tab.append(dict(line=int(r[0]), src=r[1].strip()[:90], inst=f("Instructions Executed"), smp=f("# Samples"), wf=f("L1 Wavefronts Shared"),
                         wfi=f("L1 Wavefronts Shared Ideal"), ssb=f("stall_short_sb"), lsb=f("stall_long_sb"), bar=f("stall_barrier"),
                         wait=f("stall_wait"), mio=f("stall_mio"), sel=f("stall_selected"), g=f("L2 Theoretical Sectors Global")))
