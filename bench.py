@@ -299,8 +299,19 @@ def main():
     peak, peak_kind = measured_peak()
     alg_bytes = BYTES_PER_QUERY * n                      # one launch of the dominant kernel streams the whole batch
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload (never measured
+    # under the profiler here); only quoted when the batch size is the one that was captured
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("reads") == n and dom_name in tr:
+            traffic = tr[dom_name]["dram_bytes_read"] + tr[dom_name]["dram_bytes_write"]
+            traffic_src = tr["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel_ms": dom_ms, "kernel_share_of_step": dom["total_ms"] / total_prof_ms,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom["total_ms"] / total_prof_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "step_frac": (BYTES_PER_QUERY * n + BYTES_PER_REGION * N_REGIONS) / (ms_per_step * 1e-3) / 1e9 / peak,
                 "kernels": {k: {"launches_per_step": v["launches"] / 3, "ms_per_launch": v["total_ms"] / v["launches"]} for k, v in prof.items()}}
