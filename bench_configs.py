@@ -21,6 +21,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=100_000_000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--regions", type=int, default=60_000, help="index regions (1000000 with --region-len 200,100000 = BASELINE configs[4])")
+    ap.add_argument("--region-len", default="500,500000", help="min,max of the log-uniform region length")
     ap.add_argument("--only", default="", help="comma-separated subset of: count, coverage, sorted, scan")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
@@ -43,7 +45,9 @@ def main():
            "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
     ctx.synth_reads(2, 0, n, 50, support.HG19_LENS, dev)
     dset, keep = gtb200.device_set(dev)
-    regions = support.synth_regions(60_000, 3)
+    rl = [int(x) for x in args.region_len.split(",")]
+    regions = support.synth_regions(args.regions, 3 if args.regions == 60_000 else 7, rl[0], rl[1])
+    m = args.regions
 
     def timed(name, fn, bytes_per_step, extra=None):
         for _ in range(3):
@@ -67,7 +71,7 @@ def main():
         ctx.profile(False)
         print(json.dumps(line), flush=True)
 
-    out = torch.zeros(60_000, dtype=torch.int64, device="cuda")
+    out = torch.zeros(m, dtype=torch.int64, device="cuda")
     for name, op, flags in (("count (configs[1])", gtb200.OP_COUNT, 0), ("count -i", gtb200.OP_COUNT, gtb200.IGNORE_STRAND),
                             ("coverage (configs[3], single-interval variant)", gtb200.OP_COVERAGE, 0)):
         if not wanted("coverage" if op == gtb200.OP_COVERAGE else "count"):
@@ -78,7 +82,7 @@ def main():
             ix.reset()
             ix.add_set(dset, gtb200.MEM_DEVICE)
             ix.finish_ptr(out.data_ptr(), gtb200.MEM_DEVICE)
-        timed(name, step, 13 * n + 21 * 60_000)
+        timed(name, step, 13 * n + 21 * m, {"regions": m})
         ix.close()
 
     if wanted("sorted"):
@@ -95,7 +99,7 @@ def main():
             ix.reset()
             ix.add_set(sset, gtb200.MEM_DEVICE)
             ix.finish_ptr(out.data_ptr(), gtb200.MEM_DEVICE)
-        timed("count, reads sorted by chromosome/strand/start", step_sorted, 13 * n + 21 * 60_000)
+        timed("count, reads sorted by chromosome/strand/start", step_sorted, 13 * n + 21 * m, {"regions": m})
         ix.close()
         del sdev, sset
 

@@ -48,7 +48,6 @@ constexpr int PAGE_SHIFT = 12;
 constexpr uint32_t PAGE = 1u << PAGE_SHIFT;               // elements per page (== PART_TILE: a tile's slice spans <= 2 pages)
 constexpr int UNIT_PAGES = 16;                            // pass-2 work unit = 65 536 elements
 constexpr int MAX_BUCKETS = 2048;
-constexpr int COUNT_THREADS = 256;
 constexpr size_t COUNT_SMEM_BUDGET = 200 * 1024;
 
 struct BucketView {
@@ -374,8 +373,10 @@ __global__ void __launch_bounds__(1024) bucket_units_kernel(BucketView bv) {
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
-template <bool COVERAGE, bool LINES>
-__global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketView bv, RankView rv) {
+// COUNT_THREADS x resident CTAs = 1 024 threads per SM: an index dense enough to need most of an SM's shared memory for one
+// bucket (1 M regions) runs one CTA of 1 024 threads, a sparse one (60 k regions) four of 256
+template <bool COVERAGE, bool LINES, int COUNT_THREADS>
+__global__ void __launch_bounds__(COUNT_THREADS, 1024 / COUNT_THREADS) bucket_count_kernel(BucketView bv, RankView rv) {
   extern __shared__ __align__(128) uint32_t smem[];
   const int cb = bv.ub - bv.k;
   const uint32_t n_dir = 1u << cb;
@@ -549,6 +550,21 @@ __global__ void __launch_bounds__(COUNT_THREADS, 4) bucket_count_kernel(BucketVi
   flush();
 }
 
+// pass 2 with as many threads per CTA as keeps 1 024 threads on an SM
+template <bool COVERAGE, bool LINES>
+int launch_count_pass(gtb_ctx *ctx, const char *name, unsigned ctas_per_sm, size_t smem, const BucketView &bv, const RankView &rv) {
+#define GTB_COUNT_LAUNCH(T)                                                                                                       \
+  do {                                                                                                                            \
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<COVERAGE, LINES, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    GTB_LAUNCH(ctx, name, (bucket_count_kernel<COVERAGE, LINES, T>), (unsigned)ctx->sm_count * (1024 / T), T, smem, bv, rv);       \
+  } while (0)
+  if (ctas_per_sm >= 4) GTB_COUNT_LAUNCH(256);
+  else if (ctas_per_sm >= 2) GTB_COUNT_LAUNCH(512);
+  else GTB_COUNT_LAUNCH(1024);
+#undef GTB_COUNT_LAUNCH
+  return gtb_check_launch(ctx);
+}
+
 template <typename T>
 int upload_b(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
   GTB_TRY(d.reserve(ctx, h.size() ? h.size() : 1));
@@ -607,6 +623,13 @@ int gtb_bucket_prepare(gtb_index *ix) {
   // (measured on B200: k = 9 instead of 14 for hg19 x 60 k regions takes bucket_count from 0.283 to 0.221 ms)
   int k = 4;
   while (k < 14 && (span >> (k + 1)) >= 64 * n_points) k++;
+  // ... but no finer than 2^15 cells per bucket (a 64 KB directory): a dense index (1 M regions) would otherwise be pushed to
+  // buckets so narrow that there are thousands of them
+  {
+    int ub0 = 24;
+    while (ub0 > 20 && (span >> ub0) < 256) ub0--;
+    k = std::max(k, ub0 - 15);
+  }
   if (const char *env = getenv("GTB_BUCKET_K")) k = std::max(0, std::min(16, atoi(env)));
   std::vector<uint32_t> gbase((size_t)std::max(G, 1), 0);
   uint64_t cells = 0;
@@ -733,7 +756,6 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   const bool cov = ix->op == GTB_OP_COVERAGE;
   const size_t per_sm = 227 * 1024;
   const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(4, per_sm / (bs->count_smem + 1024)));
-  const unsigned grid2 = (unsigned)ctx->sm_count * ctas_per_sm;
 
   // ---- write-combining form of pass 1 (default)
   if (bs->wc_ok && !bs->wc_off && bs->wc_smem <= ctx->smem_optin && !getenv("GTB_BUCKET_PAGED")) {
@@ -756,12 +778,10 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
       const WcQueries wq{q.n_regions, q.chrom, q.start, q.stop, q.strand, q.index_base};
       if (cov) {
         GTB_TRY(wc_partition_launch(ctx, "bucket_partition", wq, OverlapFront<true>{rv, bv}, wv, gridw, bs->wc_smem));
-        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-        GTB_LAUNCH(ctx, "bucket_coverage", (bucket_count_kernel<true, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+        GTB_TRY((launch_count_pass<true, true>)(ctx, "bucket_coverage", ctas_per_sm, bs->count_smem, bv, rv));
       } else {
         GTB_TRY(wc_partition_launch(ctx, "bucket_partition", wq, OverlapFront<false>{rv, bv}, wv, gridw, bs->wc_smem));
-        GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-        GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, true>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+        GTB_TRY((launch_count_pass<false, true>)(ctx, "bucket_count", ctas_per_sm, bs->count_smem, bv, rv));
       }
       bs->wc_queries += q.n_regions;
       if (getenv("GTB_DEBUG_WC")) {                                      // diagnostics: how the batch travelled
@@ -807,11 +827,9 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   GTB_TRY(gtb_check_launch(ctx));
   GTB_LAUNCH(ctx, "bucket_units", bucket_units_kernel, 1, 1024, 0, bv);
   if (cov) {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-    GTB_LAUNCH(ctx, "bucket_coverage", (bucket_count_kernel<true, false>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+    GTB_TRY((launch_count_pass<true, false>)(ctx, "bucket_coverage", ctas_per_sm, bs->count_smem, bv, rv));
   } else {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(bucket_count_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs->count_smem));
-    GTB_LAUNCH(ctx, "bucket_count", (bucket_count_kernel<false, false>), grid2, COUNT_THREADS, bs->count_smem, bv, rv);
+    GTB_TRY((launch_count_pass<false, false>)(ctx, "bucket_count", ctas_per_sm, bs->count_smem, bv, rv));
   }
   return gtb_check_launch(ctx);
 }

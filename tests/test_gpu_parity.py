@@ -209,6 +209,24 @@ def test_sorted_and_clustered_input(gtb, ctx, oracle):
                 ix.close()
 
 
+def test_dense_index(gtb, ctx, oracle):
+    """An index dense enough (hundreds of thousands of short regions) that one bucket's points fill most of an SM's shared
+    memory: the directory stops refining, pass 2 runs one wide CTA per SM.  Count and coverage, default engine."""
+    import torch
+    n = 1_000_000
+    reads = support.synth_reads(n, seed=51)
+    regions = support.synth_regions(250_000, seed=52, min_len=200, max_len=5_000)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in reads.items()}
+    for flags in (0, gtb.IGNORE_STRAND):
+        for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+            rc, want, _ = fn(reads, regions, flags)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, flags)
+            ix.add_device(dev)
+            assert np.array_equal(ix.finish(), want), (op, flags)
+            ix.close()
+
+
 @pytest.fixture(params=("bucketed", "direct"))
 def scan_form(request, monkeypatch):
     """Both ways of building the micro-window histogram: the write-combining partition + shared-memory counters (forced for
