@@ -163,12 +163,14 @@ def run_reference(args):
 
 
 def main():
+    global N_REGIONS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU (default: the BASELINE config)")
+    ap.add_argument("--regions", type=int, default=N_REGIONS, help="index regions (default: the BASELINE config; 1000000 = configs[4])")
     ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "bucket", "enumerate"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg (the line is then not a valid bench line)")
@@ -193,7 +195,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.reads
-    regions = support.synth_regions(N_REGIONS, SEED_REGIONS)
+    workload = "100M synthetic 50bp hg19 reads vs 60k gene regions, strand-aware count (configs[1])"
+    if args.regions != N_REGIONS:            # configs[4] shape: 1 M regions of 200 bp - 100 kb, seed 7
+        N_REGIONS = args.regions
+        regions = support.synth_regions(N_REGIONS, 7, 200, 100_000)
+        workload = "%d synthetic 50bp hg19 reads per GPU vs %d regions (200 bp - 100 kb), strand-aware count (configs[4] shape)" % (n, N_REGIONS)
+    else:
+        regions = support.synth_regions(N_REGIONS, SEED_REGIONS)
     ctx = gtb200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -363,7 +371,7 @@ def main():
         line = {"metric": "query intervals/sec (overlap-count, device-timed)", "value": value, "unit": "query intervals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-                "config": {"workload": "100M synthetic 50bp hg19 reads vs 60k gene regions, strand-aware count (configs[1])",
+                "config": {"workload": workload,
                            "reads_per_gpu": n, "n_regions": N_REGIONS, "read_len": READ_LEN, "engine": args.engine,
                            "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_QUERY * n / 1e9),
                            "parallelism": "genome-sharded x%d: region ownership by range, boundary reads replicated at ingest, one NCCL "
