@@ -32,6 +32,12 @@ static void check(gtb_ctx *ctx, int rc, const char *what) {
   exit(1);
 }
 
+[[noreturn]] static void die_query(int rc, long line) {
+  gt::die_line(line, rc == GTB_ERR_QUERY_STOP_NONPOSITIVE ? "stop position must be positive!"
+                     : rc == GTB_ERR_QUERY_START_GT_STOP ? "start position cannot be greater than stop position!"
+                                                          : "query regions should be compatible, sorted and non-overlapping!");
+}
+
 static gtb_set as_set(const gt::RegionBatch &b) {
   gtb_set s;
   s.n_regions = b.n_regions();
@@ -108,16 +114,16 @@ int main(int argc, char *argv[]) {
   gt::RegionBatch ref;
   {
     gt::RegionReader rr(ref_file, &chroms, true, 1);
-    rr.Read(&ref, INT64_MAX);
+    rr.ReadAll(&ref);
     if (VERBOSE) std::cerr << "Reading from '" << ref_file << "'; number of regions = " << ref.n_regions() << "; format = " << rr.format() << "\n";
   }
   if (IS_SORTED) {
     gt::SortChecker sc; sc.by_strand = SORTED_BY_STRAND;
     for (int64_t k = 0; k < ref.n_regions(); k++) {
-      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line[k], "index regions should be compatible, sorted and non-overlapping!");
+      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line(k), "index regions should be compatible, sorted and non-overlapping!");
       const int64_t i = ref.offset[k];
       if (!sc.Accept(chroms.name[ref.chrom[i]], (char)ref.strand[i], ref.start[i]))
-        gt::die_line(ref.line[k], std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+        gt::die_line(ref.line(k), std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
     }
   }
 
@@ -131,15 +137,13 @@ int main(int argc, char *argv[]) {
   gtb_set ref_set = as_set(ref);
   ref_set.weight = nullptr;
   rc = gtb_index_create(ctx, &ref_set, want_coverage ? GTB_OP_COVERAGE : GTB_OP_COUNT, flags, &index, &err_index);
-  if (rc == GTB_ERR_INDEX_REGION) gt::die_line(ref.line[err_index], "index regions should be compatible, sorted and non-overlapping!");
+  if (rc == GTB_ERR_INDEX_REGION) gt::die_line(ref.line(err_index), "index regions should be compatible, sorted and non-overlapping!");
   check(ctx, rc, "gtb_index_create");
 
   // ---- test (query) set: streamed in chunks; parsing of chunk k+1 overlaps the device work of chunk k
   const int64_t CHUNK = 4 << 20;
   gt::RegionBatch chunk[2];
-  std::vector<long> chunk_first_line;                                  // to translate a query index into a line number
-  std::vector<int64_t> chunk_first_index;
-  std::vector<std::vector<long>> chunk_lines;
+  long first_query_line = 0;                                           // every data line is one query: query k is on first_query_line + k
   {
     gt::RegionReader qr(test_file, &chroms, false, MAX_LABEL_VALUE);
     if (VERBOSE) std::cerr << "Reading from '" << (test_file ? test_file : "<standard input>") << "'; format = " << qr.format() << "\n";
@@ -153,29 +157,30 @@ int main(int argc, char *argv[]) {
       if (IS_SORTED)
         for (int64_t k = 0; k < b.n_regions(); k++) {
           const int64_t i = b.offset[k];
-          if (!gt::RegionWellFormed(b, k)) gt::die_line(b.line[k], "query regions should be compatible, sorted and non-overlapping!");
+          if (!gt::RegionWellFormed(b, k)) gt::die_line(b.line(k), "query regions should be compatible, sorted and non-overlapping!");
           if (!sc.Accept(chroms.name[b.chrom[i]], (char)b.strand[i], b.start[i]))
-            gt::die_line(b.line[k], std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+            gt::die_line(b.line(k), std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
         }
       gtb_set qs = as_set(b);
       check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");
-      chunk_first_index.push_back(seen);
-      chunk_lines.push_back(b.line);
+      if (seen == 0) first_query_line = b.first_line;
       seen += b.n_regions();
       which ^= 1;
+    }
+    check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");
+    if (qr.failed()) {
+      // a malformed line ended the stream; a query before it that the engine refuses comes first in the file and is the one
+      // the reference would have stopped at
+      std::vector<uint64_t> scratch((size_t)std::max<int64_t>(ref.n_regions(), 1));
+      rc = gtb_index_finish(index, scratch.data(), GTB_MEM_HOST, &err_index);
+      if (rc != GTB_ERR_QUERY_STOP_NONPOSITIVE && rc != GTB_ERR_QUERY_START_GT_STOP && rc != GTB_ERR_QUERY_REGION) qr.Fail();
+      die_query(rc, first_query_line + err_index);
     }
   }
   std::vector<uint64_t> values((size_t)std::max<int64_t>(ref.n_regions(), 1));
   rc = gtb_index_finish(index, values.data(), GTB_MEM_HOST, &err_index);
-  if (rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION) {
-    long line = 0;
-    for (size_t c = 0; c < chunk_first_index.size(); c++)
-      if (err_index >= chunk_first_index[c] && err_index < chunk_first_index[c] + (int64_t)chunk_lines[c].size())
-        line = chunk_lines[c][(size_t)(err_index - chunk_first_index[c])];
-    gt::die_line(line, rc == GTB_ERR_QUERY_STOP_NONPOSITIVE ? "stop position must be positive!"
-                       : rc == GTB_ERR_QUERY_START_GT_STOP ? "start position cannot be greater than stop position!"
-                                                            : "query regions should be compatible, sorted and non-overlapping!");
-  }
+  if (rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION)
+    die_query(rc, first_query_line + err_index);
   check(ctx, rc, "gtb_index_finish");
 
   // ---- output, reference-file order (genomic_overlaps.cpp:420-427, :449-455, :476-486, :763-772)

@@ -45,11 +45,11 @@ static std::map<std::string, long> ReadBounds(const char *genome_reg_file) {
   gt::ChromTable chroms;
   gt::RegionBatch b;
   gt::RegionReader rr(genome_reg_file, &chroms, true, 1);
-  rr.Read(&b, INT64_MAX);
+  rr.ReadAll(&b);
   for (int64_t k = 0; k < b.n_regions(); k++) {
     if (b.offset[k + 1] - b.offset[k] != 1) {
       std::cerr << "label = " << b.label[k] << '\n';
-      gt::die_line(b.line[k], "genome regions should be single-interval regions!\n");
+      gt::die_line(b.line(k), "genome regions should be single-interval regions!\n");
     }
     const std::string &chr = chroms.name[b.chrom[b.offset[k]]];
     const long stop = b.stop[b.offset[k]];
@@ -76,7 +76,7 @@ struct RefFilter {
     std::map<std::pair<int32_t, char>, std::vector<std::pair<long, long>>> tmp;
     for (int64_t k = 0; k < ref.n_regions(); k++) {
       const int64_t lo = ref.offset[k], hi = ref.offset[k + 1];
-      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line[k], "index regions should be compatible, sorted and non-overlapping!");
+      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line(k), "index regions should be compatible, sorted and non-overlapping!");
       const long s = ref.start[lo], e = ref.stop[hi - 1];
       if (s > e || e <= 0) continue;
       const char strand = ignore ? '+' : (char)ref.strand[lo];
@@ -178,9 +178,9 @@ int main(int argc, char *argv[]) {
     if (SORTED)
       for (int64_t k = 0; k < b.n_regions(); k++) {
         const int64_t i = b.offset[k];
-        if (b.offset[k + 1] - i != 1) gt::die_line(b.line[k], "single-interval regions expected for this operation!\n");
+        if (b.offset[k + 1] - i != 1) gt::die_line(b.line(k), "single-interval regions expected for this operation!\n");
         if (!sc.Accept(chroms.name[b.chrom[i]], (char)b.strand[i], b.start[i]))
-          gt::die_line(b.line[k], std::string("input regions are not sorted (sorted-by-strand = ") + (IGNORE_STRAND ? "false" : "true") + ")!");
+          gt::die_line(b.line(k), std::string("input regions are not sorted (sorted-by-strand = ") + (IGNORE_STRAND ? "false" : "true") + ")!");
       }
     gtb_set s;
     s.n_regions = b.n_regions(); s.n_intervals = (int64_t)b.chrom.size();
@@ -189,6 +189,7 @@ int main(int argc, char *argv[]) {
     s.region_offset = b.multi ? b.offset.data() : nullptr;
     check(ctx, gtb_scan_add_reads(scan, &s, GTB_MEM_HOST), "gtb_scan_add_reads");
   }
+  if (reads.failed()) reads.Fail();
   int64_t n_windows = 0;
   check(ctx, gtb_scan_finish(scan, &n_windows), "gtb_scan_finish");
 
@@ -198,13 +199,13 @@ int main(int argc, char *argv[]) {
   if (use_filter) {
     gt::RegionBatch ref;
     gt::RegionReader rr(REF_REG_FILE, &chroms, false, 1);
-    rr.Read(&ref, INT64_MAX);
+    rr.ReadAll(&ref);
     if (REF_SORTED) {
       gt::SortChecker rs; rs.by_strand = !IGNORE_STRAND;
       for (int64_t k = 0; k < ref.n_regions(); k++) {
         const int64_t i = ref.offset[k];
         if (!rs.Accept(chroms.name[ref.chrom[i]], (char)ref.strand[i], ref.start[i]))
-          gt::die_line(ref.line[k], std::string("input regions are not sorted (sorted-by-strand = ") + (IGNORE_STRAND ? "false" : "true") + ")!");
+          gt::die_line(ref.line(k), std::string("input regions are not sorted (sorted-by-strand = ") + (IGNORE_STRAND ? "false" : "true") + ")!");
       }
     }
     filter.Build(ref, IGNORE_STRAND);

@@ -1,8 +1,13 @@
 // gt_host.cpp -- see gt_host.h
 #include "gt_host.h"
+#include <errno.h>
+#include <fcntl.h>
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
+#include <algorithm>
+#include <functional>
 #include <iostream>
 
 namespace gt {
@@ -107,48 +112,123 @@ void CmdLine::OperationUsage() {
 // ---------------------------------------------------------------------------------------------
 // LineReader
 // ---------------------------------------------------------------------------------------------
+static const size_t kBlockBytes = 32u << 20;
+
 LineReader::LineReader(const char *path) {
-  buf_.resize(1 << 22);
-  if (path == nullptr) { fp_ = stdin; return; }
-  FILE *probe = fopen(path, "r");
-  if (probe == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
-  fclose(probe);
-  gz_ = gzopen(path, "rb");                          // zlib passes plain text through unchanged
-  if (gz_ == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
-  gzbuffer(gz_, 1 << 20);
+  if (path == nullptr) fd_ = 0;
+  else {
+    fd_ = open(path, O_RDONLY);
+    if (fd_ < 0) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd_, magic, 2, 0);                       // gzip sniff by magic (core.cpp:1757-1775)
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+      gz_ = gzdopen(fd_, "rb");
+      if (gz_ == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
+      gzbuffer(gz_, 1 << 20);
+    }
+  }
+  producer_ = std::thread(&LineReader::Produce, this);
 }
 
 LineReader::~LineReader() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    quit_ = true;
+  }
+  cv_.notify_all();
+  producer_.join();
   if (gz_) gzclose(gz_);
+  else if (fd_ > 0) close(fd_);
+  for (auto &b : block_) free(b.data);
 }
 
-bool LineReader::Fill() {
-  if (eof_) return false;
-  if (begin_ > 0) { memmove(buf_.data(), buf_.data() + begin_, end_ - begin_); end_ -= begin_; begin_ = 0; }
-  if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);             // a line longer than the buffer
-  size_t want = buf_.size() - end_;
-  long got = gz_ ? (long)gzread(gz_, buf_.data() + end_, (unsigned)std::min<size_t>(want, 1u << 30))
-                 : (long)fread(buf_.data() + end_, 1, want, fp_);
-  if (got <= 0) { eof_ = true; return false; }
-  end_ += (size_t)got;
+long LineReader::ReadSome(char *dst, size_t want) {
+  if (gz_) return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
+  for (;;) {
+    const ssize_t got = read(fd_, dst, want);
+    if (got < 0 && errno == EINTR) continue;
+    return (long)got;
+  }
+}
+
+void LineReader::Produce() {
+  std::vector<char> carry;                                             // the incomplete line at the end of the previous block
+  bool eof = false;
+  for (int tail = 0; !eof; tail = (tail + 1) % kBlocks) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return quit_ || ready_ < kBlocks; });
+      if (quit_) return;
+    }
+    Block &b = block_[tail];
+    // the first block is small, so that a short file (or the format sniffing of a long one) is not held up by a large read
+    const size_t want = tail == 0 && b.data == nullptr ? (1u << 20) : kBlockBytes;
+    if (b.cap < carry.size() + want) {
+      b.cap = carry.size() + want;
+      b.data = (char *)realloc(b.data, b.cap);
+      if (b.data == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
+    }
+    memcpy(b.data, carry.data(), carry.size());
+    size_t have = carry.size();
+    b.len = 0;
+    for (;;) {
+      if (have == b.cap) {                                             // a line longer than the block
+        b.cap *= 2;
+        b.data = (char *)realloc(b.data, b.cap);
+        if (b.data == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
+      }
+      const long got = ReadSome(b.data + have, b.cap - have);
+      if (got <= 0) { eof = true; break; }
+      have += (size_t)got;
+      if (have < b.cap) continue;                                      // short reads (pipe, gzip): keep filling the block
+      const char *nl = (const char *)memrchr(b.data, '\n', have);
+      if (nl != nullptr) { b.len = (size_t)(nl - b.data) + 1; break; }
+    }
+    if (eof) {                                                         // an unterminated last line is dropped (core.cpp:243)
+      const char *nl = have ? (const char *)memrchr(b.data, '\n', have) : nullptr;
+      b.len = nl ? (size_t)(nl - b.data) + 1 : 0;
+    }
+    carry.assign(b.data + b.len, b.data + have);
+    std::lock_guard<std::mutex> lk(mu_);
+    if (b.len > 0) ready_++;
+    if (eof) done_ = true;
+    cv_.notify_all();
+  }
+}
+
+bool LineReader::Acquire() {
+  std::unique_lock<std::mutex> lk(mu_);
+  if (cur_ >= 0) { ready_--; cur_ = -1; cv_.notify_all(); }
+  cv_.wait(lk, [&] { return ready_ > 0 || done_; });
+  if (ready_ == 0) return false;
+  cur_ = head_;
+  head_ = (head_ + 1) % kBlocks;
+  pos_ = 0;
   return true;
 }
 
 char *LineReader::Next() {
-  size_t scan = begin_;
-  for (;;) {
-    char *nl = (char *)memchr(buf_.data() + scan, '\n', end_ - scan);
-    if (nl) {
-      char *line = buf_.data() + begin_;
-      *nl = 0;
-      begin_ = (size_t)(nl - buf_.data()) + 1;
-      line_no_++;
-      return line;
-    }
-    const size_t had = end_ - begin_;
-    if (!Fill()) return nullptr;                                       // an unterminated last line is dropped (core.cpp:243)
-    scan = begin_ + had;
+  if (cur_ < 0 || pos_ >= block_[cur_].len) {
+    if (!Acquire()) return nullptr;
   }
+  Block &b = block_[cur_];
+  char *line = b.data + pos_;
+  char *nl = (char *)memchr(line, '\n', b.len - pos_);                 // a block ends with '\n'
+  *nl = 0;
+  pos_ = (size_t)(nl - b.data) + 1;
+  line_no_++;
+  return line;
+}
+
+bool LineReader::NextRun(char **begin, char **end) {
+  if (cur_ < 0 || pos_ >= block_[cur_].len) {
+    if (!Acquire()) return false;
+  }
+  Block &b = block_[cur_];
+  *begin = b.data + pos_;
+  *end = b.data + b.len;
+  pos_ = b.len;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,15 +259,39 @@ static char *NextToken(char **p, char delim) {
   return b;
 }
 
+// atol for the common case (blanks, sign, up to 18 digits); anything longer goes to the library so that overflow behaves alike
+static inline long FastAtol(const char *s) {
+  const char *p = s;
+  while (*p == ' ' || (unsigned)(*p - 9) < 5u) p++;
+  const bool neg = *p == '-';
+  if (*p == '-' || *p == '+') p++;
+  unsigned long v = 0;
+  int digits = 0;
+  while ((unsigned)(*p - '0') < 10u) { v = v * 10 + (unsigned)(*p - '0'); p++; digits++; }
+  if (digits > 18) return atol(s);
+  return neg ? -(long)v : (long)v;
+}
+
+// '1','+' -> '+'; '-1','-' -> '-'; '.' -> '+'; else 0 (fatal for the caller)
+static inline char StrandOf(const char *t) {
+  if (t[0] != 0 && t[1] == 0) {
+    if (t[0] == '+' || t[0] == '1' || t[0] == '.') return '+';
+    if (t[0] == '-') return '-';
+    return 0;
+  }
+  if (t[0] == '-' && t[1] == '1' && t[2] == 0) return '-';
+  return 0;
+}
+
 char ProcessStrand(const char *t) {
-  if (!strcmp(t, "1") || !strcmp(t, "+")) return '+';
-  if (!strcmp(t, "-1") || !strcmp(t, "-")) return '-';
-  if (!strcmp(t, ".")) return '+';
+  const char s = StrandOf(t);
+  if (s) return s;
   std::cerr << "Error: invalid strand '" << t << "'!\n";
   exit(1);
 }
 
 int32_t ChromTable::Get(const char *chrom) {
+  std::lock_guard<std::mutex> lk(mu_);
   auto it = id.find(chrom);
   if (it != id.end()) return it->second;
   int32_t v = (int32_t)name.size();
@@ -197,8 +301,9 @@ int32_t ChromTable::Get(const char *chrom) {
 }
 
 void RegionBatch::Clear() {
-  chrom.clear(); start.clear(); stop.clear(); strand.clear(); weight.clear(); label.clear(); line.clear();
+  chrom.clear(); start.clear(); stop.clear(); strand.clear(); weight.clear(); label.clear();
   offset.assign(1, 0);
+  first_line = 0;
   multi = false;
 }
 
@@ -225,19 +330,66 @@ bool SortChecker::Accept(const std::string &c, char s, long st) {
 // ---------------------------------------------------------------------------------------------
 // RegionReader
 // ---------------------------------------------------------------------------------------------
+// Chromosome names repeat: a thread remembers the ones it has met and asks the shared table only for new ones.
+struct RegionReader::ChromCache {
+  ChromTable *table;
+  std::string last;
+  int32_t last_id = -1;
+  std::unordered_map<std::string, int32_t> seen;
+  // names of up to 8 bytes (chr1 ... chrUn_x): the bytes themselves are the key of a small open-addressing table
+  static const int kSlots = 256;
+  uint64_t key[kSlots];
+  int32_t val[kSlots];
+  int used = 0;
+  explicit ChromCache(ChromTable *t) : table(t) { memset(key, 0, sizeof key); }
+  int32_t Get(const char *chrom) {
+    if (last_id >= 0 && strcmp(chrom, last.c_str()) == 0) return last_id;
+    last = chrom;
+    auto it = seen.find(last);
+    if (it != seen.end()) return last_id = it->second;
+    last_id = table->Get(chrom);
+    seen.emplace(last, last_id);
+    return last_id;
+  }
+  // name = [p, p + len), 1 <= len <= 8, not NUL-terminated
+  int32_t GetShort(const char *p, size_t len) {
+    uint64_t k = 0;
+    memcpy(&k, p, len);                                                // len < 8 leaves high zero bytes; a name holds no NUL, so keys are unique
+    uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 56);
+    for (;;) {
+      if (key[h] == k) return val[h];
+      if (key[h] == 0) break;
+      h = (h + 1) & (kSlots - 1);
+    }
+    char name[9];
+    memcpy(name, p, len);
+    name[len] = 0;
+    const int32_t id = table->Get(name);
+    if (used < kSlots / 2) { key[h] = k; val[h] = id; used++; }
+    return id;
+  }
+};
+
 RegionReader::RegionReader(const char *path, ChromTable *chroms, bool keep_labels, long max_label_value)
     : reader_(path), chroms_(chroms), keep_labels_(keep_labels), max_label_value_(max_label_value) {
+  const char *env = getenv("GT_PARSE_THREADS");
+  threads_ = env ? atoi(env) : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  if (threads_ < 1) threads_ = 1;
   // header skipping and format sniffing (genomic_intervals.cpp:3713-3759)
   char *next = reader_.Next();
   auto is_track = [](const char *s) { return strncmp(s, "browser ", 8) == 0 || strncmp(s, "track ", 6) == 0; };
-  if (next == nullptr) { format_ = "EMPTY"; return; }
+  auto settle = [&] {
+    fmt_ = format_ == "BED" ? F_BED : format_ == "REG" ? F_REG : format_ == "GFF" ? F_GFF : format_ == "SAM" ? F_SAM
+           : format_ == "SEQ" ? F_SEQ : format_ == "EMPTY" ? F_EMPTY : F_NONE;
+  };
+  if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
   if (is_track(next)) { while (next && is_track(next)) next = reader_.Next(); }
   else if (next[0] == '@') { format_ = "SAM"; while (next && next[0] == '@') next = reader_.Next(); }
   else if (next[0] == '#' && next[1] == '#') { format_ = "GFF"; while (next && next[0] == '#' && next[1] == '#') next = reader_.Next(); }
-  if (next == nullptr) { format_ = "EMPTY"; return; }
+  if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
   pending_ = next;
-  if (format_ != "") return;
-  if (next[0] == '>') { format_ = "SEQ"; return; }
+  if (format_ != "") { settle(); return; }
+  if (next[0] == '>') { format_ = "SEQ"; settle(); return; }
   const long n_tokens = CountTokens(next, '\t');
   if (n_tokens == 1) format_ = "BED";                                 // space-separated BED lands here
   if (n_tokens == 2) format_ = "REG";
@@ -250,34 +402,45 @@ RegionReader::RegionReader(const char *path, ChromTable *chroms, bool keep_label
     else if (n_tokens >= 11) format_ = "SAM";
     else if (n_tokens >= 8 && n_tokens <= 10) format_ = "GFF";
   }
+  settle();
 }
 
-void RegionReader::Push(RegionBatch *out, const char *chrom, char strand, long start, long stop, long line_no) {
+static bool LineError(ParseError *err, const char *msg) { err->with_line = true; err->raw = false; err->message = msg; return false; }
+static bool StrandError(ParseError *err, const char *token) {
+  err->with_line = false; err->raw = true; err->message = std::string("Error: invalid strand '") + token + "'!\n";
+  return false;
+}
+
+bool RegionReader::Push(RegionBatch *out, ChromCache *cache, const char *chrom, char strand, long start, long stop, ParseError *err) const {
   if (start < INT32_MIN || start > INT32_MAX || stop < INT32_MIN || stop > INT32_MAX)
-    die_line(line_no, "coordinate does not fit in 32 bits (not supported by the GPU engine)!");
-  out->chrom.push_back(chroms_->Get(chrom));
+    return LineError(err, "coordinate does not fit in 32 bits (not supported by the GPU engine)!");
+  out->chrom.push_back(cache->Get(chrom));
   out->strand.push_back((int8_t)strand);
   out->start.push_back((int32_t)start);
   out->stop.push_back((int32_t)stop);
+  return true;
 }
 
-void RegionReader::ParseLine(char *inp, long line_no, RegionBatch *out) {
-  std::string label;
+bool RegionReader::ParseLine(char *inp, RegionBatch *out, ChromCache *cache, ParseError *err) const {
+  const char *label = "_";
   const size_t first_interval = out->chrom.size();
-  if (format_ == "BED") {                                            // GenomicRegionBED::Read, genomic_intervals.cpp:2157-2182
+  if (fmt_ == F_BED) {                                               // GenomicRegionBED::Read, genomic_intervals.cpp:2157-2182
     const char sep = strchr(inp, '\t') == nullptr ? ' ' : '\t';
     const int n_tokens = CountTokens(inp, sep);
-    if (n_tokens < 3) die_line(line_no, "number of tokens should be at least 3 for BED format!");
+    if (n_tokens < 3) return LineError(err, "number of tokens should be at least 3 for BED format!");
     const char *chromosome = NextToken(&inp, sep);
-    const long start = atol(NextToken(&inp, sep)) + 1;
-    const long stop = atol(NextToken(&inp, sep));
+    const long start = FastAtol(NextToken(&inp, sep)) + 1;
+    const long stop = FastAtol(NextToken(&inp, sep));
     char strand = '+';
-    label = n_tokens == 3 ? "_" : NextToken(&inp, sep);
+    if (n_tokens != 3) label = NextToken(&inp, sep);
     if (n_tokens >= 5) NextToken(&inp, sep);                          // score
-    if (n_tokens >= 6) strand = ProcessStrand(NextToken(&inp, sep));
+    if (n_tokens >= 6) {
+      const char *t = NextToken(&inp, sep);
+      if ((strand = StrandOf(t)) == 0) return StrandError(err, t);
+    }
     if (n_tokens >= 8) { NextToken(&inp, sep); NextToken(&inp, sep); }  // thickStart, thickEnd
     if (n_tokens >= 9) NextToken(&inp, sep);                          // itemRgb
-    if (n_tokens != 12) Push(out, chromosome, strand, start, stop, line_no);
+    if (n_tokens != 12) { if (!Push(out, cache, chromosome, strand, start, stop, err)) return false; }
     else {
       const long n_intervals = atol(NextToken(&inp, sep));
       char *sizes = NextToken(&inp, sep);
@@ -287,75 +450,271 @@ void RegionReader::ParseLine(char *inp, long line_no, RegionBatch *out) {
       for (long k = 0; k < n_intervals; k++) bstart[k] = atol(NextToken(&starts, ','));
       for (long k = 0; k < n_intervals; k++) {
         const long s = start + bstart[k];
-        Push(out, chromosome, strand, s, bsize[k] + s - 1, line_no);
+        if (!Push(out, cache, chromosome, strand, s, bsize[k] + s - 1, err)) return false;
       }
     }
-  } else if (format_ == "REG") {                                     // GenomicRegion::Read, genomic_intervals.cpp:805-838
+  } else if (fmt_ == F_REG) {                                        // GenomicRegion::Read, genomic_intervals.cpp:805-838
     label = NextToken(&inp, '\t');
     if (strchr(inp, ',') == nullptr) {
       const int n_tokens = CountTokens(inp, ' ');
-      if (n_tokens < 4 || n_tokens % 4 != 0) die_line(line_no, "invalid number of tokens!");
+      if (n_tokens < 4 || n_tokens % 4 != 0) return LineError(err, "invalid number of tokens!");
       for (int k = 0; k < n_tokens / 4; k++) {
         const char *chromosome = NextToken(&inp, ' ');
-        const char strand = ProcessStrand(NextToken(&inp, ' '));
-        const long start = atol(NextToken(&inp, ' '));
-        const long stop = atol(NextToken(&inp, ' '));
-        Push(out, chromosome, strand, start, stop, line_no);
+        const char *t = NextToken(&inp, ' ');
+        const char strand = StrandOf(t);
+        if (strand == 0) return StrandError(err, t);
+        const long start = FastAtol(NextToken(&inp, ' '));
+        const long stop = FastAtol(NextToken(&inp, ' '));
+        if (!Push(out, cache, chromosome, strand, start, stop, err)) return false;
       }
     } else {
-      if (CountTokens(inp, ' ') != 4) die_line(line_no, "invalid number of tokens in compact format!");
+      if (CountTokens(inp, ' ') != 4) return LineError(err, "invalid number of tokens in compact format!");
       const char *chromosome = NextToken(&inp, ' ');
-      const char strand = ProcessStrand(NextToken(&inp, ' '));
+      const char *t = NextToken(&inp, ' ');
+      const char strand = StrandOf(t);
+      if (strand == 0) return StrandError(err, t);
       char *starts = NextToken(&inp, ' ');
       char *stops = NextToken(&inp, ' ');
       const int n_intervals = CountTokens(starts, ',');
-      if (CountTokens(stops, ',') != n_intervals) die_line(line_no, "number of starts/stops should be equal");
+      if (CountTokens(stops, ',') != n_intervals) return LineError(err, "number of starts/stops should be equal");
       for (int k = 0; k < n_intervals; k++) {
         const long start = atol(NextToken(&starts, ','));
         const long stop = atol(NextToken(&stops, ','));
-        Push(out, chromosome, strand, start, stop, line_no);
+        if (!Push(out, cache, chromosome, strand, start, stop, err)) return false;
       }
     }
-  } else if (format_ == "GFF") {                                     // GenomicRegionGFF::Read, genomic_intervals.cpp:3501-3517
+  } else if (fmt_ == F_GFF) {                                        // GenomicRegionGFF::Read, genomic_intervals.cpp:3501-3517
     const int n_tokens = CountTokens(inp, '\t');
-    if (n_tokens < 8 || n_tokens > 10) die_line(line_no, "wrong number of tokens for GFF format!");
+    if (n_tokens < 8 || n_tokens > 10) return LineError(err, "wrong number of tokens for GFF format!");
     const char *seqname = NextToken(&inp, '\t');
     NextToken(&inp, '\t'); NextToken(&inp, '\t');                      // source, feature
-    const long start = atol(NextToken(&inp, '\t'));
-    const long end = atol(NextToken(&inp, '\t'));
+    const long start = FastAtol(NextToken(&inp, '\t'));
+    const long end = FastAtol(NextToken(&inp, '\t'));
     NextToken(&inp, '\t');                                             // score
     const char strand = NextToken(&inp, '\t')[0];                      // raw character, NOT normalised (:3512)
     NextToken(&inp, '\t');                                             // frame
-    label = n_tokens == 8 ? "_" : NextToken(&inp, '\t');
-    Push(out, seqname, strand, start, end, line_no);
-  } else if (format_ == "SAM" || format_ == "SEQ") {
-    die("input format " + format_ + " is not supported by this build (BED, REG and GFF are)!\n");
+    if (n_tokens != 8) label = NextToken(&inp, '\t');
+    if (!Push(out, cache, seqname, strand, start, end, err)) return false;
+  } else if (fmt_ == F_SAM || fmt_ == F_SEQ) {
+    err->with_line = false; err->raw = false;
+    err->message = "input format " + format_ + " is not supported by this build (BED, REG and GFF are)!\n";
+    return false;
   } else {
-    die("unsupported input format!\n");
+    err->with_line = false; err->raw = false; err->message = "unsupported input format!\n";
+    return false;
+  }
+  if (max_label_value_ > 1) {                                          // GetLabelValue, genomic_intervals.cpp:1081-1085
+    const long w = std::min(max_label_value_, atol(label));
+    if (w < INT32_MIN || w > INT32_MAX) return LineError(err, "label value does not fit in 32 bits (not supported by the GPU engine)!");
+    out->weight.push_back((int32_t)w);
   }
   if (out->chrom.size() - first_interval != 1) out->multi = true;
   out->offset.push_back((int64_t)out->chrom.size());
-  out->line.push_back(line_no);
-  if (keep_labels_) out->label.push_back(label);
+  if (keep_labels_) out->label.emplace_back(label);
+  return true;
+}
+
+// The common case by far -- TAB-separated BED of 3 to 6 clean columns -- in one pass over the line and without writing
+// to it.  "Clean": every column non-empty and not starting with a blank, start and stop plain digit strings of at most 18
+// digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  nl = the line's '\n'.
+bool RegionReader::ParseBedLine(char *line, char *nl, RegionBatch *out, ChromCache *cache) const {
+  const char *p = line;
+  if (*p == ' ' || *p == '\t') return false;
+  while (*p != '\t' && *p != '\n') p++;
+  const size_t chrom_len = (size_t)(p - line);
+  if (*p != '\t' || chrom_len == 0 || chrom_len > 8) return false;
+  p++;
+  unsigned long start = 0, stop = 0;
+  const char *d = p;
+  while ((unsigned)(*p - '0') < 10u) start = start * 10 + (unsigned)(*p++ - '0');
+  if (p == d || p - d > 18 || *p != '\t') return false;
+  d = ++p;
+  while ((unsigned)(*p - '0') < 10u) stop = stop * 10 + (unsigned)(*p++ - '0');
+  if (p == d || p - d > 18) return false;
+  char strand = '+';
+  const char *label = nullptr, *label_end = nullptr;
+  if (*p == '\t') {                                                     // column 4: label
+    label = ++p;
+    if (*p == ' ' || *p == '\t' || *p == '\n') return false;
+    while (*p != '\t' && *p != '\n') p++;
+    label_end = p;
+    if (*p == '\t') {                                                   // column 5: score
+      p++;
+      if (*p == ' ' || *p == '\t' || *p == '\n') return false;
+      while (*p != '\t' && *p != '\n') p++;
+      if (*p == '\t') {                                                 // column 6: strand, then the end of the line
+        p++;
+        if (p[1] == '\n') {
+          if (p[0] == '+' || p[0] == '.' || p[0] == '1') strand = '+';
+          else if (p[0] == '-') strand = '-';
+          else return false;
+        } else if (p[0] == '-' && p[1] == '1' && p[2] == '\n') strand = '-';
+        else return false;
+      }
+    }
+  } else if (*p != '\n') return false;
+  start += 1;
+  if (start > (unsigned long)INT32_MAX || stop > (unsigned long)INT32_MAX) return false;
   if (max_label_value_ > 1) {                                          // GetLabelValue, genomic_intervals.cpp:1081-1085
-    const long w = std::min(max_label_value_, atol(label.c_str()));
-    if (w < INT32_MIN || w > INT32_MAX) die_line(line_no, "label value does not fit in 32 bits (not supported by the GPU engine)!");
+    long w = 0;
+    if (label != nullptr) {
+      char tmp[32];
+      const size_t n = std::min<size_t>((size_t)(label_end - label), sizeof tmp - 1);
+      if ((size_t)(label_end - label) > sizeof tmp - 1) return false;
+      memcpy(tmp, label, n);
+      tmp[n] = 0;
+      w = atol(tmp);
+    }
+    w = std::min(max_label_value_, w);
+    if (w < INT32_MIN || w > INT32_MAX) return false;
     out->weight.push_back((int32_t)w);
   }
+  out->chrom.push_back(cache->GetShort(line, chrom_len));
+  out->strand.push_back((int8_t)strand);
+  out->start.push_back((int32_t)start);
+  out->stop.push_back((int32_t)stop);
+  out->offset.push_back((int64_t)out->chrom.size());
+  if (keep_labels_) { if (label) out->label.emplace_back(label, label_end); else out->label.emplace_back("_"); }
+  return true;
+}
+
+struct RegionReader::Piece {
+  char *lo = nullptr, *hi = nullptr;
+  RegionBatch batch;
+  long lines = 0;                                                      // lines consumed, the malformed one (if any) not included
+  bool bad = false;
+  ParseError err;
+  int64_t region_at = 0, interval_at = 0;                              // where this piece's regions / intervals go in the joined batch
+};
+
+RegionReader::~RegionReader() {
+  for (Piece *p : piece_) delete p;
+}
+
+// Parses the lines of [begin, end) -- each terminated by '\n' -- and appends their regions to out.  The run is cut into
+// pieces at line boundaries, one per thread; each thread fills a batch of its own, then copies it to its place in `out`.
+bool RegionReader::ParseRun(char *begin, char *end, RegionBatch *out) {
+  const size_t bytes = (size_t)(end - begin);
+  static const size_t piece_bytes = getenv("GT_PARSE_PIECE_BYTES") ? (size_t)std::max(1L, atol(getenv("GT_PARSE_PIECE_BYTES"))) : (1u << 18);
+  const int pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, bytes / piece_bytes));
+  while ((int)piece_.size() < pieces) piece_.push_back(new Piece());
+  char *at = begin;
+  for (int i = 0; i < pieces; i++) {
+    Piece &pc = *piece_[i];
+    pc.lo = at;
+    char *want = i + 1 == pieces ? end : begin + bytes * (size_t)(i + 1) / (size_t)pieces;
+    if (want < at) want = at;
+    if (want < end && want > begin && want[-1] != '\n') {
+      char *nl = (char *)memchr(want, '\n', (size_t)(end - want));
+      want = nl ? nl + 1 : end;
+    }
+    pc.hi = at = want;
+    pc.lines = 0; pc.bad = false;
+  }
+  const bool bed = fmt_ == F_BED;
+  auto parse = [&](int i) {
+    Piece &pc = *piece_[i];
+    RegionBatch *dst = &pc.batch;
+    ChromCache cache(chroms_);
+    dst->Clear();
+    const size_t guess = (size_t)(pc.hi - pc.lo) / 24 + 16;            // avoids most reallocations the first time round
+    dst->chrom.reserve(guess); dst->start.reserve(guess); dst->stop.reserve(guess); dst->strand.reserve(guess); dst->offset.reserve(guess + 1);
+    for (char *p = pc.lo; p < pc.hi;) {
+      char *nl = (char *)memchr(p, '\n', (size_t)(pc.hi - p));
+      if (!(bed && ParseBedLine(p, nl, dst, &cache))) {
+        *nl = 0;
+        if (!ParseLine(p, dst, &cache, &pc.err)) { pc.bad = true; break; }
+      }
+      pc.lines++;
+      p = nl + 1;
+    }
+    if (pc.bad) {                                                      // drop what the malformed line left behind: whole regions only
+      const size_t keep = (size_t)dst->offset.back();
+      dst->chrom.resize(keep); dst->start.resize(keep); dst->stop.resize(keep); dst->strand.resize(keep);
+      dst->weight.resize(max_label_value_ > 1 ? dst->offset.size() - 1 : 0);
+      if (keep_labels_) dst->label.resize(dst->offset.size() - 1);
+    }
+  };
+  auto join = [&](int i) {                                             // this piece's batch to its place in out
+    const Piece &pc = *piece_[i];
+    const RegionBatch &b = pc.batch;
+    const size_t ni = b.chrom.size(), nr = (size_t)b.n_regions();
+    memcpy(out->chrom.data() + pc.interval_at, b.chrom.data(), ni * sizeof(int32_t));
+    memcpy(out->start.data() + pc.interval_at, b.start.data(), ni * sizeof(int32_t));
+    memcpy(out->stop.data() + pc.interval_at, b.stop.data(), ni * sizeof(int32_t));
+    memcpy(out->strand.data() + pc.interval_at, b.strand.data(), ni);
+    if (!b.weight.empty()) memcpy(out->weight.data() + pc.region_at, b.weight.data(), nr * sizeof(int32_t));
+    int64_t *off = out->offset.data() + pc.region_at + 1;
+    for (size_t k = 1; k <= nr; k++) off[k - 1] = pc.interval_at + b.offset[k];
+  };
+  auto run_all = [&](int n, const std::function<void(int)> &fn) {
+    if (n == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; i++) th.emplace_back(fn, i);
+    fn(0);
+    for (auto &t : th) t.join();
+  };
+  run_all(pieces, parse);
+  // pieces up to and including the first one that met a malformed line
+  int used = pieces;
+  for (int i = 0; i < pieces; i++) if (piece_[i]->bad) { used = i + 1; break; }
+  int64_t regions = out->n_regions(), intervals = (int64_t)out->chrom.size();
+  long lines = 0;
+  for (int i = 0; i < used; i++) {
+    Piece &pc = *piece_[i];
+    pc.region_at = regions; pc.interval_at = intervals;
+    regions += pc.batch.n_regions(); intervals += (int64_t)pc.batch.chrom.size();
+    lines += pc.lines;
+    out->multi = out->multi || pc.batch.multi;
+  }
+  out->chrom.resize((size_t)intervals); out->start.resize((size_t)intervals); out->stop.resize((size_t)intervals);
+  out->strand.resize((size_t)intervals); out->offset.resize((size_t)regions + 1);
+  if (max_label_value_ > 1) out->weight.resize((size_t)regions);
+  run_all(used, join);
+  if (keep_labels_)
+    for (int i = 0; i < used; i++)
+      for (auto &l : piece_[i]->batch.label) out->label.emplace_back(std::move(l));
+  if (used > 0 && piece_[used - 1]->bad) {
+    failed_ = true;
+    error_ = piece_[used - 1]->err;
+    error_.line = reader_.line_no() + lines + 1;
+    reader_.Advance(lines + 1);
+    return false;
+  }
+  reader_.Advance(lines);
+  return true;
 }
 
 int64_t RegionReader::Read(RegionBatch *out, int64_t max_regions) {
   out->Clear();
-  if (format_ == "EMPTY") return 0;
-  int64_t n = 0;
-  while (n < max_regions) {
-    char *line = pending_ ? pending_ : reader_.Next();
+  if (fmt_ == F_EMPTY || failed_) return 0;
+  if (pending_) {
+    out->first_line = reader_.line_no();
+    ChromCache cache(chroms_);
+    char *line = pending_;
     pending_ = nullptr;
-    if (line == nullptr) break;
-    ParseLine(line, reader_.line_no(), out);
-    n++;
+    if (!ParseLine(line, out, &cache, &error_)) {
+      failed_ = true;
+      error_.line = reader_.line_no();
+      const size_t keep = (size_t)out->offset.back();
+      out->chrom.resize(keep); out->start.resize(keep); out->stop.resize(keep); out->strand.resize(keep);
+      return out->n_regions();
+    }
+  } else {
+    out->first_line = reader_.line_no() + 1;
   }
-  return n;
+  while (out->n_regions() < max_regions) {
+    char *begin, *end;
+    if (!reader_.NextRun(&begin, &end)) break;
+    if (!ParseRun(begin, end, out)) break;
+  }
+  return out->n_regions();
+}
+
+void RegionReader::Fail() const {
+  if (error_.raw) { std::cerr << error_.message; exit(1); }
+  if (error_.with_line) die_line(error_.line, error_.message);
+  die(error_.message);
 }
 
 }  // namespace gt

@@ -10,9 +10,13 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <zlib.h>
 #include <map>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -67,14 +71,29 @@ class LineReader {
   // '\n' is dropped, exactly as the reference does.  The pointer is valid until the next call.
   char *Next();
   long line_no() const { return line_no_; }         // 1-based number of the line last returned
+  // The rest of the current block, or the next one: complete lines, each still terminated by '\n', in [*begin, *end);
+  // false at end.  The pointers are valid until the next call.  The caller counts the lines and reports them with Advance.
+  bool NextRun(char **begin, char **end);
+  void Advance(long n_lines) { line_no_ += n_lines; }
 
  private:
-  bool Fill();
+  // A producer thread reads (and inflates) the file into a ring of blocks that end on a line boundary while the consumer
+  // parses the previous block.
+  struct Block { char *data = nullptr; size_t cap = 0, len = 0; };
+  static const int kBlocks = 3;
+  void Produce();
+  long ReadSome(char *dst, size_t want);
+  bool Acquire();                                     // make the next block current; false at end
   gzFile gz_ = nullptr;
-  FILE *fp_ = nullptr;
-  std::vector<char> buf_;
-  size_t begin_ = 0, end_ = 0;
-  bool eof_ = false;
+  int fd_ = -1;
+  Block block_[kBlocks];
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int ready_ = 0, head_ = 0;                          // filled blocks not yet released (the current one included); next block to hand out
+  bool done_ = false, quit_ = false;
+  std::thread producer_;
+  int cur_ = -1;                                      // block the consumer holds
+  size_t pos_ = 0;                                    // first unread byte of it
   long line_no_ = 0;
 };
 
@@ -84,37 +103,99 @@ class LineReader {
 struct ChromTable {
   std::unordered_map<std::string, int32_t> id;
   std::vector<std::string> name;
-  int32_t Get(const char *chrom);
+  int32_t Get(const char *chrom);                     // thread-safe
+ private:
+  std::mutex mu_;
+};
+
+// Growable array of a plain type that does not initialise what it grows by (the parser fills it from several threads).
+template <typename T>
+class PodVec {
+ public:
+  PodVec() = default;
+  PodVec(const PodVec &) = delete;
+  PodVec &operator=(const PodVec &) = delete;
+  ~PodVec() { free(p_); }
+  T *data() { return p_; }
+  const T *data() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  T &operator[](size_t i) { return p_[i]; }
+  const T &operator[](size_t i) const { return p_[i]; }
+  T &back() { return p_[n_ - 1]; }
+  const T &back() const { return p_[n_ - 1]; }
+  void clear() { n_ = 0; }
+  void reserve(size_t n) { if (n > cap_) Grow(n); }
+  void resize(size_t n) { reserve(n); n_ = n; }      // new elements are NOT initialised
+  void push_back(T v) { if (n_ == cap_) Grow(cap_ ? cap_ * 2 : 1024); p_[n_++] = v; }
+  void assign(size_t n, T v) { resize(n); for (size_t i = 0; i < n; i++) p_[i] = v; }
+ private:
+  void Grow(size_t cap) {
+    p_ = (T *)realloc(p_, cap * sizeof(T));
+    if (p_ == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
+    cap_ = cap;
+  }
+  T *p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
 };
 
 struct RegionBatch {                                  // packed SoA, regions in file order
-  std::vector<int32_t> chrom, start, stop;
-  std::vector<int8_t> strand;
-  std::vector<int32_t> weight;                        // per region (only if weights are in use)
-  std::vector<int64_t> offset;                        // per region + 1; maintained always, passed on only if some region is multi-interval
+  PodVec<int32_t> chrom, start, stop;
+  PodVec<int8_t> strand;
+  PodVec<int32_t> weight;                             // per region (only if weights are in use)
+  PodVec<int64_t> offset;                             // per region + 1; maintained always, passed on only if some region is multi-interval
   std::vector<std::string> label;                     // per region (only if keep_labels)
-  std::vector<long> line;                             // per region: source line number
+  long first_line = 0;                                // source line of region 0; every data line is one region, so region k is on first_line + k
   bool multi = false;
   int64_t n_regions() const { return (int64_t)offset.size() - 1; }
+  long line(int64_t k) const { return first_line + (long)k; }
   void Clear();
+};
+
+// A fatal condition found while parsing.  Lines are parsed by several threads at once; the one that comes first in the file
+// is the one reported, exactly as the reference's sequential reader would.
+struct ParseError {
+  bool with_line = false;
+  long line = 0;
+  std::string message;                                // printed as die_line / die would
+  bool raw = false;                                   // message goes to stderr as is (ProcessStrand's wording)
 };
 
 class RegionReader {
  public:
   RegionReader(const char *path, ChromTable *chroms, bool keep_labels, long max_label_value);
   const std::string &format() const { return format_; }
-  // parses up to max_regions regions into `out` (cleared first); returns the number parsed (0 at end)
+  // Parses regions into `out` (cleared first) until it holds at least max_regions of them or the input ends; returns the
+  // number parsed (0 at end).  Lines are parsed by several threads.  A malformed line ends the stream: the regions before it
+  // are returned, failed() turns true and Fail() reports it -- so that a caller that streams can first report what an
+  // earlier line did wrong further down the pipeline, as the reference's line-by-line loop would.
   int64_t Read(RegionBatch *out, int64_t max_regions);
-  // sortedness check state for -S (IsBefore, genomic_intervals.cpp:396-401): call per region in order
+  bool failed() const { return failed_; }
+  [[noreturn]] void Fail() const;                     // prints the parse error the way the reference does, exit(1)
+  // Read, then Fail() at once if a line was malformed (sets that are loaded whole)
+  int64_t ReadAll(RegionBatch *out) { const int64_t n = Read(out, INT64_MAX); if (failed_) Fail(); return n; }
  private:
-  void ParseLine(char *line, long line_no, RegionBatch *out);
-  void Push(RegionBatch *out, const char *chrom, char strand, long start, long stop, long line_no);
+  enum Format { F_NONE, F_BED, F_REG, F_GFF, F_SAM, F_SEQ, F_EMPTY };
+  struct ChromCache;                                  // per-thread view of the chromosome table
+  struct Piece;                                       // one thread's share of a run
+  bool ParseLine(char *line, RegionBatch *out, ChromCache *cache, ParseError *err) const;
+  bool Push(RegionBatch *out, ChromCache *cache, const char *chrom, char strand, long start, long stop, ParseError *err) const;
+  // lines of [begin, end), over the parsing threads, appended to out; false on a malformed line (error_ set)
+  bool ParseRun(char *begin, char *end, RegionBatch *out);
+  bool ParseBedLine(char *line, char *nl, RegionBatch *out, ChromCache *cache) const;   // clean BED3-6 only; false = not handled
   LineReader reader_;
   ChromTable *chroms_;
   bool keep_labels_;
   long max_label_value_;
-  std::string format_;                                // BED REG GFF SAM EMPTY ""
+  std::string format_;                                // BED REG GFF SAM SEQ EMPTY ""
+  Format fmt_ = F_NONE;
+  int threads_ = 1;                                   // GT_PARSE_THREADS, default: the host's cores (at most 32)
   char *pending_ = nullptr;                           // first data line, already read during format detection
+  bool failed_ = false;
+  ParseError error_;
+  std::vector<Piece *> piece_;                        // kept between runs: their batches' memory is reused
+ public:
+  ~RegionReader();
 };
 
 char ProcessStrand(const char *token);                // '1','+' -> '+'; '-1','-' -> '-'; '.' -> '+'; else fatal  (genomic_intervals.cpp:5956-5962)

@@ -1,0 +1,55 @@
+// gt_regdump -- prints what the host parser (gt_host.h) makes of a region file, in the reference's REG spelling
+// (`genomic_regions reg`, genomic_intervals.cpp:880-890: LABEL <TAB> chrom strand start stop [chrom strand start stop ...]).
+// Needs no GPU: the tests use it to hold the multi-threaded parser against the reference's own reader on a CPU-only box, and
+// it doubles as a parse-rate probe (-q: parse only, print the number of regions and intervals).
+//
+//   gt_regdump [-q] [-w MAX_LABEL_VALUE] [-c CHUNK_REGIONS] FILE|-
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "../gt_host.h"
+
+int main(int argc, char **argv) {
+  bool quiet = false;
+  long max_label_value = 1;
+  int64_t chunk = INT64_MAX;
+  int a = 1;
+  for (; a < argc && argv[a][0] == '-' && argv[a][1] != 0; a++) {
+    if (!strcmp(argv[a], "-q")) quiet = true;
+    else if (!strcmp(argv[a], "-w") && a + 1 < argc) max_label_value = atol(argv[++a]);
+    else if (!strcmp(argv[a], "-c") && a + 1 < argc) chunk = atol(argv[++a]);
+    else { fprintf(stderr, "usage: gt_regdump [-q] [-w MAX_LABEL_VALUE] [-c CHUNK_REGIONS] FILE|-\n"); return 2; }
+  }
+  if (a >= argc) { fprintf(stderr, "usage: gt_regdump [-q] [-w MAX_LABEL_VALUE] [-c CHUNK_REGIONS] FILE|-\n"); return 2; }
+  const char *path = strcmp(argv[a], "-") == 0 ? nullptr : argv[a];
+  gt::ChromTable chroms;
+  gt::RegionReader rr(path, &chroms, !quiet, max_label_value);
+  gt::RegionBatch b;
+  int64_t regions = 0, intervals = 0;
+  std::string text;
+  while (rr.Read(&b, chunk) > 0) {
+    regions += b.n_regions();
+    intervals += (int64_t)b.chrom.size();
+    if (quiet) continue;
+    text.clear();
+    char num[64];
+    for (int64_t k = 0; k < b.n_regions(); k++) {
+      text += b.label[k];
+      text += '\t';
+      for (int64_t i = b.offset[k]; i < b.offset[k + 1]; i++) {
+        if (i > b.offset[k]) text += ' ';
+        text += chroms.name[b.chrom[i]];
+        snprintf(num, sizeof num, " %c %d %d", (char)b.strand[i], b.start[i], b.stop[i]);
+        text += num;
+      }
+      if (max_label_value > 1) { snprintf(num, sizeof num, "\tw=%d", b.weight[k]); text += num; }
+      snprintf(num, sizeof num, "\t#%ld\n", b.line(k));
+      text += num;
+    }
+    fwrite(text.data(), 1, text.size(), stdout);
+  }
+  fflush(stdout);
+  if (rr.failed()) rr.Fail();
+  if (quiet) printf("format %s regions %ld intervals %ld\n", rr.format().c_str(), (long)regions, (long)intervals);
+  return 0;
+}

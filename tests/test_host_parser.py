@@ -1,0 +1,217 @@
+"""The host reader of the drop-in drivers (host/gt_host.cpp: producer-thread line reader + multi-threaded BED/REG/GFF
+parsers) against the reference's own reader, on a CPU-only box: `bin/gt_regdump FILE` prints what our parser makes
+of a file in REG spelling, `oracle/_ref/genomic_regions reg FILE` does the same through the reference's
+GenomicRegionSet (genomic_intervals.cpp:3667-3914).  Run with 1 and several parsing threads and with pieces of a
+few hundred bytes, so that every line boundary is a piece boundary somewhere."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import support
+
+BIN = os.path.join(support.ROOT, "ibm-cbc-genomic-tools_b200", "bin")
+DUMP = os.path.join(BIN, "gt_regdump")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(DUMP), reason="bin/gt_regdump not built")
+
+THREADINGS = [{"GT_PARSE_THREADS": "1"}, {"GT_PARSE_THREADS": "5", "GT_PARSE_PIECE_BYTES": "300"}]
+
+
+def dump(path, env_extra, args=(), stdin=None):
+    env = dict(os.environ, **env_extra)
+    p = subprocess.run([DUMP] + list(args) + [str(path)], input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    return p.returncode, p.stdout, p.stderr
+
+
+def strip_extras(out):
+    """gt_regdump appends `\\tw=..` (with -w) and `\\t#line`; the reference prints label and intervals only"""
+    return b"".join(b"\t".join(l.split(b"\t")[:2]) + b"\n" for l in out.splitlines())
+
+
+def ref_reg(path, stdin=None):
+    if not support.have_ref():
+        pytest.skip("reference binaries not built (oracle/_ref)")
+    return support.run_ref("genomic_regions", ["reg", str(path)], stdin=stdin, check=False)
+
+
+def rand_lines(rng, n, kind):
+    names = ["chr1", "chr10", "chr2", "chrX", "chrUn_gl000220", "scaffold_12345678"]
+    out = []
+    for k in range(n):
+        c = names[rng.integers(len(names))]
+        s = int(rng.integers(0, 5_000_000))
+        e = s + int(rng.integers(1, 3000))
+        strand = "+-"[rng.integers(2)]
+        lab = "L%d" % k if rng.integers(4) else str(int(rng.integers(-3, 40)))
+        if kind == "bed3":
+            out.append(f"{c}\t{s}\t{e}")
+        elif kind == "bed4":
+            out.append(f"{c}\t{s}\t{e}\t{lab}")
+        elif kind == "bed5":
+            out.append(f"{c}\t{s}\t{e}\t{lab}\t0")
+        elif kind == "bed6":
+            st = [strand, strand, ".", "1", "-1"][rng.integers(5)]
+            out.append(f"{c}\t{s}\t{e}\t{lab}\t{rng.integers(1000)}\t{st}")
+        elif kind == "bed6_space":
+            out.append(f"{c} {s} {e} {lab} 0 {strand}")
+        elif kind == "bed_mixed":                                       # column count varies line by line; BED12 blocks among them
+            if rng.integers(3) == 0:
+                nb = int(rng.integers(1, 5))
+                sizes = [int(rng.integers(1, 50)) for _ in range(nb)]
+                starts = [i * 100 for i in range(nb)]
+                out.append("\t".join([c, str(s), str(s + starts[-1] + sizes[-1]), lab, "0", strand, str(s), str(e), "0", str(nb),
+                                      ",".join(map(str, sizes)), ",".join(map(str, starts))]))
+            else:
+                cols = [c, str(s), str(e), lab, "0", strand, str(s), str(e), "0"][:int(rng.integers(3, 10))]
+                if len(cols) == 7:
+                    cols = cols[:6]
+                out.append("\t".join(cols))
+        elif kind == "bed_odd":                                         # things the one-pass path must hand to the general one
+            pick = rng.integers(6)
+            if pick == 0:
+                out.append(f"{c}\t {s}\t{e}\t{lab}\t0\t{strand}")       # blank before a number
+            elif pick == 1:
+                out.append(f"{c}\t{s}x\t{e}abc\t{lab}\t0\t{strand}")    # atol stops at the first non-digit
+            elif pick == 2:
+                out.append(f"{c}\t{s}\t{e}\t my label\t0\t{strand}")    # leading blank in the label is skipped
+            elif pick == 3:
+                out.append(f"{c}\t-{s}\t{e}\t{lab}\t0\t{strand}")       # negative start
+            elif pick == 4:
+                out.append(f"{c}\t{s}\t{e}\t{lab}\t0\t{strand}\r")      # CR before the newline: 6th column is '+\r'?  (fatal or not: same as reference)
+            else:
+                out.append(f"{c}\t{s}\t{e}\t{lab}\t\t{strand}")         # empty score column
+        elif kind == "reg":
+            nb = int(rng.integers(1, 4))
+            iv = " ".join(f"{c} {strand} {s + 500 * i + 1} {s + 500 * i + 100}" for i in range(nb))
+            out.append(f"{lab}\t{iv}")
+        elif kind == "reg_compact":
+            nb = int(rng.integers(1, 4))
+            out.append(f"{lab}\t{c} {strand} " + ",".join(str(s + 500 * i + 1) for i in range(nb)) + " " + ",".join(str(s + 500 * i + 100) for i in range(nb)))
+        elif kind == "gff":
+            st = [strand, "."][rng.integers(2)]
+            cols = [c, "src", "feat", str(s + 1), str(e), ".", st, ".", lab][:int(rng.integers(8, 10))]
+            out.append("\t".join(cols))
+    return out
+
+
+KINDS = ["bed3", "bed4", "bed5", "bed6", "bed6_space", "bed_mixed", "reg", "reg_compact", "gff"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
+def test_parser_matches_reference_reader(tmp_path, kind, env):
+    rng = np.random.default_rng(abs(hash(kind)) % 1000 + 7)
+    lines = rand_lines(rng, 3000, kind)
+    path = tmp_path / ("in." + kind)
+    path.write_text("\n".join(lines) + "\n")
+    want = ref_reg(path)
+    got = dump(path, env)
+    assert want[0] == 0 and got[0] == 0, (want[2][-200:], got[2][-200:])
+    assert strip_extras(got[1]) == want[1]
+    # line numbers: region k is on line k + 1
+    nums = [int(l.rsplit(b"#", 1)[1]) for l in got[1].splitlines()]
+    assert nums == list(range(1, len(lines) + 1))
+
+
+@pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
+def test_odd_bed_lines_one_by_one(tmp_path, env):
+    """each odd line alone after a few clean ones: same regions, or the same fatal message and exit code"""
+    rng = np.random.default_rng(5)
+    clean = rand_lines(rng, 40, "bed6")
+    for k, odd in enumerate(rand_lines(rng, 60, "bed_odd")):
+        path = tmp_path / f"odd{k}.bed"
+        path.write_text("\n".join(clean[:20] + [odd] + clean[20:]) + "\n")
+        want = ref_reg(path)
+        got = dump(path, env)
+        assert got[0] == want[0], (odd, got[2], want[2])
+        if want[0] == 0:
+            assert strip_extras(got[1]) == want[1], odd
+        else:
+            assert got[2] == want[2], odd
+
+
+@pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
+def test_headers_gzip_stdin_and_unterminated_last_line(tmp_path, env):
+    rng = np.random.default_rng(11)
+    body = rand_lines(rng, 500, "bed6")
+    text = "track name=x\nbrowser position chr1\n" + "\n".join(body) + "\nchr1\t5\t9\tdropped\t0\t+"      # no final newline
+    path = tmp_path / "h.bed"
+    path.write_text(text)
+    want = ref_reg(path)
+    got = dump(path, env)
+    assert got[0] == 0 and strip_extras(got[1]) == want[1]
+    assert b"dropped" not in got[1]
+    first = got[1].splitlines()[0]
+    assert first.endswith(b"#3")                                         # two header lines come first
+    with gzip.open(str(path) + ".gz", "wb") as g:
+        g.write(text.encode())
+    got_gz = dump(str(path) + ".gz", env)
+    assert got_gz[1] == got[1]
+    got_in = dump("-", env, stdin=text.encode())
+    assert got_in[1] == got[1]
+    gff = "##gff-version 3\n##x\n" + "\n".join(rand_lines(rng, 50, "gff")) + "\n"
+    p2 = tmp_path / "h.gff"
+    p2.write_text(gff)
+    assert strip_extras(dump(p2, env)[1]) == ref_reg(p2)[1]
+    empty = tmp_path / "empty.bed"
+    empty.write_text("")
+    assert dump(empty, env)[:2] == (0, b"")
+
+
+@pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
+@pytest.mark.parametrize("bad,kind", [("chr1\t5", "bed6"), ("chr1\t5\t9\tx\t0\t*", "bed6"), ("lab\tchr1 + 5", "reg"),
+                                      ("lab\tchr1 + 1,2 5", "reg_compact"), ("chr1\ta\tb\t1\t2\t.\t+", "gff")])
+def test_first_malformed_line_wins(tmp_path, env, bad, kind):
+    """several malformed lines, parsed by different threads: the earliest is reported, with the reference's words;
+    the regions before it are still delivered (the drivers feed them to the engine before failing)"""
+    rng = np.random.default_rng(3)
+    lines = rand_lines(rng, 900, kind)
+    lines[400] = bad
+    lines[650] = bad
+    lines[880] = bad
+    path = tmp_path / "bad.txt"
+    path.write_text("\n".join(lines) + "\n")
+    want = ref_reg(path)
+    got = dump(path, env)
+    assert want[0] != 0 and got[0] == want[0]
+    assert got[2] == want[2]
+    assert len(got[1].splitlines()) == 400
+
+
+@pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
+def test_label_weights_and_chunked_reads(tmp_path, env):
+    rng = np.random.default_rng(17)
+    lines = rand_lines(rng, 2000, "bed6")
+    path = tmp_path / "w.bed"
+    path.write_text("\n".join(lines) + "\n")
+    whole = dump(path, env, args=["-w", "25"])
+    chunked = dump(path, dict(env, GT_PARSE_PIECE_BYTES="200"), args=["-w", "25", "-c", "100"])
+    assert whole[0] == 0 and whole[1] == chunked[1]
+    for l, src in zip(whole[1].splitlines(), lines):
+        lab = src.split("\t")[3]
+        try:
+            v = int(lab)
+        except ValueError:
+            v = 0                                                        # atol of a non-number
+        assert l.split(b"\t")[2] == b"w=%d" % min(25, v)                 # GetLabelValue, genomic_intervals.cpp:1081-1085
+
+
+def test_thread_counts_agree_on_a_large_file(tmp_path):
+    synth = os.path.join(BIN, "gt_synth_bed")
+    if not os.path.exists(synth):
+        pytest.skip("bin/gt_synth_bed not built")
+    path = tmp_path / "reads.bed"
+    with open(path, "wb") as f:
+        subprocess.run([synth, "300000", "2"], stdout=f, check=True)
+    a = dump(path, {"GT_PARSE_THREADS": "1"})
+    b = dump(path, {"GT_PARSE_THREADS": "7", "GT_PARSE_PIECE_BYTES": "65536"})
+    assert a[0] == 0 and a[1] == b[1] and len(a[1].splitlines()) == 300000
+    # and the stream is the one the device generator and tests/support.py produce
+    r = support.synth_reads(1000, 2)
+    c, s, e, st = r["chrom"], r["start"], r["stop"], r["strand"]
+    for k, l in enumerate(a[1].splitlines()[:1000]):
+        f = l.split(b"\t")[1].split(b" ")
+        assert f[0].decode() == support.HG19_NAMES[c[k]] and f[1] == bytes([int(st[k])]) and int(f[2]) == s[k] and int(f[3]) == e[k]
