@@ -27,13 +27,23 @@ BIN = os.path.join(ROOT, "ibm-cbc-genomic-tools_b200", "bin")
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
+LAST_PHASES = {}
+
+
 def timed(cmd, stdout_path):
+    """wall-clock of the whole process; our drivers also report their phases on stderr (GT_TIMING)"""
     t0 = time.perf_counter()
     with open(stdout_path, "wb") as f:
-        p = subprocess.run(cmd, stdout=f, stderr=subprocess.PIPE)
+        p = subprocess.run(cmd, stdout=f, stderr=subprocess.PIPE, env=dict(os.environ, GT_TIMING="1"))
     dt = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError("%s failed: %s" % (cmd, p.stderr.decode()[-400:]))
+    LAST_PHASES.clear()
+    for line in p.stderr.decode().splitlines():
+        if line.startswith("[gt timing]"):
+            for tok in line.split()[2:]:
+                k, v = tok.split("=")
+                LAST_PHASES[k] = float(v.rstrip("s"))
     return dt
 
 
@@ -88,13 +98,18 @@ def main():
             t_ref = timed([os.path.join(REF, tool)] + opts + pre + [sub], out_ref)
         timed([os.path.join(BIN, tool)] + opts + pre + [sub], out_sub)          # also warms the page cache and the driver
         t_sub = timed([os.path.join(BIN, tool)] + opts + pre + [sub], out_sub)
+        phases_sub = dict(LAST_PHASES)
         t_new = timed([os.path.join(BIN, tool)] + opts + pre + [reads], out_new)
+        phases_new = dict(LAST_PHASES)
+        stream = phases_new.get("stream_queries", phases_new.get("stream_reads"))
         same = (md5(out_ref) == md5(out_sub)) if have_ref else None
         emit(case=name, reference_seconds=t_ref, reference_reads=args.ref_reads,
              reference_reads_per_s=(args.ref_reads / t_ref) if t_ref else None,
              ours_seconds_same_input=round(t_sub, 3), stdout_identical=same,
              ours_seconds=round(t_new, 3), ours_reads=args.reads, ours_reads_per_s=args.reads / t_new,
              ours_text_GBps=os.path.getsize(reads) / t_new / 1e9,
+             ours_phases_same_input=phases_sub, ours_phases=phases_new,
+             ours_stream_reads_per_s=(args.reads / stream) if stream else None,
              speedup_same_input=(t_ref / t_sub) if t_ref else None,
              speedup_rate=(args.reads / t_new) / (args.ref_reads / t_ref) if t_ref else None)
         if have_ref and not same:

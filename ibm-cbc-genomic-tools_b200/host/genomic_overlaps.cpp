@@ -110,6 +110,7 @@ int main(int argc, char *argv[]) {
   const char *test_file = next_arg + 1 == argc ? nullptr : argv[next_arg + 1];
 
   // ---- reference (index) set: loaded in memory, labels kept for the output
+  gt::PhaseTimer timer;
   gt::ChromTable chroms;
   gt::RegionBatch ref;
   {
@@ -127,9 +128,11 @@ int main(int argc, char *argv[]) {
     }
   }
 
+  timer.Mark("load_reference");
   gtb_ctx *ctx = nullptr;
   int rc = gtb_ctx_create(0, &ctx);
   if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
+  timer.Mark("cuda_context");
   const bool want_coverage = op == "coverage" || op == "density";
   const unsigned flags = (MATCH_GAPS ? GTB_MATCH_GAPS : 0u) | (IGNORE_STRAND ? GTB_IGNORE_STRAND : 0u);
   gtb_index *index = nullptr;
@@ -140,6 +143,7 @@ int main(int argc, char *argv[]) {
   if (rc == GTB_ERR_INDEX_REGION) gt::die_line(ref.line(err_index), "index regions should be compatible, sorted and non-overlapping!");
   check(ctx, rc, "gtb_index_create");
 
+  timer.Mark("index");
   // ---- test (query) set: streamed in chunks; parsing of chunk k+1 overlaps the device work of chunk k
   const int64_t CHUNK = 4 << 20;
   gt::RegionBatch chunk[2];
@@ -177,12 +181,14 @@ int main(int argc, char *argv[]) {
       die_query(rc, first_query_line + err_index);
     }
   }
+  timer.Mark("stream_queries");
   std::vector<uint64_t> values((size_t)std::max<int64_t>(ref.n_regions(), 1));
   rc = gtb_index_finish(index, values.data(), GTB_MEM_HOST, &err_index);
   if (rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION)
     die_query(rc, first_query_line + err_index);
   check(ctx, rc, "gtb_index_finish");
 
+  timer.Mark("finish");
   // ---- output, reference-file order (genomic_overlaps.cpp:420-427, :449-455, :476-486, :763-772)
   auto region_size = [&](int64_t k, bool skip_gaps) -> long {        // GenomicRegion::GetSize, genomic_intervals.cpp:1047-1055
     const int64_t lo = ref.offset[k], hi = ref.offset[k + 1];
@@ -212,7 +218,10 @@ int main(int argc, char *argv[]) {
       printf("%s\t%.4e\n", ref.label[k].c_str(), rpkm);
     }
   }
+  fflush(stdout);
+  timer.Mark("print");
   gtb_index_destroy(index);
   gtb_ctx_destroy(ctx);
+  timer.Mark("teardown");
   return 0;
 }

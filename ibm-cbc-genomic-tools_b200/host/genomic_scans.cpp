@@ -131,6 +131,7 @@ int main(int argc, char *argv[]) {
   if (HELP) { cmd.OperationUsage(); exit(1); }
   const char *input_file = next_arg == argc ? nullptr : argv[next_arg];
 
+  gt::PhaseTimer timer;
   // ---- genome bounds; chromosome ids in strcmp order of the names = the reference's std::map order
   std::map<std::string, long> bounds = ReadBounds(GENOME_REG_FILE);
   gt::ChromTable chroms;
@@ -157,9 +158,11 @@ int main(int argc, char *argv[]) {
     exit(1);
   }
 
+  timer.Mark("setup");
   gtb_ctx *ctx = nullptr;
   int rc = gtb_ctx_create(0, &ctx);
   if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
+  timer.Mark("cuda_context");
   gtb_scan_params prm;
   memset(&prm, 0, sizeof prm);
   prm.win_step = WIN_DIST; prm.win_size = WIN_SIZE; prm.min_reads = MIN_READS;
@@ -167,6 +170,7 @@ int main(int argc, char *argv[]) {
   gtb_scan *scan = nullptr;
   check(ctx, gtb_scan_create(ctx, n_genome, bound.data(), &prm, &scan), "gtb_scan_create");
 
+  timer.Mark("scan_create");
   // ---- reads: streamed in chunks, parse of chunk k+1 overlaps the device work of chunk k
   const int64_t CHUNK = 4 << 20;
   gt::RegionBatch chunk[2];
@@ -190,8 +194,10 @@ int main(int argc, char *argv[]) {
     check(ctx, gtb_scan_add_reads(scan, &s, GTB_MEM_HOST), "gtb_scan_add_reads");
   }
   if (reads.failed()) reads.Fail();
+  timer.Mark("stream_reads");
   int64_t n_windows = 0;
   check(ctx, gtb_scan_finish(scan, &n_windows), "gtb_scan_finish");
+  timer.Mark("finish");
 
   // ---- optional reference filter
   RefFilter filter;
@@ -231,7 +237,10 @@ int main(int argc, char *argv[]) {
     }
   }
   if (!text.empty()) fwrite(text.data(), 1, text.size(), stdout);
+  fflush(stdout);
+  timer.Mark("print");
   gtb_scan_destroy(scan);
   gtb_ctx_destroy(ctx);
+  timer.Mark("teardown");
   return 0;
 }

@@ -5,6 +5,7 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <algorithm>
 #include <functional>
@@ -313,6 +314,26 @@ bool RegionWellFormed(const RegionBatch &b, int64_t k) {
     if (b.start[i] < b.start[i - 1] || b.start[i] <= b.stop[i - 1]) return false;
   }
   return true;
+}
+
+static double NowSeconds() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+PhaseTimer::PhaseTimer() : on_(getenv("GT_TIMING") != nullptr), last_(NowSeconds()), t0_(last_) {}
+void PhaseTimer::Mark(const char *phase) {
+  if (!on_) return;
+  const double now = NowSeconds();
+  marks_.emplace_back(phase, now - last_);
+  last_ = now;
+}
+PhaseTimer::~PhaseTimer() {
+  if (!on_) return;
+  fprintf(stderr, "[gt timing]");
+  for (auto &m : marks_) fprintf(stderr, " %s=%.3fs", m.first.c_str(), m.second);
+  fprintf(stderr, " total=%.3fs\n", NowSeconds() - t0_);
 }
 
 bool SortChecker::Accept(const std::string &c, char s, long st) {

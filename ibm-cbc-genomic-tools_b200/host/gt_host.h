@@ -201,6 +201,18 @@ class RegionReader {
 char ProcessStrand(const char *token);                // '1','+' -> '+'; '-1','-' -> '-'; '.' -> '+'; else fatal  (genomic_intervals.cpp:5956-5962)
 bool RegionWellFormed(const RegionBatch &b, int64_t k);
 
+// Wall-clock marks of a driver's phases, printed to stderr at exit when GT_TIMING is set (stdout is never touched).
+class PhaseTimer {
+ public:
+  PhaseTimer();
+  void Mark(const char *phase);                       // the time since the previous mark belongs to `phase`
+  ~PhaseTimer();
+ private:
+  bool on_;
+  double last_, t0_;
+  std::vector<std::pair<std::string, double>> marks_;
+};
+
 // -S sortedness checker (GenomicRegion::IsBefore on consecutive regions)
 struct SortChecker {
   bool by_strand = false;
