@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU (default: the BASELINE config)")
     ap.add_argument("--regions", type=int, default=N_REGIONS, help="index regions (default: the BASELINE config; 1000000 = configs[4])")
-    ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "bucket", "enumerate"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "rank", "cell", "bucket", "direct", "enumerate"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel iteration only: skip the host-buffer leg (the line is then not a valid bench line)")
     args = ap.parse_args()
@@ -205,7 +205,7 @@ def main():
     ctx = gtb200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "cell": gtb200.ENGINE_CELL, "bucket": gtb200.ENGINE_BUCKET, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
+    engine = {"auto": 0, "rank": gtb200.ENGINE_RANK, "cell": gtb200.ENGINE_CELL, "bucket": gtb200.ENGINE_BUCKET, "direct": gtb200.ENGINE_DIRECT, "enumerate": gtb200.ENGINE_ENUMERATE}[args.engine]
 
     dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
            "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}

@@ -1,0 +1,396 @@
+// gtb_direct.cu -- DIRECT engine: overlap count in ONE pass over the queries, for indices whose evaluation points fit
+// a byte counter each in one SM's shared memory (up to ~200 k slots: 100 k regions).
+//
+// Why (measured on B200, profiles/microbench/gather_rate_b200.txt and red_rate_b200.txt): a random 8-byte load from a
+// table that lives in L2 (up to 16 MB) costs 1.1 SM-cycles per element, a random shared-memory atomic 0.17, a random
+// global reduction 1.45.  The BUCKET engine pays 13 + 4 + 4 bytes of HBM traffic and two kernels' worth of
+// shared-memory work per query to avoid global reductions; this engine pays 13 bytes, one L2 gather and one shared atomic:
+//
+//   * The groups' coordinate axes are cut into cells of 2^c bp laid end to end (c chosen so that the table stays <= 16 MB:
+//     hg19 x 2 strands at c = 12 is 1.5 M cells).  One 8-byte entry per cell: the slot of the first evaluation point at or
+//     after the cell's start (24 bits), the offsets of up to three points inside the cell (12 bits each, 0xFFF = none) and
+//     a "more than three" flag.  For a query [s, e] whose ends fall into cells with at most three points
+//         jS = slot0(cell(s)) + #{p < s & (2^c - 1)},   jE likewise for e  (a second gather only if e is in another cell),
+//     which is lower_bound(points, s) / lower_bound(points, e) of the RANK engine (gtb_rank_device.cuh) without a search.
+//   * jS == jE (almost every short read): one shared-memory atomicAdd on a BYTE counter (four slots per 32-bit word).  The
+//     add that finds its byte at 127 moves 128 to the global plane (one atomicSub, one reduction), so a byte stays below 256
+//     unless more than 127 further adds land before that correction does; the add that finds 255 raises a flag.  The word is
+//     arithmetically exact throughout (transient carries between bytes cancel), so without the flag the bytes are the
+//     exact counts.  With the flag the whole batch is discarded and replayed through the general rank step by the commit kernel
+//     (which otherwise only sums) -- correct whatever the skew, and the host switches the engine off for this index.
+//   * jS != jE (a read straddling an evaluation point, ~0.1 %), more than three points in a cell, strands other than +/-,
+//     reads reaching past the group's last point, invalid intervals: the general path inline (binary search, global
+//     reductions), into per-batch delta planes so that a discarded batch leaves no trace.
+//   * Position-sorted input: a warp whose 128 queries share one slot sends one reduction of 128.
+//   * At the end each CTA writes its counters to its row of a [CTAs x slots] byte matrix (coalesced); a commit kernel sums the
+//     rows and the delta planes into the index's histogram planes.  Finalisation is the RANK engine's.
+//
+// Reference semantics reproduced: admission rules of UnsortedGenomicRegionSetOverlaps::GetQuery/NextQuery
+// (genomic_intervals.cpp:5719-5745) and the overlap predicate (:624-630, :5227-5229) through the rank formulation of
+// SURVEY.md section 7.1 -- see gtb_overlap.cuh.
+#include "gtb_rank_device.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int DR_THREADS = 1024;
+constexpr int DR_ITEMS = 4;
+constexpr int DR_TILE = DR_THREADS * DR_ITEMS;
+constexpr uint32_t DR_NOPOINT = 0xFFFu;
+constexpr size_t DR_TABLE_BYTES_MAX = (size_t)16 << 20;
+
+struct DirectView {
+  int cbits;                        // cell = 2^cbits bp (<= 12)
+  int32_t n_chrom, n_class;
+  const int2 *gtab;                 // [2 * n_chrom + 2] per (chromosome, '+'/'-'): (largest point [0: none, < 0: only points <= 0], first cell)
+  const uint2 *cells;               // [n_cells] x = slot0 | many << 24, y = p0 | p1 << 12 | p2 << 24 (p2's top 4 bits in x >> 28)
+  uint32_t n_words;                 // 32-bit words of byte counters per CTA (n_slots / 4, rounded up to a multiple of 4)
+  uint32_t *cta_counts;             // [grid][n_words]
+  ull *delta;                       // [3][n_slots] this batch's contributions that did not go through the byte counters
+  uint32_t *flag;                   // [0] generation of the last batch in which a byte counter overflowed (that batch is discarded and replayed)
+  uint32_t gen;                     // this batch's generation (1, 2, ...)
+};
+
+__device__ __forceinline__ void dr_red64(ull *p, ull v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint4 dr_ldg128(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t dr_ldg32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+template <bool NA>
+__device__ __forceinline__ uint2 dr_gather(const uint2 *p) {
+  uint2 r;
+  if (NA) asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  else asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// The general path for one query: the reference's admission rules, then the rank step (gtb_rank_device.cuh).
+// Same decisions as admit_query + rank_accumulate_kernel of gtb_overlap.cu for a single-interval, unweighted query.
+__device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t qs, int32_t qe, int sbyte, int64_t index) {
+  if ((uint32_t)c >= (uint32_t)rv.n_chrom || !rv.chrom_present[c]) return;           // :5719-5720
+  if (qe <= 0) { report_error(rv.err, index, GTB_ERR_QUERY_STOP_NONPOSITIVE); return; }   // :5740
+  if (qs > qe) { report_error(rv.err, index, GTB_ERR_QUERY_START_GT_STOP); return; }      // :5741
+  const int cls = rv.class_of[(uint8_t)sbyte];
+  if (cls < 0) return;                                                              // no index region carries this strand, :5229
+  const int g = c * rv.n_class + cls;
+  const int gb = rv.goff[g], ge = rv.goff[g + 1];
+  if (ge > gb) rank_item<false>(rv, gb, ge, qs, qe, 1);
+}
+
+// number of the cell's points that lie below offset `off` (absent points are 0xFFF and never do)
+__device__ __forceinline__ uint32_t dr_below(uint2 ent, uint32_t off) {
+  const uint32_t p0 = ent.y & 0xFFFu, p1 = (ent.y >> 12) & 0xFFFu, p2 = (ent.y >> 24) | ((ent.x >> 28) << 8);
+  return (p0 < off ? 1u : 0u) + (p1 < off ? 1u : 0u) + (p2 < off ? 1u : 0u);
+}
+
+// The 13 bytes per query come as 128-bit loads straight into registers, one tile ahead of the tile being counted, so that
+// 4 096 gathers per SM are in flight (what the gathers need to run at their 1.1 SM-cycles each).  Staging the input through a
+// TMA ring in shared memory instead was measured and lost: next to 120 KB of counters the ring leaves the L1 too small to
+// track the gathers' misses (1.85 SM-cycles per gather with 224 KB carved out), and tiles small enough to fit leave too few
+// gathers in flight (1.2 - 1.6 ms against 0.59 ms per 100 M queries; profiles/r1_experiments.md).
+template <bool NA>
+__global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
+                                                                       const __grid_constant__ DirectView dv) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *s_cnt = smem;                                              // [n_words] four byte counters per word
+  int2 *s_gtab = reinterpret_cast<int2 *>(smem + dv.n_words);          // [2 * n_chrom + 2]  8-byte entries: half the bank conflicts of 16
+  for (uint32_t i = threadIdx.x; i < dv.n_words; i += DR_THREADS) s_cnt[i] = 0;
+  const uint32_t n_gtab = 2u * (uint32_t)dv.n_chrom + 2u;
+  for (uint32_t i = threadIdx.x; i < n_gtab; i += DR_THREADS) s_gtab[i] = dv.gtab[i];
+  __syncthreads();
+  const uint32_t cbits = (uint32_t)dv.cbits, cmask = (1u << cbits) - 1u;
+  const int64_t n = q.n_regions;
+  const int64_t n_full = n / DR_TILE;
+  const int lane = threadIdx.x & 31;
+  const ull K = (ull)rv.n_slots;
+  bool overflowed = false;
+
+  // one query through everything the fast path cannot decide
+  auto slow = [&](int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) { dr_general(rv, c, s, e, (int)(int8_t)sbyte, index); };
+  // count one query in slot j of the "both" plane
+  auto bump = [&](uint32_t j) {
+    const uint32_t sh = (j & 3u) * 8u;
+    const uint32_t old = atomicAdd(&s_cnt[j >> 2], 1u << sh);
+    const uint32_t ob = (old >> sh) & 0xFFu;
+    if (ob == 127u) { atomicSub(&s_cnt[j >> 2], 128u << sh); dr_red64(dv.delta + j, 128ull); }
+    overflowed |= ob == 255u;
+  };
+
+  uint4 nc, ns, ne;
+  uint32_t nst;
+  int64_t tile = blockIdx.x;
+  if (tile < n_full) {
+    const int64_t first = tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS;
+    nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
+  }
+  for (; tile < n_full; tile += gridDim.x) {
+    const uint4 cc = nc, cs = ns, ce = ne;
+    const uint32_t stw = nst;
+    const int64_t next = tile + gridDim.x;
+    if (next < n_full) {                                               // the next tile's 13 bytes per query are on their way while this one is counted
+      const int64_t first = next * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS;
+      nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
+    }
+    const int32_t c[DR_ITEMS] = {(int)cc.x, (int)cc.y, (int)cc.z, (int)cc.w};
+    const int32_t s[DR_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
+    const int32_t e[DR_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
+    // strands: '+' = 0x2B, '-' = 0x2D.  xw has 0x00 / 0x06 in the bytes of '+' / '-' queries
+    const uint32_t xw = stw ^ 0x2B2B2B2Bu;
+    const bool odd_strand = (xw & 0xF9F9F9F9u) != 0;                   // some strand other than '+'/'-': those items take the general path
+    uint32_t kind[DR_ITEMS];                                           // 0 fast, 1 nothing to count, 2 general path
+    uint32_t cell_s[DR_ITEMS], cell_e[DR_ITEMS];
+    uint2 ent[DR_ITEMS];
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) {
+      const uint32_t ci = min((uint32_t)c[i], (uint32_t)dv.n_chrom);   // unknown chromosome -> an empty entry
+      const int2 g = s_gtab[2u * ci + ((xw >> (8 * i + 1)) & 1u)];
+      const int gmax = max(g.x, 0);
+      const bool addressable = !odd_strand || ((xw >> (8 * i)) & 0xF9u) == 0;
+      const bool valid = s[i] >= 1 && s[i] <= e[i];
+      const bool inside = (uint32_t)(s[i] - 1) < (uint32_t)gmax && e[i] <= gmax;
+      const bool nothing = valid && g.x >= 0 && (g.x == 0 || s[i] > g.x);           // no points in the group / start beyond the last one
+      kind[i] = !addressable ? 2u : (valid && inside) ? 0u : nothing ? 1u : 2u;
+      cell_s[i] = (uint32_t)g.y + ((uint32_t)s[i] >> cbits);
+      cell_e[i] = (uint32_t)g.y + ((uint32_t)e[i] >> cbits);
+      if (kind[i] != 0u) { cell_s[i] = 0; cell_e[i] = 0; }
+    }
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) ent[i] = dr_gather<NA>(dv.cells + cell_s[i]);
+    uint32_t jS[DR_ITEMS], jE[DR_ITEMS];
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) {
+      uint2 ee = ent[i];
+      if (cell_e[i] != cell_s[i]) ee = dr_gather<NA>(dv.cells + cell_e[i]);          // a read that crosses a cell boundary (~1 %)
+      if (kind[i] == 0u && (((ent[i].x | ee.x) >> 24) & 1u)) kind[i] = 2u;           // more than three points in a cell
+      jS[i] = (ent[i].x & 0xFFFFFFu) + dr_below(ent[i], (uint32_t)s[i] & cmask);
+      jE[i] = (ee.x & 0xFFFFFFu) + dr_below(ee, (uint32_t)e[i] & cmask);
+    }
+    // position-sorted input: the warp's 128 queries in one slot leave as one reduction
+    const uint32_t lead = __shfl_sync(0xffffffffu, jS[0], 0);
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) same = same && kind[i] == 0u && jS[i] == lead && jE[i] == lead;
+    if (__all_sync(0xffffffffu, same)) {
+      if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS));
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) {
+      if (kind[i] == 0u) {
+        if (jS[i] == jE[i]) bump(jS[i]);
+        else { dr_red64(dv.delta + H_SCNT * K + jS[i], 1ull); dr_red64(dv.delta + H_ECNT * K + jE[i], 1ull); }
+      } else if (kind[i] == 2u) {
+        slow(c[i], s[i], e[i], (stw >> (8 * i)) & 0xFFu, q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
+      }
+    }
+  }
+  // the last, partial tile: general path
+  if ((int64_t)blockIdx.x == n_full % gridDim.x) {
+    for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
+      slow(q.chrom[r], q.start[r], q.stop[r], (uint32_t)(uint8_t)q.strand[r], q.index_base + r);
+  }
+  if (overflowed) atomicMax(dv.flag, dv.gen);
+  __syncthreads();
+  uint4 *row = reinterpret_cast<uint4 *>(dv.cta_counts + (size_t)blockIdx.x * dv.n_words);
+  for (uint32_t i = threadIdx.x; i < dv.n_words / 4; i += DR_THREADS) row[i] = reinterpret_cast<const uint4 *>(s_cnt)[i];
+}
+
+// Sums the CTAs' byte counters and the delta planes into the index's histogram planes and clears the delta planes -- or, if a
+// byte counter overflowed somewhere in this batch (flag == the batch's generation), only clears them and then sends every
+// query through the general path straight into the histogram planes (nothing else touches those in that case).
+__global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, QueryView q, RankView rv_hist, int64_t n_slots, unsigned rows) {
+  ull *hist = rv_hist.hist;
+  const bool discard = dv.flag[0] == dv.gen;
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < dv.n_words) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (!discard)
+      for (unsigned r = 0; r < rows; r++) {
+        const uint32_t v = dv.cta_counts[(size_t)r * dv.n_words + w];
+        a0 += v & 0xFFu; a1 += (v >> 8) & 0xFFu; a2 += (v >> 16) & 0xFFu; a3 += v >> 24;
+      }
+    const uint32_t acc[4] = {a0, a1, a2, a3};
+    for (int b = 0; b < 4; b++) {
+      const int64_t j = (int64_t)w * 4 + b;
+      if (j >= n_slots) break;
+      for (int p = 0; p < H_PLANES_COUNT; p++) {
+        const ull d = dv.delta[(int64_t)p * n_slots + j];
+        const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc[b] : 0ull);
+        if (add) hist[(int64_t)p * n_slots + j] += add;
+        if (d) dv.delta[(int64_t)p * n_slots + j] = 0;
+      }
+    }
+  }
+  if (!discard) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride)
+    dr_general(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
+}
+
+template <typename T>
+int upload_d(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
+  GTB_TRY(d.reserve(ctx, std::max<size_t>(h.size(), 1)));
+  if (!h.empty()) GTB_CUDA_OK(ctx, cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return GTB_OK;
+}
+
+}  // namespace
+
+struct gtb_direct_state {
+  bool ready = false, failed = false, off = false;
+  int cbits = 0;
+  uint32_t n_cells = 0, n_words = 0;
+  unsigned grid = 0;
+  bool no_allocate = false;
+  size_t smem = 0;
+  dbuf<int2> d_gtab;
+  dbuf<uint2> d_cells;
+  dbuf<uint32_t> d_cta_counts, d_flag;
+  dbuf<ull> d_delta;
+  int64_t queries_since_check = 0;
+  uint32_t gen = 0;
+};
+
+int gtb_direct_prepare(gtb_index *ix) {
+  if (ix->direct && (ix->direct->ready || ix->direct->failed)) return ix->direct->ready ? GTB_OK : GTB_ERR_UNSUPPORTED;
+  gtb_ctx *ctx = ix->ctx;
+  if (!ix->direct) ix->direct = new gtb_direct_state();
+  gtb_direct_state *ds = ix->direct;
+  ds->failed = true;                                                    // until proven otherwise
+  if (ix->op != GTB_OP_COUNT || ix->n_slots == 0 || ix->n_slots >= (1 << 24)) return GTB_ERR_UNSUPPORTED;
+  const int G = ix->n_groups;
+  const uint32_t n_words = (uint32_t)(((ix->n_slots + 3) / 4 + 3) & ~(int64_t)3);
+  const size_t smem = (size_t)n_words * 4 + ((size_t)2 * std::max(ix->n_chrom, 1) + 2) * 8;
+  // The gathers need L1 to track their misses in: measured (profiles/microbench/gather_rate_b200.txt), a gather costs 1.02
+  // SM-cycles with up to 192 KB of the SM's 256 KB carved out as shared memory and 1.85 with 224 KB.
+  if (smem > std::min<size_t>(ctx->smem_optin, (size_t)192 * 1024)) return GTB_ERR_UNSUPPORTED;
+  // largest evaluation point per group (0: none, -1: only points <= 0)
+  std::vector<int32_t> gsize((size_t)std::max(G, 1), 0);
+  uint64_t span = 0;
+  for (int g = 0; g < G; g++) {
+    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1];
+    if (ge - gb >= 2) { const int32_t mx = ix->h_points[ge - 2]; gsize[g] = mx >= 1 ? mx : -1; }
+    if (gsize[g] > 0) span += (uint64_t)gsize[g] + 1;
+  }
+  if (span == 0) return GTB_ERR_UNSUPPORTED;
+  int cbits = 12;
+  if (const char *env = getenv("GTB_DIRECT_CELL_BITS")) cbits = std::max(4, std::min(12, atoi(env)));
+  std::vector<uint32_t> gbase((size_t)std::max(G, 1), 0);
+  uint64_t cells = 0;
+  for (int g = 0; g < G; g++) {
+    gbase[g] = (uint32_t)cells;
+    if (gsize[g] > 0) cells += ((uint64_t)gsize[g] >> cbits) + 1;
+  }
+  if (cells * sizeof(uint2) > DR_TABLE_BYTES_MAX && !getenv("GTB_DIRECT_CELL_BITS")) return GTB_ERR_UNSUPPORTED;   // the table would fall out of L2's fast range
+  if (cells >= ((uint64_t)1 << 31)) return GTB_ERR_UNSUPPORTED;
+  std::vector<uint2> tab((size_t)cells);
+  size_t many = 0;
+  for (int g = 0; g < G; g++) {
+    if (gsize[g] <= 0) continue;
+    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1] - 1;       // [gb, ge): the group's points without the sentinel
+    const uint64_t nc = ((uint64_t)gsize[g] >> cbits) + 1;
+    int32_t j = gb;
+    for (uint64_t x = 0; x < nc; x++) {
+      const int64_t lo = (int64_t)x << cbits, hi = lo + ((int64_t)1 << cbits);
+      while (j < ge && ix->h_points[j] < lo) j++;
+      uint32_t p[3] = {DR_NOPOINT, DR_NOPOINT, DR_NOPOINT};
+      int32_t t = j, cnt = 0;
+      while (t < ge && ix->h_points[t] < hi) { if (cnt < 3) p[cnt] = (uint32_t)(ix->h_points[t] - lo); cnt++; t++; }
+      // (a real point at offset 0xFFF looks like "no point" and behaves like it too: no offset is larger, so it is never below one)
+      const bool general = cnt > 3;
+      many += general ? 1 : 0;
+      uint2 ent;
+      ent.x = (uint32_t)j | (general ? 1u << 24 : 0u) | ((p[2] >> 8) << 28);
+      ent.y = p[0] | (p[1] << 12) | ((p[2] & 0xFFu) << 24);
+      tab[(size_t)gbase[g] + x] = ent;
+    }
+  }
+  std::vector<int2> gtab((size_t)2 * std::max(ix->n_chrom, 1) + 2, make_int2(0, 0));
+  const int cp = ix->h_class_of[(uint8_t)'+'], cm = ix->h_class_of[(uint8_t)'-'];
+  for (int c = 0; c < ix->n_chrom; c++)
+    for (int sgn = 0; sgn < 2; sgn++) {
+      const int cls = sgn ? cm : cp;
+      if (cls < 0) continue;
+      const int g = c * ix->n_class + cls;
+      gtab[(size_t)2 * c + sgn] = make_int2(gsize[g], (int)gbase[g]);
+    }
+  ds->cbits = cbits; ds->n_cells = (uint32_t)cells; ds->n_words = n_words; ds->smem = smem;
+  ds->no_allocate = getenv("GTB_DIRECT_NO_ALLOCATE") != nullptr;      // measured: the gathers run faster when they allocate in L1 (0.585 vs 0.682 ms)
+  ds->grid = (unsigned)ctx->sm_count;
+  GTB_TRY(upload_d(ctx, ds->d_gtab, gtab));
+  GTB_TRY(upload_d(ctx, ds->d_cells, tab));
+  GTB_TRY(ds->d_cta_counts.reserve(ctx, (size_t)ds->grid * n_words));
+  GTB_TRY(ds->d_delta.reserve(ctx, (size_t)H_PLANES_COUNT * ix->n_slots));
+  GTB_TRY(ds->d_flag.reserve(ctx, 2));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_delta.p, 0, (size_t)H_PLANES_COUNT * ix->n_slots * sizeof(ull), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (getenv("GTB_DEBUG_DIRECT"))
+    fprintf(stderr, "[gtb direct] slots %lld cells %llu (2^%d bp, %.1f MB) general cells %zu smem %zu\n", (long long)ix->n_slots,
+            (unsigned long long)cells, cbits, cells * 8 / 1e6, many, smem);
+
+  ds->ready = true; ds->failed = false;
+  return GTB_OK;
+}
+
+bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
+  if (batch_multi || q.region_offset || q.weight || ix->op != GTB_OP_COUNT) return false;   // single-interval, unweighted count
+  if (q.n_regions >= ((int64_t)1 << 40)) return false;
+  if ((((uintptr_t)q.chrom | (uintptr_t)q.start | (uintptr_t)q.stop) & 15) != 0 || ((uintptr_t)q.strand & 3) != 0) return false;   // 128-bit loads
+  if (gtb_direct_prepare(ix) != GTB_OK) return false;
+  return !ix->direct->off;
+}
+
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
+  gtb_ctx *ctx = ix->ctx;
+  if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
+  gtb_direct_state *ds = ix->direct;
+  if (q.region_offset || q.weight) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine takes single-interval, unweighted batches");
+  // skew watchdog: a replayed batch means byte counters overflow on this input -- leave the field to the BUCKET engine from now on.
+  // Checked at the first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
+  if (ds->queries_since_check > 0 && (q.index_base == 0 || ds->queries_since_check >= ((int64_t)64 << 20))) {
+    uint32_t overflow_gen = 0;
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(&overflow_gen, ds->d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (overflow_gen != 0) ds->off = true;
+    ds->queries_since_check = 0;
+    if (ds->off) return gtb_bucket_supported(ix, q, false) ? gtb_bucket_accumulate(ix, q) : gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine switched off");
+  }
+  RankView rv;
+  rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p;
+  DirectView dv;
+  dv.cbits = ds->cbits; dv.n_chrom = ix->n_chrom; dv.n_class = ix->n_class; dv.gtab = ds->d_gtab.p; dv.cells = ds->d_cells.p;
+  dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
+  if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
+  dv.gen = ds->gen;
+  const int64_t tiles = q.n_regions / DR_TILE;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ds->grid, tiles));
+  if (ds->no_allocate) {
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
+    GTB_LAUNCH(ctx, "direct_count", direct_count_kernel<true>, grid, DR_THREADS, ds->smem, q, rv, dv);
+  } else {
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
+    GTB_LAUNCH(ctx, "direct_count", direct_count_kernel<false>, grid, DR_THREADS, ds->smem, q, rv, dv);
+  }
+  GTB_TRY(gtb_check_launch(ctx));
+  RankView rv_hist = rv;
+  rv_hist.hist = ix->d_hist.p;
+  GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel, (ds->n_words + 255) / 256, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
+  ds->queries_since_check += q.n_regions;
+  return gtb_check_launch(ctx);
+}
+
+void gtb_direct_destroy(gtb_index *ix) {
+  gtb_direct_state *ds = ix->direct;
+  if (!ds) return;
+  ds->d_gtab.release(); ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
+  delete ds;
+  ix->direct = nullptr;
+}

@@ -386,7 +386,7 @@ extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, un
   ix->ctx = ctx; ix->op = op;
   ix->match_gaps = (flags & GTB_MATCH_GAPS) != 0;
   ix->ignore_strand = (flags & GTB_IGNORE_STRAND) != 0;
-  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_CELL | GTB_ENGINE_BUCKET);
+  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_CELL | GTB_ENGINE_BUCKET | GTB_ENGINE_DIRECT);
   ix->n_regions = regions->n_regions; ix->n_intervals = regions->n_intervals;
   const size_t ni = (size_t)regions->n_intervals;
   ix->h_chrom.assign(regions->chrom, regions->chrom + ni);
@@ -413,6 +413,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   gtb_ctx_synchronize(ix->ctx);
   gtb_cell_destroy(ix);
   gtb_bucket_destroy(ix);
+  gtb_direct_destroy(ix);
   ix->d_class_of.release(); ix->d_present.release(); ix->d_goff.release(); ix->d_points.release();
   ix->d_t_hi.release(); ix->d_t_lo.release(); ix->d_t_base.release(); ix->d_t_off.release();
   ix->d_hist.release(); ix->d_hist_scan.release(); ix->d_scan_scratch.release();
@@ -445,6 +446,11 @@ static unsigned choose_engine(gtb_index *ix, const QueryView &q, bool batch_mult
   if (ix->engine & GTB_ENGINE_ENUMERATE) return GTB_ENGINE_ENUMERATE;
   if (!rank_valid) return GTB_ENGINE_ENUMERATE;
   if (ix->engine & GTB_ENGINE_RANK) return GTB_ENGINE_RANK;
+  // one pass where the index is small enough for byte counters in shared memory and the batch large enough to pay for the
+  // per-batch dump of the counters; GTB_ENGINE_DIRECT asks for it whatever the batch size
+  if (!(ix->engine & (GTB_ENGINE_CELL | GTB_ENGINE_BUCKET)) && ((ix->engine & GTB_ENGINE_DIRECT) || q.n_regions >= (1 << 18)) &&
+      gtb_direct_supported(ix, q, batch_multi))
+    return GTB_ENGINE_DIRECT;
   if (!(ix->engine & GTB_ENGINE_CELL) && gtb_bucket_supported(ix, q, batch_multi)) return GTB_ENGINE_BUCKET;
   if (!(ix->engine & GTB_ENGINE_BUCKET) && gtb_cell_supported(ix, q, batch_multi)) return GTB_ENGINE_CELL;
   return GTB_ENGINE_RANK;
@@ -456,6 +462,7 @@ static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi
   const unsigned engine = choose_engine(ix, q, batch_multi);
   if (engine == GTB_ENGINE_CELL) return gtb_cell_accumulate(ix, q);
   if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
+  if (engine == GTB_ENGINE_DIRECT) return gtb_direct_accumulate(ix, q);
   RankView rv = rank_view(ix);
   if (engine == GTB_ENGINE_ENUMERATE) {
     GTB_TRY(build_enum_structures(ix));

@@ -99,6 +99,8 @@ struct gtb_index {
   struct gtb_cell_state *cell = nullptr;
   // bucket engine state (gtb_bucket.cu)
   struct gtb_bucket_state *bucket = nullptr;
+  // direct engine state (gtb_direct.cu)
+  struct gtb_direct_state *direct = nullptr;
 
   // results / errors
   dbuf<ull> d_err, d_out;
@@ -166,3 +168,9 @@ int gtb_bucket_prepare(gtb_index *ix);
 int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q);
 void gtb_bucket_destroy(gtb_index *ix);
 bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
+
+// ---- direct engine (gtb_direct.cu) ---------------------------------------------------------------
+int gtb_direct_prepare(gtb_index *ix);
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q);
+void gtb_direct_destroy(gtb_index *ix);
+bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

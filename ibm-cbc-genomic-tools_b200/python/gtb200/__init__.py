@@ -21,6 +21,7 @@ ENGINE_ENUMERATE = 1 << 16
 ENGINE_RANK = 1 << 17
 ENGINE_CELL = 1 << 18
 ENGINE_BUCKET = 1 << 19
+ENGINE_DIRECT = 1 << 20
 OP_COUNT = 0
 OP_COVERAGE = 1
 

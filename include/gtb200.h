@@ -63,7 +63,9 @@ enum {
   GTB_ENGINE_ENUMERATE = 1u << 16,  /* candidate enumeration (general; any region shape)         */
   GTB_ENGINE_RANK      = 1u << 17,  /* rank/rank-sum with global binary search                    */
   GTB_ENGINE_CELL      = 1u << 18,  /* single pass: genome-cell tables, hot-cell bitmap in shared memory        */
-  GTB_ENGINE_BUCKET    = 1u << 19   /* two passes: partition by genome bucket, rank in shared memory (default fast path) */
+  GTB_ENGINE_BUCKET    = 1u << 19,  /* two passes: partition by genome bucket, rank in shared memory (any index size)        */
+  GTB_ENGINE_DIRECT    = 1u << 20   /* one pass: slot lookup in an L2-resident cell table, byte counters in shared memory
+                                       (count, up to ~200 k evaluation points; the default there)                           */
 };
 
 enum { GTB_OP_COUNT = 0, GTB_OP_COVERAGE = 1 };

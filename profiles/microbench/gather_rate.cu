@@ -15,9 +15,9 @@ __device__ __forceinline__ uint32_t ldnc_na(const uint32_t *p) { uint32_t v; asm
 __device__ __forceinline__ uint2 ldnc64(const uint2 *p) { uint2 v; asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; }
 
 template <int MODE>
-__global__ void __launch_bounds__(512, 2) k(const uint32_t *tab, uint32_t mask, int trips, unsigned *sink) {
+__global__ void __launch_bounds__(512, 2) k(const uint32_t *tab, uint32_t mask, int trips, unsigned *sink, uint32_t nw) {
   extern __shared__ unsigned sm[];
-  for (int i = threadIdx.x; i < 24576; i += blockDim.x) sm[i] = 0;
+  for (int i = threadIdx.x; i < (int)nw; i += blockDim.x) sm[i] = 0;
   __syncthreads();
   uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
   unsigned acc = 0;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(512, 2) k(const uint32_t *tab, uint32_t mask, 
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (MODE >= 2) atomicAdd(&sm[(v[i] >> 2) % 24576u], 1u << (8 * (v[i] & 3u)));
+      if (MODE >= 2) atomicAdd(&sm[(v[i] >> 2) % nw], 1u << (8 * (v[i] & 3u)));
       else acc += v[i];
     }
   }
@@ -51,14 +51,15 @@ int main() {
   for (size_t i = 0; i < max_entries; i++) h[i] = (uint32_t)(i * 2654435761u >> 7);
   cudaMemcpy(tab, h, max_entries * 4, cudaMemcpyHostToDevice);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  size_t smem_bytes = 98304;
   auto run = [&](const char *name, auto kern, uint32_t bits) {
     const uint32_t mask = (1u << bits) - 1;
     const int tr = trips * 2;
     const double total = (double)grid * block * tr * 4;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-    kern<<<grid, block, 98304>>>(tab, mask, 8, sink);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    kern<<<grid, block, smem_bytes>>>(tab, mask, 8, sink, (uint32_t)(smem_bytes / 4));
     cudaEventRecord(a);
-    for (int r = 0; r < 5; r++) kern<<<grid, block, 98304>>>(tab, mask, tr, sink);
+    for (int r = 0; r < 5; r++) kern<<<grid, block, smem_bytes>>>(tab, mask, tr, sink, (uint32_t)(smem_bytes / 4));
     cudaEventRecord(b); cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b); ms /= 5;
     printf("%-34s table=%6.1f MB  %.3f ms for %.0f M  %.3e ops/s  %.2f SM-cycles/op(@1.965GHz)  100M would take %.3f ms\n", name,
@@ -69,6 +70,13 @@ int main() {
     run("ld.nc.v2.u32 random", k<1>, bits);
     run("ld.nc.u32 + smem byte atomic", k<2>, bits);
     run("ld.nc.na.u32 + smem byte atomic", k<3>, bits);
+  }
+  // the same gathers with more and more of the SM's 256 KB carved out as shared memory (less L1 to track misses in); one CTA per SM
+  // from 128 KB up, so the grid halves and the per-thread trip count doubles
+  for (size_t kb : {32, 64, 96, 112}) {
+    smem_bytes = kb * 1024;
+    printf("2 CTAs x %zu KB shared memory per SM: ", kb);
+    run("ld.nc.na.u32 + smem byte atomic", k<3>, 21);
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

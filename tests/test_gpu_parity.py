@@ -9,7 +9,7 @@ import support
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18, "bucket": 1 << 19}
+ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18, "bucket": 1 << 19, "direct": 1 << 20}
 CELL_KS = ("3", "6", "10")      # cell widths 8 / 64 / 1024 bp: mostly-cold, mixed, and overfull-hot-cell regimes
 
 
@@ -19,6 +19,7 @@ def cell_k(request, monkeypatch):
     # the bucket engine's knobs ride along: cell width and bucket width (12..16 bits -> several buckets on the toy genomes)
     monkeypatch.setenv("GTB_BUCKET_K", {"3": "2", "6": "5", "10": "8"}[request.param])
     monkeypatch.setenv("GTB_BUCKET_BITS", {"3": "9", "6": "12", "10": "16"}[request.param])
+    monkeypatch.setenv("GTB_DIRECT_CELL_BITS", {"3": "4", "6": "7", "10": "12"}[request.param])   # the direct engine's cell width
     if request.param == "6":
         monkeypatch.setenv("GTB_BUCKET_PAGED", "1")       # the paged form of pass 1
     if request.param == "3":
@@ -48,8 +49,8 @@ def oracle():
 @pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("case", goldens.overlap_cases(), ids=lambda c: c["name"])
 def test_overlap_golden(ctx, case, engine, cell_k):
-    if engine not in ("cell", "bucket") and cell_k != CELL_KS[0]:
-        pytest.skip("cell width only matters to the cell / bucket engines")
+    if engine not in ("cell", "bucket", "direct") and cell_k != CELL_KS[0]:
+        pytest.skip("cell width only matters to the cell / bucket / direct engines")
     multi = case["ioff"] is not None or case["qoff"] is not None
     for (op, flags), want in case["expect"].items():
         if engine == "rank" and multi and op == "count" and not (flags & 1):
@@ -93,6 +94,68 @@ def test_random_vs_oracle(ctx, oracle, seed, cell_k):
             assert rc == 0 and np.array_equal(got, want), ("coverage", flags, seed)
             got = ctx.overlap_coverage(q, idx, flags | ENGINES["enumerate"], qweight=weights, qoffsets=qoff, roffsets=ioff)
             assert np.array_equal(got, want), ("coverage/enumerate", flags, seed)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_direct_engine_vs_oracle(gtb, ctx, oracle, seed, cell_k):
+    """The one-pass DIRECT engine on batches large enough for its tiled path (tens of thousands of queries on toy genomes, so
+    that cells hold 0, 1..3 and more than three evaluation points at the three cell widths), with everything its fast path
+    must hand to the general one mixed in: strands other than +/-, chromosomes the index has never seen, reads reaching past
+    the last evaluation point, long reads spanning many cells -- and, in a second run, invalid queries whose error must be
+    the first in stream order."""
+    rng = np.random.default_rng(4200 + seed)
+    gen = randcases.rand_grid if seed % 2 else randcases.rand_single
+    idx = gen(rng, 400 if seed < 2 else 40)
+    n = 4096 * 9 + 1234
+    q = gen(rng, n, strands="+-+-+-." if seed % 2 else "+-")
+    q["chrom"][rng.random(n) < 0.02] = 7                                 # unknown chromosome
+    far = rng.random(n) < 0.05
+    q["start"][far] += 5000; q["stop"][far] += 5000                      # beyond every evaluation point
+    wide = rng.random(n) < 0.05
+    q["stop"][wide] += rng.integers(1, 6000, size=int(wide.sum())).astype(np.int32)
+    for flags in range(4):
+        rc, want, _ = oracle.count(q, idx, flags)
+        assert rc == 0
+        got = ctx.overlap_count(q, idx, flags | ENGINES["direct"])
+        assert np.array_equal(got, want), (flags, seed)
+        assert np.array_equal(ctx.overlap_count(q, idx, flags | ENGINES["bucket"]), want)
+    bad = {k: v.copy() for k, v in q.items()}
+    where = sorted(rng.choice(n, size=3, replace=False).tolist())
+    bad["stop"][where[0]] = bad["start"][where[0]] - 1                   # start > stop
+    bad["stop"][where[1]] = 0; bad["start"][where[1]] = -3               # stop <= 0
+    bad["stop"][where[2]] = bad["start"][where[2]] - 5
+    bad["chrom"][where] = idx["chrom"][0]                                # on an indexed chromosome: fatal (:5731-5741)
+    rc, _, ei = oracle.count(bad, idx, 0)
+    assert rc != 0
+    with pytest.raises(gtb.GtbError) as e:
+        ctx.overlap_count(bad, idx, ENGINES["direct"])
+    assert (e.value.code, e.value.index) == (rc, ei)
+
+
+def test_direct_engine_counter_overflow_is_replayed(gtb, ctx, oracle):
+    """Byte counters in shared memory: heavy skew (most reads on a handful of loci, in random order) makes some counter take
+    more than 127 adds before its spill lands -- or it does not, depending on timing.  Either way the result is exact: an
+    overflow discards the batch and replays it through the general step, and the index then leaves the engine."""
+    import torch
+    n = 3_000_000
+    reads = support.synth_reads(n, seed=31)
+    regions = support.synth_regions(3_000, seed=32)
+    rng = np.random.default_rng(7)
+    hot = rng.random(n) < 0.9
+    loci = rng.integers(0, 4, size=n)
+    reads["chrom"][hot] = 2
+    reads["start"][hot] = (1_000_000 + loci[hot] * 37).astype(np.int32)
+    reads["stop"] = (reads["start"] + 49).astype(np.int32)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in reads.items()}
+    for flags in (0, gtb.IGNORE_STRAND):
+        rc, want, _ = oracle.count(reads, regions, flags)
+        assert rc == 0
+        ix = gtb.Index(ctx, regions, gtb.OP_COUNT, flags | ENGINES["direct"])
+        for rep in range(3):
+            ix.reset()
+            ix.add_device(dev)
+            assert np.array_equal(ix.finish(), want), (flags, rep)
+        ix.close()
 
 
 def test_negative_and_degenerate_coordinates(ctx, oracle, cell_k):
