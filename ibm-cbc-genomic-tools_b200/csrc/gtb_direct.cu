@@ -36,20 +36,22 @@ namespace {
 constexpr int DR_THREADS = 1024;
 constexpr int DR_ITEMS = 4;
 constexpr int DR_TILE = DR_THREADS * DR_ITEMS;
-constexpr uint32_t DR_NOPOINT = 0xFFFu;
-constexpr size_t DR_TABLE_BYTES_MAX = (size_t)16 << 20;
+constexpr uint32_t DR_NOPOINT = 0xFFFFu;
+constexpr size_t DR_TABLE_BYTES_TARGET = (size_t)13 << 20;     // cells that queries can touch: inside L2's fast range (<= 16 MB measured)
 
 struct DirectView {
-  int cbits;                        // cell = 2^cbits bp (<= 12)
-  int32_t n_chrom, n_class;
-  const int2 *gtab;                 // [2 * n_chrom + 2] per (chromosome, '+'/'-'): (largest point [0: none, < 0: only points <= 0], first cell)
-  const uint2 *cells;               // [n_cells] x = slot0 | many << 24, y = p0 | p1 << 12 | p2 << 24 (p2's top 4 bits in x >> 28)
+  int cbits;                        // cell = 2^cbits bp (<= 14)
+  int32_t n_chrom;
+  uint32_t nsig;                    // 2: '+' and '-' queries have cell blocks of their own, 1: they share one (-i)
+  uint32_t stride;                  // cells per block; the last cell of every block says "nothing to count"
+  const uint2 *cells;               // [(n_chrom + 1) * nsig * stride]  x = slot0 | general << 24 | nothing << 25 | scan << 26,  y = p0 | p1 << 16 (0xFFFF: none)
   uint32_t n_words;                 // 32-bit words of byte counters per CTA (n_slots / 4, rounded up to a multiple of 4)
   uint32_t *cta_counts;             // [grid][n_words]
   ull *delta;                       // [3][n_slots] this batch's contributions that did not go through the byte counters
   uint32_t *flag;                   // [0] generation of the last batch in which a byte counter overflowed (that batch is discarded and replayed)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
 };
+constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
 
 __device__ __forceinline__ void dr_red64(ull *p, ull v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ uint4 dr_ldg128(const void *p) {
@@ -83,44 +85,45 @@ __device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t q
   if (ge > gb) rank_item<false>(rv, gb, ge, qs, qe, 1);
 }
 
-// number of the cell's points that lie below offset `off` (absent points are 0xFFF and never do)
-__device__ __forceinline__ uint32_t dr_below(uint2 ent, uint32_t off) {
-  const uint32_t p0 = ent.y & 0xFFFu, p1 = (ent.y >> 12) & 0xFFFu, p2 = (ent.y >> 24) | ((ent.x >> 28) << 8);
-  return (p0 < off ? 1u : 0u) + (p1 < off ? 1u : 0u) + (p2 < off ? 1u : 0u);
+// number of the cell's (at most two) points that lie below offset `off` (an absent point is 0xFFFF and never does)
+__device__ __forceinline__ uint32_t dr_below(uint32_t y, uint32_t off) {
+  return ((y & 0xFFFFu) < off ? 1u : 0u) + ((y >> 16) < off ? 1u : 0u);
+}
+
+// first slot at or after j whose point is >= x: the way through a cell with more than two points (four loads per round trip; a
+// group ends with a +inf sentinel, and the array is followed by slack, so the look-ahead is harmless)
+__device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uint32_t j, int32_t x) {
+  for (;;) {
+    const int32_t a = __ldg(pts + j), b = __ldg(pts + j + 1), c = __ldg(pts + j + 2), d = __ldg(pts + j + 3);
+    if (!(a < x)) return j;
+    if (!(b < x)) return j + 1;
+    if (!(c < x)) return j + 2;
+    if (!(d < x)) return j + 3;
+    j += 4;
+  }
 }
 
 // The 13 bytes per query come as 128-bit loads straight into registers, one tile ahead of the tile being counted, so that
-// 4 096 gathers per SM are in flight (what the gathers need to run at their 1.1 SM-cycles each).  Staging the input through a
-// TMA ring in shared memory instead was measured and lost: next to 120 KB of counters the ring leaves the L1 too small to
-// track the gathers' misses (1.85 SM-cycles per gather with 224 KB carved out), and tiles small enough to fit leave too few
-// gathers in flight (1.2 - 1.6 ms against 0.59 ms per 100 M queries; profiles/r1_experiments.md).
+// 4 096 gathers per SM are in flight.  Staging the input through a TMA ring in shared memory instead was measured and lost:
+// next to 120 KB of counters the ring leaves the L1 too small to track the gathers' misses (1.85 SM-cycles per gather with
+// 224 KB carved out), and tiles small enough to fit leave too few gathers in flight (1.2 - 1.6 ms against 0.59 ms per 100 M
+// queries; profiles/r1_experiments.md).
+//
+// The hot loop holds no table but the cells: every (chromosome, strand) has a block of `stride` cells, so the cell of a
+// coordinate is pure arithmetic, and what used to be per-group knowledge (no such group, beyond the last point, too many
+// points) is two flag bits of the cell entry.
 template <bool NA>
 __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
                                                                        const __grid_constant__ DirectView dv) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *s_cnt = smem;                                              // [n_words] four byte counters per word
-  int2 *s_gtab = reinterpret_cast<int2 *>(smem + dv.n_words);          // [2 * n_chrom + 2]  8-byte entries: half the bank conflicts of 16
+  extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word
   for (uint32_t i = threadIdx.x; i < dv.n_words; i += DR_THREADS) s_cnt[i] = 0;
-  const uint32_t n_gtab = 2u * (uint32_t)dv.n_chrom + 2u;
-  for (uint32_t i = threadIdx.x; i < n_gtab; i += DR_THREADS) s_gtab[i] = dv.gtab[i];
   __syncthreads();
   const uint32_t cbits = (uint32_t)dv.cbits, cmask = (1u << cbits) - 1u;
+  const uint32_t stride = dv.stride, last = stride - 1u, sigmask = dv.nsig - 1u, n_chrom = (uint32_t)dv.n_chrom;
   const int64_t n = q.n_regions;
   const int64_t n_full = n / DR_TILE;
   const int lane = threadIdx.x & 31;
-  const ull K = (ull)rv.n_slots;
   bool overflowed = false;
-
-  // one query through everything the fast path cannot decide
-  auto slow = [&](int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t index) { dr_general(rv, c, s, e, (int)(int8_t)sbyte, index); };
-  // count one query in slot j of the "both" plane
-  auto bump = [&](uint32_t j) {
-    const uint32_t sh = (j & 3u) * 8u;
-    const uint32_t old = atomicAdd(&s_cnt[j >> 2], 1u << sh);
-    const uint32_t ob = (old >> sh) & 0xFFu;
-    if (ob == 127u) { atomicSub(&s_cnt[j >> 2], 128u << sh); dr_red64(dv.delta + j, 128ull); }
-    overflowed |= ob == 255u;
-  };
 
   uint4 nc, ns, ne;
   uint32_t nst;
@@ -137,63 +140,85 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       const int64_t first = next * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS;
       nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
     }
-    const int32_t c[DR_ITEMS] = {(int)cc.x, (int)cc.y, (int)cc.z, (int)cc.w};
+    const uint32_t c[DR_ITEMS] = {cc.x, cc.y, cc.z, cc.w};
     const int32_t s[DR_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
     const int32_t e[DR_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
     // strands: '+' = 0x2B, '-' = 0x2D.  xw has 0x00 / 0x06 in the bytes of '+' / '-' queries
     const uint32_t xw = stw ^ 0x2B2B2B2Bu;
-    const bool odd_strand = (xw & 0xF9F9F9F9u) != 0;                   // some strand other than '+'/'-': those items take the general path
-    uint32_t kind[DR_ITEMS];                                           // 0 fast, 1 nothing to count, 2 general path
-    uint32_t cell_s[DR_ITEMS], cell_e[DR_ITEMS];
+    uint32_t general = 0;                                              // bit i: item i takes the general path
+    if (xw & 0xF9F9F9F9u) {                                            // some strand other than '+'/'-'
+#pragma unroll
+      for (int i = 0; i < DR_ITEMS; i++) general |= ((xw >> (8 * i)) & 0xF9u) ? (1u << i) : 0u;
+    }
+    uint32_t base[DR_ITEMS];
     uint2 ent[DR_ITEMS];
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      const uint32_t ci = min((uint32_t)c[i], (uint32_t)dv.n_chrom);   // unknown chromosome -> an empty entry
-      const int2 g = s_gtab[2u * ci + ((xw >> (8 * i + 1)) & 1u)];
-      const int gmax = max(g.x, 0);
-      const bool addressable = !odd_strand || ((xw >> (8 * i)) & 0xF9u) == 0;
-      const bool valid = s[i] >= 1 && s[i] <= e[i];
-      const bool inside = (uint32_t)(s[i] - 1) < (uint32_t)gmax && e[i] <= gmax;
-      const bool nothing = valid && g.x >= 0 && (g.x == 0 || s[i] > g.x);           // no points in the group / start beyond the last one
-      kind[i] = !addressable ? 2u : (valid && inside) ? 0u : nothing ? 1u : 2u;
-      cell_s[i] = (uint32_t)g.y + ((uint32_t)s[i] >> cbits);
-      cell_e[i] = (uint32_t)g.y + ((uint32_t)e[i] >> cbits);
-      if (kind[i] != 0u) { cell_s[i] = 0; cell_e[i] = 0; }
+      if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
+      base[i] = (min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask)) * stride;   // unknown chromosome -> the all-"nothing" block
+      ent[i] = dr_gather<NA>(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
     }
-#pragma unroll
-    for (int i = 0; i < DR_ITEMS; i++) ent[i] = dr_gather<NA>(dv.cells + cell_s[i]);
-    uint32_t jS[DR_ITEMS], jE[DR_ITEMS];
+    uint32_t jS[DR_ITEMS], jE[DR_ITEMS], j0E[DR_ITEMS];
+    uint32_t scan = 0;
+    uint32_t skip = general;                                           // bit i: item i is not counted by the fast path
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
       uint2 ee = ent[i];
-      if (cell_e[i] != cell_s[i]) ee = dr_gather<NA>(dv.cells + cell_e[i]);          // a read that crosses a cell boundary (~1 %)
-      if (kind[i] == 0u && (((ent[i].x | ee.x) >> 24) & 1u)) kind[i] = 2u;           // more than three points in a cell
-      jS[i] = (ent[i].x & 0xFFFFFFu) + dr_below(ent[i], (uint32_t)s[i] & cmask);
-      jE[i] = (ee.x & 0xFFFFFFu) + dr_below(ee, (uint32_t)e[i] & cmask);
+      if (((uint32_t)s[i] ^ (uint32_t)e[i]) >> cbits) {                // a read that crosses a cell boundary (~1 %)
+        ee = dr_gather<NA>(dv.cells + base[i] + min((uint32_t)e[i] >> cbits, last));
+      }
+      const uint32_t fl = ent[i].x | (ee.x & (DR_GENERAL | DR_SCAN));   // "nothing" is about the START: a stop beyond the last point lands in the sentinel slot
+      general |= (fl & DR_GENERAL) ? (1u << i) : 0u;                   // a group whose points are all <= 0
+      skip |= (fl & (DR_GENERAL | DR_NOTHING)) ? (1u << i) : 0u;
+      jS[i] = (ent[i].x & 0xFFFFFFu) + dr_below(ent[i].y, (uint32_t)s[i] & cmask);
+      jE[i] = (ee.x & 0xFFFFFFu) + dr_below(ee.y, (uint32_t)e[i] & cmask);
+      scan |= (fl & DR_SCAN) ? (1u << i) : 0u;
+      j0E[i] = ee.x & 0xFFFFFFu;
+    }
+    if (scan) {                                                        // more than two points in one of the cells: walk them
+#pragma unroll
+      for (int i = 0; i < DR_ITEMS; i++)
+        if ((scan >> i) & 1u) {
+          jS[i] = dr_scan(rv.points, ent[i].x & 0xFFFFFFu, s[i]);
+          jE[i] = dr_scan(rv.points, max(jS[i], j0E[i]), e[i]);
+        }
     }
     // position-sorted input: the warp's 128 queries in one slot leave as one reduction
     const uint32_t lead = __shfl_sync(0xffffffffu, jS[0], 0);
-    bool same = true;
+    bool same = skip == 0u;
 #pragma unroll
-    for (int i = 0; i < DR_ITEMS; i++) same = same && kind[i] == 0u && jS[i] == lead && jE[i] == lead;
+    for (int i = 0; i < DR_ITEMS; i++) same = same && jS[i] == lead && jE[i] == lead;
     if (__all_sync(0xffffffffu, same)) {
       if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS));
       continue;
     }
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      if (kind[i] == 0u) {
-        if (jS[i] == jE[i]) bump(jS[i]);
-        else { dr_red64(dv.delta + H_SCNT * K + jS[i], 1ull); dr_red64(dv.delta + H_ECNT * K + jE[i], 1ull); }
-      } else if (kind[i] == 2u) {
-        slow(c[i], s[i], e[i], (stw >> (8 * i)) & 0xFFu, q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
+      if (!((skip >> i) & 1u)) {
+        if (jS[i] == jE[i]) {                                          // one query in slot jS of the "both" plane
+          const uint32_t sh = (jS[i] & 3u) * 8u;
+          const uint32_t ob = (atomicAdd(&s_cnt[jS[i] >> 2], 1u << sh) >> sh) & 0xFFu;
+          if (ob >= 127u) {
+            if (ob == 127u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull); }
+            overflowed |= ob == 255u;
+          }
+        } else {
+          dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], 1ull);
+          dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], 1ull);
+        }
       }
+    }
+    if (general) {
+#pragma unroll
+      for (int i = 0; i < DR_ITEMS; i++)
+        if ((general >> i) & 1u)
+          dr_general(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
     }
   }
   // the last, partial tile: general path
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
     for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
-      slow(q.chrom[r], q.start[r], q.stop[r], (uint32_t)(uint8_t)q.strand[r], q.index_base + r);
+      dr_general(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
   __syncthreads();
@@ -245,11 +270,10 @@ int upload_d(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
 struct gtb_direct_state {
   bool ready = false, failed = false, off = false;
   int cbits = 0;
-  uint32_t n_cells = 0, n_words = 0;
+  uint32_t n_cells = 0, n_words = 0, nsig = 2, stride = 0;
   unsigned grid = 0;
   bool no_allocate = false;
   size_t smem = 0;
-  dbuf<int2> d_gtab;
   dbuf<uint2> d_cells;
   dbuf<uint32_t> d_cta_counts, d_flag;
   dbuf<ull> d_delta;
@@ -266,64 +290,60 @@ int gtb_direct_prepare(gtb_index *ix) {
   if (ix->op != GTB_OP_COUNT || ix->n_slots == 0 || ix->n_slots >= (1 << 24)) return GTB_ERR_UNSUPPORTED;
   const int G = ix->n_groups;
   const uint32_t n_words = (uint32_t)(((ix->n_slots + 3) / 4 + 3) & ~(int64_t)3);
-  const size_t smem = (size_t)n_words * 4 + ((size_t)2 * std::max(ix->n_chrom, 1) + 2) * 8;
+  const size_t smem = (size_t)n_words * 4;
   // The gathers need L1 to track their misses in: measured (profiles/microbench/gather_rate_b200.txt), a gather costs 1.02
   // SM-cycles with up to 192 KB of the SM's 256 KB carved out as shared memory and 1.85 with 224 KB.
   if (smem > std::min<size_t>(ctx->smem_optin, (size_t)192 * 1024)) return GTB_ERR_UNSUPPORTED;
   // largest evaluation point per group (0: none, -1: only points <= 0)
   std::vector<int32_t> gsize((size_t)std::max(G, 1), 0);
+  int32_t gmax = 0;
   uint64_t span = 0;
   for (int g = 0; g < G; g++) {
     const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1];
     if (ge - gb >= 2) { const int32_t mx = ix->h_points[ge - 2]; gsize[g] = mx >= 1 ? mx : -1; }
-    if (gsize[g] > 0) span += (uint64_t)gsize[g] + 1;
+    if (gsize[g] > 0) { span += (uint64_t)gsize[g] + 1; gmax = std::max(gmax, gsize[g]); }
   }
   if (span == 0) return GTB_ERR_UNSUPPORTED;
-  int cbits = 12;
-  if (const char *env = getenv("GTB_DIRECT_CELL_BITS")) cbits = std::max(4, std::min(12, atoi(env)));
-  std::vector<uint32_t> gbase((size_t)std::max(G, 1), 0);
-  uint64_t cells = 0;
-  for (int g = 0; g < G; g++) {
-    gbase[g] = (uint32_t)cells;
-    if (gsize[g] > 0) cells += ((uint64_t)gsize[g] >> cbits) + 1;
-  }
-  if (cells * sizeof(uint2) > DR_TABLE_BYTES_MAX && !getenv("GTB_DIRECT_CELL_BITS")) return GTB_ERR_UNSUPPORTED;   // the table would fall out of L2's fast range
-  if (cells >= ((uint64_t)1 << 31)) return GTB_ERR_UNSUPPORTED;
-  std::vector<uint2> tab((size_t)cells);
-  size_t many = 0;
-  for (int g = 0; g < G; g++) {
-    if (gsize[g] <= 0) continue;
-    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1] - 1;       // [gb, ge): the group's points without the sentinel
-    const uint64_t nc = ((uint64_t)gsize[g] >> cbits) + 1;
-    int32_t j = gb;
-    for (uint64_t x = 0; x < nc; x++) {
-      const int64_t lo = (int64_t)x << cbits, hi = lo + ((int64_t)1 << cbits);
-      while (j < ge && ix->h_points[j] < lo) j++;
-      uint32_t p[3] = {DR_NOPOINT, DR_NOPOINT, DR_NOPOINT};
-      int32_t t = j, cnt = 0;
-      while (t < ge && ix->h_points[t] < hi) { if (cnt < 3) p[cnt] = (uint32_t)(ix->h_points[t] - lo); cnt++; t++; }
-      // (a real point at offset 0xFFF looks like "no point" and behaves like it too: no offset is larger, so it is never below one)
-      const bool general = cnt > 3;
-      many += general ? 1 : 0;
-      uint2 ent;
-      ent.x = (uint32_t)j | (general ? 1u << 24 : 0u) | ((p[2] >> 8) << 28);
-      ent.y = p[0] | (p[1] << 12) | ((p[2] & 0xFFu) << 24);
-      tab[(size_t)gbase[g] + x] = ent;
-    }
-  }
-  std::vector<int2> gtab((size_t)2 * std::max(ix->n_chrom, 1) + 2, make_int2(0, 0));
+  // cell width: the cells that queries can touch (those up to each group's last point) should stay well inside L2
+  int cbits = 10;
+  while (cbits < 14 && (span >> cbits) * sizeof(uint2) > DR_TABLE_BYTES_TARGET) cbits++;
+  if (const char *env = getenv("GTB_DIRECT_CELL_BITS")) cbits = std::max(4, std::min(14, atoi(env)));
   const int cp = ix->h_class_of[(uint8_t)'+'], cm = ix->h_class_of[(uint8_t)'-'];
+  const uint32_t nsig = cp == cm ? 1u : 2u;
+  const uint64_t stride = ((uint64_t)gmax >> cbits) + 2;                // cells up to the largest last point, and one "nothing" cell to clamp to
+  const uint64_t blocks = ((uint64_t)ix->n_chrom + 1) * nsig;
+  const uint64_t cells = blocks * stride;
+  if (cells * sizeof(uint2) > ((size_t)1 << 30) || cells >= ((uint64_t)1 << 31)) return GTB_ERR_UNSUPPORTED;
+  std::vector<uint2> tab((size_t)cells, make_uint2(DR_NOTHING, 0xFFFFFFFFu));      // no such group: nothing to count
+  size_t many = 0;
   for (int c = 0; c < ix->n_chrom; c++)
-    for (int sgn = 0; sgn < 2; sgn++) {
-      const int cls = sgn ? cm : cp;
+    for (uint32_t sg = 0; sg < nsig; sg++) {
+      const int cls = sg ? cm : cp;
       if (cls < 0) continue;
       const int g = c * ix->n_class + cls;
-      gtab[(size_t)2 * c + sgn] = make_int2(gsize[g], (int)gbase[g]);
+      uint2 *blk = tab.data() + ((size_t)c * nsig + sg) * stride;
+      const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1] - 1;     // [gb, ge): the group's points without the sentinel
+      if (ix->h_goff[g + 1] == gb || gsize[g] == 0) continue;           // no points: nothing to count
+      if (gsize[g] < 0) {                                               // only points <= 0: left to the general path
+        for (uint64_t x = 0; x < stride; x++) blk[x] = make_uint2(DR_GENERAL, 0xFFFFFFFFu);
+        continue;
+      }
+      const uint64_t nc = ((uint64_t)gsize[g] >> cbits) + 1;            // cells that hold a point or precede one
+      int32_t j = gb;
+      for (uint64_t x = 0; x < stride; x++) {
+        if (x >= nc) { blk[x] = make_uint2((uint32_t)ge | DR_NOTHING, 0xFFFFFFFFu); continue; }   // wholly beyond the last point: the sentinel slot
+        const int64_t lo = (int64_t)x << cbits, hi = lo + ((int64_t)1 << cbits);
+        while (j < ge && ix->h_points[j] < lo) j++;
+        uint32_t p[2] = {DR_NOPOINT, DR_NOPOINT};
+        int32_t t = j, cnt = 0;
+        while (t < ge && ix->h_points[t] < hi) { if (cnt < 2) p[cnt] = (uint32_t)(ix->h_points[t] - lo); cnt++; t++; }
+        many += cnt > 2 ? 1 : 0;
+        blk[x] = make_uint2((uint32_t)j | (cnt > 2 ? DR_SCAN : 0u), p[0] | (p[1] << 16));
+      }
     }
-  ds->cbits = cbits; ds->n_cells = (uint32_t)cells; ds->n_words = n_words; ds->smem = smem;
+  ds->cbits = cbits; ds->n_cells = (uint32_t)cells; ds->n_words = n_words; ds->smem = smem; ds->nsig = nsig; ds->stride = (uint32_t)stride;
   ds->no_allocate = getenv("GTB_DIRECT_NO_ALLOCATE") != nullptr;      // measured: the gathers run faster when they allocate in L1 (0.585 vs 0.682 ms)
   ds->grid = (unsigned)ctx->sm_count;
-  GTB_TRY(upload_d(ctx, ds->d_gtab, gtab));
   GTB_TRY(upload_d(ctx, ds->d_cells, tab));
   GTB_TRY(ds->d_cta_counts.reserve(ctx, (size_t)ds->grid * n_words));
   GTB_TRY(ds->d_delta.reserve(ctx, (size_t)H_PLANES_COUNT * ix->n_slots));
@@ -332,8 +352,8 @@ int gtb_direct_prepare(gtb_index *ix) {
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   if (getenv("GTB_DEBUG_DIRECT"))
-    fprintf(stderr, "[gtb direct] slots %lld cells %llu (2^%d bp, %.1f MB) general cells %zu smem %zu\n", (long long)ix->n_slots,
-            (unsigned long long)cells, cbits, cells * 8 / 1e6, many, smem);
+    fprintf(stderr, "[gtb direct] slots %lld cells %llu (2^%d bp, %u per block, %.1f MB allocated, %.1f MB within reach) general cells %zu smem %zu\n",
+            (long long)ix->n_slots, (unsigned long long)cells, cbits, (unsigned)stride, cells * 8 / 1e6, (double)(span >> cbits) * 8 / 1e6, many, smem);
 
   ds->ready = true; ds->failed = false;
   return GTB_OK;
@@ -366,7 +386,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
   rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p;
   DirectView dv;
-  dv.cbits = ds->cbits; dv.n_chrom = ix->n_chrom; dv.n_class = ix->n_class; dv.gtab = ds->d_gtab.p; dv.cells = ds->d_cells.p;
+  dv.cbits = ds->cbits; dv.n_chrom = ix->n_chrom; dv.nsig = ds->nsig; dv.stride = ds->stride; dv.cells = ds->d_cells.p;
   dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
@@ -390,7 +410,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
 void gtb_direct_destroy(gtb_index *ix) {
   gtb_direct_state *ds = ix->direct;
   if (!ds) return;
-  ds->d_gtab.release(); ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
+  ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
   delete ds;
   ix->direct = nullptr;
 }
