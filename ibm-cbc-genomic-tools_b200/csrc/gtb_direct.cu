@@ -115,8 +115,8 @@ __device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uin
 template <bool NA>
 __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
                                                                        const __grid_constant__ DirectView dv) {
-  extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word
-  for (uint32_t i = threadIdx.x; i < dv.n_words; i += DR_THREADS) s_cnt[i] = 0;
+  extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word, then one dummy word per lane
+  for (uint32_t i = threadIdx.x; i < dv.n_words + 32u; i += DR_THREADS) s_cnt[i] = 0;
   __syncthreads();
   const uint32_t cbits = (uint32_t)dv.cbits, cmask = (1u << cbits) - 1u;
   const uint32_t stride = dv.stride, last = stride - 1u, sigmask = dv.nsig - 1u, n_chrom = (uint32_t)dv.n_chrom;
@@ -192,12 +192,20 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS));
       continue;
     }
+    // the four shared atomics go out back to back (an item with nothing for the "both" plane adds 0 to a word of its lane's own);
+    // only then are the returned bytes looked at
+    uint32_t old[DR_ITEMS];
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++) {
+      const bool both = !((skip >> i) & 1u) && jS[i] == jE[i];
+      old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((jS[i] & 3u) * 8u) : 0u);
+    }
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!((skip >> i) & 1u)) {
         if (jS[i] == jE[i]) {                                          // one query in slot jS of the "both" plane
           const uint32_t sh = (jS[i] & 3u) * 8u;
-          const uint32_t ob = (atomicAdd(&s_cnt[jS[i] >> 2], 1u << sh) >> sh) & 0xFFu;
+          const uint32_t ob = (old[i] >> sh) & 0xFFu;
           if (ob >= 127u) {
             if (ob == 127u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull); }
             overflowed |= ob == 255u;
@@ -230,23 +238,30 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 // byte counter overflowed somewhere in this batch (flag == the batch's generation), only clears them and then sends every
 // query through the general path straight into the histogram planes (nothing else touches those in that case).
 __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, QueryView q, RankView rv_hist, int64_t n_slots, unsigned rows) {
+  // a block = 32 counter words x 8 groups of rows: each thread sums its share of the rows of one word (coalesced across the warp),
+  // shared memory joins the eight partial sums, the first warp updates the planes
+  __shared__ uint32_t s_part[8][32][4];
   ull *hist = rv_hist.hist;
   const bool discard = dv.flag[0] == dv.gen;
-  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < dv.n_words) {
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (!discard)
-      for (unsigned r = 0; r < rows; r++) {
-        const uint32_t v = dv.cta_counts[(size_t)r * dv.n_words + w];
-        a0 += v & 0xFFu; a1 += (v >> 8) & 0xFFu; a2 += (v >> 16) & 0xFFu; a3 += v >> 24;
-      }
-    const uint32_t acc[4] = {a0, a1, a2, a3};
-    for (int b = 0; b < 4; b++) {
-      const int64_t j = (int64_t)w * 4 + b;
-      if (j >= n_slots) break;
+  const uint32_t lane = threadIdx.x & 31u, grp = threadIdx.x >> 5;
+  const uint32_t w = blockIdx.x * 32u + lane;
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (!discard && w < dv.n_words)
+    for (unsigned r = grp; r < rows; r += 8) {
+      const uint32_t v = dv.cta_counts[(size_t)r * dv.n_words + w];
+      a0 += v & 0xFFu; a1 += (v >> 8) & 0xFFu; a2 += (v >> 16) & 0xFFu; a3 += v >> 24;
+    }
+  s_part[grp][lane][0] = a0; s_part[grp][lane][1] = a1; s_part[grp][lane][2] = a2; s_part[grp][lane][3] = a3;
+  __syncthreads();
+  if (threadIdx.x < 128) {                                             // thread t: slot (t & 3) of word (t >> 2) of this block
+    const uint32_t wl = threadIdx.x >> 2, b = threadIdx.x & 3u;
+    const int64_t j = ((int64_t)blockIdx.x * 32 + wl) * 4 + b;
+    if (j < n_slots) {
+      uint32_t acc = 0;
+      for (int g = 0; g < 8; g++) acc += s_part[g][wl][b];
       for (int p = 0; p < H_PLANES_COUNT; p++) {
         const ull d = dv.delta[(int64_t)p * n_slots + j];
-        const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc[b] : 0ull);
+        const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc : 0ull);
         if (add) hist[(int64_t)p * n_slots + j] += add;
         if (d) dv.delta[(int64_t)p * n_slots + j] = 0;
       }
@@ -290,7 +305,7 @@ int gtb_direct_prepare(gtb_index *ix) {
   if (ix->op != GTB_OP_COUNT || ix->n_slots == 0 || ix->n_slots >= (1 << 24)) return GTB_ERR_UNSUPPORTED;
   const int G = ix->n_groups;
   const uint32_t n_words = (uint32_t)(((ix->n_slots + 3) / 4 + 3) & ~(int64_t)3);
-  const size_t smem = (size_t)n_words * 4;
+  const size_t smem = (size_t)n_words * 4 + 32 * 4;
   // The gathers need L1 to track their misses in: measured (profiles/microbench/gather_rate_b200.txt), a gather costs 1.02
   // SM-cycles with up to 192 KB of the SM's 256 KB carved out as shared memory and 1.85 with 224 KB.
   if (smem > std::min<size_t>(ctx->smem_optin, (size_t)192 * 1024)) return GTB_ERR_UNSUPPORTED;
@@ -402,7 +417,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   GTB_TRY(gtb_check_launch(ctx));
   RankView rv_hist = rv;
   rv_hist.hist = ix->d_hist.p;
-  GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel, (ds->n_words + 255) / 256, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
+  GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   ds->queries_since_check += q.n_regions;
   return gtb_check_launch(ctx);
 }
