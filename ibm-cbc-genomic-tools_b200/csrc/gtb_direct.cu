@@ -49,6 +49,7 @@ struct DirectView {
   uint32_t *cta_counts;             // [grid][n_words]
   ull *delta;                       // [3][n_slots] this batch's contributions that did not go through the byte counters
   uint32_t *flag;                   // [0] generation of the last batch in which a byte counter overflowed (that batch is discarded and replayed)
+                                    // [1] coverage: queries whose length was not the batch's common one (a global reduction each)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
 };
 constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
@@ -74,6 +75,7 @@ __device__ __forceinline__ uint2 dr_gather(const uint2 *p) {
 
 // The general path for one query: the reference's admission rules, then the rank step (gtb_rank_device.cuh).
 // Same decisions as admit_query + rank_accumulate_kernel of gtb_overlap.cu for a single-interval, unweighted query.
+template <bool COVERAGE>
 __device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t qs, int32_t qe, int sbyte, int64_t index) {
   if ((uint32_t)c >= (uint32_t)rv.n_chrom || !rv.chrom_present[c]) return;           // :5719-5720
   if (qe <= 0) { report_error(rv.err, index, GTB_ERR_QUERY_STOP_NONPOSITIVE); return; }   // :5740
@@ -82,7 +84,7 @@ __device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t q
   if (cls < 0) return;                                                              // no index region carries this strand, :5229
   const int g = c * rv.n_class + cls;
   const int gb = rv.goff[g], ge = rv.goff[g + 1];
-  if (ge > gb) rank_item<false>(rv, gb, ge, qs, qe, 1);
+  if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, 1);
 }
 
 // number of the cell's (at most two) points that lie below offset `off` (an absent point is 0xFFFF and never does)
@@ -112,7 +114,11 @@ __device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uin
 // The hot loop holds no table but the cells: every (chromosome, strand) has a block of `stride` cells, so the cell of a
 // coordinate is pure arithmetic, and what used to be per-group knowledge (no such group, beyond the last point, too many
 // points) is two flag bits of the cell entry.
-template <bool NA>
+//
+// COVERAGE: the "both" plane takes the query's length instead of 1.  Reads of a sequencing run mostly share one length, so the
+// byte counters count the queries whose length equals the batch's first query's and the commit kernel multiplies; a query of
+// another length costs a global reduction (and is counted, so that the host can leave the engine if they are many).
+template <bool COVERAGE>
 __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
                                                                        const __grid_constant__ DirectView dv) {
   extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word, then one dummy word per lane
@@ -123,6 +129,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   const int64_t n = q.n_regions;
   const int64_t n_full = n / DR_TILE;
   const int lane = threadIdx.x & 31;
+  const uint32_t len0m1 = COVERAGE && n > 0 ? (uint32_t)(q.stop[0] - q.start[0]) : 0u;   // the common length - 1
+  const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)len0m1 + 1ull : 1ull;                // what one counted query is worth in the "both" plane
+  uint32_t odd = 0;                                                    // COVERAGE: queries of another length
   bool overflowed = false;
 
   uint4 nc, ns, ne;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
       base[i] = (min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask)) * stride;   // unknown chromosome -> the all-"nothing" block
-      ent[i] = dr_gather<NA>(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
+      ent[i] = dr_gather<false>(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
     }
     uint32_t jS[DR_ITEMS], jE[DR_ITEMS], j0E[DR_ITEMS];
     uint32_t scan = 0;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     for (int i = 0; i < DR_ITEMS; i++) {
       uint2 ee = ent[i];
       if (((uint32_t)s[i] ^ (uint32_t)e[i]) >> cbits) {                // a read that crosses a cell boundary (~1 %)
-        ee = dr_gather<NA>(dv.cells + base[i] + min((uint32_t)e[i] >> cbits, last));
+        ee = dr_gather<false>(dv.cells + base[i] + min((uint32_t)e[i] >> cbits, last));
       }
       const uint32_t fl = ent[i].x | (ee.x & (DR_GENERAL | DR_SCAN));   // "nothing" is about the START: a stop beyond the last point lands in the sentinel slot
       general |= (fl & DR_GENERAL) ? (1u << i) : 0u;                   // a group whose points are all <= 0
@@ -187,9 +196,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     const uint32_t lead = __shfl_sync(0xffffffffu, jS[0], 0);
     bool same = skip == 0u;
 #pragma unroll
-    for (int i = 0; i < DR_ITEMS; i++) same = same && jS[i] == lead && jE[i] == lead;
+    for (int i = 0; i < DR_ITEMS; i++) same = same && jS[i] == lead && jE[i] == lead && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
     if (__all_sync(0xffffffffu, same)) {
-      if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS));
+      if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS) * unit);
       continue;
     }
     // the four shared atomics go out back to back (an item with nothing for the "both" plane adds 0 to a word of its lane's own);
@@ -197,22 +206,29 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     uint32_t old[DR_ITEMS];
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      const bool both = !((skip >> i) & 1u) && jS[i] == jE[i];
+      const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
       old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((jS[i] & 3u) * 8u) : 0u);
     }
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!((skip >> i) & 1u)) {
-        if (jS[i] == jE[i]) {                                          // one query in slot jS of the "both" plane
+        if (jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1)) {   // one query in slot jS of the "both" plane
           const uint32_t sh = (jS[i] & 3u) * 8u;
           const uint32_t ob = (old[i] >> sh) & 0xFFu;
           if (ob >= 127u) {
-            if (ob == 127u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull); }
+            if (ob == 127u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull * unit); }
             overflowed |= ob == 255u;
           }
+        } else if (COVERAGE && jS[i] == jE[i]) {                       // a query of another length
+          dr_red64(dv.delta + jS[i], (ull)((int64_t)e[i] - (int64_t)s[i] + 1));
+          odd++;
         } else {
           dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], 1ull);
           dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], 1ull);
+          if (COVERAGE) {
+            dr_red64(dv.delta + (ull)H_SSUM * (ull)rv.n_slots + jS[i], (ull)(int64_t)s[i]);
+            dr_red64(dv.delta + (ull)H_ESUM * (ull)rv.n_slots + jE[i], (ull)(int64_t)e[i]);
+          }
         }
       }
     }
@@ -220,15 +236,16 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
         if ((general >> i) & 1u)
-          dr_general(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
+          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
     }
   }
   // the last, partial tile: general path
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
     for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
-      dr_general(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
+      dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
+  if (COVERAGE && odd) atomicAdd(dv.flag + 1, odd);
   __syncthreads();
   uint4 *row = reinterpret_cast<uint4 *>(dv.cta_counts + (size_t)blockIdx.x * dv.n_words);
   for (uint32_t i = threadIdx.x; i < dv.n_words / 4; i += DR_THREADS) row[i] = reinterpret_cast<const uint4 *>(s_cnt)[i];
@@ -237,6 +254,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 // Sums the CTAs' byte counters and the delta planes into the index's histogram planes and clears the delta planes -- or, if a
 // byte counter overflowed somewhere in this batch (flag == the batch's generation), only clears them and then sends every
 // query through the general path straight into the histogram planes (nothing else touches those in that case).
+template <bool COVERAGE>
 __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, QueryView q, RankView rv_hist, int64_t n_slots, unsigned rows) {
   // a block = 32 counter words x 8 groups of rows: each thread sums its share of the rows of one word (coalesced across the warp),
   // shared memory joins the eight partial sums, the first warp updates the planes
@@ -259,9 +277,11 @@ __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, Query
     if (j < n_slots) {
       uint32_t acc = 0;
       for (int g = 0; g < 8; g++) acc += s_part[g][wl][b];
-      for (int p = 0; p < H_PLANES_COUNT; p++) {
+      // COVERAGE: a counted query is worth the batch's common length (direct_count_kernel)
+      const ull unit = COVERAGE && q.n_regions > 0 ? (ull)(int64_t)(q.stop[0] - q.start[0]) + 1ull : 1ull;
+      for (int p = 0; p < (COVERAGE ? H_PLANES_COVERAGE : H_PLANES_COUNT); p++) {
         const ull d = dv.delta[(int64_t)p * n_slots + j];
-        const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc : 0ull);
+        const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc * unit : 0ull);
         if (add) hist[(int64_t)p * n_slots + j] += add;
         if (d) dv.delta[(int64_t)p * n_slots + j] = 0;
       }
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, Query
   if (!discard) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride)
-    dr_general(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
+    dr_general<COVERAGE>(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
 }
 
 template <typename T>
@@ -287,13 +307,12 @@ struct gtb_direct_state {
   int cbits = 0;
   uint32_t n_cells = 0, n_words = 0, nsig = 2, stride = 0;
   unsigned grid = 0;
-  bool no_allocate = false;
   size_t smem = 0;
   dbuf<uint2> d_cells;
   dbuf<uint32_t> d_cta_counts, d_flag;
   dbuf<ull> d_delta;
   int64_t queries_since_check = 0;
-  uint32_t gen = 0;
+  uint32_t gen = 0, odd_seen = 0;
 };
 
 int gtb_direct_prepare(gtb_index *ix) {
@@ -302,7 +321,7 @@ int gtb_direct_prepare(gtb_index *ix) {
   if (!ix->direct) ix->direct = new gtb_direct_state();
   gtb_direct_state *ds = ix->direct;
   ds->failed = true;                                                    // until proven otherwise
-  if (ix->op != GTB_OP_COUNT || ix->n_slots == 0 || ix->n_slots >= (1 << 24)) return GTB_ERR_UNSUPPORTED;
+  if (ix->n_slots == 0 || ix->n_slots >= (1 << 24)) return GTB_ERR_UNSUPPORTED;
   const int G = ix->n_groups;
   const uint32_t n_words = (uint32_t)(((ix->n_slots + 3) / 4 + 3) & ~(int64_t)3);
   const size_t smem = (size_t)n_words * 4 + 32 * 4;
@@ -357,13 +376,12 @@ int gtb_direct_prepare(gtb_index *ix) {
       }
     }
   ds->cbits = cbits; ds->n_cells = (uint32_t)cells; ds->n_words = n_words; ds->smem = smem; ds->nsig = nsig; ds->stride = (uint32_t)stride;
-  ds->no_allocate = getenv("GTB_DIRECT_NO_ALLOCATE") != nullptr;      // measured: the gathers run faster when they allocate in L1 (0.585 vs 0.682 ms)
   ds->grid = (unsigned)ctx->sm_count;
   GTB_TRY(upload_d(ctx, ds->d_cells, tab));
   GTB_TRY(ds->d_cta_counts.reserve(ctx, (size_t)ds->grid * n_words));
-  GTB_TRY(ds->d_delta.reserve(ctx, (size_t)H_PLANES_COUNT * ix->n_slots));
+  GTB_TRY(ds->d_delta.reserve(ctx, (size_t)ix->planes * ix->n_slots));
   GTB_TRY(ds->d_flag.reserve(ctx, 2));
-  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_delta.p, 0, (size_t)H_PLANES_COUNT * ix->n_slots * sizeof(ull), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_delta.p, 0, (size_t)ix->planes * ix->n_slots * sizeof(ull), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   if (getenv("GTB_DEBUG_DIRECT"))
@@ -375,7 +393,7 @@ int gtb_direct_prepare(gtb_index *ix) {
 }
 
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
-  if (batch_multi || q.region_offset || q.weight || ix->op != GTB_OP_COUNT) return false;   // single-interval, unweighted count
+  if (batch_multi || q.region_offset || q.weight) return false;        // single-interval, unweighted batches
   if (q.n_regions >= ((int64_t)1 << 40)) return false;
   if ((((uintptr_t)q.chrom | (uintptr_t)q.start | (uintptr_t)q.stop) & 15) != 0 || ((uintptr_t)q.strand & 3) != 0) return false;   // 128-bit loads
   if (gtb_direct_prepare(ix) != GTB_OK) return false;
@@ -390,12 +408,15 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   // skew watchdog: a replayed batch means byte counters overflow on this input -- leave the field to the BUCKET engine from now on.
   // Checked at the first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
   if (ds->queries_since_check > 0 && (q.index_base == 0 || ds->queries_since_check >= ((int64_t)64 << 20))) {
-    uint32_t overflow_gen = 0;
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(&overflow_gen, ds->d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t seen[2] = {0, 0};                                          // overflow generation, odd-length queries so far
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(seen, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (overflow_gen != 0) ds->off = true;
+    if (seen[0] != 0) ds->off = true;
+    // coverage of reads of many lengths: each odd one is a global reduction -- the BUCKET engine does those better
+    if ((int64_t)(uint32_t)(seen[1] - ds->odd_seen) > ds->queries_since_check / 16) ds->off = true;
+    ds->odd_seen = seen[1];
     ds->queries_since_check = 0;
-    if (ds->off) return gtb_bucket_supported(ix, q, false) ? gtb_bucket_accumulate(ix, q) : gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine switched off");
+    if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
   }
   RankView rv;
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
@@ -407,17 +428,19 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   dv.gen = ds->gen;
   const int64_t tiles = q.n_regions / DR_TILE;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ds->grid, tiles));
-  if (ds->no_allocate) {
+  RankView rv_hist = rv;
+  rv_hist.hist = ix->d_hist.p;
+  if (ix->op == GTB_OP_COVERAGE) {
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
-    GTB_LAUNCH(ctx, "direct_count", direct_count_kernel<true>, grid, DR_THREADS, ds->smem, q, rv, dv);
+    GTB_LAUNCH(ctx, "direct_coverage", direct_count_kernel<true>, grid, DR_THREADS, ds->smem, q, rv, dv);
+    GTB_TRY(gtb_check_launch(ctx));
+    GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<true>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   } else {
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
     GTB_LAUNCH(ctx, "direct_count", direct_count_kernel<false>, grid, DR_THREADS, ds->smem, q, rv, dv);
+    GTB_TRY(gtb_check_launch(ctx));
+    GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<false>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   }
-  GTB_TRY(gtb_check_launch(ctx));
-  RankView rv_hist = rv;
-  rv_hist.hist = ix->d_hist.p;
-  GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   ds->queries_since_check += q.n_regions;
   return gtb_check_launch(ctx);
 }

@@ -119,6 +119,17 @@ def test_direct_engine_vs_oracle(gtb, ctx, oracle, seed, cell_k):
         got = ctx.overlap_count(q, idx, flags | ENGINES["direct"])
         assert np.array_equal(got, want), (flags, seed)
         assert np.array_equal(ctx.overlap_count(q, idx, flags | ENGINES["bucket"]), want)
+        # coverage: reads of every length (each one off the batch's common length is a reduction of its own) ...
+        rc, want, _ = oracle.coverage(q, idx, flags)
+        assert rc == 0
+        assert np.array_equal(ctx.overlap_coverage(q, idx, flags | ENGINES["direct"]), want), ("coverage", flags, seed)
+        # ... and mostly one length (the byte counters count, the commit multiplies)
+        fixed = {k: v.copy() for k, v in q.items()}
+        keep = rng.random(n) < 0.1
+        fixed["stop"] = np.where(keep, fixed["stop"], fixed["start"] + 36).astype(np.int32)
+        rc, want, _ = oracle.coverage(fixed, idx, flags)
+        assert rc == 0
+        assert np.array_equal(ctx.overlap_coverage(fixed, idx, flags | ENGINES["direct"]), want), ("coverage/fixed", flags, seed)
     bad = {k: v.copy() for k, v in q.items()}
     where = sorted(rng.choice(n, size=3, replace=False).tolist())
     bad["stop"][where[0]] = bad["start"][where[0]] - 1                   # start > stop
@@ -148,14 +159,15 @@ def test_direct_engine_counter_overflow_is_replayed(gtb, ctx, oracle):
     reads["stop"] = (reads["start"] + 49).astype(np.int32)
     dev = {k: torch.from_numpy(v).cuda() for k, v in reads.items()}
     for flags in (0, gtb.IGNORE_STRAND):
-        rc, want, _ = oracle.count(reads, regions, flags)
-        assert rc == 0
-        ix = gtb.Index(ctx, regions, gtb.OP_COUNT, flags | ENGINES["direct"])
-        for rep in range(3):
-            ix.reset()
-            ix.add_device(dev)
-            assert np.array_equal(ix.finish(), want), (flags, rep)
-        ix.close()
+        for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+            rc, want, _ = fn(reads, regions, flags)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, flags | ENGINES["direct"])
+            for rep in range(3):
+                ix.reset()
+                ix.add_device(dev)
+                assert np.array_equal(ix.finish(), want), (op, flags, rep)
+            ix.close()
 
 
 def test_negative_and_degenerate_coordinates(ctx, oracle, cell_k):
