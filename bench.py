@@ -310,14 +310,16 @@ def main():
     # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload (never measured
     # under the profiler here); only quoted when the batch size is the one that was captured
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
-            tr = json.load(f)
-        if tr.get("reads") == n and dom_name in tr:
-            traffic = tr[dom_name]["dram_bytes_read"] + tr[dom_name]["dram_bytes_write"]
-            traffic_src = tr["source"]
-    except Exception:
-        pass
+    for name in ("r1g_traffic.json", "r1e_traffic.json"):              # newest capture that knows this kernel
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)
+            if tr.get("reads") == n and dom_name in tr:
+                traffic = tr[dom_name]["dram_bytes_read"] + tr[dom_name]["dram_bytes_write"]
+                traffic_src = tr["source"]
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": dom_ms, "kernel_share_of_step": dom["total_ms"] / total_prof_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
