@@ -34,7 +34,7 @@
 namespace {
 
 constexpr int DR_THREADS = 1024;
-constexpr int DR_ITEMS = 4;
+constexpr int DR_ITEMS = 4;                                  // (the clustered-input test in the kernel spells the four items out)
 constexpr int DR_TILE = DR_THREADS * DR_ITEMS;
 constexpr uint32_t DR_NOPOINT = 0xFFFFu;
 constexpr size_t DR_TABLE_BYTES_TARGET = (size_t)13 << 20;     // cells that queries can touch: inside L2's fast range (<= 16 MB measured)
@@ -201,17 +201,32 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * DR_ITEMS) * unit);
       continue;
     }
+    // Clustered input (reads piled onto a few loci, e.g. the boundary reads a neighbouring genome shard hands over in one run):
+    // hundreds of adds would reach one byte before its first spill lands.  Neighbouring queries sharing a slot give such input
+    // away; the warp then looks for slots shared by eight or more of its lanes and sends ONE reduction for each of those.
+    uint32_t done = skip;                                              // bit i: item i needs no shared atomic
+    if (__any_sync(0xffffffffu, jS[0] == jS[1] || jS[1] == jS[2] || jS[2] == jS[3])) {
+#pragma unroll
+      for (int i = 0; i < DR_ITEMS; i++) {
+        const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
+        const uint32_t peers = __match_any_sync(0xffffffffu, both ? jS[i] : 0x80000000u | (uint32_t)lane);
+        if (both && __popc(peers) >= 8) {
+          if ((peers & ((1u << lane) - 1u)) == 0u) dr_red64(dv.delta + jS[i], (ull)__popc(peers) * unit);
+          done |= 1u << i;
+        }
+      }
+    }
     // the four shared atomics go out back to back (an item with nothing for the "both" plane adds 0 to a word of its lane's own);
     // only then are the returned bytes looked at
     uint32_t old[DR_ITEMS];
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
+      const bool both = !((done >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
       old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((jS[i] & 3u) * 8u) : 0u);
     }
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      if (!((skip >> i) & 1u)) {
+      if (!((done >> i) & 1u)) {
         if (jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1)) {   // one query in slot jS of the "both" plane
           const uint32_t sh = (jS[i] & 3u) * 8u;
           const uint32_t ob = (old[i] >> sh) & 0xFFu;
