@@ -3,8 +3,8 @@
 // The C ABI takes queries as 13 bytes per interval (int32 chrom, start, stop + int8 strand).  Over PCIe that is the
 // whole cost of an end-to-end call: the kernels need ~1 ms for 100 M reads, the copy ~24 ms.  Almost every real
 // batch is far more regular than the layout allows -- chromosome ids are small, reads are short, strands are '+'/'-' --
-// so a pool of host threads re-encodes each chunk into 8 bytes per interval while the previous chunk is on the wire:
-//     start (int32, as is)   +   meta = (stop - start) | chrom << 16 | (strand == '-') << 30
+// so a pool of host threads re-encodes each chunk into 5, 6 or 8 bytes per interval while the previous chunk is on the wire:
+//     start (int32, as is)   +   meta of 1, 2 or 4 bytes -- the widest: (stop - start) | chrom << 16 | (strand == '-') << 30
 // and a small device kernel expands it again next to the engine (gtb_overlap.cu: unpack_kernel).  A chunk holding
 // anything the packed form cannot express (chrom >= 16384, stop - start outside [0, 65535], a strand byte other than
 // '+'/'-') is sent in the plain layout instead, so results never depend on this path.
@@ -113,3 +113,67 @@ extern "C++" int gtb_ingest_pack(gtb_ingest *p, const int32_t *chrom, const int3
   });
   return bad.load() == 0;
 }
+
+// The narrower forms.  Two bytes per interval next to the start: stop - start < 256, chrom < 128
+//     meta16 = (stop - start) | chrom << 8 | (strand == '-') << 15
+// One byte: every interval of the chunk has the length of the first (what a sequencing run looks like), chrom < 128
+//     meta8 = chrom | (strand == '-') << 7
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+static uint32_t pack_slice16(const int32_t *__restrict__ chrom, const int32_t *__restrict__ start, const int32_t *__restrict__ stop,
+                             const int8_t *__restrict__ strand, int64_t n, uint16_t *__restrict__ meta) {
+  uint32_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const uint32_t c = (uint32_t)chrom[i];
+    const uint32_t d = (uint32_t)stop[i] - (uint32_t)start[i];
+    const uint32_t sb = (uint32_t)(uint8_t)strand[i];
+    const uint32_t minus = sb == (uint32_t)'-' ? 1u : 0u;
+    const uint32_t plus = sb == (uint32_t)'+' ? 1u : 0u;
+    bad |= (c >= 128u ? 1u : 0u) | (stop[i] < start[i] ? 1u : 0u) | (d >= 256u ? 1u : 0u) | ((plus | minus) ^ 1u);
+    meta[i] = (uint16_t)((d & 0xFFu) | ((c & 0x7Fu) << 8) | (minus << 15));
+  }
+  return bad;
+}
+
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+static uint32_t pack_slice8(const int32_t *__restrict__ chrom, const int32_t *__restrict__ start, const int32_t *__restrict__ stop,
+                            const int8_t *__restrict__ strand, int64_t n, uint32_t len0, uint8_t *__restrict__ meta) {
+  uint32_t bad = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const uint32_t c = (uint32_t)chrom[i];
+    const uint32_t d = (uint32_t)stop[i] - (uint32_t)start[i];
+    const uint32_t sb = (uint32_t)(uint8_t)strand[i];
+    const uint32_t minus = sb == (uint32_t)'-' ? 1u : 0u;
+    const uint32_t plus = sb == (uint32_t)'+' ? 1u : 0u;
+    bad |= (c >= 128u ? 1u : 0u) | (d != len0 ? 1u : 0u) | ((plus | minus) ^ 1u);
+    meta[i] = (uint8_t)((c & 0x7Fu) | (minus << 7));
+  }
+  return bad;
+}
+
+// Packs n queries into `width` bytes of meta per interval (1, 2 or 4; see above) with the pool; for width 1 *len0 receives the
+// common stop - start.  Returns 1 if every query fit.
+extern "C++" int gtb_ingest_pack_width(gtb_ingest *p, int width, const int32_t *chrom, const int32_t *start, const int32_t *stop,
+                                       const int8_t *strand, int64_t n, void *meta, int32_t *start_out, uint32_t *len0) {
+  if (n <= 0) return 1;
+  if (width == 4) return gtb_ingest_pack(p, chrom, start, stop, strand, n, (uint32_t *)meta, start_out);
+  const int threads = (int)p->workers.size();
+  const int64_t grain = 64 * 1024;
+  const int parts = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)threads * 4, (n + grain - 1) / grain));
+  const uint32_t common = (uint32_t)stop[0] - (uint32_t)start[0];
+  if (width == 1 && (stop[0] < start[0])) return 0;
+  if (len0) *len0 = common;
+  std::atomic<uint32_t> bad{0};
+  parallel_for(p, parts, [&](int part) {
+    const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
+    const uint32_t b = width == 2 ? pack_slice16(chrom + lo, start + lo, stop + lo, strand + lo, hi - lo, (uint16_t *)meta + lo)
+                                  : pack_slice8(chrom + lo, start + lo, stop + lo, strand + lo, hi - lo, common, (uint8_t *)meta + lo);
+    if (start_out) memcpy(start_out + lo, start + lo, (size_t)(hi - lo) * sizeof(int32_t));
+    if (b) bad.fetch_or(b, std::memory_order_relaxed);
+  });
+  return bad.load() == 0;
+}
+

@@ -24,6 +24,9 @@ int gtb_ingest_threads(const gtb_ingest *p);
 int gtb_ingest_pack(gtb_ingest *p, const int32_t *chrom, const int32_t *start, const int32_t *stop, const int8_t *strand, int64_t n,
                     uint32_t *meta, int32_t *start_out);
 
+int gtb_ingest_pack_width(gtb_ingest *p, int width, const int32_t *chrom, const int32_t *start, const int32_t *stop, const int8_t *strand,
+                          int64_t n, void *meta, int32_t *start_out, uint32_t *len0);
+
 struct gtb_pinned_slot {                   // pinned host staging for one packed chunk
   uint32_t *meta = nullptr;
   int32_t *start = nullptr;
@@ -54,6 +57,8 @@ struct gtb_ctx {
   int64_t h2d_bytes = 0, d2h_bytes = 0;        // bytes of query batches / results that crossed the host link
   double pack_rate = 0.0;                      // measured packing throughput of this context's pool, intervals/s (0: not yet known)
   int64_t pack_skipped = 0;                    // chunks sent raw because packing would have been the slower leg
+  int pack_width = 1;                          // bytes of meta per interval the next chunk tries first (1, 2, 4); widened when a chunk does not fit
+  int64_t pack_wide_chunks = 0;                // chunks since the width was last widened (a narrower form is retried now and then)
 };
 int gtb_ctx_ingest_ready(gtb_ctx *ctx, size_t n_intervals, gtb_pinned_slot **slot);   // gtb_ctx.cu
 

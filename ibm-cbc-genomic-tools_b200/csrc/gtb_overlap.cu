@@ -177,22 +177,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const 
   out[k] = total;
 }
 
-// Expands a packed chunk (start + meta, see gtb_ingest.cpp) into the SoA layout the engines read.
-__global__ void __launch_bounds__(256) unpack_kernel(int64_t n, const uint32_t *__restrict__ meta, const int32_t *__restrict__ start,
+// Expands a packed chunk (start + meta of W bytes, see gtb_ingest.cpp) into the SoA layout the engines read.
+template <int W>
+__device__ __forceinline__ void unpack_one(uint32_t m, uint32_t len0, int32_t s, int32_t &c, int32_t &e, uint32_t &sb) {
+  if (W == 4) { c = (int32_t)((m >> 16) & 0x3FFFu); e = s + (int32_t)(m & 0xFFFFu); sb = (m >> 30) ? 45u : 43u; }
+  if (W == 2) { c = (int32_t)((m >> 8) & 0x7Fu); e = s + (int32_t)(m & 0xFFu); sb = (m >> 15) ? 45u : 43u; }
+  if (W == 1) { c = (int32_t)(m & 0x7Fu); e = s + (int32_t)len0; sb = (m >> 7) ? 45u : 43u; }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) unpack_kernel(int64_t n, const void *__restrict__ meta_v, uint32_t len0, const int32_t *__restrict__ start,
                                                      int32_t *__restrict__ chrom, int32_t *__restrict__ stop, int8_t *__restrict__ strand) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    if (i + 4 <= n) {
-      const uint4 m = *reinterpret_cast<const uint4 *>(meta + i);
+    uint32_t m[4];
+    const int lim = (int)min((int64_t)4, n - i);
+    if (lim == 4) {
+      if (W == 4) { const uint4 v = *reinterpret_cast<const uint4 *>((const uint32_t *)meta_v + i); m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+      if (W == 2) { const uint2 v = *reinterpret_cast<const uint2 *>((const uint16_t *)meta_v + i); m[0] = v.x & 0xFFFFu; m[1] = v.x >> 16; m[2] = v.y & 0xFFFFu; m[3] = v.y >> 16; }
+      if (W == 1) { const uint32_t v = *reinterpret_cast<const uint32_t *>((const uint8_t *)meta_v + i); m[0] = v & 0xFFu; m[1] = (v >> 8) & 0xFFu; m[2] = (v >> 16) & 0xFFu; m[3] = v >> 24; }
       const int4 s = *reinterpret_cast<const int4 *>(start + i);
-      *reinterpret_cast<int4 *>(chrom + i) = make_int4((m.x >> 16) & 0x3FFF, (m.y >> 16) & 0x3FFF, (m.z >> 16) & 0x3FFF, (m.w >> 16) & 0x3FFF);
-      *reinterpret_cast<int4 *>(stop + i) = make_int4(s.x + (int)(m.x & 0xFFFF), s.y + (int)(m.y & 0xFFFF), s.z + (int)(m.z & 0xFFFF), s.w + (int)(m.w & 0xFFFF));
-      const uint32_t b = ((m.x >> 30) ? 45u : 43u) | (((m.y >> 30) ? 45u : 43u) << 8) | (((m.z >> 30) ? 45u : 43u) << 16) | (((m.w >> 30) ? 45u : 43u) << 24);
-      *reinterpret_cast<uint32_t *>(strand + i) = b;
+      int32_t c[4], e[4];
+      uint32_t sb[4];
+      unpack_one<W>(m[0], len0, s.x, c[0], e[0], sb[0]); unpack_one<W>(m[1], len0, s.y, c[1], e[1], sb[1]);
+      unpack_one<W>(m[2], len0, s.z, c[2], e[2], sb[2]); unpack_one<W>(m[3], len0, s.w, c[3], e[3], sb[3]);
+      *reinterpret_cast<int4 *>(chrom + i) = make_int4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<int4 *>(stop + i) = make_int4(e[0], e[1], e[2], e[3]);
+      *reinterpret_cast<uint32_t *>(strand + i) = sb[0] | (sb[1] << 8) | (sb[2] << 16) | (sb[3] << 24);
     } else {
       for (int64_t j = i; j < n; j++) {
-        const uint32_t m = meta[j];
-        chrom[j] = (m >> 16) & 0x3FFF; stop[j] = start[j] + (int)(m & 0xFFFF); strand[j] = (m >> 30) ? '-' : '+';
+        const uint32_t mj = W == 4 ? ((const uint32_t *)meta_v)[j] : W == 2 ? (uint32_t)((const uint16_t *)meta_v)[j] : (uint32_t)((const uint8_t *)meta_v)[j];
+        int32_t c, e;
+        uint32_t sb;
+        unpack_one<W>(mj, len0, start[j], c, e, sb);
+        chrom[j] = c; stop[j] = e; strand[j] = (int8_t)sb;
       }
     }
   }
@@ -528,6 +546,8 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     // Packed path (single-interval, unweighted chunks): host threads re-encode 13 B/interval into 8 B/interval in pinned
     // staging while the previous chunk is on the wire; unpack_kernel expands it next to the engine.
     bool packed = false;
+    int pack_w = 4;
+    uint32_t pack_len0 = 0;
     gtb_pinned_slot *slot = nullptr;
     // Packing pays only while the pool re-encodes faster than the link would move the 5 bytes it saves: 13 B/interval at
     // ~52 GB/s is 4 G intervals/s.  With several ranks per host (few threads each, shared memory bandwidth) it does not, and
@@ -537,19 +557,26 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
       cudaPointerAttributes attr;
       const bool start_is_pinned = cudaPointerGetAttributes(&attr, queries->start + i0) == cudaSuccess && attr.type == cudaMemoryTypeHost;
       cudaGetLastError();
+      // narrowest form first: 1 byte of meta per interval (one read length, < 128 chromosomes), then 2, then 4; a chunk that
+      // does not fit widens the form for the chunks after it, and a narrower one is tried again every 64 chunks
+      if (ctx->pack_width > 1 && ++ctx->pack_wide_chunks >= 64) { ctx->pack_width = 1; ctx->pack_wide_chunks = 0; }
       const auto t0 = std::chrono::steady_clock::now();
-      packed = gtb_ingest_pack(ctx->ingest, queries->chrom + i0, queries->start + i0, queries->stop + i0, queries->strand + i0, (int64_t)ni,
-                               slot->meta, start_is_pinned ? nullptr : slot->start) != 0;
+      for (int width = ctx->pack_width; width <= 4 && !packed; width *= 2) {
+        packed = gtb_ingest_pack_width(ctx->ingest, width, queries->chrom + i0, queries->start + i0, queries->stop + i0, queries->strand + i0,
+                                       (int64_t)ni, slot->meta, start_is_pinned ? nullptr : slot->start, &pack_len0) != 0;
+        if (packed) pack_w = width;
+        else if (width < 4) { ctx->pack_width = width * 2; ctx->pack_wide_chunks = 0; }
+      }
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       if (dt > 0) ctx->pack_rate = ctx->pack_rate == 0.0 ? (double)ni / dt : 0.5 * ctx->pack_rate + 0.5 * (double)ni / dt;
       if (packed) {
         GTB_TRY(st.meta.reserve(ctx, ni));
         GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, start_is_pinned ? queries->start + i0 : slot->start, ni * 4, cudaMemcpyHostToDevice, cs));
-        GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.meta.p, slot->meta, ni * 4, cudaMemcpyHostToDevice, cs));
+        GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.meta.p, slot->meta, ni * (size_t)pack_w, cudaMemcpyHostToDevice, cs));
         GTB_CUDA_OK(ctx, cudaEventRecord(slot->h2d_done, cs));
         slot->in_flight = true;
         ctx->packed_chunks++;
-        ctx->h2d_bytes += (int64_t)ni * 8;
+        ctx->h2d_bytes += (int64_t)ni * (4 + pack_w);
       }
     }
     if (!packed) {
@@ -573,8 +600,10 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     GTB_CUDA_OK(ctx, cudaEventRecord(st.copied, cs));
     GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied, 0));
     if (packed) {
-      GTB_LAUNCH(ctx, "unpack", unpack_kernel, gtb_grid_for((int64_t)(ni + 3) / 4, 256, (int64_t)ctx->sm_count * 8), 256, 0, (int64_t)ni,
-                 st.meta.p, st.start.p, st.chrom.p, st.stop.p, st.strand.p);
+      const unsigned ugrid = gtb_grid_for((int64_t)(ni + 3) / 4, 256, (int64_t)ctx->sm_count * 8);
+      if (pack_w == 1) GTB_LAUNCH(ctx, "unpack", unpack_kernel<1>, ugrid, 256, 0, (int64_t)ni, (const void *)st.meta.p, pack_len0, st.start.p, st.chrom.p, st.stop.p, st.strand.p);
+      else if (pack_w == 2) GTB_LAUNCH(ctx, "unpack", unpack_kernel<2>, ugrid, 256, 0, (int64_t)ni, (const void *)st.meta.p, pack_len0, st.start.p, st.chrom.p, st.stop.p, st.strand.p);
+      else GTB_LAUNCH(ctx, "unpack", unpack_kernel<4>, ugrid, 256, 0, (int64_t)ni, (const void *)st.meta.p, pack_len0, st.start.p, st.chrom.p, st.stop.p, st.strand.p);
       GTB_TRY(gtb_check_launch(ctx));
     }
     QueryView q;

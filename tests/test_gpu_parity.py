@@ -506,7 +506,7 @@ def test_full_size_properties(gtb, ctx, oracle):
 
 
 def test_packed_host_path(gtb, ctx, oracle, monkeypatch):
-    """Host-resident chunks travel re-encoded (8 B/interval) when every query fits the packed form and in the plain
+    """Host-resident chunks travel re-encoded (5, 6 or 8 B/interval) when every query fits a packed form and in the plain
     layout otherwise; both must give the oracle's values, as must a run with the packing pool switched off."""
     reads = support.synth_reads(600_000, seed=41)
     regions = support.synth_regions(4_000, seed=42)
@@ -522,6 +522,27 @@ def test_packed_host_path(gtb, ctx, oracle, monkeypatch):
             ix.add_host(q)
             assert np.array_equal(ix.finish(), want)
             ix.close()
+    # the three widths of the packed form: one read length -> 5 B/interval, lengths below 256 -> 6, longer -> 8, and a chunk
+    # that fits none of them -> the plain 13; a fresh context each so that the byte counts are the form's own
+    rng = np.random.default_rng(43)
+    n = len(reads["chrom"])
+    short = {k: v.copy() for k, v in reads.items()}
+    short["stop"] = (short["start"] + rng.integers(0, 256, size=n)).astype(np.int32)
+    longer = {k: v.copy() for k, v in reads.items()}
+    longer["stop"] = (longer["start"] + rng.integers(0, 3000, size=n)).astype(np.int32)
+    many_chrom = {k: v.copy() for k, v in reads.items()}
+    many_chrom["chrom"][rng.random(n) < 0.01] = 150                   # beyond the 7-bit chromosome field of the narrow forms
+    for q, bytes_per_interval in ((reads, 5), (short, 6), (longer, 8), (many_chrom, 8), (odd, 13)):
+        for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+            rc, want, _ = fn(q, regions, 0)
+            assert rc == 0
+            c1 = gtb.Context(0)
+            ix = gtb.Index(c1, regions, op, 0)
+            ix.add_host(q)
+            assert np.array_equal(ix.finish(), want), (bytes_per_interval, op)
+            assert c1.transfer_stats()["h2d_bytes"] == bytes_per_interval * n, (bytes_per_interval, c1.transfer_stats())
+            ix.close()
+            c1.close()
     monkeypatch.setenv("GTB_INGEST_THREADS", "0")
     c2 = gtb.Context(0)
     rc, want, _ = oracle.count(reads, regions, 0)
