@@ -1,15 +1,17 @@
-// gtb_direct.cu -- DIRECT engine: overlap count in ONE pass over the queries, for indices whose evaluation points fit
-// a byte counter each in one SM's shared memory (up to ~200 k slots: 100 k regions).
+// gtb_direct.cu -- DIRECT engine: overlap count / coverage in ONE pass over the queries, for indices whose evaluation points
+// fit a byte counter each in one SM's shared memory (up to ~190 k slots: ~95 k regions).
 //
 // Why (measured on B200, profiles/microbench/gather_rate_b200.txt and red_rate_b200.txt): a random 8-byte load from a
-// table that lives in L2 (up to 16 MB) costs 1.1 SM-cycles per element, a random shared-memory atomic 0.17, a random
+// table that lives in L2 (up to 16 MB) costs 1.05 SM-cycles per element, a random shared-memory atomic 0.17, a random
 // global reduction 1.45.  The BUCKET engine pays 13 + 4 + 4 bytes of HBM traffic and two kernels' worth of
 // shared-memory work per query to avoid global reductions; this engine pays 13 bytes, one L2 gather and one shared atomic:
 //
-//   * The groups' coordinate axes are cut into cells of 2^c bp laid end to end (c chosen so that the table stays <= 16 MB:
-//     hg19 x 2 strands at c = 12 is 1.5 M cells).  One 8-byte entry per cell: the slot of the first evaluation point at or
-//     after the cell's start (24 bits), the offsets of up to three points inside the cell (12 bits each, 0xFFF = none) and
-//     a "more than three" flag.  For a query [s, e] whose ends fall into cells with at most three points
+//   * Every (chromosome, strand) owns a block of `stride` cells of 2^c bp (c chosen so that the cells queries can reach stay
+//     within 13 MB: hg19 x 2 strands -> c = 12), so the cell of a coordinate is arithmetic.  One 8-byte entry per cell: the
+//     slot of the first evaluation point at or after the cell's start (24 bits), the offsets of up to two points inside the
+//     cell (16 bits each, 0xFFFF = none) and three flags: nothing to count here (no such group / beyond its last point), a
+//     dense cell (more than two points: walk them from the cell's first slot, four loads per round trip), general path
+//     (a group whose points are all <= 0).  For a query [s, e]
 //         jS = slot0(cell(s)) + #{p < s & (2^c - 1)},   jE likewise for e  (a second gather only if e is in another cell),
 //     which is lower_bound(points, s) / lower_bound(points, e) of the RANK engine (gtb_rank_device.cuh) without a search.
 //   * jS == jE (almost every short read): one shared-memory atomicAdd on a BYTE counter (four slots per 32-bit word).  The
@@ -18,16 +20,19 @@
 //     arithmetically exact throughout (transient carries between bytes cancel), so without the flag the bytes are the
 //     exact counts.  With the flag the whole batch is discarded and replayed through the general rank step by the commit kernel
 //     (which otherwise only sums) -- correct whatever the skew, and the host switches the engine off for this index.
-//   * jS != jE (a read straddling an evaluation point, ~0.1 %), more than three points in a cell, strands other than +/-,
-//     reads reaching past the group's last point, invalid intervals: the general path inline (binary search, global
-//     reductions), into per-batch delta planes so that a discarded batch leaves no trace.
-//   * Position-sorted input: a warp whose 128 queries share one slot sends one reduction of 128.
-//   * At the end each CTA writes its counters to its row of a [CTAs x slots] byte matrix (coalesced); a commit kernel sums the
+//   * jS != jE (a read straddling an evaluation point, ~0.1 %): reductions into per-batch delta planes.  Strands other than
+//     +/- and invalid intervals: the general path inline (admission rules, binary search), into the same delta planes, so that
+//     a discarded batch leaves no trace.
+//   * Position-sorted input: a warp whose 128 queries share one slot sends one reduction of 128.  Clustered input (neighbouring
+//     queries sharing slots): slots shared by eight or more lanes of a warp leave as one reduction each.
+//   * Coverage: the counters count the queries that have the batch's common length (the first query's) and the commit
+//     multiplies; a query of another length costs a reduction (and is counted: many of them send the index to BUCKET).
+//   * At the end each CTA writes its counters to its row of a [CTAs x slots] byte matrix (coalesced); the commit kernel sums the
 //     rows and the delta planes into the index's histogram planes.  Finalisation is the RANK engine's.
 //
 // Reference semantics reproduced: admission rules of UnsortedGenomicRegionSetOverlaps::GetQuery/NextQuery
-// (genomic_intervals.cpp:5719-5745) and the overlap predicate (:624-630, :5227-5229) through the rank formulation of
-// SURVEY.md section 7.1 -- see gtb_overlap.cuh.
+// (genomic_intervals.cpp:5719-5745), the overlap predicate (:624-630, :5227-5229) and CalcOverlap (:427-432) through the rank
+// formulation of SURVEY.md section 7.1 -- see gtb_overlap.cuh.
 #include "gtb_rank_device.cuh"
 #include <algorithm>
 
@@ -65,11 +70,10 @@ __device__ __forceinline__ uint32_t dr_ldg32(const void *p) {
   asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
-template <bool NA>
+// one cell entry; allocating in L1 (measured: 0.585 ms per 100 M queries against 0.682 ms with L1::no_allocate)
 __device__ __forceinline__ uint2 dr_gather(const uint2 *p) {
   uint2 r;
-  if (NA) asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  else asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
       base[i] = (min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask)) * stride;   // unknown chromosome -> the all-"nothing" block
-      ent[i] = dr_gather<false>(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
+      ent[i] = dr_gather(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
     }
     uint32_t jS[DR_ITEMS], jE[DR_ITEMS], j0E[DR_ITEMS];
     uint32_t scan = 0;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     for (int i = 0; i < DR_ITEMS; i++) {
       uint2 ee = ent[i];
       if (((uint32_t)s[i] ^ (uint32_t)e[i]) >> cbits) {                // a read that crosses a cell boundary (~1 %)
-        ee = dr_gather<false>(dv.cells + base[i] + min((uint32_t)e[i] >> cbits, last));
+        ee = dr_gather(dv.cells + base[i] + min((uint32_t)e[i] >> cbits, last));
       }
       const uint32_t fl = ent[i].x | (ee.x & (DR_GENERAL | DR_SCAN));   // "nothing" is about the START: a stop beyond the last point lands in the sentinel slot
       general |= (fl & DR_GENERAL) ? (1u << i) : 0u;                   // a group whose points are all <= 0
