@@ -129,6 +129,9 @@ int main(int argc, char *argv[]) {
   }
 
   timer.Mark("load_reference");
+  // The driver uses one GPU.  On a multi-GPU host the CUDA runtime would initialise every visible device first (seconds);
+  // unless the user has chosen devices, only the first one is made visible.
+  setenv("CUDA_VISIBLE_DEVICES", "0", 0);
   gtb_ctx *ctx = nullptr;
   int rc = gtb_ctx_create(0, &ctx);
   if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
