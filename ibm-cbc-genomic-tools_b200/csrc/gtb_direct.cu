@@ -330,8 +330,11 @@ struct gtb_direct_state {
   dbuf<uint2> d_cells;
   dbuf<uint32_t> d_cta_counts, d_flag;
   dbuf<ull> d_delta;
-  int64_t queries_since_check = 0;
+  int64_t queries_since_check = 0, queries_in_check = 0;            // queries since the last flag copy was issued / covered by the copy in flight
   uint32_t gen = 0, odd_seen = 0;
+  uint32_t *h_flag = nullptr;                                          // pinned: where the flag words land
+  cudaEvent_t flag_copied = nullptr;
+  bool check_pending = false;
 };
 
 int gtb_direct_prepare(gtb_index *ix) {
@@ -400,6 +403,8 @@ int gtb_direct_prepare(gtb_index *ix) {
   GTB_TRY(ds->d_cta_counts.reserve(ctx, (size_t)ds->grid * n_words));
   GTB_TRY(ds->d_delta.reserve(ctx, (size_t)ix->planes * ix->n_slots));
   GTB_TRY(ds->d_flag.reserve(ctx, 2));
+  if (!ds->h_flag) GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&ds->h_flag, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  if (!ds->flag_copied) GTB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ds->flag_copied, cudaEventDisableTiming));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_delta.p, 0, (size_t)ix->planes * ix->n_slots * sizeof(ull), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -424,19 +429,17 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
   gtb_direct_state *ds = ix->direct;
   if (q.region_offset || q.weight) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine takes single-interval, unweighted batches");
-  // skew watchdog: a replayed batch means byte counters overflow on this input -- leave the field to the BUCKET engine from now on.
-  // Checked at the first batch after a reset (the previous finish has synchronised) and every 64 M queries of a long stream.
-  if (ds->queries_since_check > 0 && (q.index_base == 0 || ds->queries_since_check >= ((int64_t)64 << 20))) {
-    uint32_t seen[2] = {0, 0};                                          // overflow generation, odd-length queries so far
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(seen, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (seen[0] != 0) ds->off = true;
-    // coverage of reads of many lengths: each odd one is a global reduction -- the BUCKET engine does those better
-    if ((int64_t)(uint32_t)(seen[1] - ds->odd_seen) > ds->queries_since_check / 16) ds->off = true;
-    ds->odd_seen = seen[1];
-    ds->queries_since_check = 0;
+  // Watchdog, without ever making the host wait: after a batch the two flag words travel to pinned host memory behind it; the
+  // next batch that finds that copy complete looks at them.  A replayed batch means byte counters overflow on this input, many
+  // odd-length reads under coverage mean a reduction each -- either way the BUCKET engine serves this index from then on.
+  if (ds->check_pending && cudaEventQuery(ds->flag_copied) == cudaSuccess) {
+    ds->check_pending = false;
+    if (ds->h_flag[0] != 0) ds->off = true;
+    if ((int64_t)(uint32_t)(ds->h_flag[1] - ds->odd_seen) > ds->queries_in_check / 16) ds->off = true;
+    ds->odd_seen = ds->h_flag[1];
     if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
   }
+  cudaGetLastError();                                                   // cudaErrorNotReady of the query above is not an error
   RankView rv;
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
   rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p;
@@ -461,6 +464,13 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
     GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<false>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   }
   ds->queries_since_check += q.n_regions;
+  if (!ds->check_pending) {
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaEventRecord(ds->flag_copied, ctx->stream));
+    ds->check_pending = true;
+    ds->queries_in_check = ds->queries_since_check;
+    ds->queries_since_check = 0;
+  }
   return gtb_check_launch(ctx);
 }
 
@@ -468,6 +478,8 @@ void gtb_direct_destroy(gtb_index *ix) {
   gtb_direct_state *ds = ix->direct;
   if (!ds) return;
   ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
+  if (ds->h_flag) cudaFreeHost(ds->h_flag);
+  if (ds->flag_copied) cudaEventDestroy(ds->flag_copied);
   delete ds;
   ix->direct = nullptr;
 }
