@@ -80,6 +80,8 @@ extern "C" int gtb_ctx_set_stream(gtb_ctx *ctx, void *cuda_stream) {
   return GTB_OK;
 }
 
+extern "C" void *gtb_ctx_get_stream(const gtb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 extern "C" int gtb_ctx_synchronize(gtb_ctx *ctx) {
   if (!ctx) return GTB_ERR_ARG;
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));

@@ -621,10 +621,10 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
 // =================================================================================================
 // finish
 // =================================================================================================
-extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int64_t *err_index) {
+// the device work of a finish: scans, finalisation, the copy of the values to `out` -- all enqueued, nothing waited for
+static int finish_enqueue(gtb_index *ix, uint64_t *out, unsigned mem) {
   if (!ix || (!out && ix->n_regions > 0)) return GTB_ERR_ARG;
   gtb_ctx *ctx = ix->ctx;
-  if (err_index) *err_index = -1;
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   CellFinalView cf{};
   GTB_TRY(gtb_cell_scan_for_finish(ix, &cf));
@@ -646,6 +646,19 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
                                      (mem & GTB_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     if (!(mem & GTB_MEM_DEVICE)) ctx->d2h_bytes += (int64_t)sizeof(ull) * ix->n_regions;
   }
+  return GTB_OK;
+}
+
+extern "C" int gtb_index_finish_async(gtb_index *ix, uint64_t *out, unsigned mem) {
+  if (!(mem & GTB_MEM_DEVICE)) return ix ? gtb_fail(ix->ctx, GTB_ERR_ARG, "gtb_index_finish_async writes to device memory") : GTB_ERR_ARG;
+  return finish_enqueue(ix, out, mem);
+}
+
+extern "C" int gtb_index_status(gtb_index *ix, int64_t *err_index) {
+  if (!ix) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (err_index) *err_index = -1;
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   ull err = ~0ull;
   GTB_CUDA_OK(ctx, cudaMemcpyAsync(&err, ix->d_err.p, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -657,6 +670,12 @@ extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int6
                                : "query regions should be compatible, sorted and non-overlapping!");
   }
   return GTB_OK;
+}
+
+extern "C" int gtb_index_finish(gtb_index *ix, uint64_t *out, unsigned mem, int64_t *err_index) {
+  if (err_index) *err_index = -1;
+  GTB_TRY(finish_enqueue(ix, out, mem));
+  return gtb_index_status(ix, err_index);
 }
 
 static int one_shot(gtb_ctx *ctx, int op, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,

@@ -35,9 +35,10 @@ ERR_UNSUPPORTED = 7
 ERR_NO_DEVICE = 100
 
 EXPORTS = [
-    "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_synchronize",
+    "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_get_stream", "gtb_ctx_synchronize",
     "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_transfer_stats", "gtb_ctx_profile", "gtb_ctx_profile_report",
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_finish",
+    "gtb_index_finish_async", "gtb_index_status",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
     "gtb_synth_reads", "gtb_synth_reads_range",
@@ -75,6 +76,7 @@ def load_library(path=LIB_PATH):
         "gtb_ctx_create": (ci, [ci, P(vp)]),
         "gtb_ctx_destroy": (None, [vp]),
         "gtb_ctx_set_stream": (ci, [vp, vp]),
+        "gtb_ctx_get_stream": (vp, [vp]),
         "gtb_ctx_synchronize": (ci, [vp]),
         "gtb_ctx_last_error": (ctypes.c_char_p, [vp]),
         "gtb_ctx_launch_count": (i64, [vp]),
@@ -86,6 +88,8 @@ def load_library(path=LIB_PATH):
         "gtb_index_reset": (ci, [vp]),
         "gtb_index_add_queries": (ci, [vp, P(_Set), u32]),
         "gtb_index_finish": (ci, [vp, vp, u32, P(i64)]),
+        "gtb_index_finish_async": (ci, [vp, vp, u32]),
+        "gtb_index_status": (ci, [vp, P(i64)]),
         "gtb_overlap_count": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_overlap_coverage": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_scan_create": (ci, [vp, ctypes.c_int32, vp, P(_ScanParams), P(vp)]),
@@ -178,6 +182,10 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self.check(lib().gtb_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def stream_ptr(self):
+        """cudaStream_t of the context's kernels, as an integer (torch.cuda.ExternalStream takes it)"""
+        return int(lib().gtb_ctx_get_stream(self._h) or 0)
 
     def synchronize(self):
         self.check(lib().gtb_ctx_synchronize(self._h))
@@ -273,6 +281,15 @@ class Index:
     def finish_ptr(self, ptr, mem):
         err = ctypes.c_int64(-1)
         rc = lib().gtb_index_finish(self._h, ctypes.c_void_p(ptr), mem, ctypes.byref(err))
+        self.ctx.check(rc, err.value)
+
+    def finish_async_ptr(self, ptr):
+        """enqueue the finish (values to device memory at ptr, valid in stream order); status() reports errors later"""
+        self.ctx.check(lib().gtb_index_finish_async(self._h, ctypes.c_void_p(ptr), MEM_DEVICE))
+
+    def status(self):
+        err = ctypes.c_int64(-1)
+        rc = lib().gtb_index_status(self._h, ctypes.byref(err))
         self.ctx.check(rc, err.value)
 
 

@@ -310,16 +310,33 @@ class ShardedDeviceOverlap:
         self.src_in_file_order = torch.from_numpy(src[order].astype(np.int64)).cuda()      # result[k] = table[src_in_file_order[k]]
         self.result = torch.zeros(plan.n_regions, dtype=torch.int64, device="cuda")
 
-    def step(self, dset, mem):
-        self.index.reset()
-        self.index.add_set(dset, mem)
-        self.index.finish_ptr(self.vals.data_ptr(), MEM_DEVICE)                # owned values stay on the device
+    def step(self, dset, mem, defer_status=False):
+        """One pass over the local reads.  With defer_status the host never waits: the engine's kernels, the collective and the
+        scatter are ordered by stream events, and the caller asks for the engine's verdict later with check() (a loop that
+        steps many times and looks at the result at the end)."""
+        torch = self.torch
+        if not defer_status:
+            self.index.reset()
+            self.index.add_set(dset, mem)
+            self.index.finish_ptr(self.vals.data_ptr(), MEM_DEVICE)            # owned values stay on the device; waits, raises GtbError
+        else:
+            # the library's kernels run on the context's stream, the collective and the scatter on torch's
+            lib_stream = torch.cuda.ExternalStream(self.ctx.stream_ptr()) if self.ctx.stream_ptr() else torch.cuda.default_stream()
+            lib_stream.wait_stream(torch.cuda.current_stream())               # last step's readers of vals are done before it is rewritten
+            self.index.reset()
+            self.index.add_set(dset, mem)
+            self.index.finish_async_ptr(self.vals.data_ptr())
+            torch.cuda.current_stream().wait_stream(lib_stream)
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.table, self.vals, group=self.group)        # THE collective
             self.torch.index_select(self.table, 0, self.src_in_file_order, out=self.result)
         else:
             self.torch.index_select(self.vals, 0, self.src_in_file_order, out=self.result)
         return self.result
+
+    def check(self):
+        """the engine's status after steps with defer_status (waits for the stream; raises GtbError like the single-GPU engine)"""
+        self.index.status()
 
     def close(self):
         self.index.close()

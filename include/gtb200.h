@@ -92,6 +92,9 @@ void gtb_ctx_destroy(gtb_ctx *ctx);
 /* Launch all work of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g.
  * so that a caller can bracket it with its own events.  NULL restores the context's own stream. */
 int  gtb_ctx_set_stream(gtb_ctx *ctx, void *cuda_stream);
+/* The CUDA stream (cudaStream_t) the context's kernels run on: its own non-blocking stream unless gtb_ctx_set_stream gave it
+ * another.  For callers that order their own device work against the library's with events instead of host waits. */
+void *gtb_ctx_get_stream(const gtb_ctx *ctx);
 int  gtb_ctx_synchronize(gtb_ctx *ctx);
 const char *gtb_ctx_last_error(const gtb_ctx *ctx);
 /* Kernel accounting: number of kernels launched by this context since creation / last reset, and
@@ -128,6 +131,11 @@ int  gtb_index_add_queries(gtb_index *index, const gtb_set *queries, unsigned me
  * A fatal query condition (GTB_ERR_QUERY_*) is reported here with *err_index = the first offending
  * query region in stream order; out is then unspecified (the reference prints nothing). */
 int  gtb_index_finish(gtb_index *index, uint64_t *out, unsigned mem, int64_t *err_index);
+/* The same in two halves, for callers that have more device work to queue behind the values (the multi-GPU driver's
+ * all-gather): gtb_index_finish_async enqueues everything and returns at once (out must be device memory and is valid in
+ * stream order); gtb_index_status then waits for the stream and reports what gtb_index_finish would have. */
+int  gtb_index_finish_async(gtb_index *index, uint64_t *out, unsigned mem);
+int  gtb_index_status(gtb_index *index, int64_t *err_index);
 
 /* One-shot conveniences == create + add + finish + destroy.
  * gtb_overlap_count    <-> GenomicRegionSetOverlaps::CountIndexOverlaps(match_gaps, ignore_strand, max_label_value)  genomic_intervals.h:2471, .cpp:5304-5317
