@@ -217,10 +217,17 @@ def main():
         dset, keep = gtb200.device_set(dev)
         n_local = n
 
+        # The library's kernels run on the context's own stream.  A step is queued without a host wait
+        # (gtb_index_finish_async), ordered against torch's stream -- where the timing events and the consumers of the
+        # result live -- by stream events; the engine's status is read once after the timed loop.
+        lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr())
+
         def step_device():
+            lib_stream.wait_stream(torch.cuda.current_stream())
             index.reset()
             index.add_set(dset, gtb200.MEM_DEVICE)
-            index.finish_ptr(out_dev.data_ptr(), gtb200.MEM_DEVICE)
+            index.finish_async_ptr(out_dev.data_ptr())
+            torch.cuda.current_stream().wait_stream(lib_stream)
             return out_dev
     else:
         # Genome-sharded: rank r owns a contiguous (chromosome, coordinate) range holding 1/world of the
@@ -288,6 +295,8 @@ def main():
         barrier()
     if world > 1:
         sh.check()
+    else:
+        index.status()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - launches0
     if dist is not None:

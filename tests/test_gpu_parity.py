@@ -435,6 +435,23 @@ def test_sharded_device_world1(gtb, ctx, oracle):
     got = sh.step(dset, gtb.MEM_DEVICE).cpu().numpy().view(np.uint64)
     rc, want, _ = oracle.count(reads, regions, 0)
     assert rc == 0 and np.array_equal(got, want)
+    # the same without a host wait inside the step (gtb_index_finish_async; streams ordered by events), status read afterwards
+    for _ in range(3):
+        out = sh.step(dset, gtb.MEM_DEVICE, defer_status=True)
+    sh.check()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    # ... and a fatal query is reported by check() exactly as the waiting form raises it
+    bad = {k: v.clone() for k, v in dev.items()}
+    bad["stop"][1234] = 0
+    bad["start"][1234] = -5
+    bad["chrom"][1234] = int(regions["chrom"][0])
+    bset, keep_bad = gtb.device_set(bad)
+    with pytest.raises(gtb.GtbError) as e1:
+        sh.step(bset, gtb.MEM_DEVICE)
+    sh.step(bset, gtb.MEM_DEVICE, defer_status=True)
+    with pytest.raises(gtb.GtbError) as e2:
+        sh.check()
+    assert (e1.value.code, e1.value.index) == (e2.value.code, e2.value.index) == (2, 1234)
     sh.close()
 
 
