@@ -215,3 +215,37 @@ def test_thread_counts_agree_on_a_large_file(tmp_path):
     for k, l in enumerate(a[1].splitlines()[:1000]):
         f = l.split(b"\t")[1].split(b" ")
         assert f[0].decode() == support.HG19_NAMES[c[k]] and f[1] == bytes([int(st[k])]) and int(f[2]) == s[k] and int(f[3]) == e[k]
+
+
+def test_blocks_and_long_lines(tmp_path):
+    """A file that spans several of the reader's 32 MB blocks (lines cut by block ends are carried over), and a line longer
+    than the reader's first block (the block grows)."""
+    synth = os.path.join(BIN, "gt_synth_bed")
+    if not os.path.exists(synth):
+        pytest.skip("bin/gt_synth_bed not built")
+    path = tmp_path / "big.bed"
+    n = 2_000_000                                                        # ~72 MB of text
+    with open(path, "wb") as f:
+        subprocess.run([synth, str(n), "9"], stdout=f, check=True)
+    assert os.path.getsize(path) > 2 * (32 << 20)
+    for env in ({"GT_PARSE_THREADS": "1"}, {"GT_PARSE_THREADS": "6"}):
+        rc, out, err = dump(path, env, args=["-q"])
+        assert rc == 0 and out.split()[-4:] == [b"regions", b"%d" % n, b"intervals", b"%d" % n], (out, err)
+    # last lines of the file through the full dump: line numbers still right after the block boundaries
+    tail = subprocess.run(["tail", "-n", "3", str(path)], stdout=subprocess.PIPE, check=True).stdout
+    small = tmp_path / "tail.bed"
+    small.write_bytes(tail)
+    want = strip_extras(dump(small, {"GT_PARSE_THREADS": "1"})[1])
+    got = dump(path, {"GT_PARSE_THREADS": "6"}, args=["-c", "500000"])[1].splitlines()[-3:]
+    assert strip_extras(b"\n".join(got) + b"\n") == want
+    assert [int(l.rsplit(b"#", 1)[1]) for l in got] == [n - 2, n - 1, n]
+    # a 3 MB label in the middle of a small file
+    rng = np.random.default_rng(23)
+    lines = rand_lines(rng, 50, "bed6")
+    lines[20] = "chr1\t100\t200\t" + "x" * (3 << 20) + "\t0\t-"
+    longp = tmp_path / "long.bed"
+    longp.write_text("\n".join(lines) + "\n")
+    want = ref_reg(longp)
+    for env in THREADINGS:
+        got = dump(longp, env)
+        assert got[0] == 0 == want[0] and strip_extras(got[1]) == want[1]
