@@ -5,6 +5,7 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 #include <algorithm>
@@ -128,6 +129,11 @@ LineReader::LineReader(const char *path) {
       gzbuffer(gz_, 1 << 20);
     }
   }
+  struct stat st;
+  if (!gz_ && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) {
+    const off_t at = lseek(fd_, 0, SEEK_CUR);
+    if (at >= 0) { regular_ = true; offset_ = at; }
+  }
   producer_ = std::thread(&LineReader::Produce, this);
 }
 
@@ -143,8 +149,45 @@ LineReader::~LineReader() {
   for (auto &b : block_) free(b.data);
 }
 
+// [offset, offset + want) of a regular file into dst; returns the bytes read (short only at the end of the file or on an error)
+static size_t PreadAll(int fd, char *dst, size_t want, off_t offset) {
+  size_t have = 0;
+  while (have < want) {
+    const ssize_t got = pread(fd, dst + have, want - have, offset + (off_t)have);
+    if (got < 0 && errno == EINTR) continue;
+    if (got <= 0) break;
+    have += (size_t)got;
+  }
+  return have;
+}
+
 long LineReader::ReadSome(char *dst, size_t want) {
   if (gz_) return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
+  if (regular_) {
+    // a regular file: one read() copies out of the page cache at a few GB/s, which the parsing threads outrun -- large requests
+    // are split over a few threads
+    const size_t slice = 8u << 20;
+    const int parts = (int)std::min<size_t>(4, want / slice);
+    if (parts <= 1) {
+      const size_t got = PreadAll(fd_, dst, want, offset_);
+      offset_ += (off_t)got;
+      return (long)got;
+    }
+    size_t got[4] = {0, 0, 0, 0};
+    const size_t each = want / (size_t)parts;
+    std::vector<std::thread> th;
+    for (int i = 1; i < parts; i++)
+      th.emplace_back([&, i] { got[i] = PreadAll(fd_, dst + each * (size_t)i, i + 1 == parts ? want - each * (size_t)i : each, offset_ + (off_t)(each * (size_t)i)); });
+    got[0] = PreadAll(fd_, dst, each, offset_);
+    for (auto &t : th) t.join();
+    size_t total = 0;                                                  // the contiguous prefix that arrived (a short part ends it: end of file)
+    for (int i = 0; i < parts; i++) {
+      total += got[i];
+      if (got[i] < (i + 1 == parts ? want - each * (size_t)i : each)) break;
+    }
+    offset_ += (off_t)total;
+    return (long)total;
+  }
   for (;;) {
     const ssize_t got = read(fd_, dst, want);
     if (got < 0 && errno == EINTR) continue;
@@ -537,57 +580,60 @@ bool RegionReader::ParseLine(char *inp, RegionBatch *out, ChromCache *cache, Par
 
 // The common case by far -- TAB-separated BED of 3 to 6 clean columns -- in one pass over the line and without writing
 // to it.  "Clean": every column non-empty and not starting with a blank, start and stop plain digit strings of at most 18
-// digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  nl = the line's '\n'.
-bool RegionReader::ParseBedLine(char *line, char *nl, RegionBatch *out, ChromCache *cache) const {
+// digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  The line ends with '\n'
+// (every block does); returns that '\n', or nullptr if the line is not for this path (nothing has been appended then).
+char *RegionReader::ParseBedLine(char *line, RegionBatch *out, ChromCache *cache) const {
   const char *p = line;
-  if (*p == ' ' || *p == '\t') return false;
+  if (*p == ' ' || *p == '\t') return nullptr;
   while (*p != '\t' && *p != '\n') p++;
   const size_t chrom_len = (size_t)(p - line);
-  if (*p != '\t' || chrom_len == 0 || chrom_len > 8) return false;
+  if (*p != '\t' || chrom_len == 0 || chrom_len > 8) return nullptr;
   p++;
   unsigned long start = 0, stop = 0;
   const char *d = p;
   while ((unsigned)(*p - '0') < 10u) start = start * 10 + (unsigned)(*p++ - '0');
-  if (p == d || p - d > 18 || *p != '\t') return false;
+  if (p == d || p - d > 18 || *p != '\t') return nullptr;
   d = ++p;
   while ((unsigned)(*p - '0') < 10u) stop = stop * 10 + (unsigned)(*p++ - '0');
-  if (p == d || p - d > 18) return false;
+  if (p == d || p - d > 18) return nullptr;
   char strand = '+';
   const char *label = nullptr, *label_end = nullptr;
   if (*p == '\t') {                                                     // column 4: label
     label = ++p;
-    if (*p == ' ' || *p == '\t' || *p == '\n') return false;
+    if (*p == ' ' || *p == '\t' || *p == '\n') return nullptr;
     while (*p != '\t' && *p != '\n') p++;
     label_end = p;
     if (*p == '\t') {                                                   // column 5: score
       p++;
-      if (*p == ' ' || *p == '\t' || *p == '\n') return false;
+      if (*p == ' ' || *p == '\t' || *p == '\n') return nullptr;
       while (*p != '\t' && *p != '\n') p++;
       if (*p == '\t') {                                                 // column 6: strand, then the end of the line
         p++;
-        if (p[1] == '\n') {
+        if (p[0] != '\n' && p[1] == '\n') {
           if (p[0] == '+' || p[0] == '.' || p[0] == '1') strand = '+';
           else if (p[0] == '-') strand = '-';
-          else return false;
-        } else if (p[0] == '-' && p[1] == '1' && p[2] == '\n') strand = '-';
-        else return false;
+          else return nullptr;
+          p += 1;
+        } else if (p[0] == '-' && p[1] == '1' && p[2] == '\n') { strand = '-'; p += 2; }
+        else return nullptr;
       }
     }
-  } else if (*p != '\n') return false;
+  } else if (*p != '\n') return nullptr;
+  // p is at the line's '\n' now
   start += 1;
-  if (start > (unsigned long)INT32_MAX || stop > (unsigned long)INT32_MAX) return false;
+  if (start > (unsigned long)INT32_MAX || stop > (unsigned long)INT32_MAX) return nullptr;
   if (max_label_value_ > 1) {                                          // GetLabelValue, genomic_intervals.cpp:1081-1085
     long w = 0;
     if (label != nullptr) {
       char tmp[32];
-      const size_t n = std::min<size_t>((size_t)(label_end - label), sizeof tmp - 1);
-      if ((size_t)(label_end - label) > sizeof tmp - 1) return false;
+      const size_t n = (size_t)(label_end - label);
+      if (n > sizeof tmp - 1) return nullptr;
       memcpy(tmp, label, n);
       tmp[n] = 0;
       w = atol(tmp);
     }
     w = std::min(max_label_value_, w);
-    if (w < INT32_MIN || w > INT32_MAX) return false;
+    if (w < INT32_MIN || w > INT32_MAX) return nullptr;
     out->weight.push_back((int32_t)w);
   }
   out->chrom.push_back(cache->GetShort(line, chrom_len));
@@ -596,7 +642,7 @@ bool RegionReader::ParseBedLine(char *line, char *nl, RegionBatch *out, ChromCac
   out->stop.push_back((int32_t)stop);
   out->offset.push_back((int64_t)out->chrom.size());
   if (keep_labels_) { if (label) out->label.emplace_back(label, label_end); else out->label.emplace_back("_"); }
-  return true;
+  return const_cast<char *>(p);
 }
 
 struct RegionReader::Piece {
@@ -641,8 +687,9 @@ bool RegionReader::ParseRun(char *begin, char *end, RegionBatch *out) {
     const size_t guess = (size_t)(pc.hi - pc.lo) / 24 + 16;            // avoids most reallocations the first time round
     dst->chrom.reserve(guess); dst->start.reserve(guess); dst->stop.reserve(guess); dst->strand.reserve(guess); dst->offset.reserve(guess + 1);
     for (char *p = pc.lo; p < pc.hi;) {
-      char *nl = (char *)memchr(p, '\n', (size_t)(pc.hi - p));
-      if (!(bed && ParseBedLine(p, nl, dst, &cache))) {
+      char *nl = bed ? ParseBedLine(p, dst, &cache) : nullptr;
+      if (nl == nullptr) {
+        nl = (char *)memchr(p, '\n', (size_t)(pc.hi - p));
         *nl = 0;
         if (!ParseLine(p, dst, &cache, &pc.err)) { pc.bad = true; break; }
       }

@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/types.h>
 #include <zlib.h>
 #include <map>
 #include <condition_variable>
@@ -86,6 +87,8 @@ class LineReader {
   bool Acquire();                                     // make the next block current; false at end
   gzFile gz_ = nullptr;
   int fd_ = -1;
+  bool regular_ = false;                              // a regular file, read with pread at offset_ (by several threads when the request is large)
+  off_t offset_ = 0;
   Block block_[kBlocks];
   std::mutex mu_;
   std::condition_variable cv_;
@@ -182,7 +185,7 @@ class RegionReader {
   bool Push(RegionBatch *out, ChromCache *cache, const char *chrom, char strand, long start, long stop, ParseError *err) const;
   // lines of [begin, end), over the parsing threads, appended to out; false on a malformed line (error_ set)
   bool ParseRun(char *begin, char *end, RegionBatch *out);
-  bool ParseBedLine(char *line, char *nl, RegionBatch *out, ChromCache *cache) const;   // clean BED3-6 only; false = not handled
+  char *ParseBedLine(char *line, RegionBatch *out, ChromCache *cache) const;   // clean BED3-6 only; the line's '\n', or nullptr = not handled
   LineReader reader_;
   ChromTable *chroms_;
   bool keep_labels_;
