@@ -559,9 +559,63 @@ bool RegionReader::ParseLine(char *inp, RegionBatch *out, ChromCache *cache, Par
     NextToken(&inp, '\t');                                             // frame
     if (n_tokens != 8) label = NextToken(&inp, '\t');
     if (!Push(out, cache, seqname, strand, start, end, err)) return false;
-  } else if (fmt_ == F_SAM || fmt_ == F_SEQ) {
+  } else if (fmt_ == F_SAM) {                                        // GenomicRegionSAM::Read, genomic_intervals.cpp:2771-2813
+    const int n_tokens = CountTokens(inp, '\t');
+    if (n_tokens < 11) return LineError(err, "number of tokens should be at least 11 for SAM format!");
+    label = NextToken(&inp, '\t');
+    const unsigned long flag = (unsigned long)FastAtol(NextToken(&inp, '\t'));
+    const char *rname = NextToken(&inp, '\t');
+    long start = FastAtol(NextToken(&inp, '\t'));                       // POS: 1-based leftmost mapping position
+    NextToken(&inp, '\t');                                              // MAPQ
+    const char *cigar = NextToken(&inp, '\t');
+    NextToken(&inp, '\t'); NextToken(&inp, '\t'); NextToken(&inp, '\t');  // RNEXT, PNEXT, TLEN
+    const char *seq = NextToken(&inp, '\t');
+    const char strand = (flag & 0x10ul) ? '-' : '+';                    // CalcStrandFromFlag, :2870-2873
+    const long seq_len = (long)strlen(seq);
+    const bool star = strcmp(cigar, "*") == 0;                          // "*" stands for <length of SEQ>M (:2791)
+    // One pass over the CIGAR (TokenizeCIGAR :2910-2918 + the loop of Read :2801-2809): operations "MD=X" consume the
+    // reference, 'N' closes a block and skips; the fragment length is what "MIS=X" add up to (:3021-3026).  '=' is in the
+    // reference's reference-consuming set but not in its tokenizer's alphabet "MIDNSHP-X": it is fatal there, and here.
+    long reference_len = 0, fragment_len = 0;
+    const size_t first = out->chrom.size();
+    const char *c = cigar;
+    for (bool first_trip = true; star ? first_trip : *c != 0; first_trip = false) {
+      long len = 0;
+      char type;
+      if (star) { len = seq_len; type = 'M'; }
+      else {
+        const char *d = c;
+        while (*c >= '0' && *c <= '9') c++;
+        if (c - d > 18) len = atol(std::string(d, c).c_str());
+        else for (; d != c; d++) len = len * 10 + (*d - '0');
+        type = *c;
+        if (type == 0 || strchr("MIDNSHP-X", type) == nullptr) {
+          err->with_line = true; err->raw = false;
+          err->message = std::string("unknown CIGAR operation type '") + (type ? std::string(1, type) : std::string()) + "'!";
+          out->chrom.resize(first); out->start.resize(first); out->stop.resize(first); out->strand.resize(first);
+          return false;
+        }
+        c++;
+      }
+      if (type == 'M' || type == 'I' || type == 'S' || type == 'X') fragment_len += len;
+      if (type != 'N') { if (type == 'M' || type == 'D' || type == 'X') reference_len += len; }
+      else {
+        if (!Push(out, cache, rname, strand, start, start + reference_len - 1, err)) return false;
+        start = start + reference_len + len;
+        reference_len = 0;
+      }
+    }
+    if (strcmp(seq, "*") != 0 && seq_len != fragment_len) {
+      err->with_line = true; err->raw = false;
+      err->message = std::string("length of aligned fragment does not match CIGAR string: \n") + "  LABEL = " + label + "\n" +
+                     "  CIGAR = " + (star ? std::to_string(seq_len) + "M" : std::string(cigar)) + "\n" + "  length(SEQ) = " + std::to_string(seq_len) + "\n";
+      out->chrom.resize(first); out->start.resize(first); out->stop.resize(first); out->strand.resize(first);
+      return false;
+    }
+    if (reference_len > 0 && !Push(out, cache, rname, strand, start, start + reference_len - 1, err)) return false;
+  } else if (fmt_ == F_SEQ) {
     err->with_line = false; err->raw = false;
-    err->message = "input format " + format_ + " is not supported by this build (BED, REG and GFF are)!\n";
+    err->message = "input format " + format_ + " is not supported by this build (BED, REG, GFF and SAM are)!\n";
     return false;
   } else {
     err->with_line = false; err->raw = false; err->message = "unsupported input format!\n";

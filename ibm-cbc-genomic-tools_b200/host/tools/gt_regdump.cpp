@@ -34,6 +34,7 @@ int main(int argc, char **argv) {
     text.clear();
     char num[64];
     for (int64_t k = 0; k < b.n_regions(); k++) {
+      if (b.offset[k + 1] == b.offset[k]) continue;                    // a region without intervals prints nothing (GenomicRegion::Print)
       text += b.label[k];
       text += '\t';
       for (int64_t i = b.offset[k]; i < b.offset[k + 1]; i++) {

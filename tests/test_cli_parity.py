@@ -269,3 +269,54 @@ def test_scans_variants(scanfiles):
                  ["counts", "-g", d / "genome.bed", "-S", d / "valid.bed"]):
         want, got = both("genomic_scans", args)
         assert got[0] == want[0] and got[1] == want[1], args
+
+
+# ------------------------------------------------------------------------------------------------
+# SAM input (GenomicRegionSAM::Read, genomic_intervals.cpp:2771-2813): POS + CIGAR -> blocks, strand from FLAG 0x10
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def samfiles(files):
+    d = files["dir"]
+    rng = np.random.default_rng(99)
+    lines = ["@HD\tVN:1.0\tSO:unsorted", "@SQ\tSN:chr1\tLN:5000"]
+    for k in range(20000):
+        c = NAMES[rng.integers(0, 5)]
+        pos = int(rng.integers(1, 2000))
+        ops, frag = [], 0
+        for j in range(int(rng.integers(1, 5))):
+            op = "M" if j == 0 else "MMMNNIDSX"[rng.integers(9)]
+            ln = int(rng.integers(1, 120))
+            ops.append("%d%s" % (ln, op))
+            frag += ln if op in "MISX" else 0
+        cigar, seq = "".join(ops), "A" * frag
+        pick = rng.integers(20)
+        if pick == 0:
+            cigar, seq = "*", "ACGT" * 9                                 # no CIGAR: <length of SEQ>M
+        elif pick == 1:
+            seq = "*"
+        flag = int(rng.integers(0, 2048))
+        if pick == 2:
+            c, pos, cigar, flag = "*", 0, "*", 4                         # unmapped
+        lines.append("\t".join([str(int(rng.integers(0, 9))), str(flag), c, str(pos), "60", cigar, "*", "0", "0", seq, "*"] +
+                               (["NM:i:1"] if k % 3 == 0 else [])))
+    (d / "q.sam").write_text("\n".join(lines) + "\n")
+    gz(d / "q.sam")
+    return d
+
+
+@pytest.mark.parametrize("op", ["count", "coverage", "density"])
+@pytest.mark.parametrize("flags", [[], ["-i"], ["-gaps"], ["--max-label-value", "5"]])
+def test_sam_queries(samfiles, op, flags):
+    assert_same("genomic_overlaps", [op] + flags + [samfiles / "idx.bed", samfiles / "q.sam"], nonempty=True)
+
+
+def test_sam_variants(samfiles, scanfiles):
+    d = samfiles
+    assert_same("genomic_overlaps", ["count", d / "midx.bed", d / "q.sam.gz"], nonempty=True)
+    assert_same("genomic_overlaps", ["count", d / "idx.gff"], stdin=(d / "q.sam").read_bytes(), nonempty=True)
+    assert_same("genomic_scans", ["counts", "-g", scanfiles / "genome.bed", "-w", "200", "-d", "50", "-min", "2", d / "q.sam"], nonempty=True)
+    bad = (d / "q.sam").read_text().splitlines()
+    bad[5000] = "r\t0\tchr1\t5\t60\t3M2I\t*\t0\t0\tACGTACGT\t*"          # SEQ length != CIGAR's: fatal with the reference's words
+    (d / "bad.sam").write_text("\n".join(bad) + "\n")
+    want, got = both("genomic_overlaps", ["count", d / "idx.bed", d / "bad.sam"])
+    assert got[0] == want[0] != 0 and got[1] == want[1] and got[2] == want[2]

@@ -90,6 +90,23 @@ def rand_lines(rng, n, kind):
         elif kind == "reg_compact":
             nb = int(rng.integers(1, 4))
             out.append(f"{lab}\t{c} {strand} " + ",".join(str(s + 500 * i + 1) for i in range(nb)) + " " + ",".join(str(s + 500 * i + 100) for i in range(nb)))
+        elif kind == "sam":
+            # POS + CIGAR: M/D/X consume the reference, N splits into blocks, I/S add to the fragment only, H/P to neither
+            ops, frag = [], 0
+            for k_op in range(int(rng.integers(1, 6))):
+                op = "M" if k_op == 0 else "MMMMIDNSHXP"[rng.integers(11)]   # (a read without a reference-consuming operation has no interval at all)
+                ln = int(rng.integers(1, 60))
+                ops.append("%d%s" % (ln, op))
+                if op in "MISX":
+                    frag += ln
+            cigar = "".join(ops)
+            pick = rng.integers(5)
+            seq = "*" if pick == 0 else "A" * frag if frag else "*"
+            if pick == 1:
+                cigar, seq = "*", "ACGT" * int(rng.integers(1, 20))       # "*" stands for <length of SEQ>M
+            flag = int(rng.integers(0, 4096))
+            cols = [lab, str(flag), c, str(s + 1), "60", cigar, "*", "0", "0", seq, "*"] + (["NM:i:0", "XS:A:+"] if rng.integers(2) else [])
+            out.append("\t".join(cols))
         elif kind == "gff":
             st = [strand, "."][rng.integers(2)]
             cols = [c, "src", "feat", str(s + 1), str(e), ".", st, ".", lab][:int(rng.integers(8, 10))]
@@ -97,7 +114,7 @@ def rand_lines(rng, n, kind):
     return out
 
 
-KINDS = ["bed3", "bed4", "bed5", "bed6", "bed6_space", "bed_mixed", "reg", "reg_compact", "gff"]
+KINDS = ["bed3", "bed4", "bed5", "bed6", "bed6_space", "bed_mixed", "reg", "reg_compact", "gff", "sam"]
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -152,6 +169,10 @@ def test_headers_gzip_stdin_and_unterminated_last_line(tmp_path, env):
     assert got_gz[1] == got[1]
     got_in = dump("-", env, stdin=text.encode())
     assert got_in[1] == got[1]
+    sam = "@HD\tVN:1.0\n@SQ\tSN:chr1\tLN:1000\n" + "\n".join(rand_lines(rng, 80, "sam")) + "\n"
+    p3 = tmp_path / "h.sam"
+    p3.write_text(sam)
+    assert strip_extras(dump(p3, env)[1]) == ref_reg(p3)[1]
     gff = "##gff-version 3\n##x\n" + "\n".join(rand_lines(rng, 50, "gff")) + "\n"
     p2 = tmp_path / "h.gff"
     p2.write_text(gff)
@@ -163,7 +184,11 @@ def test_headers_gzip_stdin_and_unterminated_last_line(tmp_path, env):
 
 @pytest.mark.parametrize("env", THREADINGS, ids=["t1", "t5"])
 @pytest.mark.parametrize("bad,kind", [("chr1\t5", "bed6"), ("chr1\t5\t9\tx\t0\t*", "bed6"), ("lab\tchr1 + 5", "reg"),
-                                      ("lab\tchr1 + 1,2 5", "reg_compact"), ("chr1\ta\tb\t1\t2\t.\t+", "gff")])
+                                      ("lab\tchr1 + 1,2 5", "reg_compact"), ("chr1\ta\tb\t1\t2\t.\t+", "gff"),
+                                      ("r\t0\tchr1\t5\t60\t10M\t*\t0\t0\tACGT", "sam"),                       # 10 columns
+                                      ("r\t0\tchr1\t5\t60\t4=\t*\t0\t0\tACGT\t*", "sam"),                    # '=' is not in the tokenizer's alphabet
+                                      ("r\t0\tchr1\t5\t60\t3M2Z\t*\t0\t0\tACGTA\t*", "sam"),
+                                      ("r7\t16\tchr1\t5\t60\t3M2I\t*\t0\t0\tACGTACGT\t*", "sam")])           # SEQ length != CIGAR's
 def test_first_malformed_line_wins(tmp_path, env, bad, kind):
     """several malformed lines, parsed by different threads: the earliest is reported, with the reference's words;
     the regions before it are still delivered (the drivers feed them to the engine before failing)"""
