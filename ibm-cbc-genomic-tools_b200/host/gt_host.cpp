@@ -447,6 +447,7 @@ RegionReader::RegionReader(const char *path, ChromTable *chroms, bool keep_label
            : format_ == "SEQ" ? F_SEQ : format_ == "EMPTY" ? F_EMPTY : F_NONE;
   };
   if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
+  if (strncmp(next, "BAM\x01", 4) == 0) die("BAM input is not supported by this build (SAM text is)!\n");   // GetFileType, core.cpp:1757-1775
   if (is_track(next)) { while (next && is_track(next)) next = reader_.Next(); }
   else if (next[0] == '@') { format_ = "SAM"; while (next && next[0] == '@') next = reader_.Next(); }
   else if (next[0] == '#' && next[1] == '#') { format_ = "GFF"; while (next && next[0] == '#' && next[1] == '#') next = reader_.Next(); }

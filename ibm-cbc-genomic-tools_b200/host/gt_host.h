@@ -5,7 +5,8 @@
 //   CmdLineWithOperations          gtools/core.h:772-932, core.cpp:2204-2646
 //   FileBufferText / FileBufferGZ  gtools/core.cpp:130-349 (incl. the "last line without newline is dropped" quirk, :243)
 //   GenomicRegionSet format sniffing and header skipping   gtools/genomic_intervals.cpp:3713-3759
-//   GenomicRegionBED::Read / GenomicRegion::Read (REG) / GenomicRegionGFF::Read   :2157-2182, :805-838, :3501-3517
+//   GenomicRegionBED::Read / GenomicRegion::Read (REG) / GenomicRegionGFF::Read / GenomicRegionSAM::Read
+//                                  :2157-2182, :805-838, :3501-3517, :2771-2813
 // Written from their behaviour; no reference code is reused.
 #pragma once
 #include <stdint.h>
