@@ -40,8 +40,8 @@ int main(int argc, char **argv) {
       for (int64_t i = b.offset[k]; i < b.offset[k + 1]; i++) {
         if (i > b.offset[k]) text += ' ';
         text += chroms.name[b.chrom[i]];
-        snprintf(num, sizeof num, " %c %d %d", (char)b.strand[i], b.start[i], b.stop[i]);
-        text += num;
+        const int len = snprintf(num, sizeof num, " %c %d %d", (char)b.strand[i], b.start[i], b.stop[i]);
+        text.append(num, (size_t)len);                                 // (a GFF strand column may be empty: the strand byte is then NUL)
       }
       if (max_label_value > 1) { snprintf(num, sizeof num, "\tw=%d", b.weight[k]); text += num; }
       snprintf(num, sizeof num, "\t#%ld\n", b.line(k));
