@@ -116,8 +116,8 @@ __device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uin
 // queries; profiles/r1_experiments.md).
 //
 // The hot loop holds no table but the cells: every (chromosome, strand) has a block of `stride` cells, so the cell of a
-// coordinate is pure arithmetic, and what used to be per-group knowledge (no such group, beyond the last point, too many
-// points) is two flag bits of the cell entry.
+// coordinate is pure arithmetic, and what used to be per-group knowledge (no such group, beyond the last point, a dense
+// cell, a group left to the general path) is three flag bits of the cell entry.
 //
 // COVERAGE: the "both" plane takes the query's length instead of 1.  Reads of a sequencing run mostly share one length, so the
 // byte counters count the queries whose length equals the batch's first query's and the commit kernel multiplies; a query of
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       scan |= (fl & DR_SCAN) ? (1u << i) : 0u;
       j0E[i] = ee.x & 0xFFFFFFu;
     }
+    scan &= ~skip;
     if (scan) {                                                        // more than two points in one of the cells: walk them
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     // hundreds of adds would reach one byte before its first spill lands.  Neighbouring queries sharing a slot give such input
     // away; the warp then looks for slots shared by eight or more of its lanes and sends ONE reduction for each of those.
     uint32_t done = skip;                                              // bit i: item i needs no shared atomic
-    if (__any_sync(0xffffffffu, jS[0] == jS[1] || jS[1] == jS[2] || jS[2] == jS[3])) {
+    if (__any_sync(0xffffffffu, (!(skip & 0x3u) && jS[0] == jS[1]) || (!(skip & 0x6u) && jS[1] == jS[2]) || (!(skip & 0xCu) && jS[2] == jS[3]))) {
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++) {
         const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
