@@ -92,8 +92,7 @@ template <bool COVERAGE>
 __device__ __noinline__ void special_query(const BucketView &bv, const RankView &rv, int32_t c, int32_t qs, int32_t qe, int strand,
                                            int64_t w, int64_t index) {
   if (qe <= 0 || qs > qe) {                                                // fatal only on indexed chromosomes, :5731-5741
-    if (bv.chrom_present[c]) report_error(rv.err, index, qe <= 0 ? GTB_ERR_QUERY_STOP_NONPOSITIVE : GTB_ERR_QUERY_START_GT_STOP);
-    return;
+    if (!bv.chrom_present[c] || !admit_interval(rv, qs, qe, index)) return;
   }
   const int cls = bv.class_of[(uint8_t)strand];
   if (cls < 0) return;                                                     // no index region carries this strand, :5229
@@ -751,7 +750,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
   RankView rv;
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
-  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p; rv.sorted_rules = ix->sorted_rules ? 1 : 0;
 
   const bool cov = ix->op == GTB_OP_COVERAGE;
   const size_t per_sm = 227 * 1024;

@@ -25,8 +25,10 @@ __device__ __forceinline__ int64_t lower_bound_u64(const ull *__restrict__ p, in
 //                    applied to every query in GetQuery/NextQuery (:5698, :5709)
 //   chromosome unknown to the index -> no matches, no checks (:5719-5720, :5731)
 //   stop <= 0, start > stop -> fatal (:5740-5741)
-__device__ __forceinline__ bool admit_query(const QueryView &q, int64_t r, const uint8_t *__restrict__ present,
-                                            int32_t n_chrom, ull *err, int64_t &lo, int64_t &hi) {
+__device__ __forceinline__ bool admit_query(const QueryView &q, int64_t r, const RankView &rv, int64_t &lo, int64_t &hi) {
+  const uint8_t *__restrict__ present = rv.chrom_present;
+  const int32_t n_chrom = rv.n_chrom;
+  ull *err = rv.err;
   if (q.region_offset) { lo = q.region_offset[r] - q.interval_base; hi = q.region_offset[r + 1] - q.interval_base; }
   else { lo = r; hi = r + 1; }
   if (hi <= lo) return false;
@@ -40,9 +42,7 @@ __device__ __forceinline__ bool admit_query(const QueryView &q, int64_t r, const
   }
   if (c < 0 || c >= n_chrom || !present[c]) return false;
   const int32_t qs = q.start[lo], qe = q.stop[hi - 1];
-  if (qe <= 0) { report_error(err, q.index_base + r, GTB_ERR_QUERY_STOP_NONPOSITIVE); return false; }
-  if (qs > qe) { report_error(err, q.index_base + r, GTB_ERR_QUERY_START_GT_STOP); return false; }
-  return true;
+  return admit_interval(rv, qs, qe, q.index_base + r);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) rank_accumulate_kernel(QueryView q, RankV
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
     int64_t lo, hi;
-    if (!admit_query(q, r, ix.chrom_present, ix.n_chrom, ix.err, lo, hi)) continue;
+    if (!admit_query(q, r, ix, lo, hi)) continue;
     const int cls = ix.class_of[(uint8_t)q.strand[lo]];            // front-interval strand, :5229
     if (cls < 0) continue;
     const int g = q.chrom[lo] * ix.n_class + cls;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
     int64_t lo, hi;
-    if (!admit_query(q, r, ix.chrom_present, ix.n_chrom, ix.err, lo, hi)) continue;
+    if (!admit_query(q, r, ix, lo, hi)) continue;
     const int32_t c = q.chrom[lo];
     const int8_t qstrand = q.strand[lo];
     const int64_t qs_true = q.start[lo], qe = q.stop[hi - 1];
@@ -136,39 +136,27 @@ __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const 
                                                        const int32_t *__restrict__ t_hi, const int32_t *__restrict__ t_lo,
                                                        const int32_t *__restrict__ t_group, const int32_t *__restrict__ goff,
                                                        const int32_t *__restrict__ points, const ull *__restrict__ scan, int64_t K,
-                                                       CellFinalView cf, const ull *__restrict__ direct, ull *__restrict__ out) {
+                                                       const ull *__restrict__ direct, ull *__restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_regions) return;
   ull total = direct ? direct[k] : 0ull;
   for (int64_t t = t_off[k]; t < t_off[k + 1]; t++) {
     const int hi = t_hi[t], lo = t_lo[t], g = t_group[t], base = goff[g];
-    // RANK engine: group-relative inclusive prefix of slot plane p at slot j
+    // group-relative inclusive prefix of slot plane p at slot j
     auto pre = [&](int p, int j) -> ull {
       const ull *a = scan + (int64_t)p * K;
       return a[j] - (base > 0 ? a[base - 1] : 0ull);
     };
-    // CELL engine: everything in the group's cells before the cell of slot j's point, plus the
-    // point's own correction counter.  cp = cell plane, xp = correction plane (-1: none).
-    auto cel = [&](int cp, int xp, int j) -> ull {
-      if (!cf.cells_scan) return 0ull;
-      const uint32_t c = cf.slot_cell[j];
-      if (c == 0xFFFFFFFFu) return 0ull;            // point <= 0 or sentinel: no fast-path query can be <= it
-      const uint32_t gb = cf.gbase[g];
-      const ull *a = cf.cells_scan + (int64_t)cp * cf.n_cells;
-      ull v = (c > 0 ? a[c - 1] : 0ull) - (gb > 0 ? a[gb - 1] : 0ull);
-      if (xp >= 0) v += cf.corr[(int64_t)xp * K + j];
-      return v;
-    };
     if (!COVERAGE) {
-      const ull starts_le_te = pre(H_BOTH, hi) + pre(H_SCNT, hi) + cel(C_BOTH, -1, hi) + cel(C_SCNT, X_SCNT, hi);   // #{qs <= te}
-      const ull stops_lt_ts = pre(H_BOTH, lo) + pre(H_ECNT, lo) + cel(C_BOTH, -1, lo) + cel(C_ECNT, X_ECNT, lo);    // #{qe <= ts-1}
+      const ull starts_le_te = pre(H_BOTH, hi) + pre(H_SCNT, hi);   // #{qs <= te}
+      const ull stops_lt_ts = pre(H_BOTH, lo) + pre(H_ECNT, lo);    // #{qe <= ts-1}
       total += starts_le_te - stops_lt_ts;
     } else {
       auto F = [&](int j) -> ull {
         const ull x = (ull)(int64_t)points[j];
-        const ull L = pre(H_BOTH, j) + cel(C_BOTH, -1, j);
-        const ull cs = pre(H_SCNT, j) + cel(C_SCNT, X_SCNT, j), ss = pre(H_SSUM, j) + cel(C_SSUM, X_SSUM, j);
-        const ull ce = pre(H_ECNT, j) + cel(C_ECNT, X_ECNT, j), se = pre(H_ESUM, j) + cel(C_ESUM, X_ESUM, j);
+        const ull L = pre(H_BOTH, j);
+        const ull cs = pre(H_SCNT, j), ss = pre(H_SSUM, j);
+        const ull ce = pre(H_ECNT, j), se = pre(H_ESUM, j);
         return L + (x + 1ull) * cs - ss - x * ce + se;
       };
       total += F(hi) - F(lo);
@@ -246,6 +234,7 @@ static int build_rank_structures(gtb_index *ix) {
   auto indexable = [&](int64_t k) {
     if (hi_of(k) <= lo_of(k)) return false;
     int64_t s = ix->h_start[lo_of(k)], e = ix->h_stop[hi_of(k) - 1];
+    if (ix->sorted_rules) return s <= e + 1;                          // the Sorted class skips nothing; zero-length spans and stops <= 0 are exact in ranks
     return !(s > e || e <= 0);                                        // :5610, :5659
   };
   // chromosome table and strand classes
@@ -379,7 +368,6 @@ extern "C" int gtb_index_reset(gtb_index *ix) {
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_hist.p, 0, sizeof(ull) * (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_direct.p, 0, sizeof(ull) * (size_t)std::max<int64_t>(ix->n_regions, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
-  GTB_TRY(gtb_cell_reset(ix));
   ix->queries_seen = 0;
   return GTB_OK;
 }
@@ -404,7 +392,8 @@ extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, un
   ix->ctx = ctx; ix->op = op;
   ix->match_gaps = (flags & GTB_MATCH_GAPS) != 0;
   ix->ignore_strand = (flags & GTB_IGNORE_STRAND) != 0;
-  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_CELL | GTB_ENGINE_BUCKET | GTB_ENGINE_DIRECT);
+  ix->sorted_rules = (flags & GTB_SORTED_RULES) != 0;
+  ix->engine = flags & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET | GTB_ENGINE_DIRECT);
   ix->n_regions = regions->n_regions; ix->n_intervals = regions->n_intervals;
   const size_t ni = (size_t)regions->n_intervals;
   ix->h_chrom.assign(regions->chrom, regions->chrom + ni);
@@ -429,7 +418,6 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   if (!ix) return;
   cudaSetDevice(ix->ctx->device);
   gtb_ctx_synchronize(ix->ctx);
-  gtb_cell_destroy(ix);
   gtb_bucket_destroy(ix);
   gtb_direct_destroy(ix);
   ix->d_class_of.release(); ix->d_present.release(); ix->d_goff.release(); ix->d_points.release();
@@ -454,7 +442,7 @@ static RankView rank_view(gtb_index *ix) {
   v.n_chrom = ix->n_chrom; v.n_class = ix->n_class;
   v.class_of = ix->d_class_of.p; v.chrom_present = ix->d_present.p;
   v.goff = ix->d_goff.p; v.points = ix->d_points.p; v.n_slots = ix->n_slots;
-  v.hist = ix->d_hist.p; v.err = ix->d_err.p;
+  v.hist = ix->d_hist.p; v.err = ix->d_err.p; v.sorted_rules = ix->sorted_rules ? 1 : 0;
   return v;
 }
 
@@ -466,11 +454,10 @@ static unsigned choose_engine(gtb_index *ix, const QueryView &q, bool batch_mult
   if (ix->engine & GTB_ENGINE_RANK) return GTB_ENGINE_RANK;
   // one pass where the index is small enough for byte counters in shared memory and the batch large enough to pay for the
   // per-batch dump of the counters; GTB_ENGINE_DIRECT asks for it whatever the batch size
-  if (!(ix->engine & (GTB_ENGINE_CELL | GTB_ENGINE_BUCKET)) && ((ix->engine & GTB_ENGINE_DIRECT) || q.n_regions >= (1 << 18)) &&
+  if (!(ix->engine & GTB_ENGINE_BUCKET) && ((ix->engine & GTB_ENGINE_DIRECT) || q.n_regions >= (1 << 18)) &&
       gtb_direct_supported(ix, q, batch_multi))
     return GTB_ENGINE_DIRECT;
-  if (!(ix->engine & GTB_ENGINE_CELL) && gtb_bucket_supported(ix, q, batch_multi)) return GTB_ENGINE_BUCKET;
-  if (!(ix->engine & GTB_ENGINE_BUCKET) && gtb_cell_supported(ix, q, batch_multi)) return GTB_ENGINE_CELL;
+  if (gtb_bucket_supported(ix, q, batch_multi)) return GTB_ENGINE_BUCKET;
   return GTB_ENGINE_RANK;
 }
 
@@ -478,7 +465,6 @@ static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi
   gtb_ctx *ctx = ix->ctx;
   if (q.n_regions <= 0) return GTB_OK;
   const unsigned engine = choose_engine(ix, q, batch_multi);
-  if (engine == GTB_ENGINE_CELL) return gtb_cell_accumulate(ix, q);
   if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
   if (engine == GTB_ENGINE_DIRECT) return gtb_direct_accumulate(ix, q);
   RankView rv = rank_view(ix);
@@ -626,9 +612,6 @@ static int finish_enqueue(gtb_index *ix, uint64_t *out, unsigned mem) {
   if (!ix || (!out && ix->n_regions > 0)) return GTB_ERR_ARG;
   gtb_ctx *ctx = ix->ctx;
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  CellFinalView cf{};
-  GTB_TRY(gtb_cell_scan_for_finish(ix, &cf));
-  cf.t_group = ix->d_t_base.p;
   const int64_t K = std::max<int64_t>(ix->n_slots, 1);
   // scan into a second buffer so that more batches may still be added after a finish
   if (ix->n_slots > 0)
@@ -637,10 +620,10 @@ static int finish_enqueue(gtb_index *ix, uint64_t *out, unsigned mem) {
     const unsigned grid = (unsigned)((ix->n_regions + 255) / 256);
     if (ix->op == GTB_OP_COVERAGE)
       GTB_LAUNCH(ctx, "finalize_coverage", finalize_kernel<true>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
-                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, cf, ix->d_direct.p, ix->d_out.p);
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
     else
       GTB_LAUNCH(ctx, "finalize_count", finalize_kernel<false>, grid, 256, 0, ix->n_regions, ix->d_t_off.p, ix->d_t_hi.p,
-                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, cf, ix->d_direct.p, ix->d_out.p);
+                 ix->d_t_lo.p, ix->d_t_base.p, ix->d_goff.p, ix->d_points.p, ix->d_hist_scan.p, K, ix->d_direct.p, ix->d_out.p);
     GTB_TRY(gtb_check_launch(ctx));
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(out, ix->d_out.p, sizeof(ull) * (size_t)ix->n_regions,
                                      (mem & GTB_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));

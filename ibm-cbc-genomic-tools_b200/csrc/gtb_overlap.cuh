@@ -15,12 +15,6 @@
 //  (2) ENUMERATE structures: indexable regions keyed by (chromosome, level, bin) in CSR order,
 //      for the cases ranks cannot express (count without -gaps when either side has
 //      multi-interval regions: "any pair of blocks overlaps", genomic_intervals.cpp:1167-1172).
-//  (3) CELL structures for the fast path (gtb_cell.cu): the groups' coordinate axes are cut into
-//      uniform cells of 2^k bp, laid end to end.  A bitmap of the "hot" cells (those containing an
-//      evaluation point) lives in shared memory; a query whose start and stop fall into one cold
-//      cell costs a single fire-and-forget red.global on an L2-resident per-cell table.  Only
-//      queries touching a hot cell compare against that cell's (<= 13) points, fetched as one
-//      32-byte record, and bump per-point correction counters.
 #pragma once
 #include "gtb_internal.cuh"
 
@@ -48,6 +42,7 @@ struct RankView {                  // device pointers
   int64_t n_slots;
   ull *hist;                       // planes of n_slots
   ull *err;                        // min over (index<<8 | code)
+  int32_t sorted_rules;            // GTB_SORTED_RULES: zero-length and stop <= 0 queries are admitted (the Sorted class has no such checks)
 };
 
 struct EnumView {
@@ -63,7 +58,7 @@ struct EnumView {
 struct gtb_index {
   gtb_ctx *ctx = nullptr;
   int op = GTB_OP_COUNT;
-  bool match_gaps = false, ignore_strand = false;
+  bool match_gaps = false, ignore_strand = false, sorted_rules = false;
   unsigned engine = GTB_ENGINE_AUTO;
   int64_t n_regions = 0, n_intervals = 0;
   bool index_multi = false;        // some index region has more than one interval
@@ -77,7 +72,7 @@ struct gtb_index {
   // rank
   int32_t n_chrom = 0, n_class = 0, n_groups = 0;
   int64_t n_slots = 0, n_targets = 0;
-  std::vector<int32_t> h_points, h_goff;       // kept for the cell engine's builder
+  std::vector<int32_t> h_points, h_goff;       // kept for the builders of the bucket and direct engines
   std::vector<int8_t> h_class_of;
   std::vector<uint8_t> h_present;
   dbuf<int8_t> d_class_of;
@@ -95,8 +90,6 @@ struct gtb_index {
   dbuf<int64_t> d_r_off;
   dbuf<ull> d_direct;
 
-  // cell engine state (gtb_cell.cu)
-  struct gtb_cell_state *cell = nullptr;
   // bucket engine state (gtb_bucket.cu)
   struct gtb_bucket_state *bucket = nullptr;
   // direct engine state (gtb_direct.cu)
@@ -117,51 +110,6 @@ struct gtb_index {
   } stages[2];
   int next_stage = 0;
 };
-
-// ---- cell engine (gtb_cell.cu) -----------------------------------------------------------------
-// planes of the per-cell tables (n_cells each) and per-slot correction tables (n_slots each)
-enum { C_BOTH = 0, C_SCNT = 1, C_ECNT = 2, C_SSUM = 3, C_ESUM = 4 };      // cell planes (count uses 0..2)
-enum { X_SCNT = 0, X_ECNT = 1, X_SSUM = 2, X_ESUM = 3 };                  // correction planes (count uses 0..1)
-
-struct __align__(16) HotRec {      // one 32-byte sector per hot cell
-  uint32_t slot_base;              // slot of the first evaluation point inside the cell
-  uint16_t n;                      // points in the cell; > HOT_MAX means "too many, use the general path"
-  uint16_t off[13];                // point & (cell width - 1), ascending
-};
-constexpr int HOT_MAX = 13;
-
-struct gtb_cell_state {
-  bool ready = false;
-  int k = 0;                       // cell width = 2^k
-  uint32_t n_cells = 0, n_words = 0, n_hot = 0;
-  int cell_planes = 3, corr_planes = 2;
-  size_t smem_bytes = 0;
-  dbuf<int32_t> d_gsize;           // [n_groups] largest evaluation point of the group (0 = empty group)
-  dbuf<uint32_t> d_gbase;          // [n_groups] first cell of the group
-  dbuf<int2> d_gtab;               // [n_groups] (gsize, gbase) interleaved
-  dbuf<uint32_t> d_bitmap, d_wrank;   // [n_words]
-  dbuf<HotRec> d_hot;              // [n_hot]
-  dbuf<uint32_t> d_slot_cell;      // [n_slots] cell of each slot's point (0xFFFFFFFF: point <= 0 or sentinel)
-  dbuf<ull> d_cells, d_cells_scan; // cell_planes * n_cells
-  dbuf<ull> d_corr;                // corr_planes * n_slots
-  bool dirty = false;              // something was accumulated since the last reset
-};
-
-struct CellFinalView {             // what finalize needs from the cell engine (all null/0 when unused)
-  const ull *cells_scan;           // inclusive prefix sums of the cell planes
-  const ull *corr;
-  const uint32_t *slot_cell;
-  const uint32_t *gbase;           // per group
-  const int32_t *t_group;          // per target
-  int64_t n_cells;
-};
-
-int gtb_cell_prepare(gtb_index *ix);
-int gtb_cell_accumulate(gtb_index *ix, const QueryView &q);
-int gtb_cell_reset(gtb_index *ix);
-int gtb_cell_scan_for_finish(gtb_index *ix, CellFinalView *out);
-void gtb_cell_destroy(gtb_index *ix);
-bool gtb_cell_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
 
 // ---- bucket engine (gtb_bucket.cu) ---------------------------------------------------------------
 int gtb_bucket_prepare(gtb_index *ix);

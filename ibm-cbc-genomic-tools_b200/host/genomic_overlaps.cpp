@@ -118,15 +118,31 @@ int main(int argc, char *argv[]) {
     rr.ReadAll(&ref);
     if (VERBOSE) std::cerr << "Reading from '" << ref_file << "'; number of regions = " << ref.n_regions() << "; format = " << rr.format() << "\n";
   }
-  if (IS_SORTED) {
-    gt::SortChecker sc; sc.by_strand = SORTED_BY_STRAND;
-    for (int64_t k = 0; k < ref.n_regions(); k++) {
+  // -S: the reference's SortedGenomicRegionSetOverlaps reads the index set lazily, while the queries advance
+  // (LoadIndexBuffer, genomic_intervals.cpp:5840-5875): an index region is checked for well-formedness when it becomes the
+  // current one and for sortedness when it is fetched, so index lines behind the last query's reach are never looked at.
+  // `index_pos` is that fetch position; advance_index() repeats the loop for one query (first interval's chromosome/strand/start,
+  // last interval's stop) and dies where the reference would.
+  int64_t index_pos = 0;
+  auto chrom_cmp = [&](int32_t a, int32_t b) { return a == b ? 0 : strcmp(chroms.name[a].c_str(), chroms.name[b].c_str()); };
+  auto advance_index = [&](int32_t qc, char qstrand, long qs, long qe) {
+    while (index_pos < ref.n_regions()) {
+      const int64_t k = index_pos, lo = ref.offset[k], hi = ref.offset[k + 1];
       if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line(k), "index regions should be compatible, sorted and non-overlapping!");
-      const int64_t i = ref.offset[k];
-      if (!sc.Accept(chroms.name[ref.chrom[i]], (char)ref.strand[i], ref.start[i]))
-        gt::die_line(ref.line(k), std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+      int d = chrom_cmp(qc, ref.chrom[lo]);                              // GenomicRegion::CalcDirection, :1225-1237
+      if (d == 0 && SORTED_BY_STRAND) d = (int)qstrand - (int)(char)ref.strand[lo];
+      if (d == 0) d = (long)ref.stop[hi - 1] < qs ? 1 : qe < (long)ref.start[lo] ? -1 : 0;
+      if (d < 0) break;
+      index_pos++;
+      if (index_pos < ref.n_regions()) {                                 // IsBefore(previous), :396-401
+        const int64_t a = ref.offset[index_pos];
+        int c = chrom_cmp(ref.chrom[a], ref.chrom[lo]);
+        bool before = c < 0;
+        if (c == 0) before = SORTED_BY_STRAND && ref.strand[a] != ref.strand[lo] ? (char)ref.strand[a] < (char)ref.strand[lo] : ref.start[a] < ref.start[lo];
+        if (before) gt::die_line(ref.line(index_pos), std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+      }
     }
-  }
+  };
 
   timer.Mark("load_reference");
   // The driver uses one GPU.  On a multi-GPU host the CUDA runtime would initialise every visible device first (seconds);
@@ -137,7 +153,8 @@ int main(int argc, char *argv[]) {
   if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
   timer.Mark("cuda_context");
   const bool want_coverage = op == "coverage" || op == "density";
-  const unsigned flags = (MATCH_GAPS ? GTB_MATCH_GAPS : 0u) | (IGNORE_STRAND ? GTB_IGNORE_STRAND : 0u);
+  // -S: the Sorted class's admission (no fatal checks on zero-length or non-positive intervals, no index region skipped)
+  const unsigned flags = (MATCH_GAPS ? GTB_MATCH_GAPS : 0u) | (IGNORE_STRAND ? GTB_IGNORE_STRAND : 0u) | (IS_SORTED ? GTB_SORTED_RULES : 0u);
   gtb_index *index = nullptr;
   int64_t err_index = -1;
   gtb_set ref_set = as_set(ref);
@@ -167,6 +184,7 @@ int main(int argc, char *argv[]) {
           if (!gt::RegionWellFormed(b, k)) gt::die_line(b.line(k), "query regions should be compatible, sorted and non-overlapping!");
           if (!sc.Accept(chroms.name[b.chrom[i]], (char)b.strand[i], b.start[i]))
             gt::die_line(b.line(k), std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+          advance_index(b.chrom[i], (char)b.strand[i], b.start[i], b.stop[b.offset[k + 1] - 1]);
         }
       gtb_set qs = as_set(b);
       check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");

@@ -14,12 +14,12 @@ LIB_PATH = os.environ.get("GTB200_LIB") or os.path.join(PKG_ROOT, "lib", "libgtb
 
 MATCH_GAPS = 1 << 0
 IGNORE_STRAND = 1 << 1
+SORTED_RULES = 1 << 2
 MEM_HOST = 0
 MEM_DEVICE = 1 << 8
 ENGINE_AUTO = 0
 ENGINE_ENUMERATE = 1 << 16
 ENGINE_RANK = 1 << 17
-ENGINE_CELL = 1 << 18
 ENGINE_BUCKET = 1 << 19
 ENGINE_DIRECT = 1 << 20
 OP_COUNT = 0

@@ -55,6 +55,11 @@ typedef struct {
 enum {
   GTB_MATCH_GAPS       = 1u << 0,
   GTB_IGNORE_STRAND    = 1u << 1,
+  /* the admission rules of SortedGenomicRegionSetOverlaps (what -S selects, genomic_intervals.cpp:5807-5937) instead of the
+   * Unsorted class's: no fatal check on queries with stop <= 0 or start == stop + 1 (a zero-length BED line), no index region
+   * skipped for those reasons; both are matched with the raw predicate of CalcDirection (:1225-1237).  Sortedness itself is
+   * the caller's to check (the drivers do).  Intervals with start > stop + 1 remain GTB_ERR_QUERY_START_GT_STOP / skipped. */
+  GTB_SORTED_RULES     = 1u << 2,
   /* where the arrays of a query/read gtb_set live */
   GTB_MEM_HOST         = 0u,        /* host memory (pinned or pageable); copied inside the call */
   GTB_MEM_DEVICE       = 1u << 8,   /* device pointers on the context's device                   */
@@ -62,7 +67,6 @@ enum {
   GTB_ENGINE_AUTO      = 0u,
   GTB_ENGINE_ENUMERATE = 1u << 16,  /* candidate enumeration (general; any region shape)         */
   GTB_ENGINE_RANK      = 1u << 17,  /* rank/rank-sum with global binary search                    */
-  GTB_ENGINE_CELL      = 1u << 18,  /* single pass: genome-cell tables, hot-cell bitmap in shared memory        */
   GTB_ENGINE_BUCKET    = 1u << 19,  /* two passes: partition by genome bucket, rank in shared memory (any index size)        */
   GTB_ENGINE_DIRECT    = 1u << 20   /* one pass: slot lookup in an L2-resident cell table, byte counters in shared memory
                                        (count, up to ~200 k evaluation points; the default there)                           */

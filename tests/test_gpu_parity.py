@@ -9,17 +9,23 @@ import support
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "cell": 1 << 18, "bucket": 1 << 19, "direct": 1 << 20}
-CELL_KS = ("3", "6", "10")      # cell widths 8 / 64 / 1024 bp: mostly-cold, mixed, and overfull-hot-cell regimes
+ENGINES = {"auto": 0, "rank": 1 << 17, "enumerate": 1 << 16, "bucket": 1 << 19, "direct": 1 << 20}
+CELL_KS = ("3", "6", "10")      # three settings of the bucket / direct engines' knobs (cell and bucket widths, kernel forms)
 
 
 @pytest.fixture(params=CELL_KS)
 def cell_k(request, monkeypatch):
-    monkeypatch.setenv("GTB_CELL_K", request.param)
     # the bucket engine's knobs ride along: cell width and bucket width (12..16 bits -> several buckets on the toy genomes)
     monkeypatch.setenv("GTB_BUCKET_K", {"3": "2", "6": "5", "10": "8"}[request.param])
     monkeypatch.setenv("GTB_BUCKET_BITS", {"3": "9", "6": "12", "10": "16"}[request.param])
     monkeypatch.setenv("GTB_DIRECT_CELL_BITS", {"3": "4", "6": "7", "10": "12"}[request.param])   # the direct engine's cell width
+    # the direct engine's two forms: "3" the first (one gather per query), "6" the second with the narrowest coarse cells and a
+    # queue so small that entries overflow and are served on the spot, "10" the second as it configures itself
+    if request.param == "3":
+        monkeypatch.setenv("GTB_DIRECT_FORM", "1")
+    if request.param == "6":
+        monkeypatch.setenv("GTB_DIRECT2_CELL_BP", "16")
+        monkeypatch.setenv("GTB_DIRECT2_QCAP", "64")
     if request.param == "6":
         monkeypatch.setenv("GTB_BUCKET_PAGED", "1")       # the paged form of pass 1
     if request.param == "3":
@@ -49,8 +55,8 @@ def oracle():
 @pytest.mark.parametrize("engine", list(ENGINES))
 @pytest.mark.parametrize("case", goldens.overlap_cases(), ids=lambda c: c["name"])
 def test_overlap_golden(ctx, case, engine, cell_k):
-    if engine not in ("cell", "bucket", "direct") and cell_k != CELL_KS[0]:
-        pytest.skip("cell width only matters to the cell / bucket / direct engines")
+    if engine not in ("bucket", "direct") and cell_k != CELL_KS[0]:
+        pytest.skip("cell width only matters to the bucket / direct engines")
     multi = case["ioff"] is not None or case["qoff"] is not None
     for (op, flags), want in case["expect"].items():
         if engine == "rank" and multi and op == "count" and not (flags & 1):
@@ -471,7 +477,7 @@ def test_synth_range_matches_numpy(gtb, ctx):
 
 def test_full_size_properties(gtb, ctx, oracle):
     """BASELINE.json configs[1] at full size (100 M reads x 60 000 regions, strand-aware), where the oracle is too slow:
-    size-independent properties.  (1) three independent device algorithms agree (bucket, cell, rank engines);
+    size-independent properties.  (1) three independent device algorithms agree (bucket, direct, rank engines);
     (2) permutation invariance; (3) additivity over query batches; (4) checksum of checksums: sum_r count[r] equals
     sum_q #regions overlapping q, the latter from an independent per-QUERY formulation (torch.searchsorted over the
     regions' sorted starts / stops); (5) coverage >= count and coverage <= 50 * count for 50-bp reads;
@@ -494,7 +500,7 @@ def test_full_size_properties(gtb, ctx, oracle):
 
     base = run(dev)
     assert np.array_equal(run(dev, engine=gtb.ENGINE_BUCKET), base)
-    assert np.array_equal(run(dev, engine=gtb.ENGINE_CELL), base)
+    assert np.array_equal(run(dev, engine=gtb.ENGINE_DIRECT), base)
     assert np.array_equal(run(dev, engine=gtb.ENGINE_RANK), base)
     assert np.array_equal(run(dev, parts=3), base)                                  # 33 333 334-read batches (unaligned tails)
     perm = torch.randperm(n, device="cuda")
