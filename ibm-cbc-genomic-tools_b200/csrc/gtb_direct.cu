@@ -34,7 +34,6 @@
 // (genomic_intervals.cpp:5719-5745), the overlap predicate (:624-630, :5227-5229) and CalcOverlap (:427-432) through the rank
 // formulation of SURVEY.md section 7.1 -- see gtb_overlap.cuh.
 #include "gtb_rank_device.cuh"
-#include "gtb_direct2_tables.h"
 #include <algorithm>
 
 namespace {
@@ -271,284 +270,6 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   for (uint32_t i = threadIdx.x; i < dv.n_words / 4; i += DR_THREADS) row[i] = reinterpret_cast<const uint4 *>(s_cnt)[i];
 }
 
-// =================================================================================================================================
-// Second form of the one-pass kernel: fewer than one L2 gather per query.
-//
-// The first form above is bound by the L1TEX pipe: a fully divergent 8-byte gather costs one tag cycle per lane (1.05 SM-cycles per
-// query measured, profiles/microbench/gather_rate_b200.txt), whatever L2 does, so one gather per query caps it near 0.48 ms per
-// 100 M queries.  Most reads, however, start nowhere near an evaluation point.  This form keeps a rank structure of the whole
-// genome in shared memory next to the byte counters (gtb_direct2_tables.h: one bit per coarse cell + an absolute slot prefix per 46
-// cells) and resolves every read that starts and ends in a cell without points with two shared-memory loads; only the others are
-// looked up in the L2-resident cell table of the first form.  Those must not drag the whole warp through the slow code, so
-// they are COMPACTED: the warps push them (start, chromosome/strand, length: 8 bytes) into a queue in shared memory, and one
-// iteration later the CTA works the queue off with all lanes busy -- gathers issued before the next tile's fast work, consumed
-// after it, one barrier per tile.  The queue is double-buffered; an entry that does not fit is served on the spot.
-//
-// Shared memory (hg19 x 60 k regions: 117 KB of counters + ~67 KB of records + 12 KB of queue <= 195 KB, which leaves the L1 the
-// 60 KB it needs to track the gathers' misses):
-//   [ byte counters | 32 dummy words | records | chromosome table | queue[2][qcap] | tails[2] ]
-constexpr int D2_THREADS = 512;
-constexpr int D2_ITEMS = 4;
-constexpr int D2_TILE = D2_THREADS * D2_ITEMS;
-constexpr int D2_DRAIN = 2;                                       // queue entries per thread and iteration: qcap <= D2_DRAIN * D2_THREADS
-
-struct Direct2View {
-  D2Params p;
-  const D2Rec *recs;                // [p.n_rec]
-  const uint32_t *gtab;             // [p.n_gt]
-  uint32_t qcap;                    // entries per queue buffer
-};
-
-// One query the fast way could not serve, with its cell entry already fetched: the first form's per-item logic.  All 32 lanes
-// call; act = this lane has a query.
-template <bool COVERAGE>
-__device__ __forceinline__ void d2_finish(bool act, int32_t s, uint32_t meta, uint2 ent, const RankView &rv, const DirectView &dv,
-                                          uint32_t *s_cnt, uint32_t len0m1, ull unit, int lane, bool &overflowed, uint32_t &odd) {
-  const uint32_t cbits = (uint32_t)dv.cbits, cmask = (1u << cbits) - 1u, last = dv.stride - 1u;
-  const int32_t e = s + (int32_t)(meta & 0xFFFFFFu);
-  const uint32_t gi = meta >> 24;
-  uint2 ee = ent;
-  if (act && (((uint32_t)s ^ (uint32_t)e) >> cbits)) ee = dr_gather(dv.cells + gi * dv.stride + min((uint32_t)e >> cbits, last));
-  const uint32_t fl = ent.x | (ee.x & (DR_GENERAL | DR_SCAN));
-  uint32_t jS = (ent.x & 0xFFFFFFu) + dr_below(ent.y, (uint32_t)s & cmask);
-  uint32_t jE = (ee.x & 0xFFFFFFu) + dr_below(ee.y, (uint32_t)e & cmask);
-  const bool skip = !act || (fl & (DR_GENERAL | DR_NOTHING)) != 0u;
-  if (!skip && (fl & DR_SCAN)) {
-    jS = dr_scan(rv.points, ent.x & 0xFFFFFFu, s);
-    jE = dr_scan(rv.points, max(jS, ee.x & 0xFFFFFFu), e);
-  }
-  if (act && (fl & DR_GENERAL))                                       // a group whose points are all <= 0 (the query itself is valid: no error to report)
-    dr_general<COVERAGE>(rv, (int32_t)(gi / dv.nsig), s, e, (gi % dv.nsig) ? '-' : '+', 0);
-  bool both = !skip && jS == jE && (!COVERAGE || (uint32_t)(e - s) == len0m1);
-  // clustered input: neighbouring entries of the queue in one slot -> slots shared by eight or more lanes leave as one reduction
-  const uint32_t key = both ? jS : 0x80000000u | (uint32_t)lane;
-  const uint32_t up = __shfl_up_sync(0xffffffffu, key, 1);
-  if (__any_sync(0xffffffffu, lane > 0 && up == key)) {
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (both && __popc(peers) >= 8) {
-      if ((peers & ((1u << lane) - 1u)) == 0u) dr_red64(dv.delta + jS, (ull)__popc(peers) * unit);
-      both = false;
-      act = false;
-    }
-  }
-  const uint32_t sh = (jS & 3u) * 8u;
-  const uint32_t old = atomicAdd(&s_cnt[both ? (jS >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << sh : 0u);
-  if (both) {
-    const uint32_t ob = (old >> sh) & 0xFFu;
-    if (ob >= 127u) {
-      if (ob == 127u) { atomicSub(&s_cnt[jS >> 2], 128u << sh); dr_red64(dv.delta + jS, 128ull * unit); }
-      overflowed |= ob == 255u;
-    }
-  } else if (act && !skip) {
-    if (COVERAGE && jS == jE) {                                        // a query of another length
-      dr_red64(dv.delta + jS, (ull)((int64_t)e - (int64_t)s + 1));
-      odd++;
-    } else {
-      dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS, 1ull);
-      dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE, 1ull);
-      if (COVERAGE) {
-        dr_red64(dv.delta + (ull)H_SSUM * (ull)rv.n_slots + jS, (ull)(int64_t)s);
-        dr_red64(dv.delta + (ull)H_ESUM * (ull)rv.n_slots + jE, (ull)(int64_t)e);
-      }
-    }
-  }
-}
-
-template <bool COVERAGE>
-__global__ void __launch_bounds__(D2_THREADS, 1) direct2_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
-                                                                        const __grid_constant__ DirectView dv, const __grid_constant__ Direct2View d2) {
-  extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word, then one dummy word per lane
-  D2Rec *const s_rec = reinterpret_cast<D2Rec *>(s_cnt + dv.n_words + 32u);
-  uint32_t *const s_gt = reinterpret_cast<uint32_t *>(s_rec + d2.p.n_rec);
-  uint2 *const s_queue = reinterpret_cast<uint2 *>(s_gt + ((d2.p.n_gt + 1u) & ~1u));
-  uint32_t *const s_tail = reinterpret_cast<uint32_t *>(s_queue + 2u * d2.qcap);
-  for (uint32_t i = threadIdx.x; i < dv.n_words + 32u; i += D2_THREADS) s_cnt[i] = 0;
-  for (uint32_t i = threadIdx.x; i < d2.p.n_rec; i += D2_THREADS) s_rec[i] = d2.recs[i];
-  for (uint32_t i = threadIdx.x; i < d2.p.n_gt; i += D2_THREADS) s_gt[i] = d2.gtab[i];
-  if (threadIdx.x < 2) s_tail[threadIdx.x] = 0;
-  __syncthreads();
-  const D2Params P = d2.p;
-  const uint32_t cbits = (uint32_t)dv.cbits, stride = dv.stride, last = stride - 1u, sigmask = dv.nsig - 1u, n_chrom = (uint32_t)dv.n_chrom;
-  const uint32_t qcap = d2.qcap;
-  const int64_t n = q.n_regions;
-  const int64_t n_full = n / D2_TILE;
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t len0m1 = COVERAGE && n > 0 ? (uint32_t)(q.stop[0] - q.start[0]) : 0u;   // the common length - 1
-  const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)len0m1 + 1ull : 1ull;
-  uint32_t odd = 0;
-  bool overflowed = false;
-  uint32_t d_cur = 0, d_prev = 0;                                      // tickets of the queue buffer being filled / being worked off that are already done
-  uint32_t it = 0;
-
-  uint4 nc, ns, ne;
-  uint32_t nst;
-  int64_t tile = blockIdx.x;
-  if (tile < n_full) {
-    const int64_t first = tile * D2_TILE + (int64_t)threadIdx.x * D2_ITEMS;
-    nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
-  }
-  for (; tile < n_full; tile += gridDim.x, it++) {
-    const uint4 cc4 = nc, cs = ns, ce = ne;
-    const uint32_t stw = nst;
-    const int64_t next = tile + gridDim.x;
-    if (next < n_full) {
-      const int64_t first = next * D2_TILE + (int64_t)threadIdx.x * D2_ITEMS;
-      nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
-    }
-    const uint32_t b = it & 1u;
-    uint2 *const q_cur = s_queue + b * qcap;
-    const uint2 *const q_prev = s_queue + (b ^ 1u) * qcap;
-    // ---- the previous tile's queue, first half: fetch the entries and send their gathers off
-    const uint32_t prev_total = s_tail[b ^ 1u] - d_prev;               // complete: the pushes ended before the last barrier
-    const uint32_t n_prev = min(prev_total, qcap);
-    uint2 de[D2_DRAIN], dent[D2_DRAIN];
-#pragma unroll
-    for (int r = 0; r < D2_DRAIN; r++) {
-      const uint32_t j = threadIdx.x + (uint32_t)r * D2_THREADS;
-      de[r] = make_uint2(0u, 0u); dent[r] = make_uint2(0u, 0u);
-      if (j < n_prev) {
-        de[r] = q_prev[j];
-        dent[r] = dr_gather(dv.cells + (de[r].y >> 24) * stride + min(de[r].x >> cbits, last));
-      }
-    }
-    // ---- this tile, the fast way
-    const uint32_t c[D2_ITEMS] = {cc4.x, cc4.y, cc4.z, cc4.w};
-    const int32_t s[D2_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
-    const int32_t e[D2_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
-    const uint32_t xw = stw ^ 0x2B2B2B2Bu;                             // 0x00 / 0x06 in the bytes of '+' / '-' queries
-    uint32_t general = 0;                                              // bit i: item i takes the general path (the reference's fatal cases, odd strands, very long reads)
-    if (xw & 0xF9F9F9F9u) {
-#pragma unroll
-      for (int i = 0; i < D2_ITEMS; i++) general |= ((xw >> (8 * i)) & 0xF9u) ? (1u << i) : 0u;
-    }
-    uint32_t slot[D2_ITEMS];
-    uint32_t fast = 0, slow = 0;
-#pragma unroll
-    for (int i = 0; i < D2_ITEMS; i++) {
-      const uint32_t len = (uint32_t)(e[i] - s[i]);
-      if (!(s[i] >= 1 && s[i] <= e[i] && len < (1u << 24))) general |= 1u << i;
-      const bool here = d2_lookup(P, s_gt, s_rec, min(c[i], n_chrom), (xw >> (8 * i + 1)) & sigmask, (uint32_t)s[i], len, slot[i]);
-      if (!((general >> i) & 1u)) { if (here) fast |= 1u << i; else slow |= 1u << i; }
-    }
-    // ---- the others go into the queue: one reservation per warp
-    {
-      const uint32_t m0 = __ballot_sync(0xffffffffu, slow & 1u), m1 = __ballot_sync(0xffffffffu, slow & 2u);
-      const uint32_t m2 = __ballot_sync(0xffffffffu, slow & 4u), m3 = __ballot_sync(0xffffffffu, slow & 8u);
-      const uint32_t n0 = __popc(m0), n1 = n0 + __popc(m1), n2 = n1 + __popc(m2), n3 = n2 + __popc(m3);
-      if (n3) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&s_tail[b], n3);
-        base = __shfl_sync(0xffffffffu, base, 0) - d_cur;
-        const uint32_t pos[D2_ITEMS] = {base + __popc(m0 & lt), base + n0 + __popc(m1 & lt), base + n1 + __popc(m2 & lt), base + n2 + __popc(m3 & lt)};
-#pragma unroll
-        for (int i = 0; i < D2_ITEMS; i++)
-          if ((slow >> i) & 1u) {
-            const uint32_t gi = min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask);
-            const uint2 ent = make_uint2((uint32_t)s[i], (gi << 24) | (uint32_t)(e[i] - s[i]));
-            if (pos[i] < qcap) { q_cur[pos[i]] = ent; slow &= ~(1u << i); }          // what stays in `slow` did not fit
-          }
-      }
-    }
-    // position-sorted input: the warp's 128 queries in one slot leave as one reduction
-    const uint32_t lead = __shfl_sync(0xffffffffu, slot[0], 0);
-    bool same = fast == 0xFu;
-#pragma unroll
-    for (int i = 0; i < D2_ITEMS; i++) same = same && slot[i] == lead && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
-    if (__all_sync(0xffffffffu, same)) {
-      if (lane == 0) dr_red64(dv.delta + lead, (ull)(32 * D2_ITEMS) * unit);
-      fast = 0;
-    } else if (__any_sync(0xffffffffu, ((fast & 0x3u) == 0x3u && slot[0] == slot[1]) || ((fast & 0x6u) == 0x6u && slot[1] == slot[2]) ||
-                                        ((fast & 0xCu) == 0xCu && slot[2] == slot[3]))) {
-      // clustered input (see the first form): slots shared by eight or more lanes leave as one reduction each
-#pragma unroll
-      for (int i = 0; i < D2_ITEMS; i++) {
-        const bool both = ((fast >> i) & 1u) && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
-        const uint32_t peers = __match_any_sync(0xffffffffu, both ? slot[i] : 0x80000000u | (uint32_t)lane);
-        if (both && __popc(peers) >= 8) {
-          if ((peers & lt) == 0u) dr_red64(dv.delta + slot[i], (ull)__popc(peers) * unit);
-          fast &= ~(1u << i);
-        }
-      }
-    }
-    // the four shared atomics back to back, then the returned bytes
-    uint32_t old[D2_ITEMS];
-#pragma unroll
-    for (int i = 0; i < D2_ITEMS; i++) {
-      const bool both = ((fast >> i) & 1u) && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
-      old[i] = atomicAdd(&s_cnt[both ? (slot[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((slot[i] & 3u) * 8u) : 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < D2_ITEMS; i++) {
-      if ((fast >> i) & 1u) {
-        if (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1) {
-          const uint32_t sh = (slot[i] & 3u) * 8u;
-          const uint32_t ob = (old[i] >> sh) & 0xFFu;
-          if (ob >= 127u) {
-            if (ob == 127u) { atomicSub(&s_cnt[slot[i] >> 2], 128u << sh); dr_red64(dv.delta + slot[i], 128ull * unit); }
-            overflowed |= ob == 255u;
-          }
-        } else {                                                       // a query of another length
-          dr_red64(dv.delta + slot[i], (ull)((int64_t)e[i] - (int64_t)s[i] + 1));
-          odd++;
-        }
-      }
-    }
-    if (general) {
-#pragma unroll
-      for (int i = 0; i < D2_ITEMS; i++)
-        if ((general >> i) & 1u)
-          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * D2_TILE + (int64_t)threadIdx.x * D2_ITEMS + i);
-    }
-    // queue full (rare: the buffers hold several standard deviations more than a tile of uniform reads sends): served on the spot
-    if (__any_sync(0xffffffffu, slow != 0u)) {
-#pragma unroll
-      for (int i = 0; i < D2_ITEMS; i++) {
-        const bool act = (slow >> i) & 1u;
-        if (!__any_sync(0xffffffffu, act)) continue;
-        const uint32_t gi = min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask);
-        uint2 ent = make_uint2(0u, 0u);
-        if (act) ent = dr_gather(dv.cells + gi * stride + min((uint32_t)s[i] >> cbits, last));
-        d2_finish<COVERAGE>(act, s[i], (gi << 24) | (uint32_t)(e[i] - s[i]), ent, rv, dv, s_cnt, len0m1, unit, lane, overflowed, odd);
-      }
-    }
-    // ---- the previous tile's queue, second half: the gathers have had the whole fast pass to arrive
-#pragma unroll
-    for (int r = 0; r < D2_DRAIN; r++) {
-      const bool act = threadIdx.x + (uint32_t)r * D2_THREADS < n_prev;
-      if (__any_sync(0xffffffffu, act))
-        d2_finish<COVERAGE>(act, (int32_t)de[r].x, de[r].y, dent[r], rv, dv, s_cnt, len0m1, unit, lane, overflowed, odd);
-    }
-    const uint32_t done_prev = d_prev + prev_total;                    // the buffer just worked off is the one the next tile fills
-    d_prev = d_cur; d_cur = done_prev;
-    __syncthreads();
-  }
-  // what the last tile queued
-  if (it > 0) {
-    const uint32_t bl = (it - 1u) & 1u;
-    const uint32_t n_last = min(s_tail[bl] - d_prev, qcap);
-    const uint2 *const q_last = s_queue + bl * qcap;
-    for (uint32_t j0 = 0; j0 < n_last; j0 += D2_THREADS) {
-      const uint32_t j = j0 + threadIdx.x;
-      const bool act = j < n_last;
-      if (!__any_sync(0xffffffffu, act)) continue;
-      uint2 en = make_uint2(0u, 0u), ent = make_uint2(0u, 0u);
-      if (act) { en = q_last[j]; ent = dr_gather(dv.cells + (en.y >> 24) * stride + min(en.x >> cbits, last)); }
-      d2_finish<COVERAGE>(act, (int32_t)en.x, en.y, ent, rv, dv, s_cnt, len0m1, unit, lane, overflowed, odd);
-    }
-  }
-  // the last, partial tile: general path
-  if ((int64_t)blockIdx.x == n_full % gridDim.x) {
-    for (int64_t r = n_full * D2_TILE + threadIdx.x; r < n; r += D2_THREADS)
-      dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
-  }
-  if (overflowed) atomicMax(dv.flag, dv.gen);
-  if (COVERAGE && odd) atomicAdd(dv.flag + 1, odd);
-  __syncthreads();
-  uint4 *row = reinterpret_cast<uint4 *>(dv.cta_counts + (size_t)blockIdx.x * dv.n_words);
-  for (uint32_t i = threadIdx.x; i < dv.n_words / 4; i += D2_THREADS) row[i] = reinterpret_cast<const uint4 *>(s_cnt)[i];
-}
-
 // Sums the CTAs' byte counters and the delta planes into the index's histogram planes and clears the delta planes -- or, if a
 // byte counter overflowed somewhere in this batch (flag == the batch's generation), only clears them and then sends every
 // query through the general path straight into the histogram planes (nothing else touches those in that case).
@@ -614,13 +335,6 @@ struct gtb_direct_state {
   uint32_t *h_flag = nullptr;                                          // pinned: where the flag words land
   cudaEvent_t flag_copied = nullptr;
   bool check_pending = false;
-  // second form (shared-memory rank structure + queue): absent when the tables do not fit next to the counters
-  bool v2 = false;
-  D2Params p2{};
-  uint32_t qcap = 0;
-  size_t smem2 = 0;
-  dbuf<D2Rec> d_recs;
-  dbuf<uint32_t> d_gtab;
 };
 
 int gtb_direct_prepare(gtb_index *ix) {
@@ -698,32 +412,6 @@ int gtb_direct_prepare(gtb_index *ix) {
     fprintf(stderr, "[gtb direct] slots %lld cells %llu (2^%d bp, %u per block, %.1f MB allocated, %.1f MB within reach) general cells %zu smem %zu\n",
             (long long)ix->n_slots, (unsigned long long)cells, cbits, (unsigned)stride, cells * 8 / 1e6, (double)(span >> cbits) * 8 / 1e6, many, smem);
 
-  // The second form: rank records + queue next to the counters, within the carve-out that leaves the L1 room for the gathers
-  // (GTB_DIRECT2_SMEM_KB, default 195; GTB_DIRECT_FORM=1 keeps the first form; GTB_DIRECT2_CELL_BP forces a cell width).
-  ds->v2 = false;
-  {
-    const char *form = getenv("GTB_DIRECT_FORM");
-    const char *kb = getenv("GTB_DIRECT2_SMEM_KB");
-    const char *qc = getenv("GTB_DIRECT2_QCAP");
-    const char *cw = getenv("GTB_DIRECT2_CELL_BP");
-    const size_t limit = std::min<size_t>(ctx->smem_optin, (size_t)(kb ? std::max(16, atoi(kb)) : 195) * 1024);
-    const uint32_t qcap = (uint32_t)std::max(64, std::min(D2_DRAIN * D2_THREADS, qc ? atoi(qc) : 768));
-    const uint32_t n_gt = (uint32_t)ix->n_chrom + 1;
-    const size_t fixed = ((size_t)n_words + 32) * 4 + (size_t)((n_gt + 1u) & ~1u) * 4 + (size_t)2 * qcap * 8 + 16;
-    const int cls_sig[2] = {cp, cm};
-    D2Tables t;
-    if (!(form && atoi(form) == 1) && ((uint64_t)ix->n_chrom + 1) * nsig <= 256 && fixed + 64 * 8 <= limit &&
-        d2_build(ix->n_chrom, ix->n_class, cls_sig, ix->h_goff, ix->h_points, (limit - fixed) / 8, t, cw ? (uint32_t)std::max(16, atoi(cw)) : 0u)) {
-      GTB_TRY(upload_d(ctx, ds->d_recs, t.recs));
-      GTB_TRY(upload_d(ctx, ds->d_gtab, t.gtab));
-      GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-      ds->p2 = t.p; ds->qcap = qcap; ds->smem2 = fixed + (size_t)t.p.n_rec * 8; ds->v2 = true;
-      if (getenv("GTB_DEBUG_DIRECT"))
-        fprintf(stderr, "[gtb direct] second form: cells of %u bp, %u records (%.1f KB), queue 2 x %u, shared memory %zu B; cells %llu: %.1f %% with points, %.1f %% phantom\n",
-                t.p.cell_w, t.p.n_rec, t.p.n_rec * 8 / 1024.0, qcap, ds->smem2, (unsigned long long)t.cells_total,
-                100.0 * t.cells_point / std::max<uint64_t>(1, t.cells_total), 100.0 * t.cells_phantom / std::max<uint64_t>(1, t.cells_total));
-    }
-  }
   ds->ready = true; ds->failed = false;
   return GTB_OK;
 }
@@ -762,23 +450,6 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   dv.gen = ds->gen;
   RankView rv_hist = rv;
   rv_hist.hist = ix->d_hist.p;
-  if (ds->v2) {
-    Direct2View d2;
-    d2.p = ds->p2; d2.recs = ds->d_recs.p; d2.gtab = ds->d_gtab.p; d2.qcap = ds->qcap;
-    const int64_t tiles = q.n_regions / D2_TILE;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ds->grid, tiles));
-    if (ix->op == GTB_OP_COVERAGE) {
-      GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct2_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem2));
-      GTB_LAUNCH(ctx, "direct_coverage", direct2_count_kernel<true>, grid, D2_THREADS, ds->smem2, q, rv, dv, d2);
-      GTB_TRY(gtb_check_launch(ctx));
-      GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<true>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
-    } else {
-      GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct2_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem2));
-      GTB_LAUNCH(ctx, "direct_count", direct2_count_kernel<false>, grid, D2_THREADS, ds->smem2, q, rv, dv, d2);
-      GTB_TRY(gtb_check_launch(ctx));
-      GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<false>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
-    }
-  } else {
   const int64_t tiles = q.n_regions / DR_TILE;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ds->grid, tiles));
   if (ix->op == GTB_OP_COVERAGE) {
@@ -792,7 +463,6 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
     GTB_TRY(gtb_check_launch(ctx));
     GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<false>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
   }
-  }
   ds->queries_since_check += q.n_regions;
   if (!ds->check_pending) {
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -804,10 +474,20 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   return gtb_check_launch(ctx);
 }
 
+// gtb_index_reset: the values go back to zero and a new query stream begins, so what the watchdog concluded about the last
+// one (byte counters overflowing, too many odd-length reads under coverage) is forgotten -- the engine is tried again.
+// The device-side odd-length counter keeps running; the host's copy of it is what the next check subtracts.
+void gtb_direct_reset(gtb_index *ix) {
+  gtb_direct_state *ds = ix->direct;
+  if (!ds) return;
+  ds->off = false;
+  ds->queries_since_check = 0;
+}
+
 void gtb_direct_destroy(gtb_index *ix) {
   gtb_direct_state *ds = ix->direct;
   if (!ds) return;
-  ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release(); ds->d_recs.release(); ds->d_gtab.release();
+  ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
   if (ds->h_flag) cudaFreeHost(ds->h_flag);
   if (ds->flag_copied) cudaEventDestroy(ds->flag_copied);
   delete ds;

@@ -368,6 +368,7 @@ extern "C" int gtb_index_reset(gtb_index *ix) {
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_hist.p, 0, sizeof(ull) * (size_t)ix->planes * (size_t)std::max<int64_t>(ix->n_slots, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_direct.p, 0, sizeof(ull) * (size_t)std::max<int64_t>(ix->n_regions, 1), ctx->stream));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
+  gtb_direct_reset(ix);
   ix->queries_seen = 0;
   return GTB_OK;
 }
@@ -382,6 +383,12 @@ extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, un
     return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
   if (regions->n_intervals > 0 && (!regions->chrom || !regions->start || !regions->stop || !regions->strand))
     return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
+  if (regions->region_offset) {
+    if (regions->region_offset[0] != 0 || regions->region_offset[regions->n_regions] != regions->n_intervals)
+      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must run from 0 to n_intervals");
+    for (int64_t k = 0; k < regions->n_regions; k++)
+      if (regions->region_offset[k + 1] < regions->region_offset[k]) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be non-decreasing");
+  }
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   for (int64_t k = 0; k < regions->n_regions; k++)
     if (!region_well_formed(regions, k)) {                             // fatal in the reference, :5607
@@ -501,8 +508,20 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
   if (!queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  const bool batch_multi = queries->region_offset != nullptr && queries->n_intervals != queries->n_regions;
-  // a CSR whose regions all have one interval is passed on as the plain single-interval layout
+  // a CSR is judged by its offsets, not by its totals (regions of 0 and 2 intervals would add up to "one each"); one whose
+  // regions all have one interval is passed on as the plain single-interval layout.  Device-resident offsets are taken as they are.
+  bool batch_multi = false;
+  if (queries->region_offset && !(mem & GTB_MEM_DEVICE)) {
+    if (queries->region_offset[0] != 0 || queries->region_offset[queries->n_regions] != queries->n_intervals)
+      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must run from 0 to n_intervals");
+    for (int64_t k = 0; k < queries->n_regions; k++) {
+      const int64_t d = queries->region_offset[k + 1] - queries->region_offset[k];
+      if (d < 1) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be increasing: every region has at least one interval");
+      batch_multi = batch_multi || d != 1;
+    }
+  } else if (queries->region_offset) {
+    batch_multi = true;
+  }
   const bool pass_offsets = batch_multi;
 
   if (mem & GTB_MEM_DEVICE) {
@@ -601,6 +620,10 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     st.in_flight = true;
   }
   ix->queries_seen += queries->n_regions;
+  // "copied inside the call" (gtb200.h): on return the caller's arrays are its own again.  Pageable memory has been staged by
+  // the runtime by now; pinned memory is read by the DMA engine after cudaMemcpyAsync returns, so the last chunk's copies are
+  // waited for (the earlier chunks' were ordered before them on the copy stream).  The kernels stay asynchronous.
+  GTB_CUDA_OK(ctx, cudaEventSynchronize(ix->stages[ix->next_stage ^ 1].copied));
   return GTB_OK;
 }
 

@@ -121,4 +121,5 @@ bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
 int gtb_direct_prepare(gtb_index *ix);
 int gtb_direct_accumulate(gtb_index *ix, const QueryView &q);
 void gtb_direct_destroy(gtb_index *ix);
+void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

@@ -509,7 +509,18 @@ extern "C" int gtb_scan_add_reads(gtb_scan *sc, const gtb_set *reads, unsigned m
     return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
   if (!reads->chrom || !reads->start || !reads->stop || !reads->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  const bool multi = reads->region_offset != nullptr && reads->n_intervals != reads->n_regions;
+  bool multi = false;
+  if (reads->region_offset && !(mem & GTB_MEM_DEVICE)) {                 // a CSR is judged by its offsets, not by its totals
+    if (reads->region_offset[0] != 0 || reads->region_offset[reads->n_regions] != reads->n_intervals)
+      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must run from 0 to n_intervals");
+    for (int64_t k = 0; k < reads->n_regions; k++) {
+      const int64_t d = reads->region_offset[k + 1] - reads->region_offset[k];
+      if (d < 1) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be increasing: every region has at least one interval");
+      multi = multi || d != 1;
+    }
+  } else if (reads->region_offset) {
+    multi = true;                                                        // device-resident offsets are taken as they are
+  }
   if (mem & GTB_MEM_DEVICE) {
     ReadView q{reads->n_regions, reads->n_intervals, reads->chrom, reads->start, reads->stop, reads->strand, reads->weight,
                multi ? reads->region_offset : nullptr, 0};
@@ -545,6 +556,9 @@ extern "C" int gtb_scan_add_reads(gtb_scan *sc, const gtb_set *reads, unsigned m
     GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));
     st.in_flight = true;
   }
+  // "copied inside the call" (gtb200.h): the caller may reuse its arrays on return, so the last chunk's copies have to have
+  // left them (pinned memory is read by the DMA engine after cudaMemcpyAsync returns); the kernels stay asynchronous
+  GTB_CUDA_OK(ctx, cudaEventSynchronize(sc->stages[sc->next_stage ^ 1].copied));
   return GTB_OK;
 }
 

@@ -233,9 +233,14 @@ int main(int argc, char *argv[]) {
     for (int64_t j = 0; j < cnt; j++) {
       const long a = WIN_DIST * (o_win[j] - 1) + 1, b = WIN_DIST * (o_win[j] - 1) + WIN_SIZE;
       if (use_filter && !filter.Overlaps(o_chrom[j], (char)o_strand[j], a, b)) continue;
-      char line[256];
-      const int len = snprintf(line, sizeof line, "%ld\t%s %c %ld %ld\n", (long)o_val[j], chroms.name[o_chrom[j]].c_str(), (char)o_strand[j], a, b);
-      text.insert(text.end(), line, line + len);
+      // value TAB chromosome SPACE strand SPACE start SPACE stop: the numbers go through a fixed buffer, the name (any length) is appended as it is
+      const std::string &name = chroms.name[o_chrom[j]];
+      char num[96];
+      int len = snprintf(num, sizeof num, "%ld\t", (long)o_val[j]);
+      text.insert(text.end(), num, num + len);
+      text.insert(text.end(), name.begin(), name.end());
+      len = snprintf(num, sizeof num, " %c %ld %ld\n", (char)o_strand[j], a, b);
+      text.insert(text.end(), num, num + len);
       if (text.size() > (1u << 24) - 512) { fwrite(text.data(), 1, text.size(), stdout); text.clear(); }
     }
   }

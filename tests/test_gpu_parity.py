@@ -19,13 +19,6 @@ def cell_k(request, monkeypatch):
     monkeypatch.setenv("GTB_BUCKET_K", {"3": "2", "6": "5", "10": "8"}[request.param])
     monkeypatch.setenv("GTB_BUCKET_BITS", {"3": "9", "6": "12", "10": "16"}[request.param])
     monkeypatch.setenv("GTB_DIRECT_CELL_BITS", {"3": "4", "6": "7", "10": "12"}[request.param])   # the direct engine's cell width
-    # the direct engine's two forms: "3" the first (one gather per query), "6" the second with the narrowest coarse cells and a
-    # queue so small that entries overflow and are served on the spot, "10" the second as it configures itself
-    if request.param == "3":
-        monkeypatch.setenv("GTB_DIRECT_FORM", "1")
-    if request.param == "6":
-        monkeypatch.setenv("GTB_DIRECT2_CELL_BP", "16")
-        monkeypatch.setenv("GTB_DIRECT2_QCAP", "64")
     if request.param == "6":
         monkeypatch.setenv("GTB_BUCKET_PAGED", "1")       # the paged form of pass 1
     if request.param == "3":
