@@ -750,7 +750,7 @@ int gtb_bucket_accumulate(gtb_index *ix, const QueryView &q) {
   bv.unit_off = bs->d_unit_off.p; bv.max_local = bs->max_local;
   RankView rv;
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
-  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p; rv.sorted_rules = ix->sorted_rules ? 1 : 0;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ix->d_hist.p; rv.err = ix->d_err.p; rv.admission = ix->admission();
 
   const bool cov = ix->op == GTB_OP_COVERAGE;
   const size_t per_sm = 227 * 1024;

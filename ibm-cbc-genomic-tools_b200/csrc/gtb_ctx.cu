@@ -234,3 +234,22 @@ int gtb_inclusive_scan_planes_u64(gtb_ctx *ctx, const unsigned long long *src, u
 int gtb_inclusive_scan_u64(gtb_ctx *ctx, unsigned long long *d, int64_t n, dbuf<unsigned long long> &scratch) {
   return gtb_inclusive_scan_planes_u64(ctx, d, d, n, 1, n, scratch);
 }
+
+// ---- file-order scatter of gathered per-shard values (the multi-GPU driver's last step) ------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) gather_u64_kernel(const unsigned long long *__restrict__ table, const int64_t *__restrict__ index,
+                                                         int64_t n, unsigned long long *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = table[index[k]];
+}
+}  // namespace
+
+extern "C" int gtb_gather_u64(gtb_ctx *ctx, const uint64_t *table, const int64_t *index, int64_t n, uint64_t *out, void *cuda_stream) {
+  if (!ctx || n < 0 || (n > 0 && (!table || !index || !out))) return GTB_ERR_ARG;
+  if (n == 0) return GTB_OK;
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  ctx->launches++;
+  gather_u64_kernel<<<gtb_grid_for(n, 256, (int64_t)ctx->sm_count * 8), 256, 0, st>>>((const unsigned long long *)table, index, n, (unsigned long long *)out);
+  return gtb_check_launch(ctx);
+}

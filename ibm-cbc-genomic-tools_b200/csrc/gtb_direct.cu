@@ -442,7 +442,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   cudaGetLastError();                                                   // cudaErrorNotReady of the query above is not an error
   RankView rv;
   rv.n_chrom = ix->n_chrom; rv.n_class = ix->n_class; rv.class_of = ix->d_class_of.p; rv.chrom_present = ix->d_present.p;
-  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p; rv.sorted_rules = ix->sorted_rules ? 1 : 0;
+  rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p; rv.admission = ix->admission();
   DirectView dv;
   dv.cbits = ds->cbits; dv.n_chrom = ix->n_chrom; dv.nsig = ds->nsig; dv.stride = ds->stride; dv.cells = ds->d_cells.p;
   dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;

@@ -165,6 +165,39 @@ __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const 
   out[k] = total;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Prepass for batches of multi-interval query regions, so that the single-interval engines can serve them:
+//   SPANS (count / coverage with -gaps, :5227, :5277): checks each region as the reference does and writes its span
+//     [first start, last stop] as one single-interval query; the engines then apply the usual admission to the spans.
+//   !SPANS (coverage without -gaps): coverage is additive over the pairs of blocks (:1196-1202), so the engines take the
+//     batch's intervals as they lie, one query per block, under admission mode 2 (no errors).  What the reference decides per
+//     REGION -- well-formedness (:5698, :5709) and the fatal span conditions on chromosomes the index knows (:5740-5741) -- is
+//     decided here.  A region on a chromosome the index has never seen contributes nothing either way.
+// -------------------------------------------------------------------------------------------------
+template <bool SPANS>
+__global__ void __launch_bounds__(256) region_prepass_kernel(QueryView q, RankView rv, int32_t *__restrict__ o_chrom, int32_t *__restrict__ o_start,
+                                                             int32_t *__restrict__ o_stop, int8_t *__restrict__ o_strand) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    const int64_t lo = q.region_offset[r] - q.interval_base, hi = q.region_offset[r + 1] - q.interval_base;
+    bool ok = hi > lo;
+    int32_t c = -1, qs = 1, qe = 0;
+    int8_t sb = 0;
+    if (ok) {
+      c = q.chrom[lo]; sb = q.strand[lo]; qs = q.start[lo]; qe = q.stop[hi - 1];
+      for (int64_t i = lo + 1; i < hi; i++)
+        if (q.chrom[i] != c || q.strand[i] != sb || q.start[i] < q.start[i - 1] || q.start[i] <= q.stop[i - 1]) { ok = false; break; }
+      if (!ok) report_error(rv.err, q.index_base + r, GTB_ERR_QUERY_REGION);
+    }
+    if (SPANS) {
+      // a region that is empty or malformed leaves a query that no engine counts and none objects to: an unknown chromosome
+      o_chrom[r] = ok ? c : -1; o_start[r] = qs; o_stop[r] = qe; o_strand[r] = sb;
+    } else if (ok && (uint32_t)c < (uint32_t)rv.n_chrom && rv.chrom_present[c]) {
+      admit_interval(rv, qs, qe, q.index_base + r);                    // reports; the blocks themselves are never an error
+    }
+  }
+}
+
 // Expands a packed chunk (start + meta of W bytes, see gtb_ingest.cpp) into the SoA layout the engines read.
 template <int W>
 __device__ __forceinline__ void unpack_one(uint32_t m, uint32_t len0, int32_t s, int32_t &c, int32_t &e, uint32_t &sb) {
@@ -234,7 +267,10 @@ static int build_rank_structures(gtb_index *ix) {
   auto indexable = [&](int64_t k) {
     if (hi_of(k) <= lo_of(k)) return false;
     int64_t s = ix->h_start[lo_of(k)], e = ix->h_stop[hi_of(k) - 1];
-    if (ix->sorted_rules) return s <= e + 1;                          // the Sorted class skips nothing; zero-length spans and stops <= 0 are exact in ranks
+    // the Sorted class skips nothing.  Regions with stop <= 0 are exact in ranks against any admitted query; regions with
+    // start > stop are not (a zero-length region against a zero-length query at the same place) and keep the value 0:
+    // a documented divergence ("Known divergences")
+    if (ix->sorted_rules) return s <= e;
     return !(s > e || e <= 0);                                        // :5610, :5659
   };
   // chromosome table and strand classes
@@ -433,6 +469,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   ix->d_keys.release(); ix->d_rid.release(); ix->d_r_chrom.release(); ix->d_r_start.release();
   ix->d_r_stop.release(); ix->d_r_strand.release(); ix->d_r_off.release(); ix->d_direct.release();
   ix->d_err.release(); ix->d_out.release();
+  ix->sp_chrom.release(); ix->sp_start.release(); ix->sp_stop.release(); ix->sp_strand.release();
   for (auto &st : ix->stages) {
     st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release(); st.meta.release();
     if (st.copied) cudaEventDestroy(st.copied);
@@ -449,7 +486,7 @@ static RankView rank_view(gtb_index *ix) {
   v.n_chrom = ix->n_chrom; v.n_class = ix->n_class;
   v.class_of = ix->d_class_of.p; v.chrom_present = ix->d_present.p;
   v.goff = ix->d_goff.p; v.points = ix->d_points.p; v.n_slots = ix->n_slots;
-  v.hist = ix->d_hist.p; v.err = ix->d_err.p; v.sorted_rules = ix->sorted_rules ? 1 : 0;
+  v.hist = ix->d_hist.p; v.err = ix->d_err.p; v.admission = ix->admission();
   return v;
 }
 
@@ -468,9 +505,44 @@ static unsigned choose_engine(gtb_index *ix, const QueryView &q, bool batch_mult
   return GTB_ENGINE_RANK;
 }
 
-static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi) {
+static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi, int64_t n_intervals);
+
+// Multi-interval query regions in front of the single-interval engines (see region_prepass_kernel).  Returns GTB_ERR_UNSUPPORTED
+// if this batch is not of that kind.
+static int accumulate_multi_fast(gtb_index *ix, const QueryView &q, int64_t n_intervals) {
+  gtb_ctx *ctx = ix->ctx;
+  const bool spans = ix->match_gaps;
+  if (q.weight || !(spans || ix->op == GTB_OP_COVERAGE) || ix->flat_blocks) return GTB_ERR_UNSUPPORTED;
+  if (ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK)) return GTB_ERR_UNSUPPORTED;
+  if (getenv("GTB_NO_MULTI_FAST")) return GTB_ERR_UNSUPPORTED;          // (tests: the general path on the same input)
+  RankView rv = rank_view(ix);
+  const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 16);
+  QueryView flat = q;
+  flat.weight = nullptr; flat.region_offset = nullptr; flat.interval_base = 0;
+  if (spans) {
+    const size_t nr = (size_t)q.n_regions;
+    GTB_TRY(ix->sp_chrom.reserve(ctx, nr)); GTB_TRY(ix->sp_start.reserve(ctx, nr)); GTB_TRY(ix->sp_stop.reserve(ctx, nr)); GTB_TRY(ix->sp_strand.reserve(ctx, nr));
+    GTB_LAUNCH(ctx, "region_spans", region_prepass_kernel<true>, grid, 256, 0, q, rv, ix->sp_chrom.p, ix->sp_start.p, ix->sp_stop.p, ix->sp_strand.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    flat.chrom = ix->sp_chrom.p; flat.start = ix->sp_start.p; flat.stop = ix->sp_stop.p; flat.strand = ix->sp_strand.p;
+    return accumulate_device(ix, flat, false, q.n_regions);              // spans are ordinary queries: the usual admission, errors by region index
+  }
+  GTB_LAUNCH(ctx, "region_check", region_prepass_kernel<false>, grid, 256, 0, q, rv, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int8_t *)nullptr);
+  GTB_TRY(gtb_check_launch(ctx));
+  flat.n_regions = n_intervals;
+  ix->flat_blocks = true;
+  const int rc = accumulate_device(ix, flat, false, n_intervals);
+  ix->flat_blocks = false;
+  return rc;
+}
+
+static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi, int64_t n_intervals) {
   gtb_ctx *ctx = ix->ctx;
   if (q.n_regions <= 0) return GTB_OK;
+  if (batch_multi) {
+    const int rc = accumulate_multi_fast(ix, q, n_intervals);
+    if (rc != GTB_ERR_UNSUPPORTED) return rc;
+  }
   const unsigned engine = choose_engine(ix, q, batch_multi);
   if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
   if (engine == GTB_ENGINE_DIRECT) return gtb_direct_accumulate(ix, q);
@@ -529,7 +601,7 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     q.n_regions = queries->n_regions; q.chrom = queries->chrom; q.start = queries->start; q.stop = queries->stop;
     q.strand = queries->strand; q.weight = queries->weight; q.region_offset = pass_offsets ? queries->region_offset : nullptr;
     q.interval_base = 0; q.index_base = ix->queries_seen;
-    GTB_TRY(accumulate_device(ix, q, batch_multi));
+    GTB_TRY(accumulate_device(ix, q, batch_multi, queries->n_intervals));
     ix->queries_seen += queries->n_regions;
     return GTB_OK;
   }
@@ -615,7 +687,7 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     q.n_regions = (int64_t)nr; q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
     q.weight = queries->weight ? st.weight.p : nullptr; q.region_offset = pass_offsets ? st.off.p : nullptr;
     q.interval_base = i0; q.index_base = ix->queries_seen + r0;
-    GTB_TRY(accumulate_device(ix, q, batch_multi));
+    GTB_TRY(accumulate_device(ix, q, batch_multi, (int64_t)ni));
     GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));
     st.in_flight = true;
   }

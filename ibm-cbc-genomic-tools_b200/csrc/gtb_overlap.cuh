@@ -42,7 +42,8 @@ struct RankView {                  // device pointers
   int64_t n_slots;
   ull *hist;                       // planes of n_slots
   ull *err;                        // min over (index<<8 | code)
-  int32_t sorted_rules;            // GTB_SORTED_RULES: zero-length and stop <= 0 queries are admitted (the Sorted class has no such checks)
+  int32_t admission;               // 0: the Unsorted class's fatal checks; 1: GTB_SORTED_RULES (zero-length and stop <= 0 queries pass);
+                                   // 2: the batch holds BLOCKS of regions that were checked as a whole (no errors; a block with start > stop counts nothing)
 };
 
 struct EnumView {
@@ -59,6 +60,8 @@ struct gtb_index {
   gtb_ctx *ctx = nullptr;
   int op = GTB_OP_COUNT;
   bool match_gaps = false, ignore_strand = false, sorted_rules = false;
+  bool flat_blocks = false;        // transient: the batch being accumulated is the flattened block list of multi-interval queries
+  int admission() const { return flat_blocks ? 2 : sorted_rules ? 1 : 0; }
   unsigned engine = GTB_ENGINE_AUTO;
   int64_t n_regions = 0, n_intervals = 0;
   bool index_multi = false;        // some index region has more than one interval
@@ -97,6 +100,9 @@ struct gtb_index {
 
   // results / errors
   dbuf<ull> d_err, d_out;
+  // spans of multi-interval query regions (-gaps): one single-interval query per region, written by the prepass
+  dbuf<int32_t> sp_chrom, sp_start, sp_stop;
+  dbuf<int8_t> sp_strand;
   int64_t queries_seen = 0;
 
   // double-buffered staging for host-resident query batches

@@ -13,7 +13,8 @@ __device__ __forceinline__ void report_error(ull *err, int64_t index, int code) 
 // "chr 5 5" become) and stops <= 0 pass and are counted by that predicate, which the rank step evaluates for them exactly.
 // Intervals inverted by more than that stay an error here (documented divergence: the reference's -S engine goes on).
 __device__ __forceinline__ bool admit_interval(const RankView &rv, int32_t qs, int32_t qe, int64_t index) {
-  if (rv.sorted_rules) {
+  if (rv.admission == 2) return qs <= qe;            // a block of a region the prepass has admitted (CalcOverlap clamps such blocks to 0, :427-432)
+  if (rv.admission == 1) {
     if ((int64_t)qs > (int64_t)qe + 1) { report_error(rv.err, index, GTB_ERR_QUERY_START_GT_STOP); return false; }
     return true;
   }

@@ -122,13 +122,14 @@ int main(int argc, char *argv[]) {
   // (LoadIndexBuffer, genomic_intervals.cpp:5840-5875): an index region is checked for well-formedness when it becomes the
   // current one and for sortedness when it is fetched, so index lines behind the last query's reach are never looked at.
   // `index_pos` is that fetch position; advance_index() repeats the loop for one query (first interval's chromosome/strand/start,
-  // last interval's stop) and dies where the reference would.
+  // last interval's stop) and dies where the reference would -- naming the region by its 0-based place in the file, because
+  // CountIndexOverlaps / CalcIndexCoverage have overwritten the index regions' line numbers with it by then (:5309, :5274).
   int64_t index_pos = 0;
   auto chrom_cmp = [&](int32_t a, int32_t b) { return a == b ? 0 : strcmp(chroms.name[a].c_str(), chroms.name[b].c_str()); };
   auto advance_index = [&](int32_t qc, char qstrand, long qs, long qe) {
     while (index_pos < ref.n_regions()) {
       const int64_t k = index_pos, lo = ref.offset[k], hi = ref.offset[k + 1];
-      if (!gt::RegionWellFormed(ref, k)) gt::die_line(ref.line(k), "index regions should be compatible, sorted and non-overlapping!");
+      if (!gt::RegionWellFormed(ref, k)) gt::die_line((long)k, "index regions should be compatible, sorted and non-overlapping!");
       int d = chrom_cmp(qc, ref.chrom[lo]);                              // GenomicRegion::CalcDirection, :1225-1237
       if (d == 0 && SORTED_BY_STRAND) d = (int)qstrand - (int)(char)ref.strand[lo];
       if (d == 0) d = (long)ref.stop[hi - 1] < qs ? 1 : qe < (long)ref.start[lo] ? -1 : 0;
@@ -139,7 +140,7 @@ int main(int argc, char *argv[]) {
         int c = chrom_cmp(ref.chrom[a], ref.chrom[lo]);
         bool before = c < 0;
         if (c == 0) before = SORTED_BY_STRAND && ref.strand[a] != ref.strand[lo] ? (char)ref.strand[a] < (char)ref.strand[lo] : ref.start[a] < ref.start[lo];
-        if (before) gt::die_line(ref.line(index_pos), std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+        if (before) gt::die_line((long)index_pos, std::string("index regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
       }
     }
   };

@@ -41,7 +41,7 @@ EXPORTS = [
     "gtb_index_finish_async", "gtb_index_status",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
-    "gtb_synth_reads", "gtb_synth_reads_range",
+    "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library(path=LIB_PATH):
         "gtb_scan_add_reads": (ci, [vp, P(_Set), u32]),
         "gtb_scan_finish": (ci, [vp, P(i64)]),
         "gtb_scan_fetch": (ci, [vp, i64, i64, vp, vp, vp, vp]),
+        "gtb_gather_u64": (ci, [vp, vp, vp, i64, vp, vp]),
         "gtb_synth_reads": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp]),
         "gtb_synth_reads_range": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_uint64,
                                        ctypes.c_uint64, vp, vp, vp, vp]),
@@ -222,6 +223,11 @@ class Context:
 
     def overlap_coverage(self, queries, regions, flags=0, qweight=None, qoffsets=None, roffsets=None):
         return self._one_shot(lib().gtb_overlap_coverage, queries, regions, flags, qweight, qoffsets, roffsets)
+
+    def gather_u64(self, table_ptr, index_ptr, n, out_ptr, cuda_stream_ptr=0):
+        """out[k] = table[index[k]] on the device (the multi-GPU driver's scatter to file order)"""
+        self.check(lib().gtb_gather_u64(self._h, ctypes.c_void_p(table_ptr), ctypes.c_void_p(index_ptr), n, ctypes.c_void_p(out_ptr),
+                                        ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
 
     def synth_reads(self, seed, first, n, read_len, chrom_len, out, p_range=None):
         """out: dict of preallocated torch CUDA tensors; p_range = (p_lo, p_hi) restricts the effective positions."""

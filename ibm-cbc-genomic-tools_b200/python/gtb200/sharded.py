@@ -311,27 +311,32 @@ class ShardedDeviceOverlap:
         self.result = torch.zeros(plan.n_regions, dtype=torch.int64, device="cuda")
 
     def step(self, dset, mem, defer_status=False):
-        """One pass over the local reads.  With defer_status the host never waits: the engine's kernels, the collective and the
-        scatter are ordered by stream events, and the caller asks for the engine's verdict later with check() (a loop that
-        steps many times and looks at the result at the end)."""
+        """One pass over the local reads (`dset`: one gtb_set or a list of them -- batches of a stream too long for one call).
+        With defer_status the host never waits: the engine's kernels, the collective and the scatter are ordered by stream
+        events, and the caller asks for the engine's verdict later with check() (a loop that steps many times and looks at the
+        result at the end)."""
         torch = self.torch
+        sets = dset if isinstance(dset, (list, tuple)) else [dset]
         if not defer_status:
             self.index.reset()
-            self.index.add_set(dset, mem)
+            for st in sets:
+                self.index.add_set(st, mem)
             self.index.finish_ptr(self.vals.data_ptr(), MEM_DEVICE)            # owned values stay on the device; waits, raises GtbError
         else:
             # the library's kernels run on the context's stream, the collective and the scatter on torch's
             lib_stream = torch.cuda.ExternalStream(self.ctx.stream_ptr()) if self.ctx.stream_ptr() else torch.cuda.default_stream()
             lib_stream.wait_stream(torch.cuda.current_stream())               # last step's readers of vals are done before it is rewritten
             self.index.reset()
-            self.index.add_set(dset, mem)
+            for st in sets:
+                self.index.add_set(st, mem)
             self.index.finish_async_ptr(self.vals.data_ptr())
             torch.cuda.current_stream().wait_stream(lib_stream)
+        cur = torch.cuda.current_stream().cuda_stream or 1           # 0 is torch's name for the legacy default stream: cudaStreamLegacy
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.table, self.vals, group=self.group)        # THE collective
-            self.torch.index_select(self.table, 0, self.src_in_file_order, out=self.result)
+            self.ctx.gather_u64(self.table.data_ptr(), self.src_in_file_order.data_ptr(), self.plan.n_regions, self.result.data_ptr(), cur)
         else:
-            self.torch.index_select(self.vals, 0, self.src_in_file_order, out=self.result)
+            self.ctx.gather_u64(self.vals.data_ptr(), self.src_in_file_order.data_ptr(), self.plan.n_regions, self.result.data_ptr(), cur)
         return self.result
 
     def check(self):

@@ -183,6 +183,13 @@ int  gtb_scan_finish(gtb_scan *scan, int64_t *n_windows);
 int  gtb_scan_fetch(gtb_scan *scan, int64_t first, int64_t count, int32_t *chrom, int8_t *strand,
                     int64_t *win, int64_t *value);
 
+/* ---- multi-GPU merge ---------------------------------------------------------------------- */
+/* out[k] = table[index[k]], k < n, all device pointers: puts the per-shard value vectors an all-gather has laid side by side
+ * (every region is owned by one shard) into index-file order -- the `hits[ireg->n_line]` indexing of
+ * genomic_intervals.cpp:5312 across shards.  Runs on cuda_stream (a cudaStream_t, e.g. the one the collective was queued
+ * on) or, if NULL, on the context's stream. */
+int  gtb_gather_u64(gtb_ctx *ctx, const uint64_t *table, const int64_t *index, int64_t n, uint64_t *out, void *cuda_stream);
+
 /* ---- synthetic inputs (bench / tests) ------------------------------------------------------ */
 /* Fills DEVICE arrays with reads [first, first+n) of the counter-based generator documented in
  * DESIGN.md ("Synthetic inputs"); identical to tests/support.py:synth_reads. */

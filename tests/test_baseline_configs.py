@@ -143,7 +143,7 @@ def test_config1_and_4_first_10M_reads(ctx, oracle, gtb, m, seed, lens):
     dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
            "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
     ctx.synth_reads(2, 0, n, 50, support.HG19_LENS, dev)
-    for flags in (0, gtb.IGNORE_STRAND):
+    for flags in (0, gtb.IGNORE_STRAND) if m < 90_000 else (0,):           # (the oracle needs half a minute per pass over 1 M regions)
         rc, want, _ = oracle.count(reads, regions, flags)
         assert rc == 0
         for eng in (0, gtb.ENGINE_BUCKET) + ((gtb.ENGINE_DIRECT,) if m < 90_000 else ()):

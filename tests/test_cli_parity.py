@@ -172,6 +172,35 @@ def test_sorted_flags(files, op):
     assert_same("genomic_overlaps", [op, "-i", "-i", d / "idx.bed", d / "q.bed"], nonempty=True)
 
 
+def test_sorted_engine_admission(tmp_path):
+    """-S selects the reference's SortedGenomicRegionSetOverlaps, whose admission differs from the default engine's
+    (genomic_intervals.cpp:5807-5937): zero-length queries (BED `chr 5 5`) and queries with stop <= 0 are not fatal but matched by
+    the raw predicate, index regions with stop <= 0 are not skipped, and the index file's order and well-formedness are only
+    looked at as far as the queries reach."""
+    (tmp_path / "idx.bed").write_text("chr1\t-30\t-5\tgneg\t0\t+\nchr1\t0\t100\tg1\t0\t+\nchr1\t60\t200\tg2\t0\t+\nchr2\t10\t20\tg3\t0\t+\n")
+    (tmp_path / "q.bed").write_text("chr1\t-10\t-3\tqn\t0\t+\nchr1\t5\t5\tq0\t0\t+\nchr1\t10\t60\tq1\t0\t+\nchr1\t60\t60\tq2\t0\t+\n"
+                                    "chr1\t70\t80\tq3\t0\t+\nchr1\t100\t100\tq4\t0\t-\nchr2\t15\t15\tq5\t0\t+\n")
+    for op in ("count", "coverage", "density"):
+        for flags in ([], ["-i"], ["-gaps"]):
+            assert_same("genomic_overlaps", [op, "-S"] + flags + [tmp_path / "idx.bed", tmp_path / "q.bed"], nonempty=True)
+    # the default engine dies on the first of these queries, and so do we
+    want, got = both("genomic_overlaps", ["count", tmp_path / "idx.bed", tmp_path / "q.bed"])
+    assert got[0] == want[0] == 1 and got[1] == want[1] == b"" and got[2] == want[2]
+    # an index line out of order BEHIND the last query's reach is never read; one the queries reach is fatal
+    (tmp_path / "late.bed").write_text("chr1\t0\t100\tg1\t0\t+\nchr1\t60\t200\tg2\t0\t+\nchr1\t500\t600\tg3\t0\t+\nchr1\t300\t400\tg4\t0\t+\n")
+    (tmp_path / "q2.bed").write_text("chr1\t10\t60\tq1\t0\t+\nchr1\t70\t80\tq3\t0\t+\n")
+    (tmp_path / "q3.bed").write_text("chr1\t10\t60\tq1\t0\t+\nchr1\t70\t80\tq3\t0\t+\nchr1\t550\t560\tq5\t0\t+\n")
+    assert_same("genomic_overlaps", ["count", "-S", tmp_path / "late.bed", tmp_path / "q2.bed"], nonempty=True)
+    want, got = both("genomic_overlaps", ["count", "-S", tmp_path / "late.bed", tmp_path / "q3.bed"])
+    assert got[0] == want[0] == 1 and got[1] == want[1] == b"" and got[2] == want[2]
+    # the same for a malformed (multi-interval, overlapping blocks) index line: read as soon as it becomes the current region, i.e.
+    # one region ahead of the queries (and named by its 0-based place in the file: CountIndexOverlaps renumbers the index, :5309)
+    (tmp_path / "late.reg").write_text("g1\tchr1 + 1 100\ng2\tchr1 + 61 200\ng3\tchr1 + 501 600\ng4\tchr1 + 801 900 chr1 + 850 950\n")
+    assert_same("genomic_overlaps", ["count", "-S", tmp_path / "late.reg", tmp_path / "q2.bed"], nonempty=True)
+    want, got = both("genomic_overlaps", ["count", "-S", tmp_path / "late.reg", tmp_path / "q3.bed"])
+    assert got[0] == want[0] == 1 and got[1] == want[1] == b"" and got[2] == want[2]
+
+
 # ------------------------------------------------------------------------------------------------
 # error paths: same exit code, nothing on stdout
 # ------------------------------------------------------------------------------------------------
