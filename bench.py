@@ -603,41 +603,57 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
+    # Host buffers in the two forms the ABI takes: the packed one a parser writes directly (gtb_index_add_packed: int32 start + one
+    # byte of chromosome | strand per read, one read length -- 5 B/read) and the general SoA gtb_set (13 B/read, which the library
+    # re-encodes to the packed form on the host before it crosses the link).  `e2e` is the packed form; `e2e_soa` the other.
     host = {k: torch.empty(n_local, dtype=v.dtype).pin_memory() for k, v in dev.items()}
     for k in host:
         host[k].copy_(dev[k])
     hset, keep2 = gtb200.pinned_set(host)
+    host_meta = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    host_meta.copy_((dev["chrom"] | ((dev["strand"] == ord("-")).int() << 7)).to(torch.uint8))
+    packed = {"n": n_local, "start": host["start"].data_ptr(), "meta": host_meta.data_ptr(), "read_len": READ_LEN}
     out_host = torch.zeros(N_REGIONS, dtype=torch.int64).pin_memory()
 
-    def step_e2e():
+    def step_e2e(form):
         if world == 1:
             index.reset()
-            index.add_set(hset, gtb200.MEM_HOST)
+            if form == "packed":
+                index.add_packed_ptr(packed["n"], packed["start"], packed["meta"], packed["read_len"], gtb200.MEM_HOST)
+            else:
+                index.add_set(hset, gtb200.MEM_HOST)
             index.finish_ptr(out_host.data_ptr(), gtb200.MEM_HOST)
         else:
-            out_host.copy_(sh.step(hset, gtb200.MEM_HOST))           # H2D of the local reads, gather, D2H of all counts
+            out_host.copy_(sh.step(packed if form == "packed" else hset, gtb200.MEM_HOST))   # H2D of the local reads, gather, D2H of all counts
+
+    def time_e2e(form, steps):
+        step_e2e(form)
+        assert int(out_host.sum().item()) == expect_sum, "e2e (%s) result differs" % form
+        barrier()
+        xfer0 = ctx.transfer_stats()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e(form)
+        barrier()
+        secs = (time.perf_counter() - t0) / steps
+        if dist is not None:
+            t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        xfer1 = ctx.transfer_stats()
+        # bytes that actually crossed PCIe per step on this rank; host_buffer_bytes is what the caller handed over
+        return {"value": n_total / secs, "unit": "query intervals/s",
+                "h2d_bytes_per_step": (xfer1["h2d_bytes"] - xfer0["h2d_bytes"]) // steps,
+                "d2h_bytes_per_step": (xfer1["d2h_bytes"] - xfer0["d2h_bytes"]) // steps + (8 * N_REGIONS if world > 1 else 0),
+                "host_buffer_bytes_per_step": (5 if form == "packed" else BYTES_PER_QUERY) * n_local,
+                "host_form": "packed: int32 start + uint8 chromosome|strand, one read length (gtb_index_add_packed)" if form == "packed"
+                             else "gtb_set SoA: int32 chrom/start/stop + int8 strand (gtb_index_add_queries)",
+                "packed_chunks": xfer1["packed_chunks"] - xfer0["packed_chunks"], "raw_chunks": xfer1["raw_chunks"] - xfer0["raw_chunks"],
+                "ms_per_step": secs * 1e3}
 
     e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
-    barrier()
-    xfer0 = ctx.transfer_stats()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    xfer1 = ctx.transfer_stats()
-    # bytes that actually crossed PCIe per step on this rank (the library re-encodes host chunks to 8 B/interval when it can);
-    # host_buffer_bytes is what the caller handed over in the ABI layout (13 B/interval)
-    e2e = {"value": n_total / e2e_s, "unit": "query intervals/s",
-           "h2d_bytes_per_step": (xfer1["h2d_bytes"] - xfer0["h2d_bytes"]) // e2e_steps,
-           "d2h_bytes_per_step": (xfer1["d2h_bytes"] - xfer0["d2h_bytes"]) // e2e_steps + (8 * N_REGIONS if world > 1 else 0),
-           "host_buffer_bytes_per_step": BYTES_PER_QUERY * n_local, "packed_chunks": xfer1["packed_chunks"] - xfer0["packed_chunks"],
-           "raw_chunks": xfer1["raw_chunks"] - xfer0["raw_chunks"], "ms_per_step": e2e_s * 1e3}
+    e2e = time_e2e("packed", e2e_steps)
+    e2e_soa = time_e2e("soa", max(2, e2e_steps // 2))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "query intervals/s",
@@ -648,7 +664,7 @@ def main():
                            "l2": "inputs (%.1f GB per step) far exceed the 126 MB L2; no flush needed" % (BYTES_PER_QUERY * n / 1e9),
                            "parallelism": "genome-sharded x%d: region ownership by range, boundary reads replicated at ingest, one NCCL "
                                           "all-gather of per-region counts" % world if world > 1 else "single GPU"},
-                "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+                "roofline": roofline, "e2e": e2e, "e2e_soa": e2e_soa, "gpu_launches": launches, "clocks": clocks.summary(),
                 "checksum": counts_check, "checksum_verified": "equals the per-query formulation's total (torch.searchsorted)"}
         if sharding:
             line["sharding"] = sharding

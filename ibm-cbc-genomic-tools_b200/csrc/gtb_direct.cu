@@ -90,6 +90,15 @@ __device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t q
   if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, 1);
 }
 
+// COVERAGE: the batch's common read length - 1, as every thread of both kernels computes it: the majority of three samples
+// (first, middle, last query), so that one atypical read at the head of a batch does not make every other read the odd one
+__device__ __forceinline__ uint32_t dr_common_len(const QueryView &q) {
+  if (q.n_regions <= 0) return 0u;
+  const int64_t m = q.n_regions / 2, z = q.n_regions - 1;
+  const uint32_t a = (uint32_t)(q.stop[0] - q.start[0]), b = (uint32_t)(q.stop[m] - q.start[m]), c = (uint32_t)(q.stop[z] - q.start[z]);
+  return b == c ? b : a;
+}
+
 // number of the cell's (at most two) points that lie below offset `off` (an absent point is 0xFFFF and never does)
 __device__ __forceinline__ uint32_t dr_below(uint32_t y, uint32_t off) {
   return ((y & 0xFFFFu) < off ? 1u : 0u) + ((y >> 16) < off ? 1u : 0u);
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   const int64_t n = q.n_regions;
   const int64_t n_full = n / DR_TILE;
   const int lane = threadIdx.x & 31;
-  const uint32_t len0m1 = COVERAGE && n > 0 ? (uint32_t)(q.stop[0] - q.start[0]) : 0u;   // the common length - 1
+  const uint32_t len0m1 = COVERAGE ? dr_common_len(q) : 0u;                            // the common length - 1
   const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)len0m1 + 1ull : 1ull;                // what one counted query is worth in the "both" plane
   uint32_t odd = 0;                                                    // COVERAGE: queries of another length
   bool overflowed = false;
@@ -209,7 +218,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     // hundreds of adds would reach one byte before its first spill lands.  Neighbouring queries sharing a slot give such input
     // away; the warp then looks for slots shared by eight or more of its lanes and sends ONE reduction for each of those.
     uint32_t done = skip;                                              // bit i: item i needs no shared atomic
-    if (__any_sync(0xffffffffu, (!(skip & 0x3u) && jS[0] == jS[1]) || (!(skip & 0x6u) && jS[1] == jS[2]) || (!(skip & 0xCu) && jS[2] == jS[3]))) {
+    // (three neighbours, not two: the mates of a read pair sit next to each other in the stream and share a slot as a rule; any
+    // run of five or more queries in one slot still has three of them in one thread)
+    if (__any_sync(0xffffffffu, (!(skip & 0x7u) && jS[0] == jS[1] && jS[1] == jS[2]) || (!(skip & 0xEu) && jS[1] == jS[2] && jS[2] == jS[3]))) {
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++) {
         const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, Query
       uint32_t acc = 0;
       for (int g = 0; g < 8; g++) acc += s_part[g][wl][b];
       // COVERAGE: a counted query is worth the batch's common length (direct_count_kernel)
-      const ull unit = COVERAGE && q.n_regions > 0 ? (ull)(int64_t)(q.stop[0] - q.start[0]) + 1ull : 1ull;
+      const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)dr_common_len(q) + 1ull : 1ull;
       for (int p = 0; p < (COVERAGE ? H_PLANES_COVERAGE : H_PLANES_COUNT); p++) {
         const ull d = dv.delta[(int64_t)p * n_slots + j];
         const ull add = discard ? 0ull : d + (p == H_BOTH ? (ull)acc * unit : 0ull);
@@ -323,6 +334,7 @@ int upload_d(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
 
 struct gtb_direct_state {
   bool ready = false, failed = false, off = false;
+  bool off_lengths = false;                                              // off because the reads have no common length (coverage): survives a reset
   int cbits = 0;
   uint32_t n_cells = 0, n_words = 0, nsig = 2, stride = 0;
   unsigned grid = 0;
@@ -435,7 +447,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   if (ds->check_pending && cudaEventQuery(ds->flag_copied) == cudaSuccess) {
     ds->check_pending = false;
     if (ds->h_flag[0] != 0) ds->off = true;
-    if ((int64_t)(uint32_t)(ds->h_flag[1] - ds->odd_seen) > ds->queries_in_check / 16) ds->off = true;
+    if ((int64_t)(uint32_t)(ds->h_flag[1] - ds->odd_seen) > ds->queries_in_check / 16) ds->off = ds->off_lengths = true;
     ds->odd_seen = ds->h_flag[1];
     if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
   }
@@ -475,12 +487,12 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
 }
 
 // gtb_index_reset: the values go back to zero and a new query stream begins, so what the watchdog concluded about the last
-// one (byte counters overflowing, too many odd-length reads under coverage) is forgotten -- the engine is tried again.
+// one's skew (byte counters overflowing) is forgotten -- the engine is tried again.
 // The device-side odd-length counter keeps running; the host's copy of it is what the next check subtracts.
 void gtb_direct_reset(gtb_index *ix) {
   gtb_direct_state *ds = ix->direct;
   if (!ds) return;
-  ds->off = false;
+  ds->off = ds->off_lengths;                                            // reads of every length: a property of the data, expected to last
   ds->queries_since_check = 0;
 }
 

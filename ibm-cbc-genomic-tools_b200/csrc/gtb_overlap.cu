@@ -266,6 +266,7 @@ static int build_rank_structures(gtb_index *ix) {
   auto hi_of = [&](int64_t k) { return ix->h_off[k + 1]; };
   auto indexable = [&](int64_t k) {
     if (hi_of(k) <= lo_of(k)) return false;
+    if (!ix->h_malformed.empty() && ix->h_malformed[(size_t)k]) return false;
     int64_t s = ix->h_start[lo_of(k)], e = ix->h_stop[hi_of(k) - 1];
     // the Sorted class skips nothing.  Regions with stop <= 0 are exact in ranks against any admitted query; regions with
     // start > stop are not (a zero-length region against a zero-length query at the same place) and keep the value 0:
@@ -372,6 +373,7 @@ static int build_enum_structures(gtb_index *ix) {
   for (int64_t k = 0; k < ix->n_regions; k++) {
     const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
     if (hi <= lo) continue;
+    if (!ix->h_malformed.empty() && ix->h_malformed[(size_t)k]) continue;
     int64_t s = ix->h_start[lo], e = ix->h_stop[hi - 1];
     if (s > e || e <= 0) continue;
     if (s <= 0) s = 1;                                                // :5660
@@ -426,12 +428,19 @@ extern "C" int gtb_index_create(gtb_ctx *ctx, const gtb_set *regions, int op, un
       if (regions->region_offset[k + 1] < regions->region_offset[k]) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be non-decreasing");
   }
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  // The Unsorted class checks every index region in its constructor (fatal, :5607).  The Sorted class checks a region when the
+  // queries reach it (:5845), so under GTB_SORTED_RULES that is the caller's business (the drivers repeat the reference's walk): a
+  // malformed region the caller let through was never reached by a query and simply has no value.
+  const bool sorted_rules = (flags & GTB_SORTED_RULES) != 0;
+  std::vector<uint8_t> malformed;
   for (int64_t k = 0; k < regions->n_regions; k++)
-    if (!region_well_formed(regions, k)) {                             // fatal in the reference, :5607
+    if (!region_well_formed(regions, k)) {
+      if (sorted_rules) { if (malformed.empty()) malformed.assign((size_t)regions->n_regions, 0); malformed[(size_t)k] = 1; continue; }
       if (err_index) *err_index = k;
       return gtb_fail(ctx, GTB_ERR_INDEX_REGION, "index regions should be compatible, sorted and non-overlapping!");
     }
   gtb_index *ix = new gtb_index();
+  ix->h_malformed.swap(malformed);
   ix->ctx = ctx; ix->op = op;
   ix->match_gaps = (flags & GTB_MATCH_GAPS) != 0;
   ix->ignore_strand = (flags & GTB_IGNORE_STRAND) != 0;
@@ -513,6 +522,9 @@ static int accumulate_multi_fast(gtb_index *ix, const QueryView &q, int64_t n_in
   gtb_ctx *ctx = ix->ctx;
   const bool spans = ix->match_gaps;
   if (q.weight || !(spans || ix->op == GTB_OP_COVERAGE) || ix->flat_blocks) return GTB_ERR_UNSUPPORTED;
+  // coverage of spans: spans are long and of every length, which neither fast engine likes (DIRECT counts reads of one common
+  // length, BUCKET packs the length into the 8 bits its elements have left); measured, the general rank step is the faster one
+  if (spans && ix->op == GTB_OP_COVERAGE) return GTB_ERR_UNSUPPORTED;
   if (ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK)) return GTB_ERR_UNSUPPORTED;
   if (getenv("GTB_NO_MULTI_FAST")) return GTB_ERR_UNSUPPORTED;          // (tests: the general path on the same input)
   RankView rv = rank_view(ix);
@@ -696,6 +708,56 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
   // the runtime by now; pinned memory is read by the DMA engine after cudaMemcpyAsync returns, so the last chunk's copies are
   // waited for (the earlier chunks' were ordered before them on the copy stream).  The kernels stay asynchronous.
   GTB_CUDA_OK(ctx, cudaEventSynchronize(ix->stages[ix->next_stage ^ 1].copied));
+  return GTB_OK;
+}
+
+// reads in the packed host form (gtb200.h): start + one byte; expanded next to the engine by unpack_kernel<1>
+extern "C" int gtb_index_add_packed(gtb_index *ix, const gtb_packed_reads *reads, unsigned mem) {
+  if (!ix || !reads) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (reads->n < 0 || reads->read_len < 1) return gtb_fail(ctx, GTB_ERR_ARG, "negative size or read length below 1");
+  if (reads->n == 0) return GTB_OK;
+  if (!reads->start || !reads->meta) return gtb_fail(ctx, GTB_ERR_ARG, "null arrays");
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const uint32_t len0 = (uint32_t)reads->read_len - 1u;
+  const int64_t CHUNK = (int64_t)4 << 20;
+  for (int64_t r0 = 0; r0 < reads->n; r0 += CHUNK) {
+    const size_t ni = (size_t)std::min(reads->n - r0, CHUNK);
+    gtb_index::stage &st = ix->stages[ix->next_stage];
+    ix->next_stage ^= 1;
+    cudaStream_t cs = ctx->copy_stream;
+    if (st.in_flight) GTB_CUDA_OK(ctx, cudaStreamWaitEvent(cs, st.consumed, 0));
+    GTB_TRY(st.chrom.reserve(ctx, ni)); GTB_TRY(st.start.reserve(ctx, ni)); GTB_TRY(st.stop.reserve(ctx, ni)); GTB_TRY(st.strand.reserve(ctx, ni));
+    const int32_t *d_start = reads->start + r0;
+    const void *d_meta = reads->meta + r0;
+    if (!(mem & GTB_MEM_DEVICE)) {
+      GTB_TRY(st.meta.reserve(ctx, (ni + 3) / 4));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, reads->start + r0, ni * 4, cudaMemcpyHostToDevice, cs));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.meta.p, reads->meta + r0, ni, cudaMemcpyHostToDevice, cs));
+      ctx->h2d_bytes += (int64_t)ni * 5;
+      ctx->packed_chunks++;
+      d_start = st.start.p; d_meta = st.meta.p;
+    } else if (((uintptr_t)d_start & 15) != 0 || ((uintptr_t)d_meta & 3) != 0) {
+      return gtb_fail(ctx, GTB_ERR_ARG, "device-resident packed reads must be 16-byte (start) and 4-byte (meta) aligned");
+    }
+    GTB_CUDA_OK(ctx, cudaEventRecord(st.copied, cs));
+    GTB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, st.copied, 0));
+    const unsigned ugrid = gtb_grid_for((int64_t)(ni + 3) / 4, 256, (int64_t)ctx->sm_count * 8);
+    int32_t *o_start = st.start.p;
+    if (mem & GTB_MEM_DEVICE) {                                         // the engine reads `start` where it lies
+      o_start = const_cast<int32_t *>(d_start);
+    }
+    GTB_LAUNCH(ctx, "unpack", unpack_kernel<1>, ugrid, 256, 0, (int64_t)ni, d_meta, len0, d_start, st.chrom.p, st.stop.p, st.strand.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    QueryView q;
+    q.n_regions = (int64_t)ni; q.chrom = st.chrom.p; q.start = o_start; q.stop = st.stop.p; q.strand = st.strand.p;
+    q.weight = nullptr; q.region_offset = nullptr; q.interval_base = 0; q.index_base = ix->queries_seen + r0;
+    GTB_TRY(accumulate_device(ix, q, false, (int64_t)ni));
+    GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));
+    st.in_flight = true;
+  }
+  ix->queries_seen += reads->n;
+  if (!(mem & GTB_MEM_DEVICE)) GTB_CUDA_OK(ctx, cudaEventSynchronize(ix->stages[ix->next_stage ^ 1].copied));   // "copied inside the call"
   return GTB_OK;
 }
 

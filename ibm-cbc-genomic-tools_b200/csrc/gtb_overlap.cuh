@@ -71,6 +71,7 @@ struct gtb_index {
   std::vector<int32_t> h_chrom, h_start, h_stop;
   std::vector<int8_t> h_strand;
   std::vector<int64_t> h_off;
+  std::vector<uint8_t> h_malformed; // GTB_SORTED_RULES only: index regions that are not well-formed (never indexed; empty = none)
 
   // rank
   int32_t n_chrom = 0, n_class = 0, n_groups = 0;

@@ -37,7 +37,7 @@ ERR_NO_DEVICE = 100
 EXPORTS = [
     "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_get_stream", "gtb_ctx_synchronize",
     "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_transfer_stats", "gtb_ctx_profile", "gtb_ctx_profile_report",
-    "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_finish",
+    "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_add_packed", "gtb_index_finish",
     "gtb_index_finish_async", "gtb_index_status",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
@@ -56,6 +56,10 @@ class _Set(ctypes.Structure):
     _fields_ = [("n_regions", ctypes.c_int64), ("n_intervals", ctypes.c_int64),
                 ("chrom", ctypes.c_void_p), ("start", ctypes.c_void_p), ("stop", ctypes.c_void_p),
                 ("strand", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("region_offset", ctypes.c_void_p)]
+
+
+class _Packed(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("start", ctypes.c_void_p), ("meta", ctypes.c_void_p), ("read_len", ctypes.c_int32)]
 
 
 class _ScanParams(ctypes.Structure):
@@ -87,6 +91,7 @@ def load_library(path=LIB_PATH):
         "gtb_index_destroy": (None, [vp]),
         "gtb_index_reset": (ci, [vp]),
         "gtb_index_add_queries": (ci, [vp, P(_Set), u32]),
+        "gtb_index_add_packed": (ci, [vp, P(_Packed), u32]),
         "gtb_index_finish": (ci, [vp, vp, u32, P(i64)]),
         "gtb_index_finish_async": (ci, [vp, vp, u32]),
         "gtb_index_status": (ci, [vp, P(i64)]),
@@ -275,6 +280,12 @@ class Index:
     def add_device(self, tensors, weight=None, offsets=None):
         st, keep = device_set(tensors, weight, offsets)
         self.add_set(st, MEM_DEVICE)
+
+    def add_packed_ptr(self, n, start_ptr, meta_ptr, read_len, mem):
+        """reads in the packed form of gtb200.h (int32 start + uint8 chromosome | strand bit, one length); host pointers are
+        copied inside the call"""
+        pk = _Packed(n, start_ptr, meta_ptr, read_len)
+        self.ctx.check(lib().gtb_index_add_packed(self._h, ctypes.byref(pk), mem))
 
     def finish(self, out=None):
         if out is None:

@@ -317,10 +317,16 @@ class ShardedDeviceOverlap:
         result at the end)."""
         torch = self.torch
         sets = dset if isinstance(dset, (list, tuple)) else [dset]
+
+        def add(st):
+            if isinstance(st, dict):                                           # reads in the packed form: {"n", "start", "meta", "read_len"} (pointers)
+                self.index.add_packed_ptr(st["n"], st["start"], st["meta"], st["read_len"], mem)
+            else:
+                self.index.add_set(st, mem)
         if not defer_status:
             self.index.reset()
             for st in sets:
-                self.index.add_set(st, mem)
+                add(st)
             self.index.finish_ptr(self.vals.data_ptr(), MEM_DEVICE)            # owned values stay on the device; waits, raises GtbError
         else:
             # the library's kernels run on the context's stream, the collective and the scatter on torch's
@@ -328,7 +334,7 @@ class ShardedDeviceOverlap:
             lib_stream.wait_stream(torch.cuda.current_stream())               # last step's readers of vals are done before it is rewritten
             self.index.reset()
             for st in sets:
-                self.index.add_set(st, mem)
+                add(st)
             self.index.finish_async_ptr(self.vals.data_ptr())
             torch.cuda.current_stream().wait_stream(lib_stream)
         cur = torch.cuda.current_stream().cuda_stream or 1           # 0 is torch's name for the legacy default stream: cudaStreamLegacy

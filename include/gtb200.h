@@ -129,6 +129,18 @@ int  gtb_index_reset(gtb_index *index);
  * (genomic_intervals.cpp:5310-5314, :5275-5282).  mem is GTB_MEM_HOST or GTB_MEM_DEVICE.
  * Batches may be any size; region indices reported in errors count across batches. */
 int  gtb_index_add_queries(gtb_index *index, const gtb_set *queries, unsigned mem);
+/* The same for a batch of single-interval, unweighted reads of ONE length in the compact form a parser can write directly:
+ * 5 bytes per read instead of the 13 of a gtb_set (read k = chromosome meta[k] & 0x7F, strand '-' if meta[k] & 0x80 else '+',
+ * [start[k], start[k] + read_len - 1]).  It is the form the library itself re-encodes host-resident gtb_set chunks into before
+ * they cross the host link; a caller that has it already saves the library the pass over 13 bytes per read.  Reads it cannot
+ * express (chromosome ids >= 128, other strands, other lengths) go through gtb_index_add_queries. */
+typedef struct {
+  int64_t n;
+  const int32_t *start;          /* [n] */
+  const uint8_t *meta;           /* [n] chromosome id | 0x80 for the '-' strand */
+  int32_t read_len;              /* >= 1 */
+} gtb_packed_reads;
+int  gtb_index_add_packed(gtb_index *index, const gtb_packed_reads *reads, unsigned mem);
 /* Completes the accumulation and writes one value per index region, in index-file order:
  * the `unsigned long *hits` / `*coverage` array CountIndexOverlaps / CalcIndexCoverage return
  * (genomic_intervals.cpp:5308, :5273).  out is host memory unless mem == GTB_MEM_DEVICE.

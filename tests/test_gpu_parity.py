@@ -564,3 +564,26 @@ def test_packed_host_path(gtb, ctx, oracle, monkeypatch):
     rc, want, _ = oracle.count(reads, regions, 0)
     assert np.array_equal(c2.overlap_count(reads, regions, 0), want)
     c2.close()
+
+
+def test_packed_reads_entry(gtb, ctx, oracle):
+    """gtb_index_add_packed: reads of one length handed over as int32 start + one byte of chromosome | strand (host and device
+    memory, count and coverage) give what the same reads give as a gtb_set."""
+    import torch
+    n = 3_000_001                                                       # not a multiple of anything
+    reads = support.synth_reads(n, seed=21, read_len=36)
+    regions = support.synth_regions(5_000, seed=22)
+    meta = (reads["chrom"].astype(np.uint8) | np.where(reads["strand"] == ord("-"), 0x80, 0).astype(np.uint8))
+    start = np.ascontiguousarray(reads["start"])
+    for op, fn in ((gtb.OP_COUNT, oracle.count), (gtb.OP_COVERAGE, oracle.coverage)):
+        for flags in (0, gtb.IGNORE_STRAND):
+            rc, want, _ = fn(reads, regions, flags)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, flags)
+            ix.add_packed_ptr(n, start.ctypes.data, meta.ctypes.data, 36, gtb.MEM_HOST)
+            assert np.array_equal(ix.finish(), want), ("host", op, flags)
+            ix.reset()
+            d_start, d_meta = torch.from_numpy(start).cuda(), torch.from_numpy(meta).cuda()
+            ix.add_packed_ptr(n, d_start.data_ptr(), d_meta.data_ptr(), 36, gtb.MEM_DEVICE)
+            assert np.array_equal(ix.finish(), want), ("device", op, flags)
+            ix.close()
