@@ -628,6 +628,7 @@ def main():
 
     def time_e2e(form, steps):
         step_e2e(form)
+        step_e2e(form)                                                   # (two untimed steps: staging buffers allocated, the host packing pool's rate known)
         assert int(out_host.sum().item()) == expect_sum, "e2e (%s) result differs" % form
         barrier()
         xfer0 = ctx.transfer_stats()

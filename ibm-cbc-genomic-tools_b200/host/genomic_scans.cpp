@@ -12,6 +12,7 @@
 #include <limits.h>
 #include <algorithm>
 #include <iostream>
+#include <thread>
 #include "gt_host.h"
 #include "gtb200.h"
 
@@ -98,6 +99,24 @@ struct RefFilter {
   }
 };
 
+// CUDA context creation off the main thread (see gt_host.h: exit_hook)
+static std::thread g_ctx_thread;
+static gtb_ctx *g_ctx = nullptr;
+static int g_ctx_rc = GTB_OK;
+static void start_context() {
+  // The driver uses one GPU.  On a multi-GPU host the CUDA runtime would initialise every visible device first (seconds);
+  // unless the user has chosen devices, only the first one is made visible.
+  setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+  g_ctx_thread = std::thread([] { g_ctx_rc = gtb_ctx_create(0, &g_ctx); });
+  gt::exit_hook = [] { if (g_ctx_thread.joinable()) g_ctx_thread.join(); };
+}
+static gtb_ctx *wait_context() {
+  if (g_ctx_thread.joinable()) g_ctx_thread.join();
+  gt::exit_hook = nullptr;
+  if (g_ctx_rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", g_ctx_rc); exit(1); }
+  return g_ctx;
+}
+
 int main(int argc, char *argv[]) {
   gt::CmdLine cmd(PROGRAM, VERSION);
   cmd.AddOperation("counts", "[OPTIONS] <REG-FILE>", "Determines input read counts in sliding windows of reference regions.", DETAILS);
@@ -132,6 +151,7 @@ int main(int argc, char *argv[]) {
   const char *input_file = next_arg == argc ? nullptr : argv[next_arg];
 
   gt::PhaseTimer timer;
+  start_context();                                                      // comes up while the genome file and the first reads are read
   // ---- genome bounds; chromosome ids in strcmp order of the names = the reference's std::map order
   std::map<std::string, long> bounds = ReadBounds(GENOME_REG_FILE);
   gt::ChromTable chroms;
@@ -142,7 +162,7 @@ int main(int argc, char *argv[]) {
   gt::RegionReader reads(input_file, &chroms, false, MAX_LABEL_VALUE);
   if (VERBOSE) std::cerr << "Reading from '" << (input_file ? input_file : "<standard input>") << "'; format = " << reads.format() << "\n";
   if (reads.format() == "SEQ") { std::cerr << "Error: this operation does not accept SEQ format!\n"; exit(1); }
-  if (reads.format() == "EMPTY") return 0;                              // scanner ctor returns early, Next() yields nothing
+  if (reads.format() == "EMPTY") exit(0);                               // scanner ctor returns early, Next() yields nothing
   if (WIN_DIST <= 0 || WIN_SIZE % WIN_DIST != 0) {
     std::cerr << "Error: window size must be a multiple of window step in 'GenomicRegionSetScanner'!\n";
     exit(1);
@@ -159,12 +179,7 @@ int main(int argc, char *argv[]) {
   }
 
   timer.Mark("setup");
-  // The driver uses one GPU.  On a multi-GPU host the CUDA runtime would initialise every visible device first (seconds);
-  // unless the user has chosen devices, only the first one is made visible.
-  setenv("CUDA_VISIBLE_DEVICES", "0", 0);
-  gtb_ctx *ctx = nullptr;
-  int rc = gtb_ctx_create(0, &ctx);
-  if (rc != GTB_OK) { fprintf(stderr, "\nError: no CUDA device available (status %d); this build has no CPU fallback\n", rc); exit(1); }
+  gtb_ctx *ctx = wait_context();
   timer.Mark("cuda_context");
   gtb_scan_params prm;
   memset(&prm, 0, sizeof prm);
@@ -247,8 +262,7 @@ int main(int argc, char *argv[]) {
   if (!text.empty()) fwrite(text.data(), 1, text.size(), stdout);
   fflush(stdout);
   timer.Mark("print");
-  gtb_scan_destroy(scan);
-  gtb_ctx_destroy(ctx);
-  timer.Mark("teardown");
+  // the process is about to end: the driver reclaims the window table (1 GB for hg19) faster than cudaFree would
+  (void)scan;
   return 0;
 }

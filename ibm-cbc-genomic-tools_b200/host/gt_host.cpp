@@ -840,4 +840,12 @@ void RegionReader::Fail() const {
   die(error_.message);
 }
 
+void (*exit_hook)() = nullptr;
+#undef exit
+void Exit(int code) {
+  if (exit_hook) { void (*h)() = exit_hook; exit_hook = nullptr; h(); }
+  ::exit(code);
+}
+#define exit(code) ::gt::Exit(code)
+
 }  // namespace gt

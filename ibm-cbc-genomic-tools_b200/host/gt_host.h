@@ -226,4 +226,13 @@ struct SortChecker {
   bool Accept(const std::string &c, char s, long st);
 };
 
+// The drivers create the CUDA context on a helper thread while the main thread reads the reference set (context creation takes
+// 0.4 - 2 s on a cold box; serialised after the loading it was most of a small run's wall time).  Every fatal path of the host
+// code ends in exit(); leaving the process while the helper thread is inside the CUDA runtime's initialisation is asking for a
+// crash in its atexit handlers, so exit() is routed through Exit(), which first runs `exit_hook` (the driver's "wait for the
+// helper thread").
+extern void (*exit_hook)();
+[[noreturn]] void Exit(int code);
+
 }  // namespace gt
+#define exit(code) ::gt::Exit(code)

@@ -41,7 +41,7 @@ EXPORTS = [
     "gtb_index_finish_async", "gtb_index_status",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
-    "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64",
+    "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64", "gtb_sort_regions",
 ]
 
 
@@ -104,6 +104,7 @@ def load_library(path=LIB_PATH):
         "gtb_scan_finish": (ci, [vp, P(i64)]),
         "gtb_scan_fetch": (ci, [vp, i64, i64, vp, vp, vp, vp]),
         "gtb_gather_u64": (ci, [vp, vp, vp, i64, vp, vp]),
+        "gtb_sort_regions": (ci, [vp, i64, vp, vp, vp, vp, ci, vp]),
         "gtb_synth_reads": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp]),
         "gtb_synth_reads_range": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_uint64,
                                        ctypes.c_uint64, vp, vp, vp, vp]),
@@ -228,6 +229,14 @@ class Context:
 
     def overlap_coverage(self, queries, regions, flags=0, qweight=None, qoffsets=None, roffsets=None):
         return self._one_shot(lib().gtb_overlap_coverage, queries, regions, flags, qweight, qoffsets, roffsets)
+
+    def sort_regions(self, chrom_rank, start, stop, strand, by_strand=False):
+        """permutation that puts regions into `genomic_regions gsort` order (device radix sort); numpy arrays in, int64 array out"""
+        cr = np.ascontiguousarray(chrom_rank, dtype=np.int32); st = np.ascontiguousarray(start, dtype=np.int32)
+        sp = np.ascontiguousarray(stop, dtype=np.int32); sd = np.ascontiguousarray(strand, dtype=np.int8)
+        perm = np.zeros(len(cr), dtype=np.int64)
+        self.check(lib().gtb_sort_regions(self._h, len(cr), _np_ptr(cr), _np_ptr(st), _np_ptr(sp), _np_ptr(sd), int(by_strand), _np_ptr(perm)))
+        return perm
 
     def gather_u64(self, table_ptr, index_ptr, n, out_ptr, cuda_stream_ptr=0):
         """out[k] = table[index[k]] on the device (the multi-GPU driver's scatter to file order)"""

@@ -195,6 +195,16 @@ int  gtb_scan_finish(gtb_scan *scan, int64_t *n_windows);
 int  gtb_scan_fetch(gtb_scan *scan, int64_t first, int64_t count, int32_t *chrom, int8_t *strand,
                     int64_t *win, int64_t *value);
 
+/* ---- global sort of a region set ----------------------------------------------------------- */
+/* The order GenomicRegionSet::RunGlobalSort prints a region set in (genomic_regions gsort, genomic_intervals.cpp:4547-4570 with
+ * BinGenomicRegions :6095-6150 and CompareBinnedGenomicRegions :6045-6049): chromosome rank ascending (the caller ranks the
+ * names in strcmp order, the reference's std::map order), with by_strand the '+' regions of a chromosome before all others,
+ * START ascending, STOP descending, equal keys in input order.  Per region: the rank of its chromosome, the START of its first
+ * interval and the STOP of its last one after the reference's r->Sort() (intervals by start), and its strand byte -- host arrays.
+ * perm[k] = input index of the region printed k-th (host array).  Device LSD radix sort, 8-bit digits, stable. */
+int  gtb_sort_regions(gtb_ctx *ctx, int64_t n_regions, const int32_t *chrom_rank, const int32_t *start, const int32_t *stop,
+                      const int8_t *strand, int by_strand, int64_t *perm);
+
 /* ---- multi-GPU merge ---------------------------------------------------------------------- */
 /* out[k] = table[index[k]], k < n, all device pointers: puts the per-shard value vectors an all-gather has laid side by side
  * (every region is owned by one shard) into index-file order -- the `hits[ireg->n_line]` indexing of

@@ -587,3 +587,22 @@ def test_packed_reads_entry(gtb, ctx, oracle):
             ix.add_packed_ptr(n, d_start.data_ptr(), d_meta.data_ptr(), 36, gtb.MEM_DEVICE)
             assert np.array_equal(ix.finish(), want), ("device", op, flags)
             ix.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 4097, 1_000_003])
+def test_sort_regions_matches_stable_lexsort(ctx, n):
+    """gtb_sort_regions (device LSD radix sort) against numpy's stable lexsort on the same key: chromosome rank, ('+' first),
+    start ascending, stop descending, ties in input order -- the order of GenomicRegionSet::RunGlobalSort."""
+    rng = np.random.default_rng(n)
+    chrom = rng.integers(0, 7 if n > 100 else 2, n).astype(np.int32)
+    start = rng.integers(-50, 400 if n < 10_000 else 3_000_000, n).astype(np.int32)          # many ties on small inputs, negative starts too
+    stop = (start + rng.integers(0, 6, n) * 100).astype(np.int32)
+    strand = rng.choice(np.array([43, 45, 46], dtype=np.int8), n)
+    if n > 1000:
+        start[::5000] = np.int32(2**31 - 1000); stop[::5000] = np.int32(2**31 - 1)            # the far end of the coordinate range
+        start[1::5000] = np.int32(-2**31); stop[1::5000] = np.int32(-2**31 + 5)
+    for by_strand in (False, True):
+        got = ctx.sort_regions(chrom, start, stop, strand, by_strand)
+        sclass = (strand != 43).astype(np.int64) if by_strand else np.zeros(n, np.int64)
+        want = np.lexsort((-stop.astype(np.int64), start.astype(np.int64), sclass, chrom.astype(np.int64)))    # last key is the primary one; lexsort is stable
+        assert np.array_equal(got, want), (n, by_strand)
