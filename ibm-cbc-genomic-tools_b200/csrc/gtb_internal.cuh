@@ -56,6 +56,7 @@ struct gtb_ctx {
   int64_t packed_chunks = 0, raw_chunks = 0;   // how the host-resident chunks travelled (diagnostics)
   int64_t h2d_bytes = 0, d2h_bytes = 0;        // bytes of query batches / results that crossed the host link
   double pack_rate = 0.0;                      // measured packing throughput of this context's pool, intervals/s (0: not yet known)
+  int64_t pack_timed = 0;                      // chunks the pool has been timed on (the first one does not count)
   int64_t pack_skipped = 0;                    // chunks sent raw because packing would have been the slower leg
   int pack_width = 1;                          // bytes of meta per interval the next chunk tries first (1, 2, 4); widened when a chunk does not fit
   int64_t pack_wide_chunks = 0;                // chunks since the width was last widened (a narrower form is retried now and then)

@@ -128,6 +128,67 @@ __global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix
 }
 
 // -------------------------------------------------------------------------------------------------
+// Per-QUERY overlap counts: the dual of the engines above, for `genomic_overlaps subset / overlap`
+// (genomic_overlaps.cpp:706-739, :782-800: the GetOverlap / NextOverlap walk of one query region).
+//   n(q) = #{targets: ts <= qe} - #{targets: te < qs}                   (targets valid: ts <= te)
+//        = #{(ts - 1) points below qe} - #{te points below qs}
+// i.e. two prefix counts over the group's sorted evaluation points, looked up at the slots of qs and qe.
+// `pre[j]` = (x: targets whose ts - 1 lies in a slot before j, y: targets whose te does), group-relative.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) query_counts_kernel(QueryView q, RankView ix, const uint2 *__restrict__ pre, uint32_t *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    uint32_t n = 0;
+    int64_t lo, hi;
+    if (admit_query(q, r, ix, lo, hi)) {
+      const int cls = ix.class_of[(uint8_t)q.strand[lo]];
+      if (cls >= 0) {
+        const int g = q.chrom[lo] * ix.n_class + cls;
+        const int gb = ix.goff[g], ge = ix.goff[g + 1];
+        if (ge > gb) {
+          const int32_t qs = q.start[lo], qe = q.stop[hi - 1];
+          const int jS = lower_bound_i32(ix.points, gb, ge - 1, qs);
+          const int jE = lower_bound_i32(ix.points, qe < qs ? gb : jS, ge - 1, qe);
+          n = pre[jE].x - pre[jS].y;
+        }
+      }
+    }
+    out[r] = n;
+  }
+}
+
+// the same where ranks cannot speak (multi-interval regions on either side without -gaps): candidates, exact predicate per pair
+__global__ void __launch_bounds__(128) query_enumerate_kernel(QueryView q, RankView ix, EnumView ev, bool ignore_strand, uint32_t *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    uint32_t n = 0;
+    int64_t lo, hi;
+    if (admit_query(q, r, ix, lo, hi)) {
+      const int32_t c = q.chrom[lo];
+      const int8_t qstrand = q.strand[lo];
+      const int64_t qs_true = q.start[lo], qe = q.stop[hi - 1];
+      const int64_t qs = qs_true <= 0 ? 1 : qs_true;                  // :5742
+      for (int l = 0; l < ENUM_LEVELS; l++) {
+        const ull k_lo = enum_key(c, l, qs >> c_enum_bits[l]);
+        const ull k_hi = enum_key(c, l, qe >> c_enum_bits[l]);
+        for (int64_t e = lower_bound_u64(ev.keys, ev.n_entries, k_lo); e < ev.n_entries && ev.keys[e] <= k_hi; e++) {
+          const int32_t k = ev.rid[e];
+          const int64_t ilo = ev.r_off[k], ihi = ev.r_off[k + 1];
+          if (!(qs <= ev.r_stop[ihi - 1] && qe >= ev.r_start[ilo])) continue;             // span test, :5752
+          if (!ignore_strand && qstrand != ev.r_strand[ilo]) continue;                   // :5229
+          bool any = false;
+          for (int64_t i = lo; i < hi && !any; i++)
+            for (int64_t j = ilo; j < ihi; j++)
+              if (!(q.start[i] > ev.r_stop[j] || q.stop[i] < ev.r_start[j])) { any = true; break; }   // :624-630
+          n += any ? 1u : 0u;
+        }
+      }
+    }
+    out[r] = n;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // finalisation: after the slot histograms have been prefix-summed, evaluate every target and sum
 // the targets of each region.  One thread per region.
 // -------------------------------------------------------------------------------------------------
@@ -478,7 +539,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   ix->d_keys.release(); ix->d_rid.release(); ix->d_r_chrom.release(); ix->d_r_start.release();
   ix->d_r_stop.release(); ix->d_r_strand.release(); ix->d_r_off.release(); ix->d_direct.release();
   ix->d_err.release(); ix->d_out.release();
-  ix->sp_chrom.release(); ix->sp_start.release(); ix->sp_stop.release(); ix->sp_strand.release();
+  ix->sp_chrom.release(); ix->sp_start.release(); ix->sp_stop.release(); ix->sp_strand.release(); ix->d_qpre.release();
   for (auto &st : ix->stages) {
     st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release(); st.meta.release();
     if (st.copied) cudaEventDestroy(st.copied);
@@ -657,7 +718,8 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
         else if (width < 4) { ctx->pack_width = width * 2; ctx->pack_wide_chunks = 0; }
       }
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (dt > 0) ctx->pack_rate = ctx->pack_rate == 0.0 ? (double)ni / dt : 0.5 * ctx->pack_rate + 0.5 * (double)ni / dt;
+      // (the pool's first chunk pays for thread start-up and first-touch of the pinned slots: not a rate to judge it by)
+      if (dt > 0 && ctx->pack_timed++ > 0) ctx->pack_rate = ctx->pack_rate == 0.0 ? (double)ni / dt : 0.5 * ctx->pack_rate + 0.5 * (double)ni / dt;
       if (packed) {
         GTB_TRY(st.meta.reserve(ctx, ni));
         GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, start_is_pinned ? queries->start + i0 : slot->start, ni * 4, cudaMemcpyHostToDevice, cs));
@@ -759,6 +821,125 @@ extern "C" int gtb_index_add_packed(gtb_index *ix, const gtb_packed_reads *reads
   ix->queries_seen += reads->n;
   if (!(mem & GTB_MEM_DEVICE)) GTB_CUDA_OK(ctx, cudaEventSynchronize(ix->stages[ix->next_stage ^ 1].copied));   // "copied inside the call"
   return GTB_OK;
+}
+
+// =================================================================================================
+// per-query overlap counts (subset / overlap)
+// =================================================================================================
+static int build_query_prefix(gtb_index *ix) {
+  if (ix->qpre_ready) return GTB_OK;
+  gtb_ctx *ctx = ix->ctx;
+  // the targets' slots are on the device (d_t_hi / d_t_lo): count them per slot there is no need -- rebuild on the host from
+  // the same region arrays the rank structures were built from
+  std::vector<uint2> pre((size_t)std::max<int64_t>(ix->n_slots, 1), make_uint2(0u, 0u));
+  auto indexable = [&](int64_t k) {
+    const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
+    if (hi <= lo) return false;
+    if (!ix->h_malformed.empty() && ix->h_malformed[(size_t)k]) return false;
+    const int64_t s = ix->h_start[lo], e = ix->h_stop[hi - 1];
+    if (ix->sorted_rules) return s <= e;
+    return !(s > e || e <= 0);
+  };
+  for (int64_t k = 0; k < ix->n_regions; k++) {
+    if (!indexable(k)) continue;
+    const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
+    const int32_t g = ix->h_chrom[lo] * ix->n_class + ix->h_class_of[(uint8_t)ix->h_strand[lo]];
+    const int32_t gb = ix->h_goff[g], ge = ix->h_goff[g + 1];
+    const int32_t *b = ix->h_points.data() + gb, *e = ix->h_points.data() + ge - 1;
+    const int32_t ts = ix->h_start[lo], te = ix->h_stop[hi - 1];
+    pre[(size_t)(std::lower_bound(b, e, ts == INT32_MIN ? INT32_MIN : ts - 1) - ix->h_points.data())].x++;
+    pre[(size_t)(std::lower_bound(b, e, te) - ix->h_points.data())].y++;
+  }
+  for (int32_t g = 0; g < ix->n_groups; g++) {                          // exclusive prefix sums inside every group
+    uint32_t ax = 0, ay = 0;
+    for (int32_t j = ix->h_goff[g]; j < ix->h_goff[g + 1]; j++) {
+      const uint2 v = pre[(size_t)j];
+      pre[(size_t)j] = make_uint2(ax, ay);
+      ax += v.x; ay += v.y;
+    }
+  }
+  GTB_TRY(upload(ctx, ix->d_qpre, pre));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ix->qpre_ready = true;
+  return GTB_OK;
+}
+
+extern "C" int gtb_index_query_counts(gtb_index *ix, const gtb_set *queries, unsigned mem, uint32_t *out, unsigned out_mem, int64_t *err_index) {
+  if (err_index) *err_index = -1;
+  if (!ix || !queries) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (ix->op != GTB_OP_COUNT) return gtb_fail(ctx, GTB_ERR_ARG, "per-query counts need an index created with GTB_OP_COUNT");
+  if (queries->n_regions < 0 || queries->n_intervals < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative sizes");
+  if (queries->n_regions == 0) return GTB_OK;
+  if (!out || !queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null arrays");
+  if (!queries->region_offset && queries->n_regions != queries->n_intervals)
+    return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  const bool dev_in = (mem & GTB_MEM_DEVICE) != 0, dev_out = (out_mem & GTB_MEM_DEVICE) != 0;
+  bool batch_multi = queries->region_offset != nullptr;
+  if (queries->region_offset && !dev_in) {
+    batch_multi = false;
+    for (int64_t k = 0; k < queries->n_regions; k++) {
+      const int64_t d = queries->region_offset[k + 1] - queries->region_offset[k];
+      if (d < 1) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be increasing: every region has at least one interval");
+      batch_multi = batch_multi || d != 1;
+    }
+  }
+  const bool ranks = ix->match_gaps || (!ix->index_multi && !batch_multi);   // spans decide (-gaps), or nothing but single intervals
+  if (ranks) GTB_TRY(build_query_prefix(ix)); else GTB_TRY(build_enum_structures(ix));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
+  RankView rv = rank_view(ix);
+  const int64_t CHUNK = (int64_t)4 << 20;
+  dbuf<uint32_t> d_out;
+  for (int64_t r0 = 0; r0 < queries->n_regions; r0 += CHUNK) {
+    const int64_t r1 = std::min(queries->n_regions, r0 + CHUNK);
+    const int64_t i0 = batch_multi && !dev_in ? queries->region_offset[r0] : r0;
+    const int64_t i1 = batch_multi && !dev_in ? queries->region_offset[r1] : r1;
+    const size_t nr = (size_t)(r1 - r0), ni = (size_t)(i1 - i0);
+    QueryView q;
+    q.weight = nullptr; q.index_base = r0; q.interval_base = 0; q.region_offset = nullptr; q.n_regions = (int64_t)nr;
+    if (dev_in) {
+      // device-resident: offsets (if any) index the arrays as passed; a chunk of regions keeps the arrays' origin
+      q.chrom = queries->chrom; q.start = queries->start; q.stop = queries->stop; q.strand = queries->strand;
+      if (batch_multi) q.region_offset = queries->region_offset + r0;
+      else { q.chrom += r0; q.start += r0; q.stop += r0; q.strand += r0; }
+    } else {
+      gtb_index::stage &st = ix->stages[0];
+      GTB_TRY(st.chrom.reserve(ctx, ni)); GTB_TRY(st.start.reserve(ctx, ni)); GTB_TRY(st.stop.reserve(ctx, ni)); GTB_TRY(st.strand.reserve(ctx, ni));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.chrom.p, queries->chrom + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, queries->start + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.stop.p, queries->stop + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.strand.p, queries->strand + i0, ni, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->h2d_bytes += (int64_t)ni * 13;
+      q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
+      if (batch_multi) {
+        GTB_TRY(st.off.reserve(ctx, nr + 1));
+        GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.off.p, queries->region_offset + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        q.region_offset = st.off.p; q.interval_base = i0;
+      }
+    }
+    uint32_t *o = dev_out ? out + r0 : nullptr;
+    if (!dev_out) { GTB_TRY(d_out.reserve(ctx, nr)); o = d_out.p; }
+    if (ranks) {
+      const unsigned grid = gtb_grid_for((int64_t)nr, 256, (int64_t)ctx->sm_count * 8);
+      GTB_LAUNCH(ctx, "query_counts", query_counts_kernel, grid, 256, 0, q, rv, (const uint2 *)ix->d_qpre.p, o);
+    } else {
+      EnumView ev;
+      ev.n_entries = ix->n_entries; ev.keys = ix->d_keys.p; ev.rid = ix->d_rid.p;
+      ev.r_chrom = ix->d_r_chrom.p; ev.r_start = ix->d_r_start.p; ev.r_stop = ix->d_r_stop.p;
+      ev.r_strand = ix->d_r_strand.p; ev.r_off = ix->d_r_off.p; ev.direct = ix->d_direct.p;
+      const unsigned grid = gtb_grid_for((int64_t)nr, 128, (int64_t)ctx->sm_count * 16);
+      GTB_LAUNCH(ctx, "query_enumerate", query_enumerate_kernel, grid, 128, 0, q, rv, ev, ix->ignore_strand, o);
+    }
+    GTB_TRY(gtb_check_launch(ctx));
+    if (!dev_out) {
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(out + r0, d_out.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->d2h_bytes += (int64_t)nr * 4;
+    }
+    GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));               // the staging buffers are reused by the next chunk
+  }
+  d_out.release();
+  return gtb_index_status(ix, err_index);
 }
 
 // =================================================================================================

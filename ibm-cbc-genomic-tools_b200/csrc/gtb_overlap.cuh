@@ -93,6 +93,9 @@ struct gtb_index {
   dbuf<int8_t> d_r_strand;
   dbuf<int64_t> d_r_off;
   dbuf<ull> d_direct;
+  // per-query counts (lazy): exclusive prefix pairs per slot, see query_counts_kernel
+  bool qpre_ready = false;
+  dbuf<uint2> d_qpre;
 
   // bucket engine state (gtb_bucket.cu)
   struct gtb_bucket_state *bucket = nullptr;

@@ -38,7 +38,7 @@ EXPORTS = [
     "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_get_stream", "gtb_ctx_synchronize",
     "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_transfer_stats", "gtb_ctx_profile", "gtb_ctx_profile_report",
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_add_packed", "gtb_index_finish",
-    "gtb_index_finish_async", "gtb_index_status",
+    "gtb_index_finish_async", "gtb_index_status", "gtb_index_query_counts",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
     "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64", "gtb_sort_regions",
@@ -95,6 +95,7 @@ def load_library(path=LIB_PATH):
         "gtb_index_finish": (ci, [vp, vp, u32, P(i64)]),
         "gtb_index_finish_async": (ci, [vp, vp, u32]),
         "gtb_index_status": (ci, [vp, P(i64)]),
+        "gtb_index_query_counts": (ci, [vp, P(_Set), u32, vp, u32, P(i64)]),
         "gtb_overlap_count": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_overlap_coverage": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_scan_create": (ci, [vp, ctypes.c_int32, vp, P(_ScanParams), P(vp)]),
@@ -295,6 +296,15 @@ class Index:
         copied inside the call"""
         pk = _Packed(n, start_ptr, meta_ptr, read_len)
         self.ctx.check(lib().gtb_index_add_packed(self._h, ctypes.byref(pk), mem))
+
+    def query_counts(self, queries, weight=None, offsets=None):
+        """per-QUERY overlap counts (uint32, one per query region) for host arrays: the dual of add + finish"""
+        st, keep = host_set(queries, weight, offsets)
+        out = np.zeros(st.n_regions, dtype=np.uint32)
+        err = ctypes.c_int64(-1)
+        rc = lib().gtb_index_query_counts(self._h, ctypes.byref(st), MEM_HOST, _np_ptr(out), MEM_HOST, ctypes.byref(err))
+        self.ctx.check(rc, err.value)
+        return out
 
     def finish(self, out=None):
         if out is None:

@@ -153,6 +153,14 @@ int  gtb_index_finish(gtb_index *index, uint64_t *out, unsigned mem, int64_t *er
 int  gtb_index_finish_async(gtb_index *index, uint64_t *out, unsigned mem);
 int  gtb_index_status(gtb_index *index, int64_t *err_index);
 
+/* The per-QUERY dual: for every query region the number of index regions it overlaps -- the length of the
+ * GetOverlap / NextOverlap walk that `genomic_overlaps subset` (is it empty?) and `overlap` (print the query once per step)
+ * make for it (genomic_overlaps.cpp:782-800, :706-739; GenomicRegionSetOverlaps::GetOverlap, genomic_intervals.cpp:5224-5250).
+ * `index` must have been created with GTB_OP_COUNT (its flags say -gaps / -i / -S rules); it is not modified, and queries
+ * streamed with gtb_index_add_queries are unaffected.  out[k] belongs to query region k (host or device memory: out_mem).
+ * Synchronous.  Fatal query conditions are reported as by gtb_index_finish. */
+int  gtb_index_query_counts(gtb_index *index, const gtb_set *queries, unsigned mem, uint32_t *out, unsigned out_mem, int64_t *err_index);
+
 /* One-shot conveniences == create + add + finish + destroy.
  * gtb_overlap_count    <-> GenomicRegionSetOverlaps::CountIndexOverlaps(match_gaps, ignore_strand, max_label_value)  genomic_intervals.h:2471, .cpp:5304-5317
  * gtb_overlap_coverage <-> GenomicRegionSetOverlaps::CalcIndexCoverage(match_gaps, ignore_strand, max_label_value)   genomic_intervals.h:2453, .cpp:5269-5285 */
