@@ -3,8 +3,9 @@
 // Same operations, flags, defaults, usage text, stdout format and exit codes as the reference driver
 // (gtools/genomic_overlaps.cpp:73-261 flags, :408-490 count/coverage/density, :746-775 rpkm); the engine calls
 // GenomicRegionSetOverlaps::CountIndexOverlaps / CalcIndexCoverage are replaced by the C ABI of include/gtb200.h.
-// The other operations of the reference (annotate, bin, dist, intersect, offset, overlap, subset) enumerate
-// pairs and are outside the accelerated path: they are listed for the usage text and refuse to run.
+// `subset` and `overlap` (:782-800, :706-739) are the per-query dual: gtb_index_query_counts + the reference's Print formats.
+// The other operations of the reference (annotate, bin, dist, intersect, offset) enumerate pairs and are outside the
+// accelerated path: they are listed for the usage text and refuse to run.
 #include <stdlib.h>
 #include <string.h>
 #include <iostream>
@@ -15,7 +16,7 @@
 static const char *PROGRAM = "genomic_overlaps";
 static const char *VERSION = "genomic_tools 2.8.1a";
 
-static bool HELP, VERBOSE, IS_SORTED, SORTED_BY_STRAND, IGNORE_STRAND, MATCH_GAPS;
+static bool HELP, VERBOSE, IS_SORTED, SORTED_BY_STRAND, IGNORE_STRAND, MATCH_GAPS, MERGE_LABELS, SUBSET_NONOVERLAPS;
 static const char *BIN_BITS;
 static long MAX_LABEL_VALUE;
 static unsigned long MIN_COUNT;
@@ -78,9 +79,9 @@ int main(int argc, char *argv[]) {
   cmd.AddOperation("dist", USAGE, "Computes the distance between a pair of intervals given breakpoints in reference file (e.g. restriction enzyme sites) [UNDER DEVELOPMENT].", "");
   cmd.AddOperation("intersect", USAGE, "Computes the intersection between all pairs of test and reference regions. Results are grouped by test region.", "");
   cmd.AddOperation("offset", USAGE, "Computes the distances of test regions from their overlapping reference regions.", "");
-  cmd.AddOperation("overlap", USAGE, "Finds the overlaps between all pairs of test and reference regions. Results are grouped by test region.", "");
+  cmd.AddOperation("overlap", USAGE, "Finds the overlaps between all pairs of test and reference regions. Results are grouped by test region.", DETAILS_REGION);
   cmd.AddOperation("rpkm", USAGE, "Computing reference region RPKM values.", DETAILS_REGION);
-  cmd.AddOperation("subset", USAGE, "Picks a subset of test regions depending on their overlap with reference regions. Results are grouped by test region.", "");
+  cmd.AddOperation("subset", USAGE, "Picks a subset of test regions depending on their overlap with reference regions. Results are grouped by test region.", DETAILS_REGION);
   if (argc < 2) {
     cmd.OperationSummary("OPERATION [OPTIONS] REFERENCE-REGION-FILE <TEST-REGION-FILE>",
                          "Performs overlap operations between a test and a reference set of genomic regions.");
@@ -112,8 +113,14 @@ int main(int argc, char *argv[]) {
     cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
     cmd.AddOption("--max-label-value", &MAX_LABEL_VALUE, 1L, "maximum region label value to be used");
     cmd.AddOption("-min", &MIN_RPKM, 0.0, "minimum RPKM");
+  } else if (op == "overlap") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("-label", &MERGE_LABELS, false, "print query label for each match");
+  } else if (op == "subset") {
+    cmd.AddOption("-gaps", &MATCH_GAPS, false, "matching gaps between intervals are considered overlaps");
+    cmd.AddOption("-inv", &SUBSET_NONOVERLAPS, false, "print test regions that do *not* overlap with reference regions");
   } else if (cmd.HasOperation(op)) {
-    std::cerr << "Operation '" << op << "' is outside the GPU-accelerated path of this build (count, coverage, density, rpkm are available)!\n";
+    std::cerr << "Operation '" << op << "' is outside the GPU-accelerated path of this build (count, coverage, density, rpkm, subset, overlap are available)!\n";
     exit(1);
   } else {
     std::cerr << "Unknown operation '" << op << "'!\n";
@@ -123,6 +130,12 @@ int main(int argc, char *argv[]) {
   if (HELP || argc - next_arg < 1) { cmd.OperationUsage(); exit(1); }
   if (IS_SORTED && SORTED_BY_STRAND && IGNORE_STRAND) {
     fprintf(stderr, "[Error]: the input is sorted by chromosome/strand/start (i.e. -S and -s are set), therefore the overlap algorithm can only report strand-specific results (i.e. -i cannot be set)!\n");
+    exit(1);
+  }
+  if (MERGE_LABELS) {
+    // -label names the matching reference regions in the order the reference's bin index walks them (a LIFO chain per bin,
+    // genomic_intervals.cpp:5665-5669): the engine counts matches, it does not order them
+    std::cerr << "Option '-label' of operation 'overlap' is outside the GPU-accelerated path of this build!\n";
     exit(1);
   }
   const char *ref_file = argv[next_arg];
@@ -165,6 +178,13 @@ int main(int argc, char *argv[]) {
     }
   };
 
+  // subset / overlap open the test set with hide_header == false: its header lines are echoed before anything else happens
+  // (genomic_overlaps.cpp:711, :787; ProcessFileHeader)
+  gt::RegionReader *qr_keep = nullptr;
+  if (op == "subset" || op == "overlap") {
+    qr_keep = new gt::RegionReader(test_file, &chroms, true, 1);
+    fwrite(qr_keep->header().data(), 1, qr_keep->header().size(), stdout);
+  }
   timer.Mark("load_reference");
   gtb_ctx *ctx = wait_context();
   int rc = GTB_OK;
@@ -181,6 +201,52 @@ int main(int argc, char *argv[]) {
   check(ctx, rc, "gtb_index_create");
 
   timer.Mark("index");
+  if (op == "subset" || op == "overlap") {
+    // ---- the per-QUERY operations (genomic_overlaps.cpp:782-800, :706-739): a query region is printed if it has an overlap (or has
+    // none: -inv), resp. once per overlapping reference region.  The engine gives the number of overlaps per query
+    // (gtb_index_query_counts); the regions are printed from their input lines the way GenomicRegion*::Print would.
+    gt::RegionReader &qr = *qr_keep;
+    if (VERBOSE) std::cerr << "Reading from '" << (test_file ? test_file : "<standard input>") << "'; format = " << qr.format() << "\n";
+    gt::SortChecker sc; sc.by_strand = SORTED_BY_STRAND;
+    gt::RegionBatch b;
+    std::vector<std::string> raw;
+    std::vector<uint32_t> n_overlaps;
+    std::string text;
+    for (;;) {
+      raw.clear();
+      const int64_t nq = qr.ReadKeep(&b, &raw, 1 << 20);
+      if (nq > 0) {
+        if (IS_SORTED)
+          for (int64_t k = 0; k < nq; k++) {
+            const int64_t i = b.offset[k];
+            if (!gt::RegionWellFormed(b, k)) gt::die_line(b.line(k), "query regions should be compatible, sorted and non-overlapping!");
+            if (!sc.Accept(chroms.name[b.chrom[i]], (char)b.strand[i], b.start[i]))
+              gt::die_line(b.line(k), std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
+            advance_index(b.chrom[i], (char)b.strand[i], b.start[i], b.stop[b.offset[k + 1] - 1]);
+          }
+        gtb_set qs = as_set(b);
+        qs.weight = nullptr;
+        n_overlaps.assign((size_t)nq, 0u);
+        rc = gtb_index_query_counts(index, &qs, GTB_MEM_HOST, n_overlaps.data(), GTB_MEM_HOST, &err_index);
+        const bool fatal = rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION;
+        if (!fatal) check(ctx, rc, "gtb_index_query_counts");
+        const int64_t upto = fatal ? err_index : nq;                     // the reference has printed the queries before the fatal one
+        text.clear();
+        for (int64_t k = 0; k < upto; k++) {
+          const uint32_t times = op == "overlap" ? n_overlaps[(size_t)k] : ((n_overlaps[(size_t)k] == 0) == SUBSET_NONOVERLAPS ? 1u : 0u);
+          for (uint32_t t = 0; t < times; t++) gt::PrintRegion(qr.format(), raw[(size_t)k], b, k, chroms, &text);
+          if (text.size() > (1u << 24)) { fwrite(text.data(), 1, text.size(), stdout); text.clear(); }
+        }
+        fwrite(text.data(), 1, text.size(), stdout);
+        if (fatal) { fflush(stdout); die_query(rc, b.line(err_index)); }
+      }
+      if (qr.failed()) { fflush(stdout); qr.Fail(); }
+      if (nq == 0) break;
+    }
+    fflush(stdout);
+    timer.Mark("stream_queries");
+    return 0;
+  }
   // ---- test (query) set: streamed in chunks; parsing of chunk k+1 overlaps the device work of chunk k
   const int64_t CHUNK = 4 << 20;
   gt::RegionBatch chunk[2];

@@ -448,9 +448,10 @@ RegionReader::RegionReader(const char *path, ChromTable *chroms, bool keep_label
   };
   if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
   if (strncmp(next, "BAM\x01", 4) == 0) die("BAM input is not supported by this build (SAM text is)!\n");   // GetFileType, core.cpp:1757-1775
-  if (is_track(next)) { while (next && is_track(next)) next = reader_.Next(); }
-  else if (next[0] == '@') { format_ = "SAM"; while (next && next[0] == '@') next = reader_.Next(); }
-  else if (next[0] == '#' && next[1] == '#') { format_ = "GFF"; while (next && next[0] == '#' && next[1] == '#') next = reader_.Next(); }
+  auto skip = [&] { header_.append(next); header_.push_back('\n'); next = reader_.Next(); };
+  if (is_track(next)) { while (next && is_track(next)) skip(); }
+  else if (next[0] == '@') { format_ = "SAM"; while (next && next[0] == '@') skip(); }
+  else if (next[0] == '#' && next[1] == '#') { format_ = "GFF"; while (next && next[0] == '#' && next[1] == '#') skip(); }
   if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
   pending_ = next;
   if (format_ != "") { settle(); return; }
@@ -832,6 +833,113 @@ int64_t RegionReader::Read(RegionBatch *out, int64_t max_regions) {
     if (!ParseRun(begin, end, out)) break;
   }
   return out->n_regions();
+}
+
+int64_t RegionReader::ReadKeep(RegionBatch *out, std::vector<std::string> *raw, int64_t max_regions) {
+  out->Clear();
+  if (fmt_ == F_EMPTY || failed_) return 0;
+  ChromCache cache(chroms_);
+  bool first = true;
+  while (out->n_regions() < max_regions) {
+    char *line = pending_;
+    if (line) pending_ = nullptr; else line = reader_.Next();
+    if (line == nullptr) break;
+    if (first) { out->first_line = reader_.line_no(); first = false; }
+    raw->emplace_back(line);                                             // before the tokeniser writes its terminators into the line
+    if (!ParseLine(line, out, &cache, &error_)) {
+      failed_ = true;
+      error_.line = reader_.line_no();
+      raw->pop_back();
+      const size_t keep = (size_t)out->offset.back();
+      out->chrom.resize(keep); out->start.resize(keep); out->stop.resize(keep); out->strand.resize(keep);
+      out->weight.resize(max_label_value_ > 1 ? out->offset.size() - 1 : 0);
+      if (keep_labels_) out->label.resize(out->offset.size() - 1);
+      break;
+    }
+  }
+  return out->n_regions();
+}
+
+static void AppendLong(std::string *out, long v) { char t[32]; out->append(t, (size_t)snprintf(t, sizeof t, "%ld", v)); }
+
+void PrintRegion(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms, std::string *out) {
+  const int64_t lo = b.offset[k], hi = b.offset[k + 1];
+  if (hi <= lo) return;                                                // "if (I.size()==0) return;"
+  const std::string &chrom = chroms.name[b.chrom[lo]];
+  std::string copy(raw);
+  char *inp = &copy[0];
+  if (format == "BED") {                                               // GenomicRegionBED::Print, :2188-2219
+    const char sep = strchr(inp, '\t') == nullptr ? ' ' : '\t';
+    const int n_tokens = CountTokens(inp, sep);
+    NextToken(&inp, sep); NextToken(&inp, sep); NextToken(&inp, sep);
+    out->append(chrom); out->push_back('\t'); AppendLong(out, (long)b.start[lo] - 1); out->push_back('\t'); AppendLong(out, (long)b.stop[hi - 1]);
+    if (n_tokens >= 4) {
+      out->push_back('\t'); out->append(b.label[k]);
+      NextToken(&inp, sep);
+      if (n_tokens >= 5) {
+        out->push_back('\t'); AppendLong(out, atol(NextToken(&inp, sep)));
+        if (n_tokens >= 6) {
+          NextToken(&inp, sep);
+          out->push_back('\t'); out->push_back((char)b.strand[lo]);
+          if (n_tokens >= 8) {
+            const long thick_start = atol(NextToken(&inp, sep)), thick_end = atol(NextToken(&inp, sep));
+            out->push_back('\t'); AppendLong(out, thick_start); out->push_back('\t'); AppendLong(out, thick_end);
+            if (n_tokens >= 9) {
+              out->push_back('\t'); out->append(NextToken(&inp, sep));
+              if (n_tokens == 12) {
+                out->push_back('\t'); AppendLong(out, (long)(hi - lo)); out->push_back('\t');
+                for (int64_t i = lo; i < hi; i++) { AppendLong(out, (long)b.stop[i] - (long)b.start[i] + 1); if (i + 1 < hi) out->push_back(','); }
+                out->append("\t0");
+                for (int64_t i = lo + 1; i < hi; i++) {
+                  if (b.start[i] <= b.stop[i - 1]) { fprintf(stderr, "Line %lu: exons cannot overlap!\n", (unsigned long)b.line(k)); exit(1); }
+                  out->push_back(','); AppendLong(out, (long)b.start[i] - (long)b.start[lo]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    out->push_back('\n');
+  } else if (format == "GFF") {                                        // GenomicRegionGFF::Print, :3523-3530
+    const int n_tokens = CountTokens(inp, '\t');
+    NextToken(&inp, '\t');
+    const char *source = NextToken(&inp, '\t'), *feature = NextToken(&inp, '\t');
+    NextToken(&inp, '\t'); NextToken(&inp, '\t');
+    const char *score = NextToken(&inp, '\t');
+    NextToken(&inp, '\t');
+    const char frame = NextToken(&inp, '\t')[0];
+    out->append(chrom); out->push_back('\t'); out->append(source); out->push_back('\t'); out->append(feature); out->push_back('\t');
+    AppendLong(out, (long)b.start[lo]); out->push_back('\t'); AppendLong(out, (long)b.stop[lo]); out->push_back('\t'); out->append(score);
+    out->push_back('\t'); out->push_back((char)b.strand[lo]); out->push_back('\t'); out->push_back(frame);
+    if (n_tokens > 8) { out->push_back('\t'); out->append(NextToken(&inp, '\t')); }
+    if (n_tokens > 9) { out->push_back('\t'); out->append(NextToken(&inp, '\t')); }
+    out->push_back('\n');
+  } else if (format == "SAM") {                                        // GenomicRegionSAM::Print, :2819-2825
+    const int n_tokens = CountTokens(inp, '\t');
+    const char *label = NextToken(&inp, '\t');
+    const long flag = atol(NextToken(&inp, '\t'));
+    NextToken(&inp, '\t'); NextToken(&inp, '\t');
+    const long mapq = atol(NextToken(&inp, '\t'));
+    const char *cigar = NextToken(&inp, '\t'), *rnext = NextToken(&inp, '\t');
+    const long pnext = atol(NextToken(&inp, '\t')), tlen = atol(NextToken(&inp, '\t'));
+    const char *seq = NextToken(&inp, '\t'), *qual = NextToken(&inp, '\t');
+    out->append(label); out->push_back('\t'); AppendLong(out, flag); out->push_back('\t'); out->append(chrom); out->push_back('\t');
+    AppendLong(out, (long)b.start[lo]); out->push_back('\t'); AppendLong(out, mapq); out->push_back('\t');
+    if (strcmp(cigar, "*") == 0) { AppendLong(out, (long)strlen(seq)); out->push_back('M'); } else out->append(cigar);   // Read replaces "*" (:2791)
+    out->push_back('\t'); out->append(rnext); out->push_back('\t'); AppendLong(out, pnext); out->push_back('\t'); AppendLong(out, tlen);
+    out->push_back('\t'); out->append(seq); out->push_back('\t'); out->append(qual);
+    if (n_tokens > 11) { out->push_back('\t'); out->append(inp); }      // OPTIONAL: the rest of the line
+    out->push_back('\n');
+  } else {                                                             // REG: GenomicRegion::Print, :843-849
+    out->append(b.label[k]); out->push_back('\t');
+    for (int64_t i = lo; i < hi; i++) {
+      out->append(chroms.name[b.chrom[i]]); out->push_back(' '); out->push_back((char)b.strand[i]); out->push_back(' ');
+      AppendLong(out, (long)b.start[i]); out->push_back(' '); AppendLong(out, (long)b.stop[i]);
+      if (i + 1 < hi) out->push_back(' ');
+    }
+    out->push_back('\n');
+  }
 }
 
 void RegionReader::Fail() const {

@@ -169,6 +169,9 @@ class RegionReader {
  public:
   RegionReader(const char *path, ChromTable *chroms, bool keep_labels, long max_label_value);
   const std::string &format() const { return format_; }
+  // the header lines skipped in front of the data (UCSC browser / track lines, SAM '@' lines, GFF '##' lines), each with its
+  // newline: the reference echoes them to stdout for sets it opens with hide_header == false (ProcessFileHeader, :3713-3731)
+  const std::string &header() const { return header_; }
   // Parses regions into `out` (cleared first) until it holds at least max_regions of them or the input ends; returns the
   // number parsed (0 at end).  Lines are parsed by several threads.  A malformed line ends the stream: the regions before it
   // are returned, failed() turns true and Fail() reports it -- so that a caller that streams can first report what an
@@ -176,6 +179,9 @@ class RegionReader {
   int64_t Read(RegionBatch *out, int64_t max_regions);
   bool failed() const { return failed_; }
   [[noreturn]] void Fail() const;                     // prints the parse error the way the reference does, exit(1)
+  // For the operations that print regions (subset, overlap, gsort): like Read, one thread, and every region's input line is
+  // kept in `raw` (appended; raw[k] belongs to region k of out).  Needs keep_labels.
+  int64_t ReadKeep(RegionBatch *out, std::vector<std::string> *raw, int64_t max_regions);
   // Read, then Fail() at once if a line was malformed (sets that are loaded whole)
   int64_t ReadAll(RegionBatch *out) { const int64_t n = Read(out, INT64_MAX); if (failed_) Fail(); return n; }
  private:
@@ -192,6 +198,7 @@ class RegionReader {
   bool keep_labels_;
   long max_label_value_;
   std::string format_;                                // BED REG GFF SAM SEQ EMPTY ""
+  std::string header_;
   Format fmt_ = F_NONE;
   int threads_ = 1;                                   // GT_PARSE_THREADS, default: the host's cores (at most 32)
   char *pending_ = nullptr;                           // first data line, already read during format detection
@@ -201,6 +208,12 @@ class RegionReader {
  public:
   ~RegionReader();
 };
+
+// What GenomicRegion{,BED,GFF,SAM}::Print writes for region k of `b` (genomic_intervals.cpp:843-849, :2188-2219, :3523-3530,
+// :2819-2825), appended to `out` with its newline: the parsed coordinates and strand, the label, and the fields of the input line
+// the reference keeps as they are (BED score / thick / rgb, GFF source / feature / score / frame / comment, the SAM columns).
+// `format` is RegionReader::format(); `raw` the region's input line.
+void PrintRegion(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms, std::string *out);
 
 char ProcessStrand(const char *token);                // '1','+' -> '+'; '-1','-' -> '-'; '.' -> '+'; else fatal  (genomic_intervals.cpp:5956-5962)
 bool RegionWellFormed(const RegionBatch &b, int64_t k);

@@ -4,18 +4,21 @@
 // it doubles as a parse-rate probe (-q: parse only, print the number of regions and intervals).
 //
 //   gt_regdump [-q] [-w MAX_LABEL_VALUE] [-c CHUNK_REGIONS] FILE|-
+//   gt_regdump -p FILE|-        every region as GenomicRegion*::Print would write it in the file's own format (gt::PrintRegion: what
+//                               `genomic_overlaps subset / overlap` and `genomic_regions gsort` print)
 #include <stdlib.h>
 #include <string.h>
 #include <string>
 #include "../gt_host.h"
 
 int main(int argc, char **argv) {
-  bool quiet = false;
+  bool quiet = false, native = false;
   long max_label_value = 1;
   int64_t chunk = INT64_MAX;
   int a = 1;
   for (; a < argc && argv[a][0] == '-' && argv[a][1] != 0; a++) {
     if (!strcmp(argv[a], "-q")) quiet = true;
+    else if (!strcmp(argv[a], "-p")) native = true;
     else if (!strcmp(argv[a], "-w") && a + 1 < argc) max_label_value = atol(argv[++a]);
     else if (!strcmp(argv[a], "-c") && a + 1 < argc) chunk = atol(argv[++a]);
     else { fprintf(stderr, "usage: gt_regdump [-q] [-w MAX_LABEL_VALUE] [-c CHUNK_REGIONS] FILE|-\n"); return 2; }
@@ -27,6 +30,21 @@ int main(int argc, char **argv) {
   gt::RegionBatch b;
   int64_t regions = 0, intervals = 0;
   std::string text;
+  if (native) {
+    fwrite(rr.header().data(), 1, rr.header().size(), stdout);
+    std::vector<std::string> raw;
+    for (;;) {
+      raw.clear();
+      const int64_t n = rr.ReadKeep(&b, &raw, 1 << 16);
+      text.clear();
+      for (int64_t k = 0; k < n; k++) gt::PrintRegion(rr.format(), raw[(size_t)k], b, k, chroms, &text);
+      fwrite(text.data(), 1, text.size(), stdout);
+      if (rr.failed()) { fflush(stdout); rr.Fail(); }
+      if (n == 0) break;
+    }
+    fflush(stdout);
+    return 0;
+  }
   while (rr.Read(&b, chunk) > 0) {
     regions += b.n_regions();
     intervals += (int64_t)b.chrom.size();

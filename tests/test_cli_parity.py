@@ -349,3 +349,57 @@ def test_sam_variants(samfiles, scanfiles):
     (d / "bad.sam").write_text("\n".join(bad) + "\n")
     want, got = both("genomic_overlaps", ["count", d / "idx.bed", d / "bad.sam"])
     assert got[0] == want[0] != 0 and got[1] == want[1] and got[2] == want[2]
+
+
+# ------------------------------------------------------------------------------------------------
+# the per-query operations: subset / overlap (genomic_overlaps.cpp:782-800, :706-739), and genomic_regions gsort
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pair", [("idx.bed", "q.bed"), ("idx_space.bed", "q.reg"), ("idx.reg", "q.gff"), ("idx.gff", "q.bed.gz"),
+                                  ("midx.bed", "mq.bed"), ("midx.reg", "mq.reg"), ("midx.bed", "q.bed"), ("idx.bed", "mq.reg")])
+@pytest.mark.parametrize("args", [["subset"], ["subset", "-inv"], ["subset", "-i"], ["subset", "-gaps", "-inv"], ["overlap"], ["overlap", "-gaps", "-i"]])
+def test_subset_overlap(files, pair, args):
+    d = files["dir"]
+    assert_same("genomic_overlaps", args + [d / pair[0], d / pair[1]], nonempty=True)
+
+
+def test_subset_overlap_sam_sorted_and_errors(files, samfiles, tmp_path):
+    d = files["dir"]
+    # SAM queries: the header lines are echoed first (the test set is opened with hide_header == false), then the records
+    for args in (["subset"], ["subset", "-inv"], ["overlap"], ["overlap", "-gaps"]):
+        want = assert_same("genomic_overlaps", args + [d / "idx.bed", d / "q.sam"], nonempty=True)
+        assert want[1].startswith(b"@HD")
+    assert_same("genomic_overlaps", ["subset", d / "midx.bed"], stdin=(d / "q.sam").read_bytes(), nonempty=True)
+    # -S
+    assert_same("genomic_overlaps", ["subset", "-S", d / "s_idx.bed", d / "s_q.bed"], nonempty=True)
+    assert_same("genomic_overlaps", ["overlap", "-S", "-s", d / "ss_idx.bed", d / "ss_q.bed"], nonempty=True)
+    assert_same("genomic_overlaps", ["subset", "-S", "-inv", "-i", d / "s_idx.bed", d / "s_q.bed"], nonempty=True)
+    # a fatal query in the middle of the file: what was printed before it stays printed, then the message and exit code 1
+    lines = (d / "q.bed").read_text().splitlines()
+    t = lines[2000].split("\t"); t[1], t[2] = "900", "100"; lines[2000] = "\t".join(t)
+    chrom_of_idx = (d / "idx.bed").read_text().split("\t", 1)[0]
+    t = lines[2000].split("\t"); t[0] = chrom_of_idx; lines[2000] = "\t".join(t)
+    (tmp_path / "bad.bed").write_text("\n".join(lines) + "\n")
+    for args in (["subset"], ["overlap"], ["subset", "-inv"]):
+        want, got = both("genomic_overlaps", args + [d / "idx.bed", tmp_path / "bad.bed"])
+        assert got[0] == want[0] == 1 and got[1] == want[1] and len(want[1]) > 0 and got[2] == want[2], args
+    # a malformed line further down: the same
+    lines[2000] = "chr1\tnot-a-number"
+    (tmp_path / "bad2.bed").write_text("\n".join(lines) + "\n")
+    want, got = both("genomic_overlaps", ["subset", d / "idx.bed", tmp_path / "bad2.bed"])
+    assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
+    # -label is refused (the order of the matches is the bin index's business)
+    assert run_new("genomic_overlaps", ["overlap", "-label", d / "idx.bed", d / "q.bed"])[0] == 1
+
+
+@pytest.mark.parametrize("name", ["q.bed", "q.reg", "q.gff", "mq.bed", "mq.reg", "q.sam", "idx_space.bed", "q.bed.gz"])
+@pytest.mark.parametrize("flags", [[], ["-s"], ["-b", "5"]])
+def test_gsort(files, samfiles, name, flags):
+    assert_same("genomic_regions", ["gsort"] + flags + [files["dir"] / name], nonempty=True)
+
+
+def test_gsort_details(files, tmp_path):
+    # intervals inside a region are put in order first (r->Sort()); equal keys keep their input order; stop descending at equal starts
+    (tmp_path / "u.reg").write_text("r1\tchr1 + 500 600 chr1 + 100 200\nr2\tchr1 - 150 160\nr3\tchr1 + 100 900\nr4\tchr1 + 100 900\nr5\tchr10 + 1 2\nr6\tchr2 - 7 9\n")
+    assert_same("genomic_regions", ["gsort", tmp_path / "u.reg"], nonempty=True)
+    assert_same("genomic_regions", ["gsort", "-s", tmp_path / "u.reg"], nonempty=True)
+    assert_same("genomic_regions", ["gsort"], stdin=(files["dir"] / "q.bed").read_bytes(), nonempty=True)

@@ -314,3 +314,36 @@ def test_mutated_lines_differential(tmp_path, kind, n_cases):
         if not ok:
             mismatches.append((mutated, want[0], got[0], want[2][-120:], got[2][-120:]))
     assert not mismatches, mismatches[:5]
+
+
+# ------------------------------------------------------------------------------------------------
+# gt::PrintRegion (what subset / overlap / gsort print) against GenomicRegion*::Print of the reference, without a GPU:
+# `genomic_overlaps subset -inv` against a reference set on a chromosome no query is on prints every query through Print()
+# ------------------------------------------------------------------------------------------------
+def test_print_region_matches_reference_print(tmp_path):
+    if not support.have_ref():
+        pytest.skip("reference binaries not built (oracle/_ref)")
+    (tmp_path / "far.bed").write_text("chrFAR\t1\t2\tx\t0\t+\n")
+    rng = np.random.default_rng(5)
+    cases = {
+        "odd.bed": "chr1 100 200 a 5 +\nchr1 100 200\nchr1 100 200 b\nchr1 100 200 c 7\nchr1\t5\t50\td\t3.7\t-\t7\t9\n"
+                   "chr1\t5\t50\td\t12\t.\t7\t9\t255,0,0\nchr1\t5\t50\td\t12\t1\t7\t9\t255,0,0\t2\n"
+                   "chr1\t1000\t2000\tgD\t0\t+\t1000\t2000\t0\t2\t100,100\t0,900\n",
+        "v.reg": "r1\tchr1 + 100 200 chr1 + 500 600\nr2\tchr1 - 150 160\nr3\tchr2 + 100,300 150,400\n",
+        "v.gff": "##gff-version 2\nchr1\tsrc\tgene\t11\t20\t.\t-\t.\tgC\nchr1\tsrc\tgene\t5\t20\t0.5\t+\t2\tgD\tnote here\nchr1\tsrc\tgene\t5\t20\t.\t.\t.\n",
+        "track.bed": "track name=x\nbrowser position chr1\nchr1\t5\t9\tz\t1\t-\n",
+    }
+    sam = ["@HD\tVN:1.0", "@SQ\tSN:chr1\tLN:5000"]
+    for k in range(500):
+        ln = int(rng.integers(1, 90))
+        cig = ("%dM" % ln) if k % 7 else "*"
+        seq = "A" * (ln if k % 7 else 36)
+        sam.append("\t".join(["r%d" % k, str(int(rng.integers(0, 2048))), "chr1", str(int(rng.integers(1, 4000))), "60", cig, "=", "7", "-3", seq, "*"] +
+                             (["NM:i:1", "XS:A:+"] if k % 3 == 0 else [])))
+    cases["q.sam"] = "\n".join(sam) + "\n"
+    for name, text in cases.items():
+        (tmp_path / name).write_text(text)
+        rc, want, err = support.run_ref("genomic_overlaps", ["subset", "-inv", tmp_path / "far.bed", tmp_path / name], check=False)
+        assert rc == 0 and len(want) > 0, (name, err)
+        rc2, got, err2 = dump(tmp_path / name, {}, args=("-p",))
+        assert rc2 == 0 and got == want, (name, got[:300], want[:300])
