@@ -351,3 +351,131 @@ class ShardedDeviceOverlap:
 
     def close(self):
         self.index.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# window counts (genomic_scans counts) over G ranks: SURVEY.md section 8e, third bullet
+# ---------------------------------------------------------------------------------------------------------------
+class ScanShardPlan:
+    """The micro-window grid of a genome, cut into G contiguous pieces of equal size (or of equal read mass, given a
+    histogram).  Micro-windows are numbered along the chromosomes in id order, `win_step` bp each; window k of a chromosome
+    sums micro-windows k-1 .. k-1+combine-1 (genomic_intervals.cpp:5058-5075), so the rank that owns micro-window m0 = k-1
+    needs the reads of micro-windows [m0, m0 + combine): a HALO of combine - 1 micro-windows to the right of its piece,
+    never across a chromosome end.  A read is routed by the micro-window of its point (start or centre); reads in a halo go to
+    two ranks.  Every rank computes the windows whose FIRST micro-window it owns; there is no exchange besides the final gather."""
+
+    def __init__(self, bound, win_step, win_size, n_shards, micro_mass=None):
+        self.bound = np.asarray(bound, dtype=np.int64)
+        self.step, self.combine, self.n_shards = int(win_step), int(win_size // win_step), int(n_shards)
+        self.n_micro = np.where(self.bound >= 0, self.bound // self.step, 0).astype(np.int64)
+        self.cum = np.concatenate([[0], np.cumsum(self.n_micro)]).astype(np.int64)         # first global micro-window of each chromosome
+        total = int(self.cum[-1])
+        if micro_mass is None:
+            cuts = [(total * s) // self.n_shards for s in range(self.n_shards + 1)]
+        else:                                                                              # (positions, cumulative read counts) on the global grid
+            pos, cs = micro_mass
+            tot = int(cs[-1]) if len(cs) else 0
+            cuts = [0] + [int(pos[min(int(np.searchsorted(cs, (tot * s) // self.n_shards)), len(pos) - 1)]) if tot else (total * s) // self.n_shards
+                          for s in range(1, self.n_shards)] + [total]
+            for s in range(1, len(cuts)):
+                cuts[s] = max(cuts[s], cuts[s - 1])
+        self.cuts = np.array(cuts, dtype=np.int64)                                           # rank s owns global micro-windows [cuts[s], cuts[s+1])
+
+    def micro_of(self, reads, op="1"):
+        """Global micro-window of every read's point, -1 if it counts nowhere (genomic_intervals.cpp:5040-5049)."""
+        chrom = np.asarray(reads["chrom"], dtype=np.int64)
+        s, e = np.asarray(reads["start"], dtype=np.int64), np.asarray(reads["stop"], dtype=np.int64)
+        known = (chrom >= 0) & (chrom < len(self.bound))
+        c = np.where(known, chrom, 0)
+        pos = s if op == "1" else s + (e - s) // 2
+        w = (pos - 1) // self.step
+        ok = known & (self.bound[c] >= 0) & ~((s > e) | (e <= 0)) & (pos >= 1) & (w < self.n_micro[c])
+        return np.where(ok, self.cum[c] + w, -1)
+
+    def route(self, reads, shard, op="1"):
+        """Indices of the reads rank `shard` must histogram: those in its piece and in the halo right of it (same chromosome)."""
+        m = self.micro_of(reads, op)
+        lo, hi = int(self.cuts[shard]), int(self.cuts[shard + 1])
+        if hi <= lo:
+            return np.zeros(0, dtype=np.int64)
+        c_last = int(np.searchsorted(self.cum, hi - 1, side="right") - 1)                   # chromosome of the piece's last micro-window
+        halo_hi = min(hi + self.combine - 1, int(self.cum[c_last + 1]))
+        return np.nonzero((m >= lo) & (m < halo_hi))[0]
+
+    def owns(self, chrom, win, shard):
+        """Whether rank `shard` emits window `win` (1-based) of chromosome `chrom`: it owns the window's first micro-window."""
+        g = self.cum[np.asarray(chrom, dtype=np.int64)] + np.asarray(win, dtype=np.int64) - 1
+        g = np.minimum(g, max(int(self.cum[-1]) - 1, 0))      # (the spurious window of a trailing chromosome without micro-windows: the last rank's)
+        return (g >= self.cuts[shard]) & (g < self.cuts[shard + 1])
+
+
+class CudaScanEngine:
+    """The per-shard engine of the product: a gtb200.Scan on this rank's GPU."""
+
+    def __init__(self, bound, win_step, win_size, op, ignore_strand, min_reads, device):
+        from . import Scan
+        self.ctx = Context(device)
+        self.scan = Scan(self.ctx, bound, win_step, win_size, op, ignore_strand, min_reads)
+
+    def add(self, reads):
+        self.scan.add_host(reads)
+
+    def finish(self):
+        n = self.scan.finish()
+        return self.scan.fetch(0, n)
+
+    def close(self):
+        self.scan.close()
+        self.ctx.close()
+
+
+class ShardedScan:
+    """genomic_scans counts over G ranks.  Every rank passes the same read batches to add() (each keeps what the plan routes
+    to it); finish() returns the qualifying windows in the reference's order (chromosome id, '+' before '-', window) on every
+    rank after ONE all-gather.  Unsorted-scanner semantics, the reference's spurious window on chromosomes shorter than one
+    window included: every rank's engine emits it, the rank that owns the chromosome's first micro-window keeps it."""
+
+    def __init__(self, bound, win_step, win_size, op="1", ignore_strand=False, min_reads=10, micro_mass=None, group=None,
+                 engine_factory=None, device=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.op = op
+        self.plan = ScanShardPlan(bound, win_step, win_size, self.world, micro_mass)
+        if engine_factory is None:
+            dev = self.rank if device is None else device
+            engine_factory = lambda *a: CudaScanEngine(*a, dev)
+        self.engine = engine_factory(np.asarray(bound, dtype=np.int64), win_step, win_size, op, ignore_strand, min_reads)
+
+    def add(self, reads):
+        ids = self.plan.route(reads, self.rank, self.op)
+        if len(ids):
+            self.engine.add({k: np.ascontiguousarray(np.asarray(reads[k])[ids]) for k in ("chrom", "start", "stop", "strand")})
+
+    def finish(self):
+        import torch
+        got = self.engine.finish()
+        keep = self.plan.owns(got["chrom"], got["win"], self.rank) if len(got["win"]) else np.zeros(0, dtype=bool)
+        mine = np.stack([got["chrom"][keep].astype(np.int64), (got["strand"][keep] != ord("+")).astype(np.int64),
+                         got["win"][keep].astype(np.int64), got["value"][keep].astype(np.int64)], 1) if keep.any() else np.zeros((0, 4), np.int64)
+        if self.world > 1:
+            backend = self.dist.get_backend(self.group)
+            dev = "cuda" if backend == "nccl" else "cpu"
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            self.dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64, device=dev), group=self.group)
+            pad = max(int(s.item()) for s in sizes)
+            buf = torch.zeros((max(pad, 1), 4), dtype=torch.int64, device=dev)
+            buf[:len(mine)] = torch.from_numpy(mine).to(dev)
+            parts = [torch.zeros_like(buf) for _ in range(self.world)]
+            self.dist.all_gather(parts, buf, group=self.group)                              # THE collective
+            allw = np.concatenate([p.cpu().numpy()[:int(s.item())] for p, s in zip(parts, sizes)], 0)
+        else:
+            allw = mine
+        order = np.lexsort((allw[:, 2], allw[:, 1], allw[:, 0]))                           # chromosome, strand, window: the reference's order
+        allw = allw[order]
+        return {"chrom": allw[:, 0].astype(np.int32), "strand": np.where(allw[:, 1] == 0, ord("+"), ord("-")).astype(np.int8),
+                "win": allw[:, 2], "value": allw[:, 3]}
+
+    def close(self):
+        self.engine.close()

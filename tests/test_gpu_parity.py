@@ -606,3 +606,27 @@ def test_sort_regions_matches_stable_lexsort(ctx, n):
         sclass = (strand != 43).astype(np.int64) if by_strand else np.zeros(n, np.int64)
         want = np.lexsort((-stop.astype(np.int64), start.astype(np.int64), sclass, chrom.astype(np.int64)))    # last key is the primary one; lexsort is stable
         assert np.array_equal(got, want), (n, by_strand)
+
+
+def test_sharded_scan_cuda_engine(gtb, oracle):
+    """gtb200.sharded.ShardedScan with the CUDA engine, every shard of a 3-way plan run in turn on this GPU: the kept windows of
+    the shards, put together, are the unsharded result (the N > 1 exchange itself is covered on the CPU over gloo)."""
+    from gtb200 import sharded
+    lens = support.HG19_LENS[:6]
+    reads = support.synth_reads(2_000_000, seed=41, chrom_lens=lens)
+    n, want = oracle.scan_counts(reads, lens, 50, 200, "1", False, 1)
+    plan = sharded.ScanShardPlan(lens, 50, 200, 3)
+    parts = []
+    for shard in range(3):
+        eng = sharded.CudaScanEngine(lens, 50, 200, "1", False, 1, 0)
+        ids = plan.route(reads, shard)
+        eng.add({k: np.ascontiguousarray(v[ids]) for k, v in reads.items()})
+        got = eng.finish()
+        keep = plan.owns(got["chrom"], got["win"], shard)
+        parts.append({k: v[keep] for k, v in got.items()})
+        eng.close()
+    allw = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    order = np.lexsort((allw["win"], allw["strand"] != ord("+"), allw["chrom"]))
+    assert len(order) == n
+    for k in ("chrom", "strand", "win", "value"):
+        assert np.array_equal(allw[k][order], want[k]), k

@@ -181,3 +181,77 @@ def test_plan_properties():
     plan = sharded.ShardPlan(idx, 4)
     assert np.all(np.diff(plan.lo) >= 0) and plan.lo[0] < 0
     assert len(plan.cut_positions()) == 3
+
+
+# ------------------------------------------------------------------------------------------------
+# window counts over several ranks (gtb200.sharded.ShardedScan): range cuts inside chromosomes, halo of combine - 1 micro-windows
+# ------------------------------------------------------------------------------------------------
+class OracleScanEngine:
+    def __init__(self, bound, win_step, win_size, op, ignore_strand, min_reads):
+        self.orc = support.Oracle()
+        self.args = (bound, win_step, win_size, op, ignore_strand, min_reads)
+        self.batches = []
+
+    def add(self, reads):
+        self.batches.append(reads)
+
+    def finish(self):
+        reads = {k: np.concatenate([b[k] for b in self.batches]) if self.batches else np.zeros(0, np.int8 if k == "strand" else np.int32)
+                 for k in ("chrom", "start", "stop", "strand")}
+        n, out = self.orc.scan_counts(reads, *self.args)
+        return out
+
+    def close(self):
+        pass
+
+
+SCAN_CASES = [dict(step=25, size=100, op="1", ign=False, mn=2), dict(step=50, size=50, op="c", ign=True, mn=1), dict(step=10, size=70, op="1", ign=False, mn=3)]
+
+
+def _scan_inputs():
+    rng = np.random.default_rng(4242)
+    bound = np.array([5000, -1, 1730, 12007, 90], dtype=np.int64)          # a chromosome absent from the genome file, one shorter than a window
+    n = 40000
+    reads = {"chrom": rng.integers(0, 6, n).astype(np.int32), "start": rng.integers(-20, 12500, n).astype(np.int32),
+             "strand": rng.choice(np.array([43, 45], np.int8), n)}
+    reads["stop"] = (reads["start"] + rng.integers(-2, 120, n)).astype(np.int32)
+    return bound, reads
+
+
+def _scan_worker(rank, world, port, out_dir):
+    try:
+        import torch.distributed as dist
+        from gtb200 import sharded
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        bound, reads = _scan_inputs()
+        for i, c in enumerate(SCAN_CASES):
+            ss = sharded.ShardedScan(bound, c["step"], c["size"], c["op"], c["ign"], c["mn"], engine_factory=lambda *a: OracleScanEngine(*a))
+            half = len(reads["chrom"]) // 2
+            ss.add({k: v[:half] for k, v in reads.items()})
+            ss.add({k: v[half:] for k, v in reads.items()})
+            got = ss.finish()
+            np.savez(os.path.join(out_dir, "scan_%d_%d_%d.npz" % (i, world, rank)), **got)
+            ss.close()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        with open(os.path.join(out_dir, "fail_%d_%d.txt" % (world, rank)), "w") as f:
+            f.write(traceback.format_exc())
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_scan_equals_unsharded(world, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_scan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    fails = [f for f in os.listdir(tmp_path) if f.startswith("fail_")]
+    assert not fails, open(os.path.join(tmp_path, fails[0])).read()
+    orc = support.Oracle()
+    bound, reads = _scan_inputs()
+    for i, c in enumerate(SCAN_CASES):
+        n, want = orc.scan_counts(reads, bound, c["step"], c["size"], c["op"], c["ign"], c["mn"])   # the Unsorted scanner, its spurious windows included
+        assert n > 50
+        for rank in range(world):
+            got = np.load(os.path.join(tmp_path, "scan_%d_%d_%d.npz" % (i, world, rank)))
+            for k in ("chrom", "strand", "win", "value"):
+                assert np.array_equal(got[k], want[k]), (i, world, rank, k)
