@@ -56,6 +56,7 @@ struct DirectView {
   uint32_t *flag;                   // [0] generation of the last batch in which a byte counter overflowed (that batch is discarded and replayed)
                                     // [1] coverage: queries whose length was not the batch's common one (a global reduction each)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
+  uint32_t n_cells;                 // entries of `cells` (bounds checks)
 };
 constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
 
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
       base[i] = (min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask)) * stride;   // unknown chromosome -> the all-"nothing" block
+      GTB_ASSERT(base[i] + last < dv.n_cells);
       ent[i] = dr_gather(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));
     }
     uint32_t jS[DR_ITEMS], jE[DR_ITEMS], j0E[DR_ITEMS];
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
       const bool both = !((done >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
+      GTB_ASSERT(!both || (ull)jS[i] < (ull)rv.n_slots);
+      GTB_ASSERT(((skip >> i) & 1u) || ((ull)jS[i] < (ull)rv.n_slots && (ull)jE[i] < (ull)rv.n_slots));
       old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((jS[i] & 3u) * 8u) : 0u);
     }
 #pragma unroll
@@ -457,7 +461,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   rv.goff = ix->d_goff.p; rv.points = ix->d_points.p; rv.n_slots = ix->n_slots; rv.hist = ds->d_delta.p; rv.err = ix->d_err.p; rv.admission = ix->admission();
   DirectView dv;
   dv.cbits = ds->cbits; dv.n_chrom = ix->n_chrom; dv.nsig = ds->nsig; dv.stride = ds->stride; dv.cells = ds->d_cells.p;
-  dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
+  dv.n_cells = ds->n_cells; dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
   RankView rv_hist = rv;

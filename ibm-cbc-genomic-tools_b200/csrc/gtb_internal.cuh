@@ -11,6 +11,17 @@
 
 #define GTB_SM_COUNT_FALLBACK 148
 
+// Bounds checks on the data-dependent indices of the kernels.  compute-sanitizer is closed on the pool this was developed
+// on (profiles/r2j_sanitizer_closed.txt), so `make checked` builds lib/libgtb200_checked.so with device-side assert() at
+// every such index; the GPU tests run against it once (GTB200_LIB=...; profiles/scripts/r2k_checked.sh).  In the product
+// build the macro is empty.
+#ifdef GTB_BOUNDS_CHECK
+#include <assert.h>
+#define GTB_ASSERT(cond) assert(cond)
+#else
+#define GTB_ASSERT(cond) ((void)0)
+#endif
+
 struct gtb_kernel_stat {
   int64_t launches = 0;
   double total_ms = 0.0;

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) query_counts_kernel(QueryView q, RankView
           const int32_t qs = q.start[lo], qe = q.stop[hi - 1];
           const int jS = lower_bound_i32(ix.points, gb, ge - 1, qs);
           const int jE = lower_bound_i32(ix.points, qe < qs ? gb : jS, ge - 1, qe);
+          GTB_ASSERT(jS >= gb && jS < ge && jE >= gb && jE < ge);
           n = pre[jE].x - pre[jS].y;
         }
       }
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(int64_t n_regions, const 
   ull total = direct ? direct[k] : 0ull;
   for (int64_t t = t_off[k]; t < t_off[k + 1]; t++) {
     const int hi = t_hi[t], lo = t_lo[t], g = t_group[t], base = goff[g];
+    GTB_ASSERT(hi >= base && hi < K && lo >= base && lo < K);
     // group-relative inclusive prefix of slot plane p at slot j
     auto pre = [&](int p, int j) -> ull {
       const ull *a = scan + (int64_t)p * K;

@@ -40,6 +40,7 @@ __device__ __forceinline__ void rank_item(const RankView &ix, int gb, int ge, in
   const int jE = lower_bound_i32(ix.points, qe < qs ? gb : jS, ge - 1, qe);   // (a zero-length interval under the Sorted class's rules: stop == start - 1)
   ull *h = ix.hist;
   const int64_t K = ix.n_slots;
+  GTB_ASSERT(gb >= 0 && jS >= gb && jS < ge && jE >= gb && jE < ge && ge <= K);
   if (jS == jE) {
     if (COVERAGE) atomicAdd(h + H_BOTH * K + jS, (ull)(w * ((int64_t)qe - qs + 1)));
     else atomicAdd(h + H_BOTH * K + jS, (ull)w);

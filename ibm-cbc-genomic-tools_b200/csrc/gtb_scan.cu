@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
     __threadfence();                                   // ordered before this CTA's plain read-modify-write of the same entry below
   };
   auto add = [&](uint32_t loc, uint32_t v) {
+    GTB_ASSERT(loc < span);
     const uint32_t sh = (loc & 1u) * 16u;
     const uint32_t old = (atomicAdd(&s_cnt[loc >> 1], v << sh) >> sh) & 0xFFFFu;
     if (old + v >= 0x8000u) fixup(loc, v, old);
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
       const uint32_t s0 = (l0 & 1u) * 16u, s1 = (l1 & 1u) * 16u, s2 = (l2 & 1u) * 16u, s3 = (l3 & 1u) * 16u;
       // (an element outside the sub-range adds 0 to the lane's own dummy word: no branch, no reconvergence barrier around the atomic)
       const uint32_t dummy = words + lane;
+      GTB_ASSERT((!in0 || l0 < span) && (!in1 || l1 < span) && (!in2 || l2 < span) && (!in3 || l3 < span) && dummy < words + 32u);
       const uint32_t o0 = atomicAdd(&s_cnt[in0 ? l0 >> 1 : dummy], in0 ? 1u << s0 : 0u) >> s0;
       const uint32_t o1 = atomicAdd(&s_cnt[in1 ? l1 >> 1 : dummy], in1 ? 1u << s1 : 0u) >> s1;
       const uint32_t o2 = atomicAdd(&s_cnt[in2 ? l2 >> 1 : dummy], in2 ? 1u << s2 : 0u) >> s2;

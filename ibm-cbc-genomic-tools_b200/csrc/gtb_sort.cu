@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(int64_t n, S
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     if (d < 256u) {
       const ull pos = s_base[warp][d] + rank;
+      GTB_ASSERT(pos < (ull)n);
       out.k0[pos] = in.k0[i]; out.k1[pos] = in.k1[i]; out.k2[pos] = in.k2[i]; out.idx[pos] = in.idx[i];
     }
     __syncwarp();
