@@ -16,6 +16,10 @@
 //     keeping its own sub-range (the bucket's elements come from L2 after the first of them) -- and adds the non-zero
 //     counters to the table with plain coalesced read-modify-writes: a bucket range belongs to exactly one CTA.
 #include "gtb_internal.cuh"
+#ifndef GTB_SCAN_WC_THREADS
+#define GTB_SCAN_WC_THREADS 1024
+#endif
+#define GTB_WC_THREADS GTB_SCAN_WC_THREADS            // this file's instance of the partition (1 024: up to 1 024 buckets, one CTA per SM)
 #include "gtb_wc_partition.cuh"
 #include <algorithm>
 
@@ -41,10 +45,28 @@ struct ReadView {
   int64_t interval_base;
 };
 
+// The micro-window table.  The reference's counters are 64-bit (`long`); here a value is a uint32 plane plus a carry plane that
+// is neither written nor read until some entry passes 2^32 (flags[0]), which halves the table's traffic for every real input
+// and keeps the arithmetic exact (mod 2^64, like the reference's) for the others.
+struct ScanTable {
+  uint32_t *lo, *hi;
+  uint32_t *flags;                 // [0] the carry plane holds something  [1] some qualifying window's value needs more than 32 bits
+};
+__device__ __forceinline__ void table_carry(const ScanTable &t, int64_t m, uint32_t c) { atomicAdd(t.hi + m, c); t.flags[0] = 1u; }
+__device__ __forceinline__ void table_add(const ScanTable &t, int64_t m, ull w) {          // entry m += w, atomically
+  const uint32_t wlo = (uint32_t)w;
+  uint32_t whi = (uint32_t)(w >> 32);
+  if (wlo) { const uint32_t old = atomicAdd(t.lo + m, wlo); whi += old + wlo < old ? 1u : 0u; }
+  if (whi) table_carry(t, m, whi);
+}
+__device__ __forceinline__ ull table_get(const ScanTable &t, bool wide, int64_t m) {
+  return (ull)t.lo[m] | (wide ? (ull)t.hi[m] << 32 : 0ull);
+}
+
 // one thread per read region; every interval of the region counts once (genomic_intervals.cpp:5039)
 __global__ void __launch_bounds__(256) scan_histogram_kernel(ReadView q, int32_t n_chrom, const int32_t *__restrict__ slot_of_chrom,
                                                              const int64_t *__restrict__ hist_off, long long win_step, int op,
-                                                             int ignore_strand, ull *__restrict__ hist) {
+                                                             int ignore_strand, ScanTable hist) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
     int64_t lo = r, hi = r + 1;
@@ -63,7 +85,7 @@ __global__ void __launch_bounds__(256) scan_histogram_kernel(ReadView q, int32_t
       if (!(ignore_strand || q.strand[i] == '+')) slot += 1;         // :5048
       const long long n_micro = hist_off[slot + 1] - hist_off[slot];
       if (win >= n_micro) continue;                                  // :5049  (w <= n)
-      atomicAdd(hist + hist_off[slot] + win, (ull)w);
+      table_add(hist, hist_off[slot] + win, (ull)w);
     }
   }
 }
@@ -79,7 +101,7 @@ struct ScanFront {
   uint32_t magic; int shift;                          // (pos - 1) / win_step == ((pos - 1) * magic) >> shift for pos - 1 < 2^31
   uint32_t mb;
   int centre, ignore_strand;
-  ull *hist;
+  ScanTable hist;
   __device__ __forceinline__ uint32_t table_size() const { return 2u * n_chrom + 2u; }
   __device__ __forceinline__ uint4 table_entry(uint32_t i) const { return tab[i]; }
   __device__ __forceinline__ uint32_t table_index(int32_t c, uint32_t xw, int i) const {
@@ -103,25 +125,24 @@ struct ScanFront {
   __device__ __forceinline__ void divert(int32_t c, int32_t s, int32_t e, uint32_t sbyte, int64_t) const {
     const uint32_t sel = ignore_strand ? 0u : (sbyte != (uint32_t)'+' ? 1u : 0u);
     uint32_t m;
-    if (micro(tab[2u * min((uint32_t)c, n_chrom) + sel], s, e, m)) atomicAdd(hist + m, 1ull);
+    if (micro(tab[2u * min((uint32_t)c, n_chrom) + sel], s, e, m)) table_add(hist, m, 1ull);
   }
 };
 
-constexpr int SB_SUB_BITS = 16;                        // micro-windows per CTA: 65 536 16-bit counters = 128 KB of shared memory
-
-// CTA (bucket b, sub-range z): counts the elements of b that fall into [z << 16, (z + 1) << 16) and adds them to the table.
+// CTA (bucket b, sub-range z): counts the elements of b that fall into [z * span, (z + 1) * span) and adds them to the table;
+// span = as many 16-bit counters as one SM's shared memory holds (hg19, step 50: buckets of 2^18 micro-windows, three CTAs each).
 // Counters are 16 bits, two to a word.  The thread whose add takes a counter from below 2^15 to 2^15 or more moves 2^15 to the
 // table; a thread that finds a counter at 3 * 2^14 or more (that correction still pending) takes its own add back and sends it to
 // the table instead.  Every thread has at most one add of <= 4 in flight, so a counter stays below 3 * 2^14 + 4 096 < 2^16.
 template <int SB_THREADS, int SB_UNROLL_>
-__global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView wv, uint32_t mb, uint32_t n_sub, uint32_t words, ull *__restrict__ hist) {
+__global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView wv, uint32_t mb, uint32_t n_sub, uint32_t words, ScanTable hist) {
   extern __shared__ __align__(16) uint32_t s_cnt[];   // [words] counters + [32] one dummy word per lane
   const uint32_t b = blockIdx.x / n_sub, z = blockIdx.x % n_sub;
   const uint32_t first = wv.line_off[b], last = wv.line_off[b + 1];
   if (first == last) return;
   for (uint32_t i = threadIdx.x * 4; i < words + 32; i += SB_THREADS * 4) *reinterpret_cast<uint4 *>(s_cnt + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const uint32_t lo = z << SB_SUB_BITS, span = 2u * words;
+  const uint32_t span = 2u * words, lo = z * span;
   const ull m0 = ((ull)b << mb) + lo;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // the rare part of an add of v that found the counter at `old`
@@ -129,10 +150,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
     const uint32_t sh = (loc & 1u) * 16u;
     if (old < 0x8000u) {                               // this add crossed 2^15: move 2^15 to the table
       atomicSub(&s_cnt[loc >> 1], 0x8000u << sh);
-      atomicAdd(hist + m0 + loc, 0x8000ull);
+      table_add(hist, (int64_t)(m0 + loc), 0x8000ull);
     } else if (old + v >= 0xC000u) {                   // the correction above is still pending and the counter keeps climbing: count elsewhere
       atomicSub(&s_cnt[loc >> 1], v << sh);
-      atomicAdd(hist + m0 + loc, (ull)v);
+      table_add(hist, (int64_t)(m0 + loc), (ull)v);
     }
     __threadfence();                                   // ordered before this CTA's plain read-modify-write of the same entry below
   };
@@ -168,7 +189,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
       if (fill[r] <= q4) continue;
       const uint32_t el[4] = {d[r].x, d[r].y, d[r].z, d[r].w};
       const uint32_t nv = min(fill[r] - q4, 4u);
-      // this CTA's sub-range only (a bucket wider than 65 536 micro-windows is read by several CTAs): keep the test lean
+      // this CTA's sub-range only (a bucket wider than one CTA's counters is read by several CTAs): keep the test lean
       const uint32_t l0 = el[0] - lo, l1 = el[1] - lo, l2 = el[2] - lo, l3 = el[3] - lo;
       const bool in0 = l0 < span, in1 = l1 < span && nv > 1u, in2 = l2 < span && nv > 2u, in3 = l3 < span && nv > 3u;
       if (!(in0 | in1 | in2 | in3)) continue;
@@ -191,12 +212,13 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
     }
   }
   __syncthreads();
-  // four counters (two words) per thread and trip: 32-byte reads and writes of the table, all loads of a trip issued before its stores
+  // two counters (one word) per thread and trip: 8-byte reads and writes of the table's uint32 plane, all loads of a trip issued
+  // before its stores; an entry that passes 2^32 here sends its carry to the other plane
   constexpr uint32_t FL_UNROLL = 4;
-  ulonglong2 *hv = reinterpret_cast<ulonglong2 *>(hist + m0);                 // m0 is a multiple of 1 024: 16-byte aligned
+  uint2 *hv = reinterpret_cast<uint2 *>(hist.lo + m0);                        // m0 is a multiple of 8
   for (uint32_t i0 = threadIdx.x; i0 < words; i0 += SB_THREADS * FL_UNROLL) {
     uint32_t w[FL_UNROLL];
-    ulonglong2 h[FL_UNROLL];
+    uint2 h[FL_UNROLL];
 #pragma unroll
     for (uint32_t r = 0; r < FL_UNROLL; r++) {
       const uint32_t i = i0 + r * SB_THREADS;
@@ -206,7 +228,12 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bucket_hist_kernel(WcView 
 #pragma unroll
     for (uint32_t r = 0; r < FL_UNROLL; r++) {
       const uint32_t i = i0 + r * SB_THREADS;
-      if (w[r]) { h[r].x += (ull)(w[r] & 0xFFFFu); h[r].y += (ull)(w[r] >> 16); hv[i] = h[r]; }
+      if (w[r]) {
+        const uint2 n = make_uint2(h[r].x + (w[r] & 0xFFFFu), h[r].y + (w[r] >> 16));
+        hv[i] = n;
+        if (n.x < h[r].x) table_carry(hist, (int64_t)(m0 + 2u * i), 1u);
+        if (n.y < h[r].y) table_carry(hist, (int64_t)(m0 + 2u * i + 1u), 1u);
+      }
     }
   }
 }
@@ -222,28 +249,35 @@ __device__ __forceinline__ int find_slot(const int64_t *__restrict__ win_off, in
   return lo;
 }
 
-__device__ __forceinline__ long long window_value(const SlotTable &t, const ull *__restrict__ hist, int slot, int64_t k0, int combine) {
+__device__ __forceinline__ long long window_value(const SlotTable &t, const ScanTable &hist, bool wide, int slot, int64_t k0, int combine) {
   const int64_t base = t.hist_off[slot];
   if (t.spurious[slot]) {
     // Next() hands back current_v[1] of a slot that has no complete window (:5128-5140); with no
     // micro-window at all the reference reads past its allocation -- 0 in practice.
-    return t.hist_off[slot + 1] - base >= 1 ? (long long)hist[base] : 0;
+    return t.hist_off[slot + 1] - base >= 1 ? (long long)table_get(hist, wide, base) : 0;
   }
   ull sum = 0;
-  for (int j = 0; j < combine; j++) sum += hist[base + k0 + j];     // :5066-5073
+  for (int j = 0; j < combine; j++) sum += table_get(hist, wide, base + k0 + j);     // :5066-5073
   return (long long)sum;
 }
 
+// What the window pass leaves on the device: 10 bytes per qualifying window (the slot says chromosome and strand); gtb_scan_fetch
+// widens a range of them to the interface's arrays.
+struct WindowsOut {
+  uint32_t *win;                   // 1-based window number inside its slot, :5109-5112
+  uint32_t *val, *val_hi;          // value; the upper half only exists if some value needs it (flags[1])
+  uint16_t *slot16; uint32_t *slot32;   // one of the two
+};
+
 // MODE 0: count qualifying windows per tile.  MODE 1: write them at tile_offset + local rank.
 template <int MODE>
-__global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, const ull *__restrict__ hist, int64_t total_windows,
-                                                                    int combine, long long min_reads, ull *__restrict__ tile_counts,
-                                                                    int32_t *__restrict__ o_chrom, int8_t *__restrict__ o_strand,
-                                                                    int64_t *__restrict__ o_win, int64_t *__restrict__ o_value) {
+__global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, ScanTable hist, int64_t total_windows,
+                                                                    int combine, long long min_reads, ull *__restrict__ tile_counts, WindowsOut out) {
   __shared__ int warp_counts[WIN_THREADS / 32];
   __shared__ ull tile_base;
   // the tile's micro-windows, staged with one pad entry per 8 so that thread t's run (8 t ...) starts in its own bank pair
   __shared__ ull s_h[(WIN_TILE + WIN_MAX_COMBINE) + (WIN_TILE + WIN_MAX_COMBINE) / 8 + 1];
+  const bool wide = *reinterpret_cast<volatile const uint32_t *>(hist.flags) != 0u;
   const int64_t tile_first = (int64_t)blockIdx.x * WIN_TILE;
   const int64_t tile_last = min(total_windows, tile_first + WIN_TILE) - 1;
   const int64_t first = tile_first + (int64_t)threadIdx.x * WIN_ITEMS;
@@ -254,8 +288,8 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
   if (tile_last < t.win_off[slot_a + 1] && !t.spurious[slot_a] && combine <= WIN_MAX_COMBINE) {
     // the whole tile lies in one (chromosome, strand) slot -- all but a few dozen tiles: coalesced load, sliding sums from shared memory
     const int n_w = (int)(tile_last - tile_first + 1), n_h = n_w + combine - 1;
-    const ull *src = hist + t.hist_off[slot_a] + (tile_first - t.win_off[slot_a]);
-    for (int i = threadIdx.x; i < n_h; i += WIN_THREADS) s_h[i + (i >> 3)] = src[i];
+    const int64_t src = t.hist_off[slot_a] + (tile_first - t.win_off[slot_a]);
+    for (int i = threadIdx.x; i < n_h; i += WIN_THREADS) s_h[i + (i >> 3)] = table_get(hist, wide, src + i);
     __syncthreads();
     const int w0 = threadIdx.x * WIN_ITEMS;
     auto at = [&](int i) { return s_h[i + (i >> 3)]; };
@@ -280,7 +314,7 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
       if (g < total_windows) {
         while (g >= t.win_off[slot + 1]) slot++;
         slot_of[i] = slot;
-        val[i] = window_value(t, hist, slot, g - t.win_off[slot], combine);
+        val[i] = window_value(t, hist, wide, slot, g - t.win_off[slot], combine);
         if (val[i] >= min_reads) keep |= 1u << i;
       }
     }
@@ -303,11 +337,15 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
   const int block_total = warp_counts[WIN_THREADS / 32 - 1];
   if (MODE == 0) {
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = (ull)block_total;
+    bool big = false;                                                   // a qualifying value beyond 32 bits: the emit pass then writes upper halves
+#pragma unroll
+    for (int i = 0; i < WIN_ITEMS; i++) big = big || ((keep >> i) & 1u && ((ull)val[i] >> 32) != 0ull);
+    if (big) hist.flags[1] = 1u;
     return;
   }
   if (threadIdx.x == 0) tile_base = blockIdx.x == 0 ? 0ull : tile_counts[blockIdx.x - 1];   // inclusive-scanned counts
   __syncthreads();                                                     // also: everybody is done reading s_h
-  // the kept windows go to shared memory in output order and leave as coalesced runs of the four output arrays
+  // the kept windows go to shared memory in output order and leave as coalesced runs of the output arrays
   __shared__ uint16_t s_idx[WIN_TILE], s_slot[WIN_TILE];
   ull *s_val = s_h;
   int r = (warp > 0 ? warp_counts[warp - 1] : 0) + inc - mine;
@@ -324,10 +362,32 @@ __global__ void __launch_bounds__(WIN_THREADS) scan_windows_kernel(SlotTable t, 
   const int64_t o0 = (int64_t)tile_base;
   for (int j = threadIdx.x; j < block_total; j += WIN_THREADS) {
     const int s = slot_a + s_slot[j];
-    o_chrom[o0 + j] = t.chrom[s]; o_strand[o0 + j] = t.strand[s];
-    o_win[o0 + j] = tile_first + s_idx[j] - t.win_off[s] + 1;           // 1-based window number, :5109-5112
-    o_value[o0 + j] = (long long)s_val[j];
+    if (out.slot16) out.slot16[o0 + j] = (uint16_t)s; else out.slot32[o0 + j] = (uint32_t)s;
+    out.win[o0 + j] = (uint32_t)(tile_first + s_idx[j] - t.win_off[s] + 1);
+    out.val[o0 + j] = (uint32_t)s_val[j];
+    if (out.val_hi) out.val_hi[o0 + j] = (uint32_t)(s_val[j] >> 32);
   }
+}
+
+// a range of the compact windows -> the arrays of gtb_scan_fetch (device staging; null pointers are skipped)
+__global__ void __launch_bounds__(256) scan_expand_kernel(SlotTable t, WindowsOut w, int64_t first, int64_t count, int32_t *__restrict__ o_chrom,
+                                                           int8_t *__restrict__ o_strand, int64_t *__restrict__ o_win, int64_t *__restrict__ o_value) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t g = first + i;
+    const int s = w.slot16 ? (int)w.slot16[g] : (int)w.slot32[g];
+    if (o_chrom) o_chrom[i] = t.chrom[s];
+    if (o_strand) o_strand[i] = t.strand[s];
+    if (o_win) o_win[i] = (int64_t)w.win[g];
+    if (o_value) o_value[i] = (int64_t)((ull)w.val[g] | (w.val_hi ? (ull)w.val_hi[g] << 32 : 0ull));
+  }
+}
+
+// gtb_scan_reset: the carry plane is cleared only if it was ever written
+__global__ void __launch_bounds__(256) scan_clear_carry_kernel(ScanTable hist, int64_t n) {
+  if (*reinterpret_cast<volatile const uint32_t *>(hist.flags) == 0u) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) hist.hi[i] = 0u;
 }
 
 }  // namespace
@@ -341,12 +401,20 @@ struct gtb_scan {
   dbuf<int32_t> d_slot_of_chrom, d_spurious, d_slot_chrom;
   dbuf<int8_t> d_slot_strand;
   dbuf<int64_t> d_hist_off, d_win_off;
-  dbuf<ull> d_hist, d_tile_counts, d_scan_scratch;
-  dbuf<int32_t> o_chrom; dbuf<int8_t> o_strand; dbuf<int64_t> o_win, o_value;
+  dbuf<uint32_t> d_lo, d_hi, d_flags;                  // the table (ScanTable)
+  dbuf<ull> d_tile_counts, d_scan_scratch;
+  dbuf<uint32_t> c_win, c_val, c_val_hi, c_slot32; dbuf<uint16_t> c_slot16;   // the qualifying windows, compact (WindowsOut)
+  bool wide_values = false;                            // c_val_hi is in use
+  dbuf<int32_t> o_chrom; dbuf<int8_t> o_strand; dbuf<int64_t> o_win, o_value;   // staging of gtb_scan_fetch
+  uint32_t *h_flags = nullptr;                         // pinned: [0..1] the table's flags, [2..3] the window total
+  ScanTable table() const { return ScanTable{d_lo.p, d_hi.p, d_flags.p}; }
+  WindowsOut windows() const {
+    return WindowsOut{c_win.p, c_val.p, wide_values ? c_val_hi.p : nullptr, n_slots <= 65536 ? c_slot16.p : nullptr, n_slots <= 65536 ? nullptr : c_slot32.p};
+  }
   // bucketed histogram (unweighted batches of at least bucket_min intervals)
   bool bucket_ok = false;
   int64_t bucket_min = (int64_t)2 << 20;
-  uint32_t mb = 0, n_buckets = 0, n_sub = 1, sb_words = 0;
+  uint32_t mb = 0, n_buckets = 0, n_sub = 1, sb_words = 0;   // a bucket = 2^mb micro-windows, counted by n_sub CTAs of 2 * sb_words counters
   uint32_t magic = 0; int shift = 0;
   dbuf<uint4> d_front_tab;
   WcBuffers wc;
@@ -366,9 +434,13 @@ static int upload_vec(gtb_ctx *ctx, dbuf<T> &d, const std::vector<T> &h) {
 
 extern "C" int gtb_scan_reset(gtb_scan *sc) {
   if (!sc) return GTB_ERR_ARG;
-  GTB_CUDA_OK(sc->ctx, cudaMemsetAsync(sc->d_hist.p, 0, sizeof(ull) * (size_t)std::max<int64_t>(sc->total_micro, 1), sc->ctx->stream));
+  gtb_ctx *ctx = sc->ctx;
+  const int64_t n = std::max<int64_t>(sc->total_micro, 1);
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(sc->d_lo.p, 0, sizeof(uint32_t) * (size_t)n, ctx->stream));
+  GTB_LAUNCH(ctx, "scan_clear_carry", scan_clear_carry_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, sc->table(), n);
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(sc->d_flags.p, 0, 2 * sizeof(uint32_t), ctx->stream));
   sc->n_out = 0;
-  return GTB_OK;
+  return gtb_check_launch(ctx);
 }
 
 extern "C" int gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bound, const gtb_scan_params *params, gtb_scan **out) {
@@ -405,23 +477,26 @@ extern "C" int gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bou
   sc->n_slots = (int32_t)slot_chrom.size();
   sc->total_micro = hist_off.back(); sc->total_windows = win_off.back();
   int rc = upload_vec(ctx, sc->d_slot_of_chrom, slot_of_chrom);
-  // bucketed histogram: <= 512 buckets of 2^mb micro-windows, at least 256 of them (fewer overfill the partition's rings);
-  // a bucket wider than one CTA's 65 536 counters is walked by 2^(mb - 16) CTAs, at most 16
+  // bucketed histogram: <= WC_MAX_BUCKETS buckets of 2^mb micro-windows, at least 256 of them (fewer overfill the partition's
+  // rings); a bucket wider than the 16-bit counters one SM's shared memory holds is walked by several CTAs, at most 16
   {
     uint32_t mb = 10;
     while (mb < 24 && ((sc->total_micro + (((int64_t)1 << mb) - 1)) >> mb) > WC_MAX_BUCKETS) mb++;
     const int64_t nb = (sc->total_micro + (((int64_t)1 << mb) - 1)) >> mb;
-    const size_t smem = wc_smem_bytes((uint32_t)std::max<int64_t>(nb, 1), (size_t)2 * std::max(n_chrom, 1) + 2);
-    if (mb <= SB_SUB_BITS + 4 && nb >= 256 && params->win_step < ((int64_t)1 << 31) && smem <= ctx->smem_optin && !getenv("GTB_SCAN_DIRECT")) {
+    const size_t tab_entries = (size_t)2 * std::max(n_chrom, 1) + 2;
+    const size_t smem = wc_smem_bytes((uint32_t)std::max<int64_t>(nb, 1), tab_entries);
+    const uint32_t max_counters = (uint32_t)(((ctx->smem_optin - 32 * 4 - 1024) / 2) & ~(size_t)7);     // 16-bit counters per CTA
+    const uint32_t n_sub = (uint32_t)((((uint64_t)1 << mb) + max_counters - 1) / max_counters);
+    if (n_sub <= 16 && nb >= 256 && params->win_step < ((int64_t)1 << 31) && smem <= ctx->smem_optin && !getenv("GTB_SCAN_DIRECT")) {
       sc->bucket_ok = true; sc->mb = mb; sc->n_buckets = (uint32_t)nb;
-      sc->n_sub = mb > SB_SUB_BITS ? 1u << (mb - SB_SUB_BITS) : 1u;
-      sc->sb_words = (mb > SB_SUB_BITS ? 1u << SB_SUB_BITS : 1u << mb) / 2;
+      sc->n_sub = n_sub;
+      sc->sb_words = (uint32_t)((((((uint64_t)1 << mb) + n_sub - 1) / n_sub + 7) & ~(uint64_t)7) / 2);
       const uint64_t d = (uint64_t)params->win_step;
       int l = 0;
       while (((uint64_t)1 << l) < d) l++;
       sc->shift = 31 + l;
       sc->magic = (uint32_t)((((uint64_t)1 << sc->shift) + d - 1) / d);      // ceil(2^(31 + l) / d): exact quotients for dividends < 2^31
-      std::vector<uint4> tab((size_t)2 * std::max(n_chrom, 1) + 2, make_uint4(0, 0, 0, 0));
+      std::vector<uint4> tab(tab_entries, make_uint4(0, 0, 0, 0));
       for (int32_t c = 0; c < n_chrom; c++) {
         const int32_t s0 = slot_of_chrom[c];
         if (s0 < 0) continue;
@@ -441,7 +516,12 @@ extern "C" int gtb_scan_create(gtb_ctx *ctx, int32_t n_chrom, const int64_t *bou
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_slot_strand, slot_strand);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_hist_off, hist_off);
   if (rc == GTB_OK) rc = upload_vec(ctx, sc->d_win_off, win_off);
-  if (rc == GTB_OK) rc = sc->d_hist.reserve(ctx, (size_t)std::max<int64_t>(sc->total_micro, 1) + 2);   // + 2: the bucketed flush moves entries in pairs
+  if (rc == GTB_OK) rc = sc->d_lo.reserve(ctx, (size_t)std::max<int64_t>(sc->total_micro, 1) + 2);   // + 2: the bucketed flush moves entries in pairs
+  if (rc == GTB_OK) rc = sc->d_hi.reserve(ctx, (size_t)std::max<int64_t>(sc->total_micro, 1) + 2);
+  if (rc == GTB_OK) rc = sc->d_flags.reserve(ctx, 2);
+  if (rc == GTB_OK && cudaHostAlloc((void **)&sc->h_flags, 4 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) rc = GTB_ERR_CUDA;
+  if (rc == GTB_OK && cudaMemsetAsync(sc->d_hi.p, 0, sizeof(uint32_t) * ((size_t)std::max<int64_t>(sc->total_micro, 1) + 2), ctx->stream) != cudaSuccess) rc = GTB_ERR_CUDA;
+  if (rc == GTB_OK && cudaMemsetAsync(sc->d_flags.p, 0, 2 * sizeof(uint32_t), ctx->stream) != cudaSuccess) rc = GTB_ERR_CUDA;
   if (rc == GTB_OK) rc = gtb_scan_reset(sc);
   if (rc == GTB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GTB_ERR_CUDA;
   for (auto &st : sc->stages) {
@@ -458,8 +538,11 @@ extern "C" void gtb_scan_destroy(gtb_scan *sc) {
   cudaSetDevice(sc->ctx->device);
   gtb_ctx_synchronize(sc->ctx);
   sc->d_slot_of_chrom.release(); sc->d_spurious.release(); sc->d_slot_chrom.release(); sc->d_slot_strand.release();
-  sc->d_hist_off.release(); sc->d_win_off.release(); sc->d_hist.release(); sc->d_tile_counts.release(); sc->d_scan_scratch.release();
+  sc->d_hist_off.release(); sc->d_win_off.release(); sc->d_lo.release(); sc->d_hi.release(); sc->d_flags.release();
+  sc->d_tile_counts.release(); sc->d_scan_scratch.release();
+  sc->c_win.release(); sc->c_val.release(); sc->c_val_hi.release(); sc->c_slot16.release(); sc->c_slot32.release();
   sc->o_chrom.release(); sc->o_strand.release(); sc->o_win.release(); sc->o_value.release();
+  if (sc->h_flags) cudaFreeHost(sc->h_flags);
   sc->d_front_tab.release(); sc->wc.release();
   for (auto &st : sc->stages) {
     st.chrom.release(); st.start.release(); st.stop.release(); st.weight.release(); st.strand.release(); st.off.release();
@@ -478,7 +561,7 @@ static int scan_accumulate_device(gtb_scan *sc, const ReadView &q) {
     unsigned gridw = 0;
     if (sc->wc.plan(ctx, q.n_intervals, sc->n_buckets, &wv, &gridw) == GTB_OK) {
       const ScanFront front{sc->d_front_tab.p, (uint32_t)sc->n_chrom, sc->magic, sc->shift, sc->mb, sc->prm.op == 'c' ? 1 : 0,
-                            sc->prm.ignore_strand ? 1 : 0, sc->d_hist.p};
+                            sc->prm.ignore_strand ? 1 : 0, sc->table()};
       const WcQueries wq{q.n_intervals, q.chrom, q.start, q.stop, q.strand, 0};
       GTB_TRY(wc_partition_launch(ctx, "scan_partition", wq, front, wv, gridw, wc_smem_bytes(sc->n_buckets, (size_t)2 * std::max(sc->n_chrom, 1) + 2)));
       const size_t smem = ((size_t)sc->sb_words + 32) * 4;
@@ -487,7 +570,7 @@ static int scan_accumulate_device(gtb_scan *sc, const ReadView &q) {
   do {                                                                                                                               \
     GTB_CUDA_OK(ctx, cudaFuncSetAttribute(scan_bucket_hist_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     GTB_LAUNCH(ctx, "scan_bucket_hist", (scan_bucket_hist_kernel<T, U>), sc->n_buckets * sc->n_sub, T, smem, wv, sc->mb, sc->n_sub,  \
-               sc->sb_words, sc->d_hist.p);                                                                                          \
+               sc->sb_words, sc->table());                                                                                           \
   } while (0)
       if (variant == 1) GTB_SB_LAUNCH(1024, 2);
       else if (variant == 2) GTB_SB_LAUNCH(512, 8);
@@ -498,7 +581,7 @@ static int scan_accumulate_device(gtb_scan *sc, const ReadView &q) {
   }
   const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 8);
   GTB_LAUNCH(ctx, "scan_histogram", scan_histogram_kernel, grid, 256, 0, q, sc->n_chrom, sc->d_slot_of_chrom.p, sc->d_hist_off.p,
-             (long long)sc->prm.win_step, (int)sc->prm.op, (int)sc->prm.ignore_strand, sc->d_hist.p);
+             (long long)sc->prm.win_step, (int)sc->prm.op, (int)sc->prm.ignore_strand, sc->table());
   return gtb_check_launch(ctx);
 }
 
@@ -573,20 +656,25 @@ extern "C" int gtb_scan_finish(gtb_scan *sc, int64_t *n_windows) {
   SlotTable t{sc->n_slots, sc->d_hist_off.p, sc->d_win_off.p, sc->d_spurious.p, sc->d_slot_chrom.p, sc->d_slot_strand.p};
   const int64_t n_tiles = (sc->total_windows + WIN_TILE - 1) / WIN_TILE;
   GTB_TRY(sc->d_tile_counts.reserve(ctx, (size_t)n_tiles));
-  GTB_LAUNCH(ctx, "scan_windows_count", scan_windows_kernel<0>, (unsigned)n_tiles, WIN_THREADS, 0, t, sc->d_hist.p, sc->total_windows,
-             sc->combine, (long long)sc->prm.min_reads, sc->d_tile_counts.p, nullptr, nullptr, nullptr, nullptr);
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(sc->d_flags.p + 1, 0, sizeof(uint32_t), ctx->stream));      // "wide values" is about this pass
+  GTB_LAUNCH(ctx, "scan_windows_count", scan_windows_kernel<0>, (unsigned)n_tiles, WIN_THREADS, 0, t, sc->table(), sc->total_windows,
+             sc->combine, (long long)sc->prm.min_reads, sc->d_tile_counts.p, WindowsOut{nullptr, nullptr, nullptr, nullptr, nullptr});
   GTB_TRY(gtb_check_launch(ctx));
   GTB_TRY(gtb_inclusive_scan_u64(ctx, sc->d_tile_counts.p, n_tiles, sc->d_scan_scratch));
-  ull total = 0;
-  GTB_CUDA_OK(ctx, cudaMemcpyAsync(&total, sc->d_tile_counts.p + (n_tiles - 1), sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(sc->h_flags + 2, sc->d_tile_counts.p + (n_tiles - 1), sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(sc->h_flags, sc->d_flags.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ull total;
+  memcpy(&total, sc->h_flags + 2, sizeof total);
   sc->n_out = (int64_t)total;
+  sc->wide_values = sc->h_flags[1] != 0u;
   *n_windows = sc->n_out;
   if (sc->n_out == 0) return GTB_OK;
-  GTB_TRY(sc->o_chrom.reserve(ctx, (size_t)sc->n_out)); GTB_TRY(sc->o_strand.reserve(ctx, (size_t)sc->n_out));
-  GTB_TRY(sc->o_win.reserve(ctx, (size_t)sc->n_out)); GTB_TRY(sc->o_value.reserve(ctx, (size_t)sc->n_out));
-  GTB_LAUNCH(ctx, "scan_windows_emit", scan_windows_kernel<1>, (unsigned)n_tiles, WIN_THREADS, 0, t, sc->d_hist.p, sc->total_windows,
-             sc->combine, (long long)sc->prm.min_reads, sc->d_tile_counts.p, sc->o_chrom.p, sc->o_strand.p, sc->o_win.p, sc->o_value.p);
+  GTB_TRY(sc->c_win.reserve(ctx, (size_t)sc->n_out)); GTB_TRY(sc->c_val.reserve(ctx, (size_t)sc->n_out));
+  if (sc->wide_values) GTB_TRY(sc->c_val_hi.reserve(ctx, (size_t)sc->n_out));
+  if (sc->n_slots <= 65536) GTB_TRY(sc->c_slot16.reserve(ctx, (size_t)sc->n_out)); else GTB_TRY(sc->c_slot32.reserve(ctx, (size_t)sc->n_out));
+  GTB_LAUNCH(ctx, "scan_windows_emit", scan_windows_kernel<1>, (unsigned)n_tiles, WIN_THREADS, 0, t, sc->table(), sc->total_windows,
+             sc->combine, (long long)sc->prm.min_reads, sc->d_tile_counts.p, sc->windows());
   GTB_TRY(gtb_check_launch(ctx));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return GTB_OK;
@@ -597,10 +685,24 @@ extern "C" int gtb_scan_fetch(gtb_scan *sc, int64_t first, int64_t count, int32_
   gtb_ctx *ctx = sc->ctx;
   if (count == 0) return GTB_OK;
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-  if (chrom) GTB_CUDA_OK(ctx, cudaMemcpyAsync(chrom, sc->o_chrom.p + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (strand) GTB_CUDA_OK(ctx, cudaMemcpyAsync(strand, sc->o_strand.p + first, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-  if (win) GTB_CUDA_OK(ctx, cudaMemcpyAsync(win, sc->o_win.p + first, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (value) GTB_CUDA_OK(ctx, cudaMemcpyAsync(value, sc->o_value.p + first, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SlotTable t{sc->n_slots, sc->d_hist_off.p, sc->d_win_off.p, sc->d_spurious.p, sc->d_slot_chrom.p, sc->d_slot_strand.p};
+  // the windows are widened piece by piece into a bounded device staging area and copied out from there
+  const int64_t PIECE = (int64_t)4 << 20;
+  const size_t np = (size_t)std::min(count, PIECE);
+  if (chrom) GTB_TRY(sc->o_chrom.reserve(ctx, np));
+  if (strand) GTB_TRY(sc->o_strand.reserve(ctx, np));
+  if (win) GTB_TRY(sc->o_win.reserve(ctx, np));
+  if (value) GTB_TRY(sc->o_value.reserve(ctx, np));
+  for (int64_t p0 = 0; p0 < count; p0 += PIECE) {
+    const int64_t n = std::min(PIECE, count - p0);
+    GTB_LAUNCH(ctx, "scan_expand", scan_expand_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, t, sc->windows(),
+               first + p0, n, chrom ? sc->o_chrom.p : nullptr, strand ? sc->o_strand.p : nullptr, win ? sc->o_win.p : nullptr, value ? sc->o_value.p : nullptr);
+    GTB_TRY(gtb_check_launch(ctx));
+    if (chrom) GTB_CUDA_OK(ctx, cudaMemcpyAsync(chrom + p0, sc->o_chrom.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (strand) GTB_CUDA_OK(ctx, cudaMemcpyAsync(strand + p0, sc->o_strand.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (win) GTB_CUDA_OK(ctx, cudaMemcpyAsync(win + p0, sc->o_win.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (value) GTB_CUDA_OK(ctx, cudaMemcpyAsync(value + p0, sc->o_value.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return GTB_OK;
 }

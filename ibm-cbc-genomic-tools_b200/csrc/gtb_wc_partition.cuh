@@ -34,7 +34,8 @@ constexpr int WC_BLOCK = 8;                               // lines per block: th
 constexpr int WC_BLOCK_ELEMS = WC_LINE * WC_BLOCK;
 constexpr int WC_CAP = 32;                                // ring capacity per bucket
 constexpr int WC_STRIDE = 36;                             // words between rings: 144 B keeps 16-byte alignment, spreads owners over all banks
-constexpr int WC_MAX_BUCKETS = 512;                       // one owner thread per bucket
+constexpr int WC_MAX_BUCKETS = WC_THREADS;                // one owner thread per bucket
+constexpr int WC_CTAS_PER_SM = WC_THREADS > 512 ? 1 : 2;  // 1 024 threads per SM either way
 #ifndef GTB_WC_STAGES
 #define GTB_WC_STAGES 1
 #endif
@@ -110,7 +111,7 @@ inline size_t wc_smem_bytes(uint32_t n_buckets, size_t table_entries) {
 }
 
 template <class Front>
-__global__ void __launch_bounds__(WC_THREADS, 2) wc_partition_kernel(const __grid_constant__ WcQueries q, const __grid_constant__ Front front,
+__global__ void __launch_bounds__(WC_THREADS, WC_CTAS_PER_SM) wc_partition_kernel(const __grid_constant__ WcQueries q, const __grid_constant__ Front front,
                                                                      const __grid_constant__ WcView wv) {
   extern __shared__ __align__(128) uint32_t smem[];
   // raw tiles: WC_STAGES buffers of chrom | start | stop (WC_TILE ints each) | strand (WC_TILE bytes), filled by TMA bulk copies
@@ -366,7 +367,7 @@ struct WcBuffers {
   // 25-bit slot ids of sorted_lines can name.
   int plan(gtb_ctx *ctx, int64_t n, uint32_t nb, WcView *wv, unsigned *grid) {
     const int64_t tiles = (n + WC_TILE - 1) / WC_TILE;
-    const unsigned gridw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 2, tiles));
+    const unsigned gridw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * WC_CTAS_PER_SM, tiles));
     const uint64_t tiles_cta = ((uint64_t)tiles + gridw - 1) / gridw;
     const uint64_t lines_per_cta = tiles_cta * (WC_TILE / WC_BLOCK_ELEMS) + nb + 1;      // full blocks + one open block per bucket
     const uint64_t total_slots = lines_per_cta * gridw;

@@ -279,3 +279,35 @@ def test_scale_limits_weights(ctx, oracle, gtb):
     rc, want, _ = oracle.coverage(reads, regions, 0, qw=w)
     assert rc == 0 and want[0] > 2 ** 40
     assert np.array_equal(ctx.overlap_coverage(reads, regions, 0, qweight=w), want)
+
+
+def test_scale_limits_scan_values_past_2_32(ctx, oracle, gtb):
+    """Window counts whose micro-windows and window values pass 2^32 (weighted reads piled onto a few micro-windows, added in
+    two batches with a reset in between): the table's carry plane and the upper halves of the emitted values come into use,
+    and go out of use again after the reset."""
+    rng = np.random.default_rng(9)
+    n = 4000
+    lens = np.array([support.HG19["chr21"], support.HG19["chr22"]], dtype=np.int64)
+    reads = {"chrom": rng.integers(0, 2, n).astype(np.int32), "start": rng.integers(1_000_000, 1_000_400, n).astype(np.int32),
+             "strand": np.where(rng.integers(0, 2, n) == 1, 43, 45).astype(np.int8)}
+    reads["stop"] = (reads["start"] + 49).astype(np.int32)
+    w = rng.integers(2_000_000_000, 2_147_483_647, n).astype(np.int32)
+    n_want, want = oracle.scan_counts(reads, lens, 50, 200, "1", False, 1, weight=w)
+    assert want["value"].max() > 2 ** 33
+    sc = gtb.Scan(ctx, lens, 50, 200, "1", False, 1)
+    sc.add_host({k: v[:n // 2] for k, v in reads.items()}, weight=w[:n // 2])
+    sc.add_host({k: v[n // 2:] for k, v in reads.items()}, weight=w[n // 2:])
+    assert sc.finish() == n_want
+    got = sc.fetch(0, n_want)
+    for k in ("chrom", "strand", "win", "value"):
+        assert np.array_equal(got[k], want[k]), k
+    # after a reset the same object counts small values again (the carry plane is cleared, the values are narrow)
+    sc.reset()
+    plain = support.synth_reads(500_000, seed=44, chrom_lens=lens)
+    n_want, want = oracle.scan_counts(plain, lens, 50, 200, "1", False, 1)
+    sc.add_host(plain)
+    assert sc.finish() == n_want
+    got = sc.fetch(0, n_want)
+    for k in ("chrom", "strand", "win", "value"):
+        assert np.array_equal(got[k], want[k]), k
+    sc.close()
