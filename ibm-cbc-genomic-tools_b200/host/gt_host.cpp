@@ -116,6 +116,145 @@ void CmdLine::OperationUsage() {
 // ---------------------------------------------------------------------------------------------
 static const size_t kBlockBytes = 32u << 20;
 
+// BAM (core.cpp:371-430, FileBufferBAM): the reference hands the header text out line by line and then every alignment as the
+// SAM line samtools' bam_format1_core writes for it (samtools/bam.c:256-340), and parses those lines as SAM.  Same here: the
+// producer thread inflates the BGZF stream (a series of gzip members: zlib's gzread walks them), decodes the records and fills
+// the line blocks with that text.  A truncated file ends the input where the last complete record ends, as samread() < 0 does.
+struct LineReader::BamDecoder {
+  gzFile gz;
+  std::vector<std::string> ref;                                         // reference sequence names
+  std::string out;                                                      // text not handed out yet
+  size_t out_pos = 0;
+  std::vector<unsigned char> rec;
+  bool eof = false;
+  explicit BamDecoder(gzFile g) : gz(g) {}
+  bool ReadExact(void *dst, size_t n) {
+    size_t have = 0;
+    while (have < n) {
+      const int got = gzread(gz, (char *)dst + have, (unsigned)std::min<size_t>(n - have, 1u << 30));
+      if (got <= 0) return false;
+      have += (size_t)got;
+    }
+    return true;
+  }
+  static int32_t I32(const unsigned char *p) { return (int32_t)((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24); }
+  static uint32_t U16(const unsigned char *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+  void PutInt(long long v) { char b[24]; const int n = snprintf(b, sizeof b, "%lld", v); out.append(b, (size_t)n); }
+  // after the magic: l_text, text, n_ref, (l_name, name, l_ref) x n_ref
+  void ReadHeader() {
+    unsigned char w[4];
+    if (!ReadExact(w, 4)) { eof = true; return; }
+    const int32_t l_text = I32(w);
+    std::string text((size_t)std::max(l_text, 0), '\0');
+    if (l_text > 0 && !ReadExact(&text[0], (size_t)l_text)) { eof = true; return; }
+    text.resize(strlen(text.c_str()));                                  // header->text is a C string to the reference
+    // the reference walks the text with GetNextToken(.., '\n') while anything is left (core.cpp:421-425, :613-625): blanks in
+    // front of a line are skipped, the last line needs no newline
+    for (const char *p = text.c_str(); *p;) {
+      while (*p == ' ') p++;
+      const size_t k = strcspn(p, "\n");
+      out.append(p, k);
+      out.push_back('\n');
+      p += k;
+      if (*p) p++;
+    }
+    if (!ReadExact(w, 4)) { eof = true; return; }
+    const int32_t n_ref = I32(w);
+    for (int32_t i = 0; i < n_ref; i++) {
+      if (!ReadExact(w, 4)) { eof = true; return; }
+      const int32_t l_name = I32(w);
+      std::string name((size_t)std::max(l_name, 0), '\0');
+      if (l_name > 0 && !ReadExact(&name[0], (size_t)l_name)) { eof = true; return; }
+      name.resize(strlen(name.c_str()));
+      if (!ReadExact(w, 4)) { eof = true; return; }                       // l_ref
+      ref.push_back(name);
+    }
+  }
+  // one alignment -> one SAM line (bam_format1_core with decimal flags)
+  bool NextRecord() {
+    unsigned char w[4];
+    if (!ReadExact(w, 4)) return false;
+    const int32_t block = I32(w);
+    if (block < 32) return false;
+    rec.resize((size_t)block);
+    if (!ReadExact(rec.data(), (size_t)block)) return false;
+    const unsigned char *r = rec.data();
+    const int32_t tid = I32(r), pos = I32(r + 4);
+    const uint32_t l_qname = r[8], mapq = r[9], n_cigar = U16(r + 12), flag = U16(r + 14);
+    const int32_t l_seq = I32(r + 16), mtid = I32(r + 20), mpos = I32(r + 24), isize = I32(r + 28);
+    const size_t fixed = 32 + (size_t)l_qname + 4 * (size_t)n_cigar + ((size_t)std::max(l_seq, 0) + 1) / 2 + (size_t)std::max(l_seq, 0);
+    if (l_seq < 0 || l_qname == 0 || fixed > (size_t)block) return false;
+    const unsigned char *qname = r + 32, *cigar = qname + l_qname, *seq = cigar + 4 * n_cigar, *qual = seq + (l_seq + 1) / 2, *aux = qual + l_seq;
+    const unsigned char *end = r + block;
+    auto name_of = [&](int32_t id) { if (id >= 0 && (size_t)id < ref.size()) out += ref[(size_t)id]; else PutInt(id); };
+    out.append((const char *)qname, l_qname - 1); out.push_back('\t');
+    PutInt(flag); out.push_back('\t');
+    if (tid < 0) out += "*\t"; else { name_of(tid); out.push_back('\t'); }
+    PutInt((long long)pos + 1); out.push_back('\t'); PutInt(mapq); out.push_back('\t');
+    if (n_cigar == 0) out.push_back('*');
+    else for (uint32_t i = 0; i < n_cigar; i++) {
+      const uint32_t c = (uint32_t)I32(cigar + 4 * i);
+      PutInt(c >> 4); out.push_back("MIDNSHP=XB??????"[c & 15u]);
+    }
+    out.push_back('\t');
+    if (mtid < 0) out += "*\t"; else if (mtid == tid) out += "=\t"; else { name_of(mtid); out.push_back('\t'); }
+    PutInt((long long)mpos + 1); out.push_back('\t'); PutInt(isize); out.push_back('\t');
+    if (l_seq) {
+      for (int32_t i = 0; i < l_seq; i++) out.push_back("=ACMGRSVTWYHKDBN"[(seq[i >> 1] >> ((~i & 1) << 2)) & 15]);
+      out.push_back('\t');
+      if (qual[0] == 0xff) out.push_back('*'); else for (int32_t i = 0; i < l_seq; i++) out.push_back((char)(qual[i] + 33));
+    } else out += "*\t*";
+    char tmp[64];
+    for (const unsigned char *s = aux; s + 3 <= end;) {
+      out.push_back('\t'); out.append((const char *)s, 2); out.push_back(':');
+      const unsigned char type = s[2];
+      s += 3;
+      auto fits = [&](size_t n) { return (size_t)(end - s) >= n; };
+      if (type == 'A' && fits(1)) { out += "A:"; out.push_back((char)*s); s += 1; }
+      else if (type == 'C' && fits(1)) { out += "i:"; PutInt(*s); s += 1; }
+      else if (type == 'c' && fits(1)) { out += "i:"; PutInt((int8_t)*s); s += 1; }
+      else if (type == 'S' && fits(2)) { out += "i:"; PutInt(U16(s)); s += 2; }
+      else if (type == 's' && fits(2)) { out += "i:"; PutInt((int16_t)U16(s)); s += 2; }
+      else if (type == 'I' && fits(4)) { out += "i:"; PutInt((uint32_t)I32(s)); s += 4; }
+      else if (type == 'i' && fits(4)) { out += "i:"; PutInt(I32(s)); s += 4; }
+      else if (type == 'f' && fits(4)) { float f; memcpy(&f, s, 4); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "f:%g", f)); s += 4; }
+      else if (type == 'd' && fits(8)) { double d; memcpy(&d, s, 8); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "d:%lg", d)); s += 8; }
+      else if (type == 'Z' || type == 'H') { out.push_back((char)type); out.push_back(':'); while (s < end && *s) out.push_back((char)*s++); if (s < end) s++; }
+      else if (type == 'B' && fits(5)) {
+        const unsigned char sub = *s++;
+        const int32_t n = I32(s);
+        s += 4;
+        out += "B:"; out.push_back((char)sub);
+        for (int32_t i = 0; i < n && s < end; i++) {
+          out.push_back(',');
+          if (sub == 'c' && fits(1)) { PutInt((int8_t)*s); s += 1; }
+          else if (sub == 'C' && fits(1)) { PutInt(*s); s += 1; }
+          else if (sub == 's' && fits(2)) { PutInt((int16_t)U16(s)); s += 2; }
+          else if (sub == 'S' && fits(2)) { PutInt(U16(s)); s += 2; }
+          else if (sub == 'i' && fits(4)) { PutInt(I32(s)); s += 4; }
+          else if (sub == 'I' && fits(4)) { PutInt((uint32_t)I32(s)); s += 4; }
+          else if (sub == 'f' && fits(4)) { float f; memcpy(&f, s, 4); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "%g", f)); s += 4; }
+          else { s = end; }
+        }
+      }
+      else break;                                                       // (a type samtools does not know ends the line's tags)
+    }
+    out.push_back('\n');
+    return true;
+  }
+  long Fill(char *dst, size_t want) {
+    while (!eof && out.size() - out_pos < want) {
+      if (out_pos > (1u << 20)) { out.erase(0, out_pos); out_pos = 0; }
+      if (!NextRecord()) eof = true;
+    }
+    const size_t n = std::min(want, out.size() - out_pos);
+    memcpy(dst, out.data() + out_pos, n);
+    out_pos += n;
+    if (out_pos == out.size()) { out.clear(); out_pos = 0; }
+    return (long)n;
+  }
+};
+
 LineReader::LineReader(const char *path) {
   if (path == nullptr) fd_ = 0;
   else {
@@ -127,6 +266,13 @@ LineReader::LineReader(const char *path) {
       gz_ = gzdopen(fd_, "rb");
       if (gz_ == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
       gzbuffer(gz_, 1 << 20);
+      const int got4 = gzread(gz_, prefix_, 4);                          // BAM or gzipped text (GetFileType, core.cpp:1764-1772)
+      prefix_len_ = got4 > 0 ? got4 : 0;
+      if (prefix_len_ == 4 && memcmp(prefix_, "BAM\1", 4) == 0) {
+        prefix_len_ = 0;
+        bam_ = new BamDecoder(gz_);
+        bam_->ReadHeader();
+      }
     }
   }
   struct stat st;
@@ -144,6 +290,7 @@ LineReader::~LineReader() {
   }
   cv_.notify_all();
   producer_.join();
+  delete bam_;
   if (gz_) gzclose(gz_);
   else if (fd_ > 0) close(fd_);
   for (auto &b : block_) free(b.data);
@@ -162,6 +309,13 @@ static size_t PreadAll(int fd, char *dst, size_t want, off_t offset) {
 }
 
 long LineReader::ReadSome(char *dst, size_t want) {
+  if (bam_) return bam_->Fill(dst, want);
+  if (prefix_pos_ < prefix_len_) {                                       // the bytes the constructor looked at
+    const size_t n = std::min(want, (size_t)(prefix_len_ - prefix_pos_));
+    memcpy(dst, prefix_ + prefix_pos_, n);
+    prefix_pos_ += (int)n;
+    return (long)n;
+  }
   if (gz_) return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
   if (regular_) {
     // a regular file: one read() copies out of the page cache at a few GB/s, which the parsing threads outrun -- large requests
@@ -447,7 +601,6 @@ RegionReader::RegionReader(const char *path, ChromTable *chroms, bool keep_label
            : format_ == "SEQ" ? F_SEQ : format_ == "EMPTY" ? F_EMPTY : F_NONE;
   };
   if (next == nullptr) { format_ = "EMPTY"; settle(); return; }
-  if (strncmp(next, "BAM\x01", 4) == 0) die("BAM input is not supported by this build (SAM text is)!\n");   // GetFileType, core.cpp:1757-1775
   auto skip = [&] { header_.append(next); header_.push_back('\n'); next = reader_.Next(); };
   if (is_track(next)) { while (next && is_track(next)) skip(); }
   else if (next[0] == '@') { format_ = "SAM"; while (next && next[0] == '@') skip(); }

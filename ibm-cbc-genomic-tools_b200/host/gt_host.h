@@ -88,6 +88,10 @@ class LineReader {
   bool Acquire();                                     // make the next block current; false at end
   gzFile gz_ = nullptr;
   int fd_ = -1;
+  struct BamDecoder;                                  // BAM input: records re-spelt as SAM text lines, as the reference's FileBufferBAM does
+  BamDecoder *bam_ = nullptr;
+  char prefix_[4];                                    // the first inflated bytes of a gzip file (read to tell BAM from text)
+  int prefix_len_ = 0, prefix_pos_ = 0;
   bool regular_ = false;                              // a regular file, read with pread at offset_ (by several threads when the request is large)
   off_t offset_ = 0;
   Block block_[kBlocks];

@@ -206,3 +206,47 @@ class Oracle:
         n2 = self.lib.orc_scan_counts(*args, n, _ptr(oc), _ptr(os_), _ptr(ow), _ptr(ov))
         assert n2 == n
         return int(n), {"chrom": oc, "strand": os_, "win": ow, "value": ov}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# A minimal BAM writer (BGZF blocks + BAM records) for the input tests: the reference reads BAM through its vendored samtools,
+# the drivers here through host/gt_host.cpp's decoder.
+# ---------------------------------------------------------------------------------------------------------------------------------
+def write_bam(path, header_text, refs, records, block_bytes=4000):
+    """refs: [(name, length)]; records: dicts with qname, flag, tid, pos (0-based), mapq, cigar [(len, op char)], mtid, mpos,
+    isize, seq (str or ''), qual (bytes of phred values or None), aux (already encoded bytes)."""
+    import struct
+    import zlib
+    raw = bytearray(b"BAM\x01")
+    text = header_text.encode()
+    raw += struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for name, length in refs:
+        nm = name.encode() + b"\x00"
+        raw += struct.pack("<i", len(nm)) + nm + struct.pack("<i", length)
+    ops = "MIDNSHP=X"
+    codes = "=ACMGRSVTWYHKDBN"
+    for r in records:
+        qn = r["qname"].encode() + b"\x00"
+        cig = b"".join(struct.pack("<I", (n << 4) | ops.index(op)) for n, op in r["cigar"])
+        seq = r.get("seq", "")
+        packed = bytearray((len(seq) + 1) // 2)
+        for i, ch in enumerate(seq):
+            packed[i >> 1] |= codes.index(ch) << (4 if i % 2 == 0 else 0)
+        qual = r.get("qual")
+        qual = bytes([0xFF] * len(seq)) if qual is None else bytes(qual)
+        aux = r.get("aux", b"")
+        core = struct.pack("<iiBBHHHiiii", r["tid"], r["pos"], len(qn), r.get("mapq", 0), 4680, len(r["cigar"]), r["flag"], len(seq),
+                           r.get("mtid", -1), r.get("mpos", -1), r.get("isize", 0))
+        body = core + qn + cig + bytes(packed) + qual + aux
+        raw += struct.pack("<i", len(body)) + body
+
+    def bgzf_block(data):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = c.compress(data) + c.flush()
+        bsize = len(comp) + 25
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + comp +
+                struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+    with open(path, "wb") as f:
+        for lo in range(0, len(raw), block_bytes):
+            f.write(bgzf_block(bytes(raw[lo:lo + block_bytes])))
+        f.write(bgzf_block(b""))                                        # the end-of-file marker block

@@ -351,6 +351,26 @@ def test_sam_variants(samfiles, scanfiles):
     assert got[0] == want[0] != 0 and got[1] == want[1] and got[2] == want[2]
 
 
+def test_bam_queries(samfiles, scanfiles):
+    """BAM input (FileBufferBAM, core.cpp:371-430): the SAM fixture's alignments written as BAM (BGZF blocks of 4 000 bytes, so
+    records straddle blocks), through count / coverage / subset / window counts"""
+    import re
+    d = samfiles
+    refs = [(n, 5000) for n in NAMES[:5]]
+    recs = []
+    for line in (d / "q.sam").read_text().splitlines():
+        if line.startswith("@"):
+            continue
+        f = line.split("\t")
+        cigar = [] if f[5] == "*" else [(int(n), op) for n, op in re.findall(r"(\d+)([MIDNSHP=X])", f[5])]
+        recs.append({"qname": f[0], "flag": int(f[1]), "tid": -1 if f[2] == "*" else NAMES.index(f[2]), "pos": int(f[3]) - 1, "mapq": int(f[4]), "cigar": cigar,
+                     "mtid": -1, "mpos": -1, "isize": 0, "seq": "" if f[9] == "*" else f[9], "qual": None, "aux": b"NMC\x01" if len(f) > 11 else b""})
+    support.write_bam(d / "q.bam", "@HD\tVN:1.0\tSO:unsorted\n@SQ\tSN:chr1\tLN:5000\n", refs, recs)
+    for args in (["count"], ["coverage", "-i"], ["density", "-gaps"], ["subset"], ["subset", "-inv"]):
+        assert_same("genomic_overlaps", args + [d / "idx.bed", d / "q.bam"], nonempty=True)
+    assert_same("genomic_scans", ["counts", "-g", scanfiles / "genome.bed", "-w", "200", "-d", "50", "-min", "2", d / "q.bam"], nonempty=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # the per-query operations: subset / overlap (genomic_overlaps.cpp:782-800, :706-739), and genomic_regions gsort
 # ------------------------------------------------------------------------------------------------

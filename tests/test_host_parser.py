@@ -347,3 +347,53 @@ def test_print_region_matches_reference_print(tmp_path):
         assert rc == 0 and len(want) > 0, (name, err)
         rc2, got, err2 = dump(tmp_path / name, {}, args=("-p",))
         assert rc2 == 0 and got == want, (name, got[:300], want[:300])
+
+
+# ------------------------------------------------------------------------------------------------
+# BAM input (FileBufferBAM, core.cpp:371-430): records re-spelt as SAM lines, then the SAM reader
+# ------------------------------------------------------------------------------------------------
+def _bam_case(tmp_path, with_header=True, n=400, seed=11):
+    import struct
+    rng = np.random.default_rng(seed)
+    refs = [("chr1", 50_000), ("chr2", 40_000), ("chrUn_gl000220", 9_000)]
+    recs = []
+    for k in range(n):
+        ln = int(rng.integers(1, 80))
+        spliced = k % 5 == 0 and ln > 10
+        cigar = [(ln // 2, "M"), (int(rng.integers(50, 900)), "N"), (ln - ln // 2, "M")] if spliced else ([(2, "S"), (ln, "M")] if k % 11 == 3 else [(ln, "M")])
+        seq_len = sum(c for c, op in cigar if op in "MIS=X")
+        aux = b""
+        if k % 3 == 0:
+            aux += b"NMC" + bytes([k % 7]) + b"XSA+" + b"MDZ" + b"%dA3" % (k % 9) + b"\x00"
+        if k % 10 == 1:
+            aux += b"ASi" + struct.pack("<i", -k) + b"XFf" + struct.pack("<f", 0.25 * k) + b"ZBBs" + struct.pack("<ihh", 2, -3, 7) + b"UQS" + struct.pack("<H", 40000)
+        unmapped = k % 37 == 36
+        recs.append({"qname": "read%d" % k, "flag": int(rng.integers(0, 2048)) & ~4 | (4 if unmapped else 0), "tid": -1 if unmapped else int(rng.integers(0, 3)),
+                     "pos": -1 if unmapped else int(rng.integers(0, 8000)), "mapq": int(rng.integers(0, 61)),
+                     "cigar": [] if (unmapped or k % 13 == 5) else cigar, "mtid": [-1, 0, 1][k % 3], "mpos": int(rng.integers(0, 8000)), "isize": int(rng.integers(-500, 500)),
+                     "seq": "" if k % 17 == 9 else "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, seq_len)),
+                     "qual": None if k % 4 == 0 else [int(x) for x in rng.integers(0, 42, seq_len)], "aux": aux})
+        if recs[-1]["seq"] == "":
+            recs[-1]["qual"] = None
+    header = "@HD\tVN:1.0\tSO:unsorted\n@SQ\tSN:chr1\tLN:50000\n@SQ\tSN:chr2\tLN:40000\n@SQ\tSN:chrUn_gl000220\tLN:9000\n@PG\tID:x" if with_header else ""
+    path = tmp_path / ("h.bam" if with_header else "n.bam")
+    support.write_bam(path, header, refs, recs)
+    return path
+
+
+@pytest.mark.parametrize("with_header", [True, False])
+def test_bam_input_matches_reference_reader(tmp_path, with_header):
+    """regions of a BAM file (spliced reads, soft clips, '*' CIGARs, unmapped reads, every aux type) and every line as Print()
+    writes it back, against the reference built with its vendored samtools"""
+    if not support.have_ref():
+        pytest.skip("reference binaries not built (oracle/_ref)")
+    path = _bam_case(tmp_path, with_header)
+    rc, want, err = ref_reg(path)
+    for env in THREADINGS:
+        rc2, got, err2 = dump(path, env)
+        assert (rc2, strip_extras(got)) == (rc, want), (got[:400], want[:400], err, err2)
+        assert rc != 0 or len(want) > 100
+    (tmp_path / "far.bed").write_text("chrFAR\t1\t2\tx\t0\t+\n")
+    rc, want, err = support.run_ref("genomic_overlaps", ["subset", "-inv", tmp_path / "far.bed", path], check=False)
+    rc2, got, err2 = dump(path, {}, args=("-p",))
+    assert (rc2, got) == (rc, want), (got[:400], want[:400], err[-300:], err2[-300:])
