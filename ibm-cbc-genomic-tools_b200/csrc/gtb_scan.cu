@@ -390,6 +390,205 @@ __global__ void __launch_bounds__(256) scan_clear_carry_kernel(ScanTable hist, i
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) hist.hi[i] = 0u;
 }
 
+
+// ---- peak statistics (PeakFinder::Run, genomic_scans.cpp:298-368) ---------------------------------------------------------------
+// Tail probabilities in double precision.  The reference calls GSL; these are the textbook forms of the same functions:
+// P(X > k), X ~ Bin(n, p) = I_p(k + 1, n - k) (regularised incomplete beta, continued fraction by the modified Lentz method);
+// P(X > k), X ~ Poisson(mu) = P(k + 1, mu) (regularised lower incomplete gamma: series below a + 1, continued fraction above).
+__device__ double pk_beta_cf(double a, double b, double x) {
+  const double TINY = 1e-300, EPS = 1e-15;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < TINY) d = TINY;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 20000; m++) {
+    const double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+    c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+    d = 1.0 / d; h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+    c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+__device__ double pk_beta_inc(double a, double b, double x) {
+  if (x <= 0.0) return 0.0;
+  if (x >= 1.0) return 1.0;
+  const double ln_bt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x);
+  if (x < (a + 1.0) / (a + b + 2.0)) return exp(ln_bt) * pk_beta_cf(a, b, x) / a;
+  return 1.0 - exp(ln_bt) * pk_beta_cf(b, a, 1.0 - x) / b;
+}
+// gsl_cdf_binomial_Q(unsigned k, double p, unsigned n)
+__device__ double pk_binomial_Q(long long k, double p, long long n) {
+  const unsigned uk = (unsigned)k, un = (unsigned)n;
+  if (uk >= un) return 0.0;
+  return pk_beta_inc((double)uk + 1.0, (double)un - (double)uk, p);
+}
+// gsl_cdf_poisson_Q(unsigned k, double mu) = gsl_cdf_gamma_P(mu, k + 1, 1)
+__device__ double pk_poisson_Q(long long k, double mu) {
+  const double a = (double)(unsigned)k + 1.0, x = mu;
+  if (x <= 0.0) return 0.0;
+  const double ln_pre = -x + a * log(x) - lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 100000; n++) { ap += 1.0; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-16) break; }
+    return sum * exp(ln_pre);
+  }
+  const double TINY = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / TINY, d = 1.0 / b, h = d;
+  for (int i = 1; i < 100000; i++) {
+    const double an = -(double)i * ((double)i - a);
+    b += 2.0;
+    d = an * d + b; if (fabs(d) < TINY) d = TINY;
+    c = b + an / c; if (fabs(c) < TINY) c = TINY;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 1e-15) break;
+  }
+  return 1.0 - exp(ln_pre) * h;
+}
+__device__ double pk_ugaussian_Q(double x) { return 0.5 * erfc(x * 0.70710678118654752440); }
+
+struct PeaksView {
+  gtb_peaks_params prm;
+  ScanTable control;               // lo == nullptr: no control scanner
+  long long win_size;
+};
+
+// a Poisson variate of mean mu for window g (inversion on a hashed uniform; the reference: gsl_ran_poisson on a time-seeded generator)
+__device__ long long pk_poisson_variate(uint64_t seed, int64_t g, double mu) {
+  uint64_t z = seed + (uint64_t)g * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+  const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  double p = exp(-mu), s = p;
+  long long k = 0;
+  while (u > s && k < 100000) { k++; p *= mu / (double)k; s += p; }
+  return k;
+}
+
+// the statistics of one window (genomic_scans.cpp:303-354); false: the window is dropped
+__device__ bool pk_window(const PeaksView &pv, long long v1, long long v2, double &pval1, double &pval2) {
+  const gtb_peaks_params &P = pv.prm;
+  const long long v0 = pv.win_size;                                      // (no uniqueness scanner)
+  v1 = min(v1, v0); v2 = min(v2, v0);
+  if (P.norm) {
+    const double ratio = P.p_signal / P.p_control;
+    if (ratio < 1.0) v2 = (long long)floor((double)(float)v2 * ratio); else v1 = (long long)floor((double)(float)v1 / ratio);
+  }
+  if (v1 < P.min_reads) return false;
+  if (P.method == GTB_PEAKS_POISSON) {
+    pval1 = pk_poisson_Q(v1 + 5, (double)(v2 + 5));
+    pval2 = pk_poisson_Q(v2 + 5, (double)(v1 + 5));
+  } else if (!P.compare) {
+    pval1 = pk_binomial_Q(v1, P.p_signal, v0 + 1);
+    pval2 = pk_binomial_Q(v2, P.p_control, v0 + 1);
+  } else if (P.method == GTB_PEAKS_BINOMIAL) {
+    const float pp_control = (float)(((double)(float)v2 + 1.0) / ((double)v0 + 1.0));
+    pval1 = pk_binomial_Q(v1, fmax((double)pp_control, P.p_signal), v0 + 1);
+    const float pp_signal = (float)(((double)(float)v1 + 1.0) / ((double)v0 + 1.0));
+    pval2 = pk_binomial_Q(v2, fmax((double)pp_signal, P.p_control), v0 + 1);
+  } else if (P.method == GTB_PEAKS_BINOMIAL2) {
+    const double pp_control = (double)(v2 + 1) / (double)P.n_control_reads, pp_signal = (double)(v1 + 1) / (double)P.n_signal_reads;
+    pval1 = pk_binomial_Q(v1 + 1, pp_control, P.n_signal_reads);
+    pval2 = pk_binomial_Q(v2 + 1, pp_signal, P.n_control_reads);
+  } else if (P.method == GTB_PEAKS_CBINOMIAL) {
+    pval1 = pk_binomial_Q(v1 + 1, 0.5, v1 + v2 + 2);
+    pval2 = pk_binomial_Q(v2 + 1, 0.5, v1 + v2 + 2);
+  } else {
+    const double pp_control = (double)(v2 + 1) / (double)P.n_control_reads, pp_signal = (double)(v1 + 1) / (double)P.n_signal_reads;
+    const double ns = (double)P.n_signal_reads, nc = (double)P.n_control_reads;
+    pval1 = pk_ugaussian_Q(((double)(v1 + 1) - ns * pp_control) / sqrt(ns * pp_control));
+    pval2 = pk_ugaussian_Q(((double)(v2 + 1) - nc * pp_signal) / sqrt(nc * pp_signal));
+  }
+  return pval1 <= P.pval_cutoff;
+}
+
+constexpr int PK_THREADS = 256, PK_ITEMS = 4, PK_TILE = PK_THREADS * PK_ITEMS;
+// MODE 0: kept windows per tile.  MODE 1: the kept windows, at the tile's offset (tile_counts inclusive-scanned), in scan order.
+template <int MODE>
+__global__ void __launch_bounds__(PK_THREADS) scan_peaks_kernel(SlotTable t, ScanTable sig, PeaksView pv, int64_t total_windows, int combine,
+                                                                 ull *__restrict__ tile_counts, WindowsOut out, double *__restrict__ o_p1, double *__restrict__ o_p2) {
+  __shared__ int warp_counts[PK_THREADS / 32];
+  const bool wide_s = *reinterpret_cast<volatile const uint32_t *>(sig.flags) != 0u;
+  const bool has_c = pv.control.lo != nullptr;
+  const bool wide_c = has_c && *reinterpret_cast<volatile const uint32_t *>(pv.control.flags) != 0u;
+  const int64_t first = (int64_t)blockIdx.x * PK_TILE + (int64_t)threadIdx.x * PK_ITEMS;
+  int slot = first < total_windows ? find_slot(t.win_off, t.n_slots, first) : 0;
+  double p1[PK_ITEMS], p2[PK_ITEMS];
+  int slot_of[PK_ITEMS];
+  unsigned keep = 0;
+  long long s1 = 0, s2 = 0;
+  bool sliding = false;                                                  // s1 / s2 hold the previous window's sums of the same slot
+#pragma unroll
+  for (int i = 0; i < PK_ITEMS; i++) {
+    const int64_t g = first + i;
+    slot_of[i] = slot;
+    if (g >= total_windows) continue;
+    if (g >= t.win_off[slot + 1]) { while (g >= t.win_off[slot + 1]) slot++; sliding = false; }
+    slot_of[i] = slot;
+    const int64_t k0 = g - t.win_off[slot];
+    if (sliding && !t.spurious[slot]) {                                 // :5066-5073, one step to the right
+      const int64_t base = t.hist_off[slot] + k0;
+      s1 += (long long)table_get(sig, wide_s, base + combine - 1) - (long long)table_get(sig, wide_s, base - 1);
+      if (has_c) s2 += (long long)table_get(pv.control, wide_c, base + combine - 1) - (long long)table_get(pv.control, wide_c, base - 1);
+    } else {
+      s1 = window_value(t, sig, wide_s, slot, k0, combine);
+      if (has_c) s2 = window_value(t, pv.control, wide_c, slot, k0, combine);
+      sliding = true;
+    }
+    const long long v2 = has_c ? s2 : pk_poisson_variate(pv.prm.seed, g, (double)pv.win_size * pv.prm.p_signal);
+    if (pk_window(pv, s1, v2, p1[i], p2[i])) keep |= 1u << i;
+  }
+  const int mine = __popc(keep);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+  if (lane == 31) warp_counts[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < PK_THREADS / 32 ? warp_counts[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += v; }
+    if (lane < PK_THREADS / 32) warp_counts[lane] = w;
+  }
+  __syncthreads();
+  if (MODE == 0) {
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = (ull)warp_counts[PK_THREADS / 32 - 1];
+    return;
+  }
+  int64_t r = (int64_t)(blockIdx.x == 0 ? 0ull : tile_counts[blockIdx.x - 1]) + (warp > 0 ? warp_counts[warp - 1] : 0) + inc - mine;
+#pragma unroll
+  for (int i = 0; i < PK_ITEMS; i++)
+    if (keep & (1u << i)) {
+      const int s = slot_of[i];
+      if (out.slot16) out.slot16[r] = (uint16_t)s; else out.slot32[r] = (uint32_t)s;
+      out.win[r] = (uint32_t)(first + i - t.win_off[s] + 1);
+      o_p1[r] = p1[i]; o_p2[r] = p2[i];
+      r++;
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_peaks_expand_kernel(SlotTable t, WindowsOut w, int64_t first, int64_t count, int32_t *__restrict__ o_chrom,
+                                                                 int8_t *__restrict__ o_strand, int64_t *__restrict__ o_win) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t g = first + i;
+    const int s = w.slot16 ? (int)w.slot16[g] : (int)w.slot32[g];
+    if (o_chrom) o_chrom[i] = t.chrom[s];
+    if (o_strand) o_strand[i] = t.strand[s];
+    if (o_win) o_win[i] = (int64_t)w.win[g];
+  }
+}
+
 }  // namespace
 
 struct gtb_scan {
@@ -405,6 +604,8 @@ struct gtb_scan {
   dbuf<ull> d_tile_counts, d_scan_scratch;
   dbuf<uint32_t> c_win, c_val, c_val_hi, c_slot32; dbuf<uint16_t> c_slot16;   // the qualifying windows, compact (WindowsOut)
   bool wide_values = false;                            // c_val_hi is in use
+  dbuf<double> pk_p1, pk_p2;                           // gtb_scan_peaks: the kept windows' tail probabilities (their slot and number in c_slot*, c_win)
+  int64_t n_peaks = 0;
   dbuf<int32_t> o_chrom; dbuf<int8_t> o_strand; dbuf<int64_t> o_win, o_value;   // staging of gtb_scan_fetch
   uint32_t *h_flags = nullptr;                         // pinned: [0..1] the table's flags, [2..3] the window total
   ScanTable table() const { return ScanTable{d_lo.p, d_hi.p, d_flags.p}; }
@@ -541,6 +742,7 @@ extern "C" void gtb_scan_destroy(gtb_scan *sc) {
   sc->d_hist_off.release(); sc->d_win_off.release(); sc->d_lo.release(); sc->d_hi.release(); sc->d_flags.release();
   sc->d_tile_counts.release(); sc->d_scan_scratch.release();
   sc->c_win.release(); sc->c_val.release(); sc->c_val_hi.release(); sc->c_slot16.release(); sc->c_slot32.release();
+  sc->pk_p1.release(); sc->pk_p2.release();
   sc->o_chrom.release(); sc->o_strand.release(); sc->o_win.release(); sc->o_value.release();
   if (sc->h_flags) cudaFreeHost(sc->h_flags);
   sc->d_front_tab.release(); sc->wc.release();
@@ -702,6 +904,76 @@ extern "C" int gtb_scan_fetch(gtb_scan *sc, int64_t first, int64_t count, int32_
     if (strand) GTB_CUDA_OK(ctx, cudaMemcpyAsync(strand + p0, sc->o_strand.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (win) GTB_CUDA_OK(ctx, cudaMemcpyAsync(win + p0, sc->o_win.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (value) GTB_CUDA_OK(ctx, cudaMemcpyAsync(value + p0, sc->o_value.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return GTB_OK;
+}
+
+extern "C" int gtb_scan_peaks(gtb_scan *sc, gtb_scan *control, const gtb_peaks_params *params, int64_t *n_windows) {
+  if (!sc || !params || !n_windows) return GTB_ERR_ARG;
+  gtb_ctx *ctx = sc->ctx;
+  *n_windows = 0; sc->n_peaks = 0; sc->n_out = 0;                        // (the window arrays are shared with gtb_scan_finish)
+  if (params->method < GTB_PEAKS_BINOMIAL || params->method > GTB_PEAKS_NORMAL) return gtb_fail(ctx, GTB_ERR_ARG, "unknown probability distribution");
+  if (!params->compare && params->method != GTB_PEAKS_BINOMIAL && params->method != GTB_PEAKS_POISSON)
+    return gtb_fail(ctx, GTB_ERR_ARG, "unknown probability distribution");                 // genomic_scans.cpp:349
+  if (control) {
+    if (control->ctx != ctx || control->total_micro != sc->total_micro || control->total_windows != sc->total_windows || control->n_slots != sc->n_slots ||
+        control->combine != sc->combine || control->prm.win_step != sc->prm.win_step)
+      return gtb_fail(ctx, GTB_ERR_ARG, "signal and control scanners differ in genome or window parameters");
+  }
+  if (sc->total_windows == 0) return GTB_OK;
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  SlotTable t{sc->n_slots, sc->d_hist_off.p, sc->d_win_off.p, sc->d_spurious.p, sc->d_slot_chrom.p, sc->d_slot_strand.p};
+  PeaksView pv;
+  pv.prm = *params; pv.win_size = (long long)sc->prm.win_size;
+  pv.control = control ? control->table() : ScanTable{nullptr, nullptr, nullptr};
+  const int64_t n_tiles = (sc->total_windows + PK_TILE - 1) / PK_TILE;
+  GTB_TRY(sc->d_tile_counts.reserve(ctx, (size_t)n_tiles));
+  const WindowsOut none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  GTB_LAUNCH(ctx, "scan_peaks_count", scan_peaks_kernel<0>, (unsigned)n_tiles, PK_THREADS, 0, t, sc->table(), pv, sc->total_windows, sc->combine,
+             sc->d_tile_counts.p, none, (double *)nullptr, (double *)nullptr);
+  GTB_TRY(gtb_check_launch(ctx));
+  GTB_TRY(gtb_inclusive_scan_u64(ctx, sc->d_tile_counts.p, n_tiles, sc->d_scan_scratch));
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(sc->h_flags + 2, sc->d_tile_counts.p + (n_tiles - 1), sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ull total;
+  memcpy(&total, sc->h_flags + 2, sizeof total);
+  sc->n_peaks = (int64_t)total;
+  *n_windows = sc->n_peaks;
+  if (total == 0) return GTB_OK;
+  GTB_TRY(sc->c_win.reserve(ctx, (size_t)total));
+  if (sc->n_slots <= 65536) GTB_TRY(sc->c_slot16.reserve(ctx, (size_t)total)); else GTB_TRY(sc->c_slot32.reserve(ctx, (size_t)total));
+  GTB_TRY(sc->pk_p1.reserve(ctx, (size_t)total)); GTB_TRY(sc->pk_p2.reserve(ctx, (size_t)total));
+  GTB_LAUNCH(ctx, "scan_peaks_emit", scan_peaks_kernel<1>, (unsigned)n_tiles, PK_THREADS, 0, t, sc->table(), pv, sc->total_windows, sc->combine,
+             sc->d_tile_counts.p, sc->windows(), sc->pk_p1.p, sc->pk_p2.p);
+  GTB_TRY(gtb_check_launch(ctx));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return GTB_OK;
+}
+
+extern "C" int gtb_scan_peaks_fetch(gtb_scan *sc, int64_t first, int64_t count, int32_t *chrom, int8_t *strand, int64_t *win, double *pval1, double *pval2) {
+  if (!sc || first < 0 || count < 0 || first + count > sc->n_peaks) return GTB_ERR_ARG;
+  gtb_ctx *ctx = sc->ctx;
+  if (count == 0) return GTB_OK;
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  SlotTable t{sc->n_slots, sc->d_hist_off.p, sc->d_win_off.p, sc->d_spurious.p, sc->d_slot_chrom.p, sc->d_slot_strand.p};
+  const int64_t PIECE = (int64_t)4 << 20;
+  const size_t np = (size_t)std::min(count, PIECE);
+  if (chrom) GTB_TRY(sc->o_chrom.reserve(ctx, np));
+  if (strand) GTB_TRY(sc->o_strand.reserve(ctx, np));
+  if (win) GTB_TRY(sc->o_win.reserve(ctx, np));
+  for (int64_t p0 = 0; p0 < count; p0 += PIECE) {
+    const int64_t n = std::min(PIECE, count - p0);
+    if (chrom || strand || win) {
+      GTB_LAUNCH(ctx, "scan_peaks_expand", scan_peaks_expand_kernel, (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, t, sc->windows(),
+                 first + p0, n, chrom ? sc->o_chrom.p : nullptr, strand ? sc->o_strand.p : nullptr, win ? sc->o_win.p : nullptr);
+      GTB_TRY(gtb_check_launch(ctx));
+    }
+    if (chrom) GTB_CUDA_OK(ctx, cudaMemcpyAsync(chrom + p0, sc->o_chrom.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (strand) GTB_CUDA_OK(ctx, cudaMemcpyAsync(strand + p0, sc->o_strand.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (win) GTB_CUDA_OK(ctx, cudaMemcpyAsync(win + p0, sc->o_win.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pval1) GTB_CUDA_OK(ctx, cudaMemcpyAsync(pval1 + p0, sc->pk_p1.p + first + p0, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pval2) GTB_CUDA_OK(ctx, cudaMemcpyAsync(pval2 + p0, sc->pk_p2.p + first + p0, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return GTB_OK;

@@ -203,6 +203,30 @@ int  gtb_scan_finish(gtb_scan *scan, int64_t *n_windows);
 int  gtb_scan_fetch(gtb_scan *scan, int64_t first, int64_t count, int32_t *chrom, int8_t *strand,
                     int64_t *win, int64_t *value);
 
+/* ---- peak statistics on two window scanners ------------------------------------------------ */
+/* PeakFinder::Run (genomic_scans.cpp:298-368): the signal scanner and the control scanner (same genome, same window
+ * parameters) are walked window by window; v1 / v2 = the two window values clamped to the window size (:303-305), optionally
+ * equalised (-norm, :307); a window with v1 >= min_reads gets the tail probabilities pval1 (signal against background or
+ * control) and pval2 (the other way round) of the chosen method (:310-352, GSL's gsl_cdf_binomial_Q / _poisson_Q /
+ * _ugaussian_Q, computed here in double precision on the device) and is kept if pval1 <= pval_cutoff (:354).
+ * control == NULL: v2 is a Poisson variate of mean win_size * p_signal (:301; the reference seeds its generator with the time,
+ * here `seed`).  The kept windows stay on the device in scan order; gtb_scan_peaks_fetch copies a range of them out. */
+enum { GTB_PEAKS_BINOMIAL = 0, GTB_PEAKS_POISSON = 1, GTB_PEAKS_BINOMIAL2 = 2, GTB_PEAKS_CBINOMIAL = 3, GTB_PEAKS_NORMAL = 4 };
+typedef struct {
+  int32_t method;          /* -M */
+  int32_t compare;         /* -cmp */
+  int32_t norm;            /* -norm */
+  int32_t reserved;
+  int64_t min_reads;       /* -min */
+  int64_t n_signal_reads, n_control_reads;   /* CountGenomicRegions of the two files (:252, :259) */
+  double p_signal, p_control;                /* reads / effective genome size (:254, :261) */
+  double pval_cutoff;      /* -pval */
+  uint64_t seed;
+} gtb_peaks_params;
+int  gtb_scan_peaks(gtb_scan *signal, gtb_scan *control, const gtb_peaks_params *params, int64_t *n_windows);
+int  gtb_scan_peaks_fetch(gtb_scan *signal, int64_t first, int64_t count, int32_t *chrom, int8_t *strand, int64_t *win,
+                          double *pval1, double *pval2);
+
 /* ---- global sort of a region set ----------------------------------------------------------- */
 /* The order GenomicRegionSet::RunGlobalSort prints a region set in (genomic_regions gsort, genomic_intervals.cpp:4547-4570 with
  * BinGenomicRegions :6095-6150 and CompareBinnedGenomicRegions :6045-6049): chromosome rank ascending (the caller ranks the
