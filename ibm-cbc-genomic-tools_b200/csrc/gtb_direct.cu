@@ -81,14 +81,14 @@ __device__ __forceinline__ uint2 dr_gather(const uint2 *p) {
 // The general path for one query: the reference's admission rules, then the rank step (gtb_rank_device.cuh).
 // Same decisions as admit_query + rank_accumulate_kernel of gtb_overlap.cu for a single-interval, unweighted query.
 template <bool COVERAGE>
-__device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t qs, int32_t qe, int sbyte, int64_t index) {
+__device__ __noinline__ void dr_general(const RankView &rv, int32_t c, int32_t qs, int32_t qe, int sbyte, int64_t index, int64_t w = 1) {
   if ((uint32_t)c >= (uint32_t)rv.n_chrom || !rv.chrom_present[c]) return;           // :5719-5720
   if (!admit_interval(rv, qs, qe, index)) return;                                      // :5740-5741
   const int cls = rv.class_of[(uint8_t)sbyte];
   if (cls < 0) return;                                                              // no index region carries this strand, :5229
   const int g = c * rv.n_class + cls;
   const int gb = rv.goff[g], ge = rv.goff[g + 1];
-  if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, 1);
+  if (ge > gb) rank_item<COVERAGE>(rv, gb, ge, qs, qe, w);
 }
 
 // COVERAGE: the batch's common read length - 1, as every thread of both kernels computes it: the majority of three samples
@@ -131,7 +131,11 @@ __device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uin
 // COVERAGE: the "both" plane takes the query's length instead of 1.  Reads of a sequencing run mostly share one length, so the
 // byte counters count the queries whose length equals the batch's first query's and the commit kernel multiplies; a query of
 // another length costs a global reduction (and is counted, so that the host can leave the engine if they are many).
-template <bool COVERAGE>
+//
+// WEIGHTED (--max-label-value: a query counts min(max, atol(label)) times, genomic_intervals.cpp:1081-1085): a weight of 1..127
+// is what the query adds to its byte counter -- the add that takes a byte from below 128 to 128 or more moves 128 out, the add
+// that would take it past 255 raises the flag -- any other weight (0, negative, larger) leaves as a reduction of its own.
+template <bool COVERAGE, bool WEIGHTED>
 __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __grid_constant__ QueryView q, const __grid_constant__ RankView rv,
                                                                        const __grid_constant__ DirectView dv) {
   extern __shared__ __align__(16) uint32_t s_cnt[];                   // [n_words] four byte counters per word, then one dummy word per lane
@@ -147,21 +151,24 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   uint32_t odd = 0;                                                    // COVERAGE: queries of another length
   bool overflowed = false;
 
-  uint4 nc, ns, ne;
+  uint4 nc, ns, ne, nw = make_uint4(1u, 1u, 1u, 1u);
   uint32_t nst;
   int64_t tile = blockIdx.x;
   if (tile < n_full) {
     const int64_t first = tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS;
     nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
+    if (WEIGHTED) nw = dr_ldg128(q.weight + first);
   }
   for (; tile < n_full; tile += gridDim.x) {
-    const uint4 cc = nc, cs = ns, ce = ne;
+    const uint4 cc = nc, cs = ns, ce = ne, cw = nw;
     const uint32_t stw = nst;
     const int64_t next = tile + gridDim.x;
     if (next < n_full) {                                               // the next tile's 13 bytes per query are on their way while this one is counted
       const int64_t first = next * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS;
       nc = dr_ldg128(q.chrom + first); ns = dr_ldg128(q.start + first); ne = dr_ldg128(q.stop + first); nst = dr_ldg32(q.strand + first);
+      if (WEIGHTED) nw = dr_ldg128(q.weight + first);
     }
+    const int32_t wt[DR_ITEMS] = {(int)cw.x, (int)cw.y, (int)cw.z, (int)cw.w};          // (all 1 unless WEIGHTED)
     const uint32_t c[DR_ITEMS] = {cc.x, cc.y, cc.z, cc.w};
     const int32_t s[DR_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
     const int32_t e[DR_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     }
     // position-sorted input: the warp's 128 queries in one slot leave as one reduction
     const uint32_t lead = __shfl_sync(0xffffffffu, jS[0], 0);
-    bool same = skip == 0u;
+    bool same = skip == 0u && !WEIGHTED;
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) same = same && jS[i] == lead && jE[i] == lead && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
     if (__all_sync(0xffffffffu, same)) {
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     uint32_t done = skip;                                              // bit i: item i needs no shared atomic
     // (three neighbours, not two: the mates of a read pair sit next to each other in the stream and share a slot as a rule; any
     // run of five or more queries in one slot still has three of them in one thread)
-    if (__any_sync(0xffffffffu, (!(skip & 0x7u) && jS[0] == jS[1] && jS[1] == jS[2]) || (!(skip & 0xEu) && jS[1] == jS[2] && jS[2] == jS[3]))) {
+    if (!WEIGHTED && __any_sync(0xffffffffu, (!(skip & 0x7u) && jS[0] == jS[1] && jS[1] == jS[2]) || (!(skip & 0xEu) && jS[1] == jS[2] && jS[2] == jS[3]))) {
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++) {
         const bool both = !((skip >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
@@ -236,32 +243,36 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     // the four shared atomics go out back to back (an item with nothing for the "both" plane adds 0 to a word of its lane's own);
     // only then are the returned bytes looked at
     uint32_t old[DR_ITEMS];
+    uint32_t counted = 0;                                              // bit i: item i went to its byte counter
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      const bool both = !((done >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1);
+      const bool both = !((done >> i) & 1u) && jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1) &&
+                        (!WEIGHTED || (uint32_t)(wt[i] - 1) < 127u);
+      counted |= both ? 1u << i : 0u;
       GTB_ASSERT(!both || (ull)jS[i] < (ull)rv.n_slots);
       GTB_ASSERT(((skip >> i) & 1u) || ((ull)jS[i] < (ull)rv.n_slots && (ull)jE[i] < (ull)rv.n_slots));
-      old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? 1u << ((jS[i] & 3u) * 8u) : 0u);
+      old[i] = atomicAdd(&s_cnt[both ? (jS[i] >> 2) : dv.n_words + (uint32_t)lane], both ? (uint32_t)wt[i] << ((jS[i] & 3u) * 8u) : 0u);
     }
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
       if (!((done >> i) & 1u)) {
-        if (jS[i] == jE[i] && (!COVERAGE || (uint32_t)(e[i] - s[i]) == len0m1)) {   // one query in slot jS of the "both" plane
+        const ull w = (ull)(int64_t)wt[i];
+        if ((counted >> i) & 1u) {                                     // the query's weight in slot jS of the "both" plane
           const uint32_t sh = (jS[i] & 3u) * 8u;
-          const uint32_t ob = (old[i] >> sh) & 0xFFu;
-          if (ob >= 127u) {
-            if (ob == 127u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull * unit); }
-            overflowed |= ob == 255u;
+          const uint32_t ob = (old[i] >> sh) & 0xFFu, nb = ob + (uint32_t)wt[i];
+          if (nb >= 128u) {
+            if (ob < 128u) { atomicSub(&s_cnt[jS[i] >> 2], 128u << sh); dr_red64(dv.delta + jS[i], 128ull * unit); }
+            overflowed |= nb > 255u;
           }
-        } else if (COVERAGE && jS[i] == jE[i]) {                       // a query of another length
-          dr_red64(dv.delta + jS[i], (ull)((int64_t)e[i] - (int64_t)s[i] + 1));
-          odd++;
+        } else if (jS[i] == jE[i]) {                                   // a query of another length (COVERAGE) or of a weight the bytes cannot take
+          dr_red64(dv.delta + jS[i], COVERAGE ? w * (ull)((int64_t)e[i] - (int64_t)s[i] + 1) : w);
+          if (COVERAGE && (uint32_t)(e[i] - s[i]) != len0m1) odd++;
         } else {
-          dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], 1ull);
-          dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], 1ull);
+          dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], w);
+          dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], w);
           if (COVERAGE) {
-            dr_red64(dv.delta + (ull)H_SSUM * (ull)rv.n_slots + jS[i], (ull)(int64_t)s[i]);
-            dr_red64(dv.delta + (ull)H_ESUM * (ull)rv.n_slots + jE[i], (ull)(int64_t)e[i]);
+            dr_red64(dv.delta + (ull)H_SSUM * (ull)rv.n_slots + jS[i], w * (ull)(int64_t)s[i]);
+            dr_red64(dv.delta + (ull)H_ESUM * (ull)rv.n_slots + jE[i], w * (ull)(int64_t)e[i]);
           }
         }
       }
@@ -270,13 +281,13 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
         if ((general >> i) & 1u)
-          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);
+          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i, wt[i]);
     }
   }
   // the last, partial tile: general path
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
     for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
-      dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
+      dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
   if (COVERAGE && odd) atomicAdd(dv.flag + 1, odd);
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, Query
   if (!discard) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride)
-    dr_general<COVERAGE>(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r);
+    dr_general<COVERAGE>(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, q.weight ? (int64_t)q.weight[r] : 1);
 }
 
 template <typename T>
@@ -433,9 +444,9 @@ int gtb_direct_prepare(gtb_index *ix) {
 }
 
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
-  if (batch_multi || q.region_offset || q.weight) return false;        // single-interval, unweighted batches
+  if (batch_multi || q.region_offset) return false;                    // single-interval batches
   if (q.n_regions >= ((int64_t)1 << 40)) return false;
-  if ((((uintptr_t)q.chrom | (uintptr_t)q.start | (uintptr_t)q.stop) & 15) != 0 || ((uintptr_t)q.strand & 3) != 0) return false;   // 128-bit loads
+  if ((((uintptr_t)q.chrom | (uintptr_t)q.start | (uintptr_t)q.stop | (uintptr_t)q.weight) & 15) != 0 || ((uintptr_t)q.strand & 3) != 0) return false;   // 128-bit loads
   if (gtb_direct_prepare(ix) != GTB_OK) return false;
   return !ix->direct->off;
 }
@@ -444,7 +455,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   gtb_ctx *ctx = ix->ctx;
   if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
   gtb_direct_state *ds = ix->direct;
-  if (q.region_offset || q.weight) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine takes single-interval, unweighted batches");
+  if (q.region_offset) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine takes single-interval batches");
   // Watchdog, without ever making the host wait: after a batch the two flag words travel to pinned host memory behind it; the
   // next batch that finds that copy complete looks at them.  A replayed batch means byte counters overflow on this input, many
   // odd-length reads under coverage mean a reduction each -- either way the BUCKET engine serves this index from then on.
@@ -454,6 +465,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
     if ((int64_t)(uint32_t)(ds->h_flag[1] - ds->odd_seen) > ds->queries_in_check / 16) ds->off = ds->off_lengths = true;
     ds->odd_seen = ds->h_flag[1];
     if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
+    if (ds->off && q.weight) return GTB_ERR_UNSUPPORTED;                                       // weighted: the caller's general rank step
   }
   cudaGetLastError();                                                   // cudaErrorNotReady of the query above is not an error
   RankView rv;
@@ -468,17 +480,19 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   rv_hist.hist = ix->d_hist.p;
   const int64_t tiles = q.n_regions / DR_TILE;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ds->grid, tiles));
+#define GTB_DIRECT_LAUNCH(COV, WGT, NAME)                                                                                                   \
+  do {                                                                                                                                     \
+    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<COV, WGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));   \
+    GTB_LAUNCH(ctx, NAME, (direct_count_kernel<COV, WGT>), grid, DR_THREADS, ds->smem, q, rv, dv);                                        \
+    GTB_TRY(gtb_check_launch(ctx));                                                                                                        \
+    GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<COV>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);       \
+  } while (0)
   if (ix->op == GTB_OP_COVERAGE) {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
-    GTB_LAUNCH(ctx, "direct_coverage", direct_count_kernel<true>, grid, DR_THREADS, ds->smem, q, rv, dv);
-    GTB_TRY(gtb_check_launch(ctx));
-    GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<true>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
+    if (q.weight) GTB_DIRECT_LAUNCH(true, true, "direct_coverage_weighted"); else GTB_DIRECT_LAUNCH(true, false, "direct_coverage");
   } else {
-    GTB_CUDA_OK(ctx, cudaFuncSetAttribute(direct_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ds->smem));
-    GTB_LAUNCH(ctx, "direct_count", direct_count_kernel<false>, grid, DR_THREADS, ds->smem, q, rv, dv);
-    GTB_TRY(gtb_check_launch(ctx));
-    GTB_LAUNCH(ctx, "direct_commit", direct_commit_kernel<false>, (ds->n_words + 31) / 32, 256, 0, dv, q, rv_hist, ix->n_slots, grid);
+    if (q.weight) GTB_DIRECT_LAUNCH(false, true, "direct_count_weighted"); else GTB_DIRECT_LAUNCH(false, false, "direct_count");
   }
+#undef GTB_DIRECT_LAUNCH
   ds->queries_since_check += q.n_regions;
   if (!ds->check_pending) {
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -620,7 +620,10 @@ static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi
   }
   const unsigned engine = choose_engine(ix, q, batch_multi);
   if (engine == GTB_ENGINE_BUCKET) return gtb_bucket_accumulate(ix, q);
-  if (engine == GTB_ENGINE_DIRECT) return gtb_direct_accumulate(ix, q);
+  if (engine == GTB_ENGINE_DIRECT) {
+    const int rc = gtb_direct_accumulate(ix, q);
+    if (rc != GTB_ERR_UNSUPPORTED || !q.weight) return rc;              // (a weighted batch the engine has just left: the general step below)
+  }
   RankView rv = rank_view(ix);
   if (engine == GTB_ENGINE_ENUMERATE) {
     GTB_TRY(build_enum_structures(ix));

@@ -142,6 +142,37 @@ def test_direct_engine_vs_oracle(gtb, ctx, oracle, seed, cell_k):
     assert (e.value.code, e.value.index) == (rc, ei)
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_direct_engine_weighted(gtb, ctx, oracle, seed, cell_k):
+    """--max-label-value weights through the DIRECT engine: weights of 1..127 ride the byte counters (a counter passes 128 after
+    two or three of the larger ones: spills all the time), everything else -- 0, negative, 128 and up, near 2^31 -- leaves as a
+    reduction of its own; count and coverage (one common read length, and every length), against the oracle."""
+    rng = np.random.default_rng(5200 + seed)
+    gen = randcases.rand_grid if seed % 2 else randcases.rand_single
+    idx = gen(rng, 300)
+    n = 4096 * 7 + 77
+    q = gen(rng, n, strands="+-+-+-." if seed % 2 else "+-")
+    w = rng.integers(1, 128, n).astype(np.int32)
+    odd = rng.random(n) < 0.1
+    w[odd] = rng.choice(np.array([0, -3, 128, 255, 70000, 2_000_000_000], dtype=np.int64), size=int(odd.sum())).astype(np.int32)
+    fixed = {k: v.copy() for k, v in q.items()}
+    fixed["stop"] = np.where(rng.random(n) < 0.1, fixed["stop"], fixed["start"] + 36).astype(np.int32)
+    for flags in range(4):
+        rc, want, _ = oracle.count(q, idx, flags, qw=w)
+        assert rc == 0
+        assert np.array_equal(ctx.overlap_count(q, idx, flags | ENGINES["direct"], qweight=w), want), (flags, seed)
+        for reads in (q, fixed):
+            rc, want, _ = oracle.coverage(reads, idx, flags, qw=w)
+            assert rc == 0
+            assert np.array_equal(ctx.overlap_coverage(reads, idx, flags | ENGINES["direct"], qweight=w), want), ("coverage", flags, seed)
+    # piled-up weighted reads: byte counters overflow before their spills land -> the batch is replayed with its weights
+    piled = {k: v.copy() for k, v in q.items()}
+    piled["chrom"][:] = q["chrom"][0]; piled["strand"][:] = q["strand"][0]
+    piled["start"][:] = q["start"][0]; piled["stop"][:] = q["stop"][0]
+    rc, want, _ = oracle.count(piled, idx, 0, qw=w)
+    assert rc == 0 and np.array_equal(ctx.overlap_count(piled, idx, ENGINES["direct"], qweight=w), want)
+
+
 def test_direct_engine_counter_overflow_is_replayed(gtb, ctx, oracle):
     """Byte counters in shared memory: heavy skew (most reads on a handful of loci, in random order) makes some counter take
     more than 127 adds before its spill lands -- or it does not, depending on timing.  Either way the result is exact: an
