@@ -55,6 +55,7 @@ struct DirectView {
   ull *delta;                       // [3][n_slots] this batch's contributions that did not go through the byte counters
   uint32_t *flag;                   // [0] generation of the last batch in which a byte counter overflowed (that batch is discarded and replayed)
                                     // [1] coverage: queries whose length was not the batch's common one (a global reduction each)
+                                    // [2] ... those of them 256 bp or longer (which the BUCKET engine's elements cannot describe)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
   uint32_t n_cells;                 // entries of `cells` (bounds checks)
 };
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   const int lane = threadIdx.x & 31;
   const uint32_t len0m1 = COVERAGE ? dr_common_len(q) : 0u;                            // the common length - 1
   const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)len0m1 + 1ull : 1ull;                // what one counted query is worth in the "both" plane
-  uint32_t odd = 0;                                                    // COVERAGE: queries of another length
+  uint32_t odd = 0, odd_long = 0;                                      // COVERAGE: queries of another length; those of 256 bp and more
   bool overflowed = false;
 
   uint4 nc, ns, ne, nw = make_uint4(1u, 1u, 1u, 1u);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
           }
         } else if (jS[i] == jE[i]) {                                   // a query of another length (COVERAGE) or of a weight the bytes cannot take
           dr_red64(dv.delta + jS[i], COVERAGE ? w * (ull)((int64_t)e[i] - (int64_t)s[i] + 1) : w);
-          if (COVERAGE && (uint32_t)(e[i] - s[i]) != len0m1) odd++;
+          if (COVERAGE && (uint32_t)(e[i] - s[i]) != len0m1) { odd++; odd_long += (uint32_t)(e[i] - s[i]) >= 255u ? 1u : 0u; }
         } else {
           dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], w);
           dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], w);
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
-  if (COVERAGE && odd) atomicAdd(dv.flag + 1, odd);
+  if (COVERAGE && odd) { atomicAdd(dv.flag + 1, odd); if (odd_long) atomicAdd(dv.flag + 2, odd_long); }
   __syncthreads();
   uint4 *row = reinterpret_cast<uint4 *>(dv.cta_counts + (size_t)blockIdx.x * dv.n_words);
   for (uint32_t i = threadIdx.x; i < dv.n_words / 4; i += DR_THREADS) row[i] = reinterpret_cast<const uint4 *>(s_cnt)[i];
@@ -358,7 +359,7 @@ struct gtb_direct_state {
   dbuf<uint32_t> d_cta_counts, d_flag;
   dbuf<ull> d_delta;
   int64_t queries_since_check = 0, queries_in_check = 0;            // queries since the last flag copy was issued / covered by the copy in flight
-  uint32_t gen = 0, odd_seen = 0;
+  uint32_t gen = 0, odd_seen = 0, long_seen = 0;
   uint32_t *h_flag = nullptr;                                          // pinned: where the flag words land
   cudaEvent_t flag_copied = nullptr;
   bool check_pending = false;
@@ -429,11 +430,11 @@ int gtb_direct_prepare(gtb_index *ix) {
   GTB_TRY(upload_d(ctx, ds->d_cells, tab));
   GTB_TRY(ds->d_cta_counts.reserve(ctx, (size_t)ds->grid * n_words));
   GTB_TRY(ds->d_delta.reserve(ctx, (size_t)ix->planes * ix->n_slots));
-  GTB_TRY(ds->d_flag.reserve(ctx, 2));
-  if (!ds->h_flag) GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&ds->h_flag, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  GTB_TRY(ds->d_flag.reserve(ctx, 3));
+  if (!ds->h_flag) GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&ds->h_flag, 3 * sizeof(uint32_t), cudaHostAllocDefault));
   if (!ds->flag_copied) GTB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ds->flag_copied, cudaEventDisableTiming));
   GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_delta.p, 0, (size_t)ix->planes * ix->n_slots * sizeof(ull), ctx->stream));
-  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->d_flag.p, 0, 3 * sizeof(uint32_t), ctx->stream));
   GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   if (getenv("GTB_DEBUG_DIRECT"))
     fprintf(stderr, "[gtb direct] slots %lld cells %llu (2^%d bp, %u per block, %.1f MB allocated, %.1f MB within reach) general cells %zu smem %zu\n",
@@ -442,6 +443,9 @@ int gtb_direct_prepare(gtb_index *ix) {
   ds->ready = true; ds->failed = false;
   return GTB_OK;
 }
+
+// the index fits the engine and the watchdog has not sent it away
+bool gtb_direct_usable(gtb_index *ix) { return gtb_direct_prepare(ix) == GTB_OK && !ix->direct->off; }
 
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
   if (batch_multi || q.region_offset) return false;                    // single-interval batches
@@ -462,8 +466,12 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   if (ds->check_pending && cudaEventQuery(ds->flag_copied) == cudaSuccess) {
     ds->check_pending = false;
     if (ds->h_flag[0] != 0) ds->off = true;
-    if ((int64_t)(uint32_t)(ds->h_flag[1] - ds->odd_seen) > ds->queries_in_check / 16) ds->off = ds->off_lengths = true;
-    ds->odd_seen = ds->h_flag[1];
+    // reads of every length: BUCKET counts them in shared memory as long as its elements can hold the length (< 256 bp);
+    // longer ones (spans of read pairs under -gaps) it would hand to the general step one by one -- those stay here, a
+    // reduction each
+    const uint32_t odd_new = ds->h_flag[1] - ds->odd_seen, long_new = ds->h_flag[2] - ds->long_seen;
+    if ((int64_t)odd_new > ds->queries_in_check / 16 && (int64_t)long_new * 2 < (int64_t)odd_new) ds->off = ds->off_lengths = true;
+    ds->odd_seen = ds->h_flag[1]; ds->long_seen = ds->h_flag[2];
     if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
     if (ds->off && q.weight) return GTB_ERR_UNSUPPORTED;                                       // weighted: the caller's general rank step
   }
@@ -495,7 +503,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
 #undef GTB_DIRECT_LAUNCH
   ds->queries_since_check += q.n_regions;
   if (!ds->check_pending) {
-    GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GTB_CUDA_OK(ctx, cudaEventRecord(ds->flag_copied, ctx->stream));
     ds->check_pending = true;
     ds->queries_in_check = ds->queries_since_check;

@@ -585,10 +585,10 @@ static int accumulate_multi_fast(gtb_index *ix, const QueryView &q, int64_t n_in
   gtb_ctx *ctx = ix->ctx;
   const bool spans = ix->match_gaps;
   if (q.weight || !(spans || ix->op == GTB_OP_COVERAGE) || ix->flat_blocks) return GTB_ERR_UNSUPPORTED;
-  // coverage of spans: spans are long and of every length, which neither fast engine likes (DIRECT counts reads of one common
-  // length, BUCKET packs the length into the 8 bits its elements have left); measured, the general rank step is the faster one
-  if (spans && ix->op == GTB_OP_COVERAGE) return GTB_ERR_UNSUPPORTED;
   if (ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK)) return GTB_ERR_UNSUPPORTED;
+  // coverage of spans: spans are long and of every length.  DIRECT takes them at a reduction each (its byte counters count reads of
+  // one common length); BUCKET's elements have 8 bits for a length, so where DIRECT cannot serve the index the general rank step does
+  if (spans && ix->op == GTB_OP_COVERAGE && ((ix->engine & GTB_ENGINE_BUCKET) || q.n_regions < (1 << 18) || !gtb_direct_usable(ix))) return GTB_ERR_UNSUPPORTED;
   if (getenv("GTB_NO_MULTI_FAST")) return GTB_ERR_UNSUPPORTED;          // (tests: the general path on the same input)
   RankView rv = rank_view(ix);
   const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 16);

@@ -133,3 +133,4 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q);
 void gtb_direct_destroy(gtb_index *ix);
 void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
+bool gtb_direct_usable(gtb_index *ix);
