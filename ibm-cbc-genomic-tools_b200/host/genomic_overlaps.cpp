@@ -53,12 +53,32 @@ static gtb_set as_set(const gt::RegionBatch &b) {
 // CUDA context creation off the main thread (see gt_host.h: exit_hook)
 static std::thread g_ctx_thread;
 static gtb_ctx *g_ctx = nullptr;
+static gtb_mgpu *g_mgpu = nullptr;
+static int g_gpus = 1;
+static std::vector<int> g_gpu_list;
 static int g_ctx_rc = GTB_OK;
 static void start_context() {
   // The driver uses one GPU.  On a multi-GPU host the CUDA runtime would initialise every visible device first (seconds);
   // unless the user has chosen devices, only the first one is made visible.
-  setenv("CUDA_VISIBLE_DEVICES", "0", 0);
-  g_ctx_thread = std::thread([] { g_ctx_rc = gtb_ctx_create(0, &g_ctx); });
+  // GTB_GPUS=N in the environment: devices 0..N-1 behind the index (gtb_mgpu_*, query batches cut into one slice per device);
+  // GTB_GPUS=a,b,c names the devices (a device may repeat: several contexts on it)
+  if (const char *env = getenv("GTB_GPUS")) {
+    if (strchr(env, ',')) {
+      for (const char *p = env; *p;) { g_gpu_list.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; }
+      g_gpus = (int)g_gpu_list.size();
+    } else {
+      g_gpus = std::max(1, std::min(64, atoi(env)));
+    }
+  }
+  if (g_gpus > 1) {
+    g_ctx_thread = std::thread([] {
+      g_ctx_rc = gtb_mgpu_create(g_gpus, g_gpu_list.empty() ? nullptr : g_gpu_list.data(), &g_mgpu);
+      if (g_ctx_rc == GTB_OK) g_ctx = gtb_mgpu_ctx(g_mgpu, 0);
+    });
+  } else {
+    setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+    g_ctx_thread = std::thread([] { g_ctx_rc = gtb_ctx_create(0, &g_ctx); });
+  }
   gt::exit_hook = [] { if (g_ctx_thread.joinable()) g_ctx_thread.join(); };
 }
 static gtb_ctx *wait_context() {
@@ -196,9 +216,19 @@ int main(int argc, char *argv[]) {
   int64_t err_index = -1;
   gtb_set ref_set = as_set(ref);
   ref_set.weight = nullptr;
-  rc = gtb_index_create(ctx, &ref_set, want_coverage ? GTB_OP_COVERAGE : GTB_OP_COUNT, flags, &index, &err_index);
+  gtb_mgpu_index *mindex = nullptr;                                     // GTB_GPUS > 1 (count / coverage / density / rpkm)
+  const bool multi_gpu = g_mgpu != nullptr && op != "subset" && op != "overlap";
+  if (multi_gpu) rc = gtb_mgpu_index_create(g_mgpu, &ref_set, want_coverage ? GTB_OP_COVERAGE : GTB_OP_COUNT, flags, &mindex, &err_index);
+  else rc = gtb_index_create(ctx, &ref_set, want_coverage ? GTB_OP_COVERAGE : GTB_OP_COUNT, flags, &index, &err_index);
   if (rc == GTB_ERR_INDEX_REGION) gt::die_line(ref.line(err_index), "index regions should be compatible, sorted and non-overlapping!");
+  if (multi_gpu && rc != GTB_OK) { fprintf(stderr, "\nError: [gtb_mgpu_index_create] %s (status %d)\n", gtb_mgpu_last_error(g_mgpu), rc); exit(1); }
   check(ctx, rc, "gtb_index_create");
+  auto mcheck = [&](int status, const char *what) {
+    if (status != GTB_OK) { fprintf(stderr, "\nError: [%s] %s (status %d)\n", what, gtb_mgpu_last_error(g_mgpu), status); exit(1); }
+  };
+  auto finish_values = [&](uint64_t *out, int64_t *ei) {
+    return multi_gpu ? gtb_mgpu_index_finish(mindex, out, ei) : gtb_index_finish(index, out, GTB_MEM_HOST, ei);
+  };
 
   timer.Mark("index");
   if (op == "subset" || op == "overlap") {
@@ -259,7 +289,7 @@ int main(int argc, char *argv[]) {
     int64_t seen = 0;
     for (;;) {
       gt::RegionBatch &b = chunk[which];
-      check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");     // the buffer about to be overwritten has been consumed
+      if (!multi_gpu) check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");     // the buffer about to be overwritten has been consumed
       if (qr.Read(&b, CHUNK) == 0) break;
       if (IS_SORTED)
         for (int64_t k = 0; k < b.n_regions(); k++) {
@@ -270,26 +300,28 @@ int main(int argc, char *argv[]) {
           advance_index(b.chrom[i], (char)b.strand[i], b.start[i], b.stop[b.offset[k + 1] - 1]);
         }
       gtb_set qs = as_set(b);
-      check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");
+      if (multi_gpu) mcheck(gtb_mgpu_index_add_queries(mindex, &qs), "gtb_mgpu_index_add_queries");   // (the copies have left the buffer on return)
+      else check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");
       if (seen == 0) first_query_line = b.first_line;
       seen += b.n_regions();
       which ^= 1;
     }
-    check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");
+    if (!multi_gpu) check(ctx, gtb_ctx_synchronize(ctx), "gtb_ctx_synchronize");
     if (qr.failed()) {
       // a malformed line ended the stream; a query before it that the engine refuses comes first in the file and is the one
       // the reference would have stopped at
       std::vector<uint64_t> scratch((size_t)std::max<int64_t>(ref.n_regions(), 1));
-      rc = gtb_index_finish(index, scratch.data(), GTB_MEM_HOST, &err_index);
+      rc = finish_values(scratch.data(), &err_index);
       if (rc != GTB_ERR_QUERY_STOP_NONPOSITIVE && rc != GTB_ERR_QUERY_START_GT_STOP && rc != GTB_ERR_QUERY_REGION) qr.Fail();
       die_query(rc, first_query_line + err_index);
     }
   }
   timer.Mark("stream_queries");
   std::vector<uint64_t> values((size_t)std::max<int64_t>(ref.n_regions(), 1));
-  rc = gtb_index_finish(index, values.data(), GTB_MEM_HOST, &err_index);
+  rc = finish_values(values.data(), &err_index);
   if (rc == GTB_ERR_QUERY_STOP_NONPOSITIVE || rc == GTB_ERR_QUERY_START_GT_STOP || rc == GTB_ERR_QUERY_REGION)
     die_query(rc, first_query_line + err_index);
+  if (multi_gpu) mcheck(rc, "gtb_mgpu_index_finish");
   check(ctx, rc, "gtb_index_finish");
 
   timer.Mark("finish");
@@ -325,6 +357,6 @@ int main(int argc, char *argv[]) {
   fflush(stdout);
   timer.Mark("print");
   // the process is about to end: the driver reclaims device memory faster than freeing it buffer by buffer would
-  (void)index;
+  (void)index; (void)mindex;
   return 0;
 }

@@ -40,7 +40,10 @@ EXPORTS = [
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_add_packed", "gtb_index_finish",
     "gtb_index_finish_async", "gtb_index_status", "gtb_index_query_counts",
     "gtb_overlap_count", "gtb_overlap_coverage",
+    "gtb_mgpu_create", "gtb_mgpu_destroy", "gtb_mgpu_device_count", "gtb_mgpu_ctx", "gtb_mgpu_last_error", "gtb_mgpu_index_create",
+    "gtb_mgpu_index_destroy", "gtb_mgpu_index_reset", "gtb_mgpu_index_add_queries", "gtb_mgpu_index_add_packed", "gtb_mgpu_index_finish",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
+    "gtb_scan_peaks", "gtb_scan_peaks_fetch",
     "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64", "gtb_sort_regions",
 ]
 
@@ -98,6 +101,17 @@ def load_library(path=LIB_PATH):
         "gtb_index_query_counts": (ci, [vp, P(_Set), u32, vp, u32, P(i64)]),
         "gtb_overlap_count": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_overlap_coverage": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
+        "gtb_mgpu_create": (ci, [ci, P(ci), P(vp)]),
+        "gtb_mgpu_destroy": (None, [vp]),
+        "gtb_mgpu_device_count": (ci, [vp]),
+        "gtb_mgpu_ctx": (vp, [vp, ci]),
+        "gtb_mgpu_last_error": (ctypes.c_char_p, [vp]),
+        "gtb_mgpu_index_create": (ci, [vp, P(_Set), ci, u32, P(vp), P(i64)]),
+        "gtb_mgpu_index_destroy": (None, [vp]),
+        "gtb_mgpu_index_reset": (ci, [vp]),
+        "gtb_mgpu_index_add_queries": (ci, [vp, P(_Set)]),
+        "gtb_mgpu_index_add_packed": (ci, [vp, P(_Packed)]),
+        "gtb_mgpu_index_finish": (ci, [vp, vp, P(i64)]),
         "gtb_scan_create": (ci, [vp, ctypes.c_int32, vp, P(_ScanParams), P(vp)]),
         "gtb_scan_destroy": (None, [vp]),
         "gtb_scan_reset": (ci, [vp]),
@@ -251,6 +265,73 @@ class Context:
         self.check(lib().gtb_synth_reads_range(self._h, seed, first, n, read_len, len(cl), _np_ptr(cl), p_lo, p_hi,
                                                out["chrom"].data_ptr(), out["start"].data_ptr(), out["stop"].data_ptr(),
                                                out["strand"].data_ptr()))
+
+
+class MultiGpu:
+    """Several GPUs behind one index in this process (gtb_mgpu_*): host-resident query batches are cut into one slice per device."""
+
+    def __init__(self, devices):
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        rc = lib().gtb_mgpu_create(len(devices), arr, ctypes.byref(self._h))
+        if rc != OK:
+            raise GtbError(rc, "gtb_mgpu_create failed", -1)
+        self.n = len(devices)
+
+    def check(self, rc, index=-1):
+        if rc != OK:
+            raise GtbError(rc, lib().gtb_mgpu_last_error(self._h).decode(), index)
+
+    def transfer_stats(self):
+        """(h2d bytes, d2h bytes, packed chunks, raw chunks) summed over the devices' contexts"""
+        tot = [0, 0, 0, 0]
+        for k in range(self.n):
+            v = [ctypes.c_int64(0) for _ in range(4)]
+            lib().gtb_ctx_transfer_stats(ctypes.c_void_p(lib().gtb_mgpu_ctx(self._h, k)), *[ctypes.byref(x) for x in v])
+            tot = [a + b.value for a, b in zip(tot, v)]
+        return tuple(tot)
+
+    def close(self):
+        if self._h:
+            lib().gtb_mgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+class MultiIndex:
+    def __init__(self, mg, regions, op=OP_COUNT, flags=0, roffsets=None):
+        self.mg = mg
+        self._h = ctypes.c_void_p()
+        rs, keep = host_set(regions, None, roffsets)
+        err = ctypes.c_int64(-1)
+        mg.check(lib().gtb_mgpu_index_create(mg._h, ctypes.byref(rs), op, flags, ctypes.byref(self._h), ctypes.byref(err)), err.value)
+        self.n_regions = rs.n_regions
+
+    def reset(self):
+        self.mg.check(lib().gtb_mgpu_index_reset(self._h))
+
+    def add_set(self, st):
+        self.mg.check(lib().gtb_mgpu_index_add_queries(self._h, ctypes.byref(st)))
+
+    def add_host(self, queries, weight=None, offsets=None):
+        st, keep = host_set(queries, weight, offsets)
+        self.add_set(st)
+
+    def add_packed_ptr(self, n, start_ptr, meta_ptr, read_len):
+        pk = _Packed(n, start_ptr, meta_ptr, read_len)
+        self.mg.check(lib().gtb_mgpu_index_add_packed(self._h, ctypes.byref(pk)))
+
+    def finish(self, out=None):
+        if out is None:
+            out = np.zeros(self.n_regions, dtype=np.uint64)
+        err = ctypes.c_int64(-1)
+        rc = lib().gtb_mgpu_index_finish(self._h, _np_ptr(out), ctypes.byref(err))
+        self.mg.check(rc, err.value)
+        return out
+
+    def close(self):
+        if self._h:
+            lib().gtb_mgpu_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
 
 
 class Index:

@@ -169,6 +169,27 @@ int  gtb_overlap_count(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_me
 int  gtb_overlap_coverage(gtb_ctx *ctx, const gtb_set *queries, unsigned queries_mem, const gtb_set *regions,
                           unsigned flags, uint64_t *out, int64_t *err_index);
 
+/* ---- several GPUs behind one index (one process, one host thread per device) --------------------------------------------- */
+/* Results are sums over queries (genomic_intervals.cpp:5310-5314): every device holds the whole index, a batch of
+ * host-resident queries is cut into one contiguous slice per device -- no routing, each slice crosses its own host link --
+ * and gtb_mgpu_index_finish adds the devices' values up (the query-sharded decomposition; the genome-sharded one,
+ * for queries that are already resident on the devices, is the torch.distributed driver of python/gtb200/sharded.py).
+ * Errors carry the stream-order index of the first offending query region over all slices.  devices[k] may repeat a device
+ * (several contexts on one GPU: what the single-GPU tests do). */
+typedef struct gtb_mgpu gtb_mgpu;
+typedef struct gtb_mgpu_index gtb_mgpu_index;
+int  gtb_mgpu_create(int n_devices, const int *devices, gtb_mgpu **out);
+void gtb_mgpu_destroy(gtb_mgpu *mg);
+int  gtb_mgpu_device_count(const gtb_mgpu *mg);
+gtb_ctx *gtb_mgpu_ctx(gtb_mgpu *mg, int k);
+const char *gtb_mgpu_last_error(const gtb_mgpu *mg);
+int  gtb_mgpu_index_create(gtb_mgpu *mg, const gtb_set *regions, int op, unsigned flags, gtb_mgpu_index **out, int64_t *err_index);
+void gtb_mgpu_index_destroy(gtb_mgpu_index *index);
+int  gtb_mgpu_index_reset(gtb_mgpu_index *index);
+int  gtb_mgpu_index_add_queries(gtb_mgpu_index *index, const gtb_set *queries);          /* host arrays */
+int  gtb_mgpu_index_add_packed(gtb_mgpu_index *index, const gtb_packed_reads *reads);    /* host arrays */
+int  gtb_mgpu_index_finish(gtb_mgpu_index *index, uint64_t *out, int64_t *err_index);    /* host array */
+
 /* ---- sliding-window read counts ----------------------------------------------------------- */
 typedef struct {
   int64_t win_step;        /* -d, genomic_scans.cpp:120 */
