@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   const int lane = threadIdx.x & 31;
   const uint32_t len0m1 = COVERAGE ? dr_common_len(q) : 0u;                            // the common length - 1
   const ull unit = COVERAGE ? (ull)(int64_t)(int32_t)len0m1 + 1ull : 1ull;                // what one counted query is worth in the "both" plane
+  uint32_t sorted_wait = 0;                                            // tiles until this warp tries the sorted-input test again
   uint32_t odd = 0, odd_long = 0;                                      // COVERAGE: queries of another length; those of 256 bp and more
   bool overflowed = false;
 
@@ -180,11 +181,52 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++) general |= ((xw >> (8 * i)) & 0xF9u) ? (1u << i) : 0u;
     }
+#pragma unroll
+    for (int i = 0; i < DR_ITEMS; i++)
+      if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
+    // Position-sorted input, before any lookup: if the warp's 128 queries lie on one chromosome between two cells that share a
+    // first slot, the later one free of evaluation points, no point lies anywhere among them -- per strand one reduction (or
+    // nothing to count).  Two uniform lookups per strand instead of 128 divergent ones and everything that follows.  A warp
+    // that fails the test (random input always does) does not try again for 16 tiles.
+    if (!WEIGHTED && sorted_wait == 0u) {
+      bool mine = general == 0u && c[0] == c[1] && c[1] == c[2] && c[2] == c[3] && c[0] < n_chrom;
+      if (COVERAGE) mine = mine && (uint32_t)(e[0] - s[0]) == len0m1 && (uint32_t)(e[1] - s[1]) == len0m1 && (uint32_t)(e[2] - s[2]) == len0m1 && (uint32_t)(e[3] - s[3]) == len0m1;
+      const uint32_t c_lo = __reduce_min_sync(0xffffffffu, c[0]), c_hi = __reduce_max_sync(0xffffffffu, c[0]);
+      bool done_fast = false;
+      if (__all_sync(0xffffffffu, mine) && c_lo == c_hi) {
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, (uint32_t)min(min(s[0], s[1]), min(s[2], s[3])));
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, (uint32_t)max(max(e[0], e[1]), max(e[2], e[3])));
+        const uint32_t n_minus = dv.nsig == 2u ? __reduce_add_sync(0xffffffffu, (uint32_t)__popc(xw & 0x02020202u)) : 0u;
+        const uint32_t cnt[2] = {32u * DR_ITEMS - n_minus, n_minus};
+        uint32_t slot[2] = {0u, 0u};
+        bool good = true, count_it[2] = {false, false};
+#pragma unroll
+        for (uint32_t sg = 0; sg < 2u; sg++) {
+          if (cnt[sg] == 0u) continue;                                  // (with one block for both strands, everything is in cnt[0])
+          const uint32_t b0 = (c_lo * dv.nsig + sg) * stride;
+          const uint2 ea = dr_gather(dv.cells + b0 + min(lo >> cbits, last)), eb = dr_gather(dv.cells + b0 + min(hi >> cbits, last));
+          if (ea.x & DR_GENERAL) { good = false; continue; }
+          if (ea.x & DR_NOTHING) continue;                              // every start is beyond the group's last point (or there is no group): nothing to count
+          good = good && !((ea.x | eb.x) & (DR_SCAN | DR_GENERAL | DR_NOTHING)) && ((ea.x ^ eb.x) & 0xFFFFFFu) == 0u && eb.y == 0xFFFFFFFFu;
+          slot[sg] = ea.x & 0xFFFFFFu; count_it[sg] = true;
+        }
+        if (good) {
+          if (lane == 0) {
+            if (count_it[0]) dr_red64(dv.delta + slot[0], (ull)cnt[0] * unit);
+            if (count_it[1]) dr_red64(dv.delta + slot[1], (ull)cnt[1] * unit);
+          }
+          done_fast = true;
+        }
+      }
+      if (done_fast) continue;
+      sorted_wait = 16u;
+    } else if (!WEIGHTED) {
+      sorted_wait--;
+    }
     uint32_t base[DR_ITEMS];
     uint2 ent[DR_ITEMS];
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++) {
-      if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
       base[i] = (min(c[i], n_chrom) * dv.nsig + ((xw >> (8 * i + 1)) & sigmask)) * stride;   // unknown chromosome -> the all-"nothing" block
       GTB_ASSERT(base[i] + last < dv.n_cells);
       ent[i] = dr_gather(dv.cells + base[i] + min((uint32_t)s[i] >> cbits, last));

@@ -129,6 +129,18 @@ def test_direct_engine_vs_oracle(gtb, ctx, oracle, seed, cell_k):
         rc, want, _ = oracle.coverage(fixed, idx, flags)
         assert rc == 0
         assert np.array_equal(ctx.overlap_coverage(fixed, idx, flags | ENGINES["direct"]), want), ("coverage/fixed", flags, seed)
+    # position-sorted input (by chromosome and start with the strands mixed, and by chromosome, strand and start): whole warps
+    # between two evaluation points leave as one reduction per strand before any lookup
+    for keys in ((q["start"], q["chrom"]), (q["start"], q["strand"], q["chrom"])):
+        order = np.lexsort(keys)
+        srt = {k: np.ascontiguousarray(v[order]) for k, v in q.items()}
+        fsrt = {k: v.copy() for k, v in srt.items()}
+        fsrt["stop"] = (fsrt["start"] + 36).astype(np.int32)
+        for flags in (0, 1):
+            rc, want, _ = oracle.count(srt, idx, flags)
+            assert rc == 0 and np.array_equal(ctx.overlap_count(srt, idx, flags | ENGINES["direct"]), want), ("sorted", flags, seed)
+            rc, want, _ = oracle.coverage(fsrt, idx, flags)
+            assert rc == 0 and np.array_equal(ctx.overlap_coverage(fsrt, idx, flags | ENGINES["direct"]), want), ("sorted coverage", flags, seed)
     bad = {k: v.copy() for k, v in q.items()}
     where = sorted(rng.choice(n, size=3, replace=False).tolist())
     bad["stop"][where[0]] = bad["start"][where[0]] - 1                   # start > stop
