@@ -656,6 +656,47 @@ def main():
     e2e = time_e2e("packed", e2e_steps)
     e2e_soa = time_e2e("soa", max(2, e2e_steps // 2))
 
+    # ---- the same reads in position order (what -S promises and aligners emit), device-resident: a secondary figure next to `value`
+    sorted_input = None
+    if world == 1:
+        key = (dev["chrom"].long() << 33) | ((dev["strand"] == ord("-")).long() << 32) | dev["start"].long()
+        order = torch.argsort(key)
+        del key
+        sdev = {k: v[order].contiguous() for k, v in dev.items()}
+        del order
+        ssets, keep3 = sets_of(sdev)
+
+        def step_sorted():
+            lib_stream.wait_stream(torch.cuda.current_stream())
+            index.reset()
+            for st in ssets:
+                index.add_set(st, gtb200.MEM_DEVICE)
+            index.finish_async_ptr(out_dev.data_ptr())
+            torch.cuda.current_stream().wait_stream(lib_stream)
+        for _ in range(args.warmup):
+            step_sorted()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            step_sorted()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        index.status()
+        assert int(out_dev.sum().item()) == expect_sum, "sorted-input result differs"
+        s_ms = s0.elapsed_time(s1) / args.steps
+        ctx.profile(True)
+        for _ in range(3):
+            step_sorted()
+        torch.cuda.synchronize()
+        sprof = ctx.profile_report()
+        ctx.profile(False)
+        s_dom = sprof[dom_name]["total_ms"] / sprof[dom_name]["launches"] if dom_name in sprof else None
+        sorted_input = {"order": "chromosome, strand, start", "ms_per_step": s_ms, "value": n / (s_ms * 1e-3),
+                        "step_frac": (BYTES_PER_QUERY * n + BYTES_PER_REGION * N_REGIONS) / (s_ms * 1e-3) / 1e9 / peak,
+                        "kernel": dom_name, "kernel_ms": s_dom, "frac": None if s_dom is None else alg_bytes / (s_dom * 1e-3) / 1e9 / peak}
+        del sdev, ssets, keep3
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "query intervals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -667,6 +708,8 @@ def main():
                                           "all-gather of per-region counts" % world if world > 1 else "single GPU"},
                 "roofline": roofline, "e2e": e2e, "e2e_soa": e2e_soa, "gpu_launches": launches, "clocks": clocks.summary(),
                 "checksum": counts_check, "checksum_verified": "equals the per-query formulation's total (torch.searchsorted)"}
+        if sorted_input:
+            line["sorted_input"] = sorted_input
         if sharding:
             line["sharding"] = sharding
         if not args.no_cpu_baseline and world == 1:

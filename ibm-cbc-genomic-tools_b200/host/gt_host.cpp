@@ -1015,6 +1015,54 @@ int64_t RegionReader::ReadKeep(RegionBatch *out, std::vector<std::string> *raw, 
 
 static void AppendLong(std::string *out, long v) { char t[32]; out->append(t, (size_t)snprintf(t, sizeof t, "%ld", v)); }
 
+void PrintModified(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms,
+                   const char *label, long start, long stop, std::string *out) {
+  const int64_t lo = b.offset[k], hi = b.offset[k + 1];
+  for (int64_t i = lo + 1; i < hi; i++)                                  // IsCompatible(false), :1009-1017
+    if (b.chrom[i] != b.chrom[lo] || b.strand[i] != b.strand[lo]) die_line(b.line(k), "intervals should have the same chromosome/strand for this operation!");
+  const std::string &chrom = chroms.name[b.chrom[lo]];
+  const char strand = (char)b.strand[lo];
+  std::string copy(raw);
+  char *inp = &copy[0];
+  if (format == "BED") {                                               // six columns whatever the input had; the score column as read (0 if absent)
+    const char sep = strchr(inp, '\t') == nullptr ? ' ' : '\t';
+    const int n_tokens = CountTokens(inp, sep);
+    long score = 0;
+    if (n_tokens >= 5) { for (int i = 0; i < 4; i++) NextToken(&inp, sep); score = atol(NextToken(&inp, sep)); }
+    out->append(chrom); out->push_back('\t'); AppendLong(out, start - 1); out->push_back('\t'); AppendLong(out, stop); out->push_back('\t');
+    out->append(label); out->push_back('\t'); AppendLong(out, score); out->push_back('\t'); out->push_back(strand); out->push_back('\n');
+  } else if (format == "GFF") {
+    const int n_tokens = CountTokens(inp, '\t');
+    NextToken(&inp, '\t');
+    const char *source = NextToken(&inp, '\t'), *feature = NextToken(&inp, '\t');
+    NextToken(&inp, '\t'); NextToken(&inp, '\t');
+    const char *score = NextToken(&inp, '\t');
+    NextToken(&inp, '\t');
+    const char frame = NextToken(&inp, '\t')[0];
+    out->append(chrom); out->push_back('\t'); out->append(source); out->push_back('\t'); out->append(feature); out->push_back('\t');
+    AppendLong(out, start); out->push_back('\t'); AppendLong(out, stop); out->push_back('\t'); out->append(score);
+    out->push_back('\t'); out->push_back(strand); out->push_back('\t'); out->push_back(frame);
+    if (n_tokens > 8) { out->push_back('\t'); out->append(label); NextToken(&inp, '\t'); }
+    if (n_tokens > 9) { out->push_back('\t'); out->append(NextToken(&inp, '\t')); }
+    out->push_back('\n');
+  } else if (format == "SAM") {
+    const int n_tokens = CountTokens(inp, '\t');
+    NextToken(&inp, '\t');
+    const long flag = atol(NextToken(&inp, '\t'));
+    for (int i = 0; i < 4; i++) NextToken(&inp, '\t');
+    const char *rnext = NextToken(&inp, '\t');
+    for (int i = 0; i < 4; i++) NextToken(&inp, '\t');
+    out->append(label); out->push_back('\t'); AppendLong(out, flag); out->push_back('\t'); out->append(chrom); out->push_back('\t');
+    AppendLong(out, start); out->append("\t255\t"); AppendLong(out, stop - start + 1); out->append("M\t"); out->append(rnext);
+    out->append("\t0\t0\t*\t*");
+    if (n_tokens > 11) { out->push_back('\t'); out->append(inp); }
+    out->push_back('\n');
+  } else {
+    out->append(label); out->push_back('\t'); out->append(chrom); out->push_back(' '); out->push_back(strand); out->push_back(' ');
+    AppendLong(out, start); out->push_back(' '); AppendLong(out, stop); out->push_back('\n');
+  }
+}
+
 void PrintRegion(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms, std::string *out) {
   const int64_t lo = b.offset[k], hi = b.offset[k + 1];
   if (hi <= lo) return;                                                // "if (I.size()==0) return;"

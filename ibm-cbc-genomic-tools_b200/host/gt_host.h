@@ -218,6 +218,11 @@ class RegionReader {
 // the reference keeps as they are (BED score / thick / rgb, GFF source / feature / score / frame / comment, the SAM columns).
 // `format` is RegionReader::format(); `raw` the region's input line.
 void PrintRegion(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms, std::string *out);
+// What GenomicRegion{,BED,GFF,SAM}::PrintModified(label, start, stop) writes for region k (genomic_intervals.cpp:909-913, :2310-2314,
+// :2854-2860, :3555-3562): the region's first interval moved to [start, stop] under a new label, the format's other columns
+// from the input line.  The region's intervals must share chromosome and strand (fatal otherwise, as in the reference).
+void PrintModified(const std::string &format, const std::string &raw, const RegionBatch &b, int64_t k, const ChromTable &chroms,
+                   const char *label, long start, long stop, std::string *out);
 
 char ProcessStrand(const char *token);                // '1','+' -> '+'; '-1','-' -> '-'; '.' -> '+'; else fatal  (genomic_intervals.cpp:5956-5962)
 bool RegionWellFormed(const RegionBatch &b, int64_t k);

@@ -44,7 +44,7 @@ EXPORTS = [
     "gtb_mgpu_index_destroy", "gtb_mgpu_index_reset", "gtb_mgpu_index_add_queries", "gtb_mgpu_index_add_packed", "gtb_mgpu_index_finish",
     "gtb_scan_create", "gtb_scan_destroy", "gtb_scan_reset", "gtb_scan_add_reads", "gtb_scan_finish", "gtb_scan_fetch",
     "gtb_scan_peaks", "gtb_scan_peaks_fetch",
-    "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64", "gtb_sort_regions",
+    "gtb_synth_reads", "gtb_synth_reads_range", "gtb_gather_u64", "gtb_sort_regions", "gtb_link_regions",
 ]
 
 
@@ -120,6 +120,7 @@ def load_library(path=LIB_PATH):
         "gtb_scan_fetch": (ci, [vp, i64, i64, vp, vp, vp, vp]),
         "gtb_gather_u64": (ci, [vp, vp, vp, i64, vp, vp]),
         "gtb_sort_regions": (ci, [vp, i64, vp, vp, vp, vp, ci, vp]),
+        "gtb_link_regions": (ci, [vp, i64, vp, vp, vp, i64, P(i64), vp, vp]),
         "gtb_synth_reads": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp]),
         "gtb_synth_reads_range": (ci, [vp, ctypes.c_uint64, i64, i64, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_uint64,
                                        ctypes.c_uint64, vp, vp, vp, vp]),
@@ -252,6 +253,16 @@ class Context:
         perm = np.zeros(len(cr), dtype=np.int64)
         self.check(lib().gtb_sort_regions(self._h, len(cr), _np_ptr(cr), _np_ptr(st), _np_ptr(sp), _np_ptr(sd), int(by_strand), _np_ptr(perm)))
         return perm
+
+    def link_regions(self, group_rank, start, stop, max_difference=0):
+        """(head index, linked stop) of the linked regions of a sorted stream (`genomic_regions link`); numpy arrays in and out"""
+        g = np.ascontiguousarray(group_rank, dtype=np.int32); st = np.ascontiguousarray(start, dtype=np.int32)
+        sp = np.ascontiguousarray(stop, dtype=np.int32)
+        head = np.zeros(max(len(g), 1), dtype=np.int64); lstop = np.zeros(max(len(g), 1), dtype=np.int32)
+        n_linked = ctypes.c_int64(0)
+        self.check(lib().gtb_link_regions(self._h, len(g), _np_ptr(g), _np_ptr(st), _np_ptr(sp), int(max_difference), ctypes.byref(n_linked),
+                                          _np_ptr(head), _np_ptr(lstop)))
+        return head[:n_linked.value], lstop[:n_linked.value]
 
     def gather_u64(self, table_ptr, index_ptr, n, out_ptr, cuda_stream_ptr=0):
         """out[k] = table[index[k]] on the device (the multi-GPU driver's scatter to file order)"""

@@ -279,6 +279,15 @@ int  gtb_synth_reads_range(gtb_ctx *ctx, uint64_t seed, int64_t first, int64_t n
                            int32_t n_chrom, const int64_t *chrom_len /*host*/, uint64_t p_lo, uint64_t p_hi,
                            int32_t *d_chrom, int32_t *d_start, int32_t *d_stop, int8_t *d_strand);
 
+/* ---- linking consecutive regions of a sorted stream ------------------------------------------ */
+/* GenomicRegionSet::RunGlobalLink (genomic_regions link, genomic_intervals.cpp:4607-4644) for max_difference >= 0: the n
+ * single-interval regions of a stream sorted by chromosome / (strand) / start -- group_rank[k] = the rank of region k's
+ * chromosome (and strand, if the stream is sorted by strand) in stream order, non-decreasing -- fall into *n_linked linked
+ * regions; linked region j begins at region head_index[j] and reaches linked_stop[j].  Host arrays; head_index and
+ * linked_stop have room for n entries.  Prefix-maximum scan + prefix sum on the device (csrc/gtb_link.cu). */
+int  gtb_link_regions(gtb_ctx *ctx, int64_t n, const int32_t *group_rank, const int32_t *start, const int32_t *stop,
+                      int64_t max_difference, int64_t *n_linked, int64_t *head_index, int32_t *linked_stop);
+
 #ifdef __cplusplus
 }
 #endif
