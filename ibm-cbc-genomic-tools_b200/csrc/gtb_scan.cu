@@ -7,14 +7,17 @@
 // window ascending).
 //
 // Two ways to build the histogram:
-//   * scan_histogram_kernel: one global reduction per read.  The table of a genome (hg19, step 50: 1 GB) is far larger than
-//     L2, so every reduction is a 32-byte read-modify-write in HBM: ~21 G reads/s measured on B200.  Kept for small batches,
-//     weighted reads and tiny genomes.
-//   * bucketed (default for large unweighted batches): the write-combining partition of gtb_wc_partition.cuh sorts the reads'
-//     micro-window numbers into <= 512 genome buckets (13 B in, 4 B out per read); scan_bucket_hist_kernel then counts each
-//     bucket in shared memory -- 65 536 16-bit counters per CTA, a bucket wider than that is walked by several CTAs, each
-//     keeping its own sub-range (the bucket's elements come from L2 after the first of them) -- and adds the non-zero
-//     counters to the table with plain coalesced read-modify-writes: a bucket range belongs to exactly one CTA.
+//   * scan_histogram_kernel: one global reduction per read.  The table of a genome (hg19, step 50: 0.5 GB) is far larger than
+//     L2, so every reduction is a 32-byte read-modify-write in HBM.  Kept for small batches, weighted reads and tiny genomes.
+//   * bucketed (default for large unweighted batches): the write-combining partition of gtb_wc_partition.cuh (this file's
+//     instance: 1 024 threads, one CTA per SM, up to 1 024 buckets) sorts the reads' micro-window numbers into genome buckets
+//     (13 B in, 4 B out per read); scan_bucket_hist_kernel then counts each bucket in shared memory -- as many 16-bit counters
+//     per CTA as an SM holds, a bucket wider than that is walked by several CTAs, each keeping its own sub-range (the bucket's
+//     elements come from L2 after the first of them) -- and adds the non-zero counters to the table with plain coalesced
+//     read-modify-writes: a bucket range belongs to exactly one CTA.
+// The table is a uint32 plane plus a carry plane that stays untouched until an entry passes 2^32 (ScanTable below); the
+// qualifying windows stay on the device in a compact form and are widened by gtb_scan_fetch.
+// genomic_scans peaks (PeakFinder::Run, genomic_scans.cpp:298-354) walks two such tables in step: scan_peaks_kernel.
 #include "gtb_internal.cuh"
 #ifndef GTB_SCAN_WC_THREADS
 #define GTB_SCAN_WC_THREADS 1024
