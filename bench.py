@@ -296,10 +296,13 @@ def run_other_config(args):
         dev["stop"] = dev["start"] + (READ_LEN - 1)
         del m1, idx, gap, span, s1, over
         off = torch.arange(0, 2 * n_pairs + 1, 2, dtype=torch.int64, device="cuda")
-        dset, keep = gtb200.device_set(dev, offsets=off)
+        dset_csr, keep = gtb200.device_set(dev, offsets=off)
+        dset_uni, keep_u = gtb200.device_set(dev, per_region=2)           # the same pairs, declared as regions of two intervals: no offsets
         out = torch.zeros(N_REGIONS, dtype=torch.int64, device="cuda")
         lines = []
-        for name, flags in (("coverage", 0), ("coverage -gaps", gtb200.MATCH_GAPS)):
+        for name, flags, dset, layout in (("coverage", 0, dset_uni, "regions of two intervals, no offsets"),
+                                          ("coverage", 0, dset_csr, "CSR offsets"),
+                                          ("coverage -gaps", gtb200.MATCH_GAPS, dset_csr, "CSR offsets")):
             index = gtb200.Index(ctx, regions, gtb200.OP_COVERAGE, flags)
 
             def step():
@@ -329,11 +332,11 @@ def run_other_config(args):
                 want += int((F(g, e_) - F(g, s_ - 1)).sum().item())
             got = int(out.sum().item())
             assert got == want, "%s: sum %d differs from the independent formulation's %d" % (name, got, want)
-            bytes_step = 13 * 2 * n_pairs + 8 * (n_pairs + 1) + BYTES_PER_REGION * N_REGIONS
+            bytes_step = 13 * 2 * n_pairs + (8 * (n_pairs + 1) if dset is dset_csr else 0) + BYTES_PER_REGION * N_REGIONS
             lines.append({"metric": "query intervals/sec (%s, device-timed)" % name, "value": 2 * n_pairs / (ms * 1e-3), "unit": "query intervals/s", "n_gpus": 1,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "int64", "data": "synthetic",
-                          "config": {"workload": "genomic_overlaps %s, %d synthetic read pairs (two 50-bp intervals per region, gap 100-400 bp) vs 60k regions (configs[3])" % (name, n_pairs),
+                          "config": {"workload": "genomic_overlaps %s, %d synthetic read pairs (two 50-bp intervals per region, gap 100-400 bp) vs 60k regions (configs[3]); layout: %s" % (name, n_pairs, layout),
                                      "intervals": 2 * n_pairs, "n_regions": N_REGIONS, "l2": "inputs (%.1f GB) far exceed the 126 MB L2" % (bytes_step / 1e9)},
                           "roofline": roofline_of(prof, 13 * 2 * n_pairs, bytes_step, ms), "e2e": None, "gpu_launches": launches, "clocks": clocks,
                           "checksum": got, "checksum_verified": "sum of coverage equals the per-interval formulation's total (torch.searchsorted + prefix sums)"})

@@ -58,6 +58,8 @@ struct DirectView {
                                     // [2] ... those of them 256 bp or longer (which the BUCKET engine's elements cannot describe)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
   uint32_t n_cells;                 // entries of `cells` (bounds checks)
+  int pair_check;                   // COVERAGE: queries 2p and 2p + 1 are the two intervals of region p, to be checked as a region
+  int region_admission;             // ... under these admission rules (0: the default engine's, 1: the Sorted class's)
 };
 constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
 
@@ -117,6 +119,18 @@ __device__ __forceinline__ uint32_t dr_scan(const int32_t *__restrict__ pts, uin
     if (!(d < x)) return j + 3;
     j += 4;
   }
+}
+
+// What the reference decides per REGION for a read pair whose two intervals the engine takes as two queries (see
+// region_prepass_kernel in gtb_overlap.cu, which does the same for regions of any shape in a pass of its own): well-formedness
+// (same chromosome and strand, sorted, non-overlapping: :5698, :5709) and the fatal conditions of the span on a chromosome the
+// index knows (:5740-5741).  Nothing is written unless something is wrong.
+__device__ __forceinline__ void dr_check_pair(const RankView &rv, int admission, uint32_t c0, uint32_t c1, uint32_t sb0, uint32_t sb1,
+                                              int32_t s0, int32_t e0, int32_t s1, int32_t e1, int64_t region) {
+  if (!(c0 == c1 && sb0 == sb1 && s1 >= s0 && s1 > e0)) { report_error(rv.err, region, GTB_ERR_QUERY_REGION); return; }
+  const bool fatal = admission == 1 ? (int64_t)s0 > (int64_t)e1 + 1 : (e1 <= 0 || s0 > e1);
+  if (fatal && c0 < (uint32_t)rv.n_chrom && rv.chrom_present[c0])
+    report_error(rv.err, region, admission == 1 || e1 > 0 ? GTB_ERR_QUERY_START_GT_STOP : GTB_ERR_QUERY_STOP_NONPOSITIVE);
 }
 
 // The 13 bytes per query come as 128-bit loads straight into registers, one tile ahead of the tile being counted, so that
@@ -184,6 +198,11 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++)
       if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
+    if (COVERAGE && dv.pair_check) {
+      const int64_t region = q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS) / 2;
+      dr_check_pair(rv, dv.region_admission, c[0], c[1], stw & 0xFFu, (stw >> 8) & 0xFFu, s[0], e[0], s[1], e[1], region);
+      dr_check_pair(rv, dv.region_admission, c[2], c[3], (stw >> 16) & 0xFFu, stw >> 24, s[2], e[2], s[3], e[3], region + 1);
+    }
     // Position-sorted input, before any lookup: if the warp's 128 queries lie on one chromosome between two cells that share a
     // first slot, the later one free of evaluation points, no point lies anywhere among them -- per strand one reduction (or
     // nothing to count).  Two uniform lookups per strand instead of 128 divergent ones and everything that follows.  A warp
@@ -331,6 +350,10 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
     for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
       dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
+    if (COVERAGE && dv.pair_check)
+      for (int64_t p = n_full * (DR_TILE / 2) + threadIdx.x; p < n / 2; p += DR_THREADS)
+        dr_check_pair(rv, dv.region_admission, (uint32_t)q.chrom[2 * p], (uint32_t)q.chrom[2 * p + 1], (uint32_t)(uint8_t)q.strand[2 * p], (uint32_t)(uint8_t)q.strand[2 * p + 1],
+                      q.start[2 * p], q.stop[2 * p], q.start[2 * p + 1], q.stop[2 * p + 1], q.index_base + p);
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
   if (COVERAGE && odd) { atomicAdd(dv.flag + 1, odd); if (odd_long) atomicAdd(dv.flag + 2, odd_long); }
@@ -497,7 +520,7 @@ bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
   return !ix->direct->off;
 }
 
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, bool pair_check) {
   gtb_ctx *ctx = ix->ctx;
   if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
   gtb_direct_state *ds = ix->direct;
@@ -526,6 +549,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q) {
   dv.n_cells = ds->n_cells; dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
+  dv.pair_check = pair_check ? 1 : 0; dv.region_admission = ix->sorted_rules ? 1 : 0;
   RankView rv_hist = rv;
   rv_hist.hist = ix->d_hist.p;
   const int64_t tiles = q.n_regions / DR_TILE;

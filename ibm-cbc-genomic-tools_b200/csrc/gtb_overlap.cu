@@ -261,6 +261,13 @@ __global__ void __launch_bounds__(256) region_prepass_kernel(QueryView q, RankVi
   }
 }
 
+// region_offset of a batch whose regions all have k intervals (the caller said so instead of sending offsets): written out only
+// for the paths that read offsets
+__global__ void __launch_bounds__(256) uniform_offsets_kernel(int64_t n_regions, int64_t k, int64_t base, int64_t *__restrict__ off) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n_regions; r += stride) off[r] = base + r * k;
+}
+
 // Expands a packed chunk (start + meta of W bytes, see gtb_ingest.cpp) into the SoA layout the engines read.
 template <int W>
 __device__ __forceinline__ void unpack_one(uint32_t m, uint32_t len0, int32_t s, int32_t &c, int32_t &e, uint32_t &sb) {
@@ -577,7 +584,7 @@ static unsigned choose_engine(gtb_index *ix, const QueryView &q, bool batch_mult
   return GTB_ENGINE_RANK;
 }
 
-static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi, int64_t n_intervals);
+static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi, int64_t n_intervals, int uniform_k = 0);
 
 // Multi-interval query regions in front of the single-interval engines (see region_prepass_kernel).  Returns GTB_ERR_UNSUPPORTED
 // if this batch is not of that kind.
@@ -611,9 +618,33 @@ static int accumulate_multi_fast(gtb_index *ix, const QueryView &q, int64_t n_in
   return rc;
 }
 
-static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi, int64_t n_intervals) {
+static int accumulate_device(gtb_index *ix, const QueryView &q_in, bool batch_multi, int64_t n_intervals, int uniform_k) {
   gtb_ctx *ctx = ix->ctx;
-  if (q.n_regions <= 0) return GTB_OK;
+  if (q_in.n_regions <= 0) return GTB_OK;
+  QueryView q = q_in;
+  if (uniform_k > 1) {
+    // Regions of k intervals each, no offsets sent.  Read pairs under coverage (k == 2, no -gaps, no weights, an index the DIRECT
+    // engine serves): the engine takes the intervals as they lie and checks every pair in its registers -- what the reference
+    // decides per region (well-formedness, :5698, :5709; the fatal span conditions, :5740-5741) costs no pass of its own.
+    const bool pairs = uniform_k == 2 && ix->op == GTB_OP_COVERAGE && !ix->match_gaps && !q.weight && !ix->flat_blocks &&
+                       !(ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET)) && n_intervals >= (1 << 18) && !getenv("GTB_NO_MULTI_FAST");
+    if (pairs) {
+      QueryView flat = q;
+      flat.n_regions = n_intervals; flat.weight = nullptr; flat.region_offset = nullptr; flat.interval_base = 0;
+      if (gtb_direct_supported(ix, flat, false)) {
+        ix->flat_blocks = true;
+        const int rc = gtb_direct_accumulate(ix, flat, /*pair_check=*/true);
+        ix->flat_blocks = false;
+        if (rc != GTB_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    // every other shape: the offsets are written out and the batch is an ordinary CSR one
+    GTB_TRY(ix->uni_off.reserve(ctx, (size_t)q.n_regions + 1));
+    GTB_LAUNCH(ctx, "uniform_offsets", uniform_offsets_kernel, gtb_grid_for(q.n_regions + 1, 256, (int64_t)ctx->sm_count * 8), 256, 0, q.n_regions, (int64_t)uniform_k,
+               q.interval_base, ix->uni_off.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    q.region_offset = ix->uni_off.p;
+  }
   if (batch_multi) {
     const int rc = accumulate_multi_fast(ix, q, n_intervals);
     if (rc != GTB_ERR_UNSUPPORTED) return rc;
@@ -654,8 +685,13 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
   gtb_ctx *ctx = ix->ctx;
   if (queries->n_regions < 0 || queries->n_intervals < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative sizes");
   if (queries->n_regions == 0) return GTB_OK;
-  if (!queries->region_offset && queries->n_regions != queries->n_intervals)
-    return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
+  // regions of k >= 2 intervals each need no offsets: region r is intervals [r * k, (r + 1) * k)
+  int uniform_k = 0;
+  if (!queries->region_offset && queries->n_regions != queries->n_intervals) {
+    if (queries->n_intervals % queries->n_regions != 0 || queries->n_intervals / queries->n_regions > (1 << 20))
+      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_intervals is not a multiple of n_regions");
+    uniform_k = (int)(queries->n_intervals / queries->n_regions);
+  }
   if (!queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");
   GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   // a CSR is judged by its offsets, not by its totals (regions of 0 and 2 intervals would add up to "one each"); one whose
@@ -672,14 +708,15 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
   } else if (queries->region_offset) {
     batch_multi = true;
   }
-  const bool pass_offsets = batch_multi;
+  const bool pass_offsets = batch_multi;                                // (offsets exist and matter)
+  if (uniform_k > 1) batch_multi = true;
 
   if (mem & GTB_MEM_DEVICE) {
     QueryView q;
     q.n_regions = queries->n_regions; q.chrom = queries->chrom; q.start = queries->start; q.stop = queries->stop;
     q.strand = queries->strand; q.weight = queries->weight; q.region_offset = pass_offsets ? queries->region_offset : nullptr;
     q.interval_base = 0; q.index_base = ix->queries_seen;
-    GTB_TRY(accumulate_device(ix, q, batch_multi, queries->n_intervals));
+    GTB_TRY(accumulate_device(ix, q, batch_multi, queries->n_intervals, uniform_k));
     ix->queries_seen += queries->n_regions;
     return GTB_OK;
   }
@@ -689,8 +726,8 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
   const int64_t CHUNK = (int64_t)4 << 20;
   for (int64_t r0 = 0; r0 < queries->n_regions; r0 += CHUNK) {
     const int64_t r1 = std::min(queries->n_regions, r0 + CHUNK);
-    const int64_t i0 = pass_offsets ? queries->region_offset[r0] : r0;
-    const int64_t i1 = pass_offsets ? queries->region_offset[r1] : r1;
+    const int64_t i0 = pass_offsets ? queries->region_offset[r0] : uniform_k > 1 ? r0 * uniform_k : r0;
+    const int64_t i1 = pass_offsets ? queries->region_offset[r1] : uniform_k > 1 ? r1 * uniform_k : r1;
     const size_t nr = (size_t)(r1 - r0), ni = (size_t)(i1 - i0);
     gtb_index::stage &st = ix->stages[ix->next_stage];
     ix->next_stage ^= 1;
@@ -766,7 +803,7 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
     q.n_regions = (int64_t)nr; q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
     q.weight = queries->weight ? st.weight.p : nullptr; q.region_offset = pass_offsets ? st.off.p : nullptr;
     q.interval_base = i0; q.index_base = ix->queries_seen + r0;
-    GTB_TRY(accumulate_device(ix, q, batch_multi, (int64_t)ni));
+    GTB_TRY(accumulate_device(ix, q, batch_multi, (int64_t)ni, uniform_k));
     GTB_CUDA_OK(ctx, cudaEventRecord(st.consumed, ctx->stream));
     st.in_flight = true;
   }

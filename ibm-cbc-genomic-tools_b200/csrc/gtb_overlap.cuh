@@ -107,6 +107,7 @@ struct gtb_index {
   // spans of multi-interval query regions (-gaps): one single-interval query per region, written by the prepass
   dbuf<int32_t> sp_chrom, sp_start, sp_stop;
   dbuf<int8_t> sp_strand;
+  dbuf<int64_t> uni_off;            // offsets written out for a batch of uniform regions (see accumulate_device)
   int64_t queries_seen = 0;
 
   // double-buffered staging for host-resident query batches
@@ -129,7 +130,8 @@ bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
 
 // ---- direct engine (gtb_direct.cu) ---------------------------------------------------------------
 int gtb_direct_prepare(gtb_index *ix);
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q);
+// pair_check: the batch is the flattened intervals of two-interval regions (coverage); every pair is checked as the reference checks a region
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, bool pair_check = false);
 void gtb_direct_destroy(gtb_index *ix);
 void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

@@ -146,26 +146,27 @@ def _np_ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
-def host_set(s, weight=None, offsets=None):
-    """dict of numpy arrays -> (gtb_set with host pointers, keepalive)."""
+def host_set(s, weight=None, offsets=None, per_region=1):
+    """dict of numpy arrays -> (gtb_set with host pointers, keepalive).  per_region = k > 1 (and no offsets): regions of k intervals each"""
     chrom = np.ascontiguousarray(s["chrom"], dtype=np.int32)
     start = np.ascontiguousarray(s["start"], dtype=np.int32)
     stop = np.ascontiguousarray(s["stop"], dtype=np.int32)
     strand = np.ascontiguousarray(s["strand"], dtype=np.int8)
     w = None if weight is None else np.ascontiguousarray(weight, dtype=np.int32)
     off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
-    n_reg = len(off) - 1 if off is not None else len(chrom)
+    n_reg = len(off) - 1 if off is not None else len(chrom) // per_region
     st = _Set(n_reg, len(chrom), _np_ptr(chrom), _np_ptr(start), _np_ptr(stop), _np_ptr(strand), _np_ptr(w), _np_ptr(off))
     return st, (chrom, start, stop, strand, w, off)
 
 
-def device_set(t, weight=None, offsets=None):
-    """dict of torch CUDA tensors (int32/int32/int32/int8) -> (gtb_set with device pointers, keepalive)."""
+def device_set(t, weight=None, offsets=None, per_region=1):
+    """dict of torch CUDA tensors (int32/int32/int32/int8) -> (gtb_set with device pointers, keepalive).
+    per_region = k > 1 (and no offsets): regions of k intervals each"""
     import torch
     assert t["chrom"].dtype == torch.int32 and t["start"].dtype == torch.int32 and t["stop"].dtype == torch.int32
     assert t["strand"].dtype == torch.int8 and t["chrom"].is_cuda
     n = t["chrom"].numel()
-    n_reg = offsets.numel() - 1 if offsets is not None else n
+    n_reg = offsets.numel() - 1 if offsets is not None else n // per_region
     st = _Set(n_reg, n, t["chrom"].data_ptr(), t["start"].data_ptr(), t["stop"].data_ptr(), t["strand"].data_ptr(),
               None if weight is None else weight.data_ptr(), None if offsets is None else offsets.data_ptr())
     return st, (t, weight, offsets)
@@ -374,13 +375,13 @@ class Index:
     def add_set(self, st, mem):
         self.ctx.check(lib().gtb_index_add_queries(self._h, ctypes.byref(st), mem))
 
-    def add_host(self, queries, weight=None, offsets=None):
-        st, keep = host_set(queries, weight, offsets)
+    def add_host(self, queries, weight=None, offsets=None, per_region=1):
+        st, keep = host_set(queries, weight, offsets, per_region)
         self.add_set(st, MEM_HOST)
         self.ctx.synchronize()          # numpy temporaries in `keep` must outlive the async copies
 
-    def add_device(self, tensors, weight=None, offsets=None):
-        st, keep = device_set(tensors, weight, offsets)
+    def add_device(self, tensors, weight=None, offsets=None, per_region=1):
+        st, keep = device_set(tensors, weight, offsets, per_region)
         self.add_set(st, MEM_DEVICE)
 
     def add_packed_ptr(self, n, start_ptr, meta_ptr, read_len, mem):

@@ -39,7 +39,9 @@ typedef struct gtb_scan gtb_scan;       /* a genome-wide micro-window histogram 
  * GenomicRegion{LABEL, vector<GenomicInterval*>} objects (genomic_intervals.h:962-964, :333-337).
  * Region k owns intervals [region_offset[k], region_offset[k+1]); region_offset == NULL means one
  * interval per region (n_intervals == n_regions), which is what BED3-BED11, GFF and single-interval
- * REG lines produce. */
+ * REG lines produce -- or, for QUERY sets with n_intervals == k * n_regions, k intervals per region
+ * (region r = intervals [r * k, (r + 1) * k): read pairs are k == 2), which saves the offsets' 8 bytes per
+ * region and, for coverage over read pairs, the pass that checks the regions. */
 typedef struct {
   int64_t n_regions;
   int64_t n_intervals;

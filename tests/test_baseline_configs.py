@@ -214,6 +214,49 @@ def test_config3_paired_coverage_abi(ctx, oracle, gtb):
     assert np.array_equal(ctx.overlap_count(pairs, regions, gtb.MATCH_GAPS, qoffsets=off), want)
 
 
+def test_config3_pairs_without_offsets(ctx, oracle, gtb):
+    """Read pairs handed over as regions of two intervals each WITHOUT offsets (gtb_set.region_offset == NULL, n_intervals ==
+    2 * n_regions): coverage takes the intervals as they lie and checks every pair in the engine's registers; the other shapes
+    (count, -gaps, a forced engine) get their offsets written out on the device.  Host and device memory, odd batch sizes, and the
+    fatal cases with the first offending REGION's stream index."""
+    import torch
+    pairs, off = synth_pairs(3_000_001, seed=15)
+    regions = support.synth_regions(60_000, 3)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in pairs.items()}
+    for op, fn, flag_sets in ((gtb.OP_COVERAGE, oracle.coverage, (0, gtb.MATCH_GAPS, gtb.IGNORE_STRAND, gtb.ENGINE_RANK)), (gtb.OP_COUNT, oracle.count, (gtb.MATCH_GAPS,))):
+        for flags in flag_sets:
+            rc, want, _ = fn(pairs, regions, flags & 3, qoff=off)
+            assert rc == 0
+            ix = gtb.Index(ctx, regions, op, flags)
+            ix.add_host(pairs, per_region=2)
+            assert np.array_equal(ix.finish(), want), ("host", op, flags)
+            ix.reset()
+            cut = 2 * 1_234_567                                            # two device batches, the second one not a multiple of a tile
+            ix.add_device({k: v[:cut] for k, v in dev.items()}, per_region=2)
+            ix.add_device({k: v[cut:] for k, v in dev.items()}, per_region=2)
+            assert np.array_equal(ix.finish(), want), ("device", op, flags)
+            ix.close()
+    # a malformed pair (mates overlap), a pair on two chromosomes, and a pair whose span ends at or before 0 on an indexed chromosome
+    for where, kind in ((2_000_123, "overlap"), (2_999_999, "chrom"), (777, "stop")):
+        bad = {k: v.copy() for k, v in pairs.items()}
+        i = 2 * where
+        if kind == "overlap":
+            bad["start"][i + 1] = bad["stop"][i]
+        elif kind == "chrom":
+            bad["chrom"][i + 1] = (bad["chrom"][i] + 1) % 24
+        else:
+            bad["chrom"][i] = bad["chrom"][i + 1] = regions["chrom"][0]
+            bad["start"][i], bad["stop"][i], bad["start"][i + 1], bad["stop"][i + 1] = -90, -60, -40, -3
+        rc, _, ei = oracle.coverage(bad, regions, 0, qoff=off)
+        assert rc != 0 and ei == where
+        ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, 0)
+        ix.add_host(bad, per_region=2)
+        with pytest.raises(gtb.GtbError) as e:
+            ix.finish()
+        assert (e.value.code, e.value.index) == (rc, where), (kind, e.value.code, e.value.index, rc)
+        ix.close()
+
+
 def test_config3_paired_density_cli(tmp_path):
     if not support.have_ref():
         pytest.skip("reference binaries not built (oracle/_ref)")
