@@ -302,6 +302,7 @@ def run_other_config(args):
         lines = []
         for name, flags, dset, layout in (("coverage", 0, dset_uni, "regions of two intervals, no offsets"),
                                           ("coverage", 0, dset_csr, "CSR offsets"),
+                                          ("coverage -gaps", gtb200.MATCH_GAPS, dset_uni, "regions of two intervals, no offsets"),
                                           ("coverage -gaps", gtb200.MATCH_GAPS, dset_csr, "CSR offsets")):
             index = gtb200.Index(ctx, regions, gtb200.OP_COVERAGE, flags)
 

@@ -58,7 +58,8 @@ struct DirectView {
                                     // [2] ... those of them 256 bp or longer (which the BUCKET engine's elements cannot describe)
   uint32_t gen;                     // this batch's generation (1, 2, ...)
   uint32_t n_cells;                 // entries of `cells` (bounds checks)
-  int pair_check;                   // COVERAGE: queries 2p and 2p + 1 are the two intervals of region p, to be checked as a region
+  int pair_check;                   // queries 2p and 2p + 1 are the two intervals of region p.  1 (COVERAGE): counted as they lie, the pair checked as
+                                    // a region.  2 (-gaps): the pair's span [first start, second stop] is the query
   int region_admission;             // ... under these admission rules (0: the default engine's, 1: the Sorted class's)
 };
 constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
@@ -185,9 +186,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
       if (WEIGHTED) nw = dr_ldg128(q.weight + first);
     }
     const int32_t wt[DR_ITEMS] = {(int)cw.x, (int)cw.y, (int)cw.z, (int)cw.w};          // (all 1 unless WEIGHTED)
-    const uint32_t c[DR_ITEMS] = {cc.x, cc.y, cc.z, cc.w};
-    const int32_t s[DR_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
-    const int32_t e[DR_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
+    uint32_t c[DR_ITEMS] = {cc.x, cc.y, cc.z, cc.w};
+    int32_t s[DR_ITEMS] = {(int)cs.x, (int)cs.y, (int)cs.z, (int)cs.w};
+    int32_t e[DR_ITEMS] = {(int)ce.x, (int)ce.y, (int)ce.z, (int)ce.w};
     // strands: '+' = 0x2B, '-' = 0x2D.  xw has 0x00 / 0x06 in the bytes of '+' / '-' queries
     const uint32_t xw = stw ^ 0x2B2B2B2Bu;
     uint32_t general = 0;                                              // bit i: item i takes the general path
@@ -198,10 +199,28 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < DR_ITEMS; i++)
       if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;            // the reference's fatal cases (or nothing, on an unknown chromosome)
-    if (COVERAGE && dv.pair_check) {
-      const int64_t region = q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS) / 2;
-      dr_check_pair(rv, dv.region_admission, c[0], c[1], stw & 0xFFu, (stw >> 8) & 0xFFu, s[0], e[0], s[1], e[1], region);
-      dr_check_pair(rv, dv.region_admission, c[2], c[3], (stw >> 16) & 0xFFu, stw >> 24, s[2], e[2], s[3], e[3], region + 1);
+    if (dv.pair_check == 1) {
+      if (COVERAGE) {
+        const int64_t region = q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS) / 2;
+        dr_check_pair(rv, dv.region_admission, c[0], c[1], stw & 0xFFu, (stw >> 8) & 0xFFu, s[0], e[0], s[1], e[1], region);
+        dr_check_pair(rv, dv.region_admission, c[2], c[3], (stw >> 16) & 0xFFu, stw >> 24, s[2], e[2], s[3], e[3], region + 1);
+      }
+    } else if (dv.pair_check == 2) {
+      // -gaps: items 0 and 2 become the spans of their pairs, items 1 and 3 queries on a chromosome nobody has (nothing to count,
+      // nothing to object to); a malformed pair is reported and counts nothing either
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        const int a = 2 * p, b = 2 * p + 1;
+        const bool ok = c[a] == c[b] && ((xw >> (8 * a)) & 0xFFu) == ((xw >> (8 * b)) & 0xFFu) && s[b] >= s[a] && s[b] > e[a];
+        if (!ok) { report_error(rv.err, q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS) / 2 + p, GTB_ERR_QUERY_REGION); c[a] = n_chrom; s[a] = 1; e[a] = 1; }
+        else e[a] = e[b];
+        c[b] = n_chrom; s[b] = 1; e[b] = 1;
+      }
+      general = 0;
+      if (xw & 0x00F900F9u) general = ((xw & 0xF9u) ? 1u : 0u) | ((xw & 0xF90000u) ? 4u : 0u);     // the strands of items 0 and 2 only
+#pragma unroll
+      for (int i = 0; i < DR_ITEMS; i += 2)
+        if (!(s[i] >= 1 && s[i] <= e[i])) general |= 1u << i;
     }
     // Position-sorted input, before any lookup: if the warp's 128 queries lie on one chromosome between two cells that share a
     // first slot, the later one free of evaluation points, no point lies anywhere among them -- per strand one reduction (or
@@ -343,17 +362,24 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
         if ((general >> i) & 1u)
-          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i, wt[i]);
+          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu),
+                               dv.pair_check == 2 ? q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i) / 2
+                                                  : q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i, wt[i]);
     }
   }
   // the last, partial tile: general path
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
-    for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
-      dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
-    if (COVERAGE && dv.pair_check)
-      for (int64_t p = n_full * (DR_TILE / 2) + threadIdx.x; p < n / 2; p += DR_THREADS)
-        dr_check_pair(rv, dv.region_admission, (uint32_t)q.chrom[2 * p], (uint32_t)q.chrom[2 * p + 1], (uint32_t)(uint8_t)q.strand[2 * p], (uint32_t)(uint8_t)q.strand[2 * p + 1],
-                      q.start[2 * p], q.stop[2 * p], q.start[2 * p + 1], q.stop[2 * p + 1], q.index_base + p);
+    if (dv.pair_check != 2)
+      for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
+        dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
+    if (dv.pair_check)
+      for (int64_t p = n_full * (DR_TILE / 2) + threadIdx.x; p < n / 2; p += DR_THREADS) {
+        const int32_t c0 = q.chrom[2 * p], c1 = q.chrom[2 * p + 1], s0 = q.start[2 * p], e0 = q.stop[2 * p], s1 = q.start[2 * p + 1], e1 = q.stop[2 * p + 1];
+        const uint32_t b0 = (uint32_t)(uint8_t)q.strand[2 * p], b1 = (uint32_t)(uint8_t)q.strand[2 * p + 1];
+        if (dv.pair_check == 1) { if (COVERAGE) dr_check_pair(rv, dv.region_admission, (uint32_t)c0, (uint32_t)c1, b0, b1, s0, e0, s1, e1, q.index_base + p); }
+        else if (!(c0 == c1 && b0 == b1 && s1 >= s0 && s1 > e0)) report_error(rv.err, q.index_base + p, GTB_ERR_QUERY_REGION);
+        else dr_general<COVERAGE>(rv, c0, s0, e1, (int)(int8_t)b0, q.index_base + p);
+      }
   }
   if (overflowed) atomicMax(dv.flag, dv.gen);
   if (COVERAGE && odd) { atomicAdd(dv.flag + 1, odd); if (odd_long) atomicAdd(dv.flag + 2, odd_long); }
@@ -520,7 +546,7 @@ bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
   return !ix->direct->off;
 }
 
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, bool pair_check) {
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
   gtb_ctx *ctx = ix->ctx;
   if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
   gtb_direct_state *ds = ix->direct;
@@ -549,7 +575,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, bool pair_check) {
   dv.n_cells = ds->n_cells; dv.n_words = ds->n_words; dv.cta_counts = ds->d_cta_counts.p; dv.delta = ds->d_delta.p; dv.flag = ds->d_flag.p;
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
-  dv.pair_check = pair_check ? 1 : 0; dv.region_admission = ix->sorted_rules ? 1 : 0;
+  dv.pair_check = pair_check; dv.region_admission = ix->sorted_rules ? 1 : 0;
   RankView rv_hist = rv;
   rv_hist.hist = ix->d_hist.p;
   const int64_t tiles = q.n_regions / DR_TILE;

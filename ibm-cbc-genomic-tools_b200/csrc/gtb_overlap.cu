@@ -626,14 +626,15 @@ static int accumulate_device(gtb_index *ix, const QueryView &q_in, bool batch_mu
     // Regions of k intervals each, no offsets sent.  Read pairs under coverage (k == 2, no -gaps, no weights, an index the DIRECT
     // engine serves): the engine takes the intervals as they lie and checks every pair in its registers -- what the reference
     // decides per region (well-formedness, :5698, :5709; the fatal span conditions, :5740-5741) costs no pass of its own.
-    const bool pairs = uniform_k == 2 && ix->op == GTB_OP_COVERAGE && !ix->match_gaps && !q.weight && !ix->flat_blocks &&
+    // Under -gaps (count or coverage) the engine takes each pair's span as the query, formed in its registers.
+    const bool pairs = uniform_k == 2 && (ix->match_gaps || ix->op == GTB_OP_COVERAGE) && !q.weight && !ix->flat_blocks &&
                        !(ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET)) && n_intervals >= (1 << 18) && !getenv("GTB_NO_MULTI_FAST");
     if (pairs) {
       QueryView flat = q;
       flat.n_regions = n_intervals; flat.weight = nullptr; flat.region_offset = nullptr; flat.interval_base = 0;
       if (gtb_direct_supported(ix, flat, false)) {
-        ix->flat_blocks = true;
-        const int rc = gtb_direct_accumulate(ix, flat, /*pair_check=*/true);
+        ix->flat_blocks = !ix->match_gaps;
+        const int rc = gtb_direct_accumulate(ix, flat, ix->match_gaps ? 2 : 1);
         ix->flat_blocks = false;
         if (rc != GTB_ERR_UNSUPPORTED) return rc;
       }

@@ -130,8 +130,9 @@ bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
 
 // ---- direct engine (gtb_direct.cu) ---------------------------------------------------------------
 int gtb_direct_prepare(gtb_index *ix);
-// pair_check: the batch is the flattened intervals of two-interval regions (coverage); every pair is checked as the reference checks a region
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, bool pair_check = false);
+// pair_check: the batch is the flattened intervals of two-interval regions.  1: the intervals are the queries (coverage), every pair
+// is checked as the reference checks a region.  2: the pairs' spans are the queries (-gaps)
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check = 0);
 void gtb_direct_destroy(gtb_index *ix);
 void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

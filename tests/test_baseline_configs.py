@@ -247,14 +247,15 @@ def test_config3_pairs_without_offsets(ctx, oracle, gtb):
         else:
             bad["chrom"][i] = bad["chrom"][i + 1] = regions["chrom"][0]
             bad["start"][i], bad["stop"][i], bad["start"][i + 1], bad["stop"][i + 1] = -90, -60, -40, -3
-        rc, _, ei = oracle.coverage(bad, regions, 0, qoff=off)
-        assert rc != 0 and ei == where
-        ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, 0)
-        ix.add_host(bad, per_region=2)
-        with pytest.raises(gtb.GtbError) as e:
-            ix.finish()
-        assert (e.value.code, e.value.index) == (rc, where), (kind, e.value.code, e.value.index, rc)
-        ix.close()
+        for flags in (0, gtb.MATCH_GAPS):                                  # the pairs checked next to their blocks / the spans formed in the engine
+            rc, _, ei = oracle.coverage(bad, regions, flags, qoff=off)
+            assert rc != 0 and ei == where
+            ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, flags)
+            ix.add_host(bad, per_region=2)
+            with pytest.raises(gtb.GtbError) as e:
+                ix.finish()
+            assert (e.value.code, e.value.index) == (rc, where), (kind, flags, e.value.code, e.value.index, rc)
+            ix.close()
 
 
 def test_config3_paired_density_cli(tmp_path):
