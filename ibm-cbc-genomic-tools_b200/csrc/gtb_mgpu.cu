@@ -98,7 +98,8 @@ extern "C" int gtb_mgpu_index_add_queries(gtb_mgpu_index *mi, const gtb_set *q) 
   if (!mi || !q) return GTB_ERR_ARG;
   if (q->n_regions < 0 || q->n_intervals < 0) return GTB_ERR_ARG;
   if (q->n_regions == 0) return GTB_OK;
-  if (!q->region_offset && q->n_regions != q->n_intervals) return GTB_ERR_ARG;
+  if (!q->region_offset && q->n_regions != q->n_intervals && q->n_intervals % q->n_regions != 0) return GTB_ERR_ARG;
+  const int64_t uniform_k = q->region_offset ? 0 : q->n_intervals / q->n_regions;      // regions of k intervals each, no offsets (gtb_set)
   const int n = (int)mi->ix.size();
   const int64_t base = mi->queries_seen;
   const int rc = each_device(mi->mg, [&](int k) {
@@ -109,7 +110,7 @@ extern "C" int gtb_mgpu_index_add_queries(gtb_mgpu_index *mi, const gtb_set *q) 
     if (r1 <= r0) return (int)GTB_OK;
     gtb_set s = *q;
     std::vector<int64_t> off;
-    int64_t i0 = r0, i1 = r1;
+    int64_t i0 = r0 * std::max<int64_t>(uniform_k, 1), i1 = r1 * std::max<int64_t>(uniform_k, 1);
     if (q->region_offset) {
       i0 = q->region_offset[r0]; i1 = q->region_offset[r1];
       off.resize((size_t)(r1 - r0) + 1);

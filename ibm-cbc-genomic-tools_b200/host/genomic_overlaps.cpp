@@ -50,6 +50,19 @@ static gtb_set as_set(const gt::RegionBatch &b) {
   return s;
 }
 
+// a streamed query batch: regions that all have the same number of intervals (read pairs) go without their offsets, which
+// spares the engine the pass that reads them (include/gtb200.h, gtb_set)
+static gtb_set as_query_set(const gt::RegionBatch &b) {
+  gtb_set s = as_set(b);
+  if (s.region_offset && s.n_regions > 0 && s.n_intervals % s.n_regions == 0) {
+    const int64_t k = s.n_intervals / s.n_regions;
+    bool uniform = k >= 2;
+    for (int64_t r = 1; uniform && r < s.n_regions; r++) uniform = b.offset[r] == r * k;
+    if (uniform) s.region_offset = nullptr;
+  }
+  return s;
+}
+
 // CUDA context creation off the main thread (see gt_host.h: exit_hook)
 static std::thread g_ctx_thread;
 static gtb_ctx *g_ctx = nullptr;
@@ -299,7 +312,7 @@ int main(int argc, char *argv[]) {
             gt::die_line(b.line(k), std::string("query regions are not sorted (sorted-by-strand = ") + (SORTED_BY_STRAND ? "true" : "false") + ")!");
           advance_index(b.chrom[i], (char)b.strand[i], b.start[i], b.stop[b.offset[k + 1] - 1]);
         }
-      gtb_set qs = as_set(b);
+      gtb_set qs = as_query_set(b);
       if (multi_gpu) mcheck(gtb_mgpu_index_add_queries(mindex, &qs), "gtb_mgpu_index_add_queries");   // (the copies have left the buffer on return)
       else check(ctx, gtb_index_add_queries(index, &qs, GTB_MEM_HOST), "gtb_index_add_queries");
       if (seen == 0) first_query_line = b.first_line;

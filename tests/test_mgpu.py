@@ -86,6 +86,24 @@ def test_mgpu_multi_interval_weights_and_errors(gtb, oracle):
         mg.close()
 
 
+def test_mgpu_pairs_without_offsets(gtb, oracle):
+    """regions of two intervals each, handed over without offsets: every device takes a slice of whole pairs"""
+    import test_baseline_configs as bc
+    pairs, off = bc.synth_pairs(700_001, seed=79)
+    regions = support.synth_regions(5_000, seed=80)
+    for devices in device_lists():
+        mg = gtb.MultiGpu(devices)
+        for flags in (0, gtb.MATCH_GAPS):
+            rc, want, _ = oracle.coverage(pairs, regions, flags, qoff=off)
+            assert rc == 0
+            ix = gtb.MultiIndex(mg, regions, gtb.OP_COVERAGE, flags)
+            st, keep = gtb.host_set(pairs, per_region=2)
+            ix.add_set(st)
+            assert np.array_equal(ix.finish(), want), (devices, flags)
+            ix.close()
+        mg.close()
+
+
 def test_mgpu_packed_reads(gtb, oracle):
     n = 2_000_003
     reads = support.synth_reads(n, seed=76, read_len=36)
