@@ -98,7 +98,7 @@ extern "C" int gtb_mgpu_index_add_queries(gtb_mgpu_index *mi, const gtb_set *q) 
   if (!mi || !q) return GTB_ERR_ARG;
   if (q->n_regions < 0 || q->n_intervals < 0) return GTB_ERR_ARG;
   if (q->n_regions == 0) return GTB_OK;
-  if (!q->region_offset && q->n_regions != q->n_intervals && q->n_intervals % q->n_regions != 0) return GTB_ERR_ARG;
+  if (!q->region_offset && q->n_regions != q->n_intervals && (q->n_intervals % q->n_regions != 0 || q->n_intervals < 2 * q->n_regions)) return GTB_ERR_ARG;
   const int64_t uniform_k = q->region_offset ? 0 : q->n_intervals / q->n_regions;      // regions of k intervals each, no offsets (gtb_set)
   const int n = (int)mi->ix.size();
   const int64_t base = mi->queries_seen;

@@ -689,8 +689,8 @@ extern "C" int gtb_index_add_queries(gtb_index *ix, const gtb_set *queries, unsi
   // regions of k >= 2 intervals each need no offsets: region r is intervals [r * k, (r + 1) * k)
   int uniform_k = 0;
   if (!queries->region_offset && queries->n_regions != queries->n_intervals) {
-    if (queries->n_intervals % queries->n_regions != 0 || queries->n_intervals / queries->n_regions > (1 << 20))
-      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_intervals is not a multiple of n_regions");
+    if (queries->n_intervals % queries->n_regions != 0 || queries->n_intervals / queries->n_regions < 2 || queries->n_intervals / queries->n_regions > (1 << 20))
+      return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_intervals is not a multiple (2 or more) of n_regions");
     uniform_k = (int)(queries->n_intervals / queries->n_regions);
   }
   if (!queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null interval arrays");

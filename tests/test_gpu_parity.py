@@ -254,6 +254,20 @@ def test_fatal_conditions(gtb, ctx, oracle):
     assert (e.value.code, e.value.index) == (5, 0)
 
 
+def test_set_shape_arguments(gtb, ctx):
+    """a query set without offsets is one interval per region, or k >= 2 per region: anything else is an argument error"""
+    import ctypes
+    idx = {"chrom": [0], "start": [1], "stop": [10], "strand": [43]}
+    ix = gtb.Index(ctx, idx, gtb.OP_COUNT, 0)
+    q = {"chrom": [0] * 6, "start": [1, 2, 3, 4, 5, 6], "stop": [3, 4, 5, 6, 7, 8], "strand": [43] * 6}
+    st, keep = gtb.host_set(q)
+    for n_regions, ok in ((6, True), (3, True), (2, True), (4, False), (5, False), (7, False)):
+        st.n_regions = n_regions
+        rc = gtb.lib().gtb_index_add_queries(ix._h, ctypes.byref(st), gtb.MEM_HOST)
+        assert (rc == 0) == ok, (n_regions, rc)
+    ix.close()
+
+
 def test_empty_inputs(ctx):
     empty = {"chrom": [], "start": [], "stop": [], "strand": []}
     idx = {"chrom": [0], "start": [1], "stop": [10], "strand": [43]}
