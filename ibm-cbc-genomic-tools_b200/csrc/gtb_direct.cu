@@ -60,7 +60,12 @@ struct DirectView {
   uint32_t n_cells;                 // entries of `cells` (bounds checks)
   int pair_check;                   // queries 2p and 2p + 1 are the two intervals of region p.  1 (COVERAGE): counted as they lie, the pair checked as
                                     // a region.  2 (-gaps): the pair's span [first start, second stop] is the query
+                                    // 3 (count without -gaps): as 2 for a pair whose span holds no evaluation point -- every region that overlaps the
+                                    // span then overlaps both mates -- and the pair itself onto the exception list otherwise
   int region_admission;             // ... under these admission rules (0: the default engine's, 1: the Sorted class's)
+  uint32_t *ex_count;               // pair_check == 3: pairs the candidate-enumeration engine has to look at (two entries each in the arrays)
+  int32_t *ex_chrom, *ex_start, *ex_stop;
+  int8_t *ex_strand;
 };
 constexpr uint32_t DR_GENERAL = 1u << 24, DR_NOTHING = 1u << 25, DR_SCAN = 1u << 26;
 
@@ -134,6 +139,21 @@ __device__ __forceinline__ void dr_check_pair(const RankView &rv, int admission,
     report_error(rv.err, region, admission == 1 || e1 > 0 ? GTB_ERR_QUERY_START_GT_STOP : GTB_ERR_QUERY_STOP_NONPOSITIVE);
 }
 
+// pair_check == 3: a read pair for the exception list
+__device__ __forceinline__ void dr_append_pair(const DirectView &dv, int32_t c, int32_t s1, int32_t e1, int32_t s2, int32_t e2, int sbyte) {
+  const uint32_t k = atomicAdd(dv.ex_count, 1u);                        // (room for every pair of the batch: cannot overflow)
+  dv.ex_chrom[2 * k] = c; dv.ex_chrom[2 * k + 1] = c;
+  dv.ex_start[2 * k] = s1; dv.ex_stop[2 * k] = e1; dv.ex_start[2 * k + 1] = s2; dv.ex_stop[2 * k + 1] = e2;
+  dv.ex_strand[2 * k] = (int8_t)sbyte; dv.ex_strand[2 * k + 1] = (int8_t)sbyte;
+}
+// ... after the checks the general path makes for the pair's span (dr_general above, without its rank step)
+__device__ __noinline__ void dr_general_pair(const RankView &rv, const DirectView &dv, int32_t c, int32_t s1, int32_t e1, int32_t s2, int32_t e2, int sbyte, int64_t index) {
+  if ((uint32_t)c >= (uint32_t)rv.n_chrom || !rv.chrom_present[c]) return;
+  if (!admit_interval(rv, s1, e2, index)) return;
+  if (rv.class_of[(uint8_t)sbyte] < 0) return;
+  dr_append_pair(dv, c, s1, e1, s2, e2, sbyte);
+}
+
 // The 13 bytes per query come as 128-bit loads straight into registers, one tile ahead of the tile being counted, so that
 // 4 096 gathers per SM are in flight.  Staging the input through a TMA ring in shared memory instead was measured and lost:
 // next to 120 KB of counters the ring leaves the L1 too small to track the gathers' misses (1.85 SM-cycles per gather with
@@ -205,8 +225,8 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
         dr_check_pair(rv, dv.region_admission, c[0], c[1], stw & 0xFFu, (stw >> 8) & 0xFFu, s[0], e[0], s[1], e[1], region);
         dr_check_pair(rv, dv.region_admission, c[2], c[3], (stw >> 16) & 0xFFu, stw >> 24, s[2], e[2], s[3], e[3], region + 1);
       }
-    } else if (dv.pair_check == 2) {
-      // -gaps: items 0 and 2 become the spans of their pairs, items 1 and 3 queries on a chromosome nobody has (nothing to count,
+    } else if (dv.pair_check >= 2) {
+      // -gaps (and count without it, see DirectView): items 0 and 2 become the spans of their pairs, items 1 and 3 queries on a chromosome nobody has (nothing to count,
       // nothing to object to); a malformed pair is reported and counts nothing either
 #pragma unroll
       for (int p = 0; p < 2; p++) {
@@ -348,6 +368,8 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
         } else if (jS[i] == jE[i]) {                                   // a query of another length (COVERAGE) or of a weight the bytes cannot take
           dr_red64(dv.delta + jS[i], COVERAGE ? w * (ull)((int64_t)e[i] - (int64_t)s[i] + 1) : w);
           if (COVERAGE && (uint32_t)(e[i] - s[i]) != len0m1) { odd++; odd_long += (uint32_t)(e[i] - s[i]) >= 255u ? 1u : 0u; }
+        } else if (!COVERAGE && !WEIGHTED && dv.pair_check == 3) {      // an evaluation point inside the pair's span: the exact engine decides
+          dr_append_pair(dv, (int32_t)c[i], s[i], i == 0 ? (int)ce.x : (int)ce.z, i == 0 ? (int)cs.y : (int)cs.w, e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu));
         } else {
           dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], w);
           dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], w);
@@ -361,15 +383,19 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     if (general) {
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
-        if ((general >> i) & 1u)
-          dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu),
-                               dv.pair_check == 2 ? q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i) / 2
-                                                  : q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i, wt[i]);
+        if ((general >> i) & 1u) {
+          const int64_t index = dv.pair_check >= 2 ? q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i) / 2
+                                                   : q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i;
+          if (!COVERAGE && !WEIGHTED && dv.pair_check == 3)
+            dr_general_pair(rv, dv, (int32_t)c[i], s[i], i == 0 ? (int)ce.x : (int)ce.z, i == 0 ? (int)cs.y : (int)cs.w, e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), index);
+          else
+            dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), index, wt[i]);
+        }
     }
   }
   // the last, partial tile: general path
   if ((int64_t)blockIdx.x == n_full % gridDim.x) {
-    if (dv.pair_check != 2)
+    if (dv.pair_check < 2)
       for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
         dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
     if (dv.pair_check)
@@ -378,6 +404,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
         const uint32_t b0 = (uint32_t)(uint8_t)q.strand[2 * p], b1 = (uint32_t)(uint8_t)q.strand[2 * p + 1];
         if (dv.pair_check == 1) { if (COVERAGE) dr_check_pair(rv, dv.region_admission, (uint32_t)c0, (uint32_t)c1, b0, b1, s0, e0, s1, e1, q.index_base + p); }
         else if (!(c0 == c1 && b0 == b1 && s1 >= s0 && s1 > e0)) report_error(rv.err, q.index_base + p, GTB_ERR_QUERY_REGION);
+        else if (dv.pair_check == 3) dr_general_pair(rv, dv, c0, s0, e0, s1, e1, (int)(int8_t)b0, q.index_base + p);
         else dr_general<COVERAGE>(rv, c0, s0, e1, (int)(int8_t)b0, q.index_base + p);
       }
   }
@@ -393,6 +420,8 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 // query through the general path straight into the histogram planes (nothing else touches those in that case).
 template <bool COVERAGE>
 __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, QueryView q, RankView rv_hist, int64_t n_slots, unsigned rows) {
+  // (pair_check >= 2: the queries are spans of pairs, not the intervals of q -- a discarded batch is not replayed here, the host
+  // sends it down the general path)
   // a block = 32 counter words x 8 groups of rows: each thread sums its share of the rows of one word (coalesced across the warp),
   // shared memory joins the eight partial sums, the first warp updates the planes
   __shared__ uint32_t s_part[8][32][4];
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(256) direct_commit_kernel(DirectView dv, Query
       }
     }
   }
-  if (!discard) return;
+  if (!discard || dv.pair_check >= 2) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride)
     dr_general<COVERAGE>(rv_hist, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, q.weight ? (int64_t)q.weight[r] : 1);
@@ -451,6 +480,11 @@ struct gtb_direct_state {
   dbuf<ull> d_delta;
   int64_t queries_since_check = 0, queries_in_check = 0;            // queries since the last flag copy was issued / covered by the copy in flight
   uint32_t gen = 0, odd_seen = 0, long_seen = 0;
+  dbuf<int32_t> ex_chrom, ex_start, ex_stop;                           // pair_check == 3: the exception list (gtb_direct_exceptions)
+  dbuf<int8_t> ex_strand;
+  dbuf<uint32_t> ex_count;
+  uint32_t *h_sync = nullptr;                                          // pinned: [0] flag word, [1] exception count of a pair batch
+  int64_t n_exceptions = 0;
   uint32_t *h_flag = nullptr;                                          // pinned: where the flag words land
   cudaEvent_t flag_copied = nullptr;
   bool check_pending = false;
@@ -563,6 +597,7 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
     const uint32_t odd_new = ds->h_flag[1] - ds->odd_seen, long_new = ds->h_flag[2] - ds->long_seen;
     if ((int64_t)odd_new > ds->queries_in_check / 16 && (int64_t)long_new * 2 < (int64_t)odd_new) ds->off = ds->off_lengths = true;
     ds->odd_seen = ds->h_flag[1]; ds->long_seen = ds->h_flag[2];
+    if (ds->off && pair_check >= 2) return GTB_ERR_UNSUPPORTED;                                 // spans of pairs: the caller's general path
     if (ds->off && gtb_bucket_supported(ix, q, false)) return gtb_bucket_accumulate(ix, q);   // (else this batch still goes here: slow, not wrong)
     if (ds->off && q.weight) return GTB_ERR_UNSUPPORTED;                                       // weighted: the caller's general rank step
   }
@@ -576,6 +611,16 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
   dv.pair_check = pair_check; dv.region_admission = ix->sorted_rules ? 1 : 0;
+  dv.ex_count = nullptr; dv.ex_chrom = dv.ex_start = dv.ex_stop = nullptr; dv.ex_strand = nullptr;
+  ds->n_exceptions = 0;
+  if (pair_check >= 2 && !ds->h_sync) GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&ds->h_sync, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  if (pair_check == 3) {
+    const size_t cap = (size_t)q.n_regions + 2;                         // two entries per pair, room for every pair
+    GTB_TRY(ds->ex_chrom.reserve(ctx, cap)); GTB_TRY(ds->ex_start.reserve(ctx, cap)); GTB_TRY(ds->ex_stop.reserve(ctx, cap)); GTB_TRY(ds->ex_strand.reserve(ctx, cap));
+    GTB_TRY(ds->ex_count.reserve(ctx, 1));
+    GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->ex_count.p, 0, sizeof(uint32_t), ctx->stream));
+    dv.ex_count = ds->ex_count.p; dv.ex_chrom = ds->ex_chrom.p; dv.ex_start = ds->ex_start.p; dv.ex_stop = ds->ex_stop.p; dv.ex_strand = ds->ex_strand.p;
+  }
   RankView rv_hist = rv;
   rv_hist.hist = ix->d_hist.p;
   const int64_t tiles = q.n_regions / DR_TILE;
@@ -593,6 +638,15 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
     if (q.weight) GTB_DIRECT_LAUNCH(false, true, "direct_count_weighted"); else GTB_DIRECT_LAUNCH(false, false, "direct_count");
   }
 #undef GTB_DIRECT_LAUNCH
+  if (pair_check >= 2) {
+    // The queries were spans formed in the kernel, so a batch whose byte counters overflowed could not be replayed there (the
+    // commit kernel has dropped it): the host has to know now.  One wait per batch; the exception count comes with it.
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_sync, ds->d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_check == 3) GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_sync + 1, ds->ex_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ds->h_sync[0] == ds->gen) { ds->off = true; return GTB_ERR_UNSUPPORTED; }       // nothing of this batch has reached the planes
+    if (pair_check == 3) ds->n_exceptions = (int64_t)ds->h_sync[1];
+  }
   ds->queries_since_check += q.n_regions;
   if (!ds->check_pending) {
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_flag, ds->d_flag.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -614,9 +668,20 @@ void gtb_direct_reset(gtb_index *ix) {
   ds->queries_since_check = 0;
 }
 
+// pair_check == 3: the pairs of the last batch that the candidate-enumeration engine has to count (two intervals each, no offsets)
+int64_t gtb_direct_exceptions(gtb_index *ix, QueryView *out) {
+  gtb_direct_state *ds = ix->direct;
+  if (!ds || ds->n_exceptions == 0) return 0;
+  out->n_regions = ds->n_exceptions; out->chrom = ds->ex_chrom.p; out->start = ds->ex_start.p; out->stop = ds->ex_stop.p; out->strand = ds->ex_strand.p;
+  out->weight = nullptr; out->region_offset = nullptr; out->interval_base = 0;
+  return ds->n_exceptions;
+}
+
 void gtb_direct_destroy(gtb_index *ix) {
   gtb_direct_state *ds = ix->direct;
   if (!ds) return;
+  ds->ex_chrom.release(); ds->ex_start.release(); ds->ex_stop.release(); ds->ex_strand.release(); ds->ex_count.release();
+  if (ds->h_sync) cudaFreeHost(ds->h_sync);
   ds->d_cells.release(); ds->d_cta_counts.release(); ds->d_flag.release(); ds->d_delta.release();
   if (ds->h_flag) cudaFreeHost(ds->h_flag);
   if (ds->flag_copied) cudaEventDestroy(ds->flag_copied);

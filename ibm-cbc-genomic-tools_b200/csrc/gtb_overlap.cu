@@ -626,16 +626,33 @@ static int accumulate_device(gtb_index *ix, const QueryView &q_in, bool batch_mu
     // Regions of k intervals each, no offsets sent.  Read pairs under coverage (k == 2, no -gaps, no weights, an index the DIRECT
     // engine serves): the engine takes the intervals as they lie and checks every pair in its registers -- what the reference
     // decides per region (well-formedness, :5698, :5709; the fatal span conditions, :5740-5741) costs no pass of its own.
-    // Under -gaps (count or coverage) the engine takes each pair's span as the query, formed in its registers.
-    const bool pairs = uniform_k == 2 && (ix->match_gaps || ix->op == GTB_OP_COVERAGE) && !q.weight && !ix->flat_blocks &&
+    // Under -gaps (count or coverage) the engine takes each pair's span as the query, formed in its registers.  Count without
+    // -gaps against single-interval index regions: a region counts a pair once if either mate overlaps it, which differs from
+    // the span's count only for regions strictly inside the gap -- a pair whose span holds no evaluation point has none, the
+    // other pairs (a percent or two) go to the candidate-enumeration engine afterwards.
+    const bool count_no_gaps = ix->op == GTB_OP_COUNT && !ix->match_gaps;
+    const bool pairs = uniform_k == 2 && (ix->match_gaps || ix->op == GTB_OP_COVERAGE || !ix->index_multi) && !q.weight && !ix->flat_blocks &&
                        !(ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET)) && n_intervals >= (1 << 18) && !getenv("GTB_NO_MULTI_FAST");
     if (pairs) {
       QueryView flat = q;
       flat.n_regions = n_intervals; flat.weight = nullptr; flat.region_offset = nullptr; flat.interval_base = 0;
       if (gtb_direct_supported(ix, flat, false)) {
-        ix->flat_blocks = !ix->match_gaps;
-        const int rc = gtb_direct_accumulate(ix, flat, ix->match_gaps ? 2 : 1);
+        const int mode = ix->match_gaps ? 2 : count_no_gaps ? 3 : 1;
+        ix->flat_blocks = mode == 1;
+        const int rc = gtb_direct_accumulate(ix, flat, mode);
         ix->flat_blocks = false;
+        if (rc == GTB_OK && mode == 3) {
+          QueryView ex = q;
+          const int64_t n_ex = gtb_direct_exceptions(ix, &ex);
+          if (n_ex > 0) {
+            ex.index_base = q.index_base;                                // (these pairs have passed every check: nothing to report)
+            GTB_TRY(ix->uni_off.reserve(ctx, (size_t)n_ex + 1));
+            GTB_LAUNCH(ctx, "uniform_offsets", uniform_offsets_kernel, gtb_grid_for(n_ex + 1, 256, (int64_t)ctx->sm_count * 8), 256, 0, n_ex, (int64_t)2, (int64_t)0, ix->uni_off.p);
+            GTB_TRY(gtb_check_launch(ctx));
+            ex.region_offset = ix->uni_off.p;
+            return accumulate_device(ix, ex, true, 2 * n_ex, 0);
+          }
+        }
         if (rc != GTB_ERR_UNSUPPORTED) return rc;
       }
     }

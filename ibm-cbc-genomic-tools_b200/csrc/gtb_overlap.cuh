@@ -132,7 +132,11 @@ bool gtb_bucket_supported(gtb_index *ix, const QueryView &q, bool batch_multi);
 int gtb_direct_prepare(gtb_index *ix);
 // pair_check: the batch is the flattened intervals of two-interval regions.  1: the intervals are the queries (coverage), every pair
 // is checked as the reference checks a region.  2: the pairs' spans are the queries (-gaps)
+//   3: count without -gaps -- spans that hold no evaluation point are counted, the other pairs are left on a list
+//   (gtb_direct_exceptions) for the enumeration engine.  GTB_ERR_UNSUPPORTED from modes 2 and 3: nothing of the batch has been
+//   counted, the caller takes its general path
 int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check = 0);
+int64_t gtb_direct_exceptions(gtb_index *ix, QueryView *out);
 void gtb_direct_destroy(gtb_index *ix);
 void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

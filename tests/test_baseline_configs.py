@@ -236,6 +236,22 @@ def test_config3_pairs_without_offsets(ctx, oracle, gtb):
             ix.add_device({k: v[cut:] for k, v in dev.items()}, per_region=2)
             assert np.array_equal(ix.finish(), want), ("device", op, flags)
             ix.close()
+    # count WITHOUT -gaps: a region counts a pair once if either mate overlaps it.  Against short regions (20-600 bp, many of them
+    # inside the 100-400 bp gaps of the pairs) the pairs whose span holds an evaluation point go to the enumeration engine, the rest
+    # are counted as spans in the one pass
+    short = support.synth_regions(80_000, 33, 20, 600)
+    for flags in (0, gtb.IGNORE_STRAND):
+        rc, want, _ = oracle.count(pairs, short, flags, qoff=off)
+        rc2, with_gaps, _ = oracle.count(pairs, short, flags | gtb.MATCH_GAPS, qoff=off)
+        assert rc == 0 and rc2 == 0 and not np.array_equal(want, with_gaps)               # (the two semantics do differ on this input)
+        ix = gtb.Index(ctx, short, gtb.OP_COUNT, flags)
+        ix.add_host(pairs, per_region=2)
+        assert np.array_equal(ix.finish(), want), ("count, host", flags)
+        ix.reset()
+        ix.add_device({k: v[:cut] for k, v in dev.items()}, per_region=2)
+        ix.add_device({k: v[cut:] for k, v in dev.items()}, per_region=2)
+        assert np.array_equal(ix.finish(), want), ("count, device", flags)
+        ix.close()
     # a malformed pair (mates overlap), a pair on two chromosomes, and a pair whose span ends at or before 0 on an indexed chromosome
     for where, kind in ((2_000_123, "overlap"), (2_999_999, "chrom"), (777, "stop")):
         bad = {k: v.copy() for k, v in pairs.items()}
@@ -247,15 +263,43 @@ def test_config3_pairs_without_offsets(ctx, oracle, gtb):
         else:
             bad["chrom"][i] = bad["chrom"][i + 1] = regions["chrom"][0]
             bad["start"][i], bad["stop"][i], bad["start"][i + 1], bad["stop"][i + 1] = -90, -60, -40, -3
-        for flags in (0, gtb.MATCH_GAPS):                                  # the pairs checked next to their blocks / the spans formed in the engine
-            rc, _, ei = oracle.coverage(bad, regions, flags, qoff=off)
+        for op, fn, flags in ((gtb.OP_COVERAGE, oracle.coverage, 0), (gtb.OP_COVERAGE, oracle.coverage, gtb.MATCH_GAPS), (gtb.OP_COUNT, oracle.count, 0)):
+            rc, _, ei = fn(bad, regions, flags, qoff=off)                  # the pairs checked next to their blocks / the spans formed in the engine
             assert rc != 0 and ei == where
-            ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, flags)
+            ix = gtb.Index(ctx, regions, op, flags)
             ix.add_host(bad, per_region=2)
             with pytest.raises(gtb.GtbError) as e:
                 ix.finish()
-            assert (e.value.code, e.value.index) == (rc, where), (kind, flags, e.value.code, e.value.index, rc)
+            assert (e.value.code, e.value.index) == (rc, where), (kind, op, flags, e.value.code, e.value.index, rc)
             ix.close()
+
+
+def test_pairs_without_offsets_skewed(ctx, oracle, gtb):
+    """most pairs piled onto four loci, in random order: byte counters overflow before their spills land, the batch is dropped
+    by the engine (its queries were spans formed in registers: no replay there) and goes down the general path -- or it is
+    not, depending on timing; exact either way"""
+    pairs, off = synth_pairs(1_500_000, seed=16)
+    rng = np.random.default_rng(17)
+    n = len(off) - 1
+    hot = rng.random(n) < 0.9
+    loc = (1_000_000 + rng.integers(0, 4, n) * 37).astype(np.int32)
+    for m in (0, 1):
+        pairs["chrom"][m::2][hot] = 2
+    pairs["start"][0::2][hot] = loc[hot]; pairs["stop"][0::2][hot] = loc[hot] + 49
+    pairs["start"][1::2][hot] = loc[hot] + 250; pairs["stop"][1::2][hot] = loc[hot] + 299
+    regions = support.synth_regions(3_000, seed=32)
+    short = support.synth_regions(3_000, 34, 20, 600)
+    short["chrom"][:200] = 2; short["start"][:200] = (1_000_000 + np.arange(200) * 3).astype(np.int32); short["stop"][:200] = short["start"][:200] + 60
+    for op, fn, flags, idx in ((gtb.OP_COVERAGE, oracle.coverage, gtb.MATCH_GAPS, regions), (gtb.OP_COUNT, oracle.count, gtb.MATCH_GAPS, regions),
+                               (gtb.OP_COUNT, oracle.count, 0, short), (gtb.OP_COVERAGE, oracle.coverage, 0, regions)):
+        rc, want, _ = fn(pairs, idx, flags, qoff=off)
+        assert rc == 0
+        ix = gtb.Index(ctx, idx, op, flags)
+        for rep in range(2):
+            ix.reset()
+            ix.add_host(pairs, per_region=2)
+            assert np.array_equal(ix.finish(), want), (op, flags, rep)
+        ix.close()
 
 
 def test_config3_paired_density_cli(tmp_path):
