@@ -62,7 +62,11 @@ struct DirectView {
                                     // a region.  2 (-gaps): the pair's span [first start, second stop] is the query
                                     // 3 (count without -gaps): as 2 for a pair whose span holds no evaluation point -- every region that overlaps the
                                     // span then overlaps both mates -- and the pair itself onto the exception list otherwise
+                                    // 4 (count without -gaps, regions of any shape): the queries ARE spans already (written by region_prepass_kernel,
+                                    // one per region); a multi-interval region whose span holds an evaluation point goes onto the exception list by its
+                                    // number (in ex_chrom), everything else is counted as the span it is
   int region_admission;             // ... under these admission rules (0: the default engine's, 1: the Sorted class's)
+  const int64_t *q_off;             // pair_check == 4: the batch's region offsets (region r has q_off[r + 1] - q_off[r] intervals)
   uint32_t *ex_count;               // pair_check == 3: pairs the candidate-enumeration engine has to look at (two entries each in the arrays)
   int32_t *ex_chrom, *ex_start, *ex_stop;
   int8_t *ex_strand;
@@ -154,6 +158,17 @@ __device__ __noinline__ void dr_general_pair(const RankView &rv, const DirectVie
   dr_append_pair(dv, c, s1, e1, s2, e2, sbyte);
 }
 
+// pair_check == 4: the general path for the span of region r -- a multi-interval region is left to the exact engine once it
+// has passed the checks, a single-interval one is its span
+template <bool COVERAGE>
+__device__ __noinline__ void dr_general_span(const RankView &rv, const DirectView &dv, int32_t c, int32_t qs, int32_t qe, int sbyte, int64_t index, int64_t r) {
+  if (dv.q_off[r + 1] - dv.q_off[r] <= 1) { dr_general<COVERAGE>(rv, c, qs, qe, sbyte, index); return; }
+  if ((uint32_t)c >= (uint32_t)rv.n_chrom || !rv.chrom_present[c]) return;
+  if (!admit_interval(rv, qs, qe, index)) return;
+  if (rv.class_of[(uint8_t)sbyte] < 0) return;
+  dv.ex_chrom[atomicAdd(dv.ex_count, 1u)] = (int32_t)r;
+}
+
 // The 13 bytes per query come as 128-bit loads straight into registers, one tile ahead of the tile being counted, so that
 // 4 096 gathers per SM are in flight.  Staging the input through a TMA ring in shared memory instead was measured and lost:
 // next to 120 KB of counters the ring leaves the L1 too small to track the gathers' misses (1.85 SM-cycles per gather with
@@ -225,7 +240,7 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
         dr_check_pair(rv, dv.region_admission, c[0], c[1], stw & 0xFFu, (stw >> 8) & 0xFFu, s[0], e[0], s[1], e[1], region);
         dr_check_pair(rv, dv.region_admission, c[2], c[3], (stw >> 16) & 0xFFu, stw >> 24, s[2], e[2], s[3], e[3], region + 1);
       }
-    } else if (dv.pair_check >= 2) {
+    } else if (dv.pair_check == 2 || dv.pair_check == 3) {
       // -gaps (and count without it, see DirectView): items 0 and 2 become the spans of their pairs, items 1 and 3 queries on a chromosome nobody has (nothing to count,
       // nothing to object to); a malformed pair is reported and counts nothing either
 #pragma unroll
@@ -370,6 +385,9 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
           if (COVERAGE && (uint32_t)(e[i] - s[i]) != len0m1) { odd++; odd_long += (uint32_t)(e[i] - s[i]) >= 255u ? 1u : 0u; }
         } else if (!COVERAGE && !WEIGHTED && dv.pair_check == 3) {      // an evaluation point inside the pair's span: the exact engine decides
           dr_append_pair(dv, (int32_t)c[i], s[i], i == 0 ? (int)ce.x : (int)ce.z, i == 0 ? (int)cs.y : (int)cs.w, e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu));
+        } else if (!COVERAGE && !WEIGHTED && dv.pair_check == 4 &&
+                   dv.q_off[tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i + 1] - dv.q_off[tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i] > 1) {
+          dv.ex_chrom[atomicAdd(dv.ex_count, 1u)] = (int32_t)(tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i);     // ... for a region of several blocks
         } else {
           dr_red64(dv.delta + (ull)H_SCNT * (ull)rv.n_slots + jS[i], w);
           dr_red64(dv.delta + (ull)H_ECNT * (ull)rv.n_slots + jE[i], w);
@@ -384,9 +402,11 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < DR_ITEMS; i++)
         if ((general >> i) & 1u) {
-          const int64_t index = dv.pair_check >= 2 ? q.index_base + (tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i) / 2
-                                                   : q.index_base + tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i;
-          if (!COVERAGE && !WEIGHTED && dv.pair_check == 3)
+          const int64_t item = tile * DR_TILE + (int64_t)threadIdx.x * DR_ITEMS + i;
+          const int64_t index = q.index_base + (dv.pair_check == 2 || dv.pair_check == 3 ? item / 2 : item);
+          if (!COVERAGE && !WEIGHTED && dv.pair_check == 4)
+            dr_general_span<COVERAGE>(rv, dv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), index, item);
+          else if (!COVERAGE && !WEIGHTED && dv.pair_check == 3)
             dr_general_pair(rv, dv, (int32_t)c[i], s[i], i == 0 ? (int)ce.x : (int)ce.z, i == 0 ? (int)cs.y : (int)cs.w, e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), index);
           else
             dr_general<COVERAGE>(rv, (int32_t)c[i], s[i], e[i], (int)(int8_t)((stw >> (8 * i)) & 0xFFu), index, wt[i]);
@@ -398,7 +418,10 @@ __global__ void __launch_bounds__(DR_THREADS, 1) direct_count_kernel(const __gri
     if (dv.pair_check < 2)
       for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
         dr_general<COVERAGE>(rv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, WEIGHTED ? (int64_t)q.weight[r] : 1);
-    if (dv.pair_check)
+    if (dv.pair_check == 4)
+      for (int64_t r = n_full * DR_TILE + threadIdx.x; r < n; r += DR_THREADS)
+        dr_general_span<COVERAGE>(rv, dv, q.chrom[r], q.start[r], q.stop[r], (int)q.strand[r], q.index_base + r, r);
+    if (dv.pair_check >= 1 && dv.pair_check <= 3)
       for (int64_t p = n_full * (DR_TILE / 2) + threadIdx.x; p < n / 2; p += DR_THREADS) {
         const int32_t c0 = q.chrom[2 * p], c1 = q.chrom[2 * p + 1], s0 = q.start[2 * p], e0 = q.stop[2 * p], s1 = q.start[2 * p + 1], e1 = q.stop[2 * p + 1];
         const uint32_t b0 = (uint32_t)(uint8_t)q.strand[2 * p], b1 = (uint32_t)(uint8_t)q.strand[2 * p + 1];
@@ -580,7 +603,7 @@ bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi) {
   return !ix->direct->off;
 }
 
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check, const int64_t *region_offsets) {
   gtb_ctx *ctx = ix->ctx;
   if (gtb_direct_prepare(ix) != GTB_OK) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "direct engine cannot serve this index");
   gtb_direct_state *ds = ix->direct;
@@ -611,9 +634,16 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
   if (++ds->gen == 0) ds->gen = 1;                                      // (a wrap after 2^32 batches could only cost a spurious replay)
   dv.gen = ds->gen;
   dv.pair_check = pair_check; dv.region_admission = ix->sorted_rules ? 1 : 0;
-  dv.ex_count = nullptr; dv.ex_chrom = dv.ex_start = dv.ex_stop = nullptr; dv.ex_strand = nullptr;
+  dv.ex_count = nullptr; dv.ex_chrom = dv.ex_start = dv.ex_stop = nullptr; dv.ex_strand = nullptr; dv.q_off = region_offsets;
   ds->n_exceptions = 0;
   if (pair_check >= 2 && !ds->h_sync) GTB_CUDA_OK(ctx, cudaHostAlloc((void **)&ds->h_sync, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  if (pair_check == 4 && !region_offsets) return gtb_fail(ctx, GTB_ERR_ARG, "direct engine: region offsets missing");
+  if (pair_check == 4) {
+    GTB_TRY(ds->ex_chrom.reserve(ctx, (size_t)q.n_regions + 2));        // region numbers, room for every region
+    GTB_TRY(ds->ex_count.reserve(ctx, 1));
+    GTB_CUDA_OK(ctx, cudaMemsetAsync(ds->ex_count.p, 0, sizeof(uint32_t), ctx->stream));
+    dv.ex_count = ds->ex_count.p; dv.ex_chrom = ds->ex_chrom.p;
+  }
   if (pair_check == 3) {
     const size_t cap = (size_t)q.n_regions + 2;                         // two entries per pair, room for every pair
     GTB_TRY(ds->ex_chrom.reserve(ctx, cap)); GTB_TRY(ds->ex_start.reserve(ctx, cap)); GTB_TRY(ds->ex_stop.reserve(ctx, cap)); GTB_TRY(ds->ex_strand.reserve(ctx, cap));
@@ -642,10 +672,10 @@ int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check) {
     // The queries were spans formed in the kernel, so a batch whose byte counters overflowed could not be replayed there (the
     // commit kernel has dropped it): the host has to know now.  One wait per batch; the exception count comes with it.
     GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_sync, ds->d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (pair_check == 3) GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_sync + 1, ds->ex_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pair_check >= 3) GTB_CUDA_OK(ctx, cudaMemcpyAsync(ds->h_sync + 1, ds->ex_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ds->h_sync[0] == ds->gen) { ds->off = true; return GTB_ERR_UNSUPPORTED; }       // nothing of this batch has reached the planes
-    if (pair_check == 3) ds->n_exceptions = (int64_t)ds->h_sync[1];
+    if (pair_check >= 3) ds->n_exceptions = (int64_t)ds->h_sync[1];
   }
   ds->queries_since_check += q.n_regions;
   if (!ds->check_pending) {
@@ -666,6 +696,14 @@ void gtb_direct_reset(gtb_index *ix) {
   if (!ds) return;
   ds->off = ds->off_lengths;                                            // reads of every length: a property of the data, expected to last
   ds->queries_since_check = 0;
+}
+
+// pair_check == 4: the numbers of the regions of the last batch that the candidate-enumeration engine has to count
+int64_t gtb_direct_exception_list(gtb_index *ix, const int32_t **list) {
+  gtb_direct_state *ds = ix->direct;
+  if (!ds || ds->n_exceptions == 0) return 0;
+  *list = ds->ex_chrom.p;
+  return ds->n_exceptions;
 }
 
 // pair_check == 3: the pairs of the last batch that the candidate-enumeration engine has to count (two intervals each, no offsets)

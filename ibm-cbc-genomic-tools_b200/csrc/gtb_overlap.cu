@@ -84,10 +84,15 @@ __device__ __forceinline__ ull enum_key(int32_t c, int level, int64_t bin) {
   return ((ull)(uint32_t)c << 35) | ((ull)level << 32) | (ull)(uint32_t)bin;
 }
 
+// region_list (with n_list entries): only those query regions, by number (what the one-pass engine has left over, see
+// accumulate_multi_fast); null: all of them
 template <bool COVERAGE>
-__global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix, EnumView ev, bool match_gaps, bool ignore_strand) {
+__global__ void __launch_bounds__(128) enumerate_kernel(QueryView q, RankView ix, EnumView ev, bool match_gaps, bool ignore_strand,
+                                                        const int32_t *__restrict__ region_list, int64_t n_list) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+  const int64_t n_work = region_list ? n_list : q.n_regions;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_work; t += stride) {
+    const int64_t r = region_list ? (int64_t)region_list[t] : t;
     int64_t lo, hi;
     if (!admit_query(q, r, ix, lo, hi)) continue;
     const int32_t c = q.chrom[lo];
@@ -588,10 +593,48 @@ static int accumulate_device(gtb_index *ix, const QueryView &q, bool batch_multi
 
 // Multi-interval query regions in front of the single-interval engines (see region_prepass_kernel).  Returns GTB_ERR_UNSUPPORTED
 // if this batch is not of that kind.
+static EnumView enum_view(gtb_index *ix) {
+  EnumView ev;
+  ev.n_entries = ix->n_entries; ev.keys = ix->d_keys.p; ev.rid = ix->d_rid.p;
+  ev.r_chrom = ix->d_r_chrom.p; ev.r_start = ix->d_r_start.p; ev.r_stop = ix->d_r_stop.p;
+  ev.r_strand = ix->d_r_strand.p; ev.r_off = ix->d_r_off.p; ev.direct = ix->d_direct.p;
+  return ev;
+}
+
 static int accumulate_multi_fast(gtb_index *ix, const QueryView &q, int64_t n_intervals) {
   gtb_ctx *ctx = ix->ctx;
   const bool spans = ix->match_gaps;
-  if (q.weight || !(spans || ix->op == GTB_OP_COVERAGE) || ix->flat_blocks) return GTB_ERR_UNSUPPORTED;
+  if (q.weight || ix->flat_blocks || ix->leftovers) return GTB_ERR_UNSUPPORTED;
+  if (!(spans || ix->op == GTB_OP_COVERAGE)) {
+    // count without -gaps: a region counts a query once if any of its blocks overlaps it.  Against single-interval index regions
+    // that is the count of the query's SPAN unless a region lies strictly inside a gap between blocks -- impossible if the span
+    // holds no evaluation point.  So: spans written by the prepass, counted by the one-pass engine, which leaves the
+    // multi-interval regions whose span does hold one (a few percent of spliced reads) on a list for the enumeration engine.
+    if (ix->index_multi || (ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK | GTB_ENGINE_BUCKET)) || q.n_regions < (1 << 18) || !gtb_direct_usable(ix) ||
+        getenv("GTB_NO_MULTI_FAST"))
+      return GTB_ERR_UNSUPPORTED;
+    RankView rv = rank_view(ix);
+    const size_t nr = (size_t)q.n_regions;
+    GTB_TRY(ix->sp_chrom.reserve(ctx, nr)); GTB_TRY(ix->sp_start.reserve(ctx, nr)); GTB_TRY(ix->sp_stop.reserve(ctx, nr)); GTB_TRY(ix->sp_strand.reserve(ctx, nr));
+    GTB_LAUNCH(ctx, "region_spans", region_prepass_kernel<true>, gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 16), 256, 0, q, rv,
+               ix->sp_chrom.p, ix->sp_start.p, ix->sp_stop.p, ix->sp_strand.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    QueryView flat = q;
+    flat.weight = nullptr; flat.region_offset = nullptr; flat.interval_base = 0;
+    flat.chrom = ix->sp_chrom.p; flat.start = ix->sp_start.p; flat.stop = ix->sp_stop.p; flat.strand = ix->sp_strand.p;
+    if (!gtb_direct_supported(ix, flat, false)) return GTB_ERR_UNSUPPORTED;
+    const int rc = gtb_direct_accumulate(ix, flat, 4, q.region_offset);
+    if (rc != GTB_OK) return rc;                                         // (GTB_ERR_UNSUPPORTED: nothing counted, the whole batch by enumeration)
+    const int32_t *list = nullptr;
+    const int64_t n_ex = gtb_direct_exception_list(ix, &list);
+    if (n_ex > 0) {
+      GTB_TRY(build_enum_structures(ix));
+      const EnumView ev = enum_view(ix);
+      GTB_LAUNCH(ctx, "enumerate_count", enumerate_kernel<false>, gtb_grid_for(n_ex, 128, (int64_t)ctx->sm_count * 16), 128, 0, q, rv, ev, false, ix->ignore_strand, list, n_ex);
+      GTB_TRY(gtb_check_launch(ctx));
+    }
+    return GTB_OK;
+  }
   if (ix->engine & (GTB_ENGINE_ENUMERATE | GTB_ENGINE_RANK)) return GTB_ERR_UNSUPPORTED;
   // coverage of spans: spans are long and of every length.  DIRECT takes them at a reduction each (its byte counters count reads of
   // one common length); BUCKET's elements have 8 bits for a length, so where DIRECT cannot serve the index the general rank step does
@@ -650,7 +693,10 @@ static int accumulate_device(gtb_index *ix, const QueryView &q_in, bool batch_mu
             GTB_LAUNCH(ctx, "uniform_offsets", uniform_offsets_kernel, gtb_grid_for(n_ex + 1, 256, (int64_t)ctx->sm_count * 8), 256, 0, n_ex, (int64_t)2, (int64_t)0, ix->uni_off.p);
             GTB_TRY(gtb_check_launch(ctx));
             ex.region_offset = ix->uni_off.p;
-            return accumulate_device(ix, ex, true, 2 * n_ex, 0);
+            ix->leftovers = true;                                        // (the engine's exception arrays are this batch: no second round there)
+            const int rc_ex = accumulate_device(ix, ex, true, 2 * n_ex, 0);
+            ix->leftovers = false;
+            return rc_ex;
           }
         }
         if (rc != GTB_ERR_UNSUPPORTED) return rc;
@@ -676,15 +722,12 @@ static int accumulate_device(gtb_index *ix, const QueryView &q_in, bool batch_mu
   RankView rv = rank_view(ix);
   if (engine == GTB_ENGINE_ENUMERATE) {
     GTB_TRY(build_enum_structures(ix));
-    EnumView ev;
-    ev.n_entries = ix->n_entries; ev.keys = ix->d_keys.p; ev.rid = ix->d_rid.p;
-    ev.r_chrom = ix->d_r_chrom.p; ev.r_start = ix->d_r_start.p; ev.r_stop = ix->d_r_stop.p;
-    ev.r_strand = ix->d_r_strand.p; ev.r_off = ix->d_r_off.p; ev.direct = ix->d_direct.p;
+    const EnumView ev = enum_view(ix);
     const unsigned grid = gtb_grid_for(q.n_regions, 128, (int64_t)ctx->sm_count * 16);
     if (ix->op == GTB_OP_COVERAGE)
-      GTB_LAUNCH(ctx, "enumerate_coverage", enumerate_kernel<true>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand);
+      GTB_LAUNCH(ctx, "enumerate_coverage", enumerate_kernel<true>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand, (const int32_t *)nullptr, (int64_t)0);
     else
-      GTB_LAUNCH(ctx, "enumerate_count", enumerate_kernel<false>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand);
+      GTB_LAUNCH(ctx, "enumerate_count", enumerate_kernel<false>, grid, 128, 0, q, rv, ev, ix->match_gaps, ix->ignore_strand, (const int32_t *)nullptr, (int64_t)0);
     return gtb_check_launch(ctx);
   }
   const unsigned grid = gtb_grid_for(q.n_regions, 256, (int64_t)ctx->sm_count * 8);

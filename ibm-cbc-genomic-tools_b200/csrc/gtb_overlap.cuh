@@ -61,6 +61,7 @@ struct gtb_index {
   int op = GTB_OP_COUNT;
   bool match_gaps = false, ignore_strand = false, sorted_rules = false;
   bool flat_blocks = false;        // transient: the batch being accumulated is the flattened block list of multi-interval queries
+  bool leftovers = false;          // transient: the batch being accumulated is what the one-pass engine has left for the enumeration engine
   int admission() const { return flat_blocks ? 2 : sorted_rules ? 1 : 0; }
   unsigned engine = GTB_ENGINE_AUTO;
   int64_t n_regions = 0, n_intervals = 0;
@@ -135,8 +136,11 @@ int gtb_direct_prepare(gtb_index *ix);
 //   3: count without -gaps -- spans that hold no evaluation point are counted, the other pairs are left on a list
 //   (gtb_direct_exceptions) for the enumeration engine.  GTB_ERR_UNSUPPORTED from modes 2 and 3: nothing of the batch has been
 //   counted, the caller takes its general path
-int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check = 0);
+//   4: count without -gaps, the queries are the spans of regions of any shape (region_offsets: the batch's offsets, rebased to 0):
+//   multi-interval regions whose span holds an evaluation point are left on a list of region numbers (gtb_direct_exception_list)
+int gtb_direct_accumulate(gtb_index *ix, const QueryView &q, int pair_check = 0, const int64_t *region_offsets = nullptr);
 int64_t gtb_direct_exceptions(gtb_index *ix, QueryView *out);
+int64_t gtb_direct_exception_list(gtb_index *ix, const int32_t **list);
 void gtb_direct_destroy(gtb_index *ix);
 void gtb_direct_reset(gtb_index *ix);     // a new query stream: the watchdog's verdict on the previous one no longer holds
 bool gtb_direct_supported(gtb_index *ix, const QueryView &q, bool batch_multi);

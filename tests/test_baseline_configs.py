@@ -274,6 +274,65 @@ def test_config3_pairs_without_offsets(ctx, oracle, gtb):
             ix.close()
 
 
+def synth_spliced(n, seed):
+    """reads of one to four blocks (30-80 bp) separated by gaps of 50-2000 bp, CSR offsets; about half of them single-block"""
+    rng = np.random.default_rng(seed)
+    base = support.synth_reads(n, seed=seed)
+    k = np.where(rng.random(n) < 0.5, 1, rng.integers(2, 5, n))
+    off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+    m = int(off[-1])
+    reg = np.repeat(np.arange(n), k)
+    j = np.arange(m) - off[reg]                                           # block number inside its region
+    blen = rng.integers(30, 81, m)
+    gap = rng.integers(50, 2001, m)
+    step = np.where(j > 0, np.roll(blen, 1) + gap, 0)                      # distance from the previous block's start
+    rel = np.cumsum(step) - np.repeat(np.cumsum(step)[off[:-1]], k)       # start relative to the region's first block
+    start = (base["start"][reg].astype(np.int64) + rel)
+    room = support.HG19_LENS[base["chrom"]][reg] - (start + blen)         # keep every block inside its chromosome
+    shift = np.repeat(np.minimum.reduceat(np.minimum(room, 0), off[:-1]), k)
+    start = np.maximum(start + shift, 1)
+    return ({"chrom": base["chrom"][reg].astype(np.int32), "start": start.astype(np.int32), "stop": (start + blen - 1).astype(np.int32),
+             "strand": base["strand"][reg].astype(np.int8)}, off)
+
+
+def test_count_spliced_reads_without_gaps(ctx, oracle, gtb):
+    """count without -gaps over regions of one to four blocks (what spliced reads in a SAM file become): the spans go through the
+    one-pass engine, the multi-block regions whose span holds an evaluation point through the enumeration engine -- against short
+    index regions (many of them inside the gaps between blocks, where the span's count would be wrong), host and device memory"""
+    import torch
+    q, off = synth_spliced(900_001, seed=91)
+    short = support.synth_regions(80_000, 33, 20, 600)
+    genes = support.synth_regions(60_000, 3)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in q.items()}
+    dev_off = torch.from_numpy(off).cuda()
+    for idx in (short, genes):
+        for flags in (0, gtb.IGNORE_STRAND):
+            rc, want, _ = oracle.count(q, idx, flags, qoff=off)
+            assert rc == 0 and want.sum() > 0
+            ix = gtb.Index(ctx, idx, gtb.OP_COUNT, flags)
+            ix.add_host(q, offsets=off)
+            assert np.array_equal(ix.finish(), want), ("host", flags)
+            ix.reset()
+            ix.add_device(dev, offsets=dev_off)
+            assert np.array_equal(ix.finish(), want), ("device", flags)
+            ix.close()
+    rc, with_gaps, _ = oracle.count(q, short, gtb.MATCH_GAPS, qoff=off)
+    rc2, without, _ = oracle.count(q, short, 0, qoff=off)
+    assert rc == 0 and rc2 == 0 and not np.array_equal(with_gaps, without)             # (the input does tell the two semantics apart)
+    # a malformed region and a fatal span keep their stream index
+    bad = {k: v.copy() for k, v in q.items()}
+    r_multi = int(np.flatnonzero(np.diff(off) > 1)[1234])
+    bad["start"][off[r_multi] + 1] = bad["stop"][off[r_multi]]             # blocks overlap
+    rc, _, ei = oracle.count(bad, genes, 0, qoff=off)
+    assert rc != 0 and ei == r_multi
+    ix = gtb.Index(ctx, genes, gtb.OP_COUNT, 0)
+    ix.add_host(bad, offsets=off)
+    with pytest.raises(gtb.GtbError) as e:
+        ix.finish()
+    assert (e.value.code, e.value.index) == (rc, r_multi)
+    ix.close()
+
+
 def test_pairs_without_offsets_skewed(ctx, oracle, gtb):
     """most pairs piled onto four loci, in random order: byte counters overflow before their spills land, the batch is dropped
     by the engine (its queries were spans formed in registers: no replay there) and goes down the general path -- or it is
