@@ -1,5 +1,7 @@
-// genomic_regions -- drop-in driver for `genomic_regions gsort`, `link` and `inv` on the B200 engine.
+// genomic_regions -- drop-in driver for `genomic_regions gsort`, `link`, `inv` and `union` on the B200 engine.
 //
+// union (GenomicRegionSet::RunUnion, genomic_intervals.cpp:4397-4403; GenomicRegion::Union, :1649-1671): every region's intervals
+// sorted by start and merged where they overlap, the region printed in its own format -- a per-line operation, on the host.
 // link (GenomicRegionSet::RunGlobalLink, genomic_intervals.cpp:4607-4644): consecutive regions of a sorted stream that are
 // compatible and lie within -d of the stop reached so far become one region.  The host reads, checks (single-interval, sorted)
 // and prints; which regions begin a linked region and where each one ends comes from the device (gtb_link_regions: a
@@ -94,6 +96,7 @@ static int64_t first_bad_region(const gt::RegionBatch &b, const gt::ChromTable &
 
 static int run_link(const char *file);
 static int run_inv(const char *file);
+static int run_union(const char *file);
 
 int main(int argc, char *argv[]) {
   gt::CmdLine cmd(PROGRAM, VERSION);
@@ -103,11 +106,13 @@ int main(int argc, char *argv[]) {
                    "* Input formats: REG, GFF, BED, SAM\n  * Operand: region-set\n  * Region requirements: single-interval\n  * Region-set requirements: sorted by chromosome/strand/start");
   cmd.AddOperation("link", "[OPTIONS] <REGION-SET>", "Links consecutive regions to produce a non-overlapping set.",
                    "* Input formats: REG, GFF, BED, SAM\n  * Operand: region-set\n  * Region requirements: single-interval\n  * Region-set requirements: sorted by chromosome/(strand)/start");
-  if (argc < 2) { cmd.OperationSummary("OPERATION [OPTIONS] <REGION-SET>", "Performs operations on genomic regions (this build: gsort, inv, link)."); exit(1); }
+  cmd.AddOperation("union", "[OPTIONS] <REGION-SET>", "Computes union of region intervals.",
+                   "* Input formats: REG, GFF, BED, SAM\n  * Operand: region\n  * Region requirements: chromosome/strand-compatible\n  * Region-set requirements: none");
+  if (argc < 2) { cmd.OperationSummary("OPERATION [OPTIONS] <REGION-SET>", "Performs operations on genomic regions (this build: gsort, inv, link, union)."); exit(1); }
   std::string op = argv[1];
   if (op[0] == '-') op = op.substr(1);
-  if (op != "gsort" && op != "link" && op != "inv") {
-    std::cerr << "Operation '" << op << "' is outside the GPU-accelerated path of this build (gsort, inv, link are available)!\n";
+  if (op != "gsort" && op != "link" && op != "inv" && op != "union") {
+    std::cerr << "Operation '" << op << "' is outside the GPU-accelerated path of this build (gsort, inv, link, union are available)!\n";
     exit(1);
   }
   cmd.SetCurrentOperation(op);
@@ -119,7 +124,7 @@ int main(int argc, char *argv[]) {
     cmd.AddOption("-b", &BIN_BITS, 12L, "bucket size (in bits) used in bucket sort");
   } else if (op == "inv") {
     cmd.AddOption("-g", &GENOME_REG_FILE, "", "genome region-set file");
-  } else {
+  } else if (op == "link") {
     cmd.AddOption("-s", &SORTED_BY_STRAND, false, "input regions are sorted by strand");
     cmd.AddOption("-d", &LINK_MAX_DIFFERENCE, 0L, "maximum difference between successive regions");
     cmd.AddOption("--label-func", &LINK_LABEL_FUNC, "", "label function = {min,max,sum,%c}, where %c is used as delimiter");
@@ -129,6 +134,7 @@ int main(int argc, char *argv[]) {
   const char *file = next_arg == argc ? nullptr : argv[next_arg];
   if (op == "link") return run_link(file);
   if (op == "inv") return run_inv(file);
+  if (op == "union") return run_union(file);
 
   gt::PhaseTimer timer;
   // the CUDA context comes up while the file is read
@@ -303,6 +309,51 @@ static int run_inv(const char *file) {
   flush(true);
   fflush(stdout);
   if (n < n_all) region_error(b.line(n), msg);
+  if (rr.failed()) rr.Fail();
+  return 0;
+}
+
+// genomic_regions union
+static int run_union(const char *file) {
+  gt::ChromTable chroms;
+  gt::RegionReader rr(file, &chroms, true, 1);
+  fwrite(rr.header().data(), 1, rr.header().size(), stdout);
+  gt::RegionBatch b;
+  std::vector<std::string> raw;
+  rr.ReadKeep(&b, &raw, INT64_MAX);
+  const int64_t n = b.n_regions();
+  std::string text;
+  std::vector<std::pair<int32_t, int32_t>> iv;
+  for (int64_t k = 0; k < n; k++) {
+    const int64_t lo = b.offset[k], hi = b.offset[k + 1];
+    int64_t m = hi - lo;
+    if (m > 1) {                                                         // "if (I.size()<=1) return;", :1651
+      for (int64_t i = lo + 1; i < hi; i++)                               // IsCompatible(false), :1116-1122
+        if (b.chrom[i] != b.chrom[lo] || b.strand[i] != b.strand[lo]) {
+          fwrite(text.data(), 1, text.size(), stdout);
+          region_error(b.line(k), "region intervals must have the same chromosome/strand for this operation!");
+        }
+      iv.clear();
+      for (int64_t i = lo; i < hi; i++) iv.emplace_back(b.start[i], b.stop[i]);
+      // Sort(): by start (CompareGenomicIntervals, :6055-6060; chromosome and strand are equal here).  What the merge leaves
+      // does not depend on the order of intervals with equal starts.
+      std::sort(iv.begin(), iv.end(), [](const std::pair<int32_t, int32_t> &x, const std::pair<int32_t, int32_t> &y) { return x.first < y.first; });
+      m = 0;
+      int32_t start = iv[0].first, stop = iv[0].second;
+      for (size_t i = 1; i < iv.size(); i++) {
+        if (stop < iv[i].first) { b.start[(size_t)(lo + m)] = start; b.stop[(size_t)(lo + m)] = stop; m++; start = iv[i].first; stop = iv[i].second; }
+        else stop = std::max(stop, iv[i].second);
+      }
+      b.start[(size_t)(lo + m)] = start; b.stop[(size_t)(lo + m)] = stop; m++;
+    }
+    const int64_t next = b.offset[(size_t)k + 1];
+    b.offset[(size_t)k + 1] = lo + m;                                     // (the region as PrintRegion is to see it)
+    gt::PrintRegion(rr.format(), raw[(size_t)k], b, k, chroms, &text);
+    b.offset[(size_t)k + 1] = next;
+    if (text.size() > (1u << 24)) { fwrite(text.data(), 1, text.size(), stdout); text.clear(); }
+  }
+  fwrite(text.data(), 1, text.size(), stdout);
+  fflush(stdout);
   if (rr.failed()) rr.Fail();
   return 0;
 }

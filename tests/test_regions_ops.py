@@ -1,4 +1,4 @@
-"""`genomic_regions inv` and `link` (GenomicRegionSet::RunGlobalInvert / RunGlobalLink, genomic_intervals.cpp:4576-4644) of this
+"""`genomic_regions inv`, `link` and `union` (GenomicRegionSet::RunGlobalInvert / RunGlobalLink / RunUnion, genomic_intervals.cpp:4576-4644, :4397) of this
 repo's driver against the reference binary: stdout byte for byte, the fatal cases with the reference's message after the output
 it had printed by then.  `inv` is a function of adjacent pairs computed on the host (no GPU needed); `link` gets the linked regions
 from the device (gtb_link_regions: prefix-maximum scan) and is a GPU test, as is the ABI-level check against the sequential loop."""
@@ -65,6 +65,58 @@ def test_inv_errors(files):
     for args in (["inv", files / "ss.bed"], ["inv", "-g", files / "genome.bed", files / "nochrom.bed"]):
         want, got = run_both(args)
         assert got[0] == want[0] != 0 and got[1] == want[1], (args, got, want)
+
+
+@pytest.fixture(scope="module")
+def union_files(tmp_path_factory):
+    """regions of one to six intervals in any order, overlapping, touching, nested, with equal starts -- as REG, BED12 (sorted
+    non-overlapping blocks, as the format demands) and SAM (spliced reads)"""
+    d = tmp_path_factory.mktemp("union")
+    rng = np.random.default_rng(9)
+    reg, bed, sam = [], [], []
+    for k in range(2000):
+        c = "chr%d" % rng.integers(1, 4)
+        st = "+-"[rng.integers(2)]
+        m = int(rng.integers(1, 7))
+        base = int(rng.integers(1, 900000))
+        starts = base + rng.integers(0, 400, m)
+        if rng.random() < 0.3:
+            starts[rng.integers(m)] = starts[0]                             # equal starts
+        stops = starts + rng.integers(0, 120, m)
+        if rng.random() < 0.3 and m > 1:
+            starts[1] = stops[0] + 1                                        # touching: stays apart
+            stops[1] = max(stops[1], starts[1])
+        reg.append("u%d\t%s\n" % (k, " ".join("%s %s %d %d" % (c, st, a, b) for a, b in zip(starts, stops))))
+        sizes = rng.integers(5, 60, m)
+        gaps = rng.integers(1, 300, m)
+        rel = np.concatenate([[0], np.cumsum(sizes[:-1] + gaps[:-1])])
+        bed.append("%s\t%d\t%d\tb%d\t%d\t%s\t%d\t%d\t0,0,255\t%d\t%s\t%s\n" % (c, base, base + rel[-1] + sizes[-1], k, k % 10, st, base, base + 3, m,
+                   ",".join(map(str, sizes)), ",".join(map(str, rel))))
+        cigar = "".join("%dM%s" % (sizes[i], "%dN" % gaps[i] if i + 1 < m else "") for i in range(m))
+        sam.append("q%d\t%d\t%s\t%d\t60\t%s\t=\t7\t-3\t%s\t*\tNM:i:1\n" % (k, 16 if st == "-" else 0, c, base, cigar, "A" * int(sizes.sum())))
+    (d / "u.reg").write_text("".join(reg))
+    (d / "u.bed").write_text("track name=x\n" + "".join(bed))
+    (d / "u.sam").write_text("@HD\tVN:1.0\n" + "".join(sam))
+    (d / "bad_strand.reg").write_text("".join(reg[:50]) + "x\tchr1 + 5 9 chr1 - 7 30\n" + "".join(reg[50:60]))
+    (d / "bad_chrom.reg").write_text("".join(reg[:5]) + "x\tchr1 + 5 9 chr2 + 7 30 chr1 + 1 2\n" + "".join(reg[5:9]))
+    (d / "bad_line.reg").write_text("".join(reg[:7]) + "x\tchr1 + 5\n" + "".join(reg[7:9]))
+    (d / "empty.bed").write_text("")
+    return d
+
+
+@pytest.mark.parametrize("name", ["u.reg", "u.bed", "u.sam", "bad_strand.reg", "bad_chrom.reg", "bad_line.reg", "empty.bed"])
+def test_union(union_files, files, name):
+    want, got = run_both(["union", union_files / name])
+    assert got[0] == want[0] and got[1] == want[1], (name, got[1][:300], want[1][:300], got[2][-200:], want[2][-200:])
+    assert got[2] == want[2] or want[0] == 0, (got[2], want[2])
+    if name.startswith("u."):
+        assert want[0] == 0 and len(want[1]) > 0
+    for single in ("ss.bed", "ss.gff", "ss.reg") if name == "u.reg" else ():
+        want, got = run_both(["union", files / single])
+        assert got[0] == want[0] == 0 and got[1] == want[1], single
+    if name == "u.reg":                                                    # standard input, and the usage text
+        want, got = run_both(["union"], stdin=(union_files / name).read_bytes())
+        assert got[0] == want[0] == 0 and got[1] == want[1]
 
 
 @pytest.mark.gpu
