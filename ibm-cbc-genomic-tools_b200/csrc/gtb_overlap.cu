@@ -194,6 +194,58 @@ __global__ void __launch_bounds__(128) query_enumerate_kernel(QueryView q, RankV
   }
 }
 
+// The walk itself: for every query region the index regions GetOverlap / NextOverlap hand out, IN THE ORDER the reference's
+// engine hands them out.  The Unsorted class (:5729-5764) walks its bin levels in turn, the bins of a level from the query's
+// first to its last, and every bin's chain from the region inserted last to the one inserted first (:5665-5669) -- the entries
+// of `ev` are sorted that way (key ascending, region number descending; levels = the reference's -B list, see build_match_structures),
+// so the walk below meets the matches in that order.  The Sorted class (:5902-5927) steps through its buffer of index regions,
+// which holds them in file order: the matches of a query are put into ascending order after the walk (by_id).
+// match_off[r] - match_base .. match_off[r + 1] - match_base: where query r's matches go (from gtb_index_query_counts).
+struct MatchLevels { int n; int bits[8]; };
+
+__global__ void __launch_bounds__(128) query_matches_kernel(QueryView q, RankView ix, EnumView ev, MatchLevels lv, bool match_gaps, bool ignore_strand, bool by_id,
+                                                            const int64_t *__restrict__ match_off, int64_t match_base, int32_t *__restrict__ match_out,
+                                                            uint32_t *__restrict__ mismatch) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
+    const int64_t room = match_off[r + 1] - match_off[r];
+    int32_t *dst = match_out + (match_off[r] - match_base);
+    int64_t n = 0;
+    int64_t lo, hi;
+    if (admit_query(q, r, ix, lo, hi)) {
+      const int32_t c = q.chrom[lo];
+      const int8_t qstrand = q.strand[lo];
+      const int64_t qs = q.start[lo], qe = q.stop[hi - 1];
+      const int64_t b_first = max(min(qs, qe), (int64_t)1), b_last = max(max(qs, qe), (int64_t)1);   // :5742; the Sorted class admits qs == qe + 1
+      for (int l = 0; l < lv.n; l++) {
+        const ull k_lo = enum_key(c, l, b_first >> lv.bits[l]);
+        const ull k_hi = enum_key(c, l, b_last >> lv.bits[l]);
+        for (int64_t e = lower_bound_u64(ev.keys, ev.n_entries, k_lo); e < ev.n_entries && ev.keys[e] <= k_hi; e++) {
+          const int32_t k = ev.rid[e];
+          const int64_t ilo = ev.r_off[k], ihi = ev.r_off[k + 1];
+          if (!(qs <= ev.r_stop[ihi - 1] && qe >= ev.r_start[ilo])) continue;             // span test, :5752
+          if (!ignore_strand && qstrand != ev.r_strand[ilo]) continue;                   // :5229
+          bool any = match_gaps;                                                          // :5227
+          for (int64_t i = lo; i < hi && !any; i++)
+            for (int64_t j = ilo; j < ihi; j++)
+              if (!(q.start[i] > ev.r_stop[j] || q.stop[i] < ev.r_start[j])) { any = true; break; }   // :624-630
+          if (!any) continue;
+          if (n < room) dst[n] = k;
+          n++;
+        }
+      }
+    }
+    if (n != room) { atomicOr(mismatch, 1u); continue; }
+    if (by_id)
+      for (int64_t a = 1; a < n; a++) {
+        const int32_t v = dst[a];
+        int64_t b = a;
+        for (; b > 0 && dst[b - 1] > v; b--) dst[b] = dst[b - 1];
+        dst[b] = v;
+      }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // finalisation: after the slot histograms have been prefix-summed, evaluate every target and sum
 // the targets of each region.  One thread per region.
@@ -550,7 +602,7 @@ extern "C" void gtb_index_destroy(gtb_index *ix) {
   ix->d_class_of.release(); ix->d_present.release(); ix->d_goff.release(); ix->d_points.release();
   ix->d_t_hi.release(); ix->d_t_lo.release(); ix->d_t_base.release(); ix->d_t_off.release();
   ix->d_hist.release(); ix->d_hist_scan.release(); ix->d_scan_scratch.release();
-  ix->d_keys.release(); ix->d_rid.release(); ix->d_r_chrom.release(); ix->d_r_start.release();
+  ix->d_keys.release(); ix->d_rid.release(); ix->d_mkeys.release(); ix->d_mrid.release(); ix->d_r_chrom.release(); ix->d_r_start.release();
   ix->d_r_stop.release(); ix->d_r_strand.release(); ix->d_r_off.release(); ix->d_direct.release();
   ix->d_err.release(); ix->d_out.release();
   ix->sp_chrom.release(); ix->sp_start.release(); ix->sp_stop.release(); ix->sp_strand.release(); ix->d_qpre.release();
@@ -1043,6 +1095,134 @@ extern "C" int gtb_index_query_counts(gtb_index *ix, const gtb_set *queries, uns
   }
   d_out.release();
   return gtb_index_status(ix, err_index);
+}
+
+// The bin index of UnsortedGenomicRegionSetOverlaps (:5600-5675) as a sorted entry list: levels of `bits` shift-bits (the -B list
+// plus the closing level of 60 bits, :5620-5637), an admitted region in the first level whose bin holds both its ends, the
+// chain of a bin from the region inserted last to the first.
+static int build_match_structures(gtb_index *ix, const int *bits, int n_levels) {
+  gtb_ctx *ctx = ix->ctx;
+  GTB_TRY(build_enum_structures(ix));                                   // (the interval arrays of the index regions)
+  if (ix->match_ready && ix->match_bits == std::vector<int>(bits, bits + n_levels)) return GTB_OK;
+  std::vector<std::pair<ull, int32_t>> ent;
+  ent.reserve((size_t)ix->n_regions);
+  for (int64_t k = 0; k < ix->n_regions; k++) {
+    const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
+    if (hi <= lo) continue;
+    if (!ix->h_malformed.empty() && ix->h_malformed[(size_t)k]) continue;
+    int64_t s = ix->h_start[lo], e = ix->h_stop[hi - 1];
+    if (s > e || e <= 0) continue;                                      // :5659
+    if (s <= 0) s = 1;                                                  // :5660
+    for (int l = 0; l < n_levels; l++)
+      if ((s >> bits[l]) == (e >> bits[l])) {
+        ent.push_back({((ull)(uint32_t)ix->h_chrom[lo] << 35) | ((ull)l << 32) | (ull)(uint32_t)(s >> bits[l]), (int32_t)k});
+        break;
+      }
+  }
+  std::sort(ent.begin(), ent.end(), [](const std::pair<ull, int32_t> &a, const std::pair<ull, int32_t> &b) {
+    return a.first != b.first ? a.first < b.first : a.second > b.second;
+  });
+  std::vector<ull> keys(ent.size());
+  std::vector<int32_t> rid(ent.size());
+  for (size_t i = 0; i < ent.size(); i++) { keys[i] = ent[i].first; rid[i] = ent[i].second; }
+  ix->n_match_entries = (int64_t)ent.size();
+  GTB_TRY(upload(ctx, ix->d_mkeys, keys));
+  GTB_TRY(upload(ctx, ix->d_mrid, rid));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  ix->match_bits.assign(bits, bits + n_levels);
+  ix->match_ready = true;
+  return GTB_OK;
+}
+
+extern "C" int gtb_index_query_matches(gtb_index *ix, const gtb_set *queries, unsigned mem, const int *bin_bits, int n_bin_bits,
+                                       const int64_t *match_offset, int32_t *matches, int64_t *err_index) {
+  if (err_index) *err_index = -1;
+  if (!ix || !queries) return GTB_ERR_ARG;
+  gtb_ctx *ctx = ix->ctx;
+  if (ix->op != GTB_OP_COUNT) return gtb_fail(ctx, GTB_ERR_ARG, "per-query matches need an index created with GTB_OP_COUNT");
+  if (queries->n_regions < 0 || queries->n_intervals < 0) return gtb_fail(ctx, GTB_ERR_ARG, "negative sizes");
+  if (queries->n_regions == 0) return GTB_OK;
+  if (mem & GTB_MEM_DEVICE) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "gtb_index_query_matches takes host-resident queries");
+  if (!match_offset || !queries->chrom || !queries->start || !queries->stop || !queries->strand) return gtb_fail(ctx, GTB_ERR_ARG, "null arrays");
+  if (!queries->region_offset && queries->n_regions != queries->n_intervals)
+    return gtb_fail(ctx, GTB_ERR_ARG, "region_offset is NULL but n_regions != n_intervals");
+  if (match_offset[queries->n_regions] > match_offset[0] && !matches) return gtb_fail(ctx, GTB_ERR_ARG, "null match array");
+  static const int default_bits[4] = {17, 20, 23, 26};
+  if (!bin_bits) { bin_bits = default_bits; n_bin_bits = 4; }
+  MatchLevels lv;
+  if (n_bin_bits < 0 || n_bin_bits > 7) return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "at most 7 bin levels (plus the closing one)");
+  for (int l = 0; l < n_bin_bits; l++) {
+    if (bin_bits[l] < 0 || bin_bits[l] > 62) return gtb_fail(ctx, GTB_ERR_ARG, "bin bits must lie in 0..62");
+    lv.bits[l] = bin_bits[l];
+  }
+  lv.bits[n_bin_bits] = 60; lv.n = n_bin_bits + 1;                      // :5637
+  GTB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  bool batch_multi = false;
+  for (int64_t k = 0; k < queries->n_regions; k++) {
+    if (queries->region_offset) {
+      const int64_t d = queries->region_offset[k + 1] - queries->region_offset[k];
+      if (d < 1) return gtb_fail(ctx, GTB_ERR_ARG, "region_offset must be increasing: every region has at least one interval");
+      batch_multi = batch_multi || d != 1;
+    }
+    if (match_offset[k + 1] < match_offset[k]) return gtb_fail(ctx, GTB_ERR_ARG, "match_offset must not decrease");
+  }
+  if (ix->sorted_rules)                                                 // the Sorted class skips no index region; the bin lists hold the Unsorted class's
+    for (int64_t k = 0; k < ix->n_regions; k++) {
+      const int64_t lo = ix->h_off[k], hi = ix->h_off[k + 1];
+      if (hi > lo && (ix->h_start[lo] > ix->h_stop[hi - 1] || ix->h_stop[hi - 1] <= 0))
+        return gtb_fail(ctx, GTB_ERR_UNSUPPORTED, "index regions with start > stop or stop <= 0 under GTB_SORTED_RULES: no match lists");
+    }
+  GTB_TRY(build_match_structures(ix, lv.bits, lv.n));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(ix->d_err.p, 0xFF, sizeof(ull), ctx->stream));
+  RankView rv = rank_view(ix);
+  EnumView ev = enum_view(ix);
+  ev.n_entries = ix->n_match_entries; ev.keys = ix->d_mkeys.p; ev.rid = ix->d_mrid.p;
+  dbuf<int32_t> d_match;
+  dbuf<int64_t> d_moff;
+  dbuf<uint32_t> d_flag;
+  GTB_TRY(d_flag.reserve(ctx, 1));
+  GTB_CUDA_OK(ctx, cudaMemsetAsync(d_flag.p, 0, sizeof(uint32_t), ctx->stream));
+  const int64_t CHUNK = (int64_t)1 << 20;
+  for (int64_t r0 = 0; r0 < queries->n_regions; r0 += CHUNK) {
+    const int64_t r1 = std::min(queries->n_regions, r0 + CHUNK);
+    const int64_t i0 = batch_multi ? queries->region_offset[r0] : r0, i1 = batch_multi ? queries->region_offset[r1] : r1;
+    const size_t nr = (size_t)(r1 - r0), ni = (size_t)(i1 - i0), nm = (size_t)(match_offset[r1] - match_offset[r0]);
+    gtb_index::stage &st = ix->stages[0];
+    GTB_TRY(st.chrom.reserve(ctx, ni)); GTB_TRY(st.start.reserve(ctx, ni)); GTB_TRY(st.stop.reserve(ctx, ni)); GTB_TRY(st.strand.reserve(ctx, ni));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.chrom.p, queries->chrom + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.start.p, queries->start + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.stop.p, queries->stop + i0, ni * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.strand.p, queries->strand + i0, ni, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += (int64_t)ni * 13 + (int64_t)(nr + 1) * 8;
+    QueryView q;
+    q.weight = nullptr; q.index_base = r0; q.interval_base = 0; q.region_offset = nullptr; q.n_regions = (int64_t)nr;
+    q.chrom = st.chrom.p; q.start = st.start.p; q.stop = st.stop.p; q.strand = st.strand.p;
+    if (batch_multi) {
+      GTB_TRY(st.off.reserve(ctx, nr + 1));
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(st.off.p, queries->region_offset + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+      q.region_offset = st.off.p; q.interval_base = i0;
+    }
+    GTB_TRY(d_moff.reserve(ctx, nr + 1));
+    GTB_TRY(d_match.reserve(ctx, nm ? nm : 1));
+    GTB_CUDA_OK(ctx, cudaMemcpyAsync(d_moff.p, match_offset + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = gtb_grid_for((int64_t)nr, 128, (int64_t)ctx->sm_count * 16);
+    GTB_LAUNCH(ctx, "query_matches", query_matches_kernel, grid, 128, 0, q, rv, ev, lv, ix->match_gaps, ix->ignore_strand, ix->sorted_rules,
+               (const int64_t *)d_moff.p, match_offset[r0], d_match.p, d_flag.p);
+    GTB_TRY(gtb_check_launch(ctx));
+    if (nm) {
+      GTB_CUDA_OK(ctx, cudaMemcpyAsync(matches + (match_offset[r0] - match_offset[0]), d_match.p, nm * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->d2h_bytes += (int64_t)nm * 4;
+    }
+    GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));               // the staging buffers are reused by the next chunk
+  }
+  uint32_t flag = 0;
+  GTB_CUDA_OK(ctx, cudaMemcpyAsync(&flag, d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GTB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  d_match.release(); d_moff.release(); d_flag.release();
+  const int rc = gtb_index_status(ix, err_index);
+  if (rc != GTB_OK) return rc;
+  if (flag) return gtb_fail(ctx, GTB_ERR_ARG, "match_offset does not agree with the counts of gtb_index_query_counts for these queries");
+  return GTB_OK;
 }
 
 // =================================================================================================

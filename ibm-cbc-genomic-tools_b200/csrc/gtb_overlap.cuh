@@ -90,6 +90,11 @@ struct gtb_index {
   bool enum_ready = false;
   int64_t n_entries = 0;
   dbuf<ull> d_keys;
+  bool match_ready = false;       // the reference's own bin index as an entry list (gtb_index_query_matches)
+  std::vector<int> match_bits;
+  int64_t n_match_entries = 0;
+  dbuf<ull> d_mkeys;
+  dbuf<int32_t> d_mrid;
   dbuf<int32_t> d_rid, d_r_chrom, d_r_start, d_r_stop;
   dbuf<int8_t> d_r_strand;
   dbuf<int64_t> d_r_off;

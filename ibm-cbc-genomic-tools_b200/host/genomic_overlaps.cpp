@@ -165,11 +165,13 @@ int main(int argc, char *argv[]) {
     fprintf(stderr, "[Error]: the input is sorted by chromosome/strand/start (i.e. -S and -s are set), therefore the overlap algorithm can only report strand-specific results (i.e. -i cannot be set)!\n");
     exit(1);
   }
-  if (MERGE_LABELS) {
-    // -label names the matching reference regions in the order the reference's bin index walks them (a LIFO chain per bin,
-    // genomic_intervals.cpp:5665-5669): the engine counts matches, it does not order them
-    std::cerr << "Option '-label' of operation 'overlap' is outside the GPU-accelerated path of this build!\n";
-    exit(1);
+  // -B: the shift-bits of the bin levels (UnsortedGenomicRegionSetOverlaps, genomic_intervals.cpp:5628-5637).  Only `overlap -label`
+  // can tell one bin layout from another: the matches of a query come out in the order the bins are walked.
+  std::vector<int> bin_bits;
+  for (const char *p = BIN_BITS; p && *p;) {
+    bin_bits.push_back(atoi(p));
+    const char *c = strchr(p, ',');
+    p = c ? c + 1 : nullptr;
   }
   const char *ref_file = argv[next_arg];
   const char *test_file = next_arg + 1 == argc ? nullptr : argv[next_arg + 1];
@@ -275,7 +277,28 @@ int main(int argc, char *argv[]) {
         if (!fatal) check(ctx, rc, "gtb_index_query_counts");
         const int64_t upto = fatal ? err_index : nq;                     // the reference has printed the queries before the fatal one
         text.clear();
-        for (int64_t k = 0; k < upto; k++) {
+        if (MERGE_LABELS && upto > 0) {
+          // overlap -label: one line per matching reference region, labelled "query:reference", in the order the reference's
+          // engine walks its matches (gtb_index_query_matches) -- for the queries in front of a fatal one, as above
+          std::vector<int64_t> m_off((size_t)upto + 1, 0);
+          for (int64_t k = 0; k < upto; k++) m_off[(size_t)k + 1] = m_off[(size_t)k] + n_overlaps[(size_t)k];
+          std::vector<int32_t> m_id((size_t)std::max<int64_t>(m_off[(size_t)upto], 1));
+          gtb_set head = qs;
+          head.n_regions = upto; head.n_intervals = b.offset[upto];
+          check(ctx, gtb_index_query_matches(index, &head, GTB_MEM_HOST, bin_bits.data(), (int)bin_bits.size(), m_off.data(), m_id.data(), &err_index), "gtb_index_query_matches");
+          for (int64_t k = 0; k < upto; k++) {
+            if (m_off[(size_t)k + 1] == m_off[(size_t)k]) continue;
+            std::string own;
+            own.swap(b.label[(size_t)k]);
+            for (int64_t t = m_off[(size_t)k]; t < m_off[(size_t)k + 1]; t++) {
+              b.label[(size_t)k] = own + ":" + ref.label[(size_t)m_id[(size_t)t]];         // genomic_overlaps.cpp:721-727
+              gt::PrintRegion(qr.format(), raw[(size_t)k], b, k, chroms, &text);
+            }
+            b.label[(size_t)k].swap(own);
+            if (text.size() > (1u << 24)) { fwrite(text.data(), 1, text.size(), stdout); text.clear(); }
+          }
+        }
+        for (int64_t k = 0; k < (MERGE_LABELS ? 0 : upto); k++) {
           const uint32_t times = op == "overlap" ? n_overlaps[(size_t)k] : ((n_overlaps[(size_t)k] == 0) == SUBSET_NONOVERLAPS ? 1u : 0u);
           for (uint32_t t = 0; t < times; t++) gt::PrintRegion(qr.format(), raw[(size_t)k], b, k, chroms, &text);
           if (text.size() > (1u << 24)) { fwrite(text.data(), 1, text.size(), stdout); text.clear(); }

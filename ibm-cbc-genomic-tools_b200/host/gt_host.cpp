@@ -1113,12 +1113,13 @@ void PrintRegion(const std::string &format, const std::string &raw, const Region
     out->append(chrom); out->push_back('\t'); out->append(source); out->push_back('\t'); out->append(feature); out->push_back('\t');
     AppendLong(out, (long)b.start[lo]); out->push_back('\t'); AppendLong(out, (long)b.stop[lo]); out->push_back('\t'); out->append(score);
     out->push_back('\t'); out->push_back((char)b.strand[lo]); out->push_back('\t'); out->push_back(frame);
-    if (n_tokens > 8) { out->push_back('\t'); out->append(NextToken(&inp, '\t')); }
+    if (n_tokens > 8) { out->push_back('\t'); NextToken(&inp, '\t'); out->append(b.label[k]); }       // LABEL (the caller may have merged another into it)
     if (n_tokens > 9) { out->push_back('\t'); out->append(NextToken(&inp, '\t')); }
     out->push_back('\n');
   } else if (format == "SAM") {                                        // GenomicRegionSAM::Print, :2819-2825
     const int n_tokens = CountTokens(inp, '\t');
-    const char *label = NextToken(&inp, '\t');
+    NextToken(&inp, '\t');
+    const std::string &label = b.label[k];                              // LABEL (the caller may have merged another into it)
     const long flag = atol(NextToken(&inp, '\t'));
     NextToken(&inp, '\t'); NextToken(&inp, '\t');
     const long mapq = atol(NextToken(&inp, '\t'));

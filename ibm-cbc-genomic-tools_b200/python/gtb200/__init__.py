@@ -5,6 +5,7 @@ the shared library is missing or no CUDA device is present, import / Context() r
 import ctypes
 import json
 import os
+import weakref
 
 import numpy as np
 
@@ -26,6 +27,7 @@ OP_COUNT = 0
 OP_COVERAGE = 1
 
 OK = 0
+ERR_ARG = 1
 ERR_QUERY_STOP_NONPOSITIVE = 2
 ERR_QUERY_START_GT_STOP = 3
 ERR_QUERY_REGION = 4
@@ -38,7 +40,7 @@ EXPORTS = [
     "gtb_abi_version", "gtb_ctx_create", "gtb_ctx_destroy", "gtb_ctx_set_stream", "gtb_ctx_get_stream", "gtb_ctx_synchronize",
     "gtb_ctx_last_error", "gtb_ctx_launch_count", "gtb_ctx_transfer_stats", "gtb_ctx_profile", "gtb_ctx_profile_report",
     "gtb_index_create", "gtb_index_destroy", "gtb_index_reset", "gtb_index_add_queries", "gtb_index_add_packed", "gtb_index_finish",
-    "gtb_index_finish_async", "gtb_index_status", "gtb_index_query_counts",
+    "gtb_index_finish_async", "gtb_index_status", "gtb_index_query_counts", "gtb_index_query_matches",
     "gtb_overlap_count", "gtb_overlap_coverage",
     "gtb_mgpu_create", "gtb_mgpu_destroy", "gtb_mgpu_device_count", "gtb_mgpu_ctx", "gtb_mgpu_last_error", "gtb_mgpu_index_create",
     "gtb_mgpu_index_destroy", "gtb_mgpu_index_reset", "gtb_mgpu_index_add_queries", "gtb_mgpu_index_add_packed", "gtb_mgpu_index_finish",
@@ -99,6 +101,7 @@ def load_library(path=LIB_PATH):
         "gtb_index_finish_async": (ci, [vp, vp, u32]),
         "gtb_index_status": (ci, [vp, P(i64)]),
         "gtb_index_query_counts": (ci, [vp, P(_Set), u32, vp, u32, P(i64)]),
+        "gtb_index_query_matches": (ci, [vp, P(_Set), u32, vp, ci, vp, vp, P(i64)]),
         "gtb_overlap_count": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_overlap_coverage": (ci, [vp, P(_Set), u32, P(_Set), u32, vp, P(i64)]),
         "gtb_mgpu_create": (ci, [ci, P(ci), P(vp)]),
@@ -188,9 +191,12 @@ class Context:
         if rc != OK:
             raise GtbError(rc, "gtb_ctx_create failed (no CUDA device? there is no CPU fallback)")
         self.device = device
+        self._children = weakref.WeakSet()      # indexes and scans of this context: closed with it (they hold device memory of it)
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib().gtb_ctx_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -357,6 +363,7 @@ class Index:
         rc = lib().gtb_index_create(ctx._h, ctypes.byref(rs), op, flags, ctypes.byref(self._h), ctypes.byref(err))
         ctx.check(rc, err.value)
         self.n_regions = rs.n_regions
+        ctx._children.add(self)
 
     def close(self):
         if self._h:
@@ -399,6 +406,20 @@ class Index:
         self.ctx.check(rc, err.value)
         return out
 
+    def query_matches(self, queries, offsets=None, bin_bits=None):
+        """(match_offset, matches): for every query region of the host arrays the index regions it overlaps, in the order the
+        reference's GetOverlap / NextOverlap walk hands them out (bin_bits: the -B list of the Unsorted class)"""
+        counts = self.query_counts(queries, offsets=offsets)
+        st, keep = host_set(queries, None, offsets)
+        off = np.concatenate([[0], np.cumsum(counts.astype(np.int64))]).astype(np.int64)
+        matches = np.zeros(max(int(off[-1]), 1), dtype=np.int32)
+        bits = None if bin_bits is None else np.ascontiguousarray(bin_bits, dtype=np.int32)
+        err = ctypes.c_int64(-1)
+        rc = lib().gtb_index_query_matches(self._h, ctypes.byref(st), MEM_HOST, None if bits is None else _np_ptr(bits), 0 if bits is None else len(bits),
+                                           _np_ptr(off), _np_ptr(matches), ctypes.byref(err))
+        self.ctx.check(rc, err.value)
+        return off, matches[:int(off[-1])]
+
     def finish(self, out=None):
         if out is None:
             out = np.zeros(self.n_regions, dtype=np.uint64)
@@ -431,6 +452,7 @@ class Scan:
         b = np.ascontiguousarray(bound, dtype=np.int64)
         prm = _ScanParams(win_step, win_size, min_reads, ord(op), int(ignore_strand), int(emulate_sorted), 0)
         ctx.check(lib().gtb_scan_create(ctx._h, len(b), _np_ptr(b), ctypes.byref(prm), ctypes.byref(self._h)))
+        ctx._children.add(self)
 
     def close(self):
         if self._h:

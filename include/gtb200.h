@@ -162,6 +162,18 @@ int  gtb_index_status(gtb_index *index, int64_t *err_index);
  * streamed with gtb_index_add_queries are unaffected.  out[k] belongs to query region k (host or device memory: out_mem).
  * Synchronous.  Fatal query conditions are reported as by gtb_index_finish. */
 int  gtb_index_query_counts(gtb_index *index, const gtb_set *queries, unsigned mem, uint32_t *out, unsigned out_mem, int64_t *err_index);
+/* The walk itself: the index regions (0-based numbers in index-file order) that GetOverlap / NextOverlap hand out for every
+ * query region, in the order the reference's engine hands them out -- what `genomic_overlaps overlap -label` prints as
+ * "query-label:index-label", one line per step (genomic_overlaps.cpp:718-731).  The Unsorted class walks its bin levels in
+ * turn, the bins of a level from the query's first to its last, every bin's chain from the region inserted last to the first
+ * (genomic_intervals.cpp:5665-5669, :5729-5764): bin_bits[0..n_bin_bits) are the shift-bits of the levels (the -B option; NULL =
+ * the default 17,20,23,26; the closing level of 60 bits is added as the reference does, :5637).  Under GTB_SORTED_RULES the
+ * matches of a query come in index-file order (the Sorted class's buffer, :5902-5927).
+ * match_offset[k] .. match_offset[k + 1] says where query k's matches go in `matches`, relative to match_offset[0]: the
+ * running sum of gtb_index_query_counts' result for the same queries (n_regions + 1 entries; GTB_ERR_ARG if it disagrees).
+ * Queries and outputs are host memory.  Synchronous.  Fatal query conditions are reported as by gtb_index_finish. */
+int  gtb_index_query_matches(gtb_index *index, const gtb_set *queries, unsigned mem, const int *bin_bits, int n_bin_bits,
+                             const int64_t *match_offset, int32_t *matches, int64_t *err_index);
 
 /* One-shot conveniences == create + add + finish + destroy.
  * gtb_overlap_count    <-> GenomicRegionSetOverlaps::CountIndexOverlaps(match_gaps, ignore_strand, max_label_value)  genomic_intervals.h:2471, .cpp:5304-5317

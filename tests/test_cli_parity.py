@@ -407,8 +407,53 @@ def test_subset_overlap_sam_sorted_and_errors(files, samfiles, tmp_path):
     (tmp_path / "bad2.bed").write_text("\n".join(lines) + "\n")
     want, got = both("genomic_overlaps", ["subset", d / "idx.bed", tmp_path / "bad2.bed"])
     assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
-    # -label is refused (the order of the matches is the bin index's business)
-    assert run_new("genomic_overlaps", ["overlap", "-label", d / "idx.bed", d / "q.bed"])[0] == 1
+
+
+@pytest.fixture(scope="module")
+def labelfiles(tmp_path_factory):
+    """index regions of every size from 10 bp to 2 Mbp (so that they land in every level of the reference's bin index and
+    share bins), queries long enough to walk several bins of several levels; plain, multi-interval and sorted copies"""
+    d = tmp_path_factory.mktemp("label")
+    rng = np.random.default_rng(4242)
+    def regions(n, max_len_log2, tag):
+        chrom = rng.integers(0, 3, n)
+        length = (2.0 ** rng.uniform(3.3, max_len_log2, n)).astype(np.int64)
+        start = rng.integers(0, 6_000_000, n)
+        strand = rng.integers(0, 2, n)
+        return ["chr%d\t%d\t%d\t%s%d\t0\t%s\n" % (chrom[k] + 1, start[k], start[k] + length[k], tag, k, "+-"[strand[k]]) for k in range(n)]
+    idx, q = regions(3000, 21, "g"), regions(6000, 18.5, "q")
+    (d / "idx.bed").write_text("".join(idx))
+    (d / "q.bed").write_text("".join(q))
+    (d / "q.gff").write_text("".join("%s\tsrc\tfeat\t%d\t%s\t.\t%s\t.\t%s\tnote\n" % (t[0], int(t[1]) + 1, t[2], t[5].strip(), t[3]) for t in (l.split("\t") for l in q)))
+    (d / "q.sam").write_text("@HD\tVN:1.0\n" + "".join("%s\t%d\t%s\t%d\t60\t%dM\t=\t7\t-3\t*\t*\n" % (t[3], 16 if t[5].strip() == "-" else 0, t[0], int(t[1]) + 1, int(t[2]) - int(t[1]))
+                                                        for t in (l.split("\t") for l in q[:1500])))
+    for name in ("idx.bed", "q.bed"):
+        env = dict(os.environ, LC_ALL="C")
+        with open(d / ("s_" + name), "wb") as f:
+            subprocess.check_call(["sort", "-s", "-k1,1", "-k2,2n", str(d / name)], stdout=f, env=env)
+        with open(d / ("ss_" + name), "wb") as f:
+            subprocess.check_call(["sort", "-s", "-k1,1", "-k6,6", "-k2,2n", str(d / name)], stdout=f, env=env)
+    return d
+
+
+@pytest.mark.parametrize("flags", [[], ["-i"], ["-gaps"], ["-B", "8,12"], ["-B", "19"], ["-B", "10,11,12,13,14,15,16"], ["-S"], ["-S", "-i"], ["-S", "-s"]])
+def test_overlap_label(labelfiles, files, flags):
+    """overlap -label: one line per (query, matching reference region) labelled "query:reference", in the order the reference's
+    engine walks the matches -- bin levels, bins, LIFO chains for the default engine (any -B), file order under -S"""
+    d = labelfiles
+    stem = "ss_" if "-s" in flags else "s_" if "-S" in flags else ""
+    want = assert_same("genomic_overlaps", ["overlap", "-label"] + flags + [d / (stem + "idx.bed"), d / (stem + "q.bed")], nonempty=True)
+    assert want[1].count(b"\n") > 10000
+    if not flags:
+        # the walk does tell bin layouts apart on this input
+        other = support.run_ref("genomic_overlaps", ["overlap", "-label", "-B", "8,12", d / "idx.bed", d / "q.bed"], check=False)
+        assert other[1] != want[1] and sorted(other[1].splitlines()) == sorted(want[1].splitlines())
+        for name in ("q.gff", "q.sam"):
+            assert_same("genomic_overlaps", ["overlap", "-label", d / "idx.bed", d / name], nonempty=True)
+        r = files["dir"]
+        for pair in (("midx.bed", "mq.bed"), ("midx.reg", "mq.reg"), ("idx.bed", "mq.reg"), ("midx.bed", "q.bed")):
+            assert_same("genomic_overlaps", ["overlap", "-label", r / pair[0], r / pair[1]], nonempty=True)
+            assert_same("genomic_overlaps", ["overlap", "-label", "-gaps", "-i", r / pair[0], r / pair[1]], nonempty=True)
 
 
 @pytest.mark.parametrize("name", ["q.bed", "q.reg", "q.gff", "mq.bed", "mq.reg", "q.sam", "idx_space.bed", "q.bed.gz"])

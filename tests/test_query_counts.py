@@ -115,3 +115,71 @@ def test_query_counts_fatal_queries(gtb, ctx):
     q["start"][1] = 150
     assert list(ix.query_counts(q)) == [1, 0, 1]
     ix.close()
+
+
+def bin_order_key(idx, ioff, bits):
+    """(level, bin, -k) of every admitted index region in the reference's bin index (genomic_intervals.cpp:5653-5672)"""
+    ioff = np.arange(len(idx["chrom"]) + 1) if ioff is None else ioff
+    bits = list(bits) + [60]
+    key = {}
+    for k in range(len(ioff) - 1):
+        s, e = int(idx["start"][ioff[k]]), int(idx["stop"][ioff[k + 1] - 1])
+        if s > e or e <= 0:
+            continue
+        s = max(s, 1)
+        for l, b in enumerate(bits):
+            if (s >> b) == (e >> b):
+                key[k] = (l, s >> b, -k)
+                break
+    return key
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_query_matches_vs_brute_force(gtb, ctx, seed):
+    """gtb_index_query_matches: the matching index regions of every query, in the order of the reference's walk (bin levels, bins,
+    LIFO chains; file order under GTB_SORTED_RULES), against the pair-by-pair definition"""
+    rng = np.random.default_rng(1900 + seed)
+    if seed % 2 == 0:
+        idx, ioff = randcases.rand_single(rng, 300), None
+        q, qoff = randcases.rand_single(rng, 2500, strands="+-."), None
+        idx["start"] = (idx["start"].astype(np.int64) * 37).astype(np.int32); idx["stop"] = (idx["stop"].astype(np.int64) * 37 + 30).astype(np.int32)
+        q["start"] = (q["start"].astype(np.int64) * 37).astype(np.int32); q["stop"] = (q["stop"].astype(np.int64) * 37 + 30).astype(np.int32)
+        bad = (q["start"] > q["stop"]) | (q["stop"] <= 0)
+        q["start"][bad] = 5; q["stop"][bad] = 50
+    else:
+        idx, ioff = randcases.rand_multi(rng, 200)
+        q, qoff = randcases.rand_multi(rng, 1200)
+    qo = np.arange(len(q["chrom"]) + 1) if qoff is None else qoff
+    io = np.arange(len(idx["chrom"]) + 1) if ioff is None else ioff
+    for flags, bits in ((0, None), (gtb.IGNORE_STRAND, [3, 6]), (gtb.MATCH_GAPS, [5]), (gtb.MATCH_GAPS | gtb.IGNORE_STRAND, [2, 4, 6, 8, 10, 12, 14]), (gtb.SORTED_RULES, None)):
+        odd = np.array([idx["start"][io[k]] > idx["stop"][io[k + 1] - 1] or idx["stop"][io[k + 1] - 1] <= 0 for k in range(len(io) - 1)])
+        ix = gtb.Index(ctx, idx, gtb.OP_COUNT, flags, roffsets=ioff)
+        if flags & gtb.SORTED_RULES and odd.any():
+            with pytest.raises(gtb.GtbError):
+                ix.query_matches(q, offsets=qoff)
+            ix.close()
+            continue
+        off, got = ix.query_matches(q, offsets=qoff, bin_bits=bits)
+        counts = brute(q, qoff, idx, ioff, bool(flags & gtb.MATCH_GAPS), bool(flags & gtb.IGNORE_STRAND))
+        assert np.array_equal(np.diff(off), counts), (seed, flags)
+        key = bin_order_key(idx, ioff, bits or [17, 20, 23, 26])
+        for a in rng.choice(len(qo) - 1, 300, replace=False):
+            m = [int(v) for v in got[off[a]:off[a + 1]]]
+            if len(m) < 2:
+                continue
+            want = sorted(m) if flags & gtb.SORTED_RULES else sorted(m, key=lambda k: key[k])
+            assert m == want, (seed, flags, a, m, want)
+            one = brute({k: v[qo[a]:qo[a + 1]] for k, v in q.items()}, None if qoff is None else np.array([0, qo[a + 1] - qo[a]]), idx, ioff,
+                        bool(flags & gtb.MATCH_GAPS), bool(flags & gtb.IGNORE_STRAND))
+            assert int(one[0]) == len(m) == len(set(m))
+        ix.close()
+    # offsets that do not belong to these queries are an argument error, not a buffer overrun
+    ix = gtb.Index(ctx, idx, gtb.OP_COUNT, 0, roffsets=ioff)
+    st, keep = gtb.host_set(q, None, qoff)
+    import ctypes
+    off = np.zeros(st.n_regions + 1, dtype=np.int64)
+    matches = np.zeros(4, dtype=np.int32)
+    err = ctypes.c_int64(-1)
+    rc = gtb.lib().gtb_index_query_matches(ix._h, ctypes.byref(st), gtb.MEM_HOST, None, 0, off.ctypes.data_as(ctypes.c_void_p), matches.ctypes.data_as(ctypes.c_void_p), ctypes.byref(err))
+    assert rc == gtb.ERR_ARG
+    ix.close()
