@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(128) query_matches_kernel(QueryView q, RankVie
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < q.n_regions; r += stride) {
     const int64_t room = match_off[r + 1] - match_off[r];
     int32_t *dst = match_out + (match_off[r] - match_base);
+    GTB_ASSERT(room >= 0 && match_off[r] >= match_base);
     int64_t n = 0;
     int64_t lo, hi;
     if (admit_query(q, r, ix, lo, hi)) {

@@ -143,7 +143,12 @@ def test_config1_and_4_first_10M_reads(ctx, oracle, gtb, m, seed, lens):
     dev = {"chrom": torch.empty(n, dtype=torch.int32, device="cuda"), "start": torch.empty(n, dtype=torch.int32, device="cuda"),
            "stop": torch.empty(n, dtype=torch.int32, device="cuda"), "strand": torch.empty(n, dtype=torch.int8, device="cuda")}
     ctx.synth_reads(2, 0, n, 50, support.HG19_LENS, dev)
-    for flags in (0, gtb.IGNORE_STRAND) if m < 90_000 else (0,):           # (the oracle needs half a minute per pass over 1 M regions)
+    # (the scalar oracle needs half a minute per pass over 1 M regions: its count and coverage passes run side by side, ctypes
+    # releases the interpreter lock for the duration of a call)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(2)
+    cov_pass = pool.submit(oracle.coverage, reads, regions, 0)
+    for flags in (0, gtb.IGNORE_STRAND) if m < 90_000 else (0,):
         rc, want, _ = oracle.count(reads, regions, flags)
         assert rc == 0
         for eng in (0, gtb.ENGINE_BUCKET) + ((gtb.ENGINE_DIRECT,) if m < 90_000 else ()):
@@ -152,7 +157,8 @@ def test_config1_and_4_first_10M_reads(ctx, oracle, gtb, m, seed, lens):
             got = ix.finish()
             ix.close()
             assert np.array_equal(got, want), (m, flags, eng)
-    rc, want, _ = oracle.coverage(reads, regions, 0)
+    rc, want, _ = cov_pass.result()
+    pool.shutdown()
     assert rc == 0
     ix = gtb.Index(ctx, regions, gtb.OP_COVERAGE, 0)
     ix.add_device(dev)
