@@ -30,20 +30,3 @@ def pytest_collection_modifyitems(config, items):
         if "gpu" in item.keywords:
             item.add_marker(skip)
 
-
-@pytest.fixture(scope="session", autouse=True)
-def _device_kept_initialised():
-    """The command-line drivers are separate processes, each of which creates a CUDA context.  Without a client the driver tears the
-    device's state down when a process exits and the next one pays for bringing it up again (about a second per invocation, several
-    hundred invocations in the suite); one context held by the test session itself keeps the device initialised, as
-    `nvidia-smi -pm 1` would.  Nothing is computed on it."""
-    ctx = None
-    if _have_gpu():
-        try:
-            import gtb200
-            ctx = gtb200.Context(0)
-        except Exception:
-            ctx = None
-    yield
-    if ctx is not None:
-        ctx.close()

@@ -124,7 +124,10 @@ def test_union(union_files, files, name):
                                    ["-d", "50", "--label-func", "min"], ["--label-func", "max", "-d", "1000"]])
 def test_link(files, flags):
     stem = "ss" if "-s" in flags else "s"
-    for ext in ("bed", "reg", "gff", "sam"):
+    # every format under the plain, the -s and the label-function runs; BED and one other format elsewhere (each run is a process
+    # with a CUDA context of its own)
+    every = flags in ([], ["-s"], ["--label-func", "+"], ["-s", "--label-func", "sum"])
+    for ext in ("bed", "reg", "gff", "sam") if every else ("bed", ("reg", "gff", "sam")[len(flags) % 3]):
         want, got = run_both(["link"] + flags + [files / ("%s.%s" % (stem, ext))])
         assert got[0] == want[0] == 0 and got[1] == want[1], (flags, ext, got[1][:200], want[1][:200], got[2][-200:])
         assert len(want[1]) > 0
