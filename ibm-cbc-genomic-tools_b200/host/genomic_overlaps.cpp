@@ -101,7 +101,7 @@ static gtb_ctx *wait_context() {
   return g_ctx;
 }
 
-int main(int argc, char *argv[]) {
+static int driver_main(int argc, char *argv[]) {
   gt::CmdLine cmd(PROGRAM, VERSION);
   const char *USAGE = "[OPTIONS] REFERENCE-REGION-FILE <TEST-REGION-FILE>";
   cmd.AddOperation("annotate", USAGE, "Annotates test regions according to reference regions.", "");
@@ -395,4 +395,9 @@ int main(int argc, char *argv[]) {
   // the process is about to end: the driver reclaims device memory faster than freeing it buffer by buffer would
   (void)index; (void)mindex;
   return 0;
+}
+
+// the driver's work is done and its output written when driver_main returns: the process leaves through gt::Exit (gt_host.h)
+int main(int argc, char *argv[]) {
+  exit(driver_main(argc, argv));
 }

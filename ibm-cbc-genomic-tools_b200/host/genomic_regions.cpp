@@ -98,7 +98,7 @@ static int run_link(const char *file);
 static int run_inv(const char *file);
 static int run_union(const char *file);
 
-int main(int argc, char *argv[]) {
+static int driver_main(int argc, char *argv[]) {
   gt::CmdLine cmd(PROGRAM, VERSION);
   cmd.AddOperation("gsort", "[OPTIONS] <REGION-SET>", "Global sort: sorts the entire region set.",
                    "* Input formats: REG, GFF, BED, SAM\n  * Operand: region-set\n  * Region requirements: none\n  * Region-set requirements: none");
@@ -356,4 +356,9 @@ static int run_union(const char *file) {
   fflush(stdout);
   if (rr.failed()) rr.Fail();
   return 0;
+}
+
+// the driver's work is done and its output written when driver_main returns: the process leaves through gt::Exit (gt_host.h)
+int main(int argc, char *argv[]) {
+  exit(driver_main(argc, argv));
 }

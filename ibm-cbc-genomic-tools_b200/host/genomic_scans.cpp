@@ -188,7 +188,7 @@ static double ComputeQValues(std::vector<double> pval, std::vector<double> pval_
 
 static int run_peaks(const char *signal_file, const char *control_file, const char *uniq_file);
 
-int main(int argc, char *argv[]) {
+static int driver_main(int argc, char *argv[]) {
   gt::CmdLine cmd(PROGRAM, VERSION);
   cmd.AddOperation("counts", "[OPTIONS] <REG-FILE>", "Determines input read counts in sliding windows of reference regions.", DETAILS);
   cmd.AddOperation("peaks", "[OPTIONS] SIGNAL-REG-FILE [CONTROL-REG-FILE [GENOME-UNIQ-REG-FILE]]", "Scans input reads to identify peaks.", DETAILS);
@@ -412,4 +412,9 @@ static int run_peaks(const char *signal_file, const char *control_file, const ch
   fwrite(text.data(), 1, text.size(), stdout);
   fflush(stdout);
   return 0;
+}
+
+// the driver's work is done and its output written when driver_main returns: the process leaves through gt::Exit (gt_host.h)
+int main(int argc, char *argv[]) {
+  exit(driver_main(argc, argv));
 }
