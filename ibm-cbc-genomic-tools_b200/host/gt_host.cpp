@@ -363,7 +363,7 @@ void LineReader::Produce() {
     const size_t want = tail == 0 && b.data == nullptr ? (1u << 20) : kBlockBytes;
     if (b.cap < carry.size() + want) {
       b.cap = carry.size() + want;
-      b.data = (char *)realloc(b.data, b.cap);
+      b.data = (char *)realloc(b.data, b.cap + 16);                     // (16 spare bytes: the parsers read whole words)
       if (b.data == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
     }
     memcpy(b.data, carry.data(), carry.size());
@@ -372,7 +372,7 @@ void LineReader::Produce() {
     for (;;) {
       if (have == b.cap) {                                             // a line longer than the block
         b.cap *= 2;
-        b.data = (char *)realloc(b.data, b.cap);
+        b.data = (char *)realloc(b.data, b.cap + 16);
         if (b.data == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
       }
       const long got = ReadSome(b.data + have, b.cap - have);
@@ -573,6 +573,9 @@ struct RegionReader::ChromCache {
   int32_t GetShort(const char *p, size_t len) {
     uint64_t k = 0;
     memcpy(&k, p, len);                                                // len < 8 leaves high zero bytes; a name holds no NUL, so keys are unique
+    return GetKey(k, p, len);
+  }
+  int32_t GetKey(uint64_t k, const char *p, size_t len) {
     uint32_t h = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 56);
     for (;;) {
       if (key[h] == k) return val[h];
@@ -791,31 +794,77 @@ bool RegionReader::ParseLine(char *inp, RegionBatch *out, ChromCache *cache, Par
 // to it.  "Clean": every column non-empty and not starting with a blank, start and stop plain digit strings of at most 18
 // digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  The line ends with '\n'
 // (every block does); returns that '\n', or nullptr if the line is not for this path (nothing has been appended then).
+// eight bytes at p as one word (the blocks of LineReader are allocated with 16 spare bytes, so a word that begins inside a line
+// may run past the block's last '\n')
+static inline uint64_t Load8(const char *p) { uint64_t w; memcpy(&w, p, 8); return w; }
+// high bit of every byte of w that equals c (exact up to and including the first match, which is all the callers look at)
+static inline uint64_t EqMask(uint64_t w, unsigned char c) {
+  const uint64_t x = w ^ (0x0101010101010101ull * c);
+  return (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
+}
+// The decimal number at *pp: 1 to 18 digits.  Eight digits at a time: the digit bytes are told from the rest in one word, moved
+// to the word's top (leading zeros below them) and folded pairwise.  *pp is left behind the last digit; false: no digit, or too many.
+static inline bool ParseDigits(const char **pp, unsigned long *value) {
+  const char *p = *pp;
+  const uint64_t t = Load8(p) ^ 0x3030303030303030ull;                  // digits -> 0..9
+  const uint64_t other = ((t + 0x7676767676767676ull) | t) & 0x8080808080808080ull;   // bytes that are not digits
+  const int n = other ? (int)(__builtin_ctzll(other) >> 3) : 8;
+  if (n == 0) return false;
+  uint64_t v = n == 8 ? t : (t & ((1ull << (8 * n)) - 1)) << (8 * (8 - n));
+  v = v * 10 + (v >> 8);
+  v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+  p += n;
+  if (n == 8) {
+    int more = 0;
+    while ((unsigned)(*p - '0') < 10u) { v = v * 10 + (unsigned)(*p++ - '0'); if (++more > 10) return false; }
+  }
+  *pp = p;
+  *value = (unsigned long)v;
+  return true;
+}
+// the first TAB or '\n' at or behind p
+static inline const char *FieldEnd(const char *p) {
+  for (;; p += 8) {
+    const uint64_t w = Load8(p);
+    const uint64_t m = EqMask(w, '\t') | EqMask(w, '\n');
+    if (m) return p + (__builtin_ctzll(m) >> 3);
+  }
+}
+
 char *RegionReader::ParseBedLine(char *line, RegionBatch *out, ChromCache *cache) const {
   const char *p = line;
   if (*p == ' ' || *p == '\t') return nullptr;
-  while (*p != '\t' && *p != '\n') p++;
-  const size_t chrom_len = (size_t)(p - line);
-  if (*p != '\t' || chrom_len == 0 || chrom_len > 8) return nullptr;
-  p++;
+  // the chromosome: at most 8 bytes up to the first TAB, no end of line before it; the bytes are the cache's key
+  const uint64_t w0 = Load8(p);
+  const uint64_t tab = EqMask(w0, '\t'), nl0 = EqMask(w0, '\n');
+  size_t chrom_len;
+  uint64_t chrom_key;
+  if (tab) {
+    if (nl0 && (nl0 & (0 - nl0)) < (tab & (0 - tab))) return nullptr;
+    chrom_len = (size_t)(__builtin_ctzll(tab) >> 3);
+    if (chrom_len == 0) return nullptr;
+    chrom_key = w0 & ((1ull << (8 * chrom_len)) - 1);
+  } else {
+    if (nl0 || p[8] != '\t') return nullptr;
+    chrom_len = 8;
+    chrom_key = w0;
+  }
+  p += chrom_len + 1;
   unsigned long start = 0, stop = 0;
-  const char *d = p;
-  while ((unsigned)(*p - '0') < 10u) start = start * 10 + (unsigned)(*p++ - '0');
-  if (p == d || p - d > 18 || *p != '\t') return nullptr;
-  d = ++p;
-  while ((unsigned)(*p - '0') < 10u) stop = stop * 10 + (unsigned)(*p++ - '0');
-  if (p == d || p - d > 18) return nullptr;
+  if (!ParseDigits(&p, &start) || *p != '\t') return nullptr;
+  ++p;
+  if (!ParseDigits(&p, &stop)) return nullptr;
   char strand = '+';
   const char *label = nullptr, *label_end = nullptr;
   if (*p == '\t') {                                                     // column 4: label
     label = ++p;
     if (*p == ' ' || *p == '\t' || *p == '\n') return nullptr;
-    while (*p != '\t' && *p != '\n') p++;
+    p = FieldEnd(p);
     label_end = p;
     if (*p == '\t') {                                                   // column 5: score
       p++;
       if (*p == ' ' || *p == '\t' || *p == '\n') return nullptr;
-      while (*p != '\t' && *p != '\n') p++;
+      p = FieldEnd(p);
       if (*p == '\t') {                                                 // column 6: strand, then the end of the line
         p++;
         if (p[0] != '\n' && p[1] == '\n') {
@@ -845,7 +894,7 @@ char *RegionReader::ParseBedLine(char *line, RegionBatch *out, ChromCache *cache
     if (w < INT32_MIN || w > INT32_MAX) return nullptr;
     out->weight.push_back((int32_t)w);
   }
-  out->chrom.push_back(cache->GetShort(line, chrom_len));
+  out->chrom.push_back(cache->GetKey(chrom_key, line, chrom_len));
   out->strand.push_back((int8_t)strand);
   out->start.push_back((int32_t)start);
   out->stop.push_back((int32_t)stop);
@@ -1154,11 +1203,12 @@ void (*exit_hook)() = nullptr;
 #undef exit
 void Exit(int code) {
   if (exit_hook) { void (*h)() = exit_hook; exit_hook = nullptr; h(); }
-  // What a driver has printed is flushed here; what is left is to unwind the CUDA runtime (modules unloaded, every allocation freed
-  // one by one, the context destroyed), which the kernel does for a dying process anyway and faster.  GT_FAST_EXIT=0 leaves
-  // the process by exit() as before.
+  // GT_FAST_EXIT=1: what the driver has printed is flushed and the process ends at once, leaving the unwinding of the CUDA runtime
+  // (modules unloaded, every allocation freed one by one, the context destroyed) to the kernel.  Off by default: measured on the
+  // GPU boxes it is lost in the spread of the context's creation (1 to 7 s, profiles/r2ag_cli_exit.json), and profilers that
+  // collect at exit need the ordinary way out.
   const char *env = getenv("GT_FAST_EXIT");
-  if (env == nullptr || env[0] != '0') {
+  if (env != nullptr && env[0] == '1') {
     fflush(nullptr);
     std::cout.flush();
     std::cerr.flush();

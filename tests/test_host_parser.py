@@ -397,3 +397,39 @@ def test_bam_input_matches_reference_reader(tmp_path, with_header):
     rc, want, err = support.run_ref("genomic_overlaps", ["subset", "-inv", tmp_path / "far.bed", path], check=False)
     rc2, got, err2 = dump(path, {}, args=("-p",))
     assert (rc2, got) == (rc, want), (got[:400], want[:400], err[-300:], err2[-300:])
+
+
+def test_bed_fast_path_word_boundaries(tmp_path):
+    """The clean-BED path reads whole 8-byte words (chromosome key, eight digits at a time, field ends): chromosome names of every
+    length around 8, numbers of 1 to 18 digits with and without leading zeros, labels and scores of every length around the word
+    size, every strand spelling, 3 to 6 columns -- against the reference's reader, in one piece and in many small ones."""
+    rng = np.random.default_rng(808)
+    chroms = ["c", "c2", "chr", "chr1", "chr10", "chrUn_g", "chrUn_gl", "chrUn_gl0", "12345678", "123456789", "scaffold_123456789"]
+    lines = []
+    for k in range(40000):
+        c = chroms[rng.integers(len(chroms))]
+        nd = int(rng.integers(1, 10))
+        a = int(rng.integers(10 ** (nd - 1) if nd > 1 else 0, 10 ** nd))
+        b = a + int(rng.integers(0, 2000))
+        sa, sb = str(a), str(b)
+        if rng.random() < 0.1:
+            sa = "0" * int(rng.integers(1, 19 - len(sa))) + sa
+        if rng.random() < 0.1:
+            sb = "0" * int(rng.integers(1, 20 - len(sb))) + sb                 # up to 19 characters: one more than the fast path takes
+        t = [c, sa, sb]
+        cols = int(rng.integers(3, 7))
+        if cols >= 4:
+            t.append("L" * int(rng.integers(1, 20)) if rng.random() < 0.5 else str(int(rng.integers(-5, 100000))))
+        if cols >= 5:
+            t.append("9" * int(rng.integers(1, 18)) if rng.random() < 0.5 else "0.%d" % k)
+        if cols >= 6:
+            t.append(["+", "-", ".", "1", "-1"][rng.integers(5)])
+        lines.append("\t".join(t))
+    lines += ["chr1\t1999999999\t2000000100\ta\t0\t+", "chr1\t2147483646\t2147483647", "chr1\t99999999\t100000000\tx", "chr1\t12345678\t123456789\tx\t5\t-1"]
+    path = tmp_path / "words.bed"
+    path.write_text("\n".join(lines) + "\n")
+    want = ref_reg(path)
+    assert want[0] == 0
+    for env in ({"GT_PARSE_THREADS": "1"}, {"GT_PARSE_THREADS": "5", "GT_PARSE_PIECE_BYTES": "777"}):
+        got = dump(path, env)
+        assert got[0] == 0 and strip_extras(got[1]) == want[1], env
