@@ -9,6 +9,7 @@
 #include <time.h>
 #include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <functional>
 #include <iostream>
 
@@ -116,22 +117,180 @@ void CmdLine::OperationUsage() {
 // ---------------------------------------------------------------------------------------------
 static const size_t kBlockBytes = 32u << 20;
 
+// [offset, offset + want) of a regular file into dst; returns the bytes read (short only at the end of the file or on an error)
+static size_t PreadAll(int fd, char *dst, size_t want, off_t offset) {
+  size_t have = 0;
+  while (have < want) {
+    const ssize_t got = pread(fd, dst + have, want - have, offset + (off_t)have);
+    if (got < 0 && errno == EINTR) continue;
+    if (got <= 0) break;
+    have += (size_t)got;
+  }
+  return have;
+}
+
+// BGZF -- what bgzip and samtools write (SAM specification, section 4.1): a series of gzip members of at most 64 KB of data each,
+// every one carrying its own compressed size in a 'BC' extra field.  zlib's gzread walks them one after the other on one thread
+// (170 MB/s of text); here the members of a stretch of the file are found by their size fields and inflated side by side.  What
+// the reader hands out is what gzread would: the data of every complete member in file order and, from a member the file ends
+// in, whatever inflates -- then the end of the input.  A complete member that does not inflate to what its trailer promises ends
+// the input in front of it.
+struct LineReader::Bgzf {
+  int fd;
+  off_t offset = 0;
+  int threads;
+  bool file_end = false, stream_end = false;
+  std::vector<unsigned char> comp;                                      // compressed bytes not consumed yet
+  std::vector<char> out;                                                // the inflated stretch
+  size_t out_pos = 0;
+  struct Member { size_t cdata, clen, at; uint32_t isize, crc; bool ok; };
+  static const size_t kStretch = 16u << 20;
+  explicit Bgzf(int f) : fd(f) {
+    const char *env = getenv("GT_INFLATE_THREADS");
+    threads = env ? atoi(env) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (threads < 1) threads = 1;
+  }
+  static uint32_t U16(const unsigned char *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+  static uint32_t U32(const unsigned char *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+  // the size of the member whose header starts at p (n bytes available), 0 if the header is not all there, -1 if it is no BGZF header
+  static long MemberSize(const unsigned char *p, size_t n, size_t *cdata_at) {
+    if (n < 12) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+    const size_t xlen = U16(p + 10);
+    if (n < 12 + xlen) return 0;
+    for (size_t x = 12; x + 4 <= 12 + xlen;) {
+      const size_t slen = U16(p + x + 2);
+      if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2 && x + 6 <= 12 + xlen) {
+        const long bsize = (long)U16(p + x + 4) + 1;
+        if ((size_t)bsize < 12 + xlen + 8) return -1;
+        *cdata_at = 12 + xlen;
+        return bsize;
+      }
+      x += 4 + slen;
+    }
+    return -1;
+  }
+  static bool IsBgzf(int fd) {                                          // does the file begin with a BGZF member?
+    unsigned char h[512];
+    const ssize_t got = pread(fd, h, sizeof h, 0);
+    size_t at;
+    return got >= 18 && MemberSize(h, (size_t)got, &at) > 0;
+  }
+  // raw deflate data -> dst; returns the bytes written (all of `room` expected), *ok = the stream ended where it should
+  static size_t InflateRaw(z_stream *zs, const unsigned char *src, size_t n, char *dst, size_t room, bool *ok) {
+    inflateReset(zs);
+    zs->next_in = const_cast<unsigned char *>(src); zs->avail_in = (unsigned)n;
+    zs->next_out = (unsigned char *)dst; zs->avail_out = (unsigned)room;
+    const int rc = inflate(zs, Z_FINISH);
+    *ok = rc == Z_STREAM_END && zs->avail_out == 0;
+    return room - zs->avail_out;
+  }
+  bool Fill() {                                                         // the next stretch; false at the end of the stream
+    out.clear(); out_pos = 0;
+    while (!stream_end && out.empty()) {
+      while (!file_end && comp.size() < kStretch) {
+        const size_t have = comp.size();
+        comp.resize(have + kStretch);
+        const size_t got = PreadAll(fd, (char *)comp.data() + have, kStretch, offset);
+        offset += (off_t)got;
+        comp.resize(have + got);
+        if (got < kStretch) file_end = true;
+      }
+      // the complete members of the buffer
+      std::vector<Member> mem;
+      size_t at = 0, total = 0;
+      bool broken = false;                                              // what is left at `at` is no complete member and never will be
+      for (;;) {
+        size_t cdata = 0;
+        const long bsize = MemberSize(comp.data() + at, comp.size() - at, &cdata);
+        if (bsize < 0) { broken = true; break; }
+        if (bsize == 0 || (size_t)bsize > comp.size() - at) { broken = file_end && comp.size() > at; break; }
+        const unsigned char *m = comp.data() + at;
+        mem.push_back({at + cdata, (size_t)bsize - cdata - 8, total, U32(m + bsize - 4), U32(m + bsize - 8), false});
+        total += mem.back().isize;
+        at += (size_t)bsize;
+      }
+      out.resize(total);
+      std::atomic<size_t> next{0};
+      auto work = [&] {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) return;
+        for (size_t i; (i = next.fetch_add(1)) < mem.size();) {
+          Member &b = mem[i];
+          bool ok = false;
+          InflateRaw(&zs, comp.data() + b.cdata, b.clen, out.data() + b.at, b.isize, &ok);
+          b.ok = ok && (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const unsigned char *)out.data() + b.at, b.isize) == b.crc;
+        }
+        inflateEnd(&zs);
+      };
+      const int n_threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, mem.size() / 8));
+      std::vector<std::thread> th;
+      for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+      work();
+      for (auto &t : th) t.join();
+      // a member that did not inflate as its header promised ends the stream behind whatever it did yield (as gzread would)
+      size_t good = 0;
+      while (good < mem.size() && mem[good].ok) good++;
+      if (good < mem.size() || broken) {
+        stream_end = true;
+        // (a complete member that is damaged yields nothing: its bytes up to the fault would be noise; a member the file ends in
+        // yields what inflates, which is what zlib hands out before it reports the unexpected end of the file)
+        size_t keep = good < mem.size() ? mem[good].at : total;
+        const unsigned char *src = nullptr;
+        size_t n = 0;
+        if (good == mem.size()) {                                       // the fragment behind the last complete member
+          size_t cdata = 0;
+          if (MemberSize(comp.data() + at, comp.size() - at, &cdata) != -1 && comp.size() - at > cdata && cdata > 0) { src = comp.data() + at + cdata; n = comp.size() - at - cdata; }
+        }
+        out.resize(keep);
+        if (src != nullptr && n > 0) {
+          z_stream zs;
+          memset(&zs, 0, sizeof zs);
+          if (inflateInit2(&zs, -15) == Z_OK) {
+            out.resize(keep + 65536);
+            zs.next_in = const_cast<unsigned char *>(src); zs.avail_in = (unsigned)std::min<size_t>(n, 1u << 20);
+            zs.next_out = (unsigned char *)out.data() + keep; zs.avail_out = 65536;
+            inflate(&zs, Z_SYNC_FLUSH);
+            out.resize(keep + (65536 - zs.avail_out));
+            inflateEnd(&zs);
+          }
+        }
+      } else {
+        comp.erase(comp.begin(), comp.begin() + (long)at);
+        if (file_end && comp.empty()) stream_end = true;
+      }
+    }
+    return !out.empty();
+  }
+  long Read(void *dst, size_t want) {
+    size_t done = 0;
+    while (done < want) {
+      if (out_pos == out.size() && !Fill()) break;
+      const size_t n = std::min(want - done, out.size() - out_pos);
+      memcpy((char *)dst + done, out.data() + out_pos, n);
+      out_pos += n; done += n;
+    }
+    return (long)done;
+  }
+};
+
 // BAM (core.cpp:371-430, FileBufferBAM): the reference hands the header text out line by line and then every alignment as the
 // SAM line samtools' bam_format1_core writes for it (samtools/bam.c:256-340), and parses those lines as SAM.  Same here: the
 // producer thread inflates the BGZF stream (a series of gzip members: zlib's gzread walks them), decodes the records and fills
 // the line blocks with that text.  A truncated file ends the input where the last complete record ends, as samread() < 0 does.
 struct LineReader::BamDecoder {
-  gzFile gz;
+  std::function<long(void *, size_t)> read_inflated;
   std::vector<std::string> ref;                                         // reference sequence names
   std::string out;                                                      // text not handed out yet
   size_t out_pos = 0;
   std::vector<unsigned char> rec;
   bool eof = false;
-  explicit BamDecoder(gzFile g) : gz(g) {}
+  explicit BamDecoder(std::function<long(void *, size_t)> r) : read_inflated(std::move(r)) {}
   bool ReadExact(void *dst, size_t n) {
     size_t have = 0;
     while (have < n) {
-      const int got = gzread(gz, (char *)dst + have, (unsigned)std::min<size_t>(n - have, 1u << 30));
+      const long got = read_inflated((char *)dst + have, n - have);
       if (got <= 0) return false;
       have += (size_t)got;
     }
@@ -263,14 +422,17 @@ LineReader::LineReader(const char *path) {
     unsigned char magic[2] = {0, 0};
     const ssize_t got = pread(fd_, magic, 2, 0);                       // gzip sniff by magic (core.cpp:1757-1775)
     if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-      gz_ = gzdopen(fd_, "rb");
+      struct stat fst;
+      const char *no_bgzf = getenv("GT_NO_BGZF");                        // (tests: the same file through zlib's gzread)
+      if (!(no_bgzf && no_bgzf[0] == '1') && fstat(fd_, &fst) == 0 && S_ISREG(fst.st_mode) && Bgzf::IsBgzf(fd_)) bgzf_ = new Bgzf(fd_);
+      gz_ = gzdopen(bgzf_ ? dup(fd_) : fd_, "rb");                       // (with BGZF the handle only marks the stream as gzip)
       if (gz_ == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
       gzbuffer(gz_, 1 << 20);
-      const int got4 = gzread(gz_, prefix_, 4);                          // BAM or gzipped text (GetFileType, core.cpp:1764-1772)
-      prefix_len_ = got4 > 0 ? got4 : 0;
+      const long got4 = ReadInflated(prefix_, 4);                        // BAM or gzipped text (GetFileType, core.cpp:1764-1772)
+      prefix_len_ = got4 > 0 ? (int)got4 : 0;
       if (prefix_len_ == 4 && memcmp(prefix_, "BAM\1", 4) == 0) {
         prefix_len_ = 0;
-        bam_ = new BamDecoder(gz_);
+        bam_ = new BamDecoder([this](void *dst, size_t n) { return ReadInflated(dst, n); });
         bam_->ReadHeader();
       }
     }
@@ -292,20 +454,14 @@ LineReader::~LineReader() {
   producer_.join();
   delete bam_;
   if (gz_) gzclose(gz_);
-  else if (fd_ > 0) close(fd_);
+  if (bgzf_) { delete bgzf_; close(fd_); }
+  else if (!gz_ && fd_ > 0) close(fd_);
   for (auto &b : block_) free(b.data);
 }
 
-// [offset, offset + want) of a regular file into dst; returns the bytes read (short only at the end of the file or on an error)
-static size_t PreadAll(int fd, char *dst, size_t want, off_t offset) {
-  size_t have = 0;
-  while (have < want) {
-    const ssize_t got = pread(fd, dst + have, want - have, offset + (off_t)have);
-    if (got < 0 && errno == EINTR) continue;
-    if (got <= 0) break;
-    have += (size_t)got;
-  }
-  return have;
+long LineReader::ReadInflated(void *dst, size_t want) {
+  if (bgzf_) return bgzf_->Read(dst, want);
+  return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
 }
 
 long LineReader::ReadSome(char *dst, size_t want) {
@@ -316,7 +472,7 @@ long LineReader::ReadSome(char *dst, size_t want) {
     prefix_pos_ += (int)n;
     return (long)n;
   }
-  if (gz_) return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
+  if (gz_) return ReadInflated(dst, want);
   if (regular_) {
     // a regular file: one read() copies out of the page cache at a few GB/s, which the parsing threads outrun -- large requests
     // are split over a few threads

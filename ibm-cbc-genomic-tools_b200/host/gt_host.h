@@ -90,6 +90,9 @@ class LineReader {
   int fd_ = -1;
   struct BamDecoder;                                  // BAM input: records re-spelt as SAM text lines, as the reference's FileBufferBAM does
   BamDecoder *bam_ = nullptr;
+  struct Bgzf;                                        // blocked gzip (bgzip, BAM): the members of a stretch of the file are inflated side by side
+  Bgzf *bgzf_ = nullptr;
+  long ReadInflated(void *dst, size_t want);          // from the gzip stream, whichever way it is read
   char prefix_[4];                                    // the first inflated bytes of a gzip file (read to tell BAM from text)
   int prefix_len_ = 0, prefix_pos_ = 0;
   bool regular_ = false;                              // a regular file, read with pread at offset_ (by several threads when the request is large)
