@@ -284,7 +284,6 @@ struct LineReader::BamDecoder {
   std::vector<std::string> ref;                                         // reference sequence names
   std::string out;                                                      // text not handed out yet
   size_t out_pos = 0;
-  std::vector<unsigned char> rec;
   bool eof = false;
   explicit BamDecoder(std::function<long(void *, size_t)> r) : read_inflated(std::move(r)) {}
   bool ReadExact(void *dst, size_t n) {
@@ -298,7 +297,6 @@ struct LineReader::BamDecoder {
   }
   static int32_t I32(const unsigned char *p) { return (int32_t)((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24); }
   static uint32_t U16(const unsigned char *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
-  void PutInt(long long v) { char b[24]; const int n = snprintf(b, sizeof b, "%lld", v); out.append(b, (size_t)n); }
   // after the magic: l_text, text, n_ref, (l_name, name, l_ref) x n_ref
   void ReadHeader() {
     unsigned char w[4];
@@ -329,15 +327,18 @@ struct LineReader::BamDecoder {
       ref.push_back(name);
     }
   }
-  // one alignment -> one SAM line (bam_format1_core with decimal flags)
-  bool NextRecord() {
-    unsigned char w[4];
-    if (!ReadExact(w, 4)) return false;
-    const int32_t block = I32(w);
-    if (block < 32) return false;
-    rec.resize((size_t)block);
-    if (!ReadExact(rec.data(), (size_t)block)) return false;
-    const unsigned char *r = rec.data();
+  // one alignment (the `block` bytes behind its length field) -> one SAM line appended to *out (bam_format1_core with decimal
+  // flags); false: the record is malformed (the stream ends in front of it, as samread() < 0 ends the reference's)
+  static void PutInt(std::string *out, long long v) {
+    char b[24];
+    char *e = b + sizeof b, *p = e;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { *--p = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *--p = '-';
+    out->append(p, (size_t)(e - p));
+  }
+  static bool FormatRecord(const unsigned char *r, int32_t block, const std::vector<std::string> &ref, std::string *outp) {
+    std::string &out = *outp;
     const int32_t tid = I32(r), pos = I32(r + 4);
     const uint32_t l_qname = r[8], mapq = r[9], n_cigar = U16(r + 12), flag = U16(r + 14);
     const int32_t l_seq = I32(r + 16), mtid = I32(r + 20), mpos = I32(r + 24), isize = I32(r + 28);
@@ -345,23 +346,32 @@ struct LineReader::BamDecoder {
     if (l_seq < 0 || l_qname == 0 || fixed > (size_t)block) return false;
     const unsigned char *qname = r + 32, *cigar = qname + l_qname, *seq = cigar + 4 * n_cigar, *qual = seq + (l_seq + 1) / 2, *aux = qual + l_seq;
     const unsigned char *end = r + block;
-    auto name_of = [&](int32_t id) { if (id >= 0 && (size_t)id < ref.size()) out += ref[(size_t)id]; else PutInt(id); };
+    auto name_of = [&](int32_t id) { if (id >= 0 && (size_t)id < ref.size()) out += ref[(size_t)id]; else PutInt(&out, id); };
     out.append((const char *)qname, l_qname - 1); out.push_back('\t');
-    PutInt(flag); out.push_back('\t');
+    PutInt(&out, flag); out.push_back('\t');
     if (tid < 0) out += "*\t"; else { name_of(tid); out.push_back('\t'); }
-    PutInt((long long)pos + 1); out.push_back('\t'); PutInt(mapq); out.push_back('\t');
+    PutInt(&out, (long long)pos + 1); out.push_back('\t'); PutInt(&out, mapq); out.push_back('\t');
     if (n_cigar == 0) out.push_back('*');
     else for (uint32_t i = 0; i < n_cigar; i++) {
       const uint32_t c = (uint32_t)I32(cigar + 4 * i);
-      PutInt(c >> 4); out.push_back("MIDNSHP=XB??????"[c & 15u]);
+      PutInt(&out, c >> 4); out.push_back("MIDNSHP=XB??????"[c & 15u]);
     }
     out.push_back('\t');
     if (mtid < 0) out += "*\t"; else if (mtid == tid) out += "=\t"; else { name_of(mtid); out.push_back('\t'); }
-    PutInt((long long)mpos + 1); out.push_back('\t'); PutInt(isize); out.push_back('\t');
+    PutInt(&out, (long long)mpos + 1); out.push_back('\t'); PutInt(&out, isize); out.push_back('\t');
     if (l_seq) {
-      for (int32_t i = 0; i < l_seq; i++) out.push_back("=ACMGRSVTWYHKDBN"[(seq[i >> 1] >> ((~i & 1) << 2)) & 15]);
+      const size_t at = out.size();
+      out.resize(at + (size_t)l_seq);
+      char *d = &out[at];
+      for (int32_t i = 0; i < l_seq; i++) d[i] = "=ACMGRSVTWYHKDBN"[(seq[i >> 1] >> ((~i & 1) << 2)) & 15];
       out.push_back('\t');
-      if (qual[0] == 0xff) out.push_back('*'); else for (int32_t i = 0; i < l_seq; i++) out.push_back((char)(qual[i] + 33));
+      if (qual[0] == 0xff) out.push_back('*');
+      else {
+        const size_t q_at = out.size();
+        out.resize(q_at + (size_t)l_seq);
+        char *q = &out[q_at];
+        for (int32_t i = 0; i < l_seq; i++) q[i] = (char)(qual[i] + 33);
+      }
     } else out += "*\t*";
     char tmp[64];
     for (const unsigned char *s = aux; s + 3 <= end;) {
@@ -370,12 +380,12 @@ struct LineReader::BamDecoder {
       s += 3;
       auto fits = [&](size_t n) { return (size_t)(end - s) >= n; };
       if (type == 'A' && fits(1)) { out += "A:"; out.push_back((char)*s); s += 1; }
-      else if (type == 'C' && fits(1)) { out += "i:"; PutInt(*s); s += 1; }
-      else if (type == 'c' && fits(1)) { out += "i:"; PutInt((int8_t)*s); s += 1; }
-      else if (type == 'S' && fits(2)) { out += "i:"; PutInt(U16(s)); s += 2; }
-      else if (type == 's' && fits(2)) { out += "i:"; PutInt((int16_t)U16(s)); s += 2; }
-      else if (type == 'I' && fits(4)) { out += "i:"; PutInt((uint32_t)I32(s)); s += 4; }
-      else if (type == 'i' && fits(4)) { out += "i:"; PutInt(I32(s)); s += 4; }
+      else if (type == 'C' && fits(1)) { out += "i:"; PutInt(&out, *s); s += 1; }
+      else if (type == 'c' && fits(1)) { out += "i:"; PutInt(&out, (int8_t)*s); s += 1; }
+      else if (type == 'S' && fits(2)) { out += "i:"; PutInt(&out, U16(s)); s += 2; }
+      else if (type == 's' && fits(2)) { out += "i:"; PutInt(&out, (int16_t)U16(s)); s += 2; }
+      else if (type == 'I' && fits(4)) { out += "i:"; PutInt(&out, (uint32_t)I32(s)); s += 4; }
+      else if (type == 'i' && fits(4)) { out += "i:"; PutInt(&out, I32(s)); s += 4; }
       else if (type == 'f' && fits(4)) { float f; memcpy(&f, s, 4); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "f:%g", f)); s += 4; }
       else if (type == 'd' && fits(8)) { double d; memcpy(&d, s, 8); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "d:%lg", d)); s += 8; }
       else if (type == 'Z' || type == 'H') { out.push_back((char)type); out.push_back(':'); while (s < end && *s) out.push_back((char)*s++); if (s < end) s++; }
@@ -386,12 +396,12 @@ struct LineReader::BamDecoder {
         out += "B:"; out.push_back((char)sub);
         for (int32_t i = 0; i < n && s < end; i++) {
           out.push_back(',');
-          if (sub == 'c' && fits(1)) { PutInt((int8_t)*s); s += 1; }
-          else if (sub == 'C' && fits(1)) { PutInt(*s); s += 1; }
-          else if (sub == 's' && fits(2)) { PutInt((int16_t)U16(s)); s += 2; }
-          else if (sub == 'S' && fits(2)) { PutInt(U16(s)); s += 2; }
-          else if (sub == 'i' && fits(4)) { PutInt(I32(s)); s += 4; }
-          else if (sub == 'I' && fits(4)) { PutInt((uint32_t)I32(s)); s += 4; }
+          if (sub == 'c' && fits(1)) { PutInt(&out, (int8_t)*s); s += 1; }
+          else if (sub == 'C' && fits(1)) { PutInt(&out, *s); s += 1; }
+          else if (sub == 's' && fits(2)) { PutInt(&out, (int16_t)U16(s)); s += 2; }
+          else if (sub == 'S' && fits(2)) { PutInt(&out, U16(s)); s += 2; }
+          else if (sub == 'i' && fits(4)) { PutInt(&out, I32(s)); s += 4; }
+          else if (sub == 'I' && fits(4)) { PutInt(&out, (uint32_t)I32(s)); s += 4; }
           else if (sub == 'f' && fits(4)) { float f; memcpy(&f, s, 4); out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "%g", f)); s += 4; }
           else { s = end; }
         }
@@ -401,10 +411,60 @@ struct LineReader::BamDecoder {
     out.push_back('\n');
     return true;
   }
+  // The next stretch of the record stream: the inflated bytes are cut into records on this thread (a walk over the length
+  // fields), the records are spelt as SAM lines on several (each thread a run of consecutive records, the runs joined in order).
+  // The stream ends in front of the first record that is incomplete or malformed.
+  std::vector<unsigned char> raw;                                       // inflated bytes: whole records in front, the beginning of one behind them
+  size_t raw_len = 0;
+  void NextStretch() {
+    static const size_t kStretch = 8u << 20;
+    if (raw.size() < kStretch + 4) raw.resize(kStretch + 4);
+    bool input_end = false;
+    while (raw_len < kStretch) {
+      const long got = read_inflated(raw.data() + raw_len, kStretch - raw_len);
+      if (got <= 0) { input_end = true; break; }
+      raw_len += (size_t)got;
+    }
+    std::vector<std::pair<size_t, int32_t>> recs;                       // (where the record's body begins, its length)
+    size_t at = 0;
+    bool bad = false;
+    for (;;) {
+      if (raw_len - at < 4) break;
+      const int32_t block = I32(raw.data() + at);
+      if (block < 32) { bad = true; break; }
+      if ((size_t)block > raw_len - at - 4) {
+        if ((size_t)block + 4 > raw.size()) raw.resize((size_t)block + 4 + kStretch);      // a record longer than the stretch: the next round holds all of it
+        break;
+      }
+      recs.emplace_back(at + 4, block);
+      at += 4 + (size_t)block;
+    }
+    const int threads = (int)std::min<size_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), std::max<size_t>(1, recs.size() / 2048));
+    std::vector<std::string> text((size_t)threads);
+    std::vector<size_t> first_bad((size_t)threads, SIZE_MAX);
+    auto work = [&](int t) {
+      const size_t lo = recs.size() * (size_t)t / (size_t)threads, hi = recs.size() * (size_t)(t + 1) / (size_t)threads;
+      text[(size_t)t].reserve((hi - lo) * 200);
+      for (size_t k = lo; k < hi; k++)
+        if (!FormatRecord(raw.data() + recs[k].first, recs[k].second, ref, &text[(size_t)t])) { first_bad[(size_t)t] = k; break; }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < threads; t++) {
+      out += text[(size_t)t];
+      if (first_bad[(size_t)t] != SIZE_MAX) { eof = true; return; }
+    }
+    if (bad) { eof = true; return; }
+    memmove(raw.data(), raw.data() + at, raw_len - at);
+    raw_len -= at;
+    if (input_end) eof = true;                                          // (what is left is the beginning of a record that never ends)
+  }
   long Fill(char *dst, size_t want) {
     while (!eof && out.size() - out_pos < want) {
-      if (out_pos > (1u << 20)) { out.erase(0, out_pos); out_pos = 0; }
-      if (!NextRecord()) eof = true;
+      if (out_pos > 0) { out.erase(0, out_pos); out_pos = 0; }
+      NextStretch();
     }
     const size_t n = std::min(want, out.size() - out_pos);
     memcpy(dst, out.data() + out_pos, n);

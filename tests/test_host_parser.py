@@ -433,3 +433,58 @@ def test_bed_fast_path_word_boundaries(tmp_path):
     for env in ({"GT_PARSE_THREADS": "1"}, {"GT_PARSE_THREADS": "5", "GT_PARSE_PIECE_BYTES": "777"}):
         got = dump(path, env)
         assert got[0] == 0 and strip_extras(got[1]) == want[1], env
+
+
+def bgzip(data, path, block=65280, level=6, eof_marker=True):
+    """blocked gzip as bgzip writes it (SAM specification 4.1): members of at most 64 KB, each with its size in a 'BC' field"""
+    import struct
+    import zlib
+
+    def member(d):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = c.compress(d) + c.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(d) & 0xFFFFFFFF, len(d)))
+    with open(path, "wb") as f:
+        for lo in range(0, len(data), block):
+            f.write(member(data[lo:lo + block]))
+        if eof_marker:
+            f.write(member(b""))
+
+
+def test_bgzf_members_inflated_side_by_side(tmp_path):
+    """bgzip'd text and BAM are inflated member by member on several threads (LineReader::Bgzf), BAM records spelt as SAM lines on
+    several threads: the same regions as the plain file gives, as zlib's gzread gives on one thread (GT_NO_BGZF=1) and as the
+    reference's reader gives -- for whole files, for files cut inside a member, inside a header and at a member's end, and for
+    stretches of more members than one round takes."""
+    rng = np.random.default_rng(606)
+    lines = "".join("chr%d\t%d\t%d\tr%d\t%d\t%s\n" % (rng.integers(1, 23), s, s + 50, k, k % 1000, "+-"[k % 2])
+                    for k, s in enumerate(rng.integers(0, 200_000_000, 700_000))).encode()
+    plain = tmp_path / "reads.bed"
+    plain.write_bytes(lines)
+    bgzip(lines, tmp_path / "reads.bed.gz", block=3000, level=1)                      # ~9 000 members, 17 MB of members: two rounds
+    want = dump(plain, {})
+    assert want[0] == 0
+    for env in ({}, {"GT_INFLATE_THREADS": "1"}, {"GT_INFLATE_THREADS": "3", "GT_PARSE_THREADS": "2"}, {"GT_NO_BGZF": "1"}):
+        got = dump(tmp_path / "reads.bed.gz", env)
+        assert got[:2] == want[:2], env
+    whole = (tmp_path / "reads.bed.gz").read_bytes()
+    for cut in (len(whole) // 3, len(whole) // 3 + 5, 1_000_003, 18, 40, len(whole) - 28, len(whole) - 27):
+        (tmp_path / "cut.bed.gz").write_bytes(whole[:cut])
+        a, b = dump(tmp_path / "cut.bed.gz", {}), dump(tmp_path / "cut.bed.gz", {"GT_NO_BGZF": "1"})
+        assert a[:2] == b[:2], cut
+        if support.have_ref() and cut < 2_000_000:
+            rc, ref_out, _ = ref_reg(tmp_path / "cut.bed.gz")
+            assert (a[0], strip_extras(a[1])) == (rc, ref_out), cut
+    # BAM: enough records for several formatting threads, and the file cut inside a member
+    path = _bam_case(tmp_path, True, n=30_000, seed=12)
+    a, b = dump(path, {}), dump(path, {"GT_NO_BGZF": "1", "GT_PARSE_THREADS": "1"})
+    assert a[0] == 0 and a[:2] == b[:2] and a[1].count(b"\n") > 25_000
+    if support.have_ref():
+        rc, ref_out, _ = ref_reg(path)
+        assert (a[0], strip_extras(a[1])) == (rc, ref_out)
+    whole = path.read_bytes()
+    for cut in (len(whole) // 2, len(whole) // 2 + 11):
+        (tmp_path / "cut.bam").write_bytes(whole[:cut])
+        a, b = dump(tmp_path / "cut.bam", {}), dump(tmp_path / "cut.bam", {"GT_NO_BGZF": "1"})
+        assert a[:2] == b[:2] and a[1].count(b"\n") > 5_000, cut
