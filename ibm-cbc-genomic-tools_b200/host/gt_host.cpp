@@ -144,7 +144,7 @@ struct LineReader::Bgzf {
   std::vector<char> out;                                                // the inflated stretch
   size_t out_pos = 0;
   struct Member { size_t cdata, clen, at; uint32_t isize, crc; bool ok; };
-  static const size_t kStretch = 16u << 20;
+  static constexpr size_t kStretch = 16u << 20;
   explicit Bgzf(int f) : fd(f) {
     const char *env = getenv("GT_INFLATE_THREADS");
     threads = env ? atoi(env) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
@@ -206,6 +206,7 @@ struct LineReader::Bgzf {
         if (bsize < 0) { broken = true; break; }
         if (bsize == 0 || (size_t)bsize > comp.size() - at) { broken = file_end && comp.size() > at; break; }
         const unsigned char *m = comp.data() + at;
+        if (U32(m + bsize - 4) > (1u << 16)) { broken = true; break; }  // (no BGZF member holds more than 64 KB)
         mem.push_back({at + cdata, (size_t)bsize - cdata - 8, total, U32(m + bsize - 4), U32(m + bsize - 8), false});
         total += mem.back().isize;
         at += (size_t)bsize;
@@ -416,15 +417,17 @@ struct LineReader::BamDecoder {
   // The stream ends in front of the first record that is incomplete or malformed.
   std::vector<unsigned char> raw;                                       // inflated bytes: whole records in front, the beginning of one behind them
   size_t raw_len = 0;
+  static constexpr size_t kStretch = 8u << 20;
+  size_t target = kStretch;                                             // bytes to have in hand before cutting: a stretch, or all of a longer record
   void NextStretch() {
-    static const size_t kStretch = 8u << 20;
-    if (raw.size() < kStretch + 4) raw.resize(kStretch + 4);
+    if (raw.size() < target) raw.resize(target);
     bool input_end = false;
-    while (raw_len < kStretch) {
-      const long got = read_inflated(raw.data() + raw_len, kStretch - raw_len);
+    while (raw_len < target) {
+      const long got = read_inflated(raw.data() + raw_len, target - raw_len);
       if (got <= 0) { input_end = true; break; }
       raw_len += (size_t)got;
     }
+    target = kStretch;
     std::vector<std::pair<size_t, int32_t>> recs;                       // (where the record's body begins, its length)
     size_t at = 0;
     bool bad = false;
@@ -433,7 +436,7 @@ struct LineReader::BamDecoder {
       const int32_t block = I32(raw.data() + at);
       if (block < 32) { bad = true; break; }
       if ((size_t)block > raw_len - at - 4) {
-        if ((size_t)block + 4 > raw.size()) raw.resize((size_t)block + 4 + kStretch);      // a record longer than the stretch: the next round holds all of it
+        target = std::max(kStretch, (size_t)block + 4);                // (a record longer than a stretch: the next round waits for all of it)
         break;
       }
       recs.emplace_back(at + 4, block);

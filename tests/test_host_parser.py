@@ -488,3 +488,17 @@ def test_bgzf_members_inflated_side_by_side(tmp_path):
         (tmp_path / "cut.bam").write_bytes(whole[:cut])
         a, b = dump(tmp_path / "cut.bam", {}), dump(tmp_path / "cut.bam", {"GT_NO_BGZF": "1"})
         assert a[:2] == b[:2] and a[1].count(b"\n") > 5_000, cut
+
+
+def test_bam_record_longer_than_a_stretch(tmp_path):
+    """a record of 9.5 MB (longer than the 8 MB of inflated stream the decoder cuts at a time) between ordinary ones"""
+    refs = [("chr1", 100_000_000)]
+    recs = [{"qname": "q%d" % k, "flag": 0, "tid": 0, "pos": 1000 + k, "mapq": 60, "cigar": [(50, "M")], "seq": "A" * 50, "qual": None} for k in range(3000)]
+    big = 9_500_000
+    recs.insert(1500, {"qname": "giant", "flag": 16, "tid": 0, "pos": 5000, "mapq": 1, "cigar": [(big, "M")], "seq": "C" * big, "qual": None})
+    support.write_bam(tmp_path / "giant.bam", "@HD\tVN:1.0\n", refs, recs, block_bytes=60000)
+    rc, got, _ = dump(tmp_path / "giant.bam", {})
+    assert rc == 0 and got.count(b"\n") == 3001 and b"giant\tchr1 - 5001 9505000" in got
+    if support.have_ref():
+        rc, want, _ = ref_reg(tmp_path / "giant.bam")
+        assert (0, strip_extras(got)) == (rc, want)
