@@ -487,8 +487,11 @@ LineReader::LineReader(const char *path) {
     if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
       struct stat fst;
       const char *no_bgzf = getenv("GT_NO_BGZF");                        // (tests: the same file through zlib's gzread)
-      if (!(no_bgzf && no_bgzf[0] == '1') && fstat(fd_, &fst) == 0 && S_ISREG(fst.st_mode) && Bgzf::IsBgzf(fd_)) bgzf_ = new Bgzf(fd_);
-      gz_ = gzdopen(bgzf_ ? dup(fd_) : fd_, "rb");                       // (with BGZF the handle only marks the stream as gzip)
+      const char *use_zlib = getenv("GT_ZLIB");                          // (tests: zlib's gzread instead of either decoder of this build)
+      const bool own = !(use_zlib && use_zlib[0] == '1');
+      if (own && !(no_bgzf && no_bgzf[0] == '1') && fstat(fd_, &fst) == 0 && S_ISREG(fst.st_mode) && Bgzf::IsBgzf(fd_)) bgzf_ = new Bgzf(fd_);
+      else if (own) gzs_ = new GzipStream(fd_);
+      gz_ = gzdopen(bgzf_ || gzs_ ? dup(fd_) : fd_, "rb");               // (with a decoder of this build the handle only marks the stream as gzip)
       if (gz_ == nullptr) { fprintf(stderr, "[CreateFileBuffer] Error: cannot open file '%s'!\n", path); exit(1); }
       gzbuffer(gz_, 1 << 20);
       const long got4 = ReadInflated(prefix_, 4);                        // BAM or gzipped text (GetFileType, core.cpp:1764-1772)
@@ -517,13 +520,14 @@ LineReader::~LineReader() {
   producer_.join();
   delete bam_;
   if (gz_) gzclose(gz_);
-  if (bgzf_) { delete bgzf_; close(fd_); }
+  if (bgzf_ || gzs_) { delete bgzf_; delete gzs_; close(fd_); }
   else if (!gz_ && fd_ > 0) close(fd_);
   for (auto &b : block_) free(b.data);
 }
 
 long LineReader::ReadInflated(void *dst, size_t want) {
   if (bgzf_) return bgzf_->Read(dst, want);
+  if (gzs_) return gzs_->Read(dst, want);
   return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
 }
 
