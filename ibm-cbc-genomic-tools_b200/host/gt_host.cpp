@@ -131,7 +131,8 @@ static size_t PreadAll(int fd, char *dst, size_t want, off_t offset) {
 
 // BGZF -- what bgzip and samtools write (SAM specification, section 4.1): a series of gzip members of at most 64 KB of data each,
 // every one carrying its own compressed size in a 'BC' extra field.  zlib's gzread walks them one after the other on one thread
-// (170 MB/s of text); here the members of a stretch of the file are found by their size fields and inflated side by side.  What
+// (170 MB/s of text); here the members of a stretch of the file are found by their size fields and inflated side by side, each
+// by this build's decoder (gt_inflate.h).  What
 // the reader hands out is what gzread would: the data of every complete member in file order and, from a member the file ends
 // in, whatever inflates -- then the end of the input.  A complete member that does not inflate to what its trailer promises ends
 // the input in front of it.
@@ -143,7 +144,9 @@ struct LineReader::Bgzf {
   std::vector<unsigned char> comp;                                      // compressed bytes not consumed yet
   std::vector<char> out;                                                // the inflated stretch
   size_t out_pos = 0;
-  struct Member { size_t cdata, clen, at; uint32_t isize, crc; bool ok; };
+  struct Member { size_t begin, size, cdata, at; uint32_t isize; bool ok; };   // the member in comp, its deflate data, its place in out
+  std::vector<GzipStream *> decoder;                                    // one per inflating thread
+  ~Bgzf() { for (GzipStream *d : decoder) delete d; }
   static constexpr size_t kStretch = 16u << 20;
   explicit Bgzf(int f) : fd(f) {
     const char *env = getenv("GT_INFLATE_THREADS");
@@ -176,15 +179,6 @@ struct LineReader::Bgzf {
     size_t at;
     return got >= 18 && MemberSize(h, (size_t)got, &at) > 0;
   }
-  // raw deflate data -> dst; returns the bytes written (all of `room` expected), *ok = the stream ended where it should
-  static size_t InflateRaw(z_stream *zs, const unsigned char *src, size_t n, char *dst, size_t room, bool *ok) {
-    inflateReset(zs);
-    zs->next_in = const_cast<unsigned char *>(src); zs->avail_in = (unsigned)n;
-    zs->next_out = (unsigned char *)dst; zs->avail_out = (unsigned)room;
-    const int rc = inflate(zs, Z_FINISH);
-    *ok = rc == Z_STREAM_END && zs->avail_out == 0;
-    return room - zs->avail_out;
-  }
   bool Fill() {                                                         // the next stretch; false at the end of the stream
     out.clear(); out_pos = 0;
     while (!stream_end && out.empty()) {
@@ -207,28 +201,26 @@ struct LineReader::Bgzf {
         if (bsize == 0 || (size_t)bsize > comp.size() - at) { broken = file_end && comp.size() > at; break; }
         const unsigned char *m = comp.data() + at;
         if (U32(m + bsize - 4) > (1u << 16)) { broken = true; break; }  // (no BGZF member holds more than 64 KB)
-        mem.push_back({at + cdata, (size_t)bsize - cdata - 8, total, U32(m + bsize - 4), U32(m + bsize - 8), false});
+        mem.push_back({at, (size_t)bsize, at + cdata, total, U32(m + bsize - 4), false});
         total += mem.back().isize;
         at += (size_t)bsize;
       }
       out.resize(total);
       std::atomic<size_t> next{0};
-      auto work = [&] {
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) return;
+      // (every member is a gzip stream of its own: header, data, CRC-32 and length, all of which the decoder checks)
+      auto work = [&](int t) {
+        GzipStream &gz = *decoder[(size_t)t];
         for (size_t i; (i = next.fetch_add(1)) < mem.size();) {
           Member &b = mem[i];
-          bool ok = false;
-          InflateRaw(&zs, comp.data() + b.cdata, b.clen, out.data() + b.at, b.isize, &ok);
-          b.ok = ok && (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const unsigned char *)out.data() + b.at, b.isize) == b.crc;
+          gz.Reset(comp.data() + b.begin, b.size);
+          b.ok = gz.Read(out.data() + b.at, (size_t)b.isize) == (long)b.isize && !gz.failed();   // (a member is far smaller than the decoder's chunk: its trailer has been checked by now)
         }
-        inflateEnd(&zs);
       };
       const int n_threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, mem.size() / 8));
+      while ((int)decoder.size() < n_threads) decoder.push_back(new GzipStream());
       std::vector<std::thread> th;
-      for (int t = 1; t < n_threads; t++) th.emplace_back(work);
-      work();
+      for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
+      work(0);
       for (auto &t : th) t.join();
       // a member that did not inflate as its header promised ends the stream behind whatever it did yield (as gzread would)
       size_t good = 0;
@@ -589,7 +581,7 @@ void LineReader::Produce() {
       b.data = (char *)realloc(b.data, b.cap + 16);                     // (16 spare bytes: the parsers read whole words)
       if (b.data == nullptr) { fprintf(stderr, "Error: out of memory!\n"); exit(1); }
     }
-    memcpy(b.data, carry.data(), carry.size());
+    if (!carry.empty()) memcpy(b.data, carry.data(), carry.size());
     size_t have = carry.size();
     b.len = 0;
     for (;;) {

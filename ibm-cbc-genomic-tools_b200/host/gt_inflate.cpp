@@ -101,6 +101,19 @@ GzipStream::GzipStream(int fd) : fd_(fd) {
   out_.resize(kHistory + kChunk + 258 + kOutSlack);
 }
 
+GzipStream::GzipStream() : GzipStream(-1) { in_eof_ = true; state_ = S_END; }
+
+void GzipStream::Reset(const uint8_t *data, size_t n) {
+  mem_ = data; mem_left_ = n;
+  in_pos_ = in_end_ = 0;
+  in_eof_ = false;
+  bitbuf_ = 0; bitcnt_ = 0;
+  out_lo_ = out_hi_ = valid_lo_ = summed_ = kHistory;
+  state_ = S_HEADER;
+  last_block_ = failed_ = any_member_ = false;
+  stored_left_ = 0;
+}
+
 // Moves what is left of the input to the front of the buffer and reads more behind it.
 void GzipStream::FillInput() {
   if (in_eof_) return;
@@ -113,6 +126,13 @@ void GzipStream::FillInput() {
     memmove(in_.data(), in_.data() + in_pos_, in_end_ - in_pos_);
     in_end_ -= in_pos_;
     in_pos_ = 0;
+  }
+  if (fd_ < 0) {                                                        // input from memory
+    const size_t n = mem_left_ < (size_t)kInCap - in_end_ ? mem_left_ : (size_t)kInCap - in_end_;
+    if (n) memcpy(in_.data() + in_end_, mem_, n);
+    mem_ += n; mem_left_ -= n; in_end_ += n;
+    if (mem_left_ == 0) { in_eof_ = true; memset(in_.data() + in_end_, 0, kInPad); }
+    return;
   }
   while (in_end_ < (size_t)kInCap) {
     const ssize_t got = read(fd_, in_.data() + in_end_, (size_t)kInCap - in_end_);

@@ -16,6 +16,8 @@ namespace gt {
 class GzipStream {
  public:
   explicit GzipStream(int fd);                       // reads from the descriptor's current position; does not close it
+  GzipStream();                                      // no input yet: Reset() names it
+  void Reset(const uint8_t *data, size_t n);         // a new stream: the n bytes at data (they must stay where they are while it is read)
   // up to `want` inflated bytes into dst; fewer only at the end of the stream (0: nothing is left).  After a fault the data in
   // front of it has been handed out and the stream is at its end.
   long Read(void *dst, size_t want);
@@ -33,6 +35,8 @@ class GzipStream {
   size_t InputLeft() const;                          // whole bytes not consumed yet (those waiting in the bit buffer included)
   void AlignToByte();
   int fd_;
+  const uint8_t *mem_ = nullptr;                     // input from memory instead of fd_ (Reset)
+  size_t mem_left_ = 0;
   std::vector<uint8_t> in_;                          // [0, in_end_) valid, kInPad zero bytes behind it once the input has ended
   size_t in_pos_ = 0, in_end_ = 0;
   bool in_eof_ = false;
