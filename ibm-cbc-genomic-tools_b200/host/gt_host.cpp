@@ -141,6 +141,7 @@ struct LineReader::Bgzf {
   off_t offset = 0;
   int threads;
   bool file_end = false, stream_end = false;
+  bool damaged = false;                                                 // the stream ended at a complete member that did not inflate to what its trailer says
   std::vector<unsigned char> comp;                                      // compressed bytes not consumed yet
   std::vector<char> out;                                                // the inflated stretch
   size_t out_pos = 0;
@@ -227,6 +228,7 @@ struct LineReader::Bgzf {
       while (good < mem.size() && mem[good].ok) good++;
       if (good < mem.size() || broken) {
         stream_end = true;
+        damaged = good < mem.size();
         // (a complete member that is damaged yields nothing: its bytes up to the fault would be noise; a member the file ends in
         // yields what inflates, which is what zlib hands out before it reports the unexpected end of the file)
         size_t keep = good < mem.size() ? mem[good].at : total;
@@ -518,8 +520,14 @@ LineReader::~LineReader() {
 }
 
 long LineReader::ReadInflated(void *dst, size_t want) {
-  if (bgzf_) return bgzf_->Read(dst, want);
-  if (gzs_) return gzs_->Read(dst, want);
+  // (a stream that ends on a fault -- damaged data, a CRC or a length that does not match -- ends the input there, as a failing
+  // gzread ends the reference's; it is not passed over in silence)
+  auto warn = [this] {
+    if (!fault_warned_) fprintf(stderr, "Warning: the gzip data is damaged (or its CRC / length does not match); the input ends in front of the fault!\n");
+    fault_warned_ = true;
+  };
+  if (bgzf_) { const long got = bgzf_->Read(dst, want); if ((size_t)got < want && bgzf_->damaged) warn(); return got; }
+  if (gzs_) { const long got = gzs_->Read(dst, want); if ((size_t)got < want && gzs_->failed()) warn(); return got; }
   return (long)gzread(gz_, dst, (unsigned)std::min<size_t>(want, 1u << 30));
 }
 

@@ -94,6 +94,7 @@ class LineReader {
   struct Bgzf;                                        // blocked gzip (bgzip, BAM): the members of a stretch of the file are inflated side by side
   Bgzf *bgzf_ = nullptr;
   GzipStream *gzs_ = nullptr;                         // any other gzip file: one thread, a decoder faster than zlib's (gt_inflate.h)
+  bool fault_warned_ = false;
   long ReadInflated(void *dst, size_t want);          // from the gzip stream, whichever way it is read
   char prefix_[4];                                    // the first inflated bytes of a gzip file (read to tell BAM from text)
   int prefix_len_ = 0, prefix_pos_ = 0;
