@@ -195,10 +195,11 @@ struct LineReader::Bgzf {
       std::vector<Member> mem;
       size_t at = 0, total = 0;
       bool broken = false;                                              // what is left at `at` is no complete member and never will be
+      bool not_bgzf = false;
       for (;;) {
         size_t cdata = 0;
         const long bsize = MemberSize(comp.data() + at, comp.size() - at, &cdata);
-        if (bsize < 0) { broken = true; break; }
+        if (bsize < 0) { broken = not_bgzf = true; break; }             // (bytes that are no BGZF member: the stream ends here, with a warning)
         if (bsize == 0 || (size_t)bsize > comp.size() - at) { broken = file_end && comp.size() > at; break; }
         const unsigned char *m = comp.data() + at;
         if (U32(m + bsize - 4) > (1u << 16)) { broken = true; break; }  // (no BGZF member holds more than 64 KB)
@@ -228,7 +229,7 @@ struct LineReader::Bgzf {
       while (good < mem.size() && mem[good].ok) good++;
       if (good < mem.size() || broken) {
         stream_end = true;
-        damaged = good < mem.size();
+        damaged = good < mem.size() || not_bgzf;
         // (a complete member that is damaged yields nothing: its bytes up to the fault would be noise; a member the file ends in
         // yields what inflates, which is what zlib hands out before it reports the unexpected end of the file)
         size_t keep = good < mem.size() ? mem[good].at : total;
