@@ -1014,10 +1014,6 @@ bool RegionReader::ParseLine(char *inp, RegionBatch *out, ChromCache *cache, Par
   return true;
 }
 
-// The common case by far -- TAB-separated BED of 3 to 6 clean columns -- in one pass over the line and without writing
-// to it.  "Clean": every column non-empty and not starting with a blank, start and stop plain digit strings of at most 18
-// digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  The line ends with '\n'
-// (every block does); returns that '\n', or nullptr if the line is not for this path (nothing has been appended then).
 // eight bytes at p as one word (the blocks of LineReader are allocated with 16 spare bytes, so a word that begins inside a line
 // may run past the block's last '\n')
 static inline uint64_t Load8(const char *p) { uint64_t w; memcpy(&w, p, 8); return w; }
@@ -1055,6 +1051,10 @@ static inline const char *FieldEnd(const char *p) {
   }
 }
 
+// The common case by far -- TAB-separated BED of 3 to 6 clean columns -- in one pass over the line and without writing
+// to it.  "Clean": every column non-empty and not starting with a blank, start and stop plain digit strings of at most 18
+// digits, strand one of + - . 1 -1.  Anything else is left to ParseLine, so the two can not disagree.  The line ends with '\n'
+// (every block does); returns that '\n', or nullptr if the line is not for this path (nothing has been appended then).
 char *RegionReader::ParseBedLine(char *line, RegionBatch *out, ChromCache *cache) const {
   const char *p = line;
   if (*p == ' ' || *p == '\t') return nullptr;
@@ -1127,6 +1127,80 @@ char *RegionReader::ParseBedLine(char *line, RegionBatch *out, ChromCache *cache
   return const_cast<char *>(p);
 }
 
+// The same for SAM lines (what BAM records are spelt as, too): the eleven mandatory columns found by their TABs without writing to
+// the line, FLAG and POS plain digit strings, a CIGAR of digits and the operations the reference knows (or "*"), at most 16
+// blocks, the length of SEQ in agreement with the CIGAR.  Every other line -- and every line when labels are weights -- is left
+// to ParseLine, which also words the errors.  Returns the line's '\n', or nullptr (nothing has been appended then).
+char *RegionReader::ParseSamLine(char *line, RegionBatch *out, ChromCache *cache) const {
+  if (max_label_value_ > 1) return nullptr;
+  const char *f[11];
+  const char *p = line;
+  for (int k = 0; k < 11; k++) {
+    f[k] = p;
+    if (*p == ' ' || *p == '\t' || *p == '\n') return nullptr;
+    p = FieldEnd(p);
+    if (k < 10) { if (*p != '\t') return nullptr; p++; }
+  }
+  const char *nl = *p == '\n' ? p : (const char *)rawmemchr(p, '\n');
+  unsigned long flag = 0, pos = 0;
+  const char *q = f[1];
+  if (!ParseDigits(&q, &flag) || q != f[2] - 1) return nullptr;
+  q = f[3];
+  if (!ParseDigits(&q, &pos) || q != f[4] - 1 || pos > (unsigned long)INT32_MAX) return nullptr;
+  const size_t rname_len = (size_t)(f[3] - 1 - f[2]), seq_len = (size_t)(f[10] - 1 - f[9]);
+  if (rname_len > 63) return nullptr;
+  const bool seq_star = seq_len == 1 && f[9][0] == '*';
+  long b_start[16], b_stop[16];
+  int n_blocks = 0;
+  long start = (long)pos, reference_len = 0, fragment_len = 0;
+  const char *c = f[5], *const c_end = f[6] - 1;
+  if (c_end - c == 1 && *c == '*') {                                     // "*" stands for <length of SEQ>M
+    reference_len = fragment_len = (long)seq_len;
+  } else {
+    while (c < c_end) {
+      unsigned long len = 0;
+      if (!ParseDigits(&c, &len) || c >= c_end || len > (unsigned long)INT32_MAX) return nullptr;
+      const char type = *c++;
+      if (type == 'M' || type == 'X') { fragment_len += (long)len; reference_len += (long)len; }
+      else if (type == 'I' || type == 'S') fragment_len += (long)len;
+      else if (type == 'D') reference_len += (long)len;
+      else if (type == 'N') {
+        if (n_blocks == 16) return nullptr;
+        b_start[n_blocks] = start; b_stop[n_blocks] = start + reference_len - 1; n_blocks++;
+        start = start + reference_len + (long)len;
+        reference_len = 0;
+      } else if (type != 'H' && type != 'P' && type != '-') return nullptr;
+    }
+  }
+  if (!seq_star && (long)seq_len != fragment_len) return nullptr;
+  if (reference_len > 0) {
+    if (n_blocks == 16) return nullptr;
+    b_start[n_blocks] = start; b_stop[n_blocks] = start + reference_len - 1; n_blocks++;
+  }
+  if (n_blocks == 0) return nullptr;
+  for (int k = 0; k < n_blocks; k++)
+    if (b_start[k] > INT32_MAX || b_stop[k] > INT32_MAX || b_stop[k] < INT32_MIN) return nullptr;
+  int32_t chrom;
+  if (rname_len <= 8) chrom = cache->GetShort(f[2], rname_len);
+  else {
+    char name[64];
+    memcpy(name, f[2], rname_len);
+    name[rname_len] = 0;
+    chrom = cache->Get(name);
+  }
+  const int8_t strand = (flag & 0x10ul) ? '-' : '+';                   // CalcStrandFromFlag, :2870-2873
+  for (int k = 0; k < n_blocks; k++) {
+    out->chrom.push_back(chrom);
+    out->strand.push_back(strand);
+    out->start.push_back((int32_t)b_start[k]);
+    out->stop.push_back((int32_t)b_stop[k]);
+  }
+  if (n_blocks != 1) out->multi = true;
+  out->offset.push_back((int64_t)out->chrom.size());
+  if (keep_labels_) out->label.emplace_back(f[0], f[1] - 1);
+  return const_cast<char *>(nl);
+}
+
 struct RegionReader::Piece {
   char *lo = nullptr, *hi = nullptr;
   RegionBatch batch;
@@ -1160,7 +1234,7 @@ bool RegionReader::ParseRun(char *begin, char *end, RegionBatch *out) {
     pc.hi = at = want;
     pc.lines = 0; pc.bad = false;
   }
-  const bool bed = fmt_ == F_BED;
+  const bool bed = fmt_ == F_BED, sam = fmt_ == F_SAM;
   auto parse = [&](int i) {
     Piece &pc = *piece_[i];
     RegionBatch *dst = &pc.batch;
@@ -1169,7 +1243,7 @@ bool RegionReader::ParseRun(char *begin, char *end, RegionBatch *out) {
     const size_t guess = (size_t)(pc.hi - pc.lo) / 24 + 16;            // avoids most reallocations the first time round
     dst->chrom.reserve(guess); dst->start.reserve(guess); dst->stop.reserve(guess); dst->strand.reserve(guess); dst->offset.reserve(guess + 1);
     for (char *p = pc.lo; p < pc.hi;) {
-      char *nl = bed ? ParseBedLine(p, dst, &cache) : nullptr;
+      char *nl = bed ? ParseBedLine(p, dst, &cache) : sam ? ParseSamLine(p, dst, &cache) : nullptr;
       if (nl == nullptr) {
         nl = (char *)memchr(p, '\n', (size_t)(pc.hi - p));
         *nl = 0;

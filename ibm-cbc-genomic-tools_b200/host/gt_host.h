@@ -203,6 +203,7 @@ class RegionReader {
   // lines of [begin, end), over the parsing threads, appended to out; false on a malformed line (error_ set)
   bool ParseRun(char *begin, char *end, RegionBatch *out);
   char *ParseBedLine(char *line, RegionBatch *out, ChromCache *cache) const;   // clean BED3-6 only; the line's '\n', or nullptr = not handled
+  char *ParseSamLine(char *line, RegionBatch *out, ChromCache *cache) const;   // clean SAM lines likewise
   LineReader reader_;
   ChromTable *chroms_;
   bool keep_labels_;

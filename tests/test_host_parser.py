@@ -502,3 +502,44 @@ def test_bam_record_longer_than_a_stretch(tmp_path):
     if support.have_ref():
         rc, want, _ = ref_reg(tmp_path / "giant.bam")
         assert (0, strip_extras(got)) == (rc, want)
+
+
+def test_sam_fast_path_shapes(tmp_path):
+    """SAM lines of every clean shape the one-pass SAM path takes, and of shapes it must leave to the general tokeniser (blank-led
+    fields, more than 16 blocks, names longer than 63 bytes): reference names of 1 to 70 bytes, positions of 1 to 9 digits and 0,
+    CIGARs over M I D N S H P X with one to twenty operations or "*", SEQ "*" or of the CIGAR's length, 0 to 3 optional fields --
+    against the reference's reader, in one piece and in many small ones."""
+    rng = np.random.default_rng(515)
+    names = ["c", "chr1", "chr10", "chrUn_gl0", "chrUn_gl000220", "*", "scaffold_" + "x" * 50, "y" * 70]
+    lines = ["@HD\tVN:1.0", "@SQ\tSN:chr1\tLN:1000"]
+    for k in range(30000):
+        ops = []
+        n_ops = int(rng.choice([1, 1, 1, 2, 3, 5, 8, 20, 40]))
+        for i in range(n_ops):
+            ops.append((int(rng.integers(1, 200)), "MIDNSHPX"[int(rng.integers(8))] if n_ops > 1 else "M"))
+        if ops[0][1] == "N":
+            ops[0] = (ops[0][0], "M")
+        frag = sum(n for n, op in ops if op in "MISX")
+        star_cigar = rng.random() < 0.05
+        cigar = "*" if star_cigar else "".join("%d%s" % t for t in ops)
+        if star_cigar:
+            seq = "A" * int(rng.integers(1, 80))
+        else:
+            seq = "*" if (rng.random() < 0.1 or frag == 0) else "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, frag))
+        pos = 0 if rng.random() < 0.03 else int(rng.integers(1, 10 ** int(rng.integers(1, 10))))
+        label = ["read%d" % k, "r", " lead", "a b", "-7", "123456789"][int(rng.integers(6))] if rng.random() < 0.3 else "q%d" % k
+        opt = ["", "\tNM:i:1", "\tNM:i:1\tXS:A:+", "\tNM:i:1\tXS:A:+\tMD:Z:50"][int(rng.integers(4))]
+        qual = "*" if rng.random() < 0.5 or seq == "*" else "I" * len(seq)
+        lines.append("%s\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t%d\t%s\t%s%s" % (label, int(rng.integers(0, 4096)), names[int(rng.integers(len(names)))], pos,
+                                                                    int(rng.integers(0, 61)), cigar, ["*", "=", "chr2"][int(rng.integers(3))],
+                                                                    int(rng.integers(0, 1000)), int(rng.integers(-500, 500)), seq, qual, opt))
+    path = tmp_path / "shapes.sam"
+    path.write_text("\n".join(lines) + "\n")
+    want = ref_reg(path)
+    assert want[0] == 0 and want[1].count(b"\n") > 25000                     # (a CIGAR that consumes no reference leaves a region without intervals: nothing is printed for it)
+    for env in ({"GT_PARSE_THREADS": "1"}, {"GT_PARSE_THREADS": "5", "GT_PARSE_PIECE_BYTES": "777"}):
+        got = dump(path, env)
+        assert got[0] == 0 and strip_extras(got[1]) == want[1], env
+    # labels as weights go through the general tokeniser: the same regions
+    got_w = dump(path, {}, args=("-w", "5"))
+    assert got_w[0] == 0 and strip_extras(got_w[1]) == want[1]
