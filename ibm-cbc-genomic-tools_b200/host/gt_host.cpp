@@ -411,6 +411,7 @@ struct LineReader::BamDecoder {
   // fields), the records are spelt as SAM lines on several (each thread a run of consecutive records, the runs joined in order).
   // The stream ends in front of the first record that is incomplete or malformed.
   std::vector<unsigned char> raw;                                       // inflated bytes: whole records in front, the beginning of one behind them
+  std::vector<std::string> text;                                        // the SAM lines of each formatting thread's run of records
   size_t raw_len = 0;
   static constexpr size_t kStretch = 8u << 20;
   size_t target = kStretch;                                             // bytes to have in hand before cutting: a stretch, or all of a longer record
@@ -438,7 +439,8 @@ struct LineReader::BamDecoder {
       at += 4 + (size_t)block;
     }
     const int threads = (int)std::min<size_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), std::max<size_t>(1, recs.size() / 2048));
-    std::vector<std::string> text((size_t)threads);
+    if (text.size() < (size_t)threads) text.resize((size_t)threads);   // (kept between stretches: their memory is reused)
+    for (auto &t : text) t.clear();
     std::vector<size_t> first_bad((size_t)threads, SIZE_MAX);
     auto work = [&](int t) {
       const size_t lo = recs.size() * (size_t)t / (size_t)threads, hi = recs.size() * (size_t)(t + 1) / (size_t)threads;
